@@ -1,0 +1,179 @@
+/* include/malevich_b200.h -- C-ABI of the B200-native Malevich draw pipeline.
+ *
+ * This is the drop-in boundary: plain C, pointers and sizes only, every entry
+ * point returns an int status (MLV_OK == 0) and mlv_last_error_string() explains a failure.
+ * Each function cites the reference interface it replaces (paths relative to the reference
+ * checkout, `source/main.c` unless stated).
+ *
+ * Threading: one host thread per mlv_device. Calls are stream-ordered and asynchronous until
+ * mlv_present_readback / mlv_finish / mlv_get_stats / any mlv_debug_read_* (these synchronise).
+ * There is NO CPU fallback: every entry point that touches pixels fails with MLV_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef MALEVICH_B200_H
+#define MALEVICH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MLV_API __attribute__((visibility("default")))
+#else
+#define MLV_API
+#endif
+
+/* ---- status codes -------------------------------------------------------------------------- */
+enum {
+	MLV_OK = 0,
+	MLV_ERR_INVALID_ARGUMENT = 1, /* reference: assert() main.c:666,670,1230 */
+	MLV_ERR_CUDA = 2,             /* CUDA runtime failure / no device (reference: none, CPU only) */
+	MLV_ERR_OUT_OF_MEMORY = 3,
+	MLV_ERR_CAPACITY = 4,         /* a per-draw arena overflowed (reference mallocs per draw, main.c:745-746,947,986) */
+	MLV_ERR_STATE = 5             /* draw issued with incomplete pipeline state */
+};
+
+/* ---- enumerations mirroring the reference's state ------------------------------------------ */
+/* PrimitiveTopology, main.c:66-69 */
+enum { MLV_PRIMITIVE_TOPOLOGY_UNDEFINED = 0, MLV_PRIMITIVE_TOPOLOGY_TRIANGLELIST = 1 };
+/* The reference binds shaders as host function pointers (VS.shader main.c:79, PS.shader main.c:99,
+ * descriptors main.c:46-52). On the device they are __device__ functions selected by id. */
+enum { MLV_VS_PASSTHROUGH = 0,     /* passthrough_vs.c:16-25 */
+       MLV_VS_BASIC = 1,           /* basic_vs.c:22-33 */
+       MLV_VS_VERTEX_LIGHTING = 2, /* vertex_lighting_vs.c:22-39 */
+       MLV_VS_FULLSCREEN = 3,      /* fullscreen_vs.c:22-39 */
+       MLV_VS_COUNT = 4 };
+enum { MLV_PS_PASSTHROUGH = 0,  /* passthrough_ps.c:13-20 */
+       MLV_PS_BASIC = 1,        /* basic_ps.c:16-27 */
+       MLV_PS_ENV_LIGHTING = 2, /* env_lighting_ps.c:13-24 */
+       MLV_PS_COUNT = 3 };
+/* Texture2D, common_shader_core.h:20-24: the reference infers the texel type from the sampler used
+ * (get_texel_u_x8 :30 vs get_texel_f_x8 :42); here it is explicit. */
+enum { MLV_FORMAT_R8G8B8A8_UNORM = 0, MLV_FORMAT_R32G32B32A32_FLOAT = 1 };
+enum { MLV_BUFFER_VERTEX = 0, MLV_BUFFER_INDEX = 1 };
+
+#define MLV_CONSTANT_BUFFER_SLOT_COUNT 16 /* COMMONSHADER_CONSTANT_BUFFER_HW_SLOT_COUNT main.c:41 */
+#define MLV_SHADER_RESOURCE_SLOT_COUNT 16 /* COMMONSHADER_INPUT_RESOURCE_REGISTER_COUNT main.c:42 */
+#define MLV_TILE_SIZE 8                   /* TILE_WIDTH/TILE_HEIGHT main.c:24-25 */
+
+/* ---- plain-data structs --------------------------------------------------------------------- */
+/* Viewport, main.c:85-92 (same field order). The viewport must equal the render-target size, as in
+ * the reference (tile pitch uses viewport.width, bins use WIDTH_IN_TILES: main.c:582,590). */
+typedef struct mlv_viewport {
+	float top_left_x, top_left_y, width, height, min_depth, max_depth;
+} mlv_viewport;
+
+/* Stats, main.c:199-206 (same field order, same accumulation points main.c:1228-1246). */
+typedef struct mlv_stats {
+	float frame_time;
+	uint32_t vertex_count;
+	uint32_t input_triangle_count;
+	uint32_t assembled_triangle_count;
+	uint32_t active_bin_count;
+	uint32_t total_triangle_count_in_bins;
+} mlv_stats;
+
+/* Replaces the compile-time WIDTH/HEIGHT (main.c:21-22) and adds the sort-first partition
+ * (SURVEY.md 8e): rank r of num_ranks owns the 8-pixel tile rows ty with (ty / stripe_height_tiles)
+ * % num_ranks == r. width and height must be multiples of 8 (WIDTH_IN_TILES main.c:28-29). */
+typedef struct mlv_device_desc {
+	uint32_t width, height;
+	int32_t cuda_device;          /* ordinal; -1 = current device */
+	uint32_t num_ranks;           /* 0 or 1 = single GPU */
+	uint32_t rank;
+	uint32_t stripe_height_tiles; /* 0 = default (1) */
+	uint64_t max_pairs_per_draw;  /* capacity of the (triangle,tile) list arena; 0 = default */
+	uint32_t flags;               /* MLV_DEVICE_* */
+	uint32_t reserved;
+} mlv_device_desc;
+enum { MLV_DEVICE_DEBUG_CAPTURE = 1 /* keep reference-layout intermediates of the last draw for mlv_debug_read_* */ };
+
+typedef struct mlv_device mlv_device;
+typedef struct mlv_buffer mlv_buffer;
+typedef struct mlv_texture mlv_texture;
+
+/* Debug read-back records, byte-compatible with the reference's x86-64 layouts. */
+typedef struct mlv_ref_triangle { /* Triangle main.c:134-139 + Setup :127-132 + EdgeFunction :121-125, 80 bytes */
+	uint64_t p_attributes;        /* host pointer in the reference; here: triangle index * 144 */
+	int32_t min_bounds[2], max_bounds[2];
+	int32_t edges[3][3];          /* a_edge_functions[k] = {a,b,c} */
+	float reciprocal_ws[3];
+	float one_over_area;
+	float max_depth;
+} mlv_ref_triangle;
+typedef struct mlv_ref_compacted_bin { uint32_t num_triangles_self, num_triangles_upto, bin_index; } mlv_ref_compacted_bin; /* main.c:146-150 */
+typedef struct mlv_ref_tile_info { uint32_t triangle_id; uint32_t _pad; uint64_t fragment_mask; } mlv_ref_tile_info;         /* main.c:159-162 */
+
+/* ---- device ---------------------------------------------------------------------------------- */
+MLV_API const char *mlv_last_error_string(void);                                    /* error() main.c:451-465 */
+MLV_API int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device); /* static frame_buffer/depth_buffer/a_bins/a_tile_min_depths main.c:35-36,229-230 */
+MLV_API void mlv_destroy_device(mlv_device *dev);
+MLV_API int mlv_finish(mlv_device *dev);
+MLV_API void *mlv_get_stream(mlv_device *dev); /* the cudaStream_t all work is launched on (for CUDA-event timing) */
+
+/* ---- resources (load_mesh main.c:526-536, load_texture main.c:538-559 hand the pipeline host pointers) */
+MLV_API int mlv_create_buffer(mlv_device *dev, const void *data, size_t bytes, int kind, mlv_buffer **out);
+MLV_API int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t bytes);
+MLV_API void mlv_release_buffer(mlv_device *dev, mlv_buffer *buf);
+MLV_API int mlv_create_texture2d(mlv_device *dev, const void *texels, uint32_t width, uint32_t height, int format, mlv_texture **out);
+MLV_API void mlv_release_texture(mlv_device *dev, mlv_texture *tex);
+
+/* ---- pipeline state: graphics_pipeline.{ia,vs,rs,ps} main.c:71-115, written by render() main.c:1276-1294 */
+MLV_API int mlv_ia_set_vertex_buffer(mlv_device *dev, mlv_buffer *vb);       /* ia.p_vertex_buffer main.c:1292 */
+MLV_API int mlv_ia_set_index_buffer(mlv_device *dev, mlv_buffer *ib);        /* ia.p_index_buffer main.c:1291 (u32 indices) */
+MLV_API int mlv_ia_set_input_layout(mlv_device *dev, uint32_t bytes_per_vertex); /* ia.input_layout main.c:1286 (must be 32) */
+MLV_API int mlv_ia_set_primitive_topology(mlv_device *dev, int topology);    /* ia.primitive_topology main.c:1276 */
+MLV_API int mlv_vs_set_shader(mlv_device *dev, int vs_id);                   /* vs.shader + vs.output_register_count main.c:1287-1288 */
+MLV_API int mlv_vs_set_constant_buffer(mlv_device *dev, uint32_t slot, const void *data, size_t bytes); /* vs.p_constant_buffers[slot] main.c:1281 (PerFrameCB main.c:169-173, 192 bytes) */
+MLV_API int mlv_vs_set_shader_resource(mlv_device *dev, uint32_t slot, mlv_texture *tex); /* vs.p_shader_resource_views[slot] main.c:1293 */
+MLV_API int mlv_rs_set_viewport(mlv_device *dev, const mlv_viewport *vp);    /* rs.viewport main.c:1277-1278 */
+MLV_API int mlv_ps_set_shader(mlv_device *dev, int ps_id);                   /* ps.shader main.c:1289 */
+MLV_API int mlv_ps_set_shader_resource(mlv_device *dev, uint32_t slot, mlv_texture *tex); /* ps.p_shader_resource_views[slot] main.c:1294 */
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+MLV_API int mlv_clear_render_target_view(mlv_device *dev, const float rgba[4]); /* clear_render_target_view main.c:1191-1202 */
+MLV_API int mlv_clear_depth_stencil_view(mlv_device *dev, float depth);         /* clear_depth_stencil_view main.c:1204-1217 */
+MLV_API int mlv_draw_indexed(mlv_device *dev, uint32_t index_count);            /* draw_indexed main.c:1219-1261 */
+MLV_API int mlv_draw(mlv_device *dev, uint32_t vertex_count);                   /* draw_indexed with identity indices (all shipped meshes) */
+
+/* ---- results ---------------------------------------------------------------------------------- */
+/* Replaces the GDI blit of frame_buffer (paint_window main.c:286-357): row-major y*W+x, colour
+ * 0x00RRGGBB from the PS path, depth f32 reversed-Z. Either pointer may be NULL. Synchronises.
+ * With num_ranks > 1 only the tiles this rank owns are meaningful unless the caller composited
+ * the ranks first (mlv_composite_*). */
+MLV_API int mlv_present_readback(mlv_device *dev, uint32_t *colors, float *depths);
+MLV_API int mlv_get_stats(mlv_device *dev, mlv_stats *out);  /* stats main.c:231,1268 */
+MLV_API int mlv_reset_stats(mlv_device *dev);                /* memset(&stats,0) main.c:1268 */
+
+/* Device-resident resolve: tiled colour/depth -> row-major device buffers with 128-bit stores. */
+MLV_API int mlv_resolve(mlv_device *dev);
+MLV_API void *mlv_resolved_color_device_ptr(mlv_device *dev); /* W*H u32, valid after mlv_resolve */
+MLV_API void *mlv_resolved_depth_device_ptr(mlv_device *dev); /* W*H f32, valid after mlv_resolve */
+
+/* Sort-first compositing. The gather buffer holds num_ranks equal chunks; rank r's
+ * chunk is the row-major colour of its owned stripes in ascending stripe order (padded to the
+ * largest rank's stripe count). mlv_composite_pack fills this rank's chunk; the caller runs
+ * ncclAllGather in place over the whole buffer on mlv_get_stream(); mlv_composite_unpack scatters all
+ * chunks into the resolved row-major colour image. */
+MLV_API int mlv_composite_layout(mlv_device *dev, void **out_gather_device_ptr, size_t *out_chunk_bytes);
+MLV_API int mlv_composite_pack(mlv_device *dev);
+MLV_API int mlv_composite_unpack(mlv_device *dev);
+
+/* ---- debug read-back of the last draw (needs MLV_DEVICE_DEBUG_CAPTURE). Each synchronises.
+ * Pass NULL data pointers to query the counts only. */
+MLV_API int mlv_debug_read_vs_out(mlv_device *dev, float *out12_per_vertex, uint32_t *out_vertex_count);        /* vertex_shader_stage output main.c:714-727, 48 B/vertex */
+MLV_API int mlv_debug_read_triangles(mlv_device *dev, mlv_ref_triangle *tris, float *attributes36, uint32_t *out_count); /* primitive_assembly_stage outputs main.c:877-906 */
+MLV_API int mlv_debug_read_bins(mlv_device *dev, uint32_t *triangle_ids, uint32_t *out_pair_count, mlv_ref_compacted_bin *bins, uint32_t *out_bin_count); /* binner outputs main.c:947-978 */
+MLV_API int mlv_debug_read_masks(mlv_device *dev, mlv_ref_tile_info *infos, uint32_t *out_pair_count);          /* rasterizer output main.c:986-1041 */
+MLV_API int mlv_debug_read_tile_min_depths(mlv_device *dev, float *out_bins);                                    /* a_tile_min_depths main.c:230 */
+
+/* how many kernels this device has launched since creation (bench.py's gpu_launches) */
+MLV_API uint64_t mlv_kernel_launch_count(mlv_device *dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MALEVICH_B200_H */

@@ -1,0 +1,127 @@
+"""ctypes binding of the C-ABI in include/malevich_b200.h (no torch types anywhere in the boundary)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmalevich_b200.so")
+
+# every symbol include/malevich_b200.h declares (tests check the library exports each of them)
+EXPORTED_SYMBOLS = [
+    "mlv_last_error_string", "mlv_create_device", "mlv_destroy_device", "mlv_finish", "mlv_get_stream",
+    "mlv_create_buffer", "mlv_update_buffer", "mlv_release_buffer", "mlv_create_texture2d", "mlv_release_texture",
+    "mlv_ia_set_vertex_buffer", "mlv_ia_set_index_buffer", "mlv_ia_set_input_layout", "mlv_ia_set_primitive_topology",
+    "mlv_vs_set_shader", "mlv_vs_set_constant_buffer", "mlv_vs_set_shader_resource", "mlv_rs_set_viewport",
+    "mlv_ps_set_shader", "mlv_ps_set_shader_resource",
+    "mlv_clear_render_target_view", "mlv_clear_depth_stencil_view", "mlv_draw_indexed", "mlv_draw",
+    "mlv_present_readback", "mlv_get_stats", "mlv_reset_stats",
+    "mlv_resolve", "mlv_resolved_color_device_ptr", "mlv_resolved_depth_device_ptr",
+    "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
+    "mlv_debug_read_vs_out", "mlv_debug_read_triangles", "mlv_debug_read_bins", "mlv_debug_read_masks",
+    "mlv_debug_read_tile_min_depths", "mlv_kernel_launch_count",
+]
+
+MLV_OK = 0
+MLV_ERR_INVALID_ARGUMENT, MLV_ERR_CUDA, MLV_ERR_OUT_OF_MEMORY, MLV_ERR_CAPACITY, MLV_ERR_STATE = 1, 2, 3, 4, 5
+PRIMITIVE_TOPOLOGY_UNDEFINED, PRIMITIVE_TOPOLOGY_TRIANGLELIST = 0, 1
+VS_PASSTHROUGH, VS_BASIC, VS_VERTEX_LIGHTING, VS_FULLSCREEN = 0, 1, 2, 3
+PS_PASSTHROUGH, PS_BASIC, PS_ENV_LIGHTING = 0, 1, 2
+FORMAT_R8G8B8A8_UNORM, FORMAT_R32G32B32A32_FLOAT = 0, 1
+BUFFER_VERTEX, BUFFER_INDEX = 0, 1
+DEVICE_DEBUG_CAPTURE = 1
+
+
+class Viewport(C.Structure):
+    _fields_ = [("top_left_x", C.c_float), ("top_left_y", C.c_float), ("width", C.c_float), ("height", C.c_float),
+                ("min_depth", C.c_float), ("max_depth", C.c_float)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("frame_time", C.c_float), ("vertex_count", C.c_uint32), ("input_triangle_count", C.c_uint32),
+                ("assembled_triangle_count", C.c_uint32), ("active_bin_count", C.c_uint32),
+                ("total_triangle_count_in_bins", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "frame_time"}
+
+
+class DeviceDesc(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("cuda_device", C.c_int32), ("num_ranks", C.c_uint32),
+                ("rank", C.c_uint32), ("stripe_height_tiles", C.c_uint32), ("max_pairs_per_draw", C.c_uint64),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class MalevichError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"malevich_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the CUDA extension. Fails loudly when it has not been built: there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make -C malevich_b200/csrc` or __graft_entry__.build(); "
+                          "malevich_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, u32, i32, f32, sz = C.c_void_p, C.c_uint32, C.c_int, C.c_float, C.c_size_t
+    P = C.POINTER
+    sig = {
+        "mlv_last_error_string": (C.c_char_p, []),
+        "mlv_create_device": (i32, [P(DeviceDesc), P(vp)]),
+        "mlv_destroy_device": (None, [vp]),
+        "mlv_finish": (i32, [vp]),
+        "mlv_get_stream": (vp, [vp]),
+        "mlv_create_buffer": (i32, [vp, vp, sz, i32, P(vp)]),
+        "mlv_update_buffer": (i32, [vp, vp, vp, sz]),
+        "mlv_release_buffer": (None, [vp, vp]),
+        "mlv_create_texture2d": (i32, [vp, vp, u32, u32, i32, P(vp)]),
+        "mlv_release_texture": (None, [vp, vp]),
+        "mlv_ia_set_vertex_buffer": (i32, [vp, vp]),
+        "mlv_ia_set_index_buffer": (i32, [vp, vp]),
+        "mlv_ia_set_input_layout": (i32, [vp, u32]),
+        "mlv_ia_set_primitive_topology": (i32, [vp, i32]),
+        "mlv_vs_set_shader": (i32, [vp, i32]),
+        "mlv_vs_set_constant_buffer": (i32, [vp, u32, vp, sz]),
+        "mlv_vs_set_shader_resource": (i32, [vp, u32, vp]),
+        "mlv_rs_set_viewport": (i32, [vp, P(Viewport)]),
+        "mlv_ps_set_shader": (i32, [vp, i32]),
+        "mlv_ps_set_shader_resource": (i32, [vp, u32, vp]),
+        "mlv_clear_render_target_view": (i32, [vp, P(f32)]),
+        "mlv_clear_depth_stencil_view": (i32, [vp, f32]),
+        "mlv_draw_indexed": (i32, [vp, u32]),
+        "mlv_draw": (i32, [vp, u32]),
+        "mlv_present_readback": (i32, [vp, vp, vp]),
+        "mlv_get_stats": (i32, [vp, P(Stats)]),
+        "mlv_reset_stats": (i32, [vp]),
+        "mlv_resolve": (i32, [vp]),
+        "mlv_resolved_color_device_ptr": (vp, [vp]),
+        "mlv_resolved_depth_device_ptr": (vp, [vp]),
+        "mlv_composite_layout": (i32, [vp, P(vp), P(sz)]),
+        "mlv_composite_pack": (i32, [vp]),
+        "mlv_composite_unpack": (i32, [vp]),
+        "mlv_debug_read_vs_out": (i32, [vp, vp, P(u32)]),
+        "mlv_debug_read_triangles": (i32, [vp, vp, vp, P(u32)]),
+        "mlv_debug_read_bins": (i32, [vp, vp, P(u32), vp, P(u32)]),
+        "mlv_debug_read_masks": (i32, [vp, vp, P(u32)]),
+        "mlv_debug_read_tile_min_depths": (i32, [vp, vp]),
+        "mlv_kernel_launch_count": (C.c_uint64, [vp]),
+    }
+    assert sorted(sig) == sorted(EXPORTED_SYMBOLS)
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != MLV_OK:
+        raise MalevichError(code, load().mlv_last_error_string().decode("utf-8", "replace"))

@@ -1,0 +1,710 @@
+// malevich_b200.cu -- C-ABI host layer over the sm_100a kernels (include/malevich_b200.h).
+//
+// Mirrors the reference's L4 boundary: a bound-state object that the host mutates
+// (graphics_pipeline main.c:71-115,222) and three entry points (clear_render_target_view :1191,
+// clear_depth_stencil_view :1204, draw_indexed :1219). Everything a draw needs stays on the device:
+// one draw = five stream-ordered kernel launches, no host synchronisation, no per-draw allocation
+// (the reference mallocs/frees seven intermediates per draw, main.c:1222-1259).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+
+#include "kernels.cuh"
+
+using namespace mlv;
+
+static const uint32_t k_rsqrt_lut_host[2048] = {
+#include "rsqrt_lut.inc"
+};
+
+static thread_local char g_last_error[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CUDA_TRY(expr)                                                                                               \
+	do {                                                                                                             \
+		cudaError_t _e = (expr);                                                                                     \
+		if(_e != cudaSuccess) return fail(_e == cudaErrorMemoryAllocation ? MLV_ERR_OUT_OF_MEMORY : MLV_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+	} while(0)
+
+struct mlv_buffer {
+	void *d;
+	size_t bytes;
+	int kind;
+};
+struct mlv_texture {
+	void *d;
+	uint32_t width, height;
+	int format;
+};
+
+struct mlv_device {
+	mlv_device_desc desc;
+	int cuda_dev;
+	cudaStream_t stream;
+	int W, H, wt, ht;
+	uint32_t num_bins;
+	Partition part;
+
+	// persistent render state (reference: static frame_buffer/depth_buffer/a_tile_min_depths)
+	uint4 *fb;
+	float *tile_min;
+	// per-draw arenas
+	uint32_t *bin_count, *bin_offset;
+	mlv_ref_compacted_bin *cbins;
+	uint32_t *pair_ids, *pair_tmp;
+	uint64_t pair_capacity;
+	uint4 *tri_cov, *tri_shade;
+	uint2 *tri_bounds;
+	uint32_t tri_capacity;
+	unsigned long long *scan_state;
+	uint32_t scan_capacity;
+	Counters *ctr;
+	uint32_t *rsqrt_lut;
+	// debug capture
+	DebugOut dbg;
+	uint32_t dbg_tri_capacity, dbg_vertex_capacity;
+	uint32_t last_index_count;
+	// present / composite
+	uint4 *resolved_color;
+	float4 *resolved_depth;
+	uint4 *gather;
+	size_t chunk_bytes;
+
+	// bound pipeline state (graphics_pipeline)
+	mlv_buffer *vb, *ib;
+	uint32_t input_layout;
+	int topology;
+	int vs_id, ps_id;
+	float cb[MLV_CONSTANT_BUFFER_SLOT_COUNT][64];
+	size_t cb_bytes[MLV_CONSTANT_BUFFER_SLOT_COUNT];
+	mlv_texture *vs_srv[MLV_SHADER_RESOURCE_SLOT_COUNT], *ps_srv[MLV_SHADER_RESOURCE_SLOT_COUNT];
+	mlv_viewport viewport;
+	bool viewport_set;
+
+	bool pend_color, pend_depth;
+	uint32_t clear_color;
+	float clear_depth;
+
+	uint32_t ticket_base, epoch;
+	uint64_t launches;
+};
+
+static int use_device(mlv_device *dev) {
+	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
+	CUDA_TRY(cudaSetDevice(dev->cuda_dev));
+	return MLV_OK;
+}
+
+static int check_launch(mlv_device *dev, const char *what) {
+	cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return fail(MLV_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+	dev->launches++;
+	return MLV_OK;
+}
+
+extern "C" {
+
+const char *mlv_last_error_string(void) { return g_last_error; }
+
+int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
+	if(!desc || !out_device) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	*out_device = nullptr;
+	if(desc->width == 0 || desc->height == 0 || (desc->width % 8) || (desc->height % 8))
+		return fail(MLV_ERR_INVALID_ARGUMENT, "render target %ux%u: width and height must be non-zero multiples of 8 (reference WIDTH_IN_TILES main.c:28-29)", desc->width,
+		            desc->height);
+	if(desc->width > 32768 || desc->height > 32768) return fail(MLV_ERR_INVALID_ARGUMENT, "render target too large");
+	const uint32_t num_ranks = desc->num_ranks ? desc->num_ranks : 1;
+	if(desc->rank >= num_ranks) return fail(MLV_ERR_INVALID_ARGUMENT, "rank %u out of range for %u ranks", desc->rank, num_ranks);
+
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if(e != cudaSuccess || count == 0) return fail(MLV_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+	int cuda_dev = desc->cuda_device;
+	if(cuda_dev < 0) CUDA_TRY(cudaGetDevice(&cuda_dev));
+	if(cuda_dev >= count) return fail(MLV_ERR_INVALID_ARGUMENT, "cuda_device %d out of range (%d devices)", cuda_dev, count);
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, cuda_dev));
+	if(prop.major != 10) return fail(MLV_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", cuda_dev, prop.major, prop.minor);
+	CUDA_TRY(cudaSetDevice(cuda_dev));
+
+	mlv_device *dev = new(std::nothrow) mlv_device();
+	if(!dev) return fail(MLV_ERR_OUT_OF_MEMORY, "host allocation failed");
+	memset(dev, 0, sizeof(*dev));
+	dev->desc = *desc;
+	dev->cuda_dev = cuda_dev;
+	dev->W = (int)desc->width;
+	dev->H = (int)desc->height;
+	dev->wt = dev->W / 8;
+	dev->ht = dev->H / 8;
+	dev->num_bins = (uint32_t)(dev->wt * dev->ht);
+	dev->part.num_ranks = (int)num_ranks;
+	dev->part.rank = (int)desc->rank;
+	dev->part.stripe_h = desc->stripe_height_tiles ? (int)desc->stripe_height_tiles : 1;
+	dev->pair_capacity = desc->max_pairs_per_draw ? desc->max_pairs_per_draw : (16ull << 20);
+	if(dev->pair_capacity > 0xfffffff0ull) dev->pair_capacity = 0xfffffff0ull;
+	dev->epoch = 0;
+	dev->vs_id = -1;
+	dev->ps_id = -1;
+
+#define CREATE_TRY(expr)                          \
+	do {                                          \
+		cudaError_t _e2 = (expr);                 \
+		if(_e2 != cudaSuccess) {                  \
+			int rc = fail(_e2 == cudaErrorMemoryAllocation ? MLV_ERR_OUT_OF_MEMORY : MLV_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e2)); \
+			mlv_destroy_device(dev);              \
+			return rc;                            \
+		}                                         \
+	} while(0)
+
+	CREATE_TRY(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+	const size_t nb = dev->num_bins;
+	CREATE_TRY(cudaMalloc(&dev->fb, nb * 32 * sizeof(uint4)));
+	CREATE_TRY(cudaMalloc(&dev->tile_min, nb * sizeof(float)));
+	CREATE_TRY(cudaMalloc(&dev->bin_count, nb * sizeof(uint32_t)));
+	CREATE_TRY(cudaMalloc(&dev->bin_offset, nb * sizeof(uint32_t)));
+	CREATE_TRY(cudaMalloc(&dev->cbins, nb * sizeof(mlv_ref_compacted_bin)));
+	CREATE_TRY(cudaMalloc(&dev->pair_ids, dev->pair_capacity * sizeof(uint32_t)));
+	CREATE_TRY(cudaMalloc(&dev->pair_tmp, dev->pair_capacity * sizeof(uint32_t)));
+	CREATE_TRY(cudaMalloc(&dev->ctr, sizeof(Counters)));
+	CREATE_TRY(cudaMalloc(&dev->rsqrt_lut, sizeof(k_rsqrt_lut_host)));
+	CREATE_TRY(cudaMalloc(&dev->resolved_color, (size_t)dev->W * dev->H * 4));
+	CREATE_TRY(cudaMalloc(&dev->resolved_depth, (size_t)dev->W * dev->H * 4));
+	CREATE_TRY(cudaMemsetAsync(dev->fb, 0, nb * 32 * sizeof(uint4), dev->stream));
+	CREATE_TRY(cudaMemsetAsync(dev->tile_min, 0, nb * sizeof(float), dev->stream));
+	CREATE_TRY(cudaMemsetAsync(dev->bin_count, 0, nb * sizeof(uint32_t), dev->stream));
+	CREATE_TRY(cudaMemsetAsync(dev->ctr, 0, sizeof(Counters), dev->stream));
+	CREATE_TRY(cudaMemcpyAsync(dev->rsqrt_lut, k_rsqrt_lut_host, sizeof(k_rsqrt_lut_host), cudaMemcpyHostToDevice, dev->stream));
+	if(num_ranks > 1) {
+		const uint32_t sh = (uint32_t)dev->part.stripe_h;
+		const uint32_t num_stripes = ((uint32_t)dev->ht + sh - 1) / sh;
+		const uint32_t local_stripes = (num_stripes + num_ranks - 1) / num_ranks;
+		dev->chunk_bytes = (size_t)local_stripes * sh * 8 * dev->W * 4;
+		CREATE_TRY(cudaMalloc(&dev->gather, dev->chunk_bytes * num_ranks));
+		CREATE_TRY(cudaMemsetAsync(dev->gather, 0, dev->chunk_bytes * num_ranks, dev->stream));
+	}
+	CREATE_TRY(cudaStreamSynchronize(dev->stream));
+#undef CREATE_TRY
+	*out_device = dev;
+	return MLV_OK;
+}
+
+void mlv_destroy_device(mlv_device *dev) {
+	if(!dev) return;
+	cudaSetDevice(dev->cuda_dev);
+	if(dev->stream) cudaStreamSynchronize(dev->stream);
+	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds,
+		             dev->scan_state, dev->ctr, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
+	for(void *p : ptrs)
+		if(p) cudaFree(p);
+	if(dev->stream) cudaStreamDestroy(dev->stream);
+	delete dev;
+}
+
+int mlv_finish(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	return MLV_OK;
+}
+
+void *mlv_get_stream(mlv_device *dev) { return dev ? (void *)dev->stream : nullptr; }
+
+// ---- resources -----------------------------------------------------------------------------------
+
+int mlv_create_buffer(mlv_device *dev, const void *data, size_t bytes, int kind, mlv_buffer **out) {
+	if(int rc = use_device(dev)) return rc;
+	if(!out || bytes == 0 || (kind != MLV_BUFFER_VERTEX && kind != MLV_BUFFER_INDEX)) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer arguments");
+	mlv_buffer *b = new(std::nothrow) mlv_buffer();
+	if(!b) return fail(MLV_ERR_OUT_OF_MEMORY, "host allocation failed");
+	b->bytes = bytes;
+	b->kind = kind;
+	cudaError_t e = cudaMalloc(&b->d, (bytes + 15) & ~(size_t)15);
+	if(e != cudaSuccess) {
+		delete b;
+		return fail(MLV_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+	}
+	*out = b;
+	if(data) return mlv_update_buffer(dev, b, data, bytes);
+	return MLV_OK;
+}
+
+int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t bytes) {
+	if(int rc = use_device(dev)) return rc;
+	if(!buf || !data || bytes > buf->bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer update");
+	CUDA_TRY(cudaMemcpyAsync(buf->d, data, bytes, cudaMemcpyHostToDevice, dev->stream));
+	return MLV_OK;
+}
+
+void mlv_release_buffer(mlv_device *dev, mlv_buffer *buf) {
+	if(!dev || !buf) return;
+	cudaSetDevice(dev->cuda_dev);
+	cudaStreamSynchronize(dev->stream);
+	if(dev->vb == buf) dev->vb = nullptr;
+	if(dev->ib == buf) dev->ib = nullptr;
+	cudaFree(buf->d);
+	delete buf;
+}
+
+int mlv_create_texture2d(mlv_device *dev, const void *texels, uint32_t width, uint32_t height, int format, mlv_texture **out) {
+	if(int rc = use_device(dev)) return rc;
+	if(!out || !texels || width == 0 || height == 0 || (format != MLV_FORMAT_R8G8B8A8_UNORM && format != MLV_FORMAT_R32G32B32A32_FLOAT))
+		return fail(MLV_ERR_INVALID_ARGUMENT, "bad texture arguments");
+	if((uint64_t)width * height > 0x7fffffffull / 4) return fail(MLV_ERR_INVALID_ARGUMENT, "texture too large for the reference's i32 texel addressing (common_shader_core.h:33,46)");
+	mlv_texture *t = new(std::nothrow) mlv_texture();
+	if(!t) return fail(MLV_ERR_OUT_OF_MEMORY, "host allocation failed");
+	t->width = width;
+	t->height = height;
+	t->format = format;
+	const size_t bytes = (size_t)width * height * (format == MLV_FORMAT_R8G8B8A8_UNORM ? 4 : 16);
+	cudaError_t e = cudaMalloc(&t->d, bytes);
+	if(e == cudaSuccess) e = cudaMemcpyAsync(t->d, texels, bytes, cudaMemcpyHostToDevice, dev->stream);
+	if(e != cudaSuccess) {
+		if(t->d) cudaFree(t->d);
+		delete t;
+		return fail(MLV_ERR_CUDA, "texture upload: %s", cudaGetErrorString(e));
+	}
+	*out = t;
+	return MLV_OK;
+}
+
+void mlv_release_texture(mlv_device *dev, mlv_texture *tex) {
+	if(!dev || !tex) return;
+	cudaSetDevice(dev->cuda_dev);
+	cudaStreamSynchronize(dev->stream);
+	for(int i = 0; i < MLV_SHADER_RESOURCE_SLOT_COUNT; ++i) {
+		if(dev->vs_srv[i] == tex) dev->vs_srv[i] = nullptr;
+		if(dev->ps_srv[i] == tex) dev->ps_srv[i] = nullptr;
+	}
+	cudaFree(tex->d);
+	delete tex;
+}
+
+// ---- pipeline state ------------------------------------------------------------------------------
+
+int mlv_ia_set_vertex_buffer(mlv_device *dev, mlv_buffer *vb) {
+	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
+	if(vb && vb->kind != MLV_BUFFER_VERTEX) return fail(MLV_ERR_INVALID_ARGUMENT, "buffer is not a vertex buffer");
+	dev->vb = vb;
+	return MLV_OK;
+}
+int mlv_ia_set_index_buffer(mlv_device *dev, mlv_buffer *ib) {
+	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
+	if(ib && ib->kind != MLV_BUFFER_INDEX) return fail(MLV_ERR_INVALID_ARGUMENT, "buffer is not an index buffer");
+	dev->ib = ib;
+	return MLV_OK;
+}
+int mlv_ia_set_input_layout(mlv_device *dev, uint32_t bytes_per_vertex) {
+	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
+	if(bytes_per_vertex != 32) return fail(MLV_ERR_INVALID_ARGUMENT, "input layout %u: every reference shader consumes 32-byte vertices (in_vertex_size/VECTOR_WIDTH main.c:1286)", bytes_per_vertex);
+	dev->input_layout = bytes_per_vertex;
+	return MLV_OK;
+}
+int mlv_ia_set_primitive_topology(mlv_device *dev, int topology) {
+	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
+	dev->topology = topology;
+	return MLV_OK;
+}
+int mlv_vs_set_shader(mlv_device *dev, int vs_id) {
+	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
+	if(vs_id < 0 || vs_id >= MLV_VS_COUNT) return fail(MLV_ERR_INVALID_ARGUMENT, "unknown vertex shader id %d", vs_id);
+	dev->vs_id = vs_id;
+	return MLV_OK;
+}
+int mlv_vs_set_constant_buffer(mlv_device *dev, uint32_t slot, const void *data, size_t bytes) {
+	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
+	if(slot >= MLV_CONSTANT_BUFFER_SLOT_COUNT || !data || bytes > sizeof(dev->cb[0])) return fail(MLV_ERR_INVALID_ARGUMENT, "bad constant buffer (slot %u, %zu bytes)", slot, bytes);
+	memcpy(dev->cb[slot], data, bytes);
+	dev->cb_bytes[slot] = bytes;
+	return MLV_OK;
+}
+int mlv_vs_set_shader_resource(mlv_device *dev, uint32_t slot, mlv_texture *tex) {
+	if(!dev || slot >= MLV_SHADER_RESOURCE_SLOT_COUNT) return fail(MLV_ERR_INVALID_ARGUMENT, "bad shader resource slot");
+	dev->vs_srv[slot] = tex;
+	return MLV_OK;
+}
+int mlv_rs_set_viewport(mlv_device *dev, const mlv_viewport *vp) {
+	if(!dev || !vp) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	if((int)vp->width != dev->W || (int)vp->height != dev->H)
+		return fail(MLV_ERR_INVALID_ARGUMENT, "viewport %gx%g must equal the render target %dx%d (reference tile pitch main.c:582,590)", vp->width, vp->height, dev->W, dev->H);
+	dev->viewport = *vp;
+	dev->viewport_set = true;
+	return MLV_OK;
+}
+int mlv_ps_set_shader(mlv_device *dev, int ps_id) {
+	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
+	if(ps_id < 0 || ps_id >= MLV_PS_COUNT) return fail(MLV_ERR_INVALID_ARGUMENT, "unknown pixel shader id %d", ps_id);
+	dev->ps_id = ps_id;
+	return MLV_OK;
+}
+int mlv_ps_set_shader_resource(mlv_device *dev, uint32_t slot, mlv_texture *tex) {
+	if(!dev || slot >= MLV_SHADER_RESOURCE_SLOT_COUNT) return fail(MLV_ERR_INVALID_ARGUMENT, "bad shader resource slot");
+	dev->ps_srv[slot] = tex;
+	return MLV_OK;
+}
+
+// ---- clears --------------------------------------------------------------------------------------
+
+static int flush_clears(mlv_device *dev) {
+	if(!dev->pend_color && !dev->pend_depth) return MLV_OK;
+	const int mode = (dev->pend_color ? 1 : 0) | (dev->pend_depth ? 2 : 0);
+	const uint32_t n = dev->num_bins * 32u;
+	k_clear<<<(n + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->tile_min, dev->num_bins, dev->clear_color, dev->clear_depth, mode);
+	dev->pend_color = dev->pend_depth = false;
+	return check_launch(dev, "k_clear");
+}
+
+int mlv_clear_render_target_view(mlv_device *dev, const float rgba[4]) {
+	if(!dev || !rgba) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	// encode_color_as_u32 (math.h:322-324): truncation, R in the low byte -- not the PS path's channel order (App. C 4)
+	dev->clear_color = (((uint32_t)(rgba[3] * 255.f)) << 24) + (((uint32_t)(rgba[2] * 255.f)) << 16) + (((uint32_t)(rgba[1] * 255.f)) << 8) + (((uint32_t)(rgba[0] * 255.f)));
+	dev->pend_color = true;
+	return MLV_OK; // the fill itself is fused with the depth clear and issued with the next draw / read-back
+}
+
+int mlv_clear_depth_stencil_view(mlv_device *dev, float depth) {
+	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
+	dev->clear_depth = depth;
+	dev->pend_depth = true;
+	return MLV_OK;
+}
+
+// ---- draw ----------------------------------------------------------------------------------------
+
+} // extern "C"
+
+template <typename T>
+static cudaError_t regrow(T **p, size_t count) {
+	if(*p) cudaFree(*p);
+	*p = nullptr;
+	return cudaMalloc((void **)p, count * sizeof(T));
+}
+
+static TexDesc tex_desc(const mlv_texture *t) {
+	TexDesc d;
+	d.data = t ? t->d : nullptr;
+	d.width = t ? (int)t->width : 0;
+	d.height = t ? (int)t->height : 0;
+	d.format = t ? t->format : 0;
+	return d;
+}
+
+template <int VS>
+static void launch_geom(mlv_device *dev, const GeomParams &gp, bool indexed) {
+	if(indexed) k_geom<VS, true><<<gp.num_blocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+	else k_geom<VS, false><<<gp.num_blocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+}
+
+static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
+	if(int rc = use_device(dev)) return rc;
+	// the reference's asserts (main.c:666,670,1230) become argument errors
+	if(dev->topology != MLV_PRIMITIVE_TOPOLOGY_TRIANGLELIST) return fail(MLV_ERR_STATE, "primitive topology must be TRIANGLELIST (main.c:666)");
+	if(count & 7u) return fail(MLV_ERR_INVALID_ARGUMENT, "index_count %u is not divisible by 8 (main.c:670)", count);
+	if(count % 3u) return fail(MLV_ERR_INVALID_ARGUMENT, "index_count %u is not divisible by 3 (main.c:1230)", count);
+	if(dev->input_layout != 32) return fail(MLV_ERR_STATE, "input layout not set");
+	if(!dev->vb) return fail(MLV_ERR_STATE, "no vertex buffer bound");
+	if(indexed && !dev->ib) return fail(MLV_ERR_STATE, "no index buffer bound");
+	if(indexed && (size_t)count * 4 > dev->ib->bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "index_count %u exceeds the bound index buffer", count);
+	if(!indexed && (size_t)count * 32 > dev->vb->bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "vertex_count %u exceeds the bound vertex buffer", count);
+	if(dev->vs_id < 0 || dev->ps_id < 0) return fail(MLV_ERR_STATE, "vertex and pixel shader must be bound");
+	if(!dev->viewport_set) return fail(MLV_ERR_STATE, "viewport not set");
+	if(dev->vs_id != MLV_VS_PASSTHROUGH && dev->cb_bytes[0] < 192) return fail(MLV_ERR_STATE, "constant buffer slot 0 must hold the 192-byte PerFrameCB (main.c:169-173)");
+	if(dev->vs_id == MLV_VS_VERTEX_LIGHTING && !(dev->vs_srv[0] && dev->vs_srv[0]->format == MLV_FORMAT_R32G32B32A32_FLOAT))
+		return fail(MLV_ERR_STATE, "vertex_lighting_vs needs an RGBA32F panorama in VS resource slot 0");
+	if(dev->ps_id == MLV_PS_BASIC && !(dev->ps_srv[0] && dev->ps_srv[0]->format == MLV_FORMAT_R8G8B8A8_UNORM))
+		return fail(MLV_ERR_STATE, "basic_ps needs an R8G8B8A8 texture in PS resource slot 0");
+	if(dev->ps_id == MLV_PS_ENV_LIGHTING && !(dev->ps_srv[0] && dev->ps_srv[0]->format == MLV_FORMAT_R32G32B32A32_FLOAT))
+		return fail(MLV_ERR_STATE, "env_lighting_ps needs an RGBA32F panorama in PS resource slot 0");
+	if(int rc = flush_clears(dev)) return rc;
+	dev->last_index_count = count;
+	if(count == 0) return MLV_OK;
+
+	const uint32_t T = count / 3u;
+	if(T >= 0x40000000u / 3u) return fail(MLV_ERR_INVALID_ARGUMENT, "draw too large");
+	// capacity of the reference's own output arrays: T + max(2T, 512) (main.c:739-740)
+	const uint32_t need_tris = T + (2u * T > 512u ? 2u * T : 512u);
+	const uint32_t nblocks = (T + MLV_GEOM_THREADS - 1) / MLV_GEOM_THREADS;
+	const bool debug = (dev->desc.flags & MLV_DEVICE_DEBUG_CAPTURE) != 0;
+	if(need_tris > dev->tri_capacity || nblocks > dev->scan_capacity || (debug && (need_tris > dev->dbg_tri_capacity || count > dev->dbg_vertex_capacity || !dev->dbg.infos))) {
+		CUDA_TRY(cudaStreamSynchronize(dev->stream));
+		if(need_tris > dev->tri_capacity) {
+			const uint32_t cap = need_tris + need_tris / 4;
+			CUDA_TRY(regrow(&dev->tri_cov, (size_t)cap * MLV_TRI_COV_U4));
+			CUDA_TRY(regrow(&dev->tri_shade, (size_t)cap * MLV_TRI_SHADE_U4));
+			CUDA_TRY(regrow(&dev->tri_bounds, (size_t)cap));
+			dev->tri_capacity = cap;
+		}
+		if(nblocks > dev->scan_capacity) {
+			const uint32_t cap = nblocks * 2;
+			CUDA_TRY(regrow(&dev->scan_state, (size_t)cap));
+			CUDA_TRY(cudaMemset(dev->scan_state, 0, (size_t)cap * sizeof(unsigned long long)));
+			dev->scan_capacity = cap;
+		}
+		if(debug) {
+			if(need_tris > dev->dbg_tri_capacity) {
+				CUDA_TRY(regrow(&dev->dbg.tris, (size_t)dev->tri_capacity));
+				CUDA_TRY(regrow(&dev->dbg.attrs, (size_t)dev->tri_capacity * 36));
+				dev->dbg_tri_capacity = dev->tri_capacity;
+			}
+			if(count > dev->dbg_vertex_capacity) {
+				CUDA_TRY(regrow(&dev->dbg.vs_out, (size_t)count * 12));
+				dev->dbg_vertex_capacity = count;
+			}
+			if(!dev->dbg.infos) CUDA_TRY(regrow(&dev->dbg.infos, (size_t)dev->pair_capacity));
+		}
+	}
+
+	dev->epoch = (dev->epoch + 1u) & 0x3fffffffu;
+	if(dev->epoch == 0u) { // 30-bit epoch wrapped: invalidate every published scan entry
+		CUDA_TRY(cudaMemsetAsync(dev->scan_state, 0, (size_t)dev->scan_capacity * sizeof(unsigned long long), dev->stream));
+		dev->epoch = 1u;
+	}
+
+	GeomParams gp;
+	memset(&gp, 0, sizeof(gp));
+	gp.ib = indexed ? (const uint32_t *)dev->ib->d : nullptr;
+	gp.vb = (const float4 *)dev->vb->d;
+	gp.tri_count = T;
+	gp.tri_capacity = need_tris;
+	memcpy(gp.cb, dev->cb[0], 192);
+	gp.vs_tex = tex_desc(dev->vs_srv[0]);
+	gp.rsqrt_lut = dev->rsqrt_lut;
+	{ // screen_from_ndc initialiser (main.c:825-830): double arithmetic rounded to f32 per entry
+		const mlv_viewport &vp = dev->viewport;
+		gp.vp_m00 = (float)((double)vp.width * 0.5);
+		gp.vp_m03 = (float)((double)vp.width * 0.5 + (double)vp.top_left_x);
+		gp.vp_m11 = (float)((double)(-vp.height) * 0.5);
+		gp.vp_m13 = (float)((double)vp.height * 0.5 + (double)vp.top_left_y);
+		gp.vp_m22 = vp.max_depth - vp.min_depth;
+		gp.vp_m23 = vp.min_depth;
+		gp.vp_w = (int)vp.width;
+		gp.vp_h = (int)vp.height;
+	}
+	gp.wt = dev->wt;
+	gp.ht = dev->ht;
+	{ // v4f32_normalize((+-1,0,0,1)) (math.h:259-270): 1.0 / (f32)sqrt(dot), double divide rounded to f32
+		const float len = (float)sqrt((double)2.0f);
+		gp.clip_k = (float)(1.0 / (double)len);
+	}
+	gp.part = dev->part;
+	gp.tri_cov = dev->tri_cov;
+	gp.tri_shade = dev->tri_shade;
+	gp.tri_bounds = dev->tri_bounds;
+	if(debug) gp.dbg = dev->dbg;
+	gp.scan_state = dev->scan_state;
+	gp.ctr = dev->ctr;
+	gp.ticket_base = dev->ticket_base;
+	gp.epoch = dev->epoch;
+	gp.num_blocks = nblocks;
+	gp.index_count = count;
+	dev->ticket_base += nblocks;
+
+	switch(dev->vs_id) {
+		case MLV_VS_PASSTHROUGH: launch_geom<0>(dev, gp, indexed); break;
+		case MLV_VS_BASIC: launch_geom<1>(dev, gp, indexed); break;
+		case MLV_VS_VERTEX_LIGHTING: launch_geom<2>(dev, gp, indexed); break;
+		default: launch_geom<3>(dev, gp, indexed); break;
+	}
+	if(int rc = check_launch(dev, "k_geom")) return rc;
+
+	BinParams bp;
+	bp.tri_bounds = dev->tri_bounds;
+	bp.bin_count = dev->bin_count;
+	bp.bin_cursor = nullptr;
+	bp.bin_offset = dev->bin_offset;
+	bp.pair_ids = dev->pair_ids;
+	bp.ctr = dev->ctr;
+	bp.wt = dev->wt;
+	bp.ht = dev->ht;
+	bp.part = dev->part;
+	uint32_t bin_blocks = (need_tris + 255u) / 256u;
+	if(bin_blocks > 148u * 16u) bin_blocks = 148u * 16u;
+	k_bin<false><<<bin_blocks, 256, 0, dev->stream>>>(bp, (uint32_t)dev->pair_capacity);
+	if(int rc = check_launch(dev, "k_bin<count>")) return rc;
+
+	ScanParams sp;
+	sp.bin_count = dev->bin_count;
+	sp.bin_cursor = nullptr;
+	sp.bin_offset = dev->bin_offset;
+	sp.cbins = dev->cbins;
+	sp.ctr = dev->ctr;
+	sp.num_bins = dev->num_bins;
+	sp.pair_capacity = (uint32_t)dev->pair_capacity;
+	k_bin_scan<<<1, 1024, 0, dev->stream>>>(sp);
+	if(int rc = check_launch(dev, "k_bin_scan")) return rc;
+
+	k_bin<true><<<bin_blocks, 256, 0, dev->stream>>>(bp, (uint32_t)dev->pair_capacity);
+	if(int rc = check_launch(dev, "k_bin<fill>")) return rc;
+
+	TileParams tp;
+	memset(&tp, 0, sizeof(tp));
+	tp.cbins = dev->cbins;
+	tp.pair_ids = dev->pair_ids;
+	tp.pair_tmp = dev->pair_tmp;
+	tp.tri_cov = dev->tri_cov;
+	tp.tri_shade = dev->tri_shade;
+	tp.fb = dev->fb;
+	tp.tile_min = dev->tile_min;
+	tp.bin_count = dev->bin_count;
+	tp.ctr = dev->ctr;
+	tp.ps_tex = tex_desc(dev->ps_srv[0]);
+	tp.rsqrt_lut = dev->rsqrt_lut;
+	if(debug) tp.dbg = dev->dbg;
+	tp.wt = dev->wt;
+	uint32_t tile_blocks = (dev->num_bins + 7u) / 8u;
+	if(tile_blocks > 148u * 8u) tile_blocks = 148u * 8u;
+	switch(dev->ps_id) {
+		case MLV_PS_PASSTHROUGH: k_tile<0><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp); break;
+		case MLV_PS_BASIC: k_tile<1><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp); break;
+		default: k_tile<2><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp); break;
+	}
+	return check_launch(dev, "k_tile");
+}
+
+extern "C" {
+
+int mlv_draw_indexed(mlv_device *dev, uint32_t index_count) { return draw_common(dev, index_count, true); }
+int mlv_draw(mlv_device *dev, uint32_t vertex_count) { return draw_common(dev, vertex_count, false); }
+
+// ---- results -------------------------------------------------------------------------------------
+
+static int check_flags(mlv_device *dev, const Counters &c) {
+	if(c.error_flags & MLV_FLAG_TRI_OVERFLOW) return fail(MLV_ERR_CAPACITY, "a draw assembled more than T + max(2T,512) triangles (the reference's own buffer bound, main.c:739-740)");
+	if(c.error_flags & MLV_FLAG_PAIR_OVERFLOW)
+		return fail(MLV_ERR_CAPACITY, "a draw produced more (triangle,tile) pairs than max_pairs_per_draw = %llu; that draw was skipped", (unsigned long long)dev->pair_capacity);
+	return MLV_OK;
+}
+
+int mlv_resolve(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	if(int rc = flush_clears(dev)) return rc;
+	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
+	k_resolve<<<(quads + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->resolved_color, dev->resolved_depth, dev->W, dev->H);
+	return check_launch(dev, "k_resolve");
+}
+
+void *mlv_resolved_color_device_ptr(mlv_device *dev) { return dev ? dev->resolved_color : nullptr; }
+void *mlv_resolved_depth_device_ptr(mlv_device *dev) { return dev ? dev->resolved_depth : nullptr; }
+
+int mlv_present_readback(mlv_device *dev, uint32_t *colors, float *depths) {
+	if(int rc = use_device(dev)) return rc;
+	if(int rc = flush_clears(dev)) return rc;
+	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
+	k_resolve<<<(quads + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->resolved_color, depths ? dev->resolved_depth : nullptr, dev->W, dev->H);
+	if(int rc = check_launch(dev, "k_resolve")) return rc;
+	const size_t bytes = (size_t)dev->W * dev->H * 4;
+	if(colors) CUDA_TRY(cudaMemcpyAsync(colors, dev->resolved_color, bytes, cudaMemcpyDeviceToHost, dev->stream));
+	if(depths) CUDA_TRY(cudaMemcpyAsync(depths, dev->resolved_depth, bytes, cudaMemcpyDeviceToHost, dev->stream));
+	Counters c;
+	CUDA_TRY(cudaMemcpyAsync(&c, dev->ctr, sizeof(c), cudaMemcpyDeviceToHost, dev->stream));
+	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	return check_flags(dev, c);
+}
+
+int mlv_get_stats(mlv_device *dev, mlv_stats *out) {
+	if(int rc = use_device(dev)) return rc;
+	if(!out) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	Counters c;
+	CUDA_TRY(cudaMemcpyAsync(&c, dev->ctr, sizeof(c), cudaMemcpyDeviceToHost, dev->stream));
+	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	*out = c.stats;
+	return check_flags(dev, c);
+}
+
+int mlv_reset_stats(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	CUDA_TRY(cudaMemsetAsync((char *)dev->ctr + offsetof(Counters, stats), 0, sizeof(mlv_stats), dev->stream));
+	CUDA_TRY(cudaMemsetAsync((char *)dev->ctr + offsetof(Counters, error_flags), 0, sizeof(uint32_t), dev->stream));
+	return MLV_OK;
+}
+
+int mlv_composite_layout(mlv_device *dev, void **out_gather_device_ptr, size_t *out_chunk_bytes) {
+	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
+	if(dev->part.num_ranks <= 1) return fail(MLV_ERR_STATE, "device was created with a single rank");
+	if(out_gather_device_ptr) *out_gather_device_ptr = dev->gather;
+	if(out_chunk_bytes) *out_chunk_bytes = dev->chunk_bytes;
+	return MLV_OK;
+}
+
+int mlv_composite_pack(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	if(dev->part.num_ranks <= 1) return fail(MLV_ERR_STATE, "device was created with a single rank");
+	if(int rc = flush_clears(dev)) return rc;
+	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
+	uint4 *chunk = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(dev->gather) + dev->chunk_bytes * (size_t)dev->part.rank);
+	k_composite_pack<<<(quads + 255) / 256, 256, 0, dev->stream>>>(dev->fb, chunk, dev->W, dev->H, dev->part);
+	return check_launch(dev, "k_composite_pack");
+}
+
+int mlv_composite_unpack(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	if(dev->part.num_ranks <= 1) return fail(MLV_ERR_STATE, "device was created with a single rank");
+	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
+	k_composite_unpack<<<(quads + 255) / 256, 256, 0, dev->stream>>>(dev->gather, dev->resolved_color, dev->W, dev->H, dev->part.num_ranks, dev->part.stripe_h, dev->chunk_bytes / 16);
+	return check_launch(dev, "k_composite_unpack");
+}
+
+// ---- debug read-back -------------------------------------------------------------------------------
+
+static int debug_counters(mlv_device *dev, Counters *c) {
+	if(int rc = use_device(dev)) return rc;
+	if(!(dev->desc.flags & MLV_DEVICE_DEBUG_CAPTURE)) return fail(MLV_ERR_STATE, "device was created without MLV_DEVICE_DEBUG_CAPTURE");
+	CUDA_TRY(cudaMemcpyAsync(c, dev->ctr, sizeof(*c), cudaMemcpyDeviceToHost, dev->stream));
+	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	return MLV_OK;
+}
+
+int mlv_debug_read_vs_out(mlv_device *dev, float *out12_per_vertex, uint32_t *out_vertex_count) {
+	Counters c;
+	if(int rc = debug_counters(dev, &c)) return rc;
+	if(out_vertex_count) *out_vertex_count = dev->last_index_count;
+	if(out12_per_vertex && dev->last_index_count) CUDA_TRY(cudaMemcpy(out12_per_vertex, dev->dbg.vs_out, (size_t)dev->last_index_count * 48, cudaMemcpyDeviceToHost));
+	return MLV_OK;
+}
+
+int mlv_debug_read_triangles(mlv_device *dev, mlv_ref_triangle *tris, float *attributes36, uint32_t *out_count) {
+	Counters c;
+	if(int rc = debug_counters(dev, &c)) return rc;
+	if(out_count) *out_count = c.tri_count;
+	if(tris && c.tri_count) CUDA_TRY(cudaMemcpy(tris, dev->dbg.tris, (size_t)c.tri_count * sizeof(mlv_ref_triangle), cudaMemcpyDeviceToHost));
+	if(attributes36 && c.tri_count) CUDA_TRY(cudaMemcpy(attributes36, dev->dbg.attrs, (size_t)c.tri_count * 144, cudaMemcpyDeviceToHost));
+	return MLV_OK;
+}
+
+int mlv_debug_read_bins(mlv_device *dev, uint32_t *triangle_ids, uint32_t *out_pair_count, mlv_ref_compacted_bin *bins, uint32_t *out_bin_count) {
+	Counters c;
+	if(int rc = debug_counters(dev, &c)) return rc;
+	if(out_pair_count) *out_pair_count = c.pair_total;
+	if(out_bin_count) *out_bin_count = c.n_cbins;
+	if(triangle_ids && c.pair_total && c.n_cbins) CUDA_TRY(cudaMemcpy(triangle_ids, dev->pair_ids, (size_t)c.pair_total * 4, cudaMemcpyDeviceToHost));
+	if(bins && c.n_cbins) CUDA_TRY(cudaMemcpy(bins, dev->cbins, (size_t)c.n_cbins * sizeof(mlv_ref_compacted_bin), cudaMemcpyDeviceToHost));
+	return MLV_OK;
+}
+
+int mlv_debug_read_masks(mlv_device *dev, mlv_ref_tile_info *infos, uint32_t *out_pair_count) {
+	Counters c;
+	if(int rc = debug_counters(dev, &c)) return rc;
+	if(out_pair_count) *out_pair_count = c.pair_total;
+	if(infos && c.pair_total && c.n_cbins) CUDA_TRY(cudaMemcpy(infos, dev->dbg.infos, (size_t)c.pair_total * sizeof(mlv_ref_tile_info), cudaMemcpyDeviceToHost));
+	return MLV_OK;
+}
+
+int mlv_debug_read_tile_min_depths(mlv_device *dev, float *out_bins) {
+	if(int rc = use_device(dev)) return rc;
+	if(!out_bins) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	if(int rc = flush_clears(dev)) return rc;
+	CUDA_TRY(cudaMemcpyAsync(out_bins, dev->tile_min, (size_t)dev->num_bins * 4, cudaMemcpyDeviceToHost, dev->stream));
+	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	return MLV_OK;
+}
+
+uint64_t mlv_kernel_launch_count(mlv_device *dev) { return dev ? dev->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,327 @@
+"""Host-side mirror of the reference's D3D11-mimicking interface (reference source/main.c).
+
+The reference host (`render()`, main.c:1265-1299) writes the fields of a global `Pipeline
+graphics_pipeline` (main.c:71-115,222) and then calls `clear_render_target_view` (:1191),
+`clear_depth_stencil_view` (:1204) and `draw_indexed` (:1219).  `Device` keeps exactly that shape:
+`dev.graphics_pipeline.{ia,vs,rs,ps}` carry the same field names, the three entry points have the
+same names and argument meaning, and the reference's asserts surface as `MalevichError`.
+Underneath, every call goes through the C-ABI of include/malevich_b200.h; host arrays bound as
+vertex/index buffers and textures are uploaded once and cached by identity, like D3D11 resources.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+
+
+@dataclass(frozen=True)
+class VertexShader:
+    """VertexShader descriptor, common_shader_core.h:10-14 ({in_vertex_size, out_vertex_size, vs_main})."""
+    in_vertex_size: int
+    out_vertex_size: int
+    vs_main: int  # device shader id instead of a host function pointer
+
+
+@dataclass(frozen=True)
+class PixelShader:
+    """PixelShader descriptor, common_shader_core.h:16-18."""
+    ps_main: int
+
+
+# the seven descriptors the reference exports (main.c:46-52); sizes are sizeof(Vs_Input/Vs_Output) of 8-wide SoA blocks
+passthrough_vs = VertexShader(256, 384, L.VS_PASSTHROUGH)
+basic_vs = VertexShader(256, 384, L.VS_BASIC)
+vertex_lighting_vs = VertexShader(256, 384, L.VS_VERTEX_LIGHTING)
+fullscreen_vs = VertexShader(256, 384, L.VS_FULLSCREEN)
+passthrough_ps = PixelShader(L.PS_PASSTHROUGH)
+basic_ps = PixelShader(L.PS_BASIC)
+env_lighting_ps = PixelShader(L.PS_ENV_LIGHTING)
+
+VECTOR_WIDTH = 8  # main.c:26
+
+
+class Texture2D:
+    """Texture2D, common_shader_core.h:20-24. `p_data` is uint32 [h, w] (R8G8B8A8) or float32 [h, w, 4]."""
+
+    def __init__(self, p_data: np.ndarray):
+        if p_data.dtype == np.uint32 and p_data.ndim == 2:
+            self.format = L.FORMAT_R8G8B8A8_UNORM
+        elif p_data.dtype == np.float32 and p_data.ndim == 3 and p_data.shape[2] == 4:
+            self.format = L.FORMAT_R32G32B32A32_FLOAT
+        else:
+            raise ValueError("Texture2D wants uint32 [h,w] or float32 [h,w,4]")
+        self.p_data = np.ascontiguousarray(p_data)
+        self.height, self.width = int(p_data.shape[0]), int(p_data.shape[1])
+
+
+@dataclass
+class Viewport:  # main.c:85-92
+    top_left_x: float = 0.0
+    top_left_y: float = 0.0
+    width: float = 0.0
+    height: float = 0.0
+    min_depth: float = 0.0
+    max_depth: float = 1.0
+
+
+@dataclass
+class IA:  # main.c:71-76
+    p_index_buffer: Optional[np.ndarray] = None
+    p_vertex_buffer: Optional[np.ndarray] = None
+    input_layout: int = 0
+    primitive_topology: int = L.PRIMITIVE_TOPOLOGY_UNDEFINED
+
+
+@dataclass
+class VS:  # main.c:78-83
+    shader: Optional[VertexShader] = None
+    output_register_count: int = 0
+    p_constant_buffers: list = field(default_factory=lambda: [None] * 16)
+    p_shader_resource_views: list = field(default_factory=lambda: [None] * 16)
+
+
+@dataclass
+class RS:  # main.c:94-96
+    viewport: Viewport = field(default_factory=Viewport)
+
+
+@dataclass
+class PS:  # main.c:98-101
+    shader: Optional[PixelShader] = None
+    p_shader_resource_views: list = field(default_factory=lambda: [None] * 16)
+
+
+@dataclass
+class Pipeline:  # main.c:109-115 (om.p_colors / om.p_depth are owned by the device here)
+    ia: IA = field(default_factory=IA)
+    vs: VS = field(default_factory=VS)
+    rs: RS = field(default_factory=RS)
+    ps: PS = field(default_factory=PS)
+
+
+REF_TRIANGLE_DTYPE = np.dtype([("p_attributes", "<u8"), ("min_bounds", "<i4", (2,)), ("max_bounds", "<i4", (2,)),
+                               ("edges", "<i4", (3, 3)), ("reciprocal_ws", "<f4", (3,)), ("one_over_area", "<f4"),
+                               ("max_depth", "<f4")])
+REF_COMPACTED_BIN_DTYPE = np.dtype([("num_triangles_self", "<u4"), ("num_triangles_upto", "<u4"), ("bin_index", "<u4")])
+REF_TILE_INFO_DTYPE = np.dtype([("triangle_id", "<u4"), ("_pad", "<u4"), ("fragment_mask", "<u8")])
+assert REF_TRIANGLE_DTYPE.itemsize == 80 and REF_COMPACTED_BIN_DTYPE.itemsize == 12 and REF_TILE_INFO_DTYPE.itemsize == 16
+
+
+class Device:
+    """One B200 running the draw pipeline for a width x height render target."""
+
+    def __init__(self, width: int, height: int, cuda_device: int = -1, num_ranks: int = 1, rank: int = 0,
+                 stripe_height_tiles: int = 1, debug_capture: bool = False, max_pairs_per_draw: int = 0):
+        self._lib = L.load()
+        self.width, self.height = int(width), int(height)
+        self.num_ranks, self.rank, self.stripe_height_tiles = num_ranks, rank, stripe_height_tiles
+        desc = L.DeviceDesc(width=width, height=height, cuda_device=cuda_device, num_ranks=num_ranks, rank=rank,
+                            stripe_height_tiles=stripe_height_tiles, max_pairs_per_draw=max_pairs_per_draw,
+                            flags=L.DEVICE_DEBUG_CAPTURE if debug_capture else 0)
+        self._h = C.c_void_p()
+        L.check(self._lib.mlv_create_device(C.byref(desc), C.byref(self._h)))
+        self.graphics_pipeline = Pipeline()
+        self._buffers = {}   # id(array) -> (array, handle)
+        self._textures = {}  # id(Texture2D) -> (tex, handle)
+
+    # ---- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            for _, h in self._buffers.values():
+                self._lib.mlv_release_buffer(self._h, h)
+            for _, h in self._textures.values():
+                self._lib.mlv_release_texture(self._h, h)
+            self._buffers.clear()
+            self._textures.clear()
+            self._lib.mlv_destroy_device(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- resources -----------------------------------------------------------------------------
+    def _buffer(self, arr: np.ndarray, kind: int):
+        key = (id(arr), kind)
+        hit = self._buffers.get(key)
+        if hit is not None and hit[0] is arr:
+            return hit[1]
+        a = np.ascontiguousarray(arr)
+        h = C.c_void_p()
+        L.check(self._lib.mlv_create_buffer(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes, kind, C.byref(h)))
+        self._buffers[key] = (arr, h)
+        return h
+
+    def _texture(self, tex: Texture2D):
+        hit = self._textures.get(id(tex))
+        if hit is not None and hit[0] is tex:
+            return hit[1]
+        h = C.c_void_p()
+        L.check(self._lib.mlv_create_texture2d(self._h, tex.p_data.ctypes.data_as(C.c_void_p), tex.width, tex.height, tex.format, C.byref(h)))
+        self._textures[id(tex)] = (tex, h)
+        return h
+
+    def upload(self, *objs):
+        """Optional: create device copies ahead of the first draw (keeps uploads out of a timed region)."""
+        for o in objs:
+            if isinstance(o, Texture2D):
+                self._texture(o)
+            elif isinstance(o, np.ndarray):
+                self._buffer(o, L.BUFFER_INDEX if o.dtype == np.uint32 and o.ndim == 1 else L.BUFFER_VERTEX)
+
+    def invalidate(self, obj):
+        """Forget the device copy of a host array / texture whose contents changed."""
+        if isinstance(obj, Texture2D):
+            hit = self._textures.pop(id(obj), None)
+            if hit:
+                self._lib.mlv_release_texture(self._h, hit[1])
+        else:
+            for kind in (L.BUFFER_VERTEX, L.BUFFER_INDEX):
+                hit = self._buffers.pop((id(obj), kind), None)
+                if hit:
+                    self._lib.mlv_release_buffer(self._h, hit[1])
+
+    # ---- the reference's three entry points ---------------------------------------------------
+    def clear_render_target_view(self, p_clear_color):  # main.c:1191
+        c = (C.c_float * 4)(*[float(np.float32(x)) for x in p_clear_color])
+        L.check(self._lib.mlv_clear_render_target_view(self._h, c))
+
+    def clear_depth_stencil_view(self, depth: float):  # main.c:1204
+        L.check(self._lib.mlv_clear_depth_stencil_view(self._h, float(depth)))
+
+    def _bind(self, need_indices: bool):
+        gp, lib, h = self.graphics_pipeline, self._lib, self._h
+        L.check(lib.mlv_ia_set_primitive_topology(h, int(gp.ia.primitive_topology)))
+        L.check(lib.mlv_ia_set_input_layout(h, int(gp.ia.input_layout)))
+        if gp.ia.p_vertex_buffer is None:
+            raise L.MalevichError(L.MLV_ERR_STATE, "ia.p_vertex_buffer is not set")
+        L.check(lib.mlv_ia_set_vertex_buffer(h, self._buffer(gp.ia.p_vertex_buffer, L.BUFFER_VERTEX)))
+        if need_indices:
+            if gp.ia.p_index_buffer is None:
+                raise L.MalevichError(L.MLV_ERR_STATE, "ia.p_index_buffer is not set")
+            L.check(lib.mlv_ia_set_index_buffer(h, self._buffer(gp.ia.p_index_buffer, L.BUFFER_INDEX)))
+        if gp.vs.shader is None or gp.ps.shader is None:
+            raise L.MalevichError(L.MLV_ERR_STATE, "vs.shader / ps.shader is not set")
+        if gp.vs.output_register_count != 3:
+            # the reference hard-codes three registers in interpolation and VS scatter (main.c:714-727,1124-1126)
+            raise L.MalevichError(L.MLV_ERR_STATE, "vs.output_register_count must be 3")
+        L.check(lib.mlv_vs_set_shader(h, gp.vs.shader.vs_main))
+        L.check(lib.mlv_ps_set_shader(h, gp.ps.shader.ps_main))
+        for slot, cb in enumerate(gp.vs.p_constant_buffers):
+            if cb is not None:
+                a = np.ascontiguousarray(cb)
+                L.check(lib.mlv_vs_set_constant_buffer(h, slot, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        for slot in range(16):
+            t = gp.vs.p_shader_resource_views[slot]
+            L.check(lib.mlv_vs_set_shader_resource(h, slot, self._texture(t) if t is not None else None))
+            t = gp.ps.p_shader_resource_views[slot]
+            L.check(lib.mlv_ps_set_shader_resource(h, slot, self._texture(t) if t is not None else None))
+        v = gp.rs.viewport
+        vp = L.Viewport(v.top_left_x, v.top_left_y, v.width, v.height, v.min_depth, v.max_depth)
+        L.check(lib.mlv_rs_set_viewport(h, C.byref(vp)))
+
+    def draw_indexed(self, index_count: int):  # main.c:1219
+        self._bind(True)
+        L.check(self._lib.mlv_draw_indexed(self._h, int(index_count)))
+
+    def draw(self, vertex_count: int):
+        self._bind(False)
+        L.check(self._lib.mlv_draw(self._h, int(vertex_count)))
+
+    # ---- results ---------------------------------------------------------------------------------
+    def present(self, want_depth: bool = True):
+        """-> (colors uint32 [H, W], depths float32 [H, W] or None); replaces the GDI blit (main.c:286-357)."""
+        colors = np.empty((self.height, self.width), dtype=np.uint32)
+        depths = np.empty((self.height, self.width), dtype=np.float32) if want_depth else None
+        L.check(self._lib.mlv_present_readback(self._h, colors.ctypes.data_as(C.c_void_p),
+                                               depths.ctypes.data_as(C.c_void_p) if want_depth else None))
+        return colors, depths
+
+    def present_into(self, colors: np.ndarray, depths: Optional[np.ndarray] = None):
+        L.check(self._lib.mlv_present_readback(self._h, colors.ctypes.data_as(C.c_void_p),
+                                               depths.ctypes.data_as(C.c_void_p) if depths is not None else None))
+
+    def finish(self):
+        L.check(self._lib.mlv_finish(self._h))
+
+    def stats(self) -> dict:
+        s = L.Stats()
+        L.check(self._lib.mlv_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):  # memset(&stats, 0) main.c:1268
+        L.check(self._lib.mlv_reset_stats(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.mlv_get_stream(self._h) or 0)
+
+    @property
+    def kernel_launch_count(self) -> int:
+        return int(self._lib.mlv_kernel_launch_count(self._h))
+
+    def resolve(self):
+        L.check(self._lib.mlv_resolve(self._h))
+
+    def resolved_color_ptr(self) -> int:
+        return int(self._lib.mlv_resolved_color_device_ptr(self._h))
+
+    def composite_layout(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        L.check(self._lib.mlv_composite_layout(self._h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def composite_pack(self):
+        L.check(self._lib.mlv_composite_pack(self._h))
+
+    def composite_unpack(self):
+        L.check(self._lib.mlv_composite_unpack(self._h))
+
+    # ---- debug read-back of the last draw ------------------------------------------------------
+    def debug_vs_out(self) -> np.ndarray:
+        n = C.c_uint32()
+        L.check(self._lib.mlv_debug_read_vs_out(self._h, None, C.byref(n)))
+        out = np.empty((n.value, 12), dtype=np.float32)
+        L.check(self._lib.mlv_debug_read_vs_out(self._h, out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return out
+
+    def debug_triangles(self):
+        n = C.c_uint32()
+        L.check(self._lib.mlv_debug_read_triangles(self._h, None, None, C.byref(n)))
+        tris = np.empty(n.value, dtype=REF_TRIANGLE_DTYPE)
+        attrs = np.empty((n.value, 9, 4), dtype=np.float32)
+        L.check(self._lib.mlv_debug_read_triangles(self._h, tris.ctypes.data_as(C.c_void_p), attrs.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return tris, attrs
+
+    def debug_bins(self):
+        npairs, nbins = C.c_uint32(), C.c_uint32()
+        L.check(self._lib.mlv_debug_read_bins(self._h, None, C.byref(npairs), None, C.byref(nbins)))
+        ids = np.empty(npairs.value, dtype=np.uint32)
+        bins = np.empty(nbins.value, dtype=REF_COMPACTED_BIN_DTYPE)
+        L.check(self._lib.mlv_debug_read_bins(self._h, ids.ctypes.data_as(C.c_void_p), C.byref(npairs), bins.ctypes.data_as(C.c_void_p), C.byref(nbins)))
+        return ids, bins
+
+    def debug_masks(self) -> np.ndarray:
+        n = C.c_uint32()
+        L.check(self._lib.mlv_debug_read_masks(self._h, None, C.byref(n)))
+        infos = np.empty(n.value, dtype=REF_TILE_INFO_DTYPE)
+        L.check(self._lib.mlv_debug_read_masks(self._h, infos.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return infos
+
+    def debug_tile_min_depths(self) -> np.ndarray:
+        out = np.empty((self.height // 8) * (self.width // 8), dtype=np.float32)
+        L.check(self._lib.mlv_debug_read_tile_min_depths(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
