@@ -170,6 +170,15 @@ MLV_API int mlv_debug_read_bins(mlv_device *dev, uint32_t *triangle_ids, uint32_
 MLV_API int mlv_debug_read_masks(mlv_device *dev, mlv_ref_tile_info *infos, uint32_t *out_pair_count);          /* rasterizer output main.c:986-1041 */
 MLV_API int mlv_debug_read_tile_min_depths(mlv_device *dev, float *out_bins);                                    /* a_tile_min_depths main.c:230 */
 
+/* Per-stage device timing (replaces the reference's Remotery scopes, rmt_BeginCPUSample main.c:663,699,737,916,
+ * 984,1047,1192,1205): between mlv_profile_begin and mlv_profile_end every kernel launch is bracketed by CUDA events
+ * on the device's stream. mlv_profile_end synchronises and returns, per stage, the summed kernel time in
+ * milliseconds and the number of launches. Arrays have MLV_STAGE_COUNT entries. */
+enum { MLV_STAGE_CLEAR = 0, MLV_STAGE_GEOMETRY = 1, MLV_STAGE_BIN_COUNT = 2, MLV_STAGE_BIN_SCAN = 3, MLV_STAGE_BIN_FILL = 4,
+       MLV_STAGE_TILE = 5, MLV_STAGE_RESOLVE = 6, MLV_STAGE_COMPOSITE = 7, MLV_STAGE_COUNT = 8 };
+MLV_API int mlv_profile_begin(mlv_device *dev);
+MLV_API int mlv_profile_end(mlv_device *dev, double *out_ms, uint32_t *out_launches);
+
 /* how many kernels this device has launched since creation (bench.py's gpu_launches) */
 MLV_API uint64_t mlv_kernel_launch_count(mlv_device *dev);
 

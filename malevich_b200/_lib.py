@@ -19,8 +19,9 @@ EXPORTED_SYMBOLS = [
     "mlv_resolve", "mlv_resolved_color_device_ptr", "mlv_resolved_depth_device_ptr",
     "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
     "mlv_debug_read_vs_out", "mlv_debug_read_triangles", "mlv_debug_read_bins", "mlv_debug_read_masks",
-    "mlv_debug_read_tile_min_depths", "mlv_kernel_launch_count",
+    "mlv_debug_read_tile_min_depths", "mlv_profile_begin", "mlv_profile_end", "mlv_kernel_launch_count",
 ]
+STAGE_NAMES = ["clear", "geometry", "bin_count", "bin_scan", "bin_fill", "tile", "resolve", "composite"]
 
 MLV_OK = 0
 MLV_ERR_INVALID_ARGUMENT, MLV_ERR_CUDA, MLV_ERR_OUT_OF_MEMORY, MLV_ERR_CAPACITY, MLV_ERR_STATE = 1, 2, 3, 4, 5
@@ -111,6 +112,8 @@ def load() -> C.CDLL:
         "mlv_debug_read_bins": (i32, [vp, vp, P(u32), vp, P(u32)]),
         "mlv_debug_read_masks": (i32, [vp, vp, P(u32)]),
         "mlv_debug_read_tile_min_depths": (i32, [vp, vp]),
+        "mlv_profile_begin": (i32, [vp]),
+        "mlv_profile_end": (i32, [vp, P(C.c_double), P(u32)]),
         "mlv_kernel_launch_count": (C.c_uint64, [vp]),
     }
     assert sorted(sig) == sorted(EXPORTED_SYMBOLS)

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <cmath>
 #include <new>
+#include <vector>
 
 #include "kernels.cuh"
 
@@ -96,6 +97,12 @@ struct mlv_device {
 
 	uint32_t ticket_base, epoch;
 	uint64_t launches;
+
+	// per-stage profiling (mlv_profile_begin/end)
+	bool prof_on;
+	std::vector<cudaEvent_t> *prof_events; // pairs (start, end)
+	std::vector<int> *prof_stages;
+	size_t prof_used;
 };
 
 static int use_device(mlv_device *dev) {
@@ -104,10 +111,28 @@ static int use_device(mlv_device *dev) {
 	return MLV_OK;
 }
 
+// Brackets one kernel launch with CUDA events when profiling is on: prof_pre before the <<<>>>, check_launch after.
+static void prof_pre(mlv_device *dev, int stage) {
+	if(!dev->prof_on) return;
+	if(dev->prof_used + 2 > dev->prof_events->size()) {
+		for(int i = 0; i < 2; ++i) {
+			cudaEvent_t e;
+			cudaEventCreate(&e);
+			dev->prof_events->push_back(e);
+		}
+	}
+	dev->prof_stages->push_back(stage);
+	cudaEventRecord((*dev->prof_events)[dev->prof_used], dev->stream);
+}
+
 static int check_launch(mlv_device *dev, const char *what) {
 	cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return fail(MLV_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
 	dev->launches++;
+	if(dev->prof_on) {
+		cudaEventRecord((*dev->prof_events)[dev->prof_used + 1], dev->stream);
+		dev->prof_used += 2;
+	}
 	return MLV_OK;
 }
 
@@ -154,6 +179,8 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	dev->epoch = 0;
 	dev->vs_id = -1;
 	dev->ps_id = -1;
+	dev->prof_events = new std::vector<cudaEvent_t>();
+	dev->prof_stages = new std::vector<int>();
 
 #define CREATE_TRY(expr)                          \
 	do {                                          \
@@ -206,6 +233,11 @@ void mlv_destroy_device(mlv_device *dev) {
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
 	if(dev->stream) cudaStreamDestroy(dev->stream);
+	if(dev->prof_events) {
+		for(cudaEvent_t e : *dev->prof_events) cudaEventDestroy(e);
+		delete dev->prof_events;
+	}
+	delete dev->prof_stages;
 	delete dev;
 }
 
@@ -356,6 +388,7 @@ static int flush_clears(mlv_device *dev) {
 	if(!dev->pend_color && !dev->pend_depth) return MLV_OK;
 	const int mode = (dev->pend_color ? 1 : 0) | (dev->pend_depth ? 2 : 0);
 	const uint32_t n = dev->num_bins * 32u;
+	prof_pre(dev, MLV_STAGE_CLEAR);
 	k_clear<<<(n + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->tile_min, dev->num_bins, dev->clear_color, dev->clear_depth, mode);
 	dev->pend_color = dev->pend_depth = false;
 	return check_launch(dev, "k_clear");
@@ -506,6 +539,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	gp.index_count = count;
 	dev->ticket_base += nblocks;
 
+	prof_pre(dev, MLV_STAGE_GEOMETRY);
 	switch(dev->vs_id) {
 		case MLV_VS_PASSTHROUGH: launch_geom<0>(dev, gp, indexed); break;
 		case MLV_VS_BASIC: launch_geom<1>(dev, gp, indexed); break;
@@ -526,6 +560,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	bp.part = dev->part;
 	uint32_t bin_blocks = (need_tris + 255u) / 256u;
 	if(bin_blocks > 148u * 16u) bin_blocks = 148u * 16u;
+	prof_pre(dev, MLV_STAGE_BIN_COUNT);
 	k_bin<false><<<bin_blocks, 256, 0, dev->stream>>>(bp, (uint32_t)dev->pair_capacity);
 	if(int rc = check_launch(dev, "k_bin<count>")) return rc;
 
@@ -537,9 +572,11 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	sp.ctr = dev->ctr;
 	sp.num_bins = dev->num_bins;
 	sp.pair_capacity = (uint32_t)dev->pair_capacity;
+	prof_pre(dev, MLV_STAGE_BIN_SCAN);
 	k_bin_scan<<<1, 1024, 0, dev->stream>>>(sp);
 	if(int rc = check_launch(dev, "k_bin_scan")) return rc;
 
+	prof_pre(dev, MLV_STAGE_BIN_FILL);
 	k_bin<true><<<bin_blocks, 256, 0, dev->stream>>>(bp, (uint32_t)dev->pair_capacity);
 	if(int rc = check_launch(dev, "k_bin<fill>")) return rc;
 
@@ -560,6 +597,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	tp.wt = dev->wt;
 	uint32_t tile_blocks = (dev->num_bins + 7u) / 8u;
 	if(tile_blocks > 148u * 8u) tile_blocks = 148u * 8u;
+	prof_pre(dev, MLV_STAGE_TILE);
 	switch(dev->ps_id) {
 		case MLV_PS_PASSTHROUGH: k_tile<0><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp); break;
 		case MLV_PS_BASIC: k_tile<1><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp); break;
@@ -586,6 +624,7 @@ int mlv_resolve(mlv_device *dev) {
 	if(int rc = use_device(dev)) return rc;
 	if(int rc = flush_clears(dev)) return rc;
 	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
+	prof_pre(dev, MLV_STAGE_RESOLVE);
 	k_resolve<<<(quads + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->resolved_color, dev->resolved_depth, dev->W, dev->H);
 	return check_launch(dev, "k_resolve");
 }
@@ -597,6 +636,7 @@ int mlv_present_readback(mlv_device *dev, uint32_t *colors, float *depths) {
 	if(int rc = use_device(dev)) return rc;
 	if(int rc = flush_clears(dev)) return rc;
 	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
+	prof_pre(dev, MLV_STAGE_RESOLVE);
 	k_resolve<<<(quads + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->resolved_color, depths ? dev->resolved_depth : nullptr, dev->W, dev->H);
 	if(int rc = check_launch(dev, "k_resolve")) return rc;
 	const size_t bytes = (size_t)dev->W * dev->H * 4;
@@ -639,6 +679,7 @@ int mlv_composite_pack(mlv_device *dev) {
 	if(int rc = flush_clears(dev)) return rc;
 	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
 	uint4 *chunk = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(dev->gather) + dev->chunk_bytes * (size_t)dev->part.rank);
+	prof_pre(dev, MLV_STAGE_COMPOSITE);
 	k_composite_pack<<<(quads + 255) / 256, 256, 0, dev->stream>>>(dev->fb, chunk, dev->W, dev->H, dev->part);
 	return check_launch(dev, "k_composite_pack");
 }
@@ -647,6 +688,7 @@ int mlv_composite_unpack(mlv_device *dev) {
 	if(int rc = use_device(dev)) return rc;
 	if(dev->part.num_ranks <= 1) return fail(MLV_ERR_STATE, "device was created with a single rank");
 	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
+	prof_pre(dev, MLV_STAGE_COMPOSITE);
 	k_composite_unpack<<<(quads + 255) / 256, 256, 0, dev->stream>>>(dev->gather, dev->resolved_color, dev->W, dev->H, dev->part.num_ranks, dev->part.stripe_h, dev->chunk_bytes / 16);
 	return check_launch(dev, "k_composite_unpack");
 }
@@ -702,6 +744,34 @@ int mlv_debug_read_tile_min_depths(mlv_device *dev, float *out_bins) {
 	if(int rc = flush_clears(dev)) return rc;
 	CUDA_TRY(cudaMemcpyAsync(out_bins, dev->tile_min, (size_t)dev->num_bins * 4, cudaMemcpyDeviceToHost, dev->stream));
 	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	return MLV_OK;
+}
+
+int mlv_profile_begin(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	dev->prof_used = 0;
+	dev->prof_stages->clear();
+	dev->prof_on = true;
+	return MLV_OK;
+}
+
+int mlv_profile_end(mlv_device *dev, double *out_ms, uint32_t *out_launches) {
+	if(int rc = use_device(dev)) return rc;
+	if(!out_ms || !out_launches) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	dev->prof_on = false;
+	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	for(int i = 0; i < MLV_STAGE_COUNT; ++i) {
+		out_ms[i] = 0.0;
+		out_launches[i] = 0;
+	}
+	for(size_t k = 0; k < dev->prof_stages->size(); ++k) {
+		float ms = 0.f;
+		CUDA_TRY(cudaEventElapsedTime(&ms, (*dev->prof_events)[2 * k], (*dev->prof_events)[2 * k + 1]));
+		const int st = (*dev->prof_stages)[k];
+		out_ms[st] += ms;
+		out_launches[st]++;
+	}
 	return MLV_OK;
 }
 

@@ -273,6 +273,16 @@ class Device:
     def kernel_launch_count(self) -> int:
         return int(self._lib.mlv_kernel_launch_count(self._h))
 
+    def profile_begin(self):
+        L.check(self._lib.mlv_profile_begin(self._h))
+
+    def profile_end(self) -> dict:
+        """-> {stage: (milliseconds, launches)} summed since profile_begin (CUDA events on the device stream)."""
+        ms = (C.c_double * len(L.STAGE_NAMES))()
+        n = (C.c_uint32 * len(L.STAGE_NAMES))()
+        L.check(self._lib.mlv_profile_end(self._h, ms, n))
+        return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(L.STAGE_NAMES)}
+
     def resolve(self):
         L.check(self._lib.mlv_resolve(self._h))
 

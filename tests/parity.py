@@ -45,16 +45,24 @@ def assert_frames_match(gpu_colors, gpu_depths, ref_colors, ref_depths, what="")
     return r
 
 
-def compare_staged_draw(dev, oracle, vs_uses_pad=False) -> dict:
+def compare_staged_draw(dev, oracle, vs_id=1) -> dict:
     """Compares every intermediate of the LAST draw (GPU device must be in debug-capture mode, oracle
     draw must have been staged). Returns a dict of booleans/counters; everything must be True/0."""
     out = {}
-    # vertex shader output: registers 0,1 and r2.x are defined; r2.yzw is uninitialised stack in the reference
+    # vertex shader output: r0, r1 and r2.x are defined by basic_vs / vertex_lighting_vs; passthrough_vs and
+    # fullscreen_vs leave UV (r1.w, r2.x) unwritten; r2.yzw is never written (uninitialised stack in the
+    # reference, f256 vertex_output[12] main.c:711) -- undefined lanes are excluded from the comparison
+    ndef = 9 if vs_id in (1, 2) else 7
     g_vs, r_vs = dev.debug_vs_out(), oracle.staged_vs_out()
     out["vs_count"] = g_vs.shape[0] == r_vs.shape[0]
     if out["vs_count"] and g_vs.shape[0]:
-        out["vs_out_bit_exact"] = bool(np.array_equal(g_vs[:, :9].view(np.uint32), r_vs[:, :9].view(np.uint32)))
-        out["vs_out_max_abs_diff"] = float(np.nanmax(np.abs(g_vs[:, :9].astype(np.float64) - r_vs[:, :9].astype(np.float64))))
+        with np.errstate(all="ignore"):
+            out["vs_out_max_abs_diff"] = float(np.nanmax(np.abs(g_vs[:, :ndef].astype(np.float64) - r_vs[:, :ndef].astype(np.float64))))
+        if vs_id == 2:  # colour lanes 4..6 to a few ulp (see below), everything else bit-exact
+            exact = [0, 1, 2, 3, 7, 8]
+            out["vs_out_bit_exact"] = bool(np.array_equal(g_vs[:, exact].view(np.uint32), r_vs[:, exact].view(np.uint32)) and out["vs_out_max_abs_diff"] <= 4e-6)
+        else:
+            out["vs_out_bit_exact"] = bool(np.array_equal(g_vs[:, :ndef].view(np.uint32), r_vs[:, :ndef].view(np.uint32)))
     g_tris, g_attrs = dev.debug_triangles()
     r_tris, r_attrs = oracle.staged_triangles()
     out["tri_count"] = (len(g_tris), len(r_tris))
@@ -67,8 +75,18 @@ def compare_staged_draw(dev, oracle, vs_uses_pad=False) -> dict:
         ga = g_attrs.reshape(-1, 3, 3, 4).view(np.uint32)
         ra = r_attrs.reshape(-1, 3, 3, 4).view(np.uint32)
         out["attr_r0"] = bool(np.array_equal(ga[:, :, 0], ra[:, :, 0]))
-        out["attr_r1"] = bool(np.array_equal(ga[:, :, 1], ra[:, :, 1]))
-        out["attr_r2x"] = bool(np.array_equal(ga[:, :, 2, 0], ra[:, :, 2, 0]))
+        if vs_id == 2:
+            # vertex_lighting_vs computes COLOR with acos/exp/pow (Intel SVML in the reference, glibc in the oracle,
+            # CUDA libdevice here): "parity unpinned" arithmetic, compared to a few ulp; UV stays bit-exact
+            gf, rf = g_attrs.reshape(-1, 3, 3, 4), r_attrs.reshape(-1, 3, 3, 4)
+            out["attr_r1_color_max_abs_diff"] = float(np.abs(gf[:, :, 1, :3].astype(np.float64) - rf[:, :, 1, :3]).max())
+            out["attr_r1"] = bool(out["attr_r1_color_max_abs_diff"] <= 4e-6 and np.array_equal(ga[:, :, 1, 3], ra[:, :, 1, 3]))
+            out["attr_r2x"] = bool(np.array_equal(ga[:, :, 2, 0], ra[:, :, 2, 0]))
+        elif ndef == 9:
+            out["attr_r1"] = bool(np.array_equal(ga[:, :, 1], ra[:, :, 1]))
+            out["attr_r2x"] = bool(np.array_equal(ga[:, :, 2, 0], ra[:, :, 2, 0]))
+        else:
+            out["attr_r1"] = bool(np.array_equal(ga[:, :, 1, :3], ra[:, :, 1, :3]))
     g_ids, g_bins = dev.debug_bins()
     r_ids, r_bins = oracle.staged_bins()
     out["pair_count"] = (len(g_ids), len(r_ids))
@@ -119,5 +137,5 @@ def render_both_staged(dev, oracle, scene, clear=True):
         gp.ps.p_shader_resource_views[0] = o.texture
         dev.draw_indexed(o.index_count)
         oracle.draw(o.vertex_buffer, o.index_buffer, o.vertex_shader.vs_main, o.pixel_shader.ps_main, o.texture, staged=True)
-        results.append((o.name, compare_staged_draw(dev, oracle)))
+        results.append((o.name, compare_staged_draw(dev, oracle, o.vertex_shader.vs_main)))
     return results
