@@ -2,15 +2,15 @@
 //
 //   k_clear      clear_render_target_view + clear_depth_stencil_view      (reference main.c:1191-1217)
 //   k_geom<VS>   input assembler + vertex shader + primitive assembly     (main.c:662-913)
-//                fused, one thread per input triangle, ordered single-pass emission
-//                (decoupled look-back scan) so that assembled-triangle ids equal the
-//                reference's single-thread order
+//                fused, one thread per input triangle, no inter-thread dependency: triangles are named by
+//                order-preserving keys instead of compacted ids (see mlv_internal.cuh)
 //   k_bin<FILL>  binner passes 1 and 2                                    (main.c:924-962)
-//   k_bin_scan   binner exclusive scan + compaction of non-empty bins     (main.c:937-974)
+//   k_bin_scan   binner exclusive scan + compaction of non-empty bins     (main.c:937-974), multi-CTA
+//                single pass with decoupled look-back
 //   k_tile<PS>   rasterizer + Hi-Z + early-Z + pixel shader + output merger (main.c:983-1189)
-//                one warp per non-empty bin, lanes over triangles for coverage (64-bit masks),
-//                lanes over pixels for depth, pixel shader run once per pixel on the winning
-//                fragment (bit-identical to in-order shading: see DESIGN.md "deferred shading")
+//                one warp per non-empty bin: lanes over triangles for coverage (64-bit masks), a 32x32 bit
+//                transpose turns them into per-pixel cover sets, lanes over pixels for depth, pixel shader
+//                run once per pixel on the last fragment that passed (bit-identical to in-order shading)
 //   k_resolve    tiled -> row-major, 128-bit stores                       (replaces GDI blit main.c:314)
 #pragma once
 #include "mlv_internal.cuh"
@@ -50,6 +50,7 @@ struct TriSetup {
 	float max_depth;
 	float4 p[3];  // screen-space positions written over register 0 (main.c:881-883)
 	int minx, miny, maxx, maxy;
+	bool nowrap;  // every edge-function evaluation on this render target is free of i32 wrap-around
 };
 
 // set_edge_function (main.c:563-575), wrapping i32 arithmetic
@@ -112,6 +113,19 @@ __device__ __forceinline__ bool setup_triangle(const float4 &c0, const float4 &c
 	S.miny = min(max(mny, 0), P.vp_h - 1);
 	S.maxx = min(mxx + 1, P.vp_w - 1);
 	S.maxy = min(mxy + 1, P.vp_h - 1);
+	// No-wrap proof: with |x_i|,|y_i| <= M and sample coordinates in [0, 16W] x [0, 16H], every term of
+	// a*(16x) + b*(16y) + c (c = -a*x_i - b*y_i) is bounded by (|a|+|b|) * max(M, 16W, 16H); if twice that stays
+	// below 2^31 no intermediate wraps and the integer edge functions equal the exact ones, so coverage is
+	// confined to the (closed) triangle and hence to [min_bounds, max_bounds].
+	{
+		long long m = max(max(abs((long long)x0), abs((long long)x1)), abs((long long)x2));
+		m = max(m, max(max(abs((long long)y0), abs((long long)y1)), abs((long long)y2)));
+		m = max(m, (long long)max(P.vp_w, P.vp_h) * 16 + 16);
+		long long ab = 0;
+#pragma unroll
+		for(int k = 0; k < 3; ++k) ab = max(ab, abs((long long)S.e[k * 3]) + abs((long long)S.e[k * 3 + 1]));
+		S.nowrap = (m < (1ll << 24)) && (2 * ab * m < (1ll << 31));
+	}
 	return true;
 }
 
@@ -146,218 +160,181 @@ __device__ __noinline__ int clip_by_plane(VsOut *v, int n, float4 pn) {
 	return nout;
 }
 
-// clipper (main.c:649-660): six planes with host-normalised normals
-__device__ __noinline__ int clip_polygon(VsOut *v, float k) {
-	int n = 3;
-	n = clip_by_plane(v, n, make_float4(k, 0.0f, 0.0f, k));
-	n = clip_by_plane(v, n, make_float4(-k, 0.0f, 0.0f, k));
-	n = clip_by_plane(v, n, make_float4(0.0f, k, 0.0f, k));
-	n = clip_by_plane(v, n, make_float4(0.0f, -k, 0.0f, k));
-	n = clip_by_plane(v, n, make_float4(0.0f, 0.0f, k, k));
-	n = clip_by_plane(v, n, make_float4(0.0f, 0.0f, -k, k));
-	return n;
+__device__ __forceinline__ uint2 pack_bounds(const TriSetup &S) {
+	return make_uint2((uint32_t)(S.minx & 0xffff) | ((uint32_t)(S.miny & 0x7fff) << 16) | (S.nowrap ? MLV_NOWRAP_BIT : 0u),
+	                  (uint32_t)(S.maxx & 0xffff) | ((uint32_t)(S.maxy & 0xffff) << 16));
 }
 
-__device__ __forceinline__ void emit_triangle(const GeomParams &P, uint32_t id, const TriSetup &S, const VsOut &v0, const VsOut &v1, const VsOut &v2) {
-	if(id >= P.tri_capacity) return;
-	// tile rectangle exactly as the binner derives it (main.c:927-928), C division truncating toward zero
-	int tx0 = max(S.minx / 8, 0), ty0 = max(S.miny / 8, 0);
-	int tx1 = min(S.maxx / 8, P.wt - 1), ty1 = min(S.maxy / 8, P.ht - 1);
-	bool owned = false;
-	if(tx0 <= tx1)
-		for(int ty = ty0; ty <= ty1 && !owned; ++ty) owned = P.part.owns_row(ty);
-	if(!owned) { // bins nothing on this rank
-		tx0 = 1;
-		tx1 = 0;
-	}
-	P.tri_bounds[id] = make_uint2((uint32_t)(tx0 & 0xffff) | ((uint32_t)(ty0 & 0xffff) << 16), (uint32_t)(tx1 & 0xffff) | ((uint32_t)(ty1 & 0xffff) << 16));
+// Does the tile rectangle the binner derives from the bounds (main.c:927-928) touch a tile row this rank owns?
+__device__ __forceinline__ bool bins_on_this_rank(const TriSetup &S, const GeomParams &P) {
+	const int tx0 = max(S.minx / 8, 0), ty0 = max(S.miny / 8, 0);
+	const int tx1 = min(S.maxx / 8, P.wt - 1), ty1 = min(S.maxy / 8, P.ht - 1);
+	if(tx0 > tx1) return false;
+	for(int ty = ty0; ty <= ty1; ++ty)
+		if(P.part.owns_row(ty)) return true;
+	return false;
+}
+
+__device__ __forceinline__ void emit_triangle(const GeomParams &P, uint32_t slot, uint32_t key, const TriSetup &S, const float4 &r1a, const float4 &r1b, const float4 &r1c,
+                                              float r2a, float r2b, float r2c) {
+	const bool owned = bins_on_this_rank(S, P);
+	const uint2 pb = pack_bounds(S);
+	P.tri_bounds[slot] = owned ? pb : make_uint2(MLV_BOUNDS_EMPTY, 0u);
 	if(owned) {
-		uint4 *cov = P.tri_cov + (size_t)id * MLV_TRI_COV_U4;
+		uint4 *cov = P.tri_cov + (size_t)slot * MLV_TRI_COV_U4;
 		cov[0] = make_uint4(S.e[0], S.e[1], S.e[2], S.e[3]);
 		cov[1] = make_uint4(S.e[4], S.e[5], S.e[6], S.e[7]);
-		cov[2] = make_uint4(S.e[8], __float_as_uint(S.max_depth), (uint32_t)(tx0 & 0xffff) | ((uint32_t)(ty0 & 0xffff) << 16),
-		                    (uint32_t)(tx1 & 0xffff) | ((uint32_t)(ty1 & 0xffff) << 16));
-		float4 *sh = reinterpret_cast<float4 *>(P.tri_shade + (size_t)id * MLV_TRI_SHADE_U4);
+		cov[2] = make_uint4(S.e[8], __float_as_uint(S.max_depth), pb.x, pb.y);
+		float4 *sh = reinterpret_cast<float4 *>(P.tri_shade + (size_t)slot * MLV_TRI_SHADE_U4);
 		sh[0] = make_float4(S.ooa, S.p[0].z, S.p[1].z, S.p[2].z);
-		sh[1] = make_float4(S.rw[0], S.rw[1], S.rw[2], v0.r2x);
-		sh[2] = v0.r1;
-		sh[3] = v1.r1;
-		sh[4] = v2.r1;
-		sh[5] = make_float4(v1.r2x, v2.r2x, 0.0f, 0.0f);
+		sh[1] = make_float4(S.rw[0], S.rw[1], S.rw[2], r2a);
+		sh[2] = r1a;
+		sh[3] = r1b;
+		sh[4] = r1c;
+		sh[5] = make_float4(r2b, r2c, 0.0f, 0.0f);
 	}
-	if(P.dbg.tris) {
+	if(P.dbg.tris) { // reference-layout copies for mlv_debug_read_triangles
 		mlv_ref_triangle t;
-		t.p_attributes = (uint64_t)id * 144ull;
+		t.p_attributes = 0;
 		t.min_bounds[0] = S.minx;
 		t.min_bounds[1] = S.miny;
 		t.max_bounds[0] = S.maxx;
 		t.max_bounds[1] = S.maxy;
-		for(int k = 0; k < 3; ++k)
-			for(int j = 0; j < 3; ++j) t.edges[k][j] = S.e[k * 3 + j];
+#pragma unroll
+		for(int k = 0; k < 3; ++k) {
+			t.edges[k][0] = S.e[k * 3 + 0];
+			t.edges[k][1] = S.e[k * 3 + 1];
+			t.edges[k][2] = S.e[k * 3 + 2];
+		}
 		t.reciprocal_ws[0] = S.rw[0];
 		t.reciprocal_ws[1] = S.rw[1];
 		t.reciprocal_ws[2] = S.rw[2];
 		t.one_over_area = S.ooa;
 		t.max_depth = S.max_depth;
-		P.dbg.tris[id] = t;
-		float4 *a = reinterpret_cast<float4 *>(P.dbg.attrs + (size_t)id * 36);
-		const VsOut *vv[3] = { &v0, &v1, &v2 };
-		for(int k = 0; k < 3; ++k) {
-			a[k * 3 + 0] = S.p[k];
-			a[k * 3 + 1] = vv[k]->r1;
-			a[k * 3 + 2] = make_float4(vv[k]->r2x, 0.0f, 0.0f, 0.0f);
-		}
+		P.dbg.tris[slot] = t;
+		float4 *a = reinterpret_cast<float4 *>(P.dbg.attrs + (size_t)slot * 36);
+		a[0] = S.p[0];
+		a[1] = r1a;
+		a[2] = make_float4(r2a, 0.0f, 0.0f, 0.0f);
+		a[3] = S.p[1];
+		a[4] = r1b;
+		a[5] = make_float4(r2b, 0.0f, 0.0f, 0.0f);
+		a[6] = S.p[2];
+		a[7] = r1c;
+		a[8] = make_float4(r2c, 0.0f, 0.0f, 0.0f);
+		P.dbg.slot_key[slot] = key;
 	}
 }
 
-#define MLV_GEOM_THREADS 256
-#define MLV_SCAN_INVALID 0ull
-#define MLV_SCAN_AGGREGATE 1ull
-#define MLV_SCAN_PREFIX 2ull
-
-__device__ __forceinline__ unsigned long long scan_pack(uint32_t epoch, unsigned long long flag, uint32_t value) {
-	return ((unsigned long long)epoch << 34) | (flag << 32) | (unsigned long long)value;
+// Slow path: clipper (main.c:649-660) + fan triangulation (main.c:797). The fan triangles take consecutive
+// overflow slots; slot t becomes a redirect to them. Returns the number of assembled triangles.
+__device__ __noinline__ uint32_t clip_and_emit(const GeomParams &P, uint32_t t, const VsOut &v0, const VsOut &v1, const VsOut &v2) {
+	VsOut poly[16];
+	poly[0] = v0;
+	poly[1] = v1;
+	poly[2] = v2;
+	const float k = P.clip_k;
+	int n = 3;
+	n = clip_by_plane(poly, n, make_float4(k, 0.0f, 0.0f, k));
+	n = clip_by_plane(poly, n, make_float4(-k, 0.0f, 0.0f, k));
+	n = clip_by_plane(poly, n, make_float4(0.0f, k, 0.0f, k));
+	n = clip_by_plane(poly, n, make_float4(0.0f, -k, 0.0f, k));
+	n = clip_by_plane(poly, n, make_float4(0.0f, 0.0f, k, k));
+	n = clip_by_plane(poly, n, make_float4(0.0f, 0.0f, -k, k));
+	const int fan = n - 2;
+	if(fan <= 0) return 0u;
+	if(fan > 8) { // cannot happen for a convex clip of a triangle by six planes (<= 9 vertices)
+		atomicOr(&P.ctr->error_flags, MLV_FLAG_TRI_OVERFLOW);
+		return 0u;
+	}
+	const uint32_t base = atomicAdd(&P.ctr->ovf_count, (uint32_t)fan);
+	if(base + (uint32_t)fan > P.ovf_capacity) {
+		atomicOr(&P.ctr->error_flags, MLV_FLAG_TRI_OVERFLOW);
+		return 0u;
+	}
+	P.tri_cov[(size_t)t * MLV_TRI_COV_U4 + 2] = make_uint4(base, 0u, MLV_REDIRECT, 0u);
+	uint32_t emitted = 0;
+	for(int j = 0; j < fan; ++j) {
+		const uint32_t slot = P.tri_count + base + (uint32_t)j;
+		const uint32_t key = (t << 3) | (uint32_t)j;
+		P.ovf_key[base + j] = key;
+		TriSetup S;
+		if(setup_triangle(poly[0].r0, poly[j + 1].r0, poly[j + 2].r0, P, S)) {
+			emit_triangle(P, slot, key, S, poly[0].r1, poly[j + 1].r1, poly[j + 2].r1, poly[0].r2x, poly[j + 1].r2x, poly[j + 2].r2x);
+			++emitted;
+		} else {
+			P.tri_bounds[slot] = make_uint2(MLV_BOUNDS_EMPTY, 0u);
+			if(P.dbg.slot_key) P.dbg.slot_key[slot] = 0xffffffffu;
+		}
+	}
+	return emitted;
 }
+
+#define MLV_GEOM_THREADS 256
 
 template <int VS, bool INDEXED>
 __global__ void __launch_bounds__(MLV_GEOM_THREADS) k_geom(const GeomParams P) {
-	__shared__ uint32_t s_tile;
-	__shared__ uint32_t s_warp_sums[MLV_GEOM_THREADS / 32];
-	__shared__ uint32_t s_block_exclusive;
-
-	// Blocks take their logical position from a ticket so that every predecessor a block may wait on in
-	// the look-back below has already started (forward progress without relying on blockIdx order).
-	if(threadIdx.x == 0) s_tile = atomicAdd(&P.ctr->ticket, 1u) - P.ticket_base;
-	__syncthreads();
-	const uint32_t tile = s_tile;
-	const uint32_t t = tile * MLV_GEOM_THREADS + threadIdx.x;
-
-	VsOut v[3];
-	TriSetup S;
-	VsOut poly[16];
-	int n_poly = 0;
-	uint32_t survivors = 0; // bit k: fan triangle (0,k+1,k+2) survives; bit 0 for the unclipped case
-	bool clipped = false;
-
+	const uint32_t t = blockIdx.x * MLV_GEOM_THREADS + threadIdx.x;
+	uint32_t emitted = 0;
 	if(t < P.tri_count) {
 		// ---- input assembler (main.c:662-696): index fetch + 32-byte vertex fetch as two 128-bit loads
-#pragma unroll
-		for(int c = 0; c < 3; ++c) {
-			const uint32_t vi = INDEXED ? __ldg(P.ib + 3u * t + c) : (3u * t + c);
-			const float4 in0 = __ldg(P.vb + 2 * (size_t)vi);
-			const float4 in1 = __ldg(P.vb + 2 * (size_t)vi + 1);
-			// ---- vertex shader (main.c:698-734)
-			v[c] = run_vs<VS>(in0, in1, P.cb, P.vs_tex, P.rsqrt_lut);
-			if(P.dbg.vs_out) {
-				float4 *o = reinterpret_cast<float4 *>(P.dbg.vs_out + (size_t)(3u * t + c) * 12);
-				o[0] = v[c].r0;
-				o[1] = v[c].r1;
-				o[2] = make_float4(v[c].r2x, 0.0f, 0.0f, 0.0f);
-			}
+		uint32_t vi0, vi1, vi2;
+		if(INDEXED) {
+			vi0 = __ldg(P.ib + 3u * t);
+			vi1 = __ldg(P.ib + 3u * t + 1u);
+			vi2 = __ldg(P.ib + 3u * t + 2u);
+		} else {
+			vi0 = 3u * t;
+			vi1 = vi0 + 1u;
+			vi2 = vi0 + 2u;
+		}
+		const float4 a0 = __ldg(P.vb + 2 * (size_t)vi0), a1 = __ldg(P.vb + 2 * (size_t)vi0 + 1);
+		const float4 b0 = __ldg(P.vb + 2 * (size_t)vi1), b1 = __ldg(P.vb + 2 * (size_t)vi1 + 1);
+		const float4 c0 = __ldg(P.vb + 2 * (size_t)vi2), c1 = __ldg(P.vb + 2 * (size_t)vi2 + 1);
+		// ---- vertex shader (main.c:698-734)
+		const VsOut v0 = run_vs<VS>(a0, a1, P.cb, P.vs_tex, P.rsqrt_lut);
+		const VsOut v1 = run_vs<VS>(b0, b1, P.cb, P.vs_tex, P.rsqrt_lut);
+		const VsOut v2 = run_vs<VS>(c0, c1, P.cb, P.vs_tex, P.rsqrt_lut);
+		if(P.dbg.vs_out) {
+			float4 *o = reinterpret_cast<float4 *>(P.dbg.vs_out + (size_t)(3u * t) * 12);
+			o[0] = v0.r0, o[1] = v0.r1, o[2] = make_float4(v0.r2x, 0.0f, 0.0f, 0.0f);
+			o[3] = v1.r0, o[4] = v1.r1, o[5] = make_float4(v1.r2x, 0.0f, 0.0f, 0.0f);
+			o[6] = v2.r0, o[7] = v2.r1, o[8] = make_float4(v2.r2x, 0.0f, 0.0f, 0.0f);
 		}
 		// ---- primitive assembly (main.c:750-908)
-		const float4 a = v[0].r0, b = v[1].r0, c = v[2].r0;
+		const float4 a = v0.r0, b = v1.r0, c = v2.r0;
 		const bool degenerate = (a.w == 0.0f || b.w == 0.0f || c.w == 0.0f); // main.c:759
 		const bool rejected =                                                // main.c:764-772
 		    (a.x < -a.w && b.x < -b.w && c.x < -c.w) || (a.x > a.w && b.x > b.w && c.x > c.w) || (a.y < -a.w && b.y < -b.w && c.y < -c.w) ||
 		    (a.y > a.w && b.y > b.w && c.y > c.w) || (a.z < 0.0f && b.z < 0.0f && c.z < 0.0f) || (a.z > a.w && b.z > b.w && c.z > c.w);
+		bool direct = false;
 		if(!degenerate && !rejected) {
 			const bool inside = // main.c:775-781
 			    (a.x >= -a.w && b.x >= -b.w && c.x >= -c.w) && (a.x <= a.w && b.x <= b.w && c.x <= c.w) && (a.y >= -a.w && b.y >= -b.w && c.y >= -c.w) &&
 			    (a.y <= a.w && b.y <= b.w && c.y <= c.w) && (a.z >= 0.0f && b.z >= 0.0f && c.z >= 0.0f) && (a.z <= a.w && b.z <= b.w && c.z <= c.w);
 			if(inside) {
-				survivors = setup_triangle(a, b, c, P, S) ? 1u : 0u;
+				TriSetup S;
+				if(setup_triangle(a, b, c, P, S)) {
+					emit_triangle(P, t, t << 3, S, v0.r1, v1.r1, v2.r1, v0.r2x, v1.r2x, v2.r2x);
+					direct = true;
+					emitted = 1u;
+				}
 			} else {
-				clipped = true;
-				poly[0] = v[0];
-				poly[1] = v[1];
-				poly[2] = v[2];
-				n_poly = clip_polygon(poly, P.clip_k);
-				for(int k = 1; k < n_poly - 1; ++k) { // fan (main.c:797-800); count the survivors now, emit them below
-					TriSetup tmp;
-					if(setup_triangle(poly[0].r0, poly[k].r0, poly[k + 1].r0, P, tmp)) survivors |= 1u << (k - 1);
-				}
+				emitted = clip_and_emit(P, t, v0, v1, v2);
 			}
+		}
+		if(!direct) {
+			P.tri_bounds[t] = make_uint2(MLV_BOUNDS_EMPTY, 0u);
+			if(P.dbg.slot_key) P.dbg.slot_key[t] = 0xffffffffu;
 		}
 	}
-
-	// ---- ordered output slots: block scan + decoupled look-back over blocks
-	const uint32_t n_out = __popc(survivors);
-	uint32_t incl = n_out;
+	// ---- stats (main.c:1228-1238): one atomic per warp
 #pragma unroll
-	for(int d = 1; d < 32; d <<= 1) {
-		const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-		if(lane_id() >= (uint32_t)d) incl += o;
-	}
-	const uint32_t warp = threadIdx.x >> 5;
-	if(lane_id() == 31) s_warp_sums[warp] = incl;
-	__syncthreads();
-	if(warp == 0) {
-		uint32_t ws = (lane_id() < MLV_GEOM_THREADS / 32) ? s_warp_sums[lane_id()] : 0u;
-		uint32_t wincl = ws;
-#pragma unroll
-		for(int d = 1; d < 32; d <<= 1) {
-			const uint32_t o = __shfl_up_sync(0xffffffffu, wincl, d);
-			if(lane_id() >= (uint32_t)d) wincl += o;
-		}
-		const uint32_t block_total = __shfl_sync(0xffffffffu, wincl, MLV_GEOM_THREADS / 32 - 1);
-		if(lane_id() < MLV_GEOM_THREADS / 32) s_warp_sums[lane_id()] = wincl - ws; // exclusive per warp
-
-		volatile unsigned long long *state = P.scan_state;
-		if(lane_id() == 0) state[tile] = scan_pack(P.epoch, tile == 0 ? MLV_SCAN_PREFIX : MLV_SCAN_AGGREGATE, block_total);
-		uint32_t exclusive = 0;
-		if(tile > 0) {
-			int look = (int)tile - 1;
-			while(true) {
-				const int idx = look - (int)lane_id();
-				unsigned long long s;
-				bool ready;
-				do { // spin until the whole window has been published for this draw
-					s = (idx >= 0) ? state[idx] : scan_pack(P.epoch, MLV_SCAN_PREFIX, 0u);
-					ready = ((uint32_t)(s >> 34) == P.epoch) && (((s >> 32) & 3ull) != MLV_SCAN_INVALID);
-				} while(!__all_sync(0xffffffffu, ready));
-				const bool is_prefix = ((s >> 32) & 3ull) == MLV_SCAN_PREFIX;
-				const uint32_t pmask = __ballot_sync(0xffffffffu, is_prefix);
-				uint32_t val = (uint32_t)s;
-				if(pmask) {
-					const int first = __ffs(pmask) - 1;
-					if((int)lane_id() > first) val = 0u;
-				}
-#pragma unroll
-				for(int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-				exclusive += val;
-				if(pmask) break;
-				look -= 32;
-			}
-			if(lane_id() == 0) state[tile] = scan_pack(P.epoch, MLV_SCAN_PREFIX, exclusive + block_total);
-		}
-		if(lane_id() == 0) {
-			s_block_exclusive = exclusive;
-			if(tile == P.num_blocks - 1) { // stats (main.c:1228-1238) and the triangle count the later stages read
-				const uint32_t total = exclusive + block_total;
-				P.ctr->tri_count = min(total, P.tri_capacity);
-				if(total > P.tri_capacity) atomicOr(&P.ctr->error_flags, MLV_FLAG_TRI_OVERFLOW);
-				P.ctr->stats.vertex_count += P.index_count;
-				P.ctr->stats.input_triangle_count += P.tri_count;
-				P.ctr->stats.assembled_triangle_count += total;
-			}
-		}
-	}
-	__syncthreads();
-
-	// ---- emission in reference order: input order, fan order inside a clipped triangle
-	if(n_out) {
-		uint32_t id = s_block_exclusive + s_warp_sums[warp] + (incl - n_out);
-		if(!clipped) {
-			emit_triangle(P, id, S, v[0], v[1], v[2]);
-		} else {
-			for(int k = 1; k < n_poly - 1; ++k) {
-				if(!(survivors & (1u << (k - 1)))) continue;
-				TriSetup tmp;
-				setup_triangle(poly[0].r0, poly[k].r0, poly[k + 1].r0, P, tmp);
-				emit_triangle(P, id++, tmp, poly[0], poly[k], poly[k + 1]);
-			}
-		}
+	for(int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
+	if(lane_id() == 0 && emitted) atomicAdd(&P.ctr->draw_tris, emitted);
+	if(t == 0) {
+		P.ctr->stats.vertex_count += P.index_count;
+		P.ctr->stats.input_triangle_count += P.tri_count;
 	}
 }
 
@@ -365,26 +342,35 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS) k_geom(const GeomParams P) {
 // binner
 // =================================================================================================
 
-// Passes 1 (count) and 2 (fill) of the reference binner (main.c:924-962). One lane per assembled
-// triangle; triangles overlapping more than 8 tiles are expanded cooperatively by the whole warp.
-// The fill pass takes slots by decrementing the counters the count pass built (they are back to zero
-// for the next draw when it finishes); the per-bin order this leaves is arbitrary and is restored to
-// ascending triangle id by k_tile before use.
+// Passes 1 (count) and 2 (fill) of the reference binner (main.c:924-962). One lane per triangle slot;
+// triangles overlapping more than 8 tiles are expanded cooperatively by the whole warp. The fill pass takes
+// list positions by decrementing the counters the count pass built (so they are back to zero for the next draw
+// when it finishes); the per-bin order this leaves is arbitrary and is restored to ascending key (= the
+// reference's ascending triangle id) by k_tile before use.
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_bin(const BinParams P, uint32_t pair_capacity) {
-	const uint32_t n = P.ctr->tri_count;
-	if(FILL && P.ctr->pair_total > pair_capacity) return;
+	const uint32_t n = P.direct_slots + P.ctr->ovf_count;
+	if(FILL && P.ctr->pair_total > pair_capacity) { // skipped draw: drain the counters the count pass built
+		for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.num_bins; i += gridDim.x * blockDim.x) P.bin_count[i] = 0u;
+		return;
+	}
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	for(uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < n; base += warps * 32u) {
-		const uint32_t id = base + lane;
+		const uint32_t slot = base + lane;
 		int tx0 = 1, ty0 = 0, tx1 = 0, ty1 = -1;
-		if(id < n) {
-			const uint2 b = __ldg(P.tri_bounds + id);
-			tx0 = (int)(short)(b.x & 0xffffu);
-			ty0 = (int)(short)(b.x >> 16);
-			tx1 = (int)(short)(b.y & 0xffffu);
-			ty1 = (int)(short)(b.y >> 16);
+		uint32_t key = 0;
+		if(slot < n) {
+			const uint2 b = __ldg(P.tri_bounds + slot);
+			if((b.x & 0xffffu) != MLV_BOUNDS_EMPTY) { // tile rectangle as the binner derives it (main.c:927-928), C division
+				const int minx = (int)(b.x & 0xffffu), miny = (int)((b.x >> 16) & 0x7fffu);
+				const int maxx = (int)(short)(b.y & 0xffffu), maxy = (int)(short)(b.y >> 16);
+				tx0 = max(minx / 8, 0);
+				ty0 = max(miny / 8, 0);
+				tx1 = min(maxx / 8, P.wt - 1);
+				ty1 = min(maxy / 8, P.ht - 1);
+			}
+			if(FILL) key = (slot < P.direct_slots) ? (slot << 3) : __ldg(P.ovf_key + (slot - P.direct_slots));
 		}
 		const int w = max(tx1 - tx0 + 1, 0), h = max(ty1 - ty0 + 1, 0);
 		const int cnt = w * h;
@@ -396,7 +382,7 @@ __global__ void __launch_bounds__(256) k_bin(const BinParams P, uint32_t pair_ca
 					const uint32_t bin = (uint32_t)(ty * P.wt + tx);
 					if(FILL) {
 						const uint32_t old = atomicSub(P.bin_count + bin, 1u);
-						P.pair_ids[P.bin_offset[bin] + old - 1u] = id;
+						P.pair_ids[P.bin_offset[bin] + old - 1u] = key;
 					} else {
 						atomicAdd(P.bin_count + bin, 1u);
 					}
@@ -409,14 +395,14 @@ __global__ void __launch_bounds__(256) k_bin(const BinParams P, uint32_t pair_ca
 			bigmask &= bigmask - 1;
 			const int bx0 = __shfl_sync(0xffffffffu, tx0, src), by0 = __shfl_sync(0xffffffffu, ty0, src);
 			const int bw = __shfl_sync(0xffffffffu, w, src), bc = __shfl_sync(0xffffffffu, cnt, src);
-			const uint32_t bid = base + (uint32_t)src;
+			const uint32_t bkey = __shfl_sync(0xffffffffu, key, src);
 			for(int k = (int)lane; k < bc; k += 32) {
 				const int ty = by0 + k / bw, tx = bx0 + k % bw;
 				if(!P.part.owns_row(ty)) continue;
 				const uint32_t bin = (uint32_t)(ty * P.wt + tx);
 				if(FILL) {
 					const uint32_t old = atomicSub(P.bin_count + bin, 1u);
-					P.pair_ids[P.bin_offset[bin] + old - 1u] = bid;
+					P.pair_ids[P.bin_offset[bin] + old - 1u] = bkey;
 				} else {
 					atomicAdd(P.bin_count + bin, 1u);
 				}
@@ -425,72 +411,110 @@ __global__ void __launch_bounds__(256) k_bin(const BinParams P, uint32_t pair_ca
 	}
 }
 
-// Exclusive scan of the per-bin counts + compaction of non-empty bins in ascending bin index
-// (main.c:937-974), stats (main.c:1245-1246). Single CTA of 1024 threads; warp w owns a contiguous
-// range of bins and walks it with coalesced 32-wide reads.
-__global__ void __launch_bounds__(1024) k_bin_scan(const ScanParams P) {
-	__shared__ uint32_t s_sum[32], s_nz[32];
-	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-	const uint32_t per_warp = ((P.num_bins + 32u * 32u - 1u) / (32u * 32u)) * 32u;
-	const uint32_t begin = warp * per_warp, end = min(begin + per_warp, P.num_bins);
-	uint32_t sum = 0, nz = 0;
-	for(uint32_t i = begin + lane; i < end; i += 32u) {
-		const uint32_t c = P.bin_count[i];
-		sum += c;
-		nz += (c != 0u);
-	}
+// ---- decoupled look-back over CTAs (single-pass prefix sum) ---------------------------------------
+#define MLV_SCAN_INVALID 0ull
+#define MLV_SCAN_AGGREGATE 1ull
+#define MLV_SCAN_PREFIX 2ull
+
+__device__ __forceinline__ unsigned long long scan_pack(uint32_t epoch, unsigned long long flag, uint32_t value) {
+	return ((unsigned long long)epoch << 34) | (flag << 32) | (unsigned long long)value;
+}
+
+// Executed by one full warp of CTA `tile`: publishes the CTA aggregate, returns the exclusive prefix over all
+// earlier CTAs. State words carry the draw epoch, so the array never needs clearing between draws.
+__device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long long *state, uint32_t tile, uint32_t epoch, uint32_t block_total) {
+	const uint32_t lane = lane_id();
+	if(lane == 0) state[tile] = scan_pack(epoch, tile == 0 ? MLV_SCAN_PREFIX : MLV_SCAN_AGGREGATE, block_total);
+	uint32_t exclusive = 0;
+	if(tile > 0) {
+		int look = (int)tile - 1;
+		while(true) {
+			const int idx = look - (int)lane;
+			unsigned long long s;
+			bool ready;
+			do { // spin until the whole window has been published for this draw
+				s = (idx >= 0) ? state[idx] : scan_pack(epoch, MLV_SCAN_PREFIX, 0u);
+				ready = ((uint32_t)(s >> 34) == epoch) && (((s >> 32) & 3ull) != MLV_SCAN_INVALID);
+			} while(!__all_sync(0xffffffffu, ready));
+			const bool is_prefix = ((s >> 32) & 3ull) == MLV_SCAN_PREFIX;
+			const uint32_t pmask = __ballot_sync(0xffffffffu, is_prefix);
+			uint32_t val = (uint32_t)s;
+			if(pmask) {
+				const int first = __ffs(pmask) - 1;
+				if((int)lane > first) val = 0u;
+			}
 #pragma unroll
-	for(int d = 16; d > 0; d >>= 1) {
-		sum += __shfl_xor_sync(0xffffffffu, sum, d);
-		nz += __shfl_xor_sync(0xffffffffu, nz, d);
-	}
-	if(lane == 0) {
-		s_sum[warp] = sum;
-		s_nz[warp] = nz;
-	}
-	__syncthreads();
-	uint32_t run_sum = 0, run_nz = 0, tot_sum = 0, tot_nz = 0;
-	for(uint32_t w2 = 0; w2 < 32u; ++w2) {
-		if(w2 < warp) {
-			run_sum += s_sum[w2];
-			run_nz += s_nz[w2];
+			for(int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+			exclusive += val;
+			if(pmask) break;
+			look -= 32;
 		}
-		tot_sum += s_sum[w2];
-		tot_nz += s_nz[w2];
+		if(lane == 0) state[tile] = scan_pack(epoch, MLV_SCAN_PREFIX, exclusive + block_total);
 	}
-	const bool overflow = tot_sum > P.pair_capacity;
-	for(uint32_t i0 = begin; i0 < end; i0 += 32u) {
-		const uint32_t i = i0 + lane;
-		const uint32_t c = (i < end) ? P.bin_count[i] : 0u;
-		uint32_t incl = c;
+	return exclusive;
+}
+
+// Exclusive scan of the per-bin counts + compaction of non-empty bins in ascending bin index
+// (main.c:937-974), stats (main.c:1245-1246). One bin per thread, 1024 bins per CTA; warp 0 resolves the
+// triangle-count prefix and warp 1 the non-empty-bin prefix concurrently.
+#define MLV_SCAN_THREADS 1024
+__global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const ScanParams P) {
+	__shared__ uint32_t s_tile;
+	__shared__ uint32_t s_sum[32], s_nz[32];
+	__shared__ uint32_t s_excl[2];
+	// CTAs take their logical position from a ticket so that every predecessor a CTA may wait on has started
+	if(threadIdx.x == 0) s_tile = atomicAdd(&P.ctr->ticket, 1u) - P.ticket_base;
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+	const uint32_t i = tile * MLV_SCAN_THREADS + threadIdx.x;
+	const uint32_t c = (i < P.num_bins) ? P.bin_count[i] : 0u;
+	uint32_t incl = c;
+#pragma unroll
+	for(int d = 1; d < 32; d <<= 1) {
+		const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+		if(lane >= (uint32_t)d) incl += o;
+	}
+	const uint32_t nzmask = __ballot_sync(0xffffffffu, c != 0u);
+	if(lane == 31) s_sum[warp] = incl;
+	if(lane == 0) s_nz[warp] = __popc(nzmask);
+	__syncthreads();
+	if(warp < 2) {
+		const uint32_t v = (warp == 0) ? s_sum[lane] : s_nz[lane];
+		uint32_t wincl = v;
 #pragma unroll
 		for(int d = 1; d < 32; d <<= 1) {
-			const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-			if(lane >= (uint32_t)d) incl += o;
+			const uint32_t o = __shfl_up_sync(0xffffffffu, wincl, d);
+			if(lane >= (uint32_t)d) wincl += o;
 		}
-		const uint32_t nzmask = __ballot_sync(0xffffffffu, c != 0u);
-		if(i < end) {
-			const uint32_t upto = run_sum + incl - c;
-			P.bin_offset[i] = upto;
-			if(c != 0u && !overflow) {
-				mlv_ref_compacted_bin cb;
-				cb.num_triangles_self = c;
-				cb.num_triangles_upto = upto;
-				cb.bin_index = i;
-				P.cbins[run_nz + __popc(nzmask & ((1u << lane) - 1u))] = cb;
+		const uint32_t block_total = __shfl_sync(0xffffffffu, wincl, 31);
+		const uint32_t excl = lookback_exclusive(warp == 0 ? P.state_sum : P.state_nz, tile, P.epoch, block_total);
+		if(warp == 0) s_sum[lane] = wincl - v;
+		else s_nz[lane] = wincl - v;
+		if(lane == 0) s_excl[warp] = excl;
+		if(tile == P.num_blocks - 1 && lane == 0) {
+			const uint32_t total = excl + block_total;
+			if(warp == 0) {
+				P.ctr->pair_total = total;
+				P.ctr->stats.total_triangle_count_in_bins += total;
+				if(total > P.pair_capacity) atomicOr(&P.ctr->error_flags, MLV_FLAG_PAIR_OVERFLOW);
+			} else {
+				P.ctr->n_cbins = total; // k_tile ignores it when the pair arena overflowed
+				P.ctr->stats.active_bin_count += total;
 			}
-			if(overflow) P.bin_count[i] = 0u; // the fill pass that would have drained the counters is skipped
 		}
-		run_sum += __shfl_sync(0xffffffffu, incl, 31);
-		run_nz += __popc(nzmask);
 	}
-	if(threadIdx.x == 0) {
-		P.ctr->pair_total = tot_sum;
-		P.ctr->n_cbins_raw = tot_nz;
-		P.ctr->n_cbins = overflow ? 0u : tot_nz;
-		if(overflow) atomicOr(&P.ctr->error_flags, MLV_FLAG_PAIR_OVERFLOW);
-		P.ctr->stats.active_bin_count += tot_nz;
-		P.ctr->stats.total_triangle_count_in_bins += tot_sum;
+	__syncthreads();
+	if(i < P.num_bins) {
+		const uint32_t upto = s_excl[0] + s_sum[warp] + incl - c;
+		P.bin_offset[i] = upto;
+		if(c != 0u) {
+			mlv_ref_compacted_bin cb;
+			cb.num_triangles_self = c;
+			cb.num_triangles_upto = upto;
+			cb.bin_index = i;
+			P.cbins[s_excl[1] + s_nz[warp] + __popc(nzmask & ((1u << lane) - 1u))] = cb;
+		}
 	}
 }
 
@@ -498,10 +522,10 @@ __global__ void __launch_bounds__(1024) k_bin_scan(const ScanParams P) {
 // tile: rasterizer + Hi-Z + early-Z + pixel shader + output merger
 // =================================================================================================
 
-// Restores ascending-id order inside one bin list (the order the reference's serial fill produces,
+// Restores ascending-key order inside one bin list (the order the reference's serial fill produces,
 // main.c:950-962). n <= 32: bitonic network in registers. Larger lists: stable LSD radix split, one bit
 // per pass, ping-ponging between the list and a scratch segment of the same extent.
-__device__ __forceinline__ void sort_bin_ids(uint32_t *ids, uint32_t *tmp, uint32_t n, uint32_t id_bits) {
+__device__ __forceinline__ void sort_bin_ids(uint32_t *ids, uint32_t *tmp, uint32_t n, uint32_t key_bits) {
 	const uint32_t lane = lane_id();
 	if(n <= 32u) {
 		uint32_t v = (lane < n) ? ids[lane] : 0xffffffffu;
@@ -522,7 +546,7 @@ __device__ __forceinline__ void sort_bin_ids(uint32_t *ids, uint32_t *tmp, uint3
 	volatile uint32_t *src = ids;
 	volatile uint32_t *dst = tmp;
 	const uint32_t lt = (1u << lane) - 1u;
-	for(uint32_t bit = 0; bit < id_bits; ++bit) {
+	for(uint32_t bit = 0; bit < key_bits; ++bit) {
 		uint32_t zeros = 0;
 		for(uint32_t i0 = 0; i0 < n; i0 += 32u) {
 			const uint32_t i = i0 + lane;
@@ -554,33 +578,50 @@ __device__ __forceinline__ void sort_bin_ids(uint32_t *ids, uint32_t *tmp, uint3
 	__syncwarp();
 }
 
-// 64 coverage tests of one triangle against one tile (main.c:1012-1038): E_k = ((a_k*x)<<4) + ((b_k*y)<<4) + c_k
-// in wrapping i32 == a_k*(16x) + b_k*(16y) + c_k (mod 2^32), stepped incrementally; inside iff (E0|E1|E2) > 0.
-__device__ __forceinline__ void coverage_64(const uint4 c0, const uint4 c1, const uint32_t c2x, uint32_t X0, uint32_t Y0, uint32_t &lo, uint32_t &hi) {
+// Coverage tests of one triangle against one tile (main.c:1012-1038): E_k = ((a_k*x)<<4) + ((b_k*y)<<4) + c_k in
+// wrapping i32 == a_k*(16x) + b_k*(16y) + c_k (mod 2^32), stepped incrementally; inside iff (E0|E1|E2) > 0.
+// lo = rows 0-3, hi = rows 4-7 of the reference's 64-bit fragment mask (bit 8*row + col).
+// Rows/columns [y0,y1] x [x0,x1] (tile-relative) are evaluated: the full tile, or -- for triangles whose
+// arithmetic provably never wraps (TriSetup::nowrap) -- the part of the tile inside the triangle's bounds,
+// outside of which the full evaluation yields 0 anyway.
+__device__ __forceinline__ void coverage(const uint4 c0, const uint4 c1, const uint32_t c2x, uint32_t X0, uint32_t Y0, int x0, int x1, int y0, int y1, uint32_t &lo,
+                                         uint32_t &hi) {
 	const uint32_t a0 = c0.x, b0 = c0.y, a1 = c0.w, b1 = c1.x, a2 = c1.z, b2 = c1.w;
-	uint32_t e0 = a0 * X0 + b0 * Y0 + c0.z;
-	uint32_t e1 = a1 * X0 + b1 * Y0 + c1.y;
-	uint32_t e2 = a2 * X0 + b2 * Y0 + c2x;
+	const uint32_t Xs = X0 + ((uint32_t)x0 << 4), Ys = Y0 + ((uint32_t)y0 << 4);
+	uint32_t e0 = a0 * Xs + b0 * Ys + c0.z;
+	uint32_t e1 = a1 * Xs + b1 * Ys + c1.y;
+	uint32_t e2 = a2 * Xs + b2 * Ys + c2x;
 	const uint32_t sx0 = a0 << 4, sx1 = a1 << 4, sx2 = a2 << 4;
 	const uint32_t sy0 = b0 << 4, sy1 = b1 << 4, sy2 = b2 << 4;
-	lo = 0u;
-	hi = 0u;
-#pragma unroll
-	for(int y = 0; y < 8; ++y) {
+	unsigned long long m = 0ull;
+	for(int y = y0; y <= y1; ++y) {
 		uint32_t r0 = e0, r1 = e1, r2 = e2;
-#pragma unroll
-		for(int x = 0; x < 8; ++x) {
-			const bool in = (int)(r0 | r1 | r2) > 0;
-			if(y < 4) lo |= in ? (1u << (y * 8 + x)) : 0u;
-			else hi |= in ? (1u << ((y - 4) * 8 + x)) : 0u;
+		uint32_t row = 0u;
+		for(int x = x0; x <= x1; ++x) {
+			row |= ((int)(r0 | r1 | r2) > 0) ? (1u << x) : 0u;
 			r0 += sx0;
 			r1 += sx1;
 			r2 += sx2;
 		}
+		m |= (unsigned long long)row << (8 * y);
 		e0 += sy0;
 		e1 += sy1;
 		e2 += sy2;
 	}
+	lo = (uint32_t)m;
+	hi = (uint32_t)(m >> 32);
+}
+
+// 32x32 bit-matrix transpose across the warp: in: lane r holds row r (bit c = M[r][c]); out: lane r holds column r.
+__device__ __forceinline__ uint32_t warp_transpose_bits(uint32_t x) {
+	const uint32_t lane = lane_id();
+#pragma unroll
+	for(int k = 16; k >= 1; k >>= 1) {
+		const uint32_t mask = (k == 16) ? 0x0000ffffu : (k == 8) ? 0x00ff00ffu : (k == 4) ? 0x0f0f0f0fu : (k == 2) ? 0x33333333u : 0x55555555u;
+		const uint32_t y = __shfl_xor_sync(0xffffffffu, x, k);
+		x = (lane & k) ? ((x & ~mask) | ((y >> k) & mask)) : ((x & mask) | ((y << k) & ~mask));
+	}
+	return x;
 }
 
 // barycentrics of one pixel (main.c:1089-1102)
@@ -596,14 +637,22 @@ __device__ __forceinline__ float interp(float v0, float v1, float v2, float u, f
 	return t;
 }
 
+// key -> record slot (follows the redirect of a clipped input triangle)
+__device__ __forceinline__ uint32_t slot_of_key(const TileParams &P, uint32_t key) {
+	const uint32_t t = key >> 3;
+	const uint4 c2 = __ldg(P.tri_cov + (size_t)t * MLV_TRI_COV_U4 + 2);
+	return (c2.z == MLV_REDIRECT) ? (P.direct_slots + c2.x + (key & 7u)) : t;
+}
+
 template <int PS>
-__device__ __forceinline__ uint32_t shade_pixel(const TileParams &P, uint32_t id, uint32_t X, uint32_t Y) {
-	const uint4 *cov = P.tri_cov + (size_t)id * MLV_TRI_COV_U4;
+__device__ __forceinline__ uint32_t shade_pixel(const TileParams &P, uint32_t key, uint32_t X, uint32_t Y) {
+	const uint32_t slot = slot_of_key(P, key);
+	const uint4 *cov = P.tri_cov + (size_t)slot * MLV_TRI_COV_U4;
 	const uint4 c0 = __ldg(cov), c1 = __ldg(cov + 1);
 	const uint32_t c2x = __ldg(reinterpret_cast<const uint32_t *>(cov + 2));
 	const uint32_t E1 = c0.w * X + c1.x * Y + c1.y;
 	const uint32_t E2 = c1.z * X + c1.w * Y + c2x;
-	const float4 *sh = reinterpret_cast<const float4 *>(P.tri_shade + (size_t)id * MLV_TRI_SHADE_U4);
+	const float4 *sh = reinterpret_cast<const float4 *>(P.tri_shade + (size_t)slot * MLV_TRI_SHADE_U4);
 	const float4 s0 = __ldg(sh), s1 = __ldg(sh + 1), r1a = __ldg(sh + 2), r1b = __ldg(sh + 3), r1c = __ldg(sh + 4), s5 = __ldg(sh + 5);
 	float bx, by;
 	barycentrics(E1, E2, s0.x, bx, by);
@@ -624,18 +673,24 @@ __device__ __forceinline__ uint32_t shade_pixel(const TileParams &P, uint32_t id
 #define MLV_TILE_THREADS 256
 
 template <int PS>
-__global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const TileParams P) {
+__global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const TileParams P, uint32_t pair_capacity) {
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	if(blockIdx.x == 0 && threadIdx.x == 0) { // every earlier kernel of this draw is done with these; re-arm them for the next draw
+		P.ctr->stats.assembled_triangle_count += P.ctr->draw_tris;
+		P.ctr->draw_tris = 0u;
+		P.ctr->last_ovf_count = P.ctr->ovf_count;
+		P.ctr->ovf_count = 0u;
+	}
+	if(P.ctr->pair_total > pair_capacity) return; // draw skipped, MLV_FLAG_PAIR_OVERFLOW is set
 	const uint32_t n_cbins = P.ctr->n_cbins;
-	const uint32_t tri_count = P.ctr->tri_count;
-	const uint32_t id_bits = 32u - __clz(max(tri_count, 2u) - 1u);
-	const uint32_t px = (lane & 3u) * 2u, py = lane >> 2;
+	const uint32_t px = lane & 7u, py = lane >> 3; // this lane's pixels: (px, py) and (px, py + 4)
 
 	for(uint32_t cb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; cb < n_cbins; cb += warps) {
 		const mlv_ref_compacted_bin bin = P.cbins[cb];
 		const uint32_t n = bin.num_triangles_self, off = bin.num_triangles_upto, b = bin.bin_index;
-		const uint32_t X0 = ((b % (uint32_t)P.wt) * 8u) << 4, Y0 = ((b / (uint32_t)P.wt) * 8u) << 4;
+		const int tile_x = (int)(b % (uint32_t)P.wt) * 8, tile_y = (int)(b / (uint32_t)P.wt) * 8;
+		const uint32_t X0 = (uint32_t)tile_x << 4, Y0 = (uint32_t)tile_y << 4;
 		const uint32_t X = X0 + (px << 4), Y = Y0 + (py << 4);
 
 		// read_tile (main.c:577-587)
@@ -645,63 +700,76 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const TileParams P) {
 		const float tile_min_old = P.tile_min[b]; // get_tile_minimum_depth: previous draws only (N3)
 
 		uint32_t *ids = P.pair_ids + off;
-		sort_bin_ids(ids, P.pair_tmp + off, n, id_bits);
+		sort_bin_ids(ids, P.pair_tmp + off, n, P.key_bits);
 
 		for(uint32_t base = 0; base < n; base += 32u) {
 			// ---- rasterizer, lanes over triangles (main.c:996-1041)
 			const uint32_t k = base + lane;
-			uint32_t id = 0, lo = 0, hi = 0;
-			uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-			uint32_t c2x = 0;
+			uint32_t key = 0, lo = 0, hi = 0;
+			uint32_t a1 = 0, b1 = 0, e1 = 0, a2 = 0, b2 = 0, e2 = 0; // E1/E2 of this lane's triangle: coefficients and value at the tile origin
+			float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f);
 			if(k < n) {
-				id = ids[k];
-				const uint4 *cov = P.tri_cov + (size_t)id * MLV_TRI_COV_U4;
-				c0 = __ldg(cov);
-				c1 = __ldg(cov + 1);
-				const uint2 c2 = __ldg(reinterpret_cast<const uint2 *>(cov + 2));
-				c2x = c2.x;
+				key = ids[k];
+				const uint32_t slot = slot_of_key(P, key);
+				const uint4 *cov = P.tri_cov + (size_t)slot * MLV_TRI_COV_U4;
+				const uint4 c2 = __ldg(cov + 2);
 				const float max_depth = __uint_as_float(c2.y);
-				if(!(max_depth < tile_min_old)) coverage_64(c0, c1, c2x, X0, Y0, lo, hi); // Hi-Z (main.c:1005-1010)
+				if(!(max_depth < tile_min_old)) { // Hi-Z (main.c:1005-1010)
+					const uint4 c0 = __ldg(cov), c1 = __ldg(cov + 1);
+					int x0 = 0, x1 = 7, y0 = 0, y1 = 7;
+					if(c2.z & MLV_NOWRAP_BIT) {
+						x0 = max((int)(c2.z & 0xffffu) - tile_x, 0);
+						y0 = max((int)((c2.z >> 16) & 0x7fffu) - tile_y, 0);
+						x1 = min((int)(short)(c2.w & 0xffffu) - tile_x, 7);
+						y1 = min((int)(short)(c2.w >> 16) - tile_y, 7);
+					}
+					coverage(c0, c1, c2.x, X0, Y0, x0, x1, y0, y1, lo, hi);
+					if(lo | hi) {
+						a1 = c0.w, b1 = c1.x, e1 = c0.w * X0 + c1.x * Y0 + c1.y;
+						a2 = c1.z, b2 = c1.w, e2 = c1.z * X0 + c1.w * Y0 + c2.x;
+						s0 = __ldg(reinterpret_cast<const float4 *>(P.tri_shade + (size_t)slot * MLV_TRI_SHADE_U4));
+					}
+				}
 				if(P.dbg.infos) {
 					mlv_ref_tile_info ti;
-					ti.triangle_id = id;
+					ti.triangle_id = key;
 					ti._pad = 0;
 					ti.fragment_mask = ((unsigned long long)hi << 32) | lo;
 					P.dbg.infos[off + k] = ti;
 				}
 			}
+			if(!__any_sync(0xffffffffu, (lo | hi) != 0u)) continue;
+			// ---- per-pixel cover sets: bit j of set0/set1 <=> triangle (base + j) covers this lane's pixel 0/1
+			const uint32_t set0 = warp_transpose_bits(lo), set1 = warp_transpose_bits(hi);
 			// ---- early-Z in list order, lanes over pixels (main.c:1060-1168)
-			uint32_t live = __ballot_sync(0xffffffffu, (lo | hi) != 0u);
-			while(live) {
-				const int src = __ffs(live) - 1;
-				live &= live - 1;
-				const uint32_t sid = __shfl_sync(0xffffffffu, id, src);
-				const uint32_t slo = __shfl_sync(0xffffffffu, lo, src), shi = __shfl_sync(0xffffffffu, hi, src);
-				const uint32_t bits = (((py < 4u) ? slo : shi) >> ((py & 3u) * 8u + px)) & 3u;
-				if(bits) {
-					const uint4 *cov = P.tri_cov + (size_t)sid * MLV_TRI_COV_U4;
-					const uint4 q0 = __ldg(cov), q1 = __ldg(cov + 1);
-					const uint32_t q2x = __ldg(reinterpret_cast<const uint32_t *>(cov + 2));
-					const float4 s0 = __ldg(reinterpret_cast<const float4 *>(P.tri_shade + (size_t)sid * MLV_TRI_SHADE_U4));
-					const uint32_t E1 = q0.w * X + q1.x * Y + q1.y;
-					const uint32_t E2 = q1.z * X + q1.w * Y + q2x;
-					if(bits & 1u) {
-						float bx, by;
-						barycentrics(E1, E2, s0.x, bx, by);
-						const float z = interp(s0.y, s0.z, s0.w, bx, by);
-						if(z >= d0) { // _CMP_GE_OQ, reversed Z (main.c:1166)
-							d0 = z;
-							win0 = sid;
-						}
+			uint32_t todo = set0 | set1;
+			while(__any_sync(0xffffffffu, todo != 0u)) {
+				const int j = todo ? (__ffs(todo) - 1) : 0;
+				const uint32_t bitj = todo ? (1u << j) : 0u; // lanes that are done only take part in the shuffles
+				todo &= ~bitj;
+				const uint32_t ta1 = __shfl_sync(0xffffffffu, a1, j), tb1 = __shfl_sync(0xffffffffu, b1, j), te1 = __shfl_sync(0xffffffffu, e1, j);
+				const uint32_t ta2 = __shfl_sync(0xffffffffu, a2, j), tb2 = __shfl_sync(0xffffffffu, b2, j), te2 = __shfl_sync(0xffffffffu, e2, j);
+				const float ooa = __shfl_sync(0xffffffffu, s0.x, j), z0 = __shfl_sync(0xffffffffu, s0.y, j);
+				const float z1 = __shfl_sync(0xffffffffu, s0.z, j), z2 = __shfl_sync(0xffffffffu, s0.w, j);
+				const uint32_t tkey = __shfl_sync(0xffffffffu, key, j);
+				const uint32_t E1 = ta1 * (px << 4) + tb1 * (py << 4) + te1;
+				const uint32_t E2 = ta2 * (px << 4) + tb2 * (py << 4) + te2;
+				if(set0 & bitj) {
+					float bx, by;
+					barycentrics(E1, E2, ooa, bx, by);
+					const float z = interp(z0, z1, z2, bx, by);
+					if(z >= d0) { // _CMP_GE_OQ, reversed Z (main.c:1166)
+						d0 = z;
+						win0 = tkey;
 					}
-					if(bits & 2u) {
-						float bx, by;
-						barycentrics(E1 + (q0.w << 4), E2 + (q1.z << 4), s0.x, bx, by);
-						const float z = interp(s0.y, s0.z, s0.w, bx, by);
-						if(z >= d1) {
-							d1 = z;
-							win1 = sid;
-						}
+				}
+				if(set1 & bitj) {
+					float bx, by;
+					barycentrics(E1 + (tb1 << 6), E2 + (tb2 << 6), ooa, bx, by); // four rows down: + b*(4*16)
+					const float z = interp(z0, z1, z2, bx, by);
+					if(z >= d1) {
+						d1 = z;
+						win1 = tkey;
 					}
 				}
 			}
@@ -709,7 +777,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const TileParams P) {
 
 		// ---- pixel shader + output merger, once per pixel on the last fragment that passed (main.c:1170-1181)
 		if(win0 != MLV_NO_WINNER) pix.x = shade_pixel<PS>(P, win0, X, Y);
-		if(win1 != MLV_NO_WINNER) pix.y = shade_pixel<PS>(P, win1, X + 16u, Y);
+		if(win1 != MLV_NO_WINNER) pix.y = shade_pixel<PS>(P, win1, X, Y + 64u);
 		pix.z = __float_as_uint(d0);
 		pix.w = __float_as_uint(d1);
 
@@ -726,38 +794,64 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const TileParams P) {
 // resolve / composite
 // =================================================================================================
 
-// Tiled -> row-major. One thread per 4 horizontally adjacent pixels: two 128-bit loads, one 128-bit colour
-// store (+ one 128-bit depth store).
+// Tiled -> row-major. One thread per 4 horizontally adjacent pixels of rows y and y+4 of a tile: four 128-bit
+// loads (64 contiguous bytes, all of them used), two 128-bit colour stores (+ two 128-bit depth stores).
+struct Quad8 {
+	uint4 c_top, c_bot;
+	float4 d_top, d_bot;
+};
+__device__ __forceinline__ Quad8 load_quad8(const uint4 *__restrict__ fb, uint32_t bin, uint32_t row, uint32_t half) {
+	const uint4 *p = fb + (size_t)bin * 32u + row * 8u + half * 4u; // lanes (x = 4*half .. 4*half+3, y = row)
+	const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+	Quad8 q;
+	q.c_top = make_uint4(a.x, b.x, c.x, d.x);
+	q.c_bot = make_uint4(a.y, b.y, c.y, d.y);
+	q.d_top = make_float4(__uint_as_float(a.z), __uint_as_float(b.z), __uint_as_float(c.z), __uint_as_float(d.z));
+	q.d_bot = make_float4(__uint_as_float(a.w), __uint_as_float(b.w), __uint_as_float(c.w), __uint_as_float(d.w));
+	return q;
+}
+
+// work item w -> (bin, row 0..3, half 0..1); 8 items per tile
 __global__ void __launch_bounds__(256) k_resolve(const uint4 *__restrict__ fb, uint4 *__restrict__ colors, float4 *__restrict__ depths, int width, int height) {
-	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; // quad index, row-major over (width/4) x height
-	const uint32_t qw = (uint32_t)width >> 2;
-	if(q >= qw * (uint32_t)height) return;
-	const uint32_t y = q / qw, xq = q % qw;
-	const uint32_t tx = xq >> 1, ty = y >> 3;
-	const uint32_t bin = ty * ((uint32_t)width >> 3) + tx;
-	const uint32_t lane = (y & 7u) * 4u + (xq & 1u) * 2u;
-	const uint4 a = __ldg(fb + (size_t)bin * 32u + lane), b = __ldg(fb + (size_t)bin * 32u + lane + 1u);
-	colors[q] = make_uint4(a.x, a.y, b.x, b.y);
-	if(depths) depths[q] = make_float4(__uint_as_float(a.z), __uint_as_float(a.w), __uint_as_float(b.z), __uint_as_float(b.w));
+	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t wt = (uint32_t)width >> 3, ht = (uint32_t)height >> 3;
+	// order work so that consecutive threads write consecutive 16-byte quads of one image row
+	const uint32_t quads_per_row = wt * 2u;
+	const uint32_t rowgroup = w / quads_per_row; // = ty * 4 + row
+	if(rowgroup >= ht * 4u) return;
+	const uint32_t xq = w % quads_per_row, ty = rowgroup >> 2, row = rowgroup & 3u;
+	const uint32_t bin = ty * wt + (xq >> 1);
+	const Quad8 q = load_quad8(fb, bin, row, xq & 1u);
+	const size_t top = ((size_t)(ty * 8u + row) * (uint32_t)width) / 4u + xq, bot = top + (size_t)width; // +4 rows = 4*width/4 quads
+	colors[top] = q.c_top;
+	colors[bot] = q.c_bot;
+	if(depths) {
+		depths[top] = q.d_top;
+		depths[bot] = q.d_bot;
+	}
 }
 
 // Sort-first compositing helpers. Chunk r of the gather buffer = row-major colour of rank r's
 // stripes in ascending stripe order. PACK: tiled framebuffer of this rank -> its own chunk.
 // UNPACK: every chunk -> the final row-major image.
+__device__ __forceinline__ uint32_t chunk_row(uint32_t ty, uint32_t y_in_tile, int stripe_h, int num_ranks) {
+	const uint32_t stripe = ty / (uint32_t)stripe_h;
+	const uint32_t local_stripe = stripe / (uint32_t)num_ranks;
+	return (local_stripe * (uint32_t)stripe_h + (ty % (uint32_t)stripe_h)) * 8u + y_in_tile;
+}
+
 __global__ void __launch_bounds__(256) k_composite_pack(const uint4 *__restrict__ fb, uint4 *__restrict__ chunk, int width, int height, Partition part) {
-	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t qw = (uint32_t)width >> 2;
-	if(q >= qw * (uint32_t)height) return;
-	const uint32_t y = q / qw, xq = q % qw;
-	const uint32_t ty = y >> 3;
+	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t wt = (uint32_t)width >> 3, ht = (uint32_t)height >> 3;
+	const uint32_t quads_per_row = wt * 2u;
+	const uint32_t rowgroup = w / quads_per_row;
+	if(rowgroup >= ht * 4u) return;
+	const uint32_t xq = w % quads_per_row, ty = rowgroup >> 2, row = rowgroup & 3u;
 	if(!part.owns_row((int)ty)) return;
-	const uint32_t stripe = ty / (uint32_t)part.stripe_h;
-	const uint32_t local_stripe = stripe / (uint32_t)part.num_ranks;
-	const uint32_t local_y = (local_stripe * (uint32_t)part.stripe_h + (ty % (uint32_t)part.stripe_h)) * 8u + (y & 7u);
-	const uint32_t bin = ty * ((uint32_t)width >> 3) + (xq >> 1);
-	const uint32_t lane = (y & 7u) * 4u + (xq & 1u) * 2u;
-	const uint4 a = __ldg(fb + (size_t)bin * 32u + lane), b = __ldg(fb + (size_t)bin * 32u + lane + 1u);
-	chunk[(size_t)local_y * qw + xq] = make_uint4(a.x, a.y, b.x, b.y);
+	const Quad8 q = load_quad8(fb, ty * wt + (xq >> 1), row, xq & 1u);
+	const size_t top = (size_t)chunk_row(ty, row, part.stripe_h, part.num_ranks) * quads_per_row + xq;
+	chunk[top] = q.c_top;
+	chunk[top + 4u * quads_per_row] = q.c_bot;
 }
 
 __global__ void __launch_bounds__(256) k_composite_unpack(const uint4 *__restrict__ gather, uint4 *__restrict__ colors, int width, int height, int num_ranks, int stripe_h,
@@ -767,11 +861,8 @@ __global__ void __launch_bounds__(256) k_composite_unpack(const uint4 *__restric
 	if(q >= qw * (uint32_t)height) return;
 	const uint32_t y = q / qw, xq = q % qw;
 	const uint32_t ty = y >> 3;
-	const uint32_t stripe = ty / (uint32_t)stripe_h;
-	const uint32_t owner = stripe % (uint32_t)num_ranks;
-	const uint32_t local_stripe = stripe / (uint32_t)num_ranks;
-	const uint32_t local_y = (local_stripe * (uint32_t)stripe_h + (ty % (uint32_t)stripe_h)) * 8u + (y & 7u);
-	colors[q] = __ldg(gather + (size_t)owner * chunk_u4 + (size_t)local_y * qw + xq);
+	const uint32_t owner = (ty / (uint32_t)stripe_h) % (uint32_t)num_ranks;
+	colors[q] = __ldg(gather + (size_t)owner * chunk_u4 + (size_t)chunk_row(ty, y & 7u, stripe_h, num_ranks) * qw + xq);
 }
 
 } // namespace mlv

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <cmath>
 #include <new>
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "kernels.cuh"
@@ -65,15 +67,16 @@ struct mlv_device {
 	uint64_t pair_capacity;
 	uint4 *tri_cov, *tri_shade;
 	uint2 *tri_bounds;
-	uint32_t tri_capacity;
-	unsigned long long *scan_state;
-	uint32_t scan_capacity;
+	uint32_t *ovf_key;
+	uint32_t tri_capacity; // slots (direct + overflow)
+	unsigned long long *scan_state; // 2 x scan_blocks look-back words
+	uint32_t scan_blocks;
 	Counters *ctr;
 	uint32_t *rsqrt_lut;
 	// debug capture
 	DebugOut dbg;
 	uint32_t dbg_tri_capacity, dbg_vertex_capacity;
-	uint32_t last_index_count;
+	uint32_t last_index_count, last_direct_slots;
 	// present / composite
 	uint4 *resolved_color;
 	float4 *resolved_depth;
@@ -202,6 +205,9 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	CREATE_TRY(cudaMalloc(&dev->pair_ids, dev->pair_capacity * sizeof(uint32_t)));
 	CREATE_TRY(cudaMalloc(&dev->pair_tmp, dev->pair_capacity * sizeof(uint32_t)));
 	CREATE_TRY(cudaMalloc(&dev->ctr, sizeof(Counters)));
+	dev->scan_blocks = (dev->num_bins + MLV_SCAN_THREADS - 1) / MLV_SCAN_THREADS;
+	CREATE_TRY(cudaMalloc(&dev->scan_state, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long)));
+	CREATE_TRY(cudaMemsetAsync(dev->scan_state, 0, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long), dev->stream));
 	CREATE_TRY(cudaMalloc(&dev->rsqrt_lut, sizeof(k_rsqrt_lut_host)));
 	CREATE_TRY(cudaMalloc(&dev->resolved_color, (size_t)dev->W * dev->H * 4));
 	CREATE_TRY(cudaMalloc(&dev->resolved_depth, (size_t)dev->W * dev->H * 4));
@@ -228,8 +234,8 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(!dev) return;
 	cudaSetDevice(dev->cuda_dev);
 	if(dev->stream) cudaStreamSynchronize(dev->stream);
-	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds,
-		             dev->scan_state, dev->ctr, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
+	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->ovf_key,
+		             dev->scan_state, dev->ctr, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
 	if(dev->stream) cudaStreamDestroy(dev->stream);
@@ -430,9 +436,9 @@ static TexDesc tex_desc(const mlv_texture *t) {
 }
 
 template <int VS>
-static void launch_geom(mlv_device *dev, const GeomParams &gp, bool indexed) {
-	if(indexed) k_geom<VS, true><<<gp.num_blocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
-	else k_geom<VS, false><<<gp.num_blocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed) {
+	if(indexed) k_geom<VS, true><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+	else k_geom<VS, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
 }
 
 static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
@@ -460,30 +466,28 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	if(count == 0) return MLV_OK;
 
 	const uint32_t T = count / 3u;
-	if(T >= 0x40000000u / 3u) return fail(MLV_ERR_INVALID_ARGUMENT, "draw too large");
-	// capacity of the reference's own output arrays: T + max(2T, 512) (main.c:739-740)
-	const uint32_t need_tris = T + (2u * T > 512u ? 2u * T : 512u);
+	if(T >= (1u << 28)) return fail(MLV_ERR_INVALID_ARGUMENT, "draw too large: triangle keys are (input_triangle << 3 | fan_index) in 32 bits");
+	// Slot capacity = the reference's own output capacity T + max(2T, 512) (main.c:739-740): T direct slots plus
+	// max(2T, 512) overflow slots for the fan triangles of clipped input triangles.
+	const uint32_t ovf_cap = (2u * T > 512u ? 2u * T : 512u);
+	const uint32_t need_slots = T + ovf_cap;
 	const uint32_t nblocks = (T + MLV_GEOM_THREADS - 1) / MLV_GEOM_THREADS;
 	const bool debug = (dev->desc.flags & MLV_DEVICE_DEBUG_CAPTURE) != 0;
-	if(need_tris > dev->tri_capacity || nblocks > dev->scan_capacity || (debug && (need_tris > dev->dbg_tri_capacity || count > dev->dbg_vertex_capacity || !dev->dbg.infos))) {
+	if(need_slots > dev->tri_capacity || (debug && (need_slots > dev->dbg_tri_capacity || count > dev->dbg_vertex_capacity || !dev->dbg.infos))) {
 		CUDA_TRY(cudaStreamSynchronize(dev->stream));
-		if(need_tris > dev->tri_capacity) {
-			const uint32_t cap = need_tris + need_tris / 4;
+		if(need_slots > dev->tri_capacity) {
+			const uint32_t cap = need_slots + need_slots / 4;
 			CUDA_TRY(regrow(&dev->tri_cov, (size_t)cap * MLV_TRI_COV_U4));
 			CUDA_TRY(regrow(&dev->tri_shade, (size_t)cap * MLV_TRI_SHADE_U4));
 			CUDA_TRY(regrow(&dev->tri_bounds, (size_t)cap));
+			CUDA_TRY(regrow(&dev->ovf_key, (size_t)cap));
 			dev->tri_capacity = cap;
 		}
-		if(nblocks > dev->scan_capacity) {
-			const uint32_t cap = nblocks * 2;
-			CUDA_TRY(regrow(&dev->scan_state, (size_t)cap));
-			CUDA_TRY(cudaMemset(dev->scan_state, 0, (size_t)cap * sizeof(unsigned long long)));
-			dev->scan_capacity = cap;
-		}
 		if(debug) {
-			if(need_tris > dev->dbg_tri_capacity) {
+			if(need_slots > dev->dbg_tri_capacity) {
 				CUDA_TRY(regrow(&dev->dbg.tris, (size_t)dev->tri_capacity));
 				CUDA_TRY(regrow(&dev->dbg.attrs, (size_t)dev->tri_capacity * 36));
+				CUDA_TRY(regrow(&dev->dbg.slot_key, (size_t)dev->tri_capacity));
 				dev->dbg_tri_capacity = dev->tri_capacity;
 			}
 			if(count > dev->dbg_vertex_capacity) {
@@ -493,10 +497,11 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 			if(!dev->dbg.infos) CUDA_TRY(regrow(&dev->dbg.infos, (size_t)dev->pair_capacity));
 		}
 	}
+	dev->last_direct_slots = T;
 
 	dev->epoch = (dev->epoch + 1u) & 0x3fffffffu;
 	if(dev->epoch == 0u) { // 30-bit epoch wrapped: invalidate every published scan entry
-		CUDA_TRY(cudaMemsetAsync(dev->scan_state, 0, (size_t)dev->scan_capacity * sizeof(unsigned long long), dev->stream));
+		CUDA_TRY(cudaMemsetAsync(dev->scan_state, 0, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long), dev->stream));
 		dev->epoch = 1u;
 	}
 
@@ -505,7 +510,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	gp.ib = indexed ? (const uint32_t *)dev->ib->d : nullptr;
 	gp.vb = (const float4 *)dev->vb->d;
 	gp.tri_count = T;
-	gp.tri_capacity = need_tris;
+	gp.ovf_capacity = ovf_cap;
 	memcpy(gp.cb, dev->cb[0], 192);
 	gp.vs_tex = tex_desc(dev->vs_srv[0]);
 	gp.rsqrt_lut = dev->rsqrt_lut;
@@ -530,50 +535,55 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	gp.tri_cov = dev->tri_cov;
 	gp.tri_shade = dev->tri_shade;
 	gp.tri_bounds = dev->tri_bounds;
+	gp.ovf_key = dev->ovf_key;
 	if(debug) gp.dbg = dev->dbg;
-	gp.scan_state = dev->scan_state;
 	gp.ctr = dev->ctr;
-	gp.ticket_base = dev->ticket_base;
-	gp.epoch = dev->epoch;
-	gp.num_blocks = nblocks;
 	gp.index_count = count;
-	dev->ticket_base += nblocks;
 
 	prof_pre(dev, MLV_STAGE_GEOMETRY);
 	switch(dev->vs_id) {
-		case MLV_VS_PASSTHROUGH: launch_geom<0>(dev, gp, indexed); break;
-		case MLV_VS_BASIC: launch_geom<1>(dev, gp, indexed); break;
-		case MLV_VS_VERTEX_LIGHTING: launch_geom<2>(dev, gp, indexed); break;
-		default: launch_geom<3>(dev, gp, indexed); break;
+		case MLV_VS_PASSTHROUGH: launch_geom<0>(dev, gp, nblocks, indexed); break;
+		case MLV_VS_BASIC: launch_geom<1>(dev, gp, nblocks, indexed); break;
+		case MLV_VS_VERTEX_LIGHTING: launch_geom<2>(dev, gp, nblocks, indexed); break;
+		default: launch_geom<3>(dev, gp, nblocks, indexed); break;
 	}
 	if(int rc = check_launch(dev, "k_geom")) return rc;
 
 	BinParams bp;
+	memset(&bp, 0, sizeof(bp));
 	bp.tri_bounds = dev->tri_bounds;
+	bp.ovf_key = dev->ovf_key;
 	bp.bin_count = dev->bin_count;
-	bp.bin_cursor = nullptr;
 	bp.bin_offset = dev->bin_offset;
 	bp.pair_ids = dev->pair_ids;
 	bp.ctr = dev->ctr;
+	bp.direct_slots = T;
+	bp.num_bins = dev->num_bins;
 	bp.wt = dev->wt;
 	bp.ht = dev->ht;
 	bp.part = dev->part;
-	uint32_t bin_blocks = (need_tris + 255u) / 256u;
+	uint32_t bin_blocks = (need_slots + 255u) / 256u;
 	if(bin_blocks > 148u * 16u) bin_blocks = 148u * 16u;
 	prof_pre(dev, MLV_STAGE_BIN_COUNT);
 	k_bin<false><<<bin_blocks, 256, 0, dev->stream>>>(bp, (uint32_t)dev->pair_capacity);
 	if(int rc = check_launch(dev, "k_bin<count>")) return rc;
 
 	ScanParams sp;
+	memset(&sp, 0, sizeof(sp));
 	sp.bin_count = dev->bin_count;
-	sp.bin_cursor = nullptr;
 	sp.bin_offset = dev->bin_offset;
 	sp.cbins = dev->cbins;
 	sp.ctr = dev->ctr;
+	sp.state_sum = dev->scan_state;
+	sp.state_nz = dev->scan_state + dev->scan_blocks;
 	sp.num_bins = dev->num_bins;
 	sp.pair_capacity = (uint32_t)dev->pair_capacity;
+	sp.ticket_base = dev->ticket_base;
+	sp.epoch = dev->epoch;
+	sp.num_blocks = dev->scan_blocks;
+	dev->ticket_base += dev->scan_blocks;
 	prof_pre(dev, MLV_STAGE_BIN_SCAN);
-	k_bin_scan<<<1, 1024, 0, dev->stream>>>(sp);
+	k_bin_scan<<<dev->scan_blocks, MLV_SCAN_THREADS, 0, dev->stream>>>(sp);
 	if(int rc = check_launch(dev, "k_bin_scan")) return rc;
 
 	prof_pre(dev, MLV_STAGE_BIN_FILL);
@@ -589,19 +599,22 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	tp.tri_shade = dev->tri_shade;
 	tp.fb = dev->fb;
 	tp.tile_min = dev->tile_min;
-	tp.bin_count = dev->bin_count;
 	tp.ctr = dev->ctr;
 	tp.ps_tex = tex_desc(dev->ps_srv[0]);
 	tp.rsqrt_lut = dev->rsqrt_lut;
 	if(debug) tp.dbg = dev->dbg;
+	tp.direct_slots = T;
+	tp.key_bits = 3u;
+	while(tp.key_bits < 32u && (T >> (tp.key_bits - 3u)) != 0u) tp.key_bits++;
 	tp.wt = dev->wt;
 	uint32_t tile_blocks = (dev->num_bins + 7u) / 8u;
 	if(tile_blocks > 148u * 8u) tile_blocks = 148u * 8u;
+	const uint32_t pcap = (uint32_t)dev->pair_capacity;
 	prof_pre(dev, MLV_STAGE_TILE);
 	switch(dev->ps_id) {
-		case MLV_PS_PASSTHROUGH: k_tile<0><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp); break;
-		case MLV_PS_BASIC: k_tile<1><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp); break;
-		default: k_tile<2><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp); break;
+		case MLV_PS_PASSTHROUGH: k_tile<0><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp, pcap); break;
+		case MLV_PS_BASIC: k_tile<1><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp, pcap); break;
+		default: k_tile<2><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp, pcap); break;
 	}
 	return check_launch(dev, "k_tile");
 }
@@ -623,9 +636,9 @@ static int check_flags(mlv_device *dev, const Counters &c) {
 int mlv_resolve(mlv_device *dev) {
 	if(int rc = use_device(dev)) return rc;
 	if(int rc = flush_clears(dev)) return rc;
-	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
+	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H; // 8 pixels (4 wide, rows y and y+4) per thread
 	prof_pre(dev, MLV_STAGE_RESOLVE);
-	k_resolve<<<(quads + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->resolved_color, dev->resolved_depth, dev->W, dev->H);
+	k_resolve<<<(items + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->resolved_color, dev->resolved_depth, dev->W, dev->H);
 	return check_launch(dev, "k_resolve");
 }
 
@@ -635,9 +648,9 @@ void *mlv_resolved_depth_device_ptr(mlv_device *dev) { return dev ? dev->resolve
 int mlv_present_readback(mlv_device *dev, uint32_t *colors, float *depths) {
 	if(int rc = use_device(dev)) return rc;
 	if(int rc = flush_clears(dev)) return rc;
-	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
+	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
 	prof_pre(dev, MLV_STAGE_RESOLVE);
-	k_resolve<<<(quads + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->resolved_color, depths ? dev->resolved_depth : nullptr, dev->W, dev->H);
+	k_resolve<<<(items + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->resolved_color, depths ? dev->resolved_depth : nullptr, dev->W, dev->H);
 	if(int rc = check_launch(dev, "k_resolve")) return rc;
 	const size_t bytes = (size_t)dev->W * dev->H * 4;
 	if(colors) CUDA_TRY(cudaMemcpyAsync(colors, dev->resolved_color, bytes, cudaMemcpyDeviceToHost, dev->stream));
@@ -677,10 +690,10 @@ int mlv_composite_pack(mlv_device *dev) {
 	if(int rc = use_device(dev)) return rc;
 	if(dev->part.num_ranks <= 1) return fail(MLV_ERR_STATE, "device was created with a single rank");
 	if(int rc = flush_clears(dev)) return rc;
-	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
+	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
 	uint4 *chunk = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(dev->gather) + dev->chunk_bytes * (size_t)dev->part.rank);
 	prof_pre(dev, MLV_STAGE_COMPOSITE);
-	k_composite_pack<<<(quads + 255) / 256, 256, 0, dev->stream>>>(dev->fb, chunk, dev->W, dev->H, dev->part);
+	k_composite_pack<<<(items + 255) / 256, 256, 0, dev->stream>>>(dev->fb, chunk, dev->W, dev->H, dev->part);
 	return check_launch(dev, "k_composite_pack");
 }
 
@@ -711,30 +724,87 @@ int mlv_debug_read_vs_out(mlv_device *dev, float *out12_per_vertex, uint32_t *ou
 	return MLV_OK;
 }
 
+// The device names triangles by order-preserving keys and stores them in slots (mlv_internal.cuh). The debug
+// read-back marshals that into the reference's compact numbering: reference id i == the i-th smallest key.
+struct DebugMap {
+	std::vector<uint32_t> keys;  // ascending
+	std::vector<uint32_t> slots; // slot of keys[i]
+	uint32_t rank(uint32_t key) const { return (uint32_t)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin()); }
+};
+
+static int build_debug_map(mlv_device *dev, const Counters &c, DebugMap &m) {
+	const uint32_t n_slots = dev->last_direct_slots + c.last_ovf_count;
+	std::vector<uint32_t> slot_key(n_slots);
+	if(n_slots) CUDA_TRY(cudaMemcpy(slot_key.data(), dev->dbg.slot_key, (size_t)n_slots * 4, cudaMemcpyDeviceToHost));
+	std::vector<std::pair<uint32_t, uint32_t>> ks;
+	for(uint32_t s = 0; s < n_slots; ++s)
+		if(slot_key[s] != 0xffffffffu) ks.emplace_back(slot_key[s], s);
+	std::sort(ks.begin(), ks.end());
+	m.keys.resize(ks.size());
+	m.slots.resize(ks.size());
+	for(size_t i = 0; i < ks.size(); ++i) {
+		m.keys[i] = ks[i].first;
+		m.slots[i] = ks[i].second;
+	}
+	return MLV_OK;
+}
+
 int mlv_debug_read_triangles(mlv_device *dev, mlv_ref_triangle *tris, float *attributes36, uint32_t *out_count) {
 	Counters c;
 	if(int rc = debug_counters(dev, &c)) return rc;
-	if(out_count) *out_count = c.tri_count;
-	if(tris && c.tri_count) CUDA_TRY(cudaMemcpy(tris, dev->dbg.tris, (size_t)c.tri_count * sizeof(mlv_ref_triangle), cudaMemcpyDeviceToHost));
-	if(attributes36 && c.tri_count) CUDA_TRY(cudaMemcpy(attributes36, dev->dbg.attrs, (size_t)c.tri_count * 144, cudaMemcpyDeviceToHost));
+	if(dev->last_index_count == 0) {
+		if(out_count) *out_count = 0;
+		return MLV_OK;
+	}
+	DebugMap m;
+	if(int rc = build_debug_map(dev, c, m)) return rc;
+	if(out_count) *out_count = (uint32_t)m.keys.size();
+	const uint32_t n_slots = dev->last_direct_slots + c.last_ovf_count;
+	if(tris && !m.keys.empty()) {
+		std::vector<mlv_ref_triangle> all(n_slots);
+		CUDA_TRY(cudaMemcpy(all.data(), dev->dbg.tris, (size_t)n_slots * sizeof(mlv_ref_triangle), cudaMemcpyDeviceToHost));
+		for(size_t i = 0; i < m.keys.size(); ++i) {
+			tris[i] = all[m.slots[i]];
+			tris[i].p_attributes = (uint64_t)i * 144ull;
+		}
+	}
+	if(attributes36 && !m.keys.empty()) {
+		std::vector<float> all((size_t)n_slots * 36);
+		CUDA_TRY(cudaMemcpy(all.data(), dev->dbg.attrs, (size_t)n_slots * 144, cudaMemcpyDeviceToHost));
+		for(size_t i = 0; i < m.keys.size(); ++i) memcpy(attributes36 + i * 36, all.data() + (size_t)m.slots[i] * 36, 144);
+	}
 	return MLV_OK;
 }
 
 int mlv_debug_read_bins(mlv_device *dev, uint32_t *triangle_ids, uint32_t *out_pair_count, mlv_ref_compacted_bin *bins, uint32_t *out_bin_count) {
 	Counters c;
 	if(int rc = debug_counters(dev, &c)) return rc;
-	if(out_pair_count) *out_pair_count = c.pair_total;
-	if(out_bin_count) *out_bin_count = c.n_cbins;
-	if(triangle_ids && c.pair_total && c.n_cbins) CUDA_TRY(cudaMemcpy(triangle_ids, dev->pair_ids, (size_t)c.pair_total * 4, cudaMemcpyDeviceToHost));
-	if(bins && c.n_cbins) CUDA_TRY(cudaMemcpy(bins, dev->cbins, (size_t)c.n_cbins * sizeof(mlv_ref_compacted_bin), cudaMemcpyDeviceToHost));
+	const bool skipped = c.pair_total > dev->pair_capacity || dev->last_index_count == 0;
+	const uint32_t pairs = skipped ? 0u : c.pair_total, nb = skipped ? 0u : c.n_cbins;
+	if(out_pair_count) *out_pair_count = pairs;
+	if(out_bin_count) *out_bin_count = nb;
+	if(triangle_ids && pairs) {
+		DebugMap m;
+		if(int rc = build_debug_map(dev, c, m)) return rc;
+		CUDA_TRY(cudaMemcpy(triangle_ids, dev->pair_ids, (size_t)pairs * 4, cudaMemcpyDeviceToHost));
+		for(uint32_t i = 0; i < pairs; ++i) triangle_ids[i] = m.rank(triangle_ids[i]);
+	}
+	if(bins && nb) CUDA_TRY(cudaMemcpy(bins, dev->cbins, (size_t)nb * sizeof(mlv_ref_compacted_bin), cudaMemcpyDeviceToHost));
 	return MLV_OK;
 }
 
 int mlv_debug_read_masks(mlv_device *dev, mlv_ref_tile_info *infos, uint32_t *out_pair_count) {
 	Counters c;
 	if(int rc = debug_counters(dev, &c)) return rc;
-	if(out_pair_count) *out_pair_count = c.pair_total;
-	if(infos && c.pair_total && c.n_cbins) CUDA_TRY(cudaMemcpy(infos, dev->dbg.infos, (size_t)c.pair_total * sizeof(mlv_ref_tile_info), cudaMemcpyDeviceToHost));
+	const bool skipped = c.pair_total > dev->pair_capacity || dev->last_index_count == 0;
+	const uint32_t pairs = skipped ? 0u : c.pair_total;
+	if(out_pair_count) *out_pair_count = pairs;
+	if(infos && pairs) {
+		DebugMap m;
+		if(int rc = build_debug_map(dev, c, m)) return rc;
+		CUDA_TRY(cudaMemcpy(infos, dev->dbg.infos, (size_t)pairs * sizeof(mlv_ref_tile_info), cudaMemcpyDeviceToHost));
+		for(uint32_t i = 0; i < pairs; ++i) infos[i].triangle_id = m.rank(infos[i].triangle_id);
+	}
 	return MLV_OK;
 }
 

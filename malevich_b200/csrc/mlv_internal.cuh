@@ -10,29 +10,40 @@ namespace mlv {
 
 // ---- HBM layouts (DESIGN.md "Data layout") ----------------------------------------------------
 //
-// Framebuffer: TILED. Tile (bin) b owns 32 consecutive uint4 (512 B). Lane l of the warp that owns
-// the tile holds pixels (x0 = 2*(l&3), y = l>>2) and (x0+1, y):  uint4 = { colour(x0), colour(x0+1),
-// depth_bits(x0), depth_bits(x0+1) }.  One LDG.128 + one STG.128 per lane per tile-draw.
+// Framebuffer: TILED. Tile (bin) b owns 32 consecutive uint4 (512 B). Lane l of the warp that owns the
+// tile holds pixels p0 = (x = l&7, y = l>>3) and p1 = (x, y+4), i.e. bits l and 32+l of the reference's
+// 64-bit fragment mask:  uint4 = { colour(p0), colour(p1), depth_bits(p0), depth_bits(p1) }.
+// One LDG.128 + one STG.128 per lane per tile-draw.
 //
-// Per assembled triangle (id = position in the reference's single-thread output order):
-//   TriCov   48 B  { a0,b0,c0,a1 | b1,c1,a2,b2 | c2, max_depth, tile_bounds_lo, tile_bounds_hi }   coverage + Hi-Z
+// Triangle identity. The reference numbers assembled triangles in single-thread output order (input order,
+// fan order inside a clipped triangle). Here a triangle is named by the order-preserving
+// KEY = (input_triangle << 3) | fan_index, so no ordered compaction (scan) is needed: ascending key ==
+// ascending reference id. Records live in SLOTS: an unclipped input triangle t uses slot t; the fan
+// triangles of a clipped input triangle use consecutive overflow slots T + base + fan_index, found through a
+// redirect stored in slot t.
+//   TriCov   48 B  { a0,b0,c0,a1 | b1,c1,a2,b2 | c2, max_depth, minx|flags_miny<<16, maxx|maxy<<16 }  coverage + Hi-Z
+//                  redirect:  word 10 == MLV_REDIRECT, word 8 = overflow base
 //   TriShade 96 B  { ooa,z0,z1,z2 | rw0,rw1,rw2,r2x_v0 | r1_v0 | r1_v1 | r1_v2 | r2x_v1,r2x_v2,0,0 }  depth + attributes
-//   bounds    8 B  int16 { tx0, ty0, tx1, ty1 } inclusive tile rectangle (tx0 > tx1 => bins nothing)
+//   bounds    8 B  { minx | (miny|nowrap<<15)<<16, maxx | maxy<<16 } int16 pixel bounds (main.c:888-898); minx == 0x7fff: bins nothing
 #define MLV_TRI_COV_U4 3
 #define MLV_TRI_SHADE_U4 6
+#define MLV_REDIRECT 0x7ffe7ffeu
+#define MLV_BOUNDS_EMPTY 0x00007fffu
+#define MLV_NOWRAP_BIT 0x80000000u /* bit 15 of miny inside word 10 */
 
 #define MLV_NO_WINNER 0xffffffffu
 
 enum { MLV_FLAG_TRI_OVERFLOW = 1u, MLV_FLAG_PAIR_OVERFLOW = 2u };
 
 struct Counters {
-	uint32_t tri_count;   // assembled triangles of the current draw (written by the last geometry block)
+	uint32_t ovf_count;   // overflow slots taken by clipped triangles in the current draw (reset by k_tile)
 	uint32_t pair_total;  // (triangle,tile) pairs of the current draw
 	uint32_t n_cbins;     // non-empty bins of the current draw (0 if the pair arena overflowed)
 	uint32_t error_flags; // sticky MLV_FLAG_*
-	uint32_t ticket;      // monotonically increasing block ticket of the geometry kernel
-	uint32_t n_cbins_raw; // non-empty bins even when overflowed
-	uint32_t pad[2];
+	uint32_t ticket;      // monotonically increasing block ticket (look-back scans)
+	uint32_t draw_tris;   // assembled triangles of the current draw
+	uint32_t last_ovf_count; // ovf_count of the last finished draw (debug read-back)
+	uint32_t pad;
 	mlv_stats stats;      // accumulated like reference main.c:1228-1246
 };
 
@@ -42,8 +53,9 @@ struct Partition { // sort-first ownership
 };
 
 struct DebugOut {
-	mlv_ref_triangle *tris; // 80 B each
-	float *attrs;           // 36 floats each (9 x float4)
+	mlv_ref_triangle *tris; // 80 B per slot
+	float *attrs;           // 36 floats per slot (9 x float4)
+	uint32_t *slot_key;     // key per slot, 0xffffffff = slot unused
 	float *vs_out;          // 12 floats per vertex
 	mlv_ref_tile_info *infos;
 };
@@ -51,8 +63,8 @@ struct DebugOut {
 struct GeomParams {
 	const uint32_t *ib;
 	const float4 *vb;
-	uint32_t tri_count;
-	uint32_t tri_capacity;
+	uint32_t tri_count;    // T: input triangles == number of direct slots
+	uint32_t ovf_capacity; // overflow slots available
 	float cb[48];
 	TexDesc vs_tex;
 	const uint32_t *rsqrt_lut;
@@ -65,34 +77,34 @@ struct GeomParams {
 	uint4 *tri_cov;
 	uint4 *tri_shade;
 	uint2 *tri_bounds;
+	uint32_t *ovf_key;
 	DebugOut dbg;
-	unsigned long long *scan_state;
 	Counters *ctr;
-	uint32_t ticket_base;
-	uint32_t epoch;
-	uint32_t num_blocks;
 	uint32_t index_count;
 };
 
 struct BinParams {
 	const uint2 *tri_bounds;
+	const uint32_t *ovf_key;
 	uint32_t *bin_count;
-	uint32_t *bin_cursor;
 	const uint32_t *bin_offset;
 	uint32_t *pair_ids;
 	Counters *ctr;
+	uint32_t direct_slots; // T
+	uint32_t num_bins;
 	int wt, ht;
 	Partition part;
 };
 
 struct ScanParams {
 	uint32_t *bin_count;
-	uint32_t *bin_cursor;
 	uint32_t *bin_offset;
 	mlv_ref_compacted_bin *cbins;
 	Counters *ctr;
+	unsigned long long *state_sum, *state_nz;
 	uint32_t num_bins;
 	uint32_t pair_capacity;
+	uint32_t ticket_base, epoch, num_blocks;
 };
 
 struct TileParams {
@@ -103,11 +115,12 @@ struct TileParams {
 	const uint4 *tri_shade;
 	uint4 *fb;
 	float *tile_min;
-	uint32_t *bin_count;
 	Counters *ctr;
 	TexDesc ps_tex;
 	const uint32_t *rsqrt_lut;
 	DebugOut dbg;
+	uint32_t direct_slots; // T
+	uint32_t key_bits;
 	int wt;
 };
 
