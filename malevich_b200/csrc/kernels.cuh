@@ -117,14 +117,13 @@ __device__ __forceinline__ bool setup_triangle(const float4 &c0, const float4 &c
 	// a*(16x) + b*(16y) + c (c = -a*x_i - b*y_i) is bounded by (|a|+|b|) * max(M, 16W, 16H); if twice that stays
 	// below 2^31 no intermediate wraps and the integer edge functions equal the exact ones, so coverage is
 	// confined to the (closed) triangle and hence to [min_bounds, max_bounds].
-	{
-		long long m = max(max(abs((long long)x0), abs((long long)x1)), abs((long long)x2));
-		m = max(m, max(max(abs((long long)y0), abs((long long)y1)), abs((long long)y2)));
-		m = max(m, (long long)max(P.vp_w, P.vp_h) * 16 + 16);
-		long long ab = 0;
+	{ // evaluated in fp32 with a 1 % safety margin (both factors are < 2^26, the products are compared far from their rounding error)
+		const int mi = max(max(max(abs(x0), abs(x1)), abs(x2)), max(max(abs(y0), abs(y1)), abs(y2)));
+		const float m = (float)max(mi, max(P.vp_w, P.vp_h) * 16 + 16);
+		float ab = 0.0f;
 #pragma unroll
-		for(int k = 0; k < 3; ++k) ab = max(ab, abs((long long)S.e[k * 3]) + abs((long long)S.e[k * 3 + 1]));
-		S.nowrap = (m < (1ll << 24)) && (2 * ab * m < (1ll << 31));
+		for(int k = 0; k < 3; ++k) ab = fmaxf(ab, fabsf((float)S.e[k * 3]) + fabsf((float)S.e[k * 3 + 1]));
+		S.nowrap = (mi < (1 << 24)) && (2.0f * ab * m < 2126008811.0f); // 0.99 * 2^31
 	}
 	return true;
 }
@@ -175,55 +174,75 @@ __device__ __forceinline__ bool bins_on_this_rank(const TriSetup &S, const GeomP
 	return false;
 }
 
+// The 144-byte record of one assembled triangle (layouts in mlv_internal.cuh).
+struct TriRecord {
+	uint4 cov[MLV_TRI_COV_U4];
+	float4 shade[MLV_TRI_SHADE_U4];
+};
+
+__device__ __forceinline__ void make_record(TriRecord &R, const TriSetup &S, uint2 pb, const float4 &r1a, const float4 &r1b, const float4 &r1c, float r2a, float r2b, float r2c) {
+	R.cov[0] = make_uint4(S.e[0], S.e[1], S.e[2], S.e[3]);
+	R.cov[1] = make_uint4(S.e[4], S.e[5], S.e[6], S.e[7]);
+	R.cov[2] = make_uint4(S.e[8], __float_as_uint(S.max_depth), pb.x, pb.y);
+	R.shade[0] = make_float4(S.ooa, S.p[0].z, S.p[1].z, S.p[2].z);
+	R.shade[1] = make_float4(S.rw[0], S.rw[1], S.rw[2], r2a);
+	R.shade[2] = r1a;
+	R.shade[3] = r1b;
+	R.shade[4] = r1c;
+	R.shade[5] = make_float4(r2b, r2c, 0.0f, 0.0f);
+}
+
+// reference-layout copies for mlv_debug_read_triangles (debug capture only)
+__device__ __forceinline__ void emit_debug(const GeomParams &P, uint32_t slot, uint32_t key, const TriSetup &S, const float4 &r1a, const float4 &r1b, const float4 &r1c, float r2a,
+                                           float r2b, float r2c) {
+	mlv_ref_triangle t;
+	t.p_attributes = 0;
+	t.min_bounds[0] = S.minx;
+	t.min_bounds[1] = S.miny;
+	t.max_bounds[0] = S.maxx;
+	t.max_bounds[1] = S.maxy;
+#pragma unroll
+	for(int k = 0; k < 3; ++k) {
+		t.edges[k][0] = S.e[k * 3 + 0];
+		t.edges[k][1] = S.e[k * 3 + 1];
+		t.edges[k][2] = S.e[k * 3 + 2];
+	}
+	t.reciprocal_ws[0] = S.rw[0];
+	t.reciprocal_ws[1] = S.rw[1];
+	t.reciprocal_ws[2] = S.rw[2];
+	t.one_over_area = S.ooa;
+	t.max_depth = S.max_depth;
+	P.dbg.tris[slot] = t;
+	float4 *a = reinterpret_cast<float4 *>(P.dbg.attrs + (size_t)slot * 36);
+	a[0] = S.p[0];
+	a[1] = r1a;
+	a[2] = make_float4(r2a, 0.0f, 0.0f, 0.0f);
+	a[3] = S.p[1];
+	a[4] = r1b;
+	a[5] = make_float4(r2b, 0.0f, 0.0f, 0.0f);
+	a[6] = S.p[2];
+	a[7] = r1c;
+	a[8] = make_float4(r2c, 0.0f, 0.0f, 0.0f);
+	P.dbg.slot_key[slot] = key;
+}
+
+// Straight (uncoalesced) emission, used by the clipping slow path only.
 __device__ __forceinline__ void emit_triangle(const GeomParams &P, uint32_t slot, uint32_t key, const TriSetup &S, const float4 &r1a, const float4 &r1b, const float4 &r1c,
                                               float r2a, float r2b, float r2c) {
 	const bool owned = bins_on_this_rank(S, P);
 	const uint2 pb = pack_bounds(S);
 	P.tri_bounds[slot] = owned ? pb : make_uint2(MLV_BOUNDS_EMPTY, 0u);
 	if(owned) {
+		TriRecord R;
+		make_record(R, S, pb, r1a, r1b, r1c, r2a, r2b, r2c);
 		uint4 *cov = P.tri_cov + (size_t)slot * MLV_TRI_COV_U4;
-		cov[0] = make_uint4(S.e[0], S.e[1], S.e[2], S.e[3]);
-		cov[1] = make_uint4(S.e[4], S.e[5], S.e[6], S.e[7]);
-		cov[2] = make_uint4(S.e[8], __float_as_uint(S.max_depth), pb.x, pb.y);
 		float4 *sh = reinterpret_cast<float4 *>(P.tri_shade + (size_t)slot * MLV_TRI_SHADE_U4);
-		sh[0] = make_float4(S.ooa, S.p[0].z, S.p[1].z, S.p[2].z);
-		sh[1] = make_float4(S.rw[0], S.rw[1], S.rw[2], r2a);
-		sh[2] = r1a;
-		sh[3] = r1b;
-		sh[4] = r1c;
-		sh[5] = make_float4(r2b, r2c, 0.0f, 0.0f);
-	}
-	if(P.dbg.tris) { // reference-layout copies for mlv_debug_read_triangles
-		mlv_ref_triangle t;
-		t.p_attributes = 0;
-		t.min_bounds[0] = S.minx;
-		t.min_bounds[1] = S.miny;
-		t.max_bounds[0] = S.maxx;
-		t.max_bounds[1] = S.maxy;
 #pragma unroll
-		for(int k = 0; k < 3; ++k) {
-			t.edges[k][0] = S.e[k * 3 + 0];
-			t.edges[k][1] = S.e[k * 3 + 1];
-			t.edges[k][2] = S.e[k * 3 + 2];
-		}
-		t.reciprocal_ws[0] = S.rw[0];
-		t.reciprocal_ws[1] = S.rw[1];
-		t.reciprocal_ws[2] = S.rw[2];
-		t.one_over_area = S.ooa;
-		t.max_depth = S.max_depth;
-		P.dbg.tris[slot] = t;
-		float4 *a = reinterpret_cast<float4 *>(P.dbg.attrs + (size_t)slot * 36);
-		a[0] = S.p[0];
-		a[1] = r1a;
-		a[2] = make_float4(r2a, 0.0f, 0.0f, 0.0f);
-		a[3] = S.p[1];
-		a[4] = r1b;
-		a[5] = make_float4(r2b, 0.0f, 0.0f, 0.0f);
-		a[6] = S.p[2];
-		a[7] = r1c;
-		a[8] = make_float4(r2c, 0.0f, 0.0f, 0.0f);
-		P.dbg.slot_key[slot] = key;
+		for(int i = 0; i < MLV_TRI_COV_U4; ++i) cov[i] = R.cov[i];
+#pragma unroll
+		for(int i = 0; i < MLV_TRI_SHADE_U4; ++i) sh[i] = R.shade[i];
 	}
+	if(P.dbg.tris) emit_debug(P, slot, key, S, r1a, r1b, r1c, r2a, r2b, r2c);
 }
 
 // Slow path: clipper (main.c:649-660) + fan triangulation (main.c:797). The fan triangles take consecutive
@@ -273,9 +292,17 @@ __device__ __noinline__ uint32_t clip_and_emit(const GeomParams &P, uint32_t t, 
 #define MLV_GEOM_THREADS 256
 
 template <int VS, bool INDEXED>
-__global__ void __launch_bounds__(MLV_GEOM_THREADS) k_geom(const GeomParams P) {
+__global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_constant__ GeomParams P) {
+	// Records are staged per warp in shared memory and written out as contiguous 512-byte rows: the 32 direct
+	// slots of a warp are adjacent in HBM, so the warp stores 1536 B of TriCov and 3072 B of TriShade with fully
+	// coalesced 128-bit stores instead of 32 scattered 16-byte pieces per instruction.
+	__shared__ uint4 s_stage[MLV_GEOM_THREADS / 32][32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)];
 	const uint32_t t = blockIdx.x * MLV_GEOM_THREADS + threadIdx.x;
+	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 	uint32_t emitted = 0;
+	bool needs_clip = false;
+	bool staged = false; // this lane has a record for its direct slot t
+	uint2 bounds = make_uint2(MLV_BOUNDS_EMPTY, 0u);
 	if(t < P.tri_count) {
 		// ---- input assembler (main.c:662-696): index fetch + 32-byte vertex fetch as two 128-bit loads
 		uint32_t vi0, vi1, vi2;
@@ -315,27 +342,91 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS) k_geom(const GeomParams P) {
 			if(inside) {
 				TriSetup S;
 				if(setup_triangle(a, b, c, P, S)) {
-					emit_triangle(P, t, t << 3, S, v0.r1, v1.r1, v2.r1, v0.r2x, v1.r2x, v2.r2x);
 					direct = true;
 					emitted = 1u;
+					if(bins_on_this_rank(S, P)) {
+						bounds = pack_bounds(S);
+						staged = true;
+						TriRecord R;
+						make_record(R, S, bounds, v0.r1, v1.r1, v2.r1, v0.r2x, v1.r2x, v2.r2x);
+						uint4 *st = s_stage[warp];
+#pragma unroll
+						for(int i = 0; i < MLV_TRI_COV_U4; ++i) st[lane * MLV_TRI_COV_U4 + i] = R.cov[i];
+#pragma unroll
+						for(int i = 0; i < MLV_TRI_SHADE_U4; ++i)
+							st[32 * MLV_TRI_COV_U4 + lane * MLV_TRI_SHADE_U4 + i] = make_uint4(__float_as_uint(R.shade[i].x), __float_as_uint(R.shade[i].y), __float_as_uint(R.shade[i].z), __float_as_uint(R.shade[i].w));
+					}
+					if(P.dbg.tris) emit_debug(P, t, t << 3, S, v0.r1, v1.r1, v2.r1, v0.r2x, v1.r2x, v2.r2x);
 				}
 			} else {
-				emitted = clip_and_emit(P, t, v0, v1, v2);
+				needs_clip = true;
 			}
 		}
-		if(!direct) {
-			P.tri_bounds[t] = make_uint2(MLV_BOUNDS_EMPTY, 0u);
-			if(P.dbg.slot_key) P.dbg.slot_key[t] = 0xffffffffu;
+		if(!direct && P.dbg.slot_key) P.dbg.slot_key[t] = 0xffffffffu;
+		P.tri_bounds[t] = bounds;
+	}
+	// ---- triangles that need the clipper are queued for k_geom_clip (one warp-aggregated atomic): the slow path
+	// would otherwise stall the 31 other lanes of the warp for many times the cost of the fast path
+	{
+		const uint32_t cmask = __ballot_sync(0xffffffffu, needs_clip);
+		if(cmask) {
+			uint32_t base = 0;
+			if(lane == 0) base = atomicAdd(&P.ctr->clip_count, (uint32_t)__popc(cmask));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if(needs_clip) P.clip_queue[base + __popc(cmask & ((1u << lane) - 1u))] = t;
+		}
+	}
+	// ---- coalesced write-out of the staged records
+	__syncwarp();
+	const uint32_t valid = __ballot_sync(0xffffffffu, staged);
+	if(valid) {
+		const uint4 *st = s_stage[warp];
+		const size_t slot0 = (size_t)(t - lane);
+		uint4 *cov = P.tri_cov + slot0 * MLV_TRI_COV_U4;
+		uint4 *sh = P.tri_shade + slot0 * MLV_TRI_SHADE_U4;
+#pragma unroll
+		for(int i = 0; i < MLV_TRI_COV_U4; ++i) {
+			const uint32_t chunk = i * 32 + lane;
+			if((valid >> (chunk / MLV_TRI_COV_U4)) & 1u) cov[chunk] = st[chunk];
+		}
+#pragma unroll
+		for(int i = 0; i < MLV_TRI_SHADE_U4; ++i) {
+			const uint32_t chunk = i * 32 + lane;
+			if((valid >> (chunk / MLV_TRI_SHADE_U4)) & 1u) sh[chunk] = st[32 * MLV_TRI_COV_U4 + chunk];
 		}
 	}
 	// ---- stats (main.c:1228-1238): one atomic per warp
 #pragma unroll
 	for(int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
-	if(lane_id() == 0 && emitted) atomicAdd(&P.ctr->draw_tris, emitted);
+	if(lane == 0 && emitted) atomicAdd(&P.ctr->draw_tris, emitted);
 	if(t == 0) {
 		P.ctr->stats.vertex_count += P.index_count;
 		P.ctr->stats.input_triangle_count += P.tri_count;
 	}
+}
+
+// Clipping pass: one thread per queued input triangle (dense, unlike the sparse occurrences inside k_geom's warps).
+// Re-runs input assembly + vertex shader for the triangle, clips, and emits the fan into overflow slots.
+template <int VS, bool INDEXED>
+__global__ void __launch_bounds__(128) k_geom_clip(const __grid_constant__ GeomParams P) {
+	const uint32_t n = P.ctr->clip_count;
+	uint32_t emitted = 0;
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t t = P.clip_queue[i];
+		uint32_t vi0 = 3u * t, vi1 = 3u * t + 1u, vi2 = 3u * t + 2u;
+		if(INDEXED) {
+			vi0 = __ldg(P.ib + vi0);
+			vi1 = __ldg(P.ib + vi1);
+			vi2 = __ldg(P.ib + vi2);
+		}
+		const VsOut v0 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi0), __ldg(P.vb + 2 * (size_t)vi0 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
+		const VsOut v1 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi1), __ldg(P.vb + 2 * (size_t)vi1 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
+		const VsOut v2 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi2), __ldg(P.vb + 2 * (size_t)vi2 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
+		emitted += clip_and_emit(P, t, v0, v1, v2);
+	}
+#pragma unroll
+	for(int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
+	if(lane_id() == 0 && emitted) atomicAdd(&P.ctr->draw_tris, emitted);
 }
 
 // =================================================================================================
@@ -348,7 +439,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS) k_geom(const GeomParams P) {
 // when it finishes); the per-bin order this leaves is arbitrary and is restored to ascending key (= the
 // reference's ascending triangle id) by k_tile before use.
 template <bool FILL>
-__global__ void __launch_bounds__(256) k_bin(const BinParams P, uint32_t pair_capacity) {
+__global__ void __launch_bounds__(256) k_bin(const __grid_constant__ BinParams P, uint32_t pair_capacity) {
 	const uint32_t n = P.direct_slots + P.ctr->ovf_count;
 	if(FILL && P.ctr->pair_total > pair_capacity) { // skipped draw: drain the counters the count pass built
 		for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.num_bins; i += gridDim.x * blockDim.x) P.bin_count[i] = 0u;
@@ -458,7 +549,7 @@ __device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long lo
 // (main.c:937-974), stats (main.c:1245-1246). One bin per thread, 1024 bins per CTA; warp 0 resolves the
 // triangle-count prefix and warp 1 the non-empty-bin prefix concurrently.
 #define MLV_SCAN_THREADS 1024
-__global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const ScanParams P) {
+__global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_constant__ ScanParams P) {
 	__shared__ uint32_t s_tile;
 	__shared__ uint32_t s_sum[32], s_nz[32];
 	__shared__ uint32_t s_excl[2];
@@ -673,7 +764,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const TileParams &P, uint32_t ke
 #define MLV_TILE_THREADS 256
 
 template <int PS>
-__global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const TileParams P, uint32_t pair_capacity) {
+__global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant__ TileParams P, uint32_t pair_capacity) {
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	if(blockIdx.x == 0 && threadIdx.x == 0) { // every earlier kernel of this draw is done with these; re-arm them for the next draw
@@ -681,6 +772,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const TileParams P, u
 		P.ctr->draw_tris = 0u;
 		P.ctr->last_ovf_count = P.ctr->ovf_count;
 		P.ctr->ovf_count = 0u;
+		P.ctr->clip_count = 0u;
 	}
 	if(P.ctr->pair_total > pair_capacity) return; // draw skipped, MLV_FLAG_PAIR_OVERFLOW is set
 	const uint32_t n_cbins = P.ctr->n_cbins;

@@ -67,7 +67,7 @@ struct mlv_device {
 	uint64_t pair_capacity;
 	uint4 *tri_cov, *tri_shade;
 	uint2 *tri_bounds;
-	uint32_t *ovf_key;
+	uint32_t *ovf_key, *clip_queue;
 	uint32_t tri_capacity; // slots (direct + overflow)
 	unsigned long long *scan_state; // 2 x scan_blocks look-back words
 	uint32_t scan_blocks;
@@ -234,7 +234,7 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(!dev) return;
 	cudaSetDevice(dev->cuda_dev);
 	if(dev->stream) cudaStreamSynchronize(dev->stream);
-	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->ovf_key,
+	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->ovf_key, dev->clip_queue,
 		             dev->scan_state, dev->ctr, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
@@ -440,6 +440,11 @@ static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks,
 	if(indexed) k_geom<VS, true><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
 	else k_geom<VS, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
 }
+template <int VS>
+static void launch_geom_clip(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed) {
+	if(indexed) k_geom_clip<VS, true><<<nblocks, 128, 0, dev->stream>>>(gp);
+	else k_geom_clip<VS, false><<<nblocks, 128, 0, dev->stream>>>(gp);
+}
 
 static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	if(int rc = use_device(dev)) return rc;
@@ -481,6 +486,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 			CUDA_TRY(regrow(&dev->tri_shade, (size_t)cap * MLV_TRI_SHADE_U4));
 			CUDA_TRY(regrow(&dev->tri_bounds, (size_t)cap));
 			CUDA_TRY(regrow(&dev->ovf_key, (size_t)cap));
+			CUDA_TRY(regrow(&dev->clip_queue, (size_t)cap));
 			dev->tri_capacity = cap;
 		}
 		if(debug) {
@@ -536,6 +542,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	gp.tri_shade = dev->tri_shade;
 	gp.tri_bounds = dev->tri_bounds;
 	gp.ovf_key = dev->ovf_key;
+	gp.clip_queue = dev->clip_queue;
 	if(debug) gp.dbg = dev->dbg;
 	gp.ctr = dev->ctr;
 	gp.index_count = count;
@@ -548,6 +555,18 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 		default: launch_geom<3>(dev, gp, nblocks, indexed); break;
 	}
 	if(int rc = check_launch(dev, "k_geom")) return rc;
+	{ // clipping pass over the (device-side) queue; a modest persistent grid, most draws queue few or no triangles
+		uint32_t cb = (T + 127u) / 128u;
+		if(cb > 148u * 4u) cb = 148u * 4u;
+		prof_pre(dev, MLV_STAGE_GEOMETRY);
+		switch(dev->vs_id) {
+			case MLV_VS_PASSTHROUGH: launch_geom_clip<0>(dev, gp, cb, indexed); break;
+			case MLV_VS_BASIC: launch_geom_clip<1>(dev, gp, cb, indexed); break;
+			case MLV_VS_VERTEX_LIGHTING: launch_geom_clip<2>(dev, gp, cb, indexed); break;
+			default: launch_geom_clip<3>(dev, gp, cb, indexed); break;
+		}
+		if(int rc = check_launch(dev, "k_geom_clip")) return rc;
+	}
 
 	BinParams bp;
 	memset(&bp, 0, sizeof(bp));

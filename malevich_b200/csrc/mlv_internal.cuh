@@ -43,7 +43,7 @@ struct Counters {
 	uint32_t ticket;      // monotonically increasing block ticket (look-back scans)
 	uint32_t draw_tris;   // assembled triangles of the current draw
 	uint32_t last_ovf_count; // ovf_count of the last finished draw (debug read-back)
-	uint32_t pad;
+	uint32_t clip_count;  // input triangles queued for k_geom_clip in the current draw (reset by k_tile)
 	mlv_stats stats;      // accumulated like reference main.c:1228-1246
 };
 
@@ -78,6 +78,7 @@ struct GeomParams {
 	uint4 *tri_shade;
 	uint2 *tri_bounds;
 	uint32_t *ovf_key;
+	uint32_t *clip_queue;
 	DebugOut dbg;
 	Counters *ctr;
 	uint32_t index_count;

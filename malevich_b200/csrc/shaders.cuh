@@ -181,8 +181,14 @@ __device__ __forceinline__ float tone_map(float c) {
 
 // f256_srgb_from_linear_approx (math.h:419-422): max(1.055*pow(c, 0.416666667) + (-0.055), 0); _mm256_max_ps
 // returns its second operand when the first is NaN.
+//
+// The reference evaluates pow through Intel SVML (un-vendored, "parity unpinned"); the oracle substitutes glibc's
+// powf. Here pow(c, y) = ex2(y * lg2(c)) on the SFU (MUFU.LG2 / MUFU.EX2): relative error ~3e-7, i.e. < 1e-4 of
+// one 8-bit colour step, far inside the colour tolerance, and ~25x fewer instructions than libdevice powf --
+// pow is the hottest arithmetic of k_tile (3 per shaded pixel). c >= 0 always (bilinear mix of u8 texels);
+// c == 0 gives lg2 = -inf, ex2(-inf) = 0 like powf(0, y).
 __device__ __forceinline__ float srgb_from_linear_approx(float c) {
-	const float v = (float)1.055 * powf(c, (float)0.416666667) + (float)-0.055;
+	const float v = (float)1.055 * __powf(c, (float)0.416666667) + (float)-0.055;
 	return (v > 0.0f) ? v : 0.0f;
 }
 
