@@ -4,7 +4,7 @@
 //   k_geom<VS>   input assembler + vertex shader + primitive assembly     (main.c:662-913)
 //                fused, one thread per input triangle, no inter-thread dependency: triangles are named by
 //                order-preserving keys instead of compacted ids (see mlv_internal.cuh)
-//   k_bin<FILL>  binner passes 1 and 2                                    (main.c:924-962)
+//   k_bin_big / k_bin_fill  binner passes 1 and 2 (pass 1 of small triangles is fused into k_geom) (main.c:924-962)
 //   k_bin_scan   binner exclusive scan + compaction of non-empty bins     (main.c:937-974), multi-CTA
 //                single pass with decoupled look-back
 //   k_tile<PS>   rasterizer + Hi-Z + early-Z + pixel shader + output merger (main.c:983-1189)
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_clear(uint4 *__restrict__ fb, float *__
 		uint2 *p = reinterpret_cast<uint2 *>(fb + i);
 		p[1] = make_uint2(d, d);
 	}
-	if((mode & 2) && (i & 31u) == 0) tile_min[i >> 5] = 0.0f;
+	if((mode & 2) && (i & 31u) == 0) tile_min[i >> 5] = __uint_as_float(MLV_TILE_MIN_CLEARED); // == 0.0 (main.c:1212-1214), tagged "not refreshed yet"
 }
 
 // =================================================================================================
@@ -164,14 +164,60 @@ __device__ __forceinline__ uint2 pack_bounds(const TriSetup &S) {
 	                  (uint32_t)(S.maxx & 0xffff) | ((uint32_t)(S.maxy & 0xffff) << 16));
 }
 
-// Does the tile rectangle the binner derives from the bounds (main.c:927-928) touch a tile row this rank owns?
-__device__ __forceinline__ bool bins_on_this_rank(const TriSetup &S, const GeomParams &P) {
-	const int tx0 = max(S.minx / 8, 0), ty0 = max(S.miny / 8, 0);
-	const int tx1 = min(S.maxx / 8, P.wt - 1), ty1 = min(S.maxy / 8, P.ht - 1);
-	if(tx0 > tx1) return false;
-	for(int ty = ty0; ty <= ty1; ++ty)
-		if(P.part.owns_row(ty)) return true;
-	return false;
+// Tile rectangle exactly as the binner derives it from the pixel bounds (main.c:927-928), C division.
+struct TileRect {
+	int tx0, ty0, tx1, ty1;
+	__device__ __forceinline__ int w() const { return max(tx1 - tx0 + 1, 0); }
+	__device__ __forceinline__ int h() const { return max(ty1 - ty0 + 1, 0); }
+};
+__device__ __forceinline__ TileRect tile_rect(int minx, int miny, int maxx, int maxy, int wt, int ht) {
+	TileRect r;
+	r.tx0 = max(minx / 8, 0);
+	r.ty0 = max(miny / 8, 0);
+	r.tx1 = min(maxx / 8, wt - 1);
+	r.ty1 = min(maxy / 8, ht - 1);
+	return r;
+}
+
+// Hi-Z (main.c:1003-1010) decides per (triangle, tile) pair from values that are final before the draw starts
+// (tile minima come from previous draws only, N3), so the test can run at binning time: a rejected pair is
+// counted for Stats and marks its bin as touched, but is never stored, sorted or rasterized. keep_all (debug
+// capture) disables this so the lists hold every pair like the reference's.
+__device__ __forceinline__ bool hiz_rejects(float max_depth, const float *__restrict__ tile_min, uint32_t bin, bool keep_all) {
+	return !keep_all && (max_depth < __ldg(tile_min + bin));
+}
+
+// Pass 1 of the binner (main.c:924-936) for one triangle with a small tile rectangle, fused into geometry.
+// Returns: pairs = (triangle, tile) pairs on this rank, live = at least one pair survives Hi-Z,
+// big = more than 8 tiles, left to k_bin_big (cooperative expansion).
+struct BinTally {
+	uint32_t pairs;
+	bool live, big;
+};
+__device__ __forceinline__ BinTally count_bins(const GeomParams &P, const TriSetup &S) {
+	BinTally r = { 0u, false, false };
+	const TileRect tr = tile_rect(S.minx, S.miny, S.maxx, S.maxy, P.wt, P.ht);
+	const int cnt = tr.w() * tr.h();
+	if(cnt <= 0) return r;
+	if(cnt > 8) {
+		for(int ty = tr.ty0; ty <= tr.ty1 && !r.live; ++ty) r.live = P.part.owns_row(ty);
+		r.big = r.live;
+		return r;
+	}
+	for(int ty = tr.ty0; ty <= tr.ty1; ++ty) {
+		if(!P.part.owns_row(ty)) continue;
+		for(int tx = tr.tx0; tx <= tr.tx1; ++tx) {
+			const uint32_t bin = (uint32_t)(ty * P.wt + tx);
+			++r.pairs;
+			if(hiz_rejects(S.max_depth, P.tile_min, bin, P.keep_all)) {
+				atomicOr(P.bin_count + bin, MLV_TOUCHED);
+			} else {
+				atomicAdd(P.bin_count + bin, 1u);
+				r.live = true;
+			}
+		}
+	}
+	return r;
 }
 
 // The 144-byte record of one assembled triangle (layouts in mlv_internal.cuh).
@@ -226,13 +272,13 @@ __device__ __forceinline__ void emit_debug(const GeomParams &P, uint32_t slot, u
 	P.dbg.slot_key[slot] = key;
 }
 
-// Straight (uncoalesced) emission, used by the clipping slow path only.
-__device__ __forceinline__ void emit_triangle(const GeomParams &P, uint32_t slot, uint32_t key, const TriSetup &S, const float4 &r1a, const float4 &r1b, const float4 &r1c,
-                                              float r2a, float r2b, float r2c) {
-	const bool owned = bins_on_this_rank(S, P);
+// Straight (uncoalesced) emission, used by the clipping pass only. Returns the pairs counted for Stats.
+__device__ __forceinline__ uint32_t emit_triangle(const GeomParams &P, uint32_t slot, uint32_t key, const TriSetup &S, const float4 &r1a, const float4 &r1b, const float4 &r1c,
+                                                  float r2a, float r2b, float r2c) {
+	const BinTally tally = count_bins(P, S);
 	const uint2 pb = pack_bounds(S);
-	P.tri_bounds[slot] = owned ? pb : make_uint2(MLV_BOUNDS_EMPTY, 0u);
-	if(owned) {
+	P.tri_bounds[slot] = tally.live ? make_uint4(pb.x, pb.y, __float_as_uint(S.max_depth), key) : make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, key);
+	if(tally.live) {
 		TriRecord R;
 		make_record(R, S, pb, r1a, r1b, r1c, r2a, r2b, r2c);
 		uint4 *cov = P.tri_cov + (size_t)slot * MLV_TRI_COV_U4;
@@ -241,13 +287,15 @@ __device__ __forceinline__ void emit_triangle(const GeomParams &P, uint32_t slot
 		for(int i = 0; i < MLV_TRI_COV_U4; ++i) cov[i] = R.cov[i];
 #pragma unroll
 		for(int i = 0; i < MLV_TRI_SHADE_U4; ++i) sh[i] = R.shade[i];
+		if(tally.big) P.big_queue[atomicAdd(&P.ctr->big_count, 1u)] = slot;
 	}
 	if(P.dbg.tris) emit_debug(P, slot, key, S, r1a, r1b, r1c, r2a, r2b, r2c);
+	return tally.pairs;
 }
 
-// Slow path: clipper (main.c:649-660) + fan triangulation (main.c:797). The fan triangles take consecutive
-// overflow slots; slot t becomes a redirect to them. Returns the number of assembled triangles.
-__device__ __noinline__ uint32_t clip_and_emit(const GeomParams &P, uint32_t t, const VsOut &v0, const VsOut &v1, const VsOut &v2) {
+// Clipper (main.c:649-660) + fan triangulation (main.c:797). The fan triangles take consecutive overflow slots;
+// slot t becomes a redirect to them. Returns the number of assembled triangles, adds the pairs to `pairs`.
+__device__ __noinline__ uint32_t clip_and_emit(const GeomParams &P, uint32_t t, const VsOut &v0, const VsOut &v1, const VsOut &v2, uint32_t &pairs) {
 	VsOut poly[16];
 	poly[0] = v0;
 	poly[1] = v1;
@@ -276,17 +324,29 @@ __device__ __noinline__ uint32_t clip_and_emit(const GeomParams &P, uint32_t t, 
 	for(int j = 0; j < fan; ++j) {
 		const uint32_t slot = P.tri_count + base + (uint32_t)j;
 		const uint32_t key = (t << 3) | (uint32_t)j;
-		P.ovf_key[base + j] = key;
 		TriSetup S;
 		if(setup_triangle(poly[0].r0, poly[j + 1].r0, poly[j + 2].r0, P, S)) {
-			emit_triangle(P, slot, key, S, poly[0].r1, poly[j + 1].r1, poly[j + 2].r1, poly[0].r2x, poly[j + 1].r2x, poly[j + 2].r2x);
+			pairs += emit_triangle(P, slot, key, S, poly[0].r1, poly[j + 1].r1, poly[j + 2].r1, poly[0].r2x, poly[j + 1].r2x, poly[j + 2].r2x);
 			++emitted;
 		} else {
-			P.tri_bounds[slot] = make_uint2(MLV_BOUNDS_EMPTY, 0u);
+			P.tri_bounds[slot] = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, key);
 			if(P.dbg.slot_key) P.dbg.slot_key[slot] = 0xffffffffu;
 		}
 	}
 	return emitted;
+}
+
+// Per-draw Stats contributions (main.c:1228-1246): one atomic per warp and counter.
+__device__ __forceinline__ void tally_stats(Counters *ctr, uint32_t emitted, uint32_t pairs) {
+#pragma unroll
+	for(int d = 16; d > 0; d >>= 1) {
+		emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
+		pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
+	}
+	if(lane_id() == 0) {
+		if(emitted) atomicAdd(&ctr->draw_tris, emitted);
+		if(pairs) atomicAdd(&ctr->draw_pairs_all, pairs);
+	}
 }
 
 #define MLV_GEOM_THREADS 256
@@ -299,10 +359,10 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 	__shared__ uint4 s_stage[MLV_GEOM_THREADS / 32][32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)];
 	const uint32_t t = blockIdx.x * MLV_GEOM_THREADS + threadIdx.x;
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-	uint32_t emitted = 0;
-	bool needs_clip = false;
+	uint32_t emitted = 0, pairs = 0;
+	bool needs_clip = false, is_big = false;
 	bool staged = false; // this lane has a record for its direct slot t
-	uint2 bounds = make_uint2(MLV_BOUNDS_EMPTY, 0u);
+	uint4 bounds = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, t << 3);
 	if(t < P.tri_count) {
 		// ---- input assembler (main.c:662-696): index fetch + 32-byte vertex fetch as two 128-bit loads
 		uint32_t vi0, vi1, vi2;
@@ -344,11 +404,16 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 				if(setup_triangle(a, b, c, P, S)) {
 					direct = true;
 					emitted = 1u;
-					if(bins_on_this_rank(S, P)) {
-						bounds = pack_bounds(S);
+					// ---- binner pass 1 + Hi-Z for this triangle; a triangle hidden in every tile it touches writes no record
+					const BinTally tally = count_bins(P, S);
+					pairs = tally.pairs;
+					is_big = tally.big;
+					if(tally.live) {
+						const uint2 pb = pack_bounds(S);
+						bounds = make_uint4(pb.x, pb.y, __float_as_uint(S.max_depth), t << 3);
 						staged = true;
 						TriRecord R;
-						make_record(R, S, bounds, v0.r1, v1.r1, v2.r1, v0.r2x, v1.r2x, v2.r2x);
+						make_record(R, S, pb, v0.r1, v1.r1, v2.r1, v0.r2x, v1.r2x, v2.r2x);
 						uint4 *st = s_stage[warp];
 #pragma unroll
 						for(int i = 0; i < MLV_TRI_COV_U4; ++i) st[lane * MLV_TRI_COV_U4 + i] = R.cov[i];
@@ -365,8 +430,8 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 		if(!direct && P.dbg.slot_key) P.dbg.slot_key[t] = 0xffffffffu;
 		P.tri_bounds[t] = bounds;
 	}
-	// ---- triangles that need the clipper are queued for k_geom_clip (one warp-aggregated atomic): the slow path
-	// would otherwise stall the 31 other lanes of the warp for many times the cost of the fast path
+	// ---- triangles that need the clipper are queued for k_geom_clip, triangles with large tile rectangles for
+	// k_bin_big (one warp-aggregated atomic each): either slow path would otherwise stall the 31 other lanes
 	{
 		const uint32_t cmask = __ballot_sync(0xffffffffu, needs_clip);
 		if(cmask) {
@@ -374,6 +439,13 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 			if(lane == 0) base = atomicAdd(&P.ctr->clip_count, (uint32_t)__popc(cmask));
 			base = __shfl_sync(0xffffffffu, base, 0);
 			if(needs_clip) P.clip_queue[base + __popc(cmask & ((1u << lane) - 1u))] = t;
+		}
+		const uint32_t bmask = __ballot_sync(0xffffffffu, is_big);
+		if(bmask) {
+			uint32_t base = 0;
+			if(lane == 0) base = atomicAdd(&P.ctr->big_count, (uint32_t)__popc(bmask));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if(is_big) P.big_queue[base + __popc(bmask & ((1u << lane) - 1u))] = t;
 		}
 	}
 	// ---- coalesced write-out of the staged records
@@ -395,10 +467,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 			if((valid >> (chunk / MLV_TRI_SHADE_U4)) & 1u) sh[chunk] = st[32 * MLV_TRI_COV_U4 + chunk];
 		}
 	}
-	// ---- stats (main.c:1228-1238): one atomic per warp
-#pragma unroll
-	for(int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
-	if(lane == 0 && emitted) atomicAdd(&P.ctr->draw_tris, emitted);
+	tally_stats(P.ctr, emitted, pairs);
 	if(t == 0) {
 		P.ctr->stats.vertex_count += P.index_count;
 		P.ctr->stats.input_triangle_count += P.tri_count;
@@ -410,7 +479,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 template <int VS, bool INDEXED>
 __global__ void __launch_bounds__(128) k_geom_clip(const __grid_constant__ GeomParams P) {
 	const uint32_t n = P.ctr->clip_count;
-	uint32_t emitted = 0;
+	uint32_t emitted = 0, pairs = 0;
 	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const uint32_t t = P.clip_queue[i];
 		uint32_t vi0 = 3u * t, vi1 = 3u * t + 1u, vi2 = 3u * t + 2u;
@@ -422,61 +491,77 @@ __global__ void __launch_bounds__(128) k_geom_clip(const __grid_constant__ GeomP
 		const VsOut v0 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi0), __ldg(P.vb + 2 * (size_t)vi0 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
 		const VsOut v1 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi1), __ldg(P.vb + 2 * (size_t)vi1 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
 		const VsOut v2 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi2), __ldg(P.vb + 2 * (size_t)vi2 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
-		emitted += clip_and_emit(P, t, v0, v1, v2);
+		emitted += clip_and_emit(P, t, v0, v1, v2, pairs);
 	}
-#pragma unroll
-	for(int d = 16; d > 0; d >>= 1) emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
-	if(lane_id() == 0 && emitted) atomicAdd(&P.ctr->draw_tris, emitted);
+	tally_stats(P.ctr, emitted, pairs);
 }
 
 // =================================================================================================
 // binner
 // =================================================================================================
 
-// Passes 1 (count) and 2 (fill) of the reference binner (main.c:924-962). One lane per triangle slot;
-// triangles overlapping more than 8 tiles are expanded cooperatively by the whole warp. The fill pass takes
-// list positions by decrementing the counters the count pass built (so they are back to zero for the next draw
-// when it finishes); the per-bin order this leaves is arbitrary and is restored to ascending key (= the
-// reference's ascending triangle id) by k_tile before use.
-template <bool FILL>
-__global__ void __launch_bounds__(256) k_bin(const __grid_constant__ BinParams P, uint32_t pair_capacity) {
-	const uint32_t n = P.direct_slots + P.ctr->ovf_count;
-	if(FILL && P.ctr->pair_total > pair_capacity) { // skipped draw: drain the counters the count pass built
-		for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.num_bins; i += gridDim.x * blockDim.x) P.bin_count[i] = 0u;
-		return;
+struct SlotBounds {
+	TileRect tr;
+	float max_depth;
+	uint32_t key;
+	bool empty;
+};
+__device__ __forceinline__ SlotBounds load_bounds(const uint4 *__restrict__ tri_bounds, uint32_t slot, int wt, int ht) {
+	const uint4 b = __ldg(tri_bounds + slot);
+	SlotBounds s;
+	s.empty = (b.x & 0xffffu) == MLV_BOUNDS_EMPTY;
+	s.tr = tile_rect((int)(b.x & 0xffffu), (int)((b.x >> 16) & 0x7fffu), (int)(short)(b.y & 0xffffu), (int)(short)(b.y >> 16), wt, ht);
+	s.max_depth = __uint_as_float(b.z);
+	s.key = b.w;
+	return s;
+}
+
+// Pass 1 of the binner (main.c:924-936) for the triangles whose tile rectangle holds more than 8 tiles (queued by
+// the geometry kernels): one warp per triangle, lanes stride over the rectangle.
+__global__ void __launch_bounds__(256) k_bin_big(const __grid_constant__ BinParams P) {
+	const uint32_t n = P.ctr->big_count;
+	const uint32_t lane = lane_id();
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	uint32_t pairs = 0;
+	for(uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+		const SlotBounds s = load_bounds(P.tri_bounds, P.big_queue[i], P.wt, P.ht);
+		const int w = s.tr.w(), cnt = w * s.tr.h();
+		for(int k = (int)lane; k < cnt; k += 32) {
+			const int ty = s.tr.ty0 + k / w, tx = s.tr.tx0 + k % w;
+			if(!P.part.owns_row(ty)) continue;
+			const uint32_t bin = (uint32_t)(ty * P.wt + tx);
+			++pairs;
+			if(hiz_rejects(s.max_depth, P.tile_min, bin, P.keep_all)) atomicOr(P.bin_count + bin, MLV_TOUCHED);
+			else atomicAdd(P.bin_count + bin, 1u);
+		}
 	}
+#pragma unroll
+	for(int d = 16; d > 0; d >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
+	if(lane == 0 && pairs) atomicAdd(&P.ctr->draw_pairs_all, pairs);
+}
+
+// Pass 2 of the binner (main.c:950-962): every surviving (triangle, tile) pair takes the next position of its
+// bin's list (atomic on the running offset the scan left in bin_offset). One lane per triangle slot; rectangles
+// of more than 8 tiles are expanded cooperatively by the whole warp. The per-bin order this leaves is arbitrary
+// and is restored to ascending key (= the reference's ascending triangle id) by k_tile before use.
+__global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinParams P, uint32_t pair_capacity) {
+	if(P.ctr->pair_total > pair_capacity) return; // draw skipped, MLV_FLAG_PAIR_OVERFLOW is set
+	const uint32_t n = P.direct_slots + P.ctr->ovf_count;
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	for(uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < n; base += warps * 32u) {
 		const uint32_t slot = base + lane;
-		int tx0 = 1, ty0 = 0, tx1 = 0, ty1 = -1;
-		uint32_t key = 0;
-		if(slot < n) {
-			const uint2 b = __ldg(P.tri_bounds + slot);
-			if((b.x & 0xffffu) != MLV_BOUNDS_EMPTY) { // tile rectangle as the binner derives it (main.c:927-928), C division
-				const int minx = (int)(b.x & 0xffffu), miny = (int)((b.x >> 16) & 0x7fffu);
-				const int maxx = (int)(short)(b.y & 0xffffu), maxy = (int)(short)(b.y >> 16);
-				tx0 = max(minx / 8, 0);
-				ty0 = max(miny / 8, 0);
-				tx1 = min(maxx / 8, P.wt - 1);
-				ty1 = min(maxy / 8, P.ht - 1);
-			}
-			if(FILL) key = (slot < P.direct_slots) ? (slot << 3) : __ldg(P.ovf_key + (slot - P.direct_slots));
-		}
-		const int w = max(tx1 - tx0 + 1, 0), h = max(ty1 - ty0 + 1, 0);
-		const int cnt = w * h;
+		SlotBounds s;
+		s.empty = true;
+		if(slot < n) s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
+		const int w = s.empty ? 0 : s.tr.w(), cnt = s.empty ? 0 : w * s.tr.h();
 		const bool big = cnt > 8;
 		if(cnt > 0 && !big) {
-			for(int ty = ty0; ty <= ty1; ++ty) {
+			for(int ty = s.tr.ty0; ty <= s.tr.ty1; ++ty) {
 				if(!P.part.owns_row(ty)) continue;
-				for(int tx = tx0; tx <= tx1; ++tx) {
+				for(int tx = s.tr.tx0; tx <= s.tr.tx1; ++tx) {
 					const uint32_t bin = (uint32_t)(ty * P.wt + tx);
-					if(FILL) {
-						const uint32_t old = atomicSub(P.bin_count + bin, 1u);
-						P.pair_ids[P.bin_offset[bin] + old - 1u] = key;
-					} else {
-						atomicAdd(P.bin_count + bin, 1u);
-					}
+					if(!hiz_rejects(s.max_depth, P.tile_min, bin, P.keep_all)) P.pair_ids[atomicAdd(P.bin_offset + bin, 1u)] = s.key;
 				}
 			}
 		}
@@ -484,19 +569,15 @@ __global__ void __launch_bounds__(256) k_bin(const __grid_constant__ BinParams P
 		while(bigmask) {
 			const int src = __ffs(bigmask) - 1;
 			bigmask &= bigmask - 1;
-			const int bx0 = __shfl_sync(0xffffffffu, tx0, src), by0 = __shfl_sync(0xffffffffu, ty0, src);
+			const int bx0 = __shfl_sync(0xffffffffu, s.tr.tx0, src), by0 = __shfl_sync(0xffffffffu, s.tr.ty0, src);
 			const int bw = __shfl_sync(0xffffffffu, w, src), bc = __shfl_sync(0xffffffffu, cnt, src);
-			const uint32_t bkey = __shfl_sync(0xffffffffu, key, src);
+			const uint32_t bkey = __shfl_sync(0xffffffffu, s.key, src);
+			const float bdepth = __shfl_sync(0xffffffffu, s.max_depth, src);
 			for(int k = (int)lane; k < bc; k += 32) {
 				const int ty = by0 + k / bw, tx = bx0 + k % bw;
 				if(!P.part.owns_row(ty)) continue;
 				const uint32_t bin = (uint32_t)(ty * P.wt + tx);
-				if(FILL) {
-					const uint32_t old = atomicSub(P.bin_count + bin, 1u);
-					P.pair_ids[P.bin_offset[bin] + old - 1u] = bkey;
-				} else {
-					atomicAdd(P.bin_count + bin, 1u);
-				}
+				if(!hiz_rejects(bdepth, P.tile_min, bin, P.keep_all)) P.pair_ids[atomicAdd(P.bin_offset + bin, 1u)] = bkey;
 			}
 		}
 	}
@@ -545,9 +626,13 @@ __device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long lo
 	return exclusive;
 }
 
-// Exclusive scan of the per-bin counts + compaction of non-empty bins in ascending bin index
-// (main.c:937-974), stats (main.c:1245-1246). One bin per thread, 1024 bins per CTA; warp 0 resolves the
-// triangle-count prefix and warp 1 the non-empty-bin prefix concurrently.
+// Exclusive scan of the per-bin counts + compaction of the bins k_tile has to visit, in ascending bin index
+// (main.c:937-974), Stats (main.c:1245-1246). One bin per thread, 1024 bins per CTA; warp 0 resolves the
+// pair-count prefix and warp 1 the work-list prefix concurrently. A bin is non-empty (counts for Stats, would
+// be in the reference's CompactedBin list) when it was touched at all; it is on the work list when it holds
+// surviving pairs, or when it was touched and its tile minimum still is the clear marker (write_tile refreshes
+// the minimum of every non-empty bin, main.c:589-603 -- for any other fully Hi-Z-rejected bin that refresh
+// would rewrite the value already stored).
 #define MLV_SCAN_THREADS 1024
 __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_constant__ ScanParams P) {
 	__shared__ uint32_t s_tile;
@@ -559,16 +644,24 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 	const uint32_t tile = s_tile;
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 	const uint32_t i = tile * MLV_SCAN_THREADS + threadIdx.x;
-	const uint32_t c = (i < P.num_bins) ? P.bin_count[i] : 0u;
+	const uint32_t raw = (i < P.num_bins) ? P.bin_count[i] : 0u;
+	const uint32_t c = raw & ~MLV_TOUCHED;
+	const bool nonempty = raw != 0u;
+	const bool work = c != 0u || (nonempty && __float_as_uint(P.tile_min[i]) == MLV_TILE_MIN_CLEARED);
+	if(nonempty) P.bin_count[i] = 0u; // ready for the next draw
 	uint32_t incl = c;
 #pragma unroll
 	for(int d = 1; d < 32; d <<= 1) {
 		const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
 		if(lane >= (uint32_t)d) incl += o;
 	}
-	const uint32_t nzmask = __ballot_sync(0xffffffffu, c != 0u);
+	const uint32_t workmask = __ballot_sync(0xffffffffu, work);
+	const uint32_t nemask = __ballot_sync(0xffffffffu, nonempty);
 	if(lane == 31) s_sum[warp] = incl;
-	if(lane == 0) s_nz[warp] = __popc(nzmask);
+	if(lane == 0) {
+		s_nz[warp] = __popc(workmask);
+		if(nemask) atomicAdd(&P.ctr->draw_active_bins, (uint32_t)__popc(nemask));
+	}
 	__syncthreads();
 	if(warp < 2) {
 		const uint32_t v = (warp == 0) ? s_sum[lane] : s_nz[lane];
@@ -587,11 +680,9 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 			const uint32_t total = excl + block_total;
 			if(warp == 0) {
 				P.ctr->pair_total = total;
-				P.ctr->stats.total_triangle_count_in_bins += total;
 				if(total > P.pair_capacity) atomicOr(&P.ctr->error_flags, MLV_FLAG_PAIR_OVERFLOW);
 			} else {
 				P.ctr->n_cbins = total; // k_tile ignores it when the pair arena overflowed
-				P.ctr->stats.active_bin_count += total;
 			}
 		}
 	}
@@ -599,12 +690,12 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 	if(i < P.num_bins) {
 		const uint32_t upto = s_excl[0] + s_sum[warp] + incl - c;
 		P.bin_offset[i] = upto;
-		if(c != 0u) {
+		if(work) {
 			mlv_ref_compacted_bin cb;
 			cb.num_triangles_self = c;
 			cb.num_triangles_upto = upto;
 			cb.bin_index = i;
-			P.cbins[s_excl[1] + s_nz[warp] + __popc(nzmask & ((1u << lane) - 1u))] = cb;
+			P.cbins[s_excl[1] + s_nz[warp] + __popc(workmask & ((1u << lane) - 1u))] = cb;
 		}
 	}
 }
@@ -767,12 +858,14 @@ template <int PS>
 __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant__ TileParams P, uint32_t pair_capacity) {
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-	if(blockIdx.x == 0 && threadIdx.x == 0) { // every earlier kernel of this draw is done with these; re-arm them for the next draw
-		P.ctr->stats.assembled_triangle_count += P.ctr->draw_tris;
-		P.ctr->draw_tris = 0u;
-		P.ctr->last_ovf_count = P.ctr->ovf_count;
-		P.ctr->ovf_count = 0u;
-		P.ctr->clip_count = 0u;
+	if(blockIdx.x == 0 && threadIdx.x == 0) { // every earlier kernel of this draw is done with these: fold them into Stats, re-arm for the next draw
+		Counters *c = P.ctr;
+		c->stats.assembled_triangle_count += c->draw_tris;
+		c->stats.total_triangle_count_in_bins += c->draw_pairs_all;
+		c->stats.active_bin_count += c->draw_active_bins;
+		c->last_ovf_count = c->ovf_count;
+		c->draw_tris = c->draw_pairs_all = c->draw_active_bins = 0u;
+		c->ovf_count = c->clip_count = c->big_count = 0u;
 	}
 	if(P.ctr->pair_total > pair_capacity) return; // draw skipped, MLV_FLAG_PAIR_OVERFLOW is set
 	const uint32_t n_cbins = P.ctr->n_cbins;
@@ -791,6 +884,13 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant
 		uint32_t win0 = MLV_NO_WINNER, win1 = MLV_NO_WINNER;
 		const float tile_min_old = P.tile_min[b]; // get_tile_minimum_depth: previous draws only (N3)
 
+		if(n == 0u) { // touched bin whose pairs were all Hi-Z-rejected at binning time: write_tile's tile-minimum refresh only
+			float m = ref_min_macro(ref_min_macro(1.0f, d0), d1);
+#pragma unroll
+			for(int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, d));
+			if(lane == 0) P.tile_min[b] = m;
+			continue;
+		}
 		uint32_t *ids = P.pair_ids + off;
 		sort_bin_ids(ids, P.pair_tmp + off, n, P.key_bits);
 

@@ -66,8 +66,8 @@ struct mlv_device {
 	uint32_t *pair_ids, *pair_tmp;
 	uint64_t pair_capacity;
 	uint4 *tri_cov, *tri_shade;
-	uint2 *tri_bounds;
-	uint32_t *ovf_key, *clip_queue;
+	uint4 *tri_bounds;
+	uint32_t *clip_queue, *big_queue;
 	uint32_t tri_capacity; // slots (direct + overflow)
 	unsigned long long *scan_state; // 2 x scan_blocks look-back words
 	uint32_t scan_blocks;
@@ -234,7 +234,7 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(!dev) return;
 	cudaSetDevice(dev->cuda_dev);
 	if(dev->stream) cudaStreamSynchronize(dev->stream);
-	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->ovf_key, dev->clip_queue,
+	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue,
 		             dev->scan_state, dev->ctr, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
@@ -485,8 +485,8 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 			CUDA_TRY(regrow(&dev->tri_cov, (size_t)cap * MLV_TRI_COV_U4));
 			CUDA_TRY(regrow(&dev->tri_shade, (size_t)cap * MLV_TRI_SHADE_U4));
 			CUDA_TRY(regrow(&dev->tri_bounds, (size_t)cap));
-			CUDA_TRY(regrow(&dev->ovf_key, (size_t)cap));
 			CUDA_TRY(regrow(&dev->clip_queue, (size_t)cap));
+			CUDA_TRY(regrow(&dev->big_queue, (size_t)cap));
 			dev->tri_capacity = cap;
 		}
 		if(debug) {
@@ -541,8 +541,11 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	gp.tri_cov = dev->tri_cov;
 	gp.tri_shade = dev->tri_shade;
 	gp.tri_bounds = dev->tri_bounds;
-	gp.ovf_key = dev->ovf_key;
 	gp.clip_queue = dev->clip_queue;
+	gp.big_queue = dev->big_queue;
+	gp.bin_count = dev->bin_count;
+	gp.tile_min = dev->tile_min;
+	gp.keep_all = debug;
 	if(debug) gp.dbg = dev->dbg;
 	gp.ctr = dev->ctr;
 	gp.index_count = count;
@@ -571,7 +574,8 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	BinParams bp;
 	memset(&bp, 0, sizeof(bp));
 	bp.tri_bounds = dev->tri_bounds;
-	bp.ovf_key = dev->ovf_key;
+	bp.big_queue = dev->big_queue;
+	bp.tile_min = dev->tile_min;
 	bp.bin_count = dev->bin_count;
 	bp.bin_offset = dev->bin_offset;
 	bp.pair_ids = dev->pair_ids;
@@ -581,11 +585,12 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	bp.wt = dev->wt;
 	bp.ht = dev->ht;
 	bp.part = dev->part;
-	uint32_t bin_blocks = (need_slots + 255u) / 256u;
-	if(bin_blocks > 148u * 16u) bin_blocks = 148u * 16u;
+	bp.keep_all = debug;
+	uint32_t big_blocks = (T + 7u) / 8u; // one warp per queued triangle, grid-stride
+	if(big_blocks > 148u * 4u) big_blocks = 148u * 4u;
 	prof_pre(dev, MLV_STAGE_BIN_COUNT);
-	k_bin<false><<<bin_blocks, 256, 0, dev->stream>>>(bp, (uint32_t)dev->pair_capacity);
-	if(int rc = check_launch(dev, "k_bin<count>")) return rc;
+	k_bin_big<<<big_blocks, 256, 0, dev->stream>>>(bp);
+	if(int rc = check_launch(dev, "k_bin_big")) return rc;
 
 	ScanParams sp;
 	memset(&sp, 0, sizeof(sp));
@@ -595,6 +600,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	sp.ctr = dev->ctr;
 	sp.state_sum = dev->scan_state;
 	sp.state_nz = dev->scan_state + dev->scan_blocks;
+	sp.tile_min = dev->tile_min;
 	sp.num_bins = dev->num_bins;
 	sp.pair_capacity = (uint32_t)dev->pair_capacity;
 	sp.ticket_base = dev->ticket_base;
@@ -605,9 +611,11 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	k_bin_scan<<<dev->scan_blocks, MLV_SCAN_THREADS, 0, dev->stream>>>(sp);
 	if(int rc = check_launch(dev, "k_bin_scan")) return rc;
 
+	uint32_t bin_blocks = (need_slots + 255u) / 256u;
+	if(bin_blocks > 148u * 16u) bin_blocks = 148u * 16u;
 	prof_pre(dev, MLV_STAGE_BIN_FILL);
-	k_bin<true><<<bin_blocks, 256, 0, dev->stream>>>(bp, (uint32_t)dev->pair_capacity);
-	if(int rc = check_launch(dev, "k_bin<fill>")) return rc;
+	k_bin_fill<<<bin_blocks, 256, 0, dev->stream>>>(bp, (uint32_t)dev->pair_capacity);
+	if(int rc = check_launch(dev, "k_bin_fill")) return rc;
 
 	TileParams tp;
 	memset(&tp, 0, sizeof(tp));

@@ -24,7 +24,8 @@ namespace mlv {
 //   TriCov   48 B  { a0,b0,c0,a1 | b1,c1,a2,b2 | c2, max_depth, minx|flags_miny<<16, maxx|maxy<<16 }  coverage + Hi-Z
 //                  redirect:  word 10 == MLV_REDIRECT, word 8 = overflow base
 //   TriShade 96 B  { ooa,z0,z1,z2 | rw0,rw1,rw2,r2x_v0 | r1_v0 | r1_v1 | r1_v2 | r2x_v1,r2x_v2,0,0 }  depth + attributes
-//   bounds    8 B  { minx | (miny|nowrap<<15)<<16, maxx | maxy<<16 } int16 pixel bounds (main.c:888-898); minx == 0x7fff: bins nothing
+//   bounds   16 B  { minx | (miny|nowrap<<15)<<16, maxx | maxy<<16, max_depth, key } int16 pixel bounds (main.c:888-898);
+//                  minx == 0x7fff: bins nothing (culled, redirected, not on this rank, or hidden by Hi-Z in every tile)
 #define MLV_TRI_COV_U4 3
 #define MLV_TRI_SHADE_U4 6
 #define MLV_REDIRECT 0x7ffe7ffeu
@@ -32,6 +33,8 @@ namespace mlv {
 #define MLV_NOWRAP_BIT 0x80000000u /* bit 15 of miny inside word 10 */
 
 #define MLV_NO_WINNER 0xffffffffu
+#define MLV_TOUCHED 0x80000000u          /* bin_count flag: bin is non-empty in the reference's sense but (so far) holds only Hi-Z-rejected pairs */
+#define MLV_TILE_MIN_CLEARED 0x80000000u /* tile_min bit pattern (-0.0f) the depth clear writes: equals 0.0 in every comparison, marks "never refreshed" */
 
 enum { MLV_FLAG_TRI_OVERFLOW = 1u, MLV_FLAG_PAIR_OVERFLOW = 2u };
 
@@ -44,6 +47,10 @@ struct Counters {
 	uint32_t draw_tris;   // assembled triangles of the current draw
 	uint32_t last_ovf_count; // ovf_count of the last finished draw (debug read-back)
 	uint32_t clip_count;  // input triangles queued for k_geom_clip in the current draw (reset by k_tile)
+	uint32_t big_count;   // triangles queued for k_bin_big in the current draw (reset by k_tile)
+	uint32_t draw_pairs_all;   // (triangle,tile) pairs of the current draw including Hi-Z-rejected ones (Stats)
+	uint32_t draw_active_bins; // non-empty bins of the current draw in the reference's sense (Stats)
+	uint32_t pad;
 	mlv_stats stats;      // accumulated like reference main.c:1228-1246
 };
 
@@ -76,25 +83,30 @@ struct GeomParams {
 	Partition part;
 	uint4 *tri_cov;
 	uint4 *tri_shade;
-	uint2 *tri_bounds;
-	uint32_t *ovf_key;
+	uint4 *tri_bounds;
 	uint32_t *clip_queue;
+	uint32_t *big_queue;
+	uint32_t *bin_count;
+	const float *tile_min;
+	bool keep_all; // debug capture: no Hi-Z at binning time, lists hold every pair like the reference's
 	DebugOut dbg;
 	Counters *ctr;
 	uint32_t index_count;
 };
 
 struct BinParams {
-	const uint2 *tri_bounds;
-	const uint32_t *ovf_key;
+	const uint4 *tri_bounds;
+	const uint32_t *big_queue;
+	const float *tile_min;
 	uint32_t *bin_count;
-	const uint32_t *bin_offset;
+	uint32_t *bin_offset;
 	uint32_t *pair_ids;
 	Counters *ctr;
 	uint32_t direct_slots; // T
 	uint32_t num_bins;
 	int wt, ht;
 	Partition part;
+	bool keep_all;
 };
 
 struct ScanParams {
@@ -103,6 +115,7 @@ struct ScanParams {
 	mlv_ref_compacted_bin *cbins;
 	Counters *ctr;
 	unsigned long long *state_sum, *state_nz;
+	const float *tile_min;
 	uint32_t num_bins;
 	uint32_t pair_capacity;
 	uint32_t ticket_base, epoch, num_blocks;
