@@ -139,6 +139,11 @@ __device__ __forceinline__ VsOut lerp_vertex(const VsOut &a, const VsOut &b, flo
 
 // clip_by_plane (main.c:609-647), plane_d = 0
 __device__ __noinline__ int clip_by_plane(VsOut *v, int n, float4 pn) {
+	{ // a plane that has the whole polygon on its inside reproduces the polygon vertex for vertex: skip the copy
+		bool all_in = n > 0;
+		for(int i = 0; i < n; ++i) all_in = all_in && (dot4_serial(pn, v[i].r0) > -0.0f);
+		if(all_in) return n;
+	}
 	VsOut res[16];
 	int nout = 0;
 	float cur = dot4_serial(pn, v[0].r0);
@@ -163,6 +168,8 @@ __device__ __forceinline__ uint2 pack_bounds(const TriSetup &S) {
 	return make_uint2((uint32_t)(S.minx & 0xffff) | ((uint32_t)(S.miny & 0x7fff) << 16) | (S.nowrap ? MLV_NOWRAP_BIT : 0u),
 	                  (uint32_t)(S.maxx & 0xffff) | ((uint32_t)(S.maxy & 0xffff) << 16));
 }
+
+#define MLV_HUGE_TILES 2048 /* tile rectangles larger than this are expanded by the whole grid, not by one warp */
 
 // Tile rectangle exactly as the binner derives it from the pixel bounds (main.c:927-928), C division.
 struct TileRect {
@@ -192,16 +199,17 @@ __device__ __forceinline__ bool hiz_rejects(float max_depth, const float *__rest
 // big = more than 8 tiles, left to k_bin_big (cooperative expansion).
 struct BinTally {
 	uint32_t pairs;
-	bool live, big;
+	bool live, big, huge;
 };
 __device__ __forceinline__ BinTally count_bins(const GeomParams &P, const TriSetup &S) {
-	BinTally r = { 0u, false, false };
+	BinTally r = { 0u, false, false, false };
 	const TileRect tr = tile_rect(S.minx, S.miny, S.maxx, S.maxy, P.wt, P.ht);
 	const int cnt = tr.w() * tr.h();
 	if(cnt <= 0) return r;
 	if(cnt > 8) {
 		for(int ty = tr.ty0; ty <= tr.ty1 && !r.live; ++ty) r.live = P.part.owns_row(ty);
-		r.big = r.live;
+		r.big = r.live && cnt <= MLV_HUGE_TILES;
+		r.huge = r.live && cnt > MLV_HUGE_TILES;
 		return r;
 	}
 	for(int ty = tr.ty0; ty <= tr.ty1; ++ty) {
@@ -288,6 +296,7 @@ __device__ __forceinline__ uint32_t emit_triangle(const GeomParams &P, uint32_t 
 #pragma unroll
 		for(int i = 0; i < MLV_TRI_SHADE_U4; ++i) sh[i] = R.shade[i];
 		if(tally.big) P.big_queue[atomicAdd(&P.ctr->big_count, 1u)] = slot;
+		if(tally.huge) P.huge_queue[atomicAdd(&P.ctr->huge_count, 1u)] = slot;
 	}
 	if(P.dbg.tris) emit_debug(P, slot, key, S, r1a, r1b, r1c, r2a, r2b, r2c);
 	return tally.pairs;
@@ -408,6 +417,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 					const BinTally tally = count_bins(P, S);
 					pairs = tally.pairs;
 					is_big = tally.big;
+					if(tally.huge) P.huge_queue[atomicAdd(&P.ctr->huge_count, 1u)] = t; // rare: sky domes, full-screen quads
 					if(tally.live) {
 						const uint2 pb = pack_bounds(S);
 						bounds = make_uint4(pb.x, pb.y, __float_as_uint(S.max_depth), t << 3);
@@ -517,7 +527,8 @@ __device__ __forceinline__ SlotBounds load_bounds(const uint4 *__restrict__ tri_
 }
 
 // Pass 1 of the binner (main.c:924-936) for the triangles whose tile rectangle holds more than 8 tiles (queued by
-// the geometry kernels): one warp per triangle, lanes stride over the rectangle.
+// the geometry kernels). Rectangles of up to MLV_HUGE_TILES tiles: one warp per triangle, lanes stride over the
+// rectangle. Larger ones (sky domes, full-screen quads): the whole grid strides over the rectangle.
 __global__ void __launch_bounds__(256) k_bin_big(const __grid_constant__ BinParams P) {
 	const uint32_t n = P.ctr->big_count;
 	const uint32_t lane = lane_id();
@@ -535,6 +546,19 @@ __global__ void __launch_bounds__(256) k_bin_big(const __grid_constant__ BinPara
 			else atomicAdd(P.bin_count + bin, 1u);
 		}
 	}
+	const uint32_t nhuge = P.ctr->huge_count;
+	for(uint32_t i = 0; i < nhuge; ++i) { // huge rectangles, grid-cooperative
+		const SlotBounds s = load_bounds(P.tri_bounds, P.huge_queue[i], P.wt, P.ht);
+		const int w = s.tr.w(), cnt = w * s.tr.h();
+		for(int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < cnt; k += (int)(gridDim.x * blockDim.x)) {
+			const int ty = s.tr.ty0 + k / w, tx = s.tr.tx0 + k % w;
+			if(!P.part.owns_row(ty)) continue;
+			const uint32_t bin = (uint32_t)(ty * P.wt + tx);
+			++pairs;
+			if(hiz_rejects(s.max_depth, P.tile_min, bin, P.keep_all)) atomicOr(P.bin_count + bin, MLV_TOUCHED);
+			else atomicAdd(P.bin_count + bin, 1u);
+		}
+	}
 #pragma unroll
 	for(int d = 16; d > 0; d >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
 	if(lane == 0 && pairs) atomicAdd(&P.ctr->draw_pairs_all, pairs);
@@ -542,8 +566,16 @@ __global__ void __launch_bounds__(256) k_bin_big(const __grid_constant__ BinPara
 
 // Pass 2 of the binner (main.c:950-962): every surviving (triangle, tile) pair takes the next position of its
 // bin's list (atomic on the running offset the scan left in bin_offset). One lane per triangle slot; rectangles
-// of more than 8 tiles are expanded cooperatively by the whole warp. The per-bin order this leaves is arbitrary
-// and is restored to ascending key (= the reference's ascending triangle id) by k_tile before use.
+// of more than 8 tiles are expanded cooperatively by the warp (four independent atomics in flight per lane),
+// huge ones by the whole grid. The per-bin order this leaves is arbitrary; k_tile does not depend on it.
+__device__ __forceinline__ void fill_one(const BinParams &P, int k, int cnt, int w, int tx0, int ty0, float max_depth, uint32_t key) {
+	if(k >= cnt) return;
+	const int ty = ty0 + k / w, tx = tx0 + k % w;
+	if(!P.part.owns_row(ty)) return;
+	const uint32_t bin = (uint32_t)(ty * P.wt + tx);
+	if(!hiz_rejects(max_depth, P.tile_min, bin, P.keep_all)) P.pair_ids[atomicAdd(P.bin_offset + bin, 1u)] = key;
+}
+
 __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinParams P, uint32_t pair_capacity) {
 	if(P.ctr->pair_total > pair_capacity) return; // draw skipped, MLV_FLAG_PAIR_OVERFLOW is set
 	const uint32_t n = P.direct_slots + P.ctr->ovf_count;
@@ -555,8 +587,7 @@ __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinPar
 		s.empty = true;
 		if(slot < n) s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
 		const int w = s.empty ? 0 : s.tr.w(), cnt = s.empty ? 0 : w * s.tr.h();
-		const bool big = cnt > 8;
-		if(cnt > 0 && !big) {
+		if(cnt > 0 && cnt <= 8) {
 			for(int ty = s.tr.ty0; ty <= s.tr.ty1; ++ty) {
 				if(!P.part.owns_row(ty)) continue;
 				for(int tx = s.tr.tx0; tx <= s.tr.tx1; ++tx) {
@@ -565,21 +596,23 @@ __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinPar
 				}
 			}
 		}
-		uint32_t bigmask = __ballot_sync(0xffffffffu, big);
-		while(bigmask) {
-			const int src = __ffs(bigmask) - 1;
-			bigmask &= bigmask - 1;
-			const int bx0 = __shfl_sync(0xffffffffu, s.tr.tx0, src), by0 = __shfl_sync(0xffffffffu, s.tr.ty0, src);
-			const int bw = __shfl_sync(0xffffffffu, w, src), bc = __shfl_sync(0xffffffffu, cnt, src);
-			const uint32_t bkey = __shfl_sync(0xffffffffu, s.key, src);
-			const float bdepth = __shfl_sync(0xffffffffu, s.max_depth, src);
-			for(int k = (int)lane; k < bc; k += 32) {
-				const int ty = by0 + k / bw, tx = bx0 + k % bw;
-				if(!P.part.owns_row(ty)) continue;
-				const uint32_t bin = (uint32_t)(ty * P.wt + tx);
-				if(!hiz_rejects(bdepth, P.tile_min, bin, P.keep_all)) P.pair_ids[atomicAdd(P.bin_offset + bin, 1u)] = bkey;
-			}
+	}
+	const uint32_t nbig = P.ctr->big_count;
+	for(uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nbig; i += warps) { // 9..MLV_HUGE_TILES tiles: one warp per triangle
+		const SlotBounds s = load_bounds(P.tri_bounds, P.big_queue[i], P.wt, P.ht);
+		const int w = s.tr.w(), cnt = w * s.tr.h();
+		for(int k = (int)lane; k < cnt; k += 128) {
+			fill_one(P, k, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, s.key);
+			fill_one(P, k + 32, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, s.key);
+			fill_one(P, k + 64, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, s.key);
+			fill_one(P, k + 96, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, s.key);
 		}
+	}
+	const uint32_t nhuge = P.ctr->huge_count;
+	for(uint32_t i = 0; i < nhuge; ++i) { // huge rectangles, grid-cooperative
+		const SlotBounds s = load_bounds(P.tri_bounds, P.huge_queue[i], P.wt, P.ht);
+		const int w = s.tr.w(), cnt = w * s.tr.h();
+		for(int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < cnt; k += (int)(gridDim.x * blockDim.x)) fill_one(P, k, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, s.key);
 	}
 }
 
@@ -634,6 +667,7 @@ __device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long lo
 // the minimum of every non-empty bin, main.c:589-603 -- for any other fully Hi-Z-rejected bin that refresh
 // would rewrite the value already stored).
 #define MLV_SCAN_THREADS 1024
+#define MLV_SCAN_ITEMS 4
 __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_constant__ ScanParams P) {
 	__shared__ uint32_t s_tile;
 	__shared__ uint32_t s_sum[32], s_nz[32];
@@ -643,25 +677,49 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 	__syncthreads();
 	const uint32_t tile = s_tile;
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-	const uint32_t i = tile * MLV_SCAN_THREADS + threadIdx.x;
-	const uint32_t raw = (i < P.num_bins) ? P.bin_count[i] : 0u;
-	const uint32_t c = raw & ~MLV_TOUCHED;
-	const bool nonempty = raw != 0u;
-	const bool work = c != 0u || (nonempty && __float_as_uint(P.tile_min[i]) == MLV_TILE_MIN_CLEARED);
-	if(nonempty) P.bin_count[i] = 0u; // ready for the next draw
-	uint32_t incl = c;
+	const uint32_t base = (tile * MLV_SCAN_THREADS + threadIdx.x) * MLV_SCAN_ITEMS; // 4 consecutive bins per thread, 16-byte accesses
+	uint32_t raw[MLV_SCAN_ITEMS], c[MLV_SCAN_ITEMS];
+	bool work[MLV_SCAN_ITEMS];
+	const bool full = base + MLV_SCAN_ITEMS <= P.num_bins;
+	if(full) {
+		const uint4 r = *reinterpret_cast<const uint4 *>(P.bin_count + base);
+		raw[0] = r.x, raw[1] = r.y, raw[2] = r.z, raw[3] = r.w;
+	} else {
+#pragma unroll
+		for(int k = 0; k < MLV_SCAN_ITEMS; ++k) raw[k] = (base + k < P.num_bins) ? P.bin_count[base + k] : 0u;
+	}
+	uint32_t tsum = 0, twork = 0, tne = 0;
+#pragma unroll
+	for(int k = 0; k < MLV_SCAN_ITEMS; ++k) {
+		c[k] = raw[k] & ~MLV_TOUCHED;
+		const bool nonempty = raw[k] != 0u;
+		work[k] = c[k] != 0u || (nonempty && __float_as_uint(P.tile_min[base + k]) == MLV_TILE_MIN_CLEARED);
+		tsum += c[k];
+		twork += work[k] ? 1u : 0u;
+		tne += nonempty ? 1u : 0u;
+	}
+	if(tne) { // counters back to zero for the next draw
+		if(full) *reinterpret_cast<uint4 *>(P.bin_count + base) = make_uint4(0u, 0u, 0u, 0u);
+		else
+			for(int k = 0; k < MLV_SCAN_ITEMS; ++k)
+				if(base + k < P.num_bins) P.bin_count[base + k] = 0u;
+	}
+	uint32_t incl = tsum, wincl_work = twork;
 #pragma unroll
 	for(int d = 1; d < 32; d <<= 1) {
-		const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-		if(lane >= (uint32_t)d) incl += o;
+		const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d), o2 = __shfl_up_sync(0xffffffffu, wincl_work, d);
+		if(lane >= (uint32_t)d) {
+			incl += o;
+			wincl_work += o2;
+		}
 	}
-	const uint32_t workmask = __ballot_sync(0xffffffffu, work);
-	const uint32_t nemask = __ballot_sync(0xffffffffu, nonempty);
-	if(lane == 31) s_sum[warp] = incl;
-	if(lane == 0) {
-		s_nz[warp] = __popc(workmask);
-		if(nemask) atomicAdd(&P.ctr->draw_active_bins, (uint32_t)__popc(nemask));
+#pragma unroll
+	for(int d = 16; d > 0; d >>= 1) tne += __shfl_xor_sync(0xffffffffu, tne, d);
+	if(lane == 31) {
+		s_sum[warp] = incl;
+		s_nz[warp] = wincl_work;
 	}
+	if(lane == 0 && tne) atomicAdd(&P.ctr->draw_active_bins, tne);
 	__syncthreads();
 	if(warp < 2) {
 		const uint32_t v = (warp == 0) ? s_sum[lane] : s_nz[lane];
@@ -687,17 +745,25 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 		}
 	}
 	__syncthreads();
-	if(i < P.num_bins) {
-		const uint32_t upto = s_excl[0] + s_sum[warp] + incl - c;
-		P.bin_offset[i] = upto;
-		if(work) {
+	uint32_t upto = s_excl[0] + s_sum[warp] + incl - tsum;
+	uint32_t wpos = s_excl[1] + s_nz[warp] + wincl_work - twork;
+	uint32_t offs[MLV_SCAN_ITEMS];
+#pragma unroll
+	for(int k = 0; k < MLV_SCAN_ITEMS; ++k) {
+		offs[k] = upto;
+		if(work[k]) {
 			mlv_ref_compacted_bin cb;
-			cb.num_triangles_self = c;
+			cb.num_triangles_self = c[k];
 			cb.num_triangles_upto = upto;
-			cb.bin_index = i;
-			P.cbins[s_excl[1] + s_nz[warp] + __popc(workmask & ((1u << lane) - 1u))] = cb;
+			cb.bin_index = base + k;
+			P.cbins[wpos++] = cb;
 		}
+		upto += c[k];
 	}
+	if(full) *reinterpret_cast<uint4 *>(P.bin_offset + base) = make_uint4(offs[0], offs[1], offs[2], offs[3]);
+	else
+		for(int k = 0; k < MLV_SCAN_ITEMS; ++k)
+			if(base + k < P.num_bins) P.bin_offset[base + k] = offs[k];
 }
 
 // =================================================================================================
@@ -865,7 +931,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant
 		c->stats.active_bin_count += c->draw_active_bins;
 		c->last_ovf_count = c->ovf_count;
 		c->draw_tris = c->draw_pairs_all = c->draw_active_bins = 0u;
-		c->ovf_count = c->clip_count = c->big_count = 0u;
+		c->ovf_count = c->clip_count = c->big_count = c->huge_count = 0u;
 	}
 	if(P.ctr->pair_total > pair_capacity) return; // draw skipped, MLV_FLAG_PAIR_OVERFLOW is set
 	const uint32_t n_cbins = P.ctr->n_cbins;
@@ -891,8 +957,13 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant
 			if(lane == 0) P.tile_min[b] = m;
 			continue;
 		}
+		// The reference walks a bin's list in ascending triangle id and lets a fragment through when z >= depth
+		// (main.c:1166), so the surviving fragment of a pixel is the one with the greatest z and, among equal z, the
+		// greatest id -- a property of the SET of fragments. Taking the maximum over (z, key) therefore gives the
+		// reference's result in any visiting order, and the list k_bin_fill left in arrival order needs no sorting.
+		// Debug capture sorts it anyway so that mlv_debug_read_bins shows the reference's per-tile order.
 		uint32_t *ids = P.pair_ids + off;
-		sort_bin_ids(ids, P.pair_tmp + off, n, P.key_bits);
+		if(P.sort_lists) sort_bin_ids(ids, P.pair_tmp + off, n, P.key_bits);
 
 		for(uint32_t base = 0; base < n; base += 32u) {
 			// ---- rasterizer, lanes over triangles (main.c:996-1041)
@@ -950,7 +1021,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant
 					float bx, by;
 					barycentrics(E1, E2, ooa, bx, by);
 					const float z = interp(z0, z1, z2, bx, by);
-					if(z >= d0) { // _CMP_GE_OQ, reversed Z (main.c:1166)
+					if(z > d0 || (z == d0 && (win0 == MLV_NO_WINNER || tkey > win0))) { // z >= depth in id order (main.c:1166), see above; false on NaN
 						d0 = z;
 						win0 = tkey;
 					}
@@ -959,7 +1030,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant
 					float bx, by;
 					barycentrics(E1 + (tb1 << 6), E2 + (tb2 << 6), ooa, bx, by); // four rows down: + b*(4*16)
 					const float z = interp(z0, z1, z2, bx, by);
-					if(z >= d1) {
+					if(z > d1 || (z == d1 && (win1 == MLV_NO_WINNER || tkey > win1))) {
 						d1 = z;
 						win1 = tkey;
 					}

@@ -67,7 +67,7 @@ struct mlv_device {
 	uint64_t pair_capacity;
 	uint4 *tri_cov, *tri_shade;
 	uint4 *tri_bounds;
-	uint32_t *clip_queue, *big_queue;
+	uint32_t *clip_queue, *big_queue, *huge_queue;
 	uint32_t tri_capacity; // slots (direct + overflow)
 	unsigned long long *scan_state; // 2 x scan_blocks look-back words
 	uint32_t scan_blocks;
@@ -205,7 +205,7 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	CREATE_TRY(cudaMalloc(&dev->pair_ids, dev->pair_capacity * sizeof(uint32_t)));
 	CREATE_TRY(cudaMalloc(&dev->pair_tmp, dev->pair_capacity * sizeof(uint32_t)));
 	CREATE_TRY(cudaMalloc(&dev->ctr, sizeof(Counters)));
-	dev->scan_blocks = (dev->num_bins + MLV_SCAN_THREADS - 1) / MLV_SCAN_THREADS;
+	dev->scan_blocks = (dev->num_bins + MLV_SCAN_THREADS * MLV_SCAN_ITEMS - 1) / (MLV_SCAN_THREADS * MLV_SCAN_ITEMS);
 	CREATE_TRY(cudaMalloc(&dev->scan_state, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long)));
 	CREATE_TRY(cudaMemsetAsync(dev->scan_state, 0, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long), dev->stream));
 	CREATE_TRY(cudaMalloc(&dev->rsqrt_lut, sizeof(k_rsqrt_lut_host)));
@@ -234,7 +234,7 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(!dev) return;
 	cudaSetDevice(dev->cuda_dev);
 	if(dev->stream) cudaStreamSynchronize(dev->stream);
-	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue,
+	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue,
 		             dev->scan_state, dev->ctr, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
@@ -487,6 +487,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 			CUDA_TRY(regrow(&dev->tri_bounds, (size_t)cap));
 			CUDA_TRY(regrow(&dev->clip_queue, (size_t)cap));
 			CUDA_TRY(regrow(&dev->big_queue, (size_t)cap));
+			CUDA_TRY(regrow(&dev->huge_queue, (size_t)cap));
 			dev->tri_capacity = cap;
 		}
 		if(debug) {
@@ -543,6 +544,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	gp.tri_bounds = dev->tri_bounds;
 	gp.clip_queue = dev->clip_queue;
 	gp.big_queue = dev->big_queue;
+	gp.huge_queue = dev->huge_queue;
 	gp.bin_count = dev->bin_count;
 	gp.tile_min = dev->tile_min;
 	gp.keep_all = debug;
@@ -575,6 +577,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	memset(&bp, 0, sizeof(bp));
 	bp.tri_bounds = dev->tri_bounds;
 	bp.big_queue = dev->big_queue;
+	bp.huge_queue = dev->huge_queue;
 	bp.tile_min = dev->tile_min;
 	bp.bin_count = dev->bin_count;
 	bp.bin_offset = dev->bin_offset;
@@ -634,6 +637,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	tp.key_bits = 3u;
 	while(tp.key_bits < 32u && (T >> (tp.key_bits - 3u)) != 0u) tp.key_bits++;
 	tp.wt = dev->wt;
+	tp.sort_lists = debug;
 	uint32_t tile_blocks = (dev->num_bins + 7u) / 8u;
 	if(tile_blocks > 148u * 8u) tile_blocks = 148u * 8u;
 	const uint32_t pcap = (uint32_t)dev->pair_capacity;

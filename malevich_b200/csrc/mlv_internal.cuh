@@ -50,7 +50,7 @@ struct Counters {
 	uint32_t big_count;   // triangles queued for k_bin_big in the current draw (reset by k_tile)
 	uint32_t draw_pairs_all;   // (triangle,tile) pairs of the current draw including Hi-Z-rejected ones (Stats)
 	uint32_t draw_active_bins; // non-empty bins of the current draw in the reference's sense (Stats)
-	uint32_t pad;
+	uint32_t huge_count;  // triangles with more than MLV_HUGE_TILES tiles in the current draw (reset by k_tile)
 	mlv_stats stats;      // accumulated like reference main.c:1228-1246
 };
 
@@ -86,6 +86,7 @@ struct GeomParams {
 	uint4 *tri_bounds;
 	uint32_t *clip_queue;
 	uint32_t *big_queue;
+	uint32_t *huge_queue;
 	uint32_t *bin_count;
 	const float *tile_min;
 	bool keep_all; // debug capture: no Hi-Z at binning time, lists hold every pair like the reference's
@@ -97,6 +98,7 @@ struct GeomParams {
 struct BinParams {
 	const uint4 *tri_bounds;
 	const uint32_t *big_queue;
+	const uint32_t *huge_queue;
 	const float *tile_min;
 	uint32_t *bin_count;
 	uint32_t *bin_offset;
@@ -136,6 +138,7 @@ struct TileParams {
 	uint32_t direct_slots; // T
 	uint32_t key_bits;
 	int wt;
+	bool sort_lists; // debug capture: restore ascending-key order inside every bin list
 };
 
 } // namespace mlv
