@@ -1,0 +1,73 @@
+"""CPU tests of the N>1 path (`-m "not gpu"`): world_size-2 (and 3) `gloo` process groups exercise the host-side
+sort-first plumbing bench.py uses on GPUs -- stripe ownership, chunk packing, in-place all-gather, unpacking --
+with the REFERENCE's frame standing in for what each rank's device would have rendered into its own stripes.
+The CUDA side of the same layout is checked on a GPU by
+tests/test_gpu_parity.py::test_sort_first_partition_composes_to_single_gpu_image.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, have_ref
+from malevich_b200 import partition
+
+
+def test_partition_covers_every_tile_row_exactly_once():
+    for h, n, s in ((720, 2, 1), (1080, 8, 1), (2160, 8, 4), (200, 3, 2), (2160, 5, 7)):
+        rows = sorted(r for k in range(n) for r in partition.owned_tile_rows(h, n, k, s))
+        assert rows == list(range(h // 8))
+        img = np.arange(h * 16, dtype=np.uint32).reshape(h, 16)
+        chunks = np.stack([partition.pack(img, n, k, s) for k in range(n)])
+        assert chunks.shape[1] == partition.chunk_rows(h, n, s)
+        assert np.array_equal(partition.unpack(chunks, h, n, s), img)
+
+
+def _worker(rank, world, port, stripe_h, frame_path, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = np.load(frame_path)
+        h, w = full.shape
+        # this rank "renders" only the stripes it owns; everything else stays at a poison value
+        mine = np.full_like(full, 0xDEADBEEF)
+        for ty in partition.owned_tile_rows(h, world, rank, stripe_h):
+            mine[ty * 8:(ty + 1) * 8] = full[ty * 8:(ty + 1) * 8]
+        rows = partition.chunk_rows(h, world, stripe_h)
+        gather = torch.zeros((world, rows, w), dtype=torch.int64)
+        gather[rank] = torch.from_numpy(partition.pack(mine, world, rank, stripe_h).astype(np.int64))
+        dist.all_gather_into_tensor(gather.view(-1), gather[rank].reshape(-1).clone())  # same call shape as bench.py's NCCL path
+        image = partition.unpack(gather.numpy().astype(np.uint32), h, world, stripe_h)
+        # Stats: bin/pair counters are per rank and must be summed; assembled triangles are replicated
+        t = torch.tensor([len(partition.owned_tile_rows(h, world, rank, stripe_h))], dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ok = np.array_equal(image, full) and int(t.item()) == h // 8
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+            f.write("OK" if ok else "MISMATCH")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,stripe_h", [(2, 1), (2, 4), (3, 1)])
+def test_gloo_composite_reproduces_the_full_frame(world, stripe_h, tmp_path):
+    if have_ref(320, 200):
+        from malevich_b200 import scenes
+        from oracle.ref_oracle import RefOracle
+        sc = scenes.toon(320, 200)
+        orc = RefOracle(320, 200, threads=1)
+        orc.render(sc)
+        frame = orc.colors()
+    else:
+        frame = np.load(os.path.join(ROOT, "tests", "golden", "small_frames.npz"))["toon_320x200/colors"]
+    frame_path = str(tmp_path / "frame.npy")
+    np.save(frame_path, frame)
+    port = 29600 + world * 10 + stripe_h
+    mp.spawn(_worker, args=(world, port, stripe_h, frame_path, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"rank{r}.txt").read() == "OK"
