@@ -50,6 +50,8 @@ struct TriSetup {
 	float max_depth;
 	float4 p[3];  // screen-space positions written over register 0 (main.c:881-883)
 	int minx, miny, maxx, maxy;
+	int sx[3], sy[3]; // snapped 28.4 vertex coordinates
+	int signed_area;
 	bool nowrap;  // every edge-function evaluation on this render target is free of i32 wrap-around
 };
 
@@ -73,9 +75,10 @@ __device__ __forceinline__ int snap(float v) {
 	return __double2int_rz(d);
 }
 
-// Projection, viewport transform, snapping, triangle setup for one (sub-)triangle (main.c:797-898).
-// Returns false when the triangle is back-face culled (signed_area > 0, main.c:856).
-__device__ __forceinline__ bool setup_triangle(const float4 &c0, const float4 &c1, const float4 &c2, const GeomParams &P, TriSetup &S) {
+// Projection, viewport transform, snapping, signed area, face culling, max depth and bounds of one
+// (sub-)triangle (main.c:797-857, 871, 888-898). Returns false when the triangle is back-face culled
+// (signed_area > 0, main.c:856). Everything binning and Hi-Z need; the edge functions follow in setup_edges().
+__device__ __forceinline__ bool setup_project(const float4 &c0, const float4 &c1, const float4 &c2, const GeomParams &P, TriSetup &S) {
 	float4 p[3] = { c0, c1, c2 };
 #pragma unroll
 	for(int i = 0; i < 3; ++i) {
@@ -97,15 +100,10 @@ __device__ __forceinline__ bool setup_triangle(const float4 &c0, const float4 &c
 	}
 	const int x0 = snap(S.p[0].x), x1 = snap(S.p[1].x), x2 = snap(S.p[2].x);
 	const int y0 = snap(S.p[0].y), y1 = snap(S.p[1].y), y2 = snap(S.p[2].y);
-	const int signed_area =
-	    (int)(((uint32_t)x1 - (uint32_t)x0) * ((uint32_t)y2 - (uint32_t)y0) - ((uint32_t)x2 - (uint32_t)x0) * ((uint32_t)y1 - (uint32_t)y0));
-	if(signed_area > 0) return false;
-	set_edge(S.e + 6, signed_area, x0, y0, x1, y1);
-	set_edge(S.e + 0, signed_area, x1, y1, x2, y2);
-	set_edge(S.e + 3, signed_area, x2, y2, x0, y0);
-	float area_f = (float)(signed_area >> 8);
-	if(area_f == 0.0f) area_f = 1.0f;
-	S.ooa = fabsf(1.0f / area_f);
+	S.sx[0] = x0, S.sx[1] = x1, S.sx[2] = x2;
+	S.sy[0] = y0, S.sy[1] = y1, S.sy[2] = y2;
+	S.signed_area = (int)(((uint32_t)x1 - (uint32_t)x0) * ((uint32_t)y2 - (uint32_t)y0) - ((uint32_t)x2 - (uint32_t)x0) * ((uint32_t)y1 - (uint32_t)y0));
+	if(S.signed_area > 0) return false;
 	S.max_depth = ref_max_macro(S.p[0].z, ref_max_macro(S.p[1].z, S.p[2].z)); // MAX3 math.h:32
 	const int mnx = min(x0, min(x1, x2)) >> 4, mny = min(y0, min(y1, y2)) >> 4;
 	const int mxx = max(x0, max(x1, x2)) >> 4, mxy = max(y0, max(y1, y2)) >> 4;
@@ -113,18 +111,34 @@ __device__ __forceinline__ bool setup_triangle(const float4 &c0, const float4 &c
 	S.miny = min(max(mny, 0), P.vp_h - 1);
 	S.maxx = min(mxx + 1, P.vp_w - 1);
 	S.maxy = min(mxy + 1, P.vp_h - 1);
+	return true;
+}
+
+// Edge functions, 1/area (main.c:858-866) and the no-wrap flag.
+__device__ __forceinline__ void setup_edges(const GeomParams &P, TriSetup &S) {
+	const int x0 = S.sx[0], x1 = S.sx[1], x2 = S.sx[2], y0 = S.sy[0], y1 = S.sy[1], y2 = S.sy[2];
+	set_edge(S.e + 6, S.signed_area, x0, y0, x1, y1);
+	set_edge(S.e + 0, S.signed_area, x1, y1, x2, y2);
+	set_edge(S.e + 3, S.signed_area, x2, y2, x0, y0);
+	float area_f = (float)(S.signed_area >> 8);
+	if(area_f == 0.0f) area_f = 1.0f;
+	S.ooa = fabsf(1.0f / area_f);
 	// No-wrap proof: with |x_i|,|y_i| <= M and sample coordinates in [0, 16W] x [0, 16H], every term of
 	// a*(16x) + b*(16y) + c (c = -a*x_i - b*y_i) is bounded by (|a|+|b|) * max(M, 16W, 16H); if twice that stays
 	// below 2^31 no intermediate wraps and the integer edge functions equal the exact ones, so coverage is
 	// confined to the (closed) triangle and hence to [min_bounds, max_bounds].
-	{ // evaluated in fp32 with a 1 % safety margin (both factors are < 2^26, the products are compared far from their rounding error)
-		const int mi = max(max(max(abs(x0), abs(x1)), abs(x2)), max(max(abs(y0), abs(y1)), abs(y2)));
-		const float m = (float)max(mi, max(P.vp_w, P.vp_h) * 16 + 16);
-		float ab = 0.0f;
+	// Evaluated in fp32 with a 1 % safety margin (both factors are < 2^26, compared far from their rounding error).
+	const int mi = max(max(max(abs(x0), abs(x1)), abs(x2)), max(max(abs(y0), abs(y1)), abs(y2)));
+	const float m = (float)max(mi, max(P.vp_w, P.vp_h) * 16 + 16);
+	float ab = 0.0f;
 #pragma unroll
-		for(int k = 0; k < 3; ++k) ab = fmaxf(ab, fabsf((float)S.e[k * 3]) + fabsf((float)S.e[k * 3 + 1]));
-		S.nowrap = (mi < (1 << 24)) && (2.0f * ab * m < 2126008811.0f); // 0.99 * 2^31
-	}
+	for(int k = 0; k < 3; ++k) ab = fmaxf(ab, fabsf((float)S.e[k * 3]) + fabsf((float)S.e[k * 3 + 1]));
+	S.nowrap = (mi < (1 << 24)) && (2.0f * ab * m < 2126008811.0f); // 0.99 * 2^31
+}
+
+__device__ __forceinline__ bool setup_triangle(const float4 &c0, const float4 &c1, const float4 &c2, const GeomParams &P, TriSetup &S) {
+	if(!setup_project(c0, c1, c2, P, S)) return false;
+	setup_edges(P, S);
 	return true;
 }
 
@@ -212,17 +226,39 @@ __device__ __forceinline__ BinTally count_bins(const GeomParams &P, const TriSet
 		r.huge = r.live && cnt > MLV_HUGE_TILES;
 		return r;
 	}
-	for(int ty = tr.ty0; ty <= tr.ty1; ++ty) {
-		if(!P.part.owns_row(ty)) continue;
-		for(int tx = tr.tx0; tx <= tr.tx1; ++tx) {
-			const uint32_t bin = (uint32_t)(ty * P.wt + tx);
-			++r.pairs;
-			if(hiz_rejects(S.max_depth, P.tile_min, bin, P.keep_all)) {
-				atomicOr(P.bin_count + bin, MLV_TOUCHED);
-			} else {
-				atomicAdd(P.bin_count + bin, 1u);
-				r.live = true;
+	// <= 8 tiles: walk the rectangle with fully unrolled, predicated steps so that the tile-minimum and counter loads
+	// of all tiles are independent and in flight together (they were a chain of dependent L2 round trips), then
+	// issue the atomics. A bin already flagged as touched needs no second atomicOr (a stale read only repeats it).
+	uint32_t bins[8];
+	bool ok[8];
+	{
+		int tx = tr.tx0, ty = tr.ty0;
+#pragma unroll
+		for(int k = 0; k < 8; ++k) {
+			ok[k] = k < cnt && P.part.owns_row(ty);
+			bins[k] = (uint32_t)(ty * P.wt + tx);
+			if(++tx > tr.tx1) {
+				tx = tr.tx0;
+				++ty;
 			}
+		}
+	}
+	float tm[8];
+	uint32_t bc[8];
+#pragma unroll
+	for(int k = 0; k < 8; ++k) {
+		tm[k] = ok[k] ? __ldg(P.tile_min + bins[k]) : 0.0f;
+		bc[k] = (ok[k] && !P.keep_all) ? __ldcg(P.bin_count + bins[k]) : 0u;
+	}
+#pragma unroll
+	for(int k = 0; k < 8; ++k) {
+		if(!ok[k]) continue;
+		++r.pairs;
+		if(!P.keep_all && S.max_depth < tm[k]) { // Hi-Z (main.c:1006), see hiz_rejects
+			if(!(bc[k] & MLV_TOUCHED)) atomicOr(P.bin_count + bins[k], MLV_TOUCHED);
+		} else {
+			atomicAdd(P.bin_count + bins[k], 1u);
+			r.live = true;
 		}
 	}
 	return r;
@@ -360,7 +396,7 @@ __device__ __forceinline__ void tally_stats(Counters *ctr, uint32_t emitted, uin
 
 #define MLV_GEOM_THREADS 256
 
-template <int VS, bool INDEXED>
+template <int VS, bool INDEXED, bool DEBUG>
 __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_constant__ GeomParams P) {
 	// Records are staged per warp in shared memory and written out as contiguous 512-byte rows: the 32 direct
 	// slots of a warp are adjacent in HBM, so the warp stores 1536 B of TriCov and 3072 B of TriShade with fully
@@ -373,7 +409,9 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 	bool staged = false; // this lane has a record for its direct slot t
 	uint4 bounds = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, t << 3);
 	if(t < P.tri_count) {
-		// ---- input assembler (main.c:662-696): index fetch + 32-byte vertex fetch as two 128-bit loads
+		// ---- input assembler (main.c:662-696): index fetch + vertex fetch. Work is done lazily: positions for every
+		// triangle, the second half of each vertex and the attribute part of the vertex shader only for triangles
+		// that survive culling and Hi-Z (the reference shades all of them; the results are the same values).
 		uint32_t vi0, vi1, vi2;
 		if(INDEXED) {
 			vi0 = __ldg(P.ib + 3u * t);
@@ -384,21 +422,19 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 			vi1 = vi0 + 1u;
 			vi2 = vi0 + 2u;
 		}
-		const float4 a0 = __ldg(P.vb + 2 * (size_t)vi0), a1 = __ldg(P.vb + 2 * (size_t)vi0 + 1);
-		const float4 b0 = __ldg(P.vb + 2 * (size_t)vi1), b1 = __ldg(P.vb + 2 * (size_t)vi1 + 1);
-		const float4 c0 = __ldg(P.vb + 2 * (size_t)vi2), c1 = __ldg(P.vb + 2 * (size_t)vi2 + 1);
-		// ---- vertex shader (main.c:698-734)
-		const VsOut v0 = run_vs<VS>(a0, a1, P.cb, P.vs_tex, P.rsqrt_lut);
-		const VsOut v1 = run_vs<VS>(b0, b1, P.cb, P.vs_tex, P.rsqrt_lut);
-		const VsOut v2 = run_vs<VS>(c0, c1, P.cb, P.vs_tex, P.rsqrt_lut);
-		if(P.dbg.vs_out) {
+		const float4 a0 = __ldg(P.vb + 2 * (size_t)vi0), b0 = __ldg(P.vb + 2 * (size_t)vi1), c0 = __ldg(P.vb + 2 * (size_t)vi2);
+		// ---- vertex shader, position part (main.c:698-734)
+		const float4 a = vs_position<VS>(a0, P.cb), b = vs_position<VS>(b0, P.cb), c = vs_position<VS>(c0, P.cb);
+		if(DEBUG) {
+			const VsOut v0 = run_vs<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
+			const VsOut v1 = run_vs<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
+			const VsOut v2 = run_vs<VS>(c0, __ldg(P.vb + 2 * (size_t)vi2 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
 			float4 *o = reinterpret_cast<float4 *>(P.dbg.vs_out + (size_t)(3u * t) * 12);
 			o[0] = v0.r0, o[1] = v0.r1, o[2] = make_float4(v0.r2x, 0.0f, 0.0f, 0.0f);
 			o[3] = v1.r0, o[4] = v1.r1, o[5] = make_float4(v1.r2x, 0.0f, 0.0f, 0.0f);
 			o[6] = v2.r0, o[7] = v2.r1, o[8] = make_float4(v2.r2x, 0.0f, 0.0f, 0.0f);
 		}
 		// ---- primitive assembly (main.c:750-908)
-		const float4 a = v0.r0, b = v1.r0, c = v2.r0;
 		const bool degenerate = (a.w == 0.0f || b.w == 0.0f || c.w == 0.0f); // main.c:759
 		const bool rejected =                                                // main.c:764-772
 		    (a.x < -a.w && b.x < -b.w && c.x < -c.w) || (a.x > a.w && b.x > b.w && c.x > c.w) || (a.y < -a.w && b.y < -b.w && c.y < -c.w) ||
@@ -410,7 +446,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 			    (a.y <= a.w && b.y <= b.w && c.y <= c.w) && (a.z >= 0.0f && b.z >= 0.0f && c.z >= 0.0f) && (a.z <= a.w && b.z <= b.w && c.z <= c.w);
 			if(inside) {
 				TriSetup S;
-				if(setup_triangle(a, b, c, P, S)) {
+				if(setup_project(a, b, c, P, S)) {
 					direct = true;
 					emitted = 1u;
 					// ---- binner pass 1 + Hi-Z for this triangle; a triangle hidden in every tile it touches writes no record
@@ -418,26 +454,35 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 					pairs = tally.pairs;
 					is_big = tally.big;
 					if(tally.huge) P.huge_queue[atomicAdd(&P.ctr->huge_count, 1u)] = t; // rare: sky domes, full-screen quads
-					if(tally.live) {
-						const uint2 pb = pack_bounds(S);
-						bounds = make_uint4(pb.x, pb.y, __float_as_uint(S.max_depth), t << 3);
-						staged = true;
-						TriRecord R;
-						make_record(R, S, pb, v0.r1, v1.r1, v2.r1, v0.r2x, v1.r2x, v2.r2x);
-						uint4 *st = s_stage[warp];
+					if(tally.live || DEBUG) {
+						setup_edges(P, S);
+						// ---- vertex shader, attribute part
+						float4 r1a, r1b, r1c;
+						float r2a, r2b, r2c;
+						vs_attributes<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), a, P.cb, P.vs_tex, P.rsqrt_lut, r1a, r2a);
+						vs_attributes<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), b, P.cb, P.vs_tex, P.rsqrt_lut, r1b, r2b);
+						vs_attributes<VS>(c0, __ldg(P.vb + 2 * (size_t)vi2 + 1), c, P.cb, P.vs_tex, P.rsqrt_lut, r1c, r2c);
+						if(tally.live) {
+							const uint2 pb = pack_bounds(S);
+							bounds = make_uint4(pb.x, pb.y, __float_as_uint(S.max_depth), t << 3);
+							staged = true;
+							TriRecord R;
+							make_record(R, S, pb, r1a, r1b, r1c, r2a, r2b, r2c);
+							uint4 *st = s_stage[warp];
 #pragma unroll
-						for(int i = 0; i < MLV_TRI_COV_U4; ++i) st[lane * MLV_TRI_COV_U4 + i] = R.cov[i];
+							for(int i = 0; i < MLV_TRI_COV_U4; ++i) st[lane * MLV_TRI_COV_U4 + i] = R.cov[i];
 #pragma unroll
-						for(int i = 0; i < MLV_TRI_SHADE_U4; ++i)
-							st[32 * MLV_TRI_COV_U4 + lane * MLV_TRI_SHADE_U4 + i] = make_uint4(__float_as_uint(R.shade[i].x), __float_as_uint(R.shade[i].y), __float_as_uint(R.shade[i].z), __float_as_uint(R.shade[i].w));
+							for(int i = 0; i < MLV_TRI_SHADE_U4; ++i)
+								st[32 * MLV_TRI_COV_U4 + lane * MLV_TRI_SHADE_U4 + i] = make_uint4(__float_as_uint(R.shade[i].x), __float_as_uint(R.shade[i].y), __float_as_uint(R.shade[i].z), __float_as_uint(R.shade[i].w));
+						}
+						if(DEBUG) emit_debug(P, t, t << 3, S, r1a, r1b, r1c, r2a, r2b, r2c);
 					}
-					if(P.dbg.tris) emit_debug(P, t, t << 3, S, v0.r1, v1.r1, v2.r1, v0.r2x, v1.r2x, v2.r2x);
 				}
 			} else {
 				needs_clip = true;
 			}
 		}
-		if(!direct && P.dbg.slot_key) P.dbg.slot_key[t] = 0xffffffffu;
+		if(DEBUG && !direct) P.dbg.slot_key[t] = 0xffffffffu;
 		P.tri_bounds[t] = bounds;
 	}
 	// ---- triangles that need the clipper are queued for k_geom_clip, triangles with large tile rectangles for
@@ -587,14 +632,26 @@ __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinPar
 		s.empty = true;
 		if(slot < n) s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
 		const int w = s.empty ? 0 : s.tr.w(), cnt = s.empty ? 0 : w * s.tr.h();
-		if(cnt > 0 && cnt <= 8) {
-			for(int ty = s.tr.ty0; ty <= s.tr.ty1; ++ty) {
-				if(!P.part.owns_row(ty)) continue;
-				for(int tx = s.tr.tx0; tx <= s.tr.tx1; ++tx) {
-					const uint32_t bin = (uint32_t)(ty * P.wt + tx);
-					if(!hiz_rejects(s.max_depth, P.tile_min, bin, P.keep_all)) P.pair_ids[atomicAdd(P.bin_offset + bin, 1u)] = s.key;
+		if(cnt > 0 && cnt <= 8) { // unrolled, predicated walk: all tile-minimum loads, then all atomics, then all stores
+			uint32_t bins[8], pos[8];
+			bool ok[8];
+			int tx = s.tr.tx0, ty = s.tr.ty0;
+#pragma unroll
+			for(int k = 0; k < 8; ++k) {
+				ok[k] = k < cnt && P.part.owns_row(ty);
+				bins[k] = (uint32_t)(ty * P.wt + tx);
+				if(++tx > s.tr.tx1) {
+					tx = s.tr.tx0;
+					++ty;
 				}
 			}
+#pragma unroll
+			for(int k = 0; k < 8; ++k) ok[k] = ok[k] && !hiz_rejects(s.max_depth, P.tile_min, bins[k], P.keep_all);
+#pragma unroll
+			for(int k = 0; k < 8; ++k) pos[k] = ok[k] ? atomicAdd(P.bin_offset + bins[k], 1u) : 0u;
+#pragma unroll
+			for(int k = 0; k < 8; ++k)
+				if(ok[k]) P.pair_ids[pos[k]] = s.key;
 		}
 	}
 	const uint32_t nbig = P.ctr->big_count;

@@ -437,8 +437,11 @@ static TexDesc tex_desc(const mlv_texture *t) {
 
 template <int VS>
 static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed) {
-	if(indexed) k_geom<VS, true><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
-	else k_geom<VS, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+	const bool debug = gp.keep_all;
+	if(indexed && debug) k_geom<VS, true, true><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+	else if(indexed) k_geom<VS, true, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+	else if(debug) k_geom<VS, false, true><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+	else k_geom<VS, false, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
 }
 template <int VS>
 static void launch_geom_clip(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed) {

@@ -195,54 +195,71 @@ __device__ __forceinline__ float srgb_from_linear_approx(float c) {
 // ---- vertex shaders ------------------------------------------------------------------------------
 // Input vertex = 8 floats (ia.input_layout == 32 bytes): in0 = floats 0..3, in1 = floats 4..7.
 
+// Each program is split into its SV_POSITION part and its attribute part: the geometry kernel needs the
+// position of every triangle but the attributes only of the triangles that survive culling and Hi-Z.
+
 template <int VS>
-__device__ __forceinline__ VsOut run_vs(float4 in0, float4 in1, const float *__restrict__ cb, const TexDesc &tex, const uint32_t *__restrict__ lut);
+__device__ __forceinline__ float4 vs_position(float4 in0, const float *__restrict__ cb);
+template <int VS>
+__device__ __forceinline__ void vs_attributes(float4 in0, float4 in1, float4 pos, const float *__restrict__ cb, const TexDesc &tex, const uint32_t *__restrict__ lut, float4 &r1,
+                                              float &r2x);
 
 // passthrough_vs.c:16-25 -- Vs_Input {POSITION xyzw, COLOR xyz, pad}
 template <>
-__device__ __forceinline__ VsOut run_vs<0>(float4 in0, float4 in1, const float *__restrict__, const TexDesc &, const uint32_t *__restrict__) {
-	VsOut o;
-	o.r0 = make_float4(__fmaf_rn(in0.x, 2.0f, -1.0f), __fmaf_rn(in0.y, 2.0f, -1.0f), in0.z, in0.w);
-	o.r1 = make_float4(in1.x, in1.y, in1.z, 0.0f);
-	o.r2x = 0.0f;
-	return o;
+__device__ __forceinline__ float4 vs_position<0>(float4 in0, const float *__restrict__) {
+	return make_float4(__fmaf_rn(in0.x, 2.0f, -1.0f), __fmaf_rn(in0.y, 2.0f, -1.0f), in0.z, in0.w);
+}
+template <>
+__device__ __forceinline__ void vs_attributes<0>(float4, float4 in1, float4, const float *__restrict__, const TexDesc &, const uint32_t *__restrict__, float4 &r1, float &r2x) {
+	r1 = make_float4(in1.x, in1.y, in1.z, 0.0f);
+	r2x = 0.0f;
 }
 
 // basic_vs.c:22-33 -- Vs_Input {POSITION xyz, NORMAL xyz, UV xy}
 template <>
-__device__ __forceinline__ VsOut run_vs<1>(float4 in0, float4 in1, const float *__restrict__ cb, const TexDesc &, const uint32_t *__restrict__ lut) {
-	VsOut o;
-	o.r0 = mul_m4_v4_pairwise(cb, make_float4(in0.x, in0.y, in0.z, 1.0f));
+__device__ __forceinline__ float4 vs_position<1>(float4 in0, const float *__restrict__ cb) {
+	return mul_m4_v4_pairwise(cb, make_float4(in0.x, in0.y, in0.z, 1.0f));
+}
+template <>
+__device__ __forceinline__ void vs_attributes<1>(float4 in0, float4 in1, float4, const float *__restrict__, const TexDesc &, const uint32_t *__restrict__ lut, float4 &r1, float &r2x) {
 	float nx = in0.w, ny = in1.x, nz = in1.y;
 	normalize3(nx, ny, nz, lut);
-	o.r1 = make_float4(nx, ny, nz, in1.z);
-	o.r2x = in1.w;
-	return o;
+	r1 = make_float4(nx, ny, nz, in1.z);
+	r2x = in1.w;
 }
 
 // vertex_lighting_vs.c:22-39
 template <>
-__device__ __forceinline__ VsOut run_vs<2>(float4 in0, float4 in1, const float *__restrict__ cb, const TexDesc &tex, const uint32_t *__restrict__ lut) {
-	VsOut o;
-	o.r0 = mul_m4_v4_pairwise(cb, make_float4(in0.x, in0.y, in0.z, 1.0f));
+__device__ __forceinline__ float4 vs_position<2>(float4 in0, const float *__restrict__ cb) {
+	return mul_m4_v4_pairwise(cb, make_float4(in0.x, in0.y, in0.z, 1.0f));
+}
+template <>
+__device__ __forceinline__ void vs_attributes<2>(float4 in0, float4 in1, float4, const float *__restrict__, const TexDesc &tex, const uint32_t *__restrict__ lut, float4 &r1, float &r2x) {
 	float nx = in0.w, ny = in1.x, nz = in1.y;
 	normalize3(nx, ny, nz, lut);
 	const float4 c = sample_latlon(tex, nx, ny, nz, lut);
-	o.r1 = make_float4(tone_map(c.x), tone_map(c.y), tone_map(c.z), in1.z);
-	o.r2x = in1.w;
-	return o;
+	r1 = make_float4(tone_map(c.x), tone_map(c.y), tone_map(c.z), in1.z);
+	r2x = in1.w;
 }
 
 // fullscreen_vs.c:22-39 -- Vs_Input {POSITION xyzw, VIEW_DIR xyz, pad}; cb+16 = view_from_clip, cb+32 = world_from_view
 template <>
-__device__ __forceinline__ VsOut run_vs<3>(float4 in0, float4 in1, const float *__restrict__ cb, const TexDesc &, const uint32_t *__restrict__) {
-	VsOut o;
-	const float4 pos_cs = make_float4(__fmaf_rn(in0.x, 2.0f, -1.0f), __fmaf_rn(in0.y, 2.0f, -1.0f), in0.z, in0.w);
+__device__ __forceinline__ float4 vs_position<3>(float4 in0, const float *__restrict__) {
+	return make_float4(__fmaf_rn(in0.x, 2.0f, -1.0f), __fmaf_rn(in0.y, 2.0f, -1.0f), in0.z, in0.w);
+}
+template <>
+__device__ __forceinline__ void vs_attributes<3>(float4, float4, float4 pos_cs, const float *__restrict__ cb, const TexDesc &, const uint32_t *__restrict__, float4 &r1, float &r2x) {
 	const float4 dir_vs = mul_m4_v4_pairwise(cb + 16, pos_cs);
 	const float4 dir_ws = mul_m4_v4_pairwise(cb + 32, make_float4(dir_vs.x, dir_vs.y, dir_vs.z, 0.0f));
-	o.r0 = pos_cs;
-	o.r1 = make_float4(dir_ws.x, dir_ws.y, dir_ws.z, 0.0f);
-	o.r2x = 0.0f;
+	r1 = make_float4(dir_ws.x, dir_ws.y, dir_ws.z, 0.0f);
+	r2x = 0.0f;
+}
+
+template <int VS>
+__device__ __forceinline__ VsOut run_vs(float4 in0, float4 in1, const float *__restrict__ cb, const TexDesc &tex, const uint32_t *__restrict__ lut) {
+	VsOut o;
+	o.r0 = vs_position<VS>(in0, cb);
+	vs_attributes<VS>(in0, in1, o.r0, cb, tex, lut, o.r1, o.r2x);
 	return o;
 }
 
