@@ -75,31 +75,40 @@ __device__ __forceinline__ int snap(float v) {
 	return __double2int_rz(d);
 }
 
-// Projection, viewport transform, snapping, signed area, face culling, max depth and bounds of one
-// (sub-)triangle (main.c:797-857, 871, 888-898). Returns false when the triangle is back-face culled
-// (signed_area > 0, main.c:856). Everything binning and Hi-Z need; the edge functions follow in setup_edges().
-__device__ __forceinline__ bool setup_project(const float4 &c0, const float4 &c1, const float4 &c2, const GeomParams &P, TriSetup &S) {
-	float4 p[3] = { c0, c1, c2 };
-#pragma unroll
-	for(int i = 0; i < 3; ++i) {
-		// a_reciprocal_ws[i] = 1.0 / w  (double divide rounded to f32 == correctly rounded f32 divide)
-		const float rw = 1.0f / p[i].w;
-		S.rw[i] = rw;
-		p[i].x *= rw;
-		p[i].y *= rw;
-		p[i].z *= rw;
-		p[i].w *= rw;
-		// m4x4f32_mul_v4f32(&screen_from_ndc, v): serial dot products with the literal zero entries
-		const float4 v = p[i];
-		float4 s;
-		s.x = P.vp_m00 * v.x + 0.0f * v.y + 0.0f * v.z + P.vp_m03 * v.w;
-		s.y = 0.0f * v.x + P.vp_m11 * v.y + 0.0f * v.z + P.vp_m13 * v.w;
-		s.z = 0.0f * v.x + 0.0f * v.y + P.vp_m22 * v.z + P.vp_m23 * v.w;
-		s.w = 0.0f * v.x + 0.0f * v.y + 0.0f * v.z + 1.0f * v.w;
-		S.p[i] = s;
-	}
-	const int x0 = snap(S.p[0].x), x1 = snap(S.p[1].x), x2 = snap(S.p[2].x);
-	const int y0 = snap(S.p[0].y), y1 = snap(S.p[1].y), y2 = snap(S.p[2].y);
+// Per-vertex part of primitive assembly (main.c:803-848): 1/w, projection, viewport transform, snap to 28.4.
+// A pure function of the clip-space position, so it can be evaluated once per vertex (k_vertex) or once per
+// triangle corner (as the reference does) with identical results.
+struct ProjVertex {
+	float4 s; // screen-space position (x, y, z, w ~ 1), what the reference stores back into register 0 (main.c:881-883)
+	float rw; // a_reciprocal_ws
+	int sx, sy;
+};
+__device__ __forceinline__ ProjVertex project_vertex(float4 p, const GeomParams &P) {
+	ProjVertex o;
+	// a_reciprocal_ws[i] = 1.0 / w  (double divide rounded to f32 == correctly rounded f32 divide)
+	const float rw = 1.0f / p.w;
+	o.rw = rw;
+	p.x *= rw;
+	p.y *= rw;
+	p.z *= rw;
+	p.w *= rw;
+	// m4x4f32_mul_v4f32(&screen_from_ndc, v): serial dot products with the literal zero entries
+	o.s.x = P.vp_m00 * p.x + 0.0f * p.y + 0.0f * p.z + P.vp_m03 * p.w;
+	o.s.y = 0.0f * p.x + P.vp_m11 * p.y + 0.0f * p.z + P.vp_m13 * p.w;
+	o.s.z = 0.0f * p.x + 0.0f * p.y + P.vp_m22 * p.z + P.vp_m23 * p.w;
+	o.s.w = 0.0f * p.x + 0.0f * p.y + 0.0f * p.z + 1.0f * p.w;
+	o.sx = snap(o.s.x);
+	o.sy = snap(o.s.y);
+	return o;
+}
+
+// Per-triangle part: signed area, face culling, max depth and bounds (main.c:851-857, 871, 888-898). Returns false
+// when the triangle is back-face culled (signed_area > 0, main.c:856). Everything binning and Hi-Z need; the edge
+// functions follow in setup_edges().
+__device__ __forceinline__ bool setup_from_projected(const ProjVertex &v0, const ProjVertex &v1, const ProjVertex &v2, const GeomParams &P, TriSetup &S) {
+	S.rw[0] = v0.rw, S.rw[1] = v1.rw, S.rw[2] = v2.rw;
+	S.p[0] = v0.s, S.p[1] = v1.s, S.p[2] = v2.s;
+	const int x0 = v0.sx, x1 = v1.sx, x2 = v2.sx, y0 = v0.sy, y1 = v1.sy, y2 = v2.sy;
 	S.sx[0] = x0, S.sx[1] = x1, S.sx[2] = x2;
 	S.sy[0] = y0, S.sy[1] = y1, S.sy[2] = y2;
 	S.signed_area = (int)(((uint32_t)x1 - (uint32_t)x0) * ((uint32_t)y2 - (uint32_t)y0) - ((uint32_t)x2 - (uint32_t)x0) * ((uint32_t)y1 - (uint32_t)y0));
@@ -112,6 +121,10 @@ __device__ __forceinline__ bool setup_project(const float4 &c0, const float4 &c1
 	S.maxx = min(mxx + 1, P.vp_w - 1);
 	S.maxy = min(mxy + 1, P.vp_h - 1);
 	return true;
+}
+
+__device__ __forceinline__ bool setup_project(const float4 &c0, const float4 &c1, const float4 &c2, const GeomParams &P, TriSetup &S) {
+	return setup_from_projected(project_vertex(c0, P), project_vertex(c1, P), project_vertex(c2, P), P, S);
 }
 
 // Edge functions, 1/area (main.c:858-866) and the no-wrap flag.
@@ -346,13 +359,23 @@ __device__ __noinline__ uint32_t clip_and_emit(const GeomParams &P, uint32_t t, 
 	poly[1] = v1;
 	poly[2] = v2;
 	const float k = P.clip_k;
+	// A plane pass reproduces its input vertex for vertex when the whole polygon is strictly inside (see
+	// clip_by_plane), and every polygon vertex is a convex combination of v0,v1,v2. So a plane that has the three
+	// ORIGINAL vertices inside by a margin that dwarfs the rounding error of the interpolated vertices
+	// (<= ~30 ulp of the largest coordinate, margin = 1e-3 of it) cannot clip anything and is skipped without
+	// being evaluated; planes closer than that go through the literal pass.
+	const float big = fmaxf(fmaxf(fabsf(v0.r0.x) + fabsf(v0.r0.y) + fabsf(v0.r0.z) + fabsf(v0.r0.w), fabsf(v1.r0.x) + fabsf(v1.r0.y) + fabsf(v1.r0.z) + fabsf(v1.r0.w)),
+	                        fabsf(v2.r0.x) + fabsf(v2.r0.y) + fabsf(v2.r0.z) + fabsf(v2.r0.w));
+	const float margin = 1e-3f * big;
 	int n = 3;
-	n = clip_by_plane(poly, n, make_float4(k, 0.0f, 0.0f, k));
-	n = clip_by_plane(poly, n, make_float4(-k, 0.0f, 0.0f, k));
-	n = clip_by_plane(poly, n, make_float4(0.0f, k, 0.0f, k));
-	n = clip_by_plane(poly, n, make_float4(0.0f, -k, 0.0f, k));
-	n = clip_by_plane(poly, n, make_float4(0.0f, 0.0f, k, k));
-	n = clip_by_plane(poly, n, make_float4(0.0f, 0.0f, -k, k));
+	const float4 planes[6] = { make_float4(k, 0.0f, 0.0f, k),  make_float4(-k, 0.0f, 0.0f, k), make_float4(0.0f, k, 0.0f, k),
+		                       make_float4(0.0f, -k, 0.0f, k), make_float4(0.0f, 0.0f, k, k),  make_float4(0.0f, 0.0f, -k, k) };
+#pragma unroll
+	for(int pl = 0; pl < 6; ++pl) {
+		const float d0 = dot4_serial(planes[pl], v0.r0), d1 = dot4_serial(planes[pl], v1.r0), d2 = dot4_serial(planes[pl], v2.r0);
+		if(fminf(fminf(d0, d1), d2) > margin) continue; // safely inside (false for NaN: literal pass)
+		n = clip_by_plane(poly, n, planes[pl]);
+	}
 	const int fan = n - 2;
 	if(fan <= 0) return 0u;
 	if(fan > 8) { // cannot happen for a convex clip of a triangle by six planes (<= 9 vertices)
@@ -382,21 +405,39 @@ __device__ __noinline__ uint32_t clip_and_emit(const GeomParams &P, uint32_t t, 
 }
 
 // Per-draw Stats contributions (main.c:1228-1246): one atomic per warp and counter.
-__device__ __forceinline__ void tally_stats(Counters *ctr, uint32_t emitted, uint32_t pairs) {
+// Stats go to one of MLV_STAT_STRIPES 64-bit accumulators, 128 bytes apart (L2 atomics serialise per address: with
+// one shared counter the ~40 k warps of a 1.25 M-triangle draw queued up behind each other). k_tile folds them.
+// High word: assembled triangles, low word: (triangle, tile) pairs.
+__device__ __forceinline__ void tally_stats(unsigned long long *stripes, uint32_t emitted, uint32_t pairs) {
 #pragma unroll
 	for(int d = 16; d > 0; d >>= 1) {
 		emitted += __shfl_xor_sync(0xffffffffu, emitted, d);
 		pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
 	}
-	if(lane_id() == 0) {
-		if(emitted) atomicAdd(&ctr->draw_tris, emitted);
-		if(pairs) atomicAdd(&ctr->draw_pairs_all, pairs);
+	if(lane_id() == 0 && (emitted | pairs)) {
+		const uint32_t stripe = (blockIdx.x * 8u + (threadIdx.x >> 5)) % MLV_STAT_STRIPES;
+		atomicAdd(stripes + stripe * 16u, ((unsigned long long)emitted << 32) | pairs);
 	}
 }
 
 #define MLV_GEOM_THREADS 256
 
-template <int VS, bool INDEXED, bool DEBUG>
+// Post-transform vertex cache (the reference's TODO at main.c:672; it re-shades every index, vertex_count =
+// index_count main.c:673). For indexed meshes that reuse vertices, k_vertex evaluates the position part of the vertex
+// shader and the per-vertex part of primitive assembly once per UNIQUE vertex; k_geom<VCACHE> then gathers 32 bytes
+// per corner from an L2-resident table instead of fetching, transforming, dividing and snapping it again. Both are
+// pure functions of the vertex, so the values are the ones the reference computes per corner.
+template <int VS>
+__global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ GeomParams P, uint32_t vertex_count) {
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if(v >= vertex_count) return;
+	const float4 pos = vs_position<VS>(__ldg(P.vb + 2 * (size_t)v), P.cb);
+	const ProjVertex pv = project_vertex(pos, P);
+	P.vcache[2 * (size_t)v] = pos;
+	P.vcache[2 * (size_t)v + 1] = make_float4(__int_as_float(pv.sx), __int_as_float(pv.sy), pv.s.z, pv.rw);
+}
+
+template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
 __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_constant__ GeomParams P) {
 	// Records are staged per warp in shared memory and written out as contiguous 512-byte rows: the 32 direct
 	// slots of a warp are adjacent in HBM, so the warp stores 1536 B of TriCov and 3072 B of TriShade with fully
@@ -422,9 +463,16 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 			vi1 = vi0 + 1u;
 			vi2 = vi0 + 2u;
 		}
-		const float4 a0 = __ldg(P.vb + 2 * (size_t)vi0), b0 = __ldg(P.vb + 2 * (size_t)vi1), c0 = __ldg(P.vb + 2 * (size_t)vi2);
-		// ---- vertex shader, position part (main.c:698-734)
-		const float4 a = vs_position<VS>(a0, P.cb), b = vs_position<VS>(b0, P.cb), c = vs_position<VS>(c0, P.cb);
+		float4 a0, b0, c0, a, b, c, qa, qb, qc; // first half of each input vertex; clip-space positions; cached per-vertex projection
+		if(VCACHE) {
+			a = __ldg(P.vcache + 2 * (size_t)vi0), qa = __ldg(P.vcache + 2 * (size_t)vi0 + 1);
+			b = __ldg(P.vcache + 2 * (size_t)vi1), qb = __ldg(P.vcache + 2 * (size_t)vi1 + 1);
+			c = __ldg(P.vcache + 2 * (size_t)vi2), qc = __ldg(P.vcache + 2 * (size_t)vi2 + 1);
+		} else {
+			a0 = __ldg(P.vb + 2 * (size_t)vi0), b0 = __ldg(P.vb + 2 * (size_t)vi1), c0 = __ldg(P.vb + 2 * (size_t)vi2);
+			// ---- vertex shader, position part (main.c:698-734)
+			a = vs_position<VS>(a0, P.cb), b = vs_position<VS>(b0, P.cb), c = vs_position<VS>(c0, P.cb);
+		}
 		if(DEBUG) {
 			const VsOut v0 = run_vs<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
 			const VsOut v1 = run_vs<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
@@ -446,7 +494,17 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 			    (a.y <= a.w && b.y <= b.w && c.y <= c.w) && (a.z >= 0.0f && b.z >= 0.0f && c.z >= 0.0f) && (a.z <= a.w && b.z <= b.w && c.z <= c.w);
 			if(inside) {
 				TriSetup S;
-				if(setup_project(a, b, c, P, S)) {
+				bool kept;
+				if(VCACHE) {
+					ProjVertex pa, pb, pc; // s.x, s.y, s.w are not needed outside debug capture (which never uses the cache)
+					pa.s = make_float4(0.0f, 0.0f, qa.z, 0.0f), pa.rw = qa.w, pa.sx = __float_as_int(qa.x), pa.sy = __float_as_int(qa.y);
+					pb.s = make_float4(0.0f, 0.0f, qb.z, 0.0f), pb.rw = qb.w, pb.sx = __float_as_int(qb.x), pb.sy = __float_as_int(qb.y);
+					pc.s = make_float4(0.0f, 0.0f, qc.z, 0.0f), pc.rw = qc.w, pc.sx = __float_as_int(qc.x), pc.sy = __float_as_int(qc.y);
+					kept = setup_from_projected(pa, pb, pc, P, S);
+				} else {
+					kept = setup_project(a, b, c, P, S);
+				}
+				if(kept) {
 					direct = true;
 					emitted = 1u;
 					// ---- binner pass 1 + Hi-Z for this triangle; a triangle hidden in every tile it touches writes no record
@@ -459,6 +517,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 						// ---- vertex shader, attribute part
 						float4 r1a, r1b, r1c;
 						float r2a, r2b, r2c;
+						if(VCACHE) a0 = __ldg(P.vb + 2 * (size_t)vi0), b0 = __ldg(P.vb + 2 * (size_t)vi1), c0 = __ldg(P.vb + 2 * (size_t)vi2);
 						vs_attributes<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), a, P.cb, P.vs_tex, P.rsqrt_lut, r1a, r2a);
 						vs_attributes<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), b, P.cb, P.vs_tex, P.rsqrt_lut, r1b, r2b);
 						vs_attributes<VS>(c0, __ldg(P.vb + 2 * (size_t)vi2 + 1), c, P.cb, P.vs_tex, P.rsqrt_lut, r1c, r2c);
@@ -522,7 +581,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 			if((valid >> (chunk / MLV_TRI_SHADE_U4)) & 1u) sh[chunk] = st[32 * MLV_TRI_COV_U4 + chunk];
 		}
 	}
-	tally_stats(P.ctr, emitted, pairs);
+	tally_stats(P.stat_stripes, emitted, pairs);
 	if(t == 0) {
 		P.ctr->stats.vertex_count += P.index_count;
 		P.ctr->stats.input_triangle_count += P.tri_count;
@@ -548,7 +607,7 @@ __global__ void __launch_bounds__(128) k_geom_clip(const __grid_constant__ GeomP
 		const VsOut v2 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi2), __ldg(P.vb + 2 * (size_t)vi2 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
 		emitted += clip_and_emit(P, t, v0, v1, v2, pairs);
 	}
-	tally_stats(P.ctr, emitted, pairs);
+	tally_stats(P.stat_stripes, emitted, pairs);
 }
 
 // =================================================================================================
@@ -604,9 +663,7 @@ __global__ void __launch_bounds__(256) k_bin_big(const __grid_constant__ BinPara
 			else atomicAdd(P.bin_count + bin, 1u);
 		}
 	}
-#pragma unroll
-	for(int d = 16; d > 0; d >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
-	if(lane == 0 && pairs) atomicAdd(&P.ctr->draw_pairs_all, pairs);
+	tally_stats(P.stat_stripes, 0u, pairs);
 }
 
 // Pass 2 of the binner (main.c:950-962): every surviving (triangle, tile) pair takes the next position of its
@@ -981,14 +1038,29 @@ template <int PS>
 __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant__ TileParams P, uint32_t pair_capacity) {
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-	if(blockIdx.x == 0 && threadIdx.x == 0) { // every earlier kernel of this draw is done with these: fold them into Stats, re-arm for the next draw
-		Counters *c = P.ctr;
-		c->stats.assembled_triangle_count += c->draw_tris;
-		c->stats.total_triangle_count_in_bins += c->draw_pairs_all;
-		c->stats.active_bin_count += c->draw_active_bins;
-		c->last_ovf_count = c->ovf_count;
-		c->draw_tris = c->draw_pairs_all = c->draw_active_bins = 0u;
-		c->ovf_count = c->clip_count = c->big_count = c->huge_count = 0u;
+	if(blockIdx.x == 0 && threadIdx.x < 32) { // every earlier kernel of this draw is done with these: fold them into Stats, re-arm for the next draw
+		uint32_t tris = 0, pairs = 0;
+#pragma unroll
+		for(uint32_t i = lane; i < MLV_STAT_STRIPES; i += 32u) {
+			const unsigned long long v = P.stat_stripes[i * 16u];
+			P.stat_stripes[i * 16u] = 0ull;
+			tris += (uint32_t)(v >> 32);
+			pairs += (uint32_t)v;
+		}
+#pragma unroll
+		for(int d = 16; d > 0; d >>= 1) {
+			tris += __shfl_xor_sync(0xffffffffu, tris, d);
+			pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
+		}
+		if(lane == 0) {
+			Counters *c = P.ctr;
+			c->stats.assembled_triangle_count += tris;
+			c->stats.total_triangle_count_in_bins += pairs;
+			c->stats.active_bin_count += c->draw_active_bins;
+			c->last_ovf_count = c->ovf_count;
+			c->draw_active_bins = 0u;
+			c->ovf_count = c->clip_count = c->big_count = c->huge_count = 0u;
+		}
 	}
 	if(P.ctr->pair_total > pair_capacity) return; // draw skipped, MLV_FLAG_PAIR_OVERFLOW is set
 	const uint32_t n_cbins = P.ctr->n_cbins;

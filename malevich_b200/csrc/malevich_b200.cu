@@ -68,10 +68,13 @@ struct mlv_device {
 	uint4 *tri_cov, *tri_shade;
 	uint4 *tri_bounds;
 	uint32_t *clip_queue, *big_queue, *huge_queue;
+	float4 *vcache;
+	uint32_t vcache_capacity;
 	uint32_t tri_capacity; // slots (direct + overflow)
 	unsigned long long *scan_state; // 2 x scan_blocks look-back words
 	uint32_t scan_blocks;
 	Counters *ctr;
+	unsigned long long *stat_stripes;
 	uint32_t *rsqrt_lut;
 	// debug capture
 	DebugOut dbg;
@@ -205,6 +208,8 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	CREATE_TRY(cudaMalloc(&dev->pair_ids, dev->pair_capacity * sizeof(uint32_t)));
 	CREATE_TRY(cudaMalloc(&dev->pair_tmp, dev->pair_capacity * sizeof(uint32_t)));
 	CREATE_TRY(cudaMalloc(&dev->ctr, sizeof(Counters)));
+	CREATE_TRY(cudaMalloc(&dev->stat_stripes, MLV_STAT_STRIPES * 128));
+	CREATE_TRY(cudaMemsetAsync(dev->stat_stripes, 0, MLV_STAT_STRIPES * 128, dev->stream));
 	dev->scan_blocks = (dev->num_bins + MLV_SCAN_THREADS * MLV_SCAN_ITEMS - 1) / (MLV_SCAN_THREADS * MLV_SCAN_ITEMS);
 	CREATE_TRY(cudaMalloc(&dev->scan_state, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long)));
 	CREATE_TRY(cudaMemsetAsync(dev->scan_state, 0, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long), dev->stream));
@@ -234,8 +239,8 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(!dev) return;
 	cudaSetDevice(dev->cuda_dev);
 	if(dev->stream) cudaStreamSynchronize(dev->stream);
-	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue,
-		             dev->scan_state, dev->ctr, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
+	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue, dev->vcache,
+		             dev->scan_state, dev->ctr, dev->stat_stripes, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
 	if(dev->stream) cudaStreamDestroy(dev->stream);
@@ -436,12 +441,16 @@ static TexDesc tex_desc(const mlv_texture *t) {
 }
 
 template <int VS>
-static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed) {
+static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed, uint32_t vcache_vertices) {
 	const bool debug = gp.keep_all;
-	if(indexed && debug) k_geom<VS, true, true><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
-	else if(indexed) k_geom<VS, true, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
-	else if(debug) k_geom<VS, false, true><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
-	else k_geom<VS, false, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+	if(vcache_vertices) {
+		k_vertex<VS><<<(vcache_vertices + 255u) / 256u, 256, 0, dev->stream>>>(gp, vcache_vertices);
+		dev->launches++;
+		k_geom<VS, true, false, true><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+	} else if(indexed && debug) k_geom<VS, true, true, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+	else if(indexed) k_geom<VS, true, false, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+	else if(debug) k_geom<VS, false, true, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+	else k_geom<VS, false, false, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
 }
 template <int VS>
 static void launch_geom_clip(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed) {
@@ -553,14 +562,30 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	gp.keep_all = debug;
 	if(debug) gp.dbg = dev->dbg;
 	gp.ctr = dev->ctr;
+	gp.stat_stripes = dev->stat_stripes;
 	gp.index_count = count;
 
+	// Post-transform vertex cache: worth it when the index buffer references each vertex of the buffer about twice or
+	// more (the bound vertex buffer's size is the only vertex count a D3D11-style draw call has).
+	uint32_t vcache_vertices = 0;
+	if(indexed && !debug) {
+		const uint64_t vb_vertices = dev->vb->bytes / 32;
+		if(vb_vertices > 0 && vb_vertices <= 0x7fffffffull && (uint64_t)count >= 2 * vb_vertices) {
+			vcache_vertices = (uint32_t)vb_vertices;
+			if(vcache_vertices > dev->vcache_capacity) {
+				CUDA_TRY(cudaStreamSynchronize(dev->stream));
+				CUDA_TRY(regrow(&dev->vcache, (size_t)vcache_vertices * 2));
+				dev->vcache_capacity = vcache_vertices;
+			}
+			gp.vcache = dev->vcache;
+		}
+	}
 	prof_pre(dev, MLV_STAGE_GEOMETRY);
 	switch(dev->vs_id) {
-		case MLV_VS_PASSTHROUGH: launch_geom<0>(dev, gp, nblocks, indexed); break;
-		case MLV_VS_BASIC: launch_geom<1>(dev, gp, nblocks, indexed); break;
-		case MLV_VS_VERTEX_LIGHTING: launch_geom<2>(dev, gp, nblocks, indexed); break;
-		default: launch_geom<3>(dev, gp, nblocks, indexed); break;
+		case MLV_VS_PASSTHROUGH: launch_geom<0>(dev, gp, nblocks, indexed, vcache_vertices); break;
+		case MLV_VS_BASIC: launch_geom<1>(dev, gp, nblocks, indexed, vcache_vertices); break;
+		case MLV_VS_VERTEX_LIGHTING: launch_geom<2>(dev, gp, nblocks, indexed, vcache_vertices); break;
+		default: launch_geom<3>(dev, gp, nblocks, indexed, vcache_vertices); break;
 	}
 	if(int rc = check_launch(dev, "k_geom")) return rc;
 	{ // clipping pass over the (device-side) queue; a modest persistent grid, most draws queue few or no triangles
@@ -586,6 +611,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	bp.bin_offset = dev->bin_offset;
 	bp.pair_ids = dev->pair_ids;
 	bp.ctr = dev->ctr;
+	bp.stat_stripes = dev->stat_stripes;
 	bp.direct_slots = T;
 	bp.num_bins = dev->num_bins;
 	bp.wt = dev->wt;
@@ -633,6 +659,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	tp.fb = dev->fb;
 	tp.tile_min = dev->tile_min;
 	tp.ctr = dev->ctr;
+	tp.stat_stripes = dev->stat_stripes;
 	tp.ps_tex = tex_desc(dev->ps_srv[0]);
 	tp.rsqrt_lut = dev->rsqrt_lut;
 	if(debug) tp.dbg = dev->dbg;

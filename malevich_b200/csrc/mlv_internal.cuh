@@ -33,6 +33,7 @@ namespace mlv {
 #define MLV_NOWRAP_BIT 0x80000000u /* bit 15 of miny inside word 10 */
 
 #define MLV_NO_WINNER 0xffffffffu
+#define MLV_STAT_STRIPES 64u
 #define MLV_TOUCHED 0x80000000u          /* bin_count flag: bin is non-empty in the reference's sense but (so far) holds only Hi-Z-rejected pairs */
 #define MLV_TILE_MIN_CLEARED 0x80000000u /* tile_min bit pattern (-0.0f) the depth clear writes: equals 0.0 in every comparison, marks "never refreshed" */
 
@@ -84,6 +85,7 @@ struct GeomParams {
 	uint4 *tri_cov;
 	uint4 *tri_shade;
 	uint4 *tri_bounds;
+	float4 *vcache; // 2 x float4 per unique vertex: clip-space position, {snapped x, snapped y, screen z, 1/w}
 	uint32_t *clip_queue;
 	uint32_t *big_queue;
 	uint32_t *huge_queue;
@@ -92,6 +94,7 @@ struct GeomParams {
 	bool keep_all; // debug capture: no Hi-Z at binning time, lists hold every pair like the reference's
 	DebugOut dbg;
 	Counters *ctr;
+	unsigned long long *stat_stripes;
 	uint32_t index_count;
 };
 
@@ -104,6 +107,7 @@ struct BinParams {
 	uint32_t *bin_offset;
 	uint32_t *pair_ids;
 	Counters *ctr;
+	unsigned long long *stat_stripes;
 	uint32_t direct_slots; // T
 	uint32_t num_bins;
 	int wt, ht;
@@ -132,6 +136,7 @@ struct TileParams {
 	uint4 *fb;
 	float *tile_min;
 	Counters *ctr;
+	unsigned long long *stat_stripes;
 	TexDesc ps_tex;
 	const uint32_t *rsqrt_lut;
 	DebugOut dbg;
