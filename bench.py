@@ -169,7 +169,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if multi:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     scene = build_scene(args.config)
-    dev = Device(scene.width, scene.height, cuda_device=local_rank, num_ranks=world, rank=rank, stripe_height_tiles=args.stripe)
+    # sort-first split: by default one contiguous band of tile rows per rank (lets a rank skip geometry chunks outside its band)
+    stripe = args.stripe if args.stripe > 0 else max(1, -(-(scene.height // 8) // world))
+    dev = Device(scene.width, scene.height, cuda_device=local_rank, num_ranks=world, rank=rank, stripe_height_tiles=stripe)
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local_rank))
     scenes.upload(dev, scene)
 
@@ -221,8 +223,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     dev.reset_stats()
     frame()
     stats_local = dev.stats()
-    stats = reduce_sum_dict({k: stats_local[k] for k in ("active_bin_count", "total_triangle_count_in_bins")})
-    stats["assembled_triangle_count"] = stats_local["assembled_triangle_count"]  # replicated front-end: identical on every rank
+    # per-rank shares (a triangle is counted by the rank that owns its first tile row); the sum is the reference's Stats
+    stats = reduce_sum_dict({k: stats_local[k] for k in ("assembled_triangle_count", "active_bin_count", "total_triangle_count_in_bins")})
 
     # ---- timed region: device-resident inputs, CUDA events on the launching stream, max over ranks
     sampler = ClockSampler(local_rank)
@@ -319,7 +321,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "mtri_per_s": scene.input_triangles * fps / 1e6, "gpix_per_s": scene.width * scene.height * fps / 1e9,
             "config": {"workload": workload_name(args.config, scene), "input_triangles": scene.input_triangles, "draws": len(scene.objects),
                        "assembled_triangles": stats["assembled_triangle_count"], "tri_tile_pairs": stats["total_triangle_count_in_bins"],
-                       "tile_draws": stats["active_bin_count"], "parallelism": f"sort-first x{world}, stripe {args.stripe} tile rows" if multi else "single GPU",
+                       "tile_draws": stats["active_bin_count"], "parallelism": f"sort-first x{world}, stripe {stripe} tile rows" if multi else "single GPU",
                        "l2": "no flush: per-frame working set (inputs + per-draw setup records) >> 126 MB L2" if args.config == 5 else "no flush"},
             "roofline": {"bound": "hbm", "kernel": {"geometry": "k_geom", "tile": "k_tile", "bin": "k_bin+k_bin_scan"}[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes_per_launch,
@@ -346,7 +348,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5])
-    ap.add_argument("--stripe", type=int, default=1, help="stripe height in tile rows for the sort-first split")
+    ap.add_argument("--stripe", type=int, default=0, help="stripe height in tile rows for the sort-first split (0 = one contiguous band per rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

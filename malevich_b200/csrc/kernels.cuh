@@ -23,9 +23,9 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 // clear
 // =================================================================================================
 // mode bit 0: colour, bit 1: depth (+ tile minima := 0, main.c:1212-1214)
-__global__ void __launch_bounds__(256) k_clear(uint4 *__restrict__ fb, float *__restrict__ tile_min, uint32_t num_bins, uint32_t color, float depth, int mode) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= num_bins * 32u) return;
+__global__ void __launch_bounds__(256) k_clear(uint4 *__restrict__ fb, float *__restrict__ tile_min, uint32_t bin_begin, uint32_t bin_end, uint32_t color, float depth, int mode) {
+	const uint32_t i = bin_begin * 32u + blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= bin_end * 32u) return;
 	const uint32_t d = __float_as_uint(depth);
 	if(mode == 3) {
 		fb[i] = make_uint4(color, color, d, d);
@@ -351,10 +351,8 @@ __device__ __forceinline__ uint32_t emit_triangle(const GeomParams &P, uint32_t 
 	return tally.pairs;
 }
 
-// Clipper (main.c:649-660) + fan triangulation (main.c:797). The fan triangles take consecutive overflow slots;
-// slot t becomes a redirect to them. Returns the number of assembled triangles, adds the pairs to `pairs`.
-__device__ __noinline__ uint32_t clip_and_emit(const GeomParams &P, uint32_t t, const VsOut &v0, const VsOut &v1, const VsOut &v2, uint32_t &pairs) {
-	VsOut poly[16];
+// Clipper (main.c:649-660): returns the vertex count of the clipped polygon left in poly[].
+__device__ __noinline__ int clip_polygon(const GeomParams &P, const VsOut &v0, const VsOut &v1, const VsOut &v2, VsOut *poly) {
 	poly[0] = v0;
 	poly[1] = v1;
 	poly[2] = v2;
@@ -376,17 +374,12 @@ __device__ __noinline__ uint32_t clip_and_emit(const GeomParams &P, uint32_t t, 
 		if(fminf(fminf(d0, d1), d2) > margin) continue; // safely inside (false for NaN: literal pass)
 		n = clip_by_plane(poly, n, planes[pl]);
 	}
-	const int fan = n - 2;
-	if(fan <= 0) return 0u;
-	if(fan > 8) { // cannot happen for a convex clip of a triangle by six planes (<= 9 vertices)
-		atomicOr(&P.ctr->error_flags, MLV_FLAG_TRI_OVERFLOW);
-		return 0u;
-	}
-	const uint32_t base = atomicAdd(&P.ctr->ovf_count, (uint32_t)fan);
-	if(base + (uint32_t)fan > P.ovf_capacity) {
-		atomicOr(&P.ctr->error_flags, MLV_FLAG_TRI_OVERFLOW);
-		return 0u;
-	}
+	return n;
+}
+
+// Fan triangulation (main.c:797) of a clipped polygon into the consecutive overflow slots T + base + j; slot t
+// becomes a redirect to them. Returns the number of assembled triangles, adds the pairs to `pairs`.
+__device__ __noinline__ uint32_t emit_fan(const GeomParams &P, uint32_t t, const VsOut *poly, int fan, uint32_t base, uint32_t &pairs) {
 	P.tri_cov[(size_t)t * MLV_TRI_COV_U4 + 2] = make_uint4(base, 0u, MLV_REDIRECT, 0u);
 	uint32_t emitted = 0;
 	for(int j = 0; j < fan; ++j) {
@@ -395,7 +388,7 @@ __device__ __noinline__ uint32_t clip_and_emit(const GeomParams &P, uint32_t t, 
 		TriSetup S;
 		if(setup_triangle(poly[0].r0, poly[j + 1].r0, poly[j + 2].r0, P, S)) {
 			pairs += emit_triangle(P, slot, key, S, poly[0].r1, poly[j + 1].r1, poly[j + 2].r1, poly[0].r2x, poly[j + 1].r2x, poly[j + 2].r2x);
-			++emitted;
+			if(P.part.owns_row(S.miny / 8)) ++emitted;
 		} else {
 			P.tri_bounds[slot] = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, key);
 			if(P.dbg.slot_key) P.dbg.slot_key[slot] = 0xffffffffu;
@@ -421,6 +414,90 @@ __device__ __forceinline__ void tally_stats(unsigned long long *stripes, uint32_
 }
 
 #define MLV_GEOM_THREADS 256
+
+// ---- sort-first chunk culling (multi-GPU only) -------------------------------------------
+// A chunk = the MLV_GEOM_THREADS input triangles of one k_geom CTA. k_chunk_bounds computes the object-space AABB of
+// each chunk once per (vertex buffer, index buffer) pair; it is cached with the index buffer until either buffer is
+// updated. Per draw, each k_geom CTA projects the 8 corners of its chunk's box and skips the whole chunk -- no index
+// or vertex fetch -- when no tile row in the box's conservative screen-y range belongs to this rank. With contiguous
+// bands per rank a rank then fetches and shades ~1/N of the geometry instead of all of it.
+// Only for the vertex shaders whose SV_POSITION is clip_from_world * POSITION.xyz (basic_vs, vertex_lighting_vs).
+template <bool INDEXED>
+__global__ void __launch_bounds__(MLV_GEOM_THREADS) k_chunk_bounds(const uint32_t *__restrict__ ib, const float4 *__restrict__ vb, uint32_t tri_count, float4 *__restrict__ chunk_bounds) {
+	__shared__ float s_min[3][MLV_GEOM_THREADS / 32], s_max[3][MLV_GEOM_THREADS / 32];
+	__shared__ int s_bad[MLV_GEOM_THREADS / 32];
+	const uint32_t t = blockIdx.x * MLV_GEOM_THREADS + threadIdx.x;
+	float mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY };
+	int bad = 0;
+	if(t < tri_count) {
+#pragma unroll
+		for(int c = 0; c < 3; ++c) {
+			const uint32_t vi = INDEXED ? __ldg(ib + 3u * t + c) : 3u * t + c;
+			const float4 p = __ldg(vb + 2 * (size_t)vi);
+			const float q[3] = { p.x, p.y, p.z };
+#pragma unroll
+			for(int k = 0; k < 3; ++k) {
+				if(!(fabsf(q[k]) <= 3.0e38f)) bad = 1; // NaN / Inf: never cull this chunk
+				mn[k] = fminf(mn[k], q[k]);
+				mx[k] = fmaxf(mx[k], q[k]);
+			}
+		}
+	}
+#pragma unroll
+	for(int d = 16; d > 0; d >>= 1) {
+#pragma unroll
+		for(int k = 0; k < 3; ++k) {
+			mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], d));
+			mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], d));
+		}
+		bad |= __shfl_xor_sync(0xffffffffu, bad, d);
+	}
+	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+	if(lane == 0) {
+		for(int k = 0; k < 3; ++k) s_min[k][warp] = mn[k], s_max[k][warp] = mx[k];
+		s_bad[warp] = bad;
+	}
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		for(int w = 1; w < MLV_GEOM_THREADS / 32; ++w) {
+			for(int k = 0; k < 3; ++k) mn[k] = fminf(mn[k], s_min[k][w]), mx[k] = fmaxf(mx[k], s_max[k][w]);
+			bad |= s_bad[w];
+		}
+		chunk_bounds[2 * (size_t)blockIdx.x] = make_float4(mn[0], mn[1], mn[2], bad ? 1.0f : 0.0f);
+		chunk_bounds[2 * (size_t)blockIdx.x + 1] = make_float4(mx[0], mx[1], mx[2], 0.0f);
+	}
+}
+
+// true when the chunk certainly bins nothing on this rank. Executed by the first warp of a CTA (lanes 0-7: corners).
+__device__ __forceinline__ bool chunk_is_foreign(const GeomParams &P, uint32_t chunk) {
+	const float4 lo = __ldg(P.chunk_bounds + 2 * (size_t)chunk), hi = __ldg(P.chunk_bounds + 2 * (size_t)chunk + 1);
+	const uint32_t lane = lane_id();
+	const float4 corner = make_float4((lane & 1u) ? hi.x : lo.x, (lane & 2u) ? hi.y : lo.y, (lane & 4u) ? hi.z : lo.z, 1.0f);
+	const float4 cs = mul_m4_v4_pairwise(P.cb, corner);
+	// behind or near the eye plane the projection of the box is unbounded: keep the chunk
+	const bool ok = cs.w > 1e-6f && fabsf(cs.y) <= 3.0e38f;
+	const float ys = P.vp_m11 * (cs.y / cs.w) + P.vp_m13; // screen y of the corner (the exact path adds rounding of a few ulp)
+	float ymin = ok ? ys : -INFINITY, ymax = ok ? ys : INFINITY;
+	bool all_ok = ok;
+#pragma unroll
+	for(int d = 4; d > 0; d >>= 1) {
+		ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, d));
+		ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, d));
+		const int other_ok = __shfl_xor_sync(0xffffffffu, (int)all_ok, d); // (not inside the &&: every lane must execute the shuffle)
+		all_ok = all_ok && other_ok;
+	}
+	if(!all_ok || lo.w != 0.0f) return false;
+	// conservative tile-row range: 2 pixels of slack for rounding + the +1 of max_bounds (main.c:897-898), clamped like
+	// min_bounds/max_bounds are (main.c:892-898)
+	const float h = (float)P.vp_h;
+	const int py0 = (int)floorf(fminf(fmaxf(ymin - 2.0f, 0.0f), h - 1.0f));
+	const int py1 = (int)floorf(fminf(fmaxf(ymax + 3.0f, 0.0f), h - 1.0f));
+	const int s0 = (py0 >> 3) / P.part.stripe_h, s1 = (py1 >> 3) / P.part.stripe_h;
+	if(s1 - s0 + 1 >= P.part.num_ranks) return false;
+	for(int st = s0; st <= s1; ++st)
+		if(st % P.part.num_ranks == P.part.rank) return false;
+	return true;
+}
 
 // Post-transform vertex cache (the reference's TODO at main.c:672; it re-shades every index, vertex_count =
 // index_count main.c:673). For indexed meshes that reuse vertices, k_vertex evaluates the position part of the vertex
@@ -449,6 +526,22 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 	bool needs_clip = false, is_big = false;
 	bool staged = false; // this lane has a record for its direct slot t
 	uint4 bounds = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, t << 3);
+	if(t == 0) { // Stats (main.c:1228-1232)
+		P.ctr->stats.vertex_count += P.index_count;
+		P.ctr->stats.input_triangle_count += P.tri_count;
+	}
+	if(P.chunk_bounds) { // sort-first: skip chunks that cannot touch this rank's tile rows
+		__shared__ int s_foreign;
+		if(warp == 0) {
+			const bool foreign = chunk_is_foreign(P, blockIdx.x);
+			if(lane == 0) {
+				s_foreign = foreign;
+				P.chunk_live[blockIdx.x] = foreign ? 0 : 1;
+			}
+		}
+		__syncthreads();
+		if(s_foreign) return;
+	}
 	if(t < P.tri_count) {
 		// ---- input assembler (main.c:662-696): index fetch + vertex fetch. Work is done lazily: positions for every
 		// triangle, the second half of each vertex and the attribute part of the vertex shader only for triangles
@@ -506,7 +599,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 				}
 				if(kept) {
 					direct = true;
-					emitted = 1u;
+					emitted = P.part.owns_row(S.miny / 8) ? 1u : 0u; // counted once across ranks: by the owner of its first tile row
 					// ---- binner pass 1 + Hi-Z for this triangle; a triangle hidden in every tile it touches writes no record
 					const BinTally tally = count_bins(P, S);
 					pairs = tally.pairs;
@@ -582,10 +675,6 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 		}
 	}
 	tally_stats(P.stat_stripes, emitted, pairs);
-	if(t == 0) {
-		P.ctr->stats.vertex_count += P.index_count;
-		P.ctr->stats.input_triangle_count += P.tri_count;
-	}
 }
 
 // Clipping pass: one thread per queued input triangle (dense, unlike the sparse occurrences inside k_geom's warps).
@@ -593,19 +682,47 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 template <int VS, bool INDEXED>
 __global__ void __launch_bounds__(128) k_geom_clip(const __grid_constant__ GeomParams P) {
 	const uint32_t n = P.ctr->clip_count;
+	const uint32_t lane = lane_id();
 	uint32_t emitted = 0, pairs = 0;
-	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		const uint32_t t = P.clip_queue[i];
-		uint32_t vi0 = 3u * t, vi1 = 3u * t + 1u, vi2 = 3u * t + 2u;
-		if(INDEXED) {
-			vi0 = __ldg(P.ib + vi0);
-			vi1 = __ldg(P.ib + vi1);
-			vi2 = __ldg(P.ib + vi2);
+	// warp-uniform trip count: the overflow slots of a whole warp are taken with ONE atomic (7 000 same-address atomics
+	// with return value per draw were a serial chain of their own)
+	for(uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
+		const uint32_t i = i0 + lane;
+		VsOut poly[16];
+		int fan = 0;
+		uint32_t t = 0;
+		if(i < n) {
+			t = P.clip_queue[i];
+			uint32_t vi0 = 3u * t, vi1 = 3u * t + 1u, vi2 = 3u * t + 2u;
+			if(INDEXED) {
+				vi0 = __ldg(P.ib + vi0);
+				vi1 = __ldg(P.ib + vi1);
+				vi2 = __ldg(P.ib + vi2);
+			}
+			const VsOut v0 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi0), __ldg(P.vb + 2 * (size_t)vi0 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
+			const VsOut v1 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi1), __ldg(P.vb + 2 * (size_t)vi1 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
+			const VsOut v2 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi2), __ldg(P.vb + 2 * (size_t)vi2 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
+			fan = clip_polygon(P, v0, v1, v2, poly) - 2;
+			if(fan > 8) { // cannot happen for a convex clip of a triangle by six planes (<= 9 vertices)
+				atomicOr(&P.ctr->error_flags, MLV_FLAG_TRI_OVERFLOW);
+				fan = 0;
+			}
+			if(fan < 0) fan = 0;
 		}
-		const VsOut v0 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi0), __ldg(P.vb + 2 * (size_t)vi0 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
-		const VsOut v1 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi1), __ldg(P.vb + 2 * (size_t)vi1 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
-		const VsOut v2 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi2), __ldg(P.vb + 2 * (size_t)vi2 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
-		emitted += clip_and_emit(P, t, v0, v1, v2, pairs);
+		uint32_t incl = (uint32_t)fan;
+#pragma unroll
+		for(int d = 1; d < 32; d <<= 1) {
+			const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+			if(lane >= (uint32_t)d) incl += o;
+		}
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+		uint32_t base = 0;
+		if(lane == 0 && total) base = atomicAdd(&P.ctr->ovf_count, total);
+		base = __shfl_sync(0xffffffffu, base, 0) + incl - (uint32_t)fan;
+		if(fan > 0) {
+			if(base + (uint32_t)fan > P.ovf_capacity) atomicOr(&P.ctr->error_flags, MLV_FLAG_TRI_OVERFLOW);
+			else emitted += emit_fan(P, t, poly, fan, base, pairs);
+		}
 	}
 	tally_stats(P.stat_stripes, emitted, pairs);
 }
@@ -679,7 +796,7 @@ __device__ __forceinline__ void fill_one(const BinParams &P, int k, int cnt, int
 }
 
 __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinParams P, uint32_t pair_capacity) {
-	if(P.ctr->pair_total > pair_capacity) return; // draw skipped, MLV_FLAG_PAIR_OVERFLOW is set
+	if(P.ctr->pair_total > pair_capacity || P.ctr->pair_total == 0u) return; // draw skipped (MLV_FLAG_PAIR_OVERFLOW is set) / nothing survived Hi-Z
 	const uint32_t n = P.direct_slots + P.ctr->ovf_count;
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -687,7 +804,9 @@ __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinPar
 		const uint32_t slot = base + lane;
 		SlotBounds s;
 		s.empty = true;
-		if(slot < n) s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
+		// slots of chunks k_geom skipped on this rank hold stale bounds from an earlier draw
+		const bool live_chunk = !P.chunk_live || slot >= P.direct_slots || __ldg(P.chunk_live + slot / MLV_GEOM_THREADS) != 0;
+		if(slot < n && live_chunk) s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
 		const int w = s.empty ? 0 : s.tr.w(), cnt = s.empty ? 0 : w * s.tr.h();
 		if(cnt > 0 && cnt <= 8) { // unrolled, predicated walk: all tile-minimum loads, then all atomics, then all stores
 			uint32_t bins[8], pos[8];
@@ -791,16 +910,16 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 	__syncthreads();
 	const uint32_t tile = s_tile;
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-	const uint32_t base = (tile * MLV_SCAN_THREADS + threadIdx.x) * MLV_SCAN_ITEMS; // 4 consecutive bins per thread, 16-byte accesses
+	const uint32_t base = P.bin_begin + (tile * MLV_SCAN_THREADS + threadIdx.x) * MLV_SCAN_ITEMS; // 4 consecutive bins per thread, 16-byte accesses
 	uint32_t raw[MLV_SCAN_ITEMS], c[MLV_SCAN_ITEMS];
 	bool work[MLV_SCAN_ITEMS];
-	const bool full = base + MLV_SCAN_ITEMS <= P.num_bins;
+	const bool full = base + MLV_SCAN_ITEMS <= P.bin_end;
 	if(full) {
 		const uint4 r = *reinterpret_cast<const uint4 *>(P.bin_count + base);
 		raw[0] = r.x, raw[1] = r.y, raw[2] = r.z, raw[3] = r.w;
 	} else {
 #pragma unroll
-		for(int k = 0; k < MLV_SCAN_ITEMS; ++k) raw[k] = (base + k < P.num_bins) ? P.bin_count[base + k] : 0u;
+		for(int k = 0; k < MLV_SCAN_ITEMS; ++k) raw[k] = (base + k < P.bin_end) ? P.bin_count[base + k] : 0u;
 	}
 	uint32_t tsum = 0, twork = 0, tne = 0;
 #pragma unroll
@@ -816,7 +935,7 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 		if(full) *reinterpret_cast<uint4 *>(P.bin_count + base) = make_uint4(0u, 0u, 0u, 0u);
 		else
 			for(int k = 0; k < MLV_SCAN_ITEMS; ++k)
-				if(base + k < P.num_bins) P.bin_count[base + k] = 0u;
+				if(base + k < P.bin_end) P.bin_count[base + k] = 0u;
 	}
 	uint32_t incl = tsum, wincl_work = twork;
 #pragma unroll
@@ -877,7 +996,7 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 	if(full) *reinterpret_cast<uint4 *>(P.bin_offset + base) = make_uint4(offs[0], offs[1], offs[2], offs[3]);
 	else
 		for(int k = 0; k < MLV_SCAN_ITEMS; ++k)
-			if(base + k < P.num_bins) P.bin_offset[base + k] = offs[k];
+			if(base + k < P.bin_end) P.bin_offset[base + k] = offs[k];
 }
 
 // =================================================================================================

@@ -42,6 +42,13 @@ struct mlv_buffer {
 	void *d;
 	size_t bytes;
 	int kind;
+	uint64_t version;          // bumped by every update
+	// sort-first chunk bounds cached with the buffer that defines the triangle list (index buffer, or vertex buffer for mlv_draw)
+	float4 *chunk_bounds;
+	uint32_t chunk_capacity, chunk_count;
+	const mlv_buffer *chunk_vb;
+	uint64_t chunk_vb_version, chunk_self_version;
+	int chunk_indexed;
 };
 struct mlv_texture {
 	void *d;
@@ -70,6 +77,9 @@ struct mlv_device {
 	uint32_t *clip_queue, *big_queue, *huge_queue;
 	float4 *vcache;
 	uint32_t vcache_capacity;
+	uint8_t *chunk_live;
+	uint32_t chunk_live_capacity;
+	uint32_t bin_begin, bin_end; // bins this rank can touch: everything, or one contiguous band
 	uint32_t tri_capacity; // slots (direct + overflow)
 	unsigned long long *scan_state; // 2 x scan_blocks look-back words
 	uint32_t scan_blocks;
@@ -180,6 +190,15 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	dev->part.num_ranks = (int)num_ranks;
 	dev->part.rank = (int)desc->rank;
 	dev->part.stripe_h = desc->stripe_height_tiles ? (int)desc->stripe_height_tiles : 1;
+	dev->bin_begin = 0;
+	dev->bin_end = dev->num_bins;
+	if(num_ranks > 1 && (uint64_t)dev->part.stripe_h * num_ranks >= (uint64_t)dev->ht) { // one contiguous band of tile rows per rank
+		const uint32_t row_lo = (uint32_t)dev->part.stripe_h * desc->rank;
+		const uint32_t row_hi = row_lo + (uint32_t)dev->part.stripe_h;
+		dev->bin_begin = (row_lo < (uint32_t)dev->ht ? row_lo : (uint32_t)dev->ht) * (uint32_t)dev->wt;
+		dev->bin_end = (row_hi < (uint32_t)dev->ht ? row_hi : (uint32_t)dev->ht) * (uint32_t)dev->wt;
+		dev->bin_begin &= ~3u; // k_bin_scan uses 16-byte accesses
+	}
 	dev->pair_capacity = desc->max_pairs_per_draw ? desc->max_pairs_per_draw : (16ull << 20);
 	if(dev->pair_capacity > 0xfffffff0ull) dev->pair_capacity = 0xfffffff0ull;
 	dev->epoch = 0;
@@ -210,7 +229,8 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	CREATE_TRY(cudaMalloc(&dev->ctr, sizeof(Counters)));
 	CREATE_TRY(cudaMalloc(&dev->stat_stripes, MLV_STAT_STRIPES * 128));
 	CREATE_TRY(cudaMemsetAsync(dev->stat_stripes, 0, MLV_STAT_STRIPES * 128, dev->stream));
-	dev->scan_blocks = (dev->num_bins + MLV_SCAN_THREADS * MLV_SCAN_ITEMS - 1) / (MLV_SCAN_THREADS * MLV_SCAN_ITEMS);
+	dev->scan_blocks = (dev->bin_end - dev->bin_begin + MLV_SCAN_THREADS * MLV_SCAN_ITEMS - 1) / (MLV_SCAN_THREADS * MLV_SCAN_ITEMS);
+	if(dev->scan_blocks == 0) dev->scan_blocks = 1;
 	CREATE_TRY(cudaMalloc(&dev->scan_state, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long)));
 	CREATE_TRY(cudaMemsetAsync(dev->scan_state, 0, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long), dev->stream));
 	CREATE_TRY(cudaMalloc(&dev->rsqrt_lut, sizeof(k_rsqrt_lut_host)));
@@ -239,7 +259,7 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(!dev) return;
 	cudaSetDevice(dev->cuda_dev);
 	if(dev->stream) cudaStreamSynchronize(dev->stream);
-	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue, dev->vcache,
+	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue, dev->vcache, dev->chunk_live,
 		             dev->scan_state, dev->ctr, dev->stat_stripes, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
@@ -267,6 +287,7 @@ int mlv_create_buffer(mlv_device *dev, const void *data, size_t bytes, int kind,
 	if(!out || bytes == 0 || (kind != MLV_BUFFER_VERTEX && kind != MLV_BUFFER_INDEX)) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer arguments");
 	mlv_buffer *b = new(std::nothrow) mlv_buffer();
 	if(!b) return fail(MLV_ERR_OUT_OF_MEMORY, "host allocation failed");
+	memset(b, 0, sizeof(*b));
 	b->bytes = bytes;
 	b->kind = kind;
 	cudaError_t e = cudaMalloc(&b->d, (bytes + 15) & ~(size_t)15);
@@ -283,6 +304,7 @@ int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t
 	if(int rc = use_device(dev)) return rc;
 	if(!buf || !data || bytes > buf->bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer update");
 	CUDA_TRY(cudaMemcpyAsync(buf->d, data, bytes, cudaMemcpyHostToDevice, dev->stream));
+	buf->version++;
 	return MLV_OK;
 }
 
@@ -292,6 +314,7 @@ void mlv_release_buffer(mlv_device *dev, mlv_buffer *buf) {
 	cudaStreamSynchronize(dev->stream);
 	if(dev->vb == buf) dev->vb = nullptr;
 	if(dev->ib == buf) dev->ib = nullptr;
+	if(buf->chunk_bounds) cudaFree(buf->chunk_bounds);
 	cudaFree(buf->d);
 	delete buf;
 }
@@ -398,9 +421,13 @@ int mlv_ps_set_shader_resource(mlv_device *dev, uint32_t slot, mlv_texture *tex)
 static int flush_clears(mlv_device *dev) {
 	if(!dev->pend_color && !dev->pend_depth) return MLV_OK;
 	const int mode = (dev->pend_color ? 1 : 0) | (dev->pend_depth ? 2 : 0);
-	const uint32_t n = dev->num_bins * 32u;
+	const uint32_t n = (dev->bin_end - dev->bin_begin) * 32u; // this rank's band only (nobody reads the tiles of other ranks)
+	if(n == 0) { // a rank without tile rows (more ranks than stripes)
+		dev->pend_color = dev->pend_depth = false;
+		return MLV_OK;
+	}
 	prof_pre(dev, MLV_STAGE_CLEAR);
-	k_clear<<<(n + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->tile_min, dev->num_bins, dev->clear_color, dev->clear_depth, mode);
+	k_clear<<<(n + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->tile_min, dev->bin_begin, dev->bin_end, dev->clear_color, dev->clear_depth, mode);
 	dev->pend_color = dev->pend_depth = false;
 	return check_launch(dev, "k_clear");
 }
@@ -565,10 +592,39 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	gp.stat_stripes = dev->stat_stripes;
 	gp.index_count = count;
 
+	// Sort-first chunk culling (multi-GPU): object-space chunk bounds cached with the buffer that defines the triangle list.
+	if(dev->part.num_ranks > 1 && !debug && (dev->vs_id == MLV_VS_BASIC || dev->vs_id == MLV_VS_VERTEX_LIGHTING)) {
+		mlv_buffer *owner = indexed ? dev->ib : dev->vb;
+		const bool valid = owner->chunk_bounds && owner->chunk_count == nblocks && owner->chunk_indexed == (indexed ? 1 : 0) && owner->chunk_self_version == owner->version &&
+		                   owner->chunk_vb == dev->vb && owner->chunk_vb_version == dev->vb->version;
+		if(!valid) {
+			if(nblocks > owner->chunk_capacity) {
+				CUDA_TRY(cudaStreamSynchronize(dev->stream));
+				CUDA_TRY(regrow(&owner->chunk_bounds, (size_t)nblocks * 2));
+				owner->chunk_capacity = nblocks;
+			}
+			prof_pre(dev, MLV_STAGE_GEOMETRY);
+			if(indexed) k_chunk_bounds<true><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp.ib, gp.vb, T, owner->chunk_bounds);
+			else k_chunk_bounds<false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp.ib, gp.vb, T, owner->chunk_bounds);
+			if(int rc = check_launch(dev, "k_chunk_bounds")) return rc;
+			owner->chunk_count = nblocks;
+			owner->chunk_indexed = indexed ? 1 : 0;
+			owner->chunk_self_version = owner->version;
+			owner->chunk_vb = dev->vb;
+			owner->chunk_vb_version = dev->vb->version;
+		}
+		if(nblocks > dev->chunk_live_capacity) {
+			CUDA_TRY(cudaStreamSynchronize(dev->stream));
+			CUDA_TRY(regrow(&dev->chunk_live, (size_t)nblocks));
+			dev->chunk_live_capacity = nblocks;
+		}
+		gp.chunk_bounds = owner->chunk_bounds;
+		gp.chunk_live = dev->chunk_live;
+	}
 	// Post-transform vertex cache: worth it when the index buffer references each vertex of the buffer about twice or
 	// more (the bound vertex buffer's size is the only vertex count a D3D11-style draw call has).
 	uint32_t vcache_vertices = 0;
-	if(indexed && !debug) {
+	if(indexed && !debug && !gp.chunk_bounds) { // (with chunk culling a rank touches ~1/N of the vertices; transforming all of them would cost more)
 		const uint64_t vb_vertices = dev->vb->bytes / 32;
 		if(vb_vertices > 0 && vb_vertices <= 0x7fffffffull && (uint64_t)count >= 2 * vb_vertices) {
 			vcache_vertices = (uint32_t)vb_vertices;
@@ -606,6 +662,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	bp.tri_bounds = dev->tri_bounds;
 	bp.big_queue = dev->big_queue;
 	bp.huge_queue = dev->huge_queue;
+	bp.chunk_live = gp.chunk_live;
 	bp.tile_min = dev->tile_min;
 	bp.bin_count = dev->bin_count;
 	bp.bin_offset = dev->bin_offset;
@@ -633,7 +690,8 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	sp.state_sum = dev->scan_state;
 	sp.state_nz = dev->scan_state + dev->scan_blocks;
 	sp.tile_min = dev->tile_min;
-	sp.num_bins = dev->num_bins;
+	sp.bin_begin = dev->bin_begin;
+	sp.bin_end = dev->bin_end;
 	sp.pair_capacity = (uint32_t)dev->pair_capacity;
 	sp.ticket_base = dev->ticket_base;
 	sp.epoch = dev->epoch;

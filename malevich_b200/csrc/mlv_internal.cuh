@@ -85,6 +85,8 @@ struct GeomParams {
 	uint4 *tri_cov;
 	uint4 *tri_shade;
 	uint4 *tri_bounds;
+	const float4 *chunk_bounds; // sort-first chunk culling: 2 x float4 per k_geom CTA, or null
+	uint8_t *chunk_live;        // written by k_geom: 1 = this rank processed the chunk
 	float4 *vcache; // 2 x float4 per unique vertex: clip-space position, {snapped x, snapped y, screen z, 1/w}
 	uint32_t *clip_queue;
 	uint32_t *big_queue;
@@ -102,6 +104,7 @@ struct BinParams {
 	const uint4 *tri_bounds;
 	const uint32_t *big_queue;
 	const uint32_t *huge_queue;
+	const uint8_t *chunk_live;
 	const float *tile_min;
 	uint32_t *bin_count;
 	uint32_t *bin_offset;
@@ -122,7 +125,7 @@ struct ScanParams {
 	Counters *ctr;
 	unsigned long long *state_sum, *state_nz;
 	const float *tile_min;
-	uint32_t num_bins;
+	uint32_t bin_begin, bin_end; // this rank's bins (the whole render target unless it owns one contiguous band)
 	uint32_t pair_capacity;
 	uint32_t ticket_base, epoch, num_blocks;
 };

@@ -191,24 +191,30 @@ def test_clipping_heavy_camera_against_live_reference():
 def test_sort_first_partition_composes_to_single_gpu_image():
     """SURVEY.md 8e on ONE GPU: render each rank's stripes with its own device object, exchange the packed chunks by
     hand (what ncclAllGather does), unpack -- the composed image must be bit-identical to the single-device image and
-    the per-rank bin/pair counters must sum to the single-device Stats."""
+    the per-rank counters (assembled triangles, bins, pairs) must sum to the single-device Stats. Covers interleaved
+    stripes and contiguous bands (where chunk culling and the band-restricted scan/clear are active)."""
+    for case, combos in (("ftm_320x200", ((2, 1), (4, 2), (3, 1), (8, 1), (2, 13), (4, 7), (5, 5))), ("synth_320x200", ((2, 13), (8, 4), (3, 2))),
+                         ("emily_320x200", ((2, 13), (4, 7))), ("loco_320x200", ((2, 13), (3, 9)))):
+        _check_partition(cases.SMALL[case](), combos)
+
+
+def _check_partition(sc, combos):
     import torch
     from malevich_b200 import scenes
-    sc = cases.SMALL["ftm_320x200"]()
     with _device(sc.width, sc.height) as dev:
         scenes.render(dev, sc)
         ref_col, ref_dep = dev.present()
         ref_stats = dev.stats()
-    for world, stripe in ((2, 1), (4, 2), (3, 1), (8, 1)):
+    for world, stripe in combos:
         devs = [_device(sc.width, sc.height, num_ranks=world, rank=r, stripe_height_tiles=stripe) for r in range(world)]
         try:
-            chunks, sums = [], {"active_bin_count": 0, "total_triangle_count_in_bins": 0}
+            chunks, sums = [], {"assembled_triangle_count": 0, "active_bin_count": 0, "total_triangle_count_in_bins": 0}
             for d in devs:
                 scenes.render(d, sc)
                 d.composite_pack()
                 d.finish()
                 st = d.stats()
-                assert st["assembled_triangle_count"] == ref_stats["assembled_triangle_count"]
+                assert st["vertex_count"] == ref_stats["vertex_count"] and st["input_triangle_count"] == ref_stats["input_triangle_count"]
                 for k in sums:
                     sums[k] += st[k]
             assert sums == {k: ref_stats[k] for k in sums}
