@@ -307,13 +307,18 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         peak, peak_src = load_peaks()
         b_alg, b_stage = algorithmic_bytes(scene, stats, len(scene.objects))
         fps = 1e3 / ms
-        # dominant kernel = the stage with the largest summed kernel time
-        kernel_stages = {"geometry": stage_ms["geometry"], "tile": stage_ms["tile"], "bin": stage_ms["bin_count"] + stage_ms["bin_scan"] + stage_ms["bin_fill"]}
-        dom = max(kernel_stages, key=kernel_stages.get)
-        dom_launches = {"geometry": stage_launches["geometry"], "tile": stage_launches["tile"], "bin": stage_launches["bin_count"]}[dom]
-        dom_ms_per_launch = kernel_stages[dom] / max(dom_launches, 1)
-        # with N ranks the tile stage of one rank touches 1/N of the tiles; bytes per launch per rank scale accordingly
-        dom_bytes_per_launch = b_stage[dom] / max(dom_launches, 1) / (world if dom != "geometry" else 1)
+        # dominant kernel = the kernel with the largest summed time over the step; its algorithmic bytes (SURVEY.md 8d per-unit
+        # figures x the units it processed) over its own CUDA-event time
+        kernel_ms = {"k_geom": stage_ms["geometry"], "k_tile": stage_ms["tile"], "k_geom_clip": stage_ms["clip"], "k_vertex": stage_ms["vertex_cache"],
+                     "k_bin_scan": stage_ms["bin_scan"], "k_bin_fill": stage_ms["bin_fill"]}
+        kernel_launches = {"k_geom": stage_launches["geometry"], "k_tile": stage_launches["tile"], "k_geom_clip": stage_launches["clip"], "k_vertex": stage_launches["vertex_cache"],
+                           "k_bin_scan": stage_launches["bin_scan"], "k_bin_fill": stage_launches["bin_fill"]}
+        kernel_bytes = {"k_geom": b_stage["geometry"], "k_tile": b_stage["tile"] / world, "k_geom_clip": 0, "k_vertex": 0, "k_bin_scan": 16 * (scene.width // 8) * (scene.height // 8) * len(scene.objects) / world,
+                        "k_bin_fill": 8 * stats["total_triangle_count_in_bins"] / world}
+        dom = max(("k_geom", "k_tile"), key=kernel_ms.get)  # the two kernels that carry the record stream; the others move < 5 % of the bytes
+        dom_launches = kernel_launches[dom]
+        dom_ms_per_launch = kernel_ms[dom] / max(dom_launches, 1)
+        dom_bytes_per_launch = kernel_bytes[dom] / max(dom_launches, 1)
         achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9 if dom_ms_per_launch > 0 else 0.0
         out = {
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
@@ -323,7 +328,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                        "assembled_triangles": stats["assembled_triangle_count"], "tri_tile_pairs": stats["total_triangle_count_in_bins"],
                        "tile_draws": stats["active_bin_count"], "parallelism": f"sort-first x{world}, stripe {stripe} tile rows" if multi else "single GPU",
                        "l2": "no flush: per-frame working set (inputs + per-draw setup records) >> 126 MB L2" if args.config == 5 else "no flush"},
-            "roofline": {"bound": "hbm", "kernel": {"geometry": "k_geom", "tile": "k_tile", "bin": "k_bin+k_bin_scan"}[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes_per_launch,
                          "ms_per_launch": dom_ms_per_launch, "launches_per_step": dom_launches},
             "roofline_frame": {"algorithmic_bytes_per_frame": b_alg, "achieved": b_alg / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",

@@ -174,8 +174,17 @@ MLV_API int mlv_debug_read_tile_min_depths(mlv_device *dev, float *out_bins);   
  * 984,1047,1192,1205): between mlv_profile_begin and mlv_profile_end every kernel launch is bracketed by CUDA events
  * on the device's stream. mlv_profile_end synchronises and returns, per stage, the summed kernel time in
  * milliseconds and the number of launches. Arrays have MLV_STAGE_COUNT entries. */
-enum { MLV_STAGE_CLEAR = 0, MLV_STAGE_GEOMETRY = 1, MLV_STAGE_BIN_COUNT = 2, MLV_STAGE_BIN_SCAN = 3, MLV_STAGE_BIN_FILL = 4,
-       MLV_STAGE_TILE = 5, MLV_STAGE_RESOLVE = 6, MLV_STAGE_COMPOSITE = 7, MLV_STAGE_COUNT = 8 };
+enum { MLV_STAGE_CLEAR = 0,      /* k_clear */
+       MLV_STAGE_GEOMETRY = 1,   /* k_geom (+ k_chunk_bounds when the sort-first chunk bounds are (re)built) */
+       MLV_STAGE_BIN_COUNT = 2,  /* k_bin_big */
+       MLV_STAGE_BIN_SCAN = 3,   /* k_bin_scan */
+       MLV_STAGE_BIN_FILL = 4,   /* k_bin_fill */
+       MLV_STAGE_TILE = 5,       /* k_tile */
+       MLV_STAGE_RESOLVE = 6,    /* k_resolve */
+       MLV_STAGE_COMPOSITE = 7,  /* k_composite_pack / k_composite_unpack */
+       MLV_STAGE_VERTEX = 8,     /* k_vertex (post-transform vertex cache) */
+       MLV_STAGE_CLIP = 9,       /* k_geom_clip */
+       MLV_STAGE_COUNT = 10 };
 MLV_API int mlv_profile_begin(mlv_device *dev);
 MLV_API int mlv_profile_end(mlv_device *dev, double *out_ms, uint32_t *out_launches);
 

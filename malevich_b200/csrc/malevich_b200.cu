@@ -3,7 +3,7 @@
 // Mirrors the reference's L4 boundary: a bound-state object that the host mutates
 // (graphics_pipeline main.c:71-115,222) and three entry points (clear_render_target_view :1191,
 // clear_depth_stencil_view :1204, draw_indexed :1219). Everything a draw needs stays on the device:
-// one draw = five stream-ordered kernel launches, no host synchronisation, no per-draw allocation
+// one draw = six or seven stream-ordered kernel launches, no host synchronisation, no per-draw allocation
 // (the reference mallocs/frees seven intermediates per draw, main.c:1222-1259).
 #include <cstdarg>
 #include <cstdio>
@@ -471,10 +471,15 @@ template <int VS>
 static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed, uint32_t vcache_vertices) {
 	const bool debug = gp.keep_all;
 	if(vcache_vertices) {
+		prof_pre(dev, MLV_STAGE_VERTEX);
 		k_vertex<VS><<<(vcache_vertices + 255u) / 256u, 256, 0, dev->stream>>>(gp, vcache_vertices);
-		dev->launches++;
+		check_launch(dev, "k_vertex");
+		prof_pre(dev, MLV_STAGE_GEOMETRY);
 		k_geom<VS, true, false, true><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
-	} else if(indexed && debug) k_geom<VS, true, true, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+		return;
+	}
+	prof_pre(dev, MLV_STAGE_GEOMETRY);
+	if(indexed && debug) k_geom<VS, true, true, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
 	else if(indexed) k_geom<VS, true, false, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
 	else if(debug) k_geom<VS, false, true, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
 	else k_geom<VS, false, false, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
@@ -636,7 +641,6 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 			gp.vcache = dev->vcache;
 		}
 	}
-	prof_pre(dev, MLV_STAGE_GEOMETRY);
 	switch(dev->vs_id) {
 		case MLV_VS_PASSTHROUGH: launch_geom<0>(dev, gp, nblocks, indexed, vcache_vertices); break;
 		case MLV_VS_BASIC: launch_geom<1>(dev, gp, nblocks, indexed, vcache_vertices); break;
@@ -645,9 +649,11 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	}
 	if(int rc = check_launch(dev, "k_geom")) return rc;
 	{ // clipping pass over the (device-side) queue; a modest persistent grid, most draws queue few or no triangles
+		// one thread per queued triangle: the clipper is a long dependent chain per triangle, so the queue is spread over
+		// as many warps as it has entries (concentrating it on fewer CTAs was measured slower: 28 vs 20 us)
 		uint32_t cb = (T + 127u) / 128u;
 		if(cb > 148u * 4u) cb = 148u * 4u;
-		prof_pre(dev, MLV_STAGE_GEOMETRY);
+		prof_pre(dev, MLV_STAGE_CLIP);
 		switch(dev->vs_id) {
 			case MLV_VS_PASSTHROUGH: launch_geom_clip<0>(dev, gp, cb, indexed); break;
 			case MLV_VS_BASIC: launch_geom_clip<1>(dev, gp, cb, indexed); break;
