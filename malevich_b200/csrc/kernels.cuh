@@ -19,11 +19,21 @@ namespace mlv {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// Programmatic dependent launch (sm_90+): every kernel is launched with programmaticStreamSerialization, lets the
+// NEXT kernel of the stream start launching at once (its CTAs become resident as SM resources free up) and then waits
+// here until the PREVIOUS kernel has completed and its writes are visible. Semantics are those of plain stream order;
+// what is saved is the launch latency between the ~7 dependent kernels of every draw.
+__device__ __forceinline__ void pdl_prologue() {
+	asm volatile("griddepcontrol.launch_dependents;");
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // =================================================================================================
 // clear
 // =================================================================================================
 // mode bit 0: colour, bit 1: depth (+ tile minima := 0, main.c:1212-1214)
 __global__ void __launch_bounds__(256) k_clear(uint4 *__restrict__ fb, float *__restrict__ tile_min, uint32_t bin_begin, uint32_t bin_end, uint32_t color, float depth, int mode) {
+	pdl_prologue();
 	const uint32_t i = bin_begin * 32u + blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= bin_end * 32u) return;
 	const uint32_t d = __float_as_uint(depth);
@@ -424,6 +434,7 @@ __device__ __forceinline__ void tally_stats(unsigned long long *stripes, uint32_
 // Only for the vertex shaders whose SV_POSITION is clip_from_world * POSITION.xyz (basic_vs, vertex_lighting_vs).
 template <bool INDEXED>
 __global__ void __launch_bounds__(MLV_GEOM_THREADS) k_chunk_bounds(const uint32_t *__restrict__ ib, const float4 *__restrict__ vb, uint32_t tri_count, float4 *__restrict__ chunk_bounds) {
+	pdl_prologue();
 	__shared__ float s_min[3][MLV_GEOM_THREADS / 32], s_max[3][MLV_GEOM_THREADS / 32];
 	__shared__ int s_bad[MLV_GEOM_THREADS / 32];
 	const uint32_t t = blockIdx.x * MLV_GEOM_THREADS + threadIdx.x;
@@ -506,6 +517,7 @@ __device__ __forceinline__ bool chunk_is_foreign(const GeomParams &P, uint32_t c
 // pure functions of the vertex, so the values are the ones the reference computes per corner.
 template <int VS>
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ GeomParams P, uint32_t vertex_count) {
+	pdl_prologue();
 	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
 	if(v >= vertex_count) return;
 	const float4 pos = vs_position<VS>(__ldg(P.vb + 2 * (size_t)v), P.cb);
@@ -516,6 +528,7 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ GeomPara
 
 template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
 __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_constant__ GeomParams P) {
+	pdl_prologue();
 	// Records are staged per warp in shared memory and written out as contiguous 512-byte rows: the 32 direct
 	// slots of a warp are adjacent in HBM, so the warp stores 1536 B of TriCov and 3072 B of TriShade with fully
 	// coalesced 128-bit stores instead of 32 scattered 16-byte pieces per instruction.
@@ -681,6 +694,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 // Re-runs input assembly + vertex shader for the triangle, clips, and emits the fan into overflow slots.
 template <int VS, bool INDEXED>
 __global__ void __launch_bounds__(128) k_geom_clip(const __grid_constant__ GeomParams P) {
+	pdl_prologue();
 	const uint32_t n = P.ctr->clip_count;
 	const uint32_t lane = lane_id();
 	uint32_t emitted = 0, pairs = 0;
@@ -751,6 +765,7 @@ __device__ __forceinline__ SlotBounds load_bounds(const uint4 *__restrict__ tri_
 // the geometry kernels). Rectangles of up to MLV_HUGE_TILES tiles: one warp per triangle, lanes stride over the
 // rectangle. Larger ones (sky domes, full-screen quads): the whole grid strides over the rectangle.
 __global__ void __launch_bounds__(256) k_bin_big(const __grid_constant__ BinParams P) {
+	pdl_prologue();
 	const uint32_t n = P.ctr->big_count;
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -796,6 +811,7 @@ __device__ __forceinline__ void fill_one(const BinParams &P, int k, int cnt, int
 }
 
 __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinParams P, uint32_t pair_capacity) {
+	pdl_prologue();
 	if(P.ctr->pair_total > pair_capacity || P.ctr->pair_total == 0u) return; // draw skipped (MLV_FLAG_PAIR_OVERFLOW is set) / nothing survived Hi-Z
 	const uint32_t n = P.direct_slots + P.ctr->ovf_count;
 	const uint32_t lane = lane_id();
@@ -902,6 +918,7 @@ __device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long lo
 #define MLV_SCAN_THREADS 1024
 #define MLV_SCAN_ITEMS 4
 __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_constant__ ScanParams P) {
+	pdl_prologue();
 	__shared__ uint32_t s_tile;
 	__shared__ uint32_t s_sum[32], s_nz[32];
 	__shared__ uint32_t s_excl[2];
@@ -1155,6 +1172,7 @@ __device__ __forceinline__ uint32_t shade_pixel(const TileParams &P, uint32_t ke
 
 template <int PS>
 __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant__ TileParams P, uint32_t pair_capacity) {
+	pdl_prologue();
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	if(blockIdx.x == 0 && threadIdx.x < 32) { // every earlier kernel of this draw is done with these: fold them into Stats, re-arm for the next draw
@@ -1324,6 +1342,7 @@ __device__ __forceinline__ Quad8 load_quad8(const uint4 *__restrict__ fb, uint32
 
 // work item w -> (bin, row 0..3, half 0..1); 8 items per tile
 __global__ void __launch_bounds__(256) k_resolve(const uint4 *__restrict__ fb, uint4 *__restrict__ colors, float4 *__restrict__ depths, int width, int height) {
+	pdl_prologue();
 	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t wt = (uint32_t)width >> 3, ht = (uint32_t)height >> 3;
 	// order work so that consecutive threads write consecutive 16-byte quads of one image row
@@ -1352,6 +1371,7 @@ __device__ __forceinline__ uint32_t chunk_row(uint32_t ty, uint32_t y_in_tile, i
 }
 
 __global__ void __launch_bounds__(256) k_composite_pack(const uint4 *__restrict__ fb, uint4 *__restrict__ chunk, int width, int height, Partition part) {
+	pdl_prologue();
 	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t wt = (uint32_t)width >> 3, ht = (uint32_t)height >> 3;
 	const uint32_t quads_per_row = wt * 2u;
@@ -1367,6 +1387,7 @@ __global__ void __launch_bounds__(256) k_composite_pack(const uint4 *__restrict_
 
 __global__ void __launch_bounds__(256) k_composite_unpack(const uint4 *__restrict__ gather, uint4 *__restrict__ colors, int width, int height, int num_ranks, int stripe_h,
                                                           size_t chunk_u4) {
+	pdl_prologue();
 	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t qw = (uint32_t)width >> 2;
 	if(q >= qw * (uint32_t)height) return;

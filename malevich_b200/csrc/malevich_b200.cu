@@ -121,6 +121,22 @@ struct mlv_device {
 	size_t prof_used;
 };
 
+// Every kernel goes through here: launched with programmatic stream serialisation (see pdl_prologue in kernels.cuh).
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), uint32_t grid, uint32_t block, cudaStream_t stream, Args &&...args) {
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.gridDim = dim3(grid, 1, 1);
+	cfg.blockDim = dim3(block, 1, 1);
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 static int use_device(mlv_device *dev) {
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	CUDA_TRY(cudaSetDevice(dev->cuda_dev));
@@ -427,7 +443,7 @@ static int flush_clears(mlv_device *dev) {
 		return MLV_OK;
 	}
 	prof_pre(dev, MLV_STAGE_CLEAR);
-	k_clear<<<(n + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->tile_min, dev->bin_begin, dev->bin_end, dev->clear_color, dev->clear_depth, mode);
+	launch_pdl(k_clear, (n + 255) / 256, 256, dev->stream, dev->fb, dev->tile_min, dev->bin_begin, dev->bin_end, dev->clear_color, dev->clear_depth, mode);
 	dev->pend_color = dev->pend_depth = false;
 	return check_launch(dev, "k_clear");
 }
@@ -472,22 +488,22 @@ static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks,
 	const bool debug = gp.keep_all;
 	if(vcache_vertices) {
 		prof_pre(dev, MLV_STAGE_VERTEX);
-		k_vertex<VS><<<(vcache_vertices + 255u) / 256u, 256, 0, dev->stream>>>(gp, vcache_vertices);
+		launch_pdl(k_vertex<VS>, (vcache_vertices + 255u) / 256u, 256, dev->stream, gp, vcache_vertices);
 		check_launch(dev, "k_vertex");
 		prof_pre(dev, MLV_STAGE_GEOMETRY);
-		k_geom<VS, true, false, true><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+		launch_pdl(k_geom<VS, true, false, true>, nblocks, MLV_GEOM_THREADS, dev->stream, gp);
 		return;
 	}
 	prof_pre(dev, MLV_STAGE_GEOMETRY);
-	if(indexed && debug) k_geom<VS, true, true, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
-	else if(indexed) k_geom<VS, true, false, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
-	else if(debug) k_geom<VS, false, true, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
-	else k_geom<VS, false, false, false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp);
+	if(indexed && debug) launch_pdl(k_geom<VS, true, true, false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp);
+	else if(indexed) launch_pdl(k_geom<VS, true, false, false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp);
+	else if(debug) launch_pdl(k_geom<VS, false, true, false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp);
+	else launch_pdl(k_geom<VS, false, false, false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp);
 }
 template <int VS>
 static void launch_geom_clip(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed) {
-	if(indexed) k_geom_clip<VS, true><<<nblocks, 128, 0, dev->stream>>>(gp);
-	else k_geom_clip<VS, false><<<nblocks, 128, 0, dev->stream>>>(gp);
+	if(indexed) launch_pdl(k_geom_clip<VS, true>, nblocks, 128, dev->stream, gp);
+	else launch_pdl(k_geom_clip<VS, false>, nblocks, 128, dev->stream, gp);
 }
 
 static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
@@ -609,8 +625,8 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 				owner->chunk_capacity = nblocks;
 			}
 			prof_pre(dev, MLV_STAGE_GEOMETRY);
-			if(indexed) k_chunk_bounds<true><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp.ib, gp.vb, T, owner->chunk_bounds);
-			else k_chunk_bounds<false><<<nblocks, MLV_GEOM_THREADS, 0, dev->stream>>>(gp.ib, gp.vb, T, owner->chunk_bounds);
+			if(indexed) launch_pdl(k_chunk_bounds<true>, nblocks, MLV_GEOM_THREADS, dev->stream, gp.ib, gp.vb, T, owner->chunk_bounds);
+			else launch_pdl(k_chunk_bounds<false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp.ib, gp.vb, T, owner->chunk_bounds);
 			if(int rc = check_launch(dev, "k_chunk_bounds")) return rc;
 			owner->chunk_count = nblocks;
 			owner->chunk_indexed = indexed ? 1 : 0;
@@ -684,7 +700,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	uint32_t big_blocks = (T + 7u) / 8u; // one warp per queued triangle, grid-stride
 	if(big_blocks > 148u * 4u) big_blocks = 148u * 4u;
 	prof_pre(dev, MLV_STAGE_BIN_COUNT);
-	k_bin_big<<<big_blocks, 256, 0, dev->stream>>>(bp);
+	launch_pdl(k_bin_big, big_blocks, 256, dev->stream, bp);
 	if(int rc = check_launch(dev, "k_bin_big")) return rc;
 
 	ScanParams sp;
@@ -704,13 +720,13 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	sp.num_blocks = dev->scan_blocks;
 	dev->ticket_base += dev->scan_blocks;
 	prof_pre(dev, MLV_STAGE_BIN_SCAN);
-	k_bin_scan<<<dev->scan_blocks, MLV_SCAN_THREADS, 0, dev->stream>>>(sp);
+	launch_pdl(k_bin_scan, dev->scan_blocks, MLV_SCAN_THREADS, dev->stream, sp);
 	if(int rc = check_launch(dev, "k_bin_scan")) return rc;
 
 	uint32_t bin_blocks = (need_slots + 255u) / 256u;
 	if(bin_blocks > 148u * 16u) bin_blocks = 148u * 16u;
 	prof_pre(dev, MLV_STAGE_BIN_FILL);
-	k_bin_fill<<<bin_blocks, 256, 0, dev->stream>>>(bp, (uint32_t)dev->pair_capacity);
+	launch_pdl(k_bin_fill, bin_blocks, 256, dev->stream, bp, (uint32_t)dev->pair_capacity);
 	if(int rc = check_launch(dev, "k_bin_fill")) return rc;
 
 	TileParams tp;
@@ -737,9 +753,9 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	const uint32_t pcap = (uint32_t)dev->pair_capacity;
 	prof_pre(dev, MLV_STAGE_TILE);
 	switch(dev->ps_id) {
-		case MLV_PS_PASSTHROUGH: k_tile<0><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp, pcap); break;
-		case MLV_PS_BASIC: k_tile<1><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp, pcap); break;
-		default: k_tile<2><<<tile_blocks, MLV_TILE_THREADS, 0, dev->stream>>>(tp, pcap); break;
+		case MLV_PS_PASSTHROUGH: launch_pdl(k_tile<0>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
+		case MLV_PS_BASIC: launch_pdl(k_tile<1>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
+		default: launch_pdl(k_tile<2>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
 	}
 	return check_launch(dev, "k_tile");
 }
@@ -763,7 +779,7 @@ int mlv_resolve(mlv_device *dev) {
 	if(int rc = flush_clears(dev)) return rc;
 	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H; // 8 pixels (4 wide, rows y and y+4) per thread
 	prof_pre(dev, MLV_STAGE_RESOLVE);
-	k_resolve<<<(items + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->resolved_color, dev->resolved_depth, dev->W, dev->H);
+	launch_pdl(k_resolve, (items + 255) / 256, 256, dev->stream, dev->fb, dev->resolved_color, dev->resolved_depth, dev->W, dev->H);
 	return check_launch(dev, "k_resolve");
 }
 
@@ -775,7 +791,7 @@ int mlv_present_readback(mlv_device *dev, uint32_t *colors, float *depths) {
 	if(int rc = flush_clears(dev)) return rc;
 	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
 	prof_pre(dev, MLV_STAGE_RESOLVE);
-	k_resolve<<<(items + 255) / 256, 256, 0, dev->stream>>>(dev->fb, dev->resolved_color, depths ? dev->resolved_depth : nullptr, dev->W, dev->H);
+	launch_pdl(k_resolve, (items + 255) / 256, 256, dev->stream, dev->fb, dev->resolved_color, depths ? dev->resolved_depth : nullptr, dev->W, dev->H);
 	if(int rc = check_launch(dev, "k_resolve")) return rc;
 	const size_t bytes = (size_t)dev->W * dev->H * 4;
 	if(colors) CUDA_TRY(cudaMemcpyAsync(colors, dev->resolved_color, bytes, cudaMemcpyDeviceToHost, dev->stream));
@@ -818,7 +834,7 @@ int mlv_composite_pack(mlv_device *dev) {
 	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
 	uint4 *chunk = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(dev->gather) + dev->chunk_bytes * (size_t)dev->part.rank);
 	prof_pre(dev, MLV_STAGE_COMPOSITE);
-	k_composite_pack<<<(items + 255) / 256, 256, 0, dev->stream>>>(dev->fb, chunk, dev->W, dev->H, dev->part);
+	launch_pdl(k_composite_pack, (items + 255) / 256, 256, dev->stream, dev->fb, chunk, dev->W, dev->H, dev->part);
 	return check_launch(dev, "k_composite_pack");
 }
 
@@ -827,7 +843,7 @@ int mlv_composite_unpack(mlv_device *dev) {
 	if(dev->part.num_ranks <= 1) return fail(MLV_ERR_STATE, "device was created with a single rank");
 	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
 	prof_pre(dev, MLV_STAGE_COMPOSITE);
-	k_composite_unpack<<<(quads + 255) / 256, 256, 0, dev->stream>>>(dev->gather, dev->resolved_color, dev->W, dev->H, dev->part.num_ranks, dev->part.stripe_h, dev->chunk_bytes / 16);
+	launch_pdl(k_composite_unpack, (quads + 255) / 256, 256, dev->stream, dev->gather, dev->resolved_color, dev->W, dev->H, dev->part.num_ranks, dev->part.stripe_h, dev->chunk_bytes / 16);
 	return check_launch(dev, "k_composite_unpack");
 }
 
