@@ -174,30 +174,55 @@ __device__ __forceinline__ VsOut lerp_vertex(const VsOut &a, const VsOut &b, flo
 	return o;
 }
 
-// clip_by_plane (main.c:609-647), plane_d = 0
-__device__ __noinline__ int clip_by_plane(VsOut *v, int n, float4 pn) {
-	{ // a plane that has the whole polygon on its inside reproduces the polygon vertex for vertex: skip the copy
+// Polygons of the clipper live in SHARED memory, one column per thread: element (vertex v, component c) of thread `tid`
+// is at p[(v * 9 + c) * MLV_CLIP_THREADS], p already offset by tid -- conflict-free, and a fixed ~30-cycle access.
+// (As per-thread local arrays the two 16-vertex polygons of every thread overflowed L1 and each of the hundreds of
+// dependent accesses of the clipping loop became an L2 round trip: k_geom_clip was a 20 us latency chain.)
+#define MLV_CLIP_THREADS 64
+#define MLV_CLIP_MAXV 10 /* a triangle clipped by six planes has at most 9 vertices (MAX_NUM_CLIP_VERTICES is 16, main.c:38) */
+__device__ __forceinline__ VsOut poly_load(const float *p, int v) {
+	const float *q = p + v * 9 * MLV_CLIP_THREADS;
+	VsOut o;
+	o.r0 = make_float4(q[0], q[MLV_CLIP_THREADS], q[2 * MLV_CLIP_THREADS], q[3 * MLV_CLIP_THREADS]);
+	o.r1 = make_float4(q[4 * MLV_CLIP_THREADS], q[5 * MLV_CLIP_THREADS], q[6 * MLV_CLIP_THREADS], q[7 * MLV_CLIP_THREADS]);
+	o.r2x = q[8 * MLV_CLIP_THREADS];
+	return o;
+}
+__device__ __forceinline__ float4 poly_load_pos(const float *p, int v) {
+	const float *q = p + v * 9 * MLV_CLIP_THREADS;
+	return make_float4(q[0], q[MLV_CLIP_THREADS], q[2 * MLV_CLIP_THREADS], q[3 * MLV_CLIP_THREADS]);
+}
+__device__ __forceinline__ void poly_store(float *p, int v, const VsOut &o) {
+	float *q = p + v * 9 * MLV_CLIP_THREADS;
+	q[0] = o.r0.x, q[MLV_CLIP_THREADS] = o.r0.y, q[2 * MLV_CLIP_THREADS] = o.r0.z, q[3 * MLV_CLIP_THREADS] = o.r0.w;
+	q[4 * MLV_CLIP_THREADS] = o.r1.x, q[5 * MLV_CLIP_THREADS] = o.r1.y, q[6 * MLV_CLIP_THREADS] = o.r1.z, q[7 * MLV_CLIP_THREADS] = o.r1.w;
+	q[8 * MLV_CLIP_THREADS] = o.r2x;
+}
+
+// clip_by_plane (main.c:609-647), plane_d = 0: src -> dst. Returns the new vertex count, or -1 when the whole polygon
+// is inside (the pass would reproduce it vertex for vertex; the caller keeps src).
+__device__ __forceinline__ int clip_by_plane(const float *src, float *dst, int n, float4 pn) {
+	{
 		bool all_in = n > 0;
-		for(int i = 0; i < n; ++i) all_in = all_in && (dot4_serial(pn, v[i].r0) > -0.0f);
-		if(all_in) return n;
+		for(int i = 0; i < n; ++i) all_in = all_in && (dot4_serial(pn, poly_load_pos(src, i)) > -0.0f);
+		if(all_in) return -1;
 	}
-	VsOut res[16];
 	int nout = 0;
-	float cur = dot4_serial(pn, v[0].r0);
+	float cur = dot4_serial(pn, poly_load_pos(src, 0));
 	bool cur_in = cur > -0.0f;
 	for(int i = 0; i < n; ++i) {
-		const int next = (i + 1) % n;
-		if(cur_in && nout < 16) res[nout++] = v[i];
-		const float nd = dot4_serial(pn, v[next].r0);
+		const int next = (i + 1 == n) ? 0 : i + 1;
+		const VsOut vi = poly_load(src, i);
+		if(cur_in && nout < MLV_CLIP_MAXV) poly_store(dst, nout++, vi);
+		const float nd = dot4_serial(pn, poly_load_pos(src, next));
 		const bool nin = nd > -0.0f;
-		if(cur_in != nin && nout < 16) {
+		if(cur_in != nin && nout < MLV_CLIP_MAXV) {
 			const float t = (0.0f + cur) / (cur - nd);
-			res[nout++] = lerp_vertex(v[i], v[next], t);
+			poly_store(dst, nout++, lerp_vertex(vi, poly_load(src, next), t));
 		}
 		cur = nd;
 		cur_in = nin;
 	}
-	for(int i = 0; i < nout; ++i) v[i] = res[i];
 	return nout;
 }
 
@@ -362,10 +387,10 @@ __device__ __forceinline__ uint32_t emit_triangle(const GeomParams &P, uint32_t 
 }
 
 // Clipper (main.c:649-660): returns the vertex count of the clipped polygon left in poly[].
-__device__ __noinline__ int clip_polygon(const GeomParams &P, const VsOut &v0, const VsOut &v1, const VsOut &v2, VsOut *poly) {
-	poly[0] = v0;
-	poly[1] = v1;
-	poly[2] = v2;
+__device__ __forceinline__ int clip_polygon(const GeomParams &P, const VsOut &v0, const VsOut &v1, const VsOut &v2, float *&cur, float *&other) {
+	poly_store(cur, 0, v0);
+	poly_store(cur, 1, v1);
+	poly_store(cur, 2, v2);
 	const float k = P.clip_k;
 	// A plane pass reproduces its input vertex for vertex when the whole polygon is strictly inside (see
 	// clip_by_plane), and every polygon vertex is a convex combination of v0,v1,v2. So a plane that has the three
@@ -382,22 +407,29 @@ __device__ __noinline__ int clip_polygon(const GeomParams &P, const VsOut &v0, c
 	for(int pl = 0; pl < 6; ++pl) {
 		const float d0 = dot4_serial(planes[pl], v0.r0), d1 = dot4_serial(planes[pl], v1.r0), d2 = dot4_serial(planes[pl], v2.r0);
 		if(fminf(fminf(d0, d1), d2) > margin) continue; // safely inside (false for NaN: literal pass)
-		n = clip_by_plane(poly, n, planes[pl]);
+		const int m = clip_by_plane(cur, other, n, planes[pl]);
+		if(m >= 0) { // ping-pong
+			n = m;
+			float *sw = cur;
+			cur = other;
+			other = sw;
+		}
 	}
 	return n;
 }
 
 // Fan triangulation (main.c:797) of a clipped polygon into the consecutive overflow slots T + base + j; slot t
 // becomes a redirect to them. Returns the number of assembled triangles, adds the pairs to `pairs`.
-__device__ __noinline__ uint32_t emit_fan(const GeomParams &P, uint32_t t, const VsOut *poly, int fan, uint32_t base, uint32_t &pairs) {
-	P.tri_cov[(size_t)t * MLV_TRI_COV_U4 + 2] = make_uint4(base, 0u, MLV_REDIRECT, 0u);
+__device__ __forceinline__ uint32_t emit_fan(const GeomParams &P, uint32_t t, const float *poly, int fan, uint32_t base, uint32_t &pairs, int j_first, int j_step) {
+	if(j_first == 0) P.tri_cov[(size_t)t * MLV_TRI_COV_U4 + 2] = make_uint4(base, 0u, MLV_REDIRECT, 0u);
 	uint32_t emitted = 0;
-	for(int j = 0; j < fan; ++j) {
+	for(int j = j_first; j < fan; j += j_step) {
 		const uint32_t slot = P.tri_count + base + (uint32_t)j;
 		const uint32_t key = (t << 3) | (uint32_t)j;
 		TriSetup S;
-		if(setup_triangle(poly[0].r0, poly[j + 1].r0, poly[j + 2].r0, P, S)) {
-			pairs += emit_triangle(P, slot, key, S, poly[0].r1, poly[j + 1].r1, poly[j + 2].r1, poly[0].r2x, poly[j + 1].r2x, poly[j + 2].r2x);
+		const VsOut p0 = poly_load(poly, 0), p1 = poly_load(poly, j + 1), p2 = poly_load(poly, j + 2);
+		if(setup_triangle(p0.r0, p1.r0, p2.r0, P, S)) {
+			pairs += emit_triangle(P, slot, key, S, p0.r1, p1.r1, p2.r1, p0.r2x, p1.r2x, p2.r2x);
 			if(P.part.owns_row(S.miny / 8)) ++emitted;
 		} else {
 			P.tri_bounds[slot] = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, key);
@@ -690,19 +722,24 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 	tally_stats(P.stat_stripes, emitted, pairs);
 }
 
-// Clipping pass: one thread per queued input triangle (dense, unlike the sparse occurrences inside k_geom's warps).
+#define MLV_CLIP_SPLIT 4u
+// Clipping pass over the queued input triangles (dense, unlike the sparse occurrences inside k_geom's warps).
 // Re-runs input assembly + vertex shader for the triangle, clips, and emits the fan into overflow slots.
 template <int VS, bool INDEXED>
-__global__ void __launch_bounds__(128) k_geom_clip(const __grid_constant__ GeomParams P) {
+__global__ void __launch_bounds__(MLV_CLIP_THREADS) k_geom_clip(const __grid_constant__ GeomParams P) {
+	__shared__ float s_poly[2][MLV_CLIP_MAXV * 9 * MLV_CLIP_THREADS];
 	pdl_prologue();
 	const uint32_t n = P.ctr->clip_count;
 	const uint32_t lane = lane_id();
 	uint32_t emitted = 0, pairs = 0;
-	// warp-uniform trip count: the overflow slots of a whole warp are taken with ONE atomic (7 000 same-address atomics
-	// with return value per draw were a serial chain of their own)
-	for(uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {
-		const uint32_t i = i0 + lane;
-		VsOut poly[16];
+	// MLV_CLIP_SPLIT consecutive lanes work on the same queued triangle: each repeats the (cheap, deterministic) vertex
+	// shading and clipping and then sets up and emits every MLV_CLIP_SPLIT-th fan triangle. The kernel is one long
+	// dependent chain per thread with far too few threads to hide it, so what counts is the length of that chain,
+	// not the redundant work. Warp-uniform trip count: the overflow slots of a whole warp are taken with ONE atomic.
+	const uint32_t sub = lane % MLV_CLIP_SPLIT;
+	for(uint32_t i0 = ((blockIdx.x * blockDim.x + threadIdx.x) & ~31u) / MLV_CLIP_SPLIT; i0 < n; i0 += (gridDim.x * blockDim.x) / MLV_CLIP_SPLIT) {
+		const uint32_t i = i0 + lane / MLV_CLIP_SPLIT;
+		float *poly = s_poly[0] + threadIdx.x, *scratch = s_poly[1] + threadIdx.x;
 		int fan = 0;
 		uint32_t t = 0;
 		if(i < n) {
@@ -716,14 +753,14 @@ __global__ void __launch_bounds__(128) k_geom_clip(const __grid_constant__ GeomP
 			const VsOut v0 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi0), __ldg(P.vb + 2 * (size_t)vi0 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
 			const VsOut v1 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi1), __ldg(P.vb + 2 * (size_t)vi1 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
 			const VsOut v2 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi2), __ldg(P.vb + 2 * (size_t)vi2 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
-			fan = clip_polygon(P, v0, v1, v2, poly) - 2;
+			fan = clip_polygon(P, v0, v1, v2, poly, scratch) - 2;
 			if(fan > 8) { // cannot happen for a convex clip of a triangle by six planes (<= 9 vertices)
 				atomicOr(&P.ctr->error_flags, MLV_FLAG_TRI_OVERFLOW);
 				fan = 0;
 			}
 			if(fan < 0) fan = 0;
 		}
-		uint32_t incl = (uint32_t)fan;
+		uint32_t incl = (sub == 0u) ? (uint32_t)fan : 0u; // one allocation per triangle
 #pragma unroll
 		for(int d = 1; d < 32; d <<= 1) {
 			const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
@@ -732,10 +769,11 @@ __global__ void __launch_bounds__(128) k_geom_clip(const __grid_constant__ GeomP
 		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
 		uint32_t base = 0;
 		if(lane == 0 && total) base = atomicAdd(&P.ctr->ovf_count, total);
-		base = __shfl_sync(0xffffffffu, base, 0) + incl - (uint32_t)fan;
+		base = __shfl_sync(0xffffffffu, base, 0) + incl - ((sub == 0u) ? (uint32_t)fan : 0u);
+		base = __shfl_sync(0xffffffffu, base, (int)(lane - sub)); // the group shares the base of its first lane
 		if(fan > 0) {
 			if(base + (uint32_t)fan > P.ovf_capacity) atomicOr(&P.ctr->error_flags, MLV_FLAG_TRI_OVERFLOW);
-			else emitted += emit_fan(P, t, poly, fan, base, pairs);
+			else emitted += emit_fan(P, t, poly, fan, base, pairs, (int)sub, MLV_CLIP_SPLIT);
 		}
 	}
 	tally_stats(P.stat_stripes, emitted, pairs);

@@ -502,8 +502,8 @@ static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks,
 }
 template <int VS>
 static void launch_geom_clip(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed) {
-	if(indexed) launch_pdl(k_geom_clip<VS, true>, nblocks, 128, dev->stream, gp);
-	else launch_pdl(k_geom_clip<VS, false>, nblocks, 128, dev->stream, gp);
+	if(indexed) launch_pdl(k_geom_clip<VS, true>, nblocks, MLV_CLIP_THREADS, dev->stream, gp);
+	else launch_pdl(k_geom_clip<VS, false>, nblocks, MLV_CLIP_THREADS, dev->stream, gp);
 }
 
 static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
@@ -667,7 +667,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	{ // clipping pass over the (device-side) queue; a modest persistent grid, most draws queue few or no triangles
 		// one thread per queued triangle: the clipper is a long dependent chain per triangle, so the queue is spread over
 		// as many warps as it has entries (concentrating it on fewer CTAs was measured slower: 28 vs 20 us)
-		uint32_t cb = (T + 127u) / 128u;
+		uint32_t cb = (T * MLV_CLIP_SPLIT + MLV_CLIP_THREADS - 1u) / MLV_CLIP_THREADS;
 		if(cb > 148u * 4u) cb = 148u * 4u;
 		prof_pre(dev, MLV_STAGE_CLIP);
 		switch(dev->vs_id) {
