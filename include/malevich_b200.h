@@ -54,6 +54,7 @@ enum { MLV_PS_PASSTHROUGH = 0,  /* passthrough_ps.c:13-20 */
  * (get_texel_u_x8 :30 vs get_texel_f_x8 :42); here it is explicit. */
 enum { MLV_FORMAT_R8G8B8A8_UNORM = 0, MLV_FORMAT_R32G32B32A32_FLOAT = 1 };
 enum { MLV_BUFFER_VERTEX = 0, MLV_BUFFER_INDEX = 1 };
+enum { MLV_INDEX_U32 = 0, MLV_INDEX_U16 = 1 }; /* the reference has u32 only ("TODO: 16-bit index buffers", main.c:72) */
 
 #define MLV_CONSTANT_BUFFER_SLOT_COUNT 16 /* COMMONSHADER_CONSTANT_BUFFER_HW_SLOT_COUNT main.c:41 */
 #define MLV_SHADER_RESOURCE_SLOT_COUNT 16 /* COMMONSHADER_INPUT_RESOURCE_REGISTER_COUNT main.c:42 */
@@ -124,6 +125,7 @@ MLV_API void mlv_release_texture(mlv_device *dev, mlv_texture *tex);
 /* ---- pipeline state: graphics_pipeline.{ia,vs,rs,ps} main.c:71-115, written by render() main.c:1276-1294 */
 MLV_API int mlv_ia_set_vertex_buffer(mlv_device *dev, mlv_buffer *vb);       /* ia.p_vertex_buffer main.c:1292 */
 MLV_API int mlv_ia_set_index_buffer(mlv_device *dev, mlv_buffer *ib);        /* ia.p_index_buffer main.c:1291 (u32 indices) */
+MLV_API int mlv_ia_set_index_format(mlv_device *dev, int format);            /* MLV_INDEX_U32 (default, what the reference has) or MLV_INDEX_U16 (its TODO at main.c:72) */
 MLV_API int mlv_ia_set_input_layout(mlv_device *dev, uint32_t bytes_per_vertex); /* ia.input_layout main.c:1286 (must be 32) */
 MLV_API int mlv_ia_set_primitive_topology(mlv_device *dev, int topology);    /* ia.primitive_topology main.c:1276 */
 MLV_API int mlv_vs_set_shader(mlv_device *dev, int vs_id);                   /* vs.shader + vs.output_register_count main.c:1287-1288 */
@@ -137,6 +139,7 @@ MLV_API int mlv_ps_set_shader_resource(mlv_device *dev, uint32_t slot, mlv_textu
 MLV_API int mlv_clear_render_target_view(mlv_device *dev, const float rgba[4]); /* clear_render_target_view main.c:1191-1202 */
 MLV_API int mlv_clear_depth_stencil_view(mlv_device *dev, float depth);         /* clear_depth_stencil_view main.c:1204-1217 */
 MLV_API int mlv_draw_indexed(mlv_device *dev, uint32_t index_count);            /* draw_indexed main.c:1219-1261 */
+MLV_API int mlv_draw_indexed_ex(mlv_device *dev, uint32_t index_count, uint32_t start_index_location, int32_t base_vertex_location); /* ID3D11DeviceContext::DrawIndexed in full: the reference's TODO at main.c:1219 */
 MLV_API int mlv_draw(mlv_device *dev, uint32_t vertex_count);                   /* draw_indexed with identity indices (all shipped meshes) */
 
 /* ---- results ---------------------------------------------------------------------------------- */

@@ -11,10 +11,10 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmalevich_b200.so")
 EXPORTED_SYMBOLS = [
     "mlv_last_error_string", "mlv_create_device", "mlv_destroy_device", "mlv_finish", "mlv_get_stream",
     "mlv_create_buffer", "mlv_update_buffer", "mlv_release_buffer", "mlv_create_texture2d", "mlv_release_texture",
-    "mlv_ia_set_vertex_buffer", "mlv_ia_set_index_buffer", "mlv_ia_set_input_layout", "mlv_ia_set_primitive_topology",
+    "mlv_ia_set_vertex_buffer", "mlv_ia_set_index_buffer", "mlv_ia_set_index_format", "mlv_ia_set_input_layout", "mlv_ia_set_primitive_topology",
     "mlv_vs_set_shader", "mlv_vs_set_constant_buffer", "mlv_vs_set_shader_resource", "mlv_rs_set_viewport",
     "mlv_ps_set_shader", "mlv_ps_set_shader_resource",
-    "mlv_clear_render_target_view", "mlv_clear_depth_stencil_view", "mlv_draw_indexed", "mlv_draw",
+    "mlv_clear_render_target_view", "mlv_clear_depth_stencil_view", "mlv_draw_indexed", "mlv_draw_indexed_ex", "mlv_draw",
     "mlv_present_readback", "mlv_get_stats", "mlv_reset_stats",
     "mlv_resolve", "mlv_resolved_color_device_ptr", "mlv_resolved_depth_device_ptr",
     "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
@@ -30,6 +30,7 @@ VS_PASSTHROUGH, VS_BASIC, VS_VERTEX_LIGHTING, VS_FULLSCREEN = 0, 1, 2, 3
 PS_PASSTHROUGH, PS_BASIC, PS_ENV_LIGHTING = 0, 1, 2
 FORMAT_R8G8B8A8_UNORM, FORMAT_R32G32B32A32_FLOAT = 0, 1
 BUFFER_VERTEX, BUFFER_INDEX = 0, 1
+INDEX_U32, INDEX_U16 = 0, 1
 DEVICE_DEBUG_CAPTURE = 1
 
 
@@ -86,6 +87,7 @@ def load() -> C.CDLL:
         "mlv_release_texture": (None, [vp, vp]),
         "mlv_ia_set_vertex_buffer": (i32, [vp, vp]),
         "mlv_ia_set_index_buffer": (i32, [vp, vp]),
+        "mlv_ia_set_index_format": (i32, [vp, i32]),
         "mlv_ia_set_input_layout": (i32, [vp, u32]),
         "mlv_ia_set_primitive_topology": (i32, [vp, i32]),
         "mlv_vs_set_shader": (i32, [vp, i32]),
@@ -97,6 +99,7 @@ def load() -> C.CDLL:
         "mlv_clear_render_target_view": (i32, [vp, P(f32)]),
         "mlv_clear_depth_stencil_view": (i32, [vp, f32]),
         "mlv_draw_indexed": (i32, [vp, u32]),
+        "mlv_draw_indexed_ex": (i32, [vp, u32, u32, C.c_int32]),
         "mlv_draw": (i32, [vp, u32]),
         "mlv_present_readback": (i32, [vp, vp, vp]),
         "mlv_get_stats": (i32, [vp, P(Stats)]),

@@ -465,7 +465,7 @@ __device__ __forceinline__ void tally_stats(unsigned long long *stripes, uint32_
 // bands per rank a rank then fetches and shades ~1/N of the geometry instead of all of it.
 // Only for the vertex shaders whose SV_POSITION is clip_from_world * POSITION.xyz (basic_vs, vertex_lighting_vs).
 template <bool INDEXED>
-__global__ void __launch_bounds__(MLV_GEOM_THREADS) k_chunk_bounds(const uint32_t *__restrict__ ib, const float4 *__restrict__ vb, uint32_t tri_count, float4 *__restrict__ chunk_bounds) {
+__global__ void __launch_bounds__(MLV_GEOM_THREADS) k_chunk_bounds(const IndexStream ix, const float4 *__restrict__ vb, uint32_t tri_count, float4 *__restrict__ chunk_bounds) {
 	pdl_prologue();
 	__shared__ float s_min[3][MLV_GEOM_THREADS / 32], s_max[3][MLV_GEOM_THREADS / 32];
 	__shared__ int s_bad[MLV_GEOM_THREADS / 32];
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS) k_chunk_bounds(const uint32_
 	if(t < tri_count) {
 #pragma unroll
 		for(int c = 0; c < 3; ++c) {
-			const uint32_t vi = INDEXED ? __ldg(ib + 3u * t + c) : 3u * t + c;
+			const uint32_t vi = INDEXED ? ix.fetch(3u * t + c) : 3u * t + c;
 			const float4 p = __ldg(vb + 2 * (size_t)vi);
 			const float q[3] = { p.x, p.y, p.z };
 #pragma unroll
@@ -593,9 +593,9 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 		// that survive culling and Hi-Z (the reference shades all of them; the results are the same values).
 		uint32_t vi0, vi1, vi2;
 		if(INDEXED) {
-			vi0 = __ldg(P.ib + 3u * t);
-			vi1 = __ldg(P.ib + 3u * t + 1u);
-			vi2 = __ldg(P.ib + 3u * t + 2u);
+			vi0 = P.ix.fetch(3u * t);
+			vi1 = P.ix.fetch(3u * t + 1u);
+			vi2 = P.ix.fetch(3u * t + 2u);
 		} else {
 			vi0 = 3u * t;
 			vi1 = vi0 + 1u;
@@ -746,9 +746,9 @@ __global__ void __launch_bounds__(MLV_CLIP_THREADS) k_geom_clip(const __grid_con
 			t = P.clip_queue[i];
 			uint32_t vi0 = 3u * t, vi1 = 3u * t + 1u, vi2 = 3u * t + 2u;
 			if(INDEXED) {
-				vi0 = __ldg(P.ib + vi0);
-				vi1 = __ldg(P.ib + vi1);
-				vi2 = __ldg(P.ib + vi2);
+				vi0 = P.ix.fetch(vi0);
+				vi1 = P.ix.fetch(vi1);
+				vi2 = P.ix.fetch(vi2);
 			}
 			const VsOut v0 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi0), __ldg(P.vb + 2 * (size_t)vi0 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
 			const VsOut v1 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi1), __ldg(P.vb + 2 * (size_t)vi1 + 1), P.cb, P.vs_tex, P.rsqrt_lut);

@@ -49,6 +49,8 @@ struct mlv_buffer {
 	const mlv_buffer *chunk_vb;
 	uint64_t chunk_vb_version, chunk_self_version;
 	int chunk_indexed;
+	uint32_t chunk_start_index, chunk_index16;
+	int32_t chunk_base_vertex;
 };
 struct mlv_texture {
 	void *d;
@@ -98,6 +100,7 @@ struct mlv_device {
 
 	// bound pipeline state (graphics_pipeline)
 	mlv_buffer *vb, *ib;
+	int index_format; // MLV_INDEX_*
 	uint32_t input_layout;
 	int topology;
 	int vs_id, ps_id;
@@ -383,6 +386,12 @@ int mlv_ia_set_index_buffer(mlv_device *dev, mlv_buffer *ib) {
 	dev->ib = ib;
 	return MLV_OK;
 }
+int mlv_ia_set_index_format(mlv_device *dev, int format) {
+	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
+	if(format != MLV_INDEX_U32 && format != MLV_INDEX_U16) return fail(MLV_ERR_INVALID_ARGUMENT, "unknown index format %d", format);
+	dev->index_format = format;
+	return MLV_OK;
+}
 int mlv_ia_set_input_layout(mlv_device *dev, uint32_t bytes_per_vertex) {
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	if(bytes_per_vertex != 32) return fail(MLV_ERR_INVALID_ARGUMENT, "input layout %u: every reference shader consumes 32-byte vertices (in_vertex_size/VECTOR_WIDTH main.c:1286)", bytes_per_vertex);
@@ -506,7 +515,7 @@ static void launch_geom_clip(mlv_device *dev, const GeomParams &gp, uint32_t nbl
 	else launch_pdl(k_geom_clip<VS, false>, nblocks, MLV_CLIP_THREADS, dev->stream, gp);
 }
 
-static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
+static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t start_index = 0, int32_t base_vertex = 0) {
 	if(int rc = use_device(dev)) return rc;
 	// the reference's asserts (main.c:666,670,1230) become argument errors
 	if(dev->topology != MLV_PRIMITIVE_TOPOLOGY_TRIANGLELIST) return fail(MLV_ERR_STATE, "primitive topology must be TRIANGLELIST (main.c:666)");
@@ -515,7 +524,8 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	if(dev->input_layout != 32) return fail(MLV_ERR_STATE, "input layout not set");
 	if(!dev->vb) return fail(MLV_ERR_STATE, "no vertex buffer bound");
 	if(indexed && !dev->ib) return fail(MLV_ERR_STATE, "no index buffer bound");
-	if(indexed && (size_t)count * 4 > dev->ib->bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "index_count %u exceeds the bound index buffer", count);
+	const size_t index_bytes = dev->index_format == MLV_INDEX_U16 ? 2 : 4;
+	if(indexed && ((size_t)start_index + count) * index_bytes > dev->ib->bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "index range [%u, %u) exceeds the bound index buffer", start_index, start_index + count);
 	if(!indexed && (size_t)count * 32 > dev->vb->bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "vertex_count %u exceeds the bound vertex buffer", count);
 	if(dev->vs_id < 0 || dev->ps_id < 0) return fail(MLV_ERR_STATE, "vertex and pixel shader must be bound");
 	if(!dev->viewport_set) return fail(MLV_ERR_STATE, "viewport not set");
@@ -574,7 +584,10 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 
 	GeomParams gp;
 	memset(&gp, 0, sizeof(gp));
-	gp.ib = indexed ? (const uint32_t *)dev->ib->d : nullptr;
+	gp.ix.ib = indexed ? dev->ib->d : nullptr;
+	gp.ix.start_index = start_index;
+	gp.ix.base_vertex = base_vertex;
+	gp.ix.index16 = dev->index_format == MLV_INDEX_U16 ? 1u : 0u;
 	gp.vb = (const float4 *)dev->vb->d;
 	gp.tri_count = T;
 	gp.ovf_capacity = ovf_cap;
@@ -617,7 +630,8 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 	if(dev->part.num_ranks > 1 && !debug && (dev->vs_id == MLV_VS_BASIC || dev->vs_id == MLV_VS_VERTEX_LIGHTING)) {
 		mlv_buffer *owner = indexed ? dev->ib : dev->vb;
 		const bool valid = owner->chunk_bounds && owner->chunk_count == nblocks && owner->chunk_indexed == (indexed ? 1 : 0) && owner->chunk_self_version == owner->version &&
-		                   owner->chunk_vb == dev->vb && owner->chunk_vb_version == dev->vb->version;
+		                   owner->chunk_vb == dev->vb && owner->chunk_vb_version == dev->vb->version && owner->chunk_start_index == start_index &&
+		                   owner->chunk_base_vertex == base_vertex && owner->chunk_index16 == gp.ix.index16;
 		if(!valid) {
 			if(nblocks > owner->chunk_capacity) {
 				CUDA_TRY(cudaStreamSynchronize(dev->stream));
@@ -625,14 +639,17 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed) {
 				owner->chunk_capacity = nblocks;
 			}
 			prof_pre(dev, MLV_STAGE_GEOMETRY);
-			if(indexed) launch_pdl(k_chunk_bounds<true>, nblocks, MLV_GEOM_THREADS, dev->stream, gp.ib, gp.vb, T, owner->chunk_bounds);
-			else launch_pdl(k_chunk_bounds<false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp.ib, gp.vb, T, owner->chunk_bounds);
+			if(indexed) launch_pdl(k_chunk_bounds<true>, nblocks, MLV_GEOM_THREADS, dev->stream, gp.ix, gp.vb, T, owner->chunk_bounds);
+			else launch_pdl(k_chunk_bounds<false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp.ix, gp.vb, T, owner->chunk_bounds);
 			if(int rc = check_launch(dev, "k_chunk_bounds")) return rc;
 			owner->chunk_count = nblocks;
 			owner->chunk_indexed = indexed ? 1 : 0;
 			owner->chunk_self_version = owner->version;
 			owner->chunk_vb = dev->vb;
 			owner->chunk_vb_version = dev->vb->version;
+			owner->chunk_start_index = start_index;
+			owner->chunk_base_vertex = base_vertex;
+			owner->chunk_index16 = gp.ix.index16;
 		}
 		if(nblocks > dev->chunk_live_capacity) {
 			CUDA_TRY(cudaStreamSynchronize(dev->stream));
@@ -764,6 +781,9 @@ extern "C" {
 
 int mlv_draw_indexed(mlv_device *dev, uint32_t index_count) { return draw_common(dev, index_count, true); }
 int mlv_draw(mlv_device *dev, uint32_t vertex_count) { return draw_common(dev, vertex_count, false); }
+int mlv_draw_indexed_ex(mlv_device *dev, uint32_t index_count, uint32_t start_index_location, int32_t base_vertex_location) {
+	return draw_common(dev, index_count, true, start_index_location, base_vertex_location);
+}
 
 // ---- results -------------------------------------------------------------------------------------
 

@@ -68,8 +68,21 @@ struct DebugOut {
 	mlv_ref_tile_info *infos;
 };
 
+// Index fetch of the input assembler (main.c:681-683) with the parts of ID3D11DeviceContext::DrawIndexed the reference
+// leaves as TODOs: 16-bit index buffers (main.c:72), StartIndexLocation and BaseVertexLocation (main.c:1219).
+struct IndexStream {
+	const void *ib;
+	uint32_t start_index;
+	int32_t base_vertex;
+	uint32_t index16; // 0: u32 indices, 1: u16 indices
+	__device__ __forceinline__ uint32_t fetch(uint32_t i) const {
+		const uint32_t raw = index16 ? (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(ib) + start_index + i) : __ldg(reinterpret_cast<const uint32_t *>(ib) + start_index + i);
+		return raw + (uint32_t)base_vertex;
+	}
+};
+
 struct GeomParams {
-	const uint32_t *ib;
+	IndexStream ix;
 	const float4 *vb;
 	uint32_t tri_count;    // T: input triangles == number of direct slots
 	uint32_t ovf_capacity; // overflow slots available

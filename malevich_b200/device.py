@@ -154,6 +154,11 @@ class Device:
             pass
 
     # ---- resources -----------------------------------------------------------------------------
+    def _index_buffer(self, arr: np.ndarray):
+        """u32 index arrays as in the reference; u16 arrays select the 16-bit index format (the reference's TODO, main.c:72)."""
+        L.check(self._lib.mlv_ia_set_index_format(self._h, L.INDEX_U16 if arr.dtype == np.uint16 else L.INDEX_U32))
+        return self._buffer(arr, L.BUFFER_INDEX)
+
     def _buffer(self, arr: np.ndarray, kind: int):
         key = (id(arr), kind)
         hit = self._buffers.get(key)
@@ -180,7 +185,7 @@ class Device:
             if isinstance(o, Texture2D):
                 self._texture(o)
             elif isinstance(o, np.ndarray):
-                self._buffer(o, L.BUFFER_INDEX if o.dtype == np.uint32 and o.ndim == 1 else L.BUFFER_VERTEX)
+                self._buffer(o, L.BUFFER_INDEX if o.dtype in (np.uint32, np.uint16) and o.ndim == 1 else L.BUFFER_VERTEX)
 
     def invalidate(self, obj):
         """Forget the device copy of a host array / texture whose contents changed."""
@@ -212,7 +217,7 @@ class Device:
         if need_indices:
             if gp.ia.p_index_buffer is None:
                 raise L.MalevichError(L.MLV_ERR_STATE, "ia.p_index_buffer is not set")
-            L.check(lib.mlv_ia_set_index_buffer(h, self._buffer(gp.ia.p_index_buffer, L.BUFFER_INDEX)))
+            L.check(lib.mlv_ia_set_index_buffer(h, self._index_buffer(gp.ia.p_index_buffer)))
         if gp.vs.shader is None or gp.ps.shader is None:
             raise L.MalevichError(L.MLV_ERR_STATE, "vs.shader / ps.shader is not set")
         if gp.vs.output_register_count != 3:
@@ -233,9 +238,12 @@ class Device:
         vp = L.Viewport(v.top_left_x, v.top_left_y, v.width, v.height, v.min_depth, v.max_depth)
         L.check(lib.mlv_rs_set_viewport(h, C.byref(vp)))
 
-    def draw_indexed(self, index_count: int):  # main.c:1219
+    def draw_indexed(self, index_count: int, start_index_location: int = 0, base_vertex_location: int = 0):  # main.c:1219 (+ its TODO arguments)
         self._bind(True)
-        L.check(self._lib.mlv_draw_indexed(self._h, int(index_count)))
+        if start_index_location or base_vertex_location:
+            L.check(self._lib.mlv_draw_indexed_ex(self._h, int(index_count), int(start_index_location), int(base_vertex_location)))
+        else:
+            L.check(self._lib.mlv_draw_indexed(self._h, int(index_count)))
 
     def draw(self, vertex_count: int):
         self._bind(False)

@@ -125,6 +125,46 @@ def test_draw_without_indices_equals_draw_indexed_with_identity_indices():
     assert np.array_equal(c1, c2) and np.array_equal(d1.view(np.uint32), d2.view(np.uint32))
 
 
+def test_draw_indexed_extensions_16bit_indices_start_index_base_vertex():
+    """The reference's TODOs (main.c:72, 1219) implemented: u16 index buffers, StartIndexLocation, BaseVertexLocation.
+    Oracle: the same triangles drawn the reference's way (u32 indices from 0) must give the same frame and Stats."""
+    from malevich_b200 import scenes
+    sc = cases.SMALL["emily_320x200"]()  # indexed sphere (vertex reuse) + fullscreen quad
+    with _device(sc.width, sc.height) as dev:
+        scenes.render(dev, sc)
+        ref_col, ref_dep = dev.present()
+        ref_stats = dev.stats()
+        # (a) u16 indices
+        o = sc.objects[0]
+        assert o.vertex_buffer.shape[0] < 65536
+        sc16 = scenes.Scene(sc.name, sc.width, sc.height, [scenes.SceneObject(o.vertex_buffer, o.index_buffer.astype(np.uint16), o.vertex_shader, o.pixel_shader, o.texture)] + sc.objects[1:],
+                            sc.per_frame_cb)
+        dev.reset_stats()
+        scenes.render(dev, sc16)
+        c, d = dev.present()
+        assert np.array_equal(c, ref_col) and np.array_equal(d.view(np.uint32), ref_dep.view(np.uint32)) and dev.stats() == ref_stats
+        # (b) one shared vertex/index buffer pair, sub-ranges addressed with start index + base vertex
+        pad_v = np.zeros((5, 8), np.float32)          # junk in front so that base_vertex matters
+        pad_i = np.full(24, 3, np.uint32)              # junk in front so that start_index matters
+        vb_all = np.concatenate([pad_v, o.vertex_buffer])
+        ib_all = np.concatenate([pad_i, o.index_buffer])
+        dev.reset_stats()
+        dev.clear_render_target_view(scenes.CLEAR_COLOR)
+        dev.clear_depth_stencil_view(0.0)
+        gp = dev.graphics_pipeline
+        gp.ia.p_vertex_buffer, gp.ia.p_index_buffer = vb_all, ib_all
+        gp.vs.shader, gp.ps.shader = o.vertex_shader, o.pixel_shader
+        gp.vs.p_shader_resource_views[0] = gp.ps.p_shader_resource_views[0] = o.texture
+        dev.draw_indexed(o.index_count, start_index_location=24, base_vertex_location=5)
+        q = sc.objects[1]
+        gp.ia.p_vertex_buffer, gp.ia.p_index_buffer = q.vertex_buffer, q.index_buffer
+        gp.vs.shader, gp.ps.shader = q.vertex_shader, q.pixel_shader
+        gp.vs.p_shader_resource_views[0] = gp.ps.p_shader_resource_views[0] = q.texture
+        dev.draw_indexed(q.index_count)
+        c, d = dev.present()
+        assert np.array_equal(c, ref_col) and np.array_equal(d.view(np.uint32), ref_dep.view(np.uint32)) and dev.stats() == ref_stats
+
+
 def test_edge_cases_and_error_behaviour():
     from malevich_b200 import MalevichError, scenes
     from malevich_b200 import _lib as L
