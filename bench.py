@@ -320,6 +320,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dom_ms_per_launch = kernel_ms[dom] / max(dom_launches, 1)
         dom_bytes_per_launch = kernel_bytes[dom] / max(dom_launches, 1)
         achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9 if dom_ms_per_launch > 0 else 0.0
+        # measured DRAM bytes per launch of that kernel from the committed ncu capture (same workload, 1 GPU), else null
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic_config5_n1.json")
+        if args.config == 5 and world == 1 and os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f)["kernels"].get(dom, {}).get("dram_bytes_per_launch")
         out = {
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
@@ -329,7 +335,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                        "tile_draws": stats["active_bin_count"], "parallelism": f"sort-first x{world}, stripe {stripe} tile rows" if multi else "single GPU",
                        "l2": "no flush: per-frame working set (inputs + per-draw setup records) >> 126 MB L2" if args.config == 5 else "no flush"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes_per_launch,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes_per_launch,
                          "ms_per_launch": dom_ms_per_launch, "launches_per_step": dom_launches},
             "roofline_frame": {"algorithmic_bytes_per_frame": b_alg, "achieved": b_alg / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
                                "frac": b_alg / (ms * 1e-3) / 1e9 / world / peak, "bytes_by_stage": b_stage},
