@@ -511,25 +511,21 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS) k_chunk_bounds(const IndexSt
 	}
 }
 
-// true when the chunk certainly bins nothing on this rank. Executed by the first warp of a CTA (lanes 0-7: corners).
+// true when the chunk certainly bins nothing on this rank
 __device__ __forceinline__ bool chunk_is_foreign(const GeomParams &P, uint32_t chunk) {
 	const float4 lo = __ldg(P.chunk_bounds + 2 * (size_t)chunk), hi = __ldg(P.chunk_bounds + 2 * (size_t)chunk + 1);
-	const uint32_t lane = lane_id();
-	const float4 corner = make_float4((lane & 1u) ? hi.x : lo.x, (lane & 2u) ? hi.y : lo.y, (lane & 4u) ? hi.z : lo.z, 1.0f);
-	const float4 cs = mul_m4_v4_pairwise(P.cb, corner);
-	// behind or near the eye plane the projection of the box is unbounded: keep the chunk
-	const bool ok = cs.w > 1e-6f && fabsf(cs.y) <= 3.0e38f;
-	const float ys = P.vp_m11 * (cs.y / cs.w) + P.vp_m13; // screen y of the corner (the exact path adds rounding of a few ulp)
-	float ymin = ok ? ys : -INFINITY, ymax = ok ? ys : INFINITY;
-	bool all_ok = ok;
+	if(lo.w != 0.0f) return false; // the chunk holds a NaN / Inf position
+	float ymin = INFINITY, ymax = -INFINITY;
 #pragma unroll
-	for(int d = 4; d > 0; d >>= 1) {
-		ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, d));
-		ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, d));
-		const int other_ok = __shfl_xor_sync(0xffffffffu, (int)all_ok, d); // (not inside the &&: every lane must execute the shuffle)
-		all_ok = all_ok && other_ok;
+	for(int k = 0; k < 8; ++k) {
+		const float4 corner = make_float4((k & 1) ? hi.x : lo.x, (k & 2) ? hi.y : lo.y, (k & 4) ? hi.z : lo.z, 1.0f);
+		const float4 cs = mul_m4_v4_pairwise(P.cb, corner);
+		// behind or near the eye plane the projection of the box is unbounded: keep the chunk
+		if(!(cs.w > 1e-6f && fabsf(cs.y) <= 3.0e38f)) return false;
+		const float ys = P.vp_m11 * (cs.y / cs.w) + P.vp_m13; // screen y of the corner (the exact path adds rounding of a few ulp)
+		ymin = fminf(ymin, ys);
+		ymax = fmaxf(ymax, ys);
 	}
-	if(!all_ok || lo.w != 0.0f) return false;
 	// conservative tile-row range: 2 pixels of slack for rounding + the +1 of max_bounds (main.c:897-898), clamped like
 	// min_bounds/max_bounds are (main.c:892-898)
 	const float h = (float)P.vp_h;
@@ -540,6 +536,23 @@ __device__ __forceinline__ bool chunk_is_foreign(const GeomParams &P, uint32_t c
 	for(int st = s0; st <= s1; ++st)
 		if(st % P.part.num_ranks == P.part.rank) return false;
 	return true;
+}
+
+// One thread per chunk: cull test + compaction of the chunks this rank has to process (order is irrelevant: triangles
+// carry their keys). k_geom then runs as a persistent grid over that list, so a skipped chunk costs one thread here
+// instead of a CTA launch there.
+__global__ void __launch_bounds__(256) k_chunk_select(const __grid_constant__ GeomParams P, uint32_t num_chunks) {
+	pdl_prologue();
+	const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = chunk < num_chunks && !chunk_is_foreign(P, chunk);
+	if(chunk < num_chunks) P.chunk_live[chunk] = live ? 1 : 0;
+	const uint32_t mask = __ballot_sync(0xffffffffu, live);
+	if(mask) {
+		uint32_t base = 0;
+		if(lane_id() == 0) base = atomicAdd(&P.ctr->live_chunks, (uint32_t)__popc(mask));
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if(live) P.live_list[base + __popc(mask & ((1u << lane_id()) - 1u))] = chunk;
+	}
 }
 
 // Post-transform vertex cache (the reference's TODO at main.c:672; it re-shades every index, vertex_count =
@@ -565,28 +578,20 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 	// slots of a warp are adjacent in HBM, so the warp stores 1536 B of TriCov and 3072 B of TriShade with fully
 	// coalesced 128-bit stores instead of 32 scattered 16-byte pieces per instruction.
 	__shared__ uint4 s_stage[MLV_GEOM_THREADS / 32][32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)];
-	const uint32_t t = blockIdx.x * MLV_GEOM_THREADS + threadIdx.x;
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 	uint32_t emitted = 0, pairs = 0;
-	bool needs_clip = false, is_big = false;
-	bool staged = false; // this lane has a record for its direct slot t
-	uint4 bounds = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, t << 3);
-	if(t == 0) { // Stats (main.c:1228-1232)
+	if(blockIdx.x == 0 && threadIdx.x == 0) { // Stats (main.c:1228-1232)
 		P.ctr->stats.vertex_count += P.index_count;
 		P.ctr->stats.input_triangle_count += P.tri_count;
 	}
-	if(P.chunk_bounds) { // sort-first: skip chunks that cannot touch this rank's tile rows
-		__shared__ int s_foreign;
-		if(warp == 0) {
-			const bool foreign = chunk_is_foreign(P, blockIdx.x);
-			if(lane == 0) {
-				s_foreign = foreign;
-				P.chunk_live[blockIdx.x] = foreign ? 0 : 1;
-			}
-		}
-		__syncthreads();
-		if(s_foreign) return;
-	}
+	// Single GPU: CTA b processes chunk b. Sort-first: a persistent grid walks the list of chunks k_chunk_select kept.
+	const uint32_t num_items = P.live_list ? P.ctr->live_chunks : gridDim.x;
+	for(uint32_t item = blockIdx.x; item < num_items; item += gridDim.x) {
+	const uint32_t chunk = P.live_list ? P.live_list[item] : item;
+	const uint32_t t = chunk * MLV_GEOM_THREADS + threadIdx.x;
+	bool needs_clip = false, is_big = false;
+	bool staged = false; // this lane has a record for its direct slot t
+	uint4 bounds = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, t << 3);
 	if(t < P.tri_count) {
 		// ---- input assembler (main.c:662-696): index fetch + vertex fetch. Work is done lazily: positions for every
 		// triangle, the second half of each vertex and the attribute part of the vertex shader only for triangles
@@ -718,6 +723,8 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 			const uint32_t chunk = i * 32 + lane;
 			if((valid >> (chunk / MLV_TRI_SHADE_U4)) & 1u) sh[chunk] = st[32 * MLV_TRI_COV_U4 + chunk];
 		}
+	}
+	__syncwarp(); // the staging rows are reused by the next chunk of a persistent CTA
 	}
 	tally_stats(P.stat_stripes, emitted, pairs);
 }
@@ -1234,7 +1241,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant
 			c->stats.active_bin_count += c->draw_active_bins;
 			c->last_ovf_count = c->ovf_count;
 			c->draw_active_bins = 0u;
-			c->ovf_count = c->clip_count = c->big_count = c->huge_count = 0u;
+			c->ovf_count = c->clip_count = c->big_count = c->huge_count = c->live_chunks = 0u;
 		}
 	}
 	if(P.ctr->pair_total > pair_capacity) return; // draw skipped, MLV_FLAG_PAIR_OVERFLOW is set

@@ -80,6 +80,7 @@ struct mlv_device {
 	float4 *vcache;
 	uint32_t vcache_capacity;
 	uint8_t *chunk_live;
+	uint32_t *live_list;
 	uint32_t chunk_live_capacity;
 	uint32_t bin_begin, bin_end; // bins this rank can touch: everything, or one contiguous band
 	uint32_t tri_capacity; // slots (direct + overflow)
@@ -278,7 +279,7 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(!dev) return;
 	cudaSetDevice(dev->cuda_dev);
 	if(dev->stream) cudaStreamSynchronize(dev->stream);
-	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue, dev->vcache, dev->chunk_live,
+	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue, dev->vcache, dev->chunk_live, dev->live_list,
 		             dev->scan_state, dev->ctr, dev->stat_stripes, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
@@ -495,6 +496,7 @@ static TexDesc tex_desc(const mlv_texture *t) {
 template <int VS>
 static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed, uint32_t vcache_vertices) {
 	const bool debug = gp.keep_all;
+	if(gp.live_list && nblocks > 148u * 4u) nblocks = 148u * 4u; // persistent grid over the live-chunk list
 	if(vcache_vertices) {
 		prof_pre(dev, MLV_STAGE_VERTEX);
 		launch_pdl(k_vertex<VS>, (vcache_vertices + 255u) / 256u, 256, dev->stream, gp, vcache_vertices);
@@ -654,10 +656,15 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 		if(nblocks > dev->chunk_live_capacity) {
 			CUDA_TRY(cudaStreamSynchronize(dev->stream));
 			CUDA_TRY(regrow(&dev->chunk_live, (size_t)nblocks));
+			CUDA_TRY(regrow(&dev->live_list, (size_t)nblocks));
 			dev->chunk_live_capacity = nblocks;
 		}
 		gp.chunk_bounds = owner->chunk_bounds;
 		gp.chunk_live = dev->chunk_live;
+		gp.live_list = dev->live_list;
+		prof_pre(dev, MLV_STAGE_GEOMETRY);
+		launch_pdl(k_chunk_select, (nblocks + 255u) / 256u, 256, dev->stream, gp, nblocks);
+		if(int rc = check_launch(dev, "k_chunk_select")) return rc;
 	}
 	// Post-transform vertex cache: worth it when the index buffer references each vertex of the buffer about twice or
 	// more (the bound vertex buffer's size is the only vertex count a D3D11-style draw call has).
