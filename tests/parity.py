@@ -14,6 +14,25 @@ COLOR_TOL_FRACTION = 0.999  # >= 99.9 % of pixels within 1/255 per channel
 COLOR_TOL_MAX = 2           # none off by more than 2/255
 
 
+def host_vrsqrtps_matches_table(oracle) -> bool:
+    """The live oracle executes the HOST's vrsqrtps (math.h:278), a hardware-defined approximation; the
+    GPU reproduces the Intel table committed in csrc/rsqrt_lut.inc. On a host whose instruction differs (non-Intel)
+    the live oracle is not the canonical reference for anything that goes through a normal; the committed golden frames
+    (generated on an Intel host) remain valid."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "malevich_b200", "csrc", "rsqrt_lut.inc")).read()
+    lut = [int(x, 16) for x in re.findall(r"0x([0-9a-f]{8})u", txt)]
+    for parity_bit in (0, 1):
+        for i in range(0, 1024, 7):
+            x = np.array([((127 + parity_bit) << 23) | (i << 13)], dtype=np.uint32).view(np.float32)[0]
+            got = int(np.float32(oracle.rsqrt(float(x))).view(np.uint32))
+            if got != lut[parity_bit * 1024 + i]:
+                return False
+    return True
+
+
 def channel_diff(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     """max over the four bytes of |a - b| per pixel."""
     d = np.zeros(a.shape, dtype=np.int32)

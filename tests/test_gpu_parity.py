@@ -58,6 +58,8 @@ def test_every_stage_against_live_reference(name):
     if not have_ref(sc.width, sc.height):
         pytest.skip("oracle/_ref not available for this resolution")
     orc = _oracle(sc.width, sc.height)
+    if not parity.host_vrsqrtps_matches_table(orc):
+        pytest.skip("host vrsqrtps differs from the committed Intel table: live oracle not canonical here (golden-frame tests still apply)")
     with _device(sc.width, sc.height, debug_capture=True) as dev:
         results = parity.render_both_staged(dev, orc, sc)
         for draw_name, res in results:
@@ -81,7 +83,7 @@ def test_config5_full_size_against_live_reference():
     assert _fnv(dep) == GOLDEN[name]["depth_fnv"]  # depth bit-exact against the reference, via the committed hash
     if have_ref(sc.width, sc.height):
         orc = _oracle(sc.width, sc.height)
-        orc.render(sc)
+        orc.render(sc)  # (basic_ps does not read the normal, so this comparison does not depend on the host's vrsqrtps)
         parity.assert_frames_match(col, dep, orc.colors(), orc.depths(), name)
 
 
@@ -220,6 +222,8 @@ def test_clipping_heavy_camera_against_live_reference():
         cb = camera.per_frame_cb(320, 200, *pose)
         sc = scenes.ftm(320, 200, cb=cb)
         orc = _oracle(320, 200)
+        if not parity.host_vrsqrtps_matches_table(orc):
+            pytest.skip("host vrsqrtps differs from the committed Intel table")
         with _device(320, 200, debug_capture=True) as dev:
             for draw_name, res in parity.render_both_staged(dev, orc, sc):
                 assert parity.staged_ok(res), f"{pose}/{draw_name}: {res}"
