@@ -263,6 +263,45 @@ struct BinTally {
 	uint32_t pairs;
 	bool live, big, huge;
 };
+// Rectangles of at most N tiles: walk them with fully unrolled, predicated steps so that the tile-minimum and counter
+// loads of all tiles are independent and in flight together (they were a chain of dependent L2 round trips), then
+// issue the atomics. A bin already flagged as touched needs no second atomicOr (a stale read only repeats it).
+template <int N>
+__device__ __forceinline__ void count_small_rect(const GeomParams &P, const TileRect &tr, int cnt, float max_depth, BinTally &r) {
+	uint32_t bins[N];
+	bool ok[N];
+	{
+		int tx = tr.tx0, ty = tr.ty0;
+#pragma unroll
+		for(int k = 0; k < N; ++k) {
+			ok[k] = k < cnt && P.part.owns_row(ty);
+			bins[k] = (uint32_t)(ty * P.wt + tx);
+			if(++tx > tr.tx1) {
+				tx = tr.tx0;
+				++ty;
+			}
+		}
+	}
+	float tm[N];
+	uint32_t bc[N];
+#pragma unroll
+	for(int k = 0; k < N; ++k) {
+		tm[k] = ok[k] ? __ldg(P.tile_min + bins[k]) : 0.0f;
+		bc[k] = (ok[k] && !P.keep_all) ? __ldcg(P.bin_count + bins[k]) : 0u;
+	}
+#pragma unroll
+	for(int k = 0; k < N; ++k) {
+		if(!ok[k]) continue;
+		++r.pairs;
+		if(!P.keep_all && max_depth < tm[k]) { // Hi-Z (main.c:1006), see hiz_rejects
+			if(!(bc[k] & MLV_TOUCHED)) atomicOr(P.bin_count + bins[k], MLV_TOUCHED);
+		} else {
+			atomicAdd(P.bin_count + bins[k], 1u);
+			r.live = true;
+		}
+	}
+}
+
 __device__ __forceinline__ BinTally count_bins(const GeomParams &P, const TriSetup &S) {
 	BinTally r = { 0u, false, false, false };
 	const TileRect tr = tile_rect(S.minx, S.miny, S.maxx, S.maxy, P.wt, P.ht);
@@ -274,41 +313,10 @@ __device__ __forceinline__ BinTally count_bins(const GeomParams &P, const TriSet
 		r.huge = r.live && cnt > MLV_HUGE_TILES;
 		return r;
 	}
-	// <= 8 tiles: walk the rectangle with fully unrolled, predicated steps so that the tile-minimum and counter loads
-	// of all tiles are independent and in flight together (they were a chain of dependent L2 round trips), then
-	// issue the atomics. A bin already flagged as touched needs no second atomicOr (a stale read only repeats it).
-	uint32_t bins[8];
-	bool ok[8];
-	{
-		int tx = tr.tx0, ty = tr.ty0;
-#pragma unroll
-		for(int k = 0; k < 8; ++k) {
-			ok[k] = k < cnt && P.part.owns_row(ty);
-			bins[k] = (uint32_t)(ty * P.wt + tx);
-			if(++tx > tr.tx1) {
-				tx = tr.tx0;
-				++ty;
-			}
-		}
-	}
-	float tm[8];
-	uint32_t bc[8];
-#pragma unroll
-	for(int k = 0; k < 8; ++k) {
-		tm[k] = ok[k] ? __ldg(P.tile_min + bins[k]) : 0.0f;
-		bc[k] = (ok[k] && !P.keep_all) ? __ldcg(P.bin_count + bins[k]) : 0u;
-	}
-#pragma unroll
-	for(int k = 0; k < 8; ++k) {
-		if(!ok[k]) continue;
-		++r.pairs;
-		if(!P.keep_all && S.max_depth < tm[k]) { // Hi-Z (main.c:1006), see hiz_rejects
-			if(!(bc[k] & MLV_TOUCHED)) atomicOr(P.bin_count + bins[k], MLV_TOUCHED);
-		} else {
-			atomicAdd(P.bin_count + bins[k], 1u);
-			r.live = true;
-		}
-	}
+	// dense meshes of pixel-sized triangles (BASELINE config 5: 2.2 tiles per triangle) almost never need more than
+	// four steps; the eight-step walk costs a third of the geometry kernel's instructions when every lane pays for it
+	if(cnt <= 4) count_small_rect<4>(P, tr, cnt, S.max_depth, r);
+	else count_small_rect<8>(P, tr, cnt, S.max_depth, r);
 	return r;
 }
 
@@ -538,23 +546,6 @@ __device__ __forceinline__ bool chunk_is_foreign(const GeomParams &P, uint32_t c
 	return true;
 }
 
-// One thread per chunk: cull test + compaction of the chunks this rank has to process (order is irrelevant: triangles
-// carry their keys). k_geom then runs as a persistent grid over that list, so a skipped chunk costs one thread here
-// instead of a CTA launch there.
-__global__ void __launch_bounds__(256) k_chunk_select(const __grid_constant__ GeomParams P, uint32_t num_chunks) {
-	pdl_prologue();
-	const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool live = chunk < num_chunks && !chunk_is_foreign(P, chunk);
-	if(chunk < num_chunks) P.chunk_live[chunk] = live ? 1 : 0;
-	const uint32_t mask = __ballot_sync(0xffffffffu, live);
-	if(mask) {
-		uint32_t base = 0;
-		if(lane_id() == 0) base = atomicAdd(&P.ctr->live_chunks, (uint32_t)__popc(mask));
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if(live) P.live_list[base + __popc(mask & ((1u << lane_id()) - 1u))] = chunk;
-	}
-}
-
 // Post-transform vertex cache (the reference's TODO at main.c:672; it re-shades every index, vertex_count =
 // index_count main.c:673). For indexed meshes that reuse vertices, k_vertex evaluates the position part of the vertex
 // shader and the per-vertex part of primitive assembly once per UNIQUE vertex; k_geom<VCACHE> then gathers 32 bytes
@@ -584,10 +575,26 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 		P.ctr->stats.vertex_count += P.index_count;
 		P.ctr->stats.input_triangle_count += P.tri_count;
 	}
-	// Single GPU: CTA b processes chunk b. Sort-first: a persistent grid walks the list of chunks k_chunk_select kept.
-	const uint32_t num_items = P.live_list ? P.ctr->live_chunks : gridDim.x;
-	for(uint32_t item = blockIdx.x; item < num_items; item += gridDim.x) {
-	const uint32_t chunk = P.live_list ? P.live_list[item] : item;
+	// Single GPU: CTA b processes chunk b (the loops below run once). Sort-first: a persistent grid strides over the
+	// chunks; each round, thread k of the CTA tests the cached object-space bounds of the CTA's k-th chunk against this
+	// rank's tile rows, so a foreign chunk costs one thread's cull test instead of a CTA (or a kernel of its own).
+	__shared__ uint8_t s_live[MLV_GEOM_THREADS];
+	const uint32_t num_chunks = (P.tri_count + MLV_GEOM_THREADS - 1u) / MLV_GEOM_THREADS;
+	for(uint32_t first = blockIdx.x; first < num_chunks; first += gridDim.x * MLV_GEOM_THREADS) {
+	if(P.chunk_bounds) {
+		const uint32_t c = first + threadIdx.x * gridDim.x;
+		bool live = false;
+		if(c < num_chunks) {
+			live = !chunk_is_foreign(P, c);
+			P.chunk_live[c] = live ? 1 : 0; // k_bin_fill skips the stale bounds of the chunks nobody rewrote
+		}
+		s_live[threadIdx.x] = live ? 1 : 0;
+		__syncthreads();
+	}
+	for(uint32_t k = 0; k < MLV_GEOM_THREADS; ++k) {
+	const uint32_t chunk = first + k * gridDim.x;
+	if(chunk >= num_chunks) break;
+	if(P.chunk_bounds && !s_live[k]) continue;
 	const uint32_t t = chunk * MLV_GEOM_THREADS + threadIdx.x;
 	bool needs_clip = false, is_big = false;
 	bool staged = false; // this lane has a record for its direct slot t
@@ -649,10 +656,10 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 				}
 				if(kept) {
 					direct = true;
-					emitted = P.part.owns_row(S.miny / 8) ? 1u : 0u; // counted once across ranks: by the owner of its first tile row
+					emitted += P.part.owns_row(S.miny / 8) ? 1u : 0u; // counted once across ranks: by the owner of its first tile row
 					// ---- binner pass 1 + Hi-Z for this triangle; a triangle hidden in every tile it touches writes no record
 					const BinTally tally = count_bins(P, S);
-					pairs = tally.pairs;
+					pairs += tally.pairs;
 					is_big = tally.big;
 					if(tally.huge) P.huge_queue[atomicAdd(&P.ctr->huge_count, 1u)] = t; // rare: sky domes, full-screen quads
 					if(tally.live || DEBUG) {
@@ -725,6 +732,8 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 		}
 	}
 	__syncwarp(); // the staging rows are reused by the next chunk of a persistent CTA
+	}
+	if(P.chunk_bounds) __syncthreads(); // s_live is rewritten by the next round
 	}
 	tally_stats(P.stat_stripes, emitted, pairs);
 }
@@ -855,6 +864,30 @@ __device__ __forceinline__ void fill_one(const BinParams &P, int k, int cnt, int
 	if(!hiz_rejects(max_depth, P.tile_min, bin, P.keep_all)) P.pair_ids[atomicAdd(P.bin_offset + bin, 1u)] = key;
 }
 
+// unrolled, predicated walk over a rectangle of at most N tiles: all tile-minimum loads, then all atomics, then all stores
+template <int N>
+__device__ __forceinline__ void fill_small_rect(const BinParams &P, const SlotBounds &s, int cnt) {
+	uint32_t bins[N], pos[N];
+	bool ok[N];
+	int tx = s.tr.tx0, ty = s.tr.ty0;
+#pragma unroll
+	for(int k = 0; k < N; ++k) {
+		ok[k] = k < cnt && P.part.owns_row(ty);
+		bins[k] = (uint32_t)(ty * P.wt + tx);
+		if(++tx > s.tr.tx1) {
+			tx = s.tr.tx0;
+			++ty;
+		}
+	}
+#pragma unroll
+	for(int k = 0; k < N; ++k) ok[k] = ok[k] && !hiz_rejects(s.max_depth, P.tile_min, bins[k], P.keep_all);
+#pragma unroll
+	for(int k = 0; k < N; ++k) pos[k] = ok[k] ? atomicAdd(P.bin_offset + bins[k], 1u) : 0u;
+#pragma unroll
+	for(int k = 0; k < N; ++k)
+		if(ok[k]) P.pair_ids[pos[k]] = s.key;
+}
+
 __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinParams P, uint32_t pair_capacity) {
 	pdl_prologue();
 	if(P.ctr->pair_total > pair_capacity || P.ctr->pair_total == 0u) return; // draw skipped (MLV_FLAG_PAIR_OVERFLOW is set) / nothing survived Hi-Z
@@ -869,27 +902,8 @@ __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinPar
 		const bool live_chunk = !P.chunk_live || slot >= P.direct_slots || __ldg(P.chunk_live + slot / MLV_GEOM_THREADS) != 0;
 		if(slot < n && live_chunk) s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
 		const int w = s.empty ? 0 : s.tr.w(), cnt = s.empty ? 0 : w * s.tr.h();
-		if(cnt > 0 && cnt <= 8) { // unrolled, predicated walk: all tile-minimum loads, then all atomics, then all stores
-			uint32_t bins[8], pos[8];
-			bool ok[8];
-			int tx = s.tr.tx0, ty = s.tr.ty0;
-#pragma unroll
-			for(int k = 0; k < 8; ++k) {
-				ok[k] = k < cnt && P.part.owns_row(ty);
-				bins[k] = (uint32_t)(ty * P.wt + tx);
-				if(++tx > s.tr.tx1) {
-					tx = s.tr.tx0;
-					++ty;
-				}
-			}
-#pragma unroll
-			for(int k = 0; k < 8; ++k) ok[k] = ok[k] && !hiz_rejects(s.max_depth, P.tile_min, bins[k], P.keep_all);
-#pragma unroll
-			for(int k = 0; k < 8; ++k) pos[k] = ok[k] ? atomicAdd(P.bin_offset + bins[k], 1u) : 0u;
-#pragma unroll
-			for(int k = 0; k < 8; ++k)
-				if(ok[k]) P.pair_ids[pos[k]] = s.key;
-		}
+		if(cnt > 0 && cnt <= 4) fill_small_rect<4>(P, s, cnt);
+		else if(cnt > 0 && cnt <= 8) fill_small_rect<8>(P, s, cnt);
 	}
 	const uint32_t nbig = P.ctr->big_count;
 	for(uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nbig; i += warps) { // 9..MLV_HUGE_TILES tiles: one warp per triangle
@@ -1241,7 +1255,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant
 			c->stats.active_bin_count += c->draw_active_bins;
 			c->last_ovf_count = c->ovf_count;
 			c->draw_active_bins = 0u;
-			c->ovf_count = c->clip_count = c->big_count = c->huge_count = c->live_chunks = 0u;
+			c->ovf_count = c->clip_count = c->big_count = c->huge_count = 0u;
 		}
 	}
 	if(P.ctr->pair_total > pair_capacity) return; // draw skipped, MLV_FLAG_PAIR_OVERFLOW is set

@@ -77,10 +77,16 @@ struct mlv_device {
 	uint4 *tri_cov, *tri_shade;
 	uint4 *tri_bounds;
 	uint32_t *clip_queue, *big_queue, *huge_queue;
-	float4 *vcache;
+	// Post-transform vertex cache, double-buffered: k_vertex of draw d+1 depends on nothing draw d produces, so it runs
+	// on a second stream underneath draw d's binning and tile kernels and joins the main stream before k_geom.
+	float4 *vcache[2];
 	uint32_t vcache_capacity;
+	int vcache_sel;
+	cudaStream_t side_stream;
+	cudaEvent_t ev_vertex_done, ev_main_sync, ev_cache_free[2];
+	bool cache_free_recorded[2];
+	bool side_needs_sync; // a buffer was written on the main stream since the side stream last synchronised with it
 	uint8_t *chunk_live;
-	uint32_t *live_list;
 	uint32_t chunk_live_capacity;
 	uint32_t bin_begin, bin_end; // bins this rank can touch: everything, or one contiguous band
 	uint32_t tri_capacity; // slots (direct + overflow)
@@ -238,6 +244,12 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	} while(0)
 
 	CREATE_TRY(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+	CREATE_TRY(cudaStreamCreateWithFlags(&dev->side_stream, cudaStreamNonBlocking));
+	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_vertex_done, cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_main_sync, cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_cache_free[0], cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_cache_free[1], cudaEventDisableTiming));
+	dev->side_needs_sync = true;
 	const size_t nb = dev->num_bins;
 	CREATE_TRY(cudaMalloc(&dev->fb, nb * 32 * sizeof(uint4)));
 	CREATE_TRY(cudaMalloc(&dev->tile_min, nb * sizeof(float)));
@@ -279,11 +291,15 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(!dev) return;
 	cudaSetDevice(dev->cuda_dev);
 	if(dev->stream) cudaStreamSynchronize(dev->stream);
-	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue, dev->vcache, dev->chunk_live, dev->live_list,
+	if(dev->side_stream) cudaStreamSynchronize(dev->side_stream);
+	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue, dev->vcache[0], dev->vcache[1], dev->chunk_live,
 		             dev->scan_state, dev->ctr, dev->stat_stripes, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
 	if(dev->stream) cudaStreamDestroy(dev->stream);
+	if(dev->side_stream) cudaStreamDestroy(dev->side_stream);
+	for(cudaEvent_t e : { dev->ev_vertex_done, dev->ev_main_sync, dev->ev_cache_free[0], dev->ev_cache_free[1] })
+		if(e) cudaEventDestroy(e);
 	if(dev->prof_events) {
 		for(cudaEvent_t e : *dev->prof_events) cudaEventDestroy(e);
 		delete dev->prof_events;
@@ -324,6 +340,7 @@ int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t
 	if(int rc = use_device(dev)) return rc;
 	if(!buf || !data || bytes > buf->bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer update");
 	CUDA_TRY(cudaMemcpyAsync(buf->d, data, bytes, cudaMemcpyHostToDevice, dev->stream));
+	dev->side_needs_sync = true;
 	buf->version++;
 	return MLV_OK;
 }
@@ -496,13 +513,33 @@ static TexDesc tex_desc(const mlv_texture *t) {
 template <int VS>
 static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed, uint32_t vcache_vertices) {
 	const bool debug = gp.keep_all;
-	if(gp.live_list && nblocks > 148u * 4u) nblocks = 148u * 4u; // persistent grid over the live-chunk list
+	if(gp.chunk_bounds && nblocks > 148u * 4u) nblocks = 148u * 4u; // sort-first: persistent grid, chunks culled inside k_geom
 	if(vcache_vertices) {
+		const int sel = dev->vcache_sel;
+		dev->vcache_sel ^= 1;
+		// Per-stage profiling brackets every kernel with events on the main stream, so it keeps k_vertex there.
+		cudaStream_t vs_stream = dev->prof_on ? dev->stream : dev->side_stream;
+		if(!dev->prof_on) {
+			if(dev->side_needs_sync) { // uploads are ordered on the main stream: everything issued so far comes first
+				cudaEventRecord(dev->ev_main_sync, dev->stream);
+				cudaStreamWaitEvent(dev->side_stream, dev->ev_main_sync, 0);
+				dev->side_needs_sync = false;
+			} else if(dev->cache_free_recorded[sel]) { // the k_geom that read this half of the cache two draws ago
+				cudaStreamWaitEvent(dev->side_stream, dev->ev_cache_free[sel], 0);
+			}
+		}
 		prof_pre(dev, MLV_STAGE_VERTEX);
-		launch_pdl(k_vertex<VS>, (vcache_vertices + 255u) / 256u, 256, dev->stream, gp, vcache_vertices);
+		launch_pdl(k_vertex<VS>, (vcache_vertices + 255u) / 256u, 256, vs_stream, gp, vcache_vertices);
 		check_launch(dev, "k_vertex");
+		if(!dev->prof_on) {
+			cudaEventRecord(dev->ev_vertex_done, dev->side_stream);
+			cudaStreamWaitEvent(dev->stream, dev->ev_vertex_done, 0);
+		}
 		prof_pre(dev, MLV_STAGE_GEOMETRY);
 		launch_pdl(k_geom<VS, true, false, true>, nblocks, MLV_GEOM_THREADS, dev->stream, gp);
+		// (recorded before check_launch's profiling event so the GEOMETRY bracket still closes on the kernel)
+		cudaEventRecord(dev->ev_cache_free[sel], dev->stream);
+		dev->cache_free_recorded[sel] = true;
 		return;
 	}
 	prof_pre(dev, MLV_STAGE_GEOMETRY);
@@ -656,15 +693,10 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 		if(nblocks > dev->chunk_live_capacity) {
 			CUDA_TRY(cudaStreamSynchronize(dev->stream));
 			CUDA_TRY(regrow(&dev->chunk_live, (size_t)nblocks));
-			CUDA_TRY(regrow(&dev->live_list, (size_t)nblocks));
 			dev->chunk_live_capacity = nblocks;
 		}
 		gp.chunk_bounds = owner->chunk_bounds;
 		gp.chunk_live = dev->chunk_live;
-		gp.live_list = dev->live_list;
-		prof_pre(dev, MLV_STAGE_GEOMETRY);
-		launch_pdl(k_chunk_select, (nblocks + 255u) / 256u, 256, dev->stream, gp, nblocks);
-		if(int rc = check_launch(dev, "k_chunk_select")) return rc;
 	}
 	// Post-transform vertex cache: worth it when the index buffer references each vertex of the buffer about twice or
 	// more (the bound vertex buffer's size is the only vertex count a D3D11-style draw call has).
@@ -675,10 +707,12 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 			vcache_vertices = (uint32_t)vb_vertices;
 			if(vcache_vertices > dev->vcache_capacity) {
 				CUDA_TRY(cudaStreamSynchronize(dev->stream));
-				CUDA_TRY(regrow(&dev->vcache, (size_t)vcache_vertices * 2));
+				CUDA_TRY(cudaStreamSynchronize(dev->side_stream));
+				CUDA_TRY(regrow(&dev->vcache[0], (size_t)vcache_vertices * 2));
+				CUDA_TRY(regrow(&dev->vcache[1], (size_t)vcache_vertices * 2));
 				dev->vcache_capacity = vcache_vertices;
 			}
-			gp.vcache = dev->vcache;
+			gp.vcache = dev->vcache[dev->vcache_sel];
 		}
 	}
 	switch(dev->vs_id) {

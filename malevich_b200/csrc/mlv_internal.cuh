@@ -52,7 +52,7 @@ struct Counters {
 	uint32_t draw_pairs_all;   // (triangle,tile) pairs of the current draw including Hi-Z-rejected ones (Stats)
 	uint32_t draw_active_bins; // non-empty bins of the current draw in the reference's sense (Stats)
 	uint32_t huge_count;  // triangles with more than MLV_HUGE_TILES tiles in the current draw (reset by k_tile)
-	uint32_t live_chunks; // chunks on k_geom's work list in the current draw (sort-first only, reset by k_tile)
+	uint32_t reserved0;
 	uint32_t pad[3];
 	mlv_stats stats;      // accumulated like reference main.c:1228-1246
 };
@@ -101,8 +101,7 @@ struct GeomParams {
 	uint4 *tri_shade;
 	uint4 *tri_bounds;
 	const float4 *chunk_bounds; // sort-first chunk culling: 2 x float4 per k_geom CTA, or null
-	uint8_t *chunk_live;        // written by k_chunk_select: 1 = this rank processes the chunk
-	uint32_t *live_list;        // compacted list of those chunks (k_geom's work list), or null
+	uint8_t *chunk_live;        // written by k_geom's cull test: 1 = this rank processed the chunk
 	float4 *vcache; // 2 x float4 per unique vertex: clip-space position, {snapped x, snapped y, screen z, 1/w}
 	uint32_t *clip_queue;
 	uint32_t *big_queue;

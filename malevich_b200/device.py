@@ -128,6 +128,7 @@ class Device:
         self.graphics_pipeline = Pipeline()
         self._buffers = {}   # id(array) -> (array, handle)
         self._textures = {}  # id(Texture2D) -> (tex, handle)
+        self._sent = {}      # pipeline state as last sent through the C-ABI (see _bind)
 
     # ---- lifetime ------------------------------------------------------------------------------
     def close(self):
@@ -154,11 +155,6 @@ class Device:
             pass
 
     # ---- resources -----------------------------------------------------------------------------
-    def _index_buffer(self, arr: np.ndarray):
-        """u32 index arrays as in the reference; u16 arrays select the 16-bit index format (the reference's TODO, main.c:72)."""
-        L.check(self._lib.mlv_ia_set_index_format(self._h, L.INDEX_U16 if arr.dtype == np.uint16 else L.INDEX_U32))
-        return self._buffer(arr, L.BUFFER_INDEX)
-
     def _buffer(self, arr: np.ndarray, kind: int):
         key = (id(arr), kind)
         hit = self._buffers.get(key)
@@ -189,6 +185,7 @@ class Device:
 
     def invalidate(self, obj):
         """Forget the device copy of a host array / texture whose contents changed."""
+        self._sent.clear()
         if isinstance(obj, Texture2D):
             hit = self._textures.pop(id(obj), None)
             if hit:
@@ -208,35 +205,72 @@ class Device:
         L.check(self._lib.mlv_clear_depth_stencil_view(self._h, float(depth)))
 
     def _bind(self, need_indices: bool):
-        gp, lib, h = self.graphics_pipeline, self._lib, self._h
-        L.check(lib.mlv_ia_set_primitive_topology(h, int(gp.ia.primitive_topology)))
-        L.check(lib.mlv_ia_set_input_layout(h, int(gp.ia.input_layout)))
+        """Snapshot `graphics_pipeline` into the device, like the C shim does on every draw (host/malevich_compat.c).
+        Only state that differs from what was last sent crosses the C-ABI: a draw that re-binds the same objects costs one
+        ctypes call (the draw itself), which matters once the GPU side of a draw is tens of microseconds."""
+        gp, lib, h, sent = self.graphics_pipeline, self._lib, self._h, self._sent
+        v = int(gp.ia.primitive_topology)
+        if sent.get("topology") != v:
+            L.check(lib.mlv_ia_set_primitive_topology(h, v))
+            sent["topology"] = v
+        v = int(gp.ia.input_layout)
+        if sent.get("layout") != v:
+            L.check(lib.mlv_ia_set_input_layout(h, v))
+            sent["layout"] = v
         if gp.ia.p_vertex_buffer is None:
             raise L.MalevichError(L.MLV_ERR_STATE, "ia.p_vertex_buffer is not set")
-        L.check(lib.mlv_ia_set_vertex_buffer(h, self._buffer(gp.ia.p_vertex_buffer, L.BUFFER_VERTEX)))
+        hb = self._buffer(gp.ia.p_vertex_buffer, L.BUFFER_VERTEX)
+        if sent.get("vb") is not hb:
+            L.check(lib.mlv_ia_set_vertex_buffer(h, hb))
+            sent["vb"] = hb
         if need_indices:
-            if gp.ia.p_index_buffer is None:
+            ib = gp.ia.p_index_buffer
+            if ib is None:
                 raise L.MalevichError(L.MLV_ERR_STATE, "ia.p_index_buffer is not set")
-            L.check(lib.mlv_ia_set_index_buffer(h, self._index_buffer(gp.ia.p_index_buffer)))
+            fmt = L.INDEX_U16 if ib.dtype == np.uint16 else L.INDEX_U32  # u16 = the reference's TODO (main.c:72)
+            if sent.get("index_format") != fmt:
+                L.check(lib.mlv_ia_set_index_format(h, fmt))
+                sent["index_format"] = fmt
+            hb = self._buffer(ib, L.BUFFER_INDEX)
+            if sent.get("ib") is not hb:
+                L.check(lib.mlv_ia_set_index_buffer(h, hb))
+                sent["ib"] = hb
         if gp.vs.shader is None or gp.ps.shader is None:
             raise L.MalevichError(L.MLV_ERR_STATE, "vs.shader / ps.shader is not set")
         if gp.vs.output_register_count != 3:
             # the reference hard-codes three registers in interpolation and VS scatter (main.c:714-727,1124-1126)
             raise L.MalevichError(L.MLV_ERR_STATE, "vs.output_register_count must be 3")
-        L.check(lib.mlv_vs_set_shader(h, gp.vs.shader.vs_main))
-        L.check(lib.mlv_ps_set_shader(h, gp.ps.shader.ps_main))
+        v = gp.vs.shader.vs_main
+        if sent.get("vs") != v:
+            L.check(lib.mlv_vs_set_shader(h, v))
+            sent["vs"] = v
+        v = gp.ps.shader.ps_main
+        if sent.get("ps") != v:
+            L.check(lib.mlv_ps_set_shader(h, v))
+            sent["ps"] = v
         for slot, cb in enumerate(gp.vs.p_constant_buffers):
             if cb is not None:
-                a = np.ascontiguousarray(cb)
-                L.check(lib.mlv_vs_set_constant_buffer(h, slot, a.ctypes.data_as(C.c_void_p), a.nbytes))
+                raw = np.ascontiguousarray(cb).tobytes()  # the contents, not the object: hosts rewrite the camera in place every frame
+                if sent.get(("cb", slot)) != raw:
+                    L.check(lib.mlv_vs_set_constant_buffer(h, slot, raw, len(raw)))
+                    sent[("cb", slot)] = raw
+        sent_vs, sent_ps = sent.setdefault("vs_srv", [None] * 16), sent.setdefault("ps_srv", [None] * 16)
+        vs_srv, ps_srv = gp.vs.p_shader_resource_views, gp.ps.p_shader_resource_views
         for slot in range(16):
-            t = gp.vs.p_shader_resource_views[slot]
-            L.check(lib.mlv_vs_set_shader_resource(h, slot, self._texture(t) if t is not None else None))
-            t = gp.ps.p_shader_resource_views[slot]
-            L.check(lib.mlv_ps_set_shader_resource(h, slot, self._texture(t) if t is not None else None))
+            t = vs_srv[slot]
+            if t is not sent_vs[slot]:
+                L.check(lib.mlv_vs_set_shader_resource(h, slot, self._texture(t) if t is not None else None))
+                sent_vs[slot] = t
+            t = ps_srv[slot]
+            if t is not sent_ps[slot]:
+                L.check(lib.mlv_ps_set_shader_resource(h, slot, self._texture(t) if t is not None else None))
+                sent_ps[slot] = t
         v = gp.rs.viewport
-        vp = L.Viewport(v.top_left_x, v.top_left_y, v.width, v.height, v.min_depth, v.max_depth)
-        L.check(lib.mlv_rs_set_viewport(h, C.byref(vp)))
+        v = (v.top_left_x, v.top_left_y, v.width, v.height, v.min_depth, v.max_depth)
+        if sent.get("viewport") != v:
+            vp = L.Viewport(*v)
+            L.check(lib.mlv_rs_set_viewport(h, C.byref(vp)))
+            sent["viewport"] = v
 
     def draw_indexed(self, index_count: int, start_index_location: int = 0, base_vertex_location: int = 0):  # main.c:1219 (+ its TODO arguments)
         self._bind(True)

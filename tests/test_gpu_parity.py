@@ -242,6 +242,13 @@ def test_sort_first_partition_composes_to_single_gpu_image():
         _check_partition(cases.SMALL[case](), combos)
 
 
+def test_sort_first_partition_with_several_chunks_per_persistent_cta():
+    """Same check on a mesh of 2 x 400 000 triangles (1 563 chunks of 256 per draw): with sort-first culling k_geom runs as
+    a persistent grid of at most 592 CTAs, so every CTA walks several chunks and carries its Stats across them."""
+    from malevich_b200 import scenes
+    _check_partition(scenes.synthetic(1280, 720, layers=2, nx=500, ny=400), ((2, 45), (4, 23), (8, 2)))
+
+
 def _check_partition(sc, combos):
     import torch
     from malevich_b200 import scenes
