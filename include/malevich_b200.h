@@ -117,6 +117,9 @@ MLV_API void *mlv_get_stream(mlv_device *dev); /* the cudaStream_t all work is l
 
 /* ---- resources (load_mesh main.c:526-536, load_texture main.c:538-559 hand the pipeline host pointers) */
 MLV_API int mlv_create_buffer(mlv_device *dev, const void *data, size_t bytes, int kind, mlv_buffer **out);
+/* Uploads are asynchronous and run on the device's copy stream: the copy starts after every draw issued so far and
+ * each later draw waits only for the buffers it binds, so uploading mesh k+1 overlaps drawing mesh k. `data` must stay
+ * valid until mlv_finish / mlv_present_readback returns when it points to page-locked memory. */
 MLV_API int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t bytes);
 MLV_API void mlv_release_buffer(mlv_device *dev, mlv_buffer *buf);
 MLV_API int mlv_create_texture2d(mlv_device *dev, const void *texels, uint32_t width, uint32_t height, int format, mlv_texture **out);

@@ -43,6 +43,8 @@ struct mlv_buffer {
 	size_t bytes;
 	int kind;
 	uint64_t version;          // bumped by every update
+	cudaEvent_t ready;         // recorded on the copy stream after the last upload
+	bool ready_pending;        // no draw has waited on `ready` yet
 	// sort-first chunk bounds cached with the buffer that defines the triangle list (index buffer, or vertex buffer for mlv_draw)
 	float4 *chunk_bounds;
 	uint32_t chunk_capacity, chunk_count;
@@ -83,9 +85,13 @@ struct mlv_device {
 	uint32_t vcache_capacity;
 	int vcache_sel;
 	cudaStream_t side_stream;
+	// Buffer uploads run on a copy stream: a draw waits only for the buffers it binds, so the upload of mesh k+1
+	// overlaps the draw of mesh k (a host that streams its geometry every frame is otherwise PCIe-then-render serial).
+	cudaStream_t copy_stream;
+	cudaEvent_t ev_copy_after_main;
 	cudaEvent_t ev_vertex_done, ev_main_sync, ev_cache_free[2];
 	bool cache_free_recorded[2];
-	bool side_needs_sync; // a buffer was written on the main stream since the side stream last synchronised with it
+	bool side_needs_sync; // the side stream has not yet been ordered after the device's creation-time work on the main stream
 	uint8_t *chunk_live;
 	uint32_t chunk_live_capacity;
 	uint32_t bin_begin, bin_end; // bins this rank can touch: everything, or one contiguous band
@@ -245,6 +251,8 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 
 	CREATE_TRY(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
 	CREATE_TRY(cudaStreamCreateWithFlags(&dev->side_stream, cudaStreamNonBlocking));
+	CREATE_TRY(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
+	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_copy_after_main, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_vertex_done, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_main_sync, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_cache_free[0], cudaEventDisableTiming));
@@ -292,13 +300,15 @@ void mlv_destroy_device(mlv_device *dev) {
 	cudaSetDevice(dev->cuda_dev);
 	if(dev->stream) cudaStreamSynchronize(dev->stream);
 	if(dev->side_stream) cudaStreamSynchronize(dev->side_stream);
+	if(dev->copy_stream) cudaStreamSynchronize(dev->copy_stream);
 	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue, dev->vcache[0], dev->vcache[1], dev->chunk_live,
 		             dev->scan_state, dev->ctr, dev->stat_stripes, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
 	if(dev->stream) cudaStreamDestroy(dev->stream);
 	if(dev->side_stream) cudaStreamDestroy(dev->side_stream);
-	for(cudaEvent_t e : { dev->ev_vertex_done, dev->ev_main_sync, dev->ev_cache_free[0], dev->ev_cache_free[1] })
+	if(dev->copy_stream) cudaStreamDestroy(dev->copy_stream);
+	for(cudaEvent_t e : { dev->ev_copy_after_main, dev->ev_vertex_done, dev->ev_main_sync, dev->ev_cache_free[0], dev->ev_cache_free[1] })
 		if(e) cudaEventDestroy(e);
 	if(dev->prof_events) {
 		for(cudaEvent_t e : *dev->prof_events) cudaEventDestroy(e);
@@ -311,6 +321,7 @@ void mlv_destroy_device(mlv_device *dev) {
 int mlv_finish(mlv_device *dev) {
 	if(int rc = use_device(dev)) return rc;
 	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	CUDA_TRY(cudaStreamSynchronize(dev->copy_stream)); // uploads no draw has consumed yet
 	return MLV_OK;
 }
 
@@ -327,6 +338,7 @@ int mlv_create_buffer(mlv_device *dev, const void *data, size_t bytes, int kind,
 	b->bytes = bytes;
 	b->kind = kind;
 	cudaError_t e = cudaMalloc(&b->d, (bytes + 15) & ~(size_t)15);
+	if(e == cudaSuccess && (e = cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming)) != cudaSuccess) cudaFree(b->d);
 	if(e != cudaSuccess) {
 		delete b;
 		return fail(MLV_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
@@ -339,8 +351,13 @@ int mlv_create_buffer(mlv_device *dev, const void *data, size_t bytes, int kind,
 int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t bytes) {
 	if(int rc = use_device(dev)) return rc;
 	if(!buf || !data || bytes > buf->bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer update");
-	CUDA_TRY(cudaMemcpyAsync(buf->d, data, bytes, cudaMemcpyHostToDevice, dev->stream));
-	dev->side_needs_sync = true;
+	// after every draw issued so far (any of them may read this buffer; each k_vertex on the side stream has already
+	// been joined into the main stream by its k_geom), before the first draw that binds it afterwards (bind_ready)
+	CUDA_TRY(cudaEventRecord(dev->ev_copy_after_main, dev->stream));
+	CUDA_TRY(cudaStreamWaitEvent(dev->copy_stream, dev->ev_copy_after_main, 0));
+	CUDA_TRY(cudaMemcpyAsync(buf->d, data, bytes, cudaMemcpyHostToDevice, dev->copy_stream));
+	CUDA_TRY(cudaEventRecord(buf->ready, dev->copy_stream));
+	buf->ready_pending = true;
 	buf->version++;
 	return MLV_OK;
 }
@@ -349,8 +366,10 @@ void mlv_release_buffer(mlv_device *dev, mlv_buffer *buf) {
 	if(!dev || !buf) return;
 	cudaSetDevice(dev->cuda_dev);
 	cudaStreamSynchronize(dev->stream);
+	cudaStreamSynchronize(dev->copy_stream);
 	if(dev->vb == buf) dev->vb = nullptr;
 	if(dev->ib == buf) dev->ib = nullptr;
+	if(buf->ready) cudaEventDestroy(buf->ready);
 	if(buf->chunk_bounds) cudaFree(buf->chunk_bounds);
 	cudaFree(buf->d);
 	delete buf;
@@ -520,7 +539,7 @@ static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks,
 		// Per-stage profiling brackets every kernel with events on the main stream, so it keeps k_vertex there.
 		cudaStream_t vs_stream = dev->prof_on ? dev->stream : dev->side_stream;
 		if(!dev->prof_on) {
-			if(dev->side_needs_sync) { // uploads are ordered on the main stream: everything issued so far comes first
+			if(dev->side_needs_sync) { // first use: everything issued on the main stream so far comes first
 				cudaEventRecord(dev->ev_main_sync, dev->stream);
 				cudaStreamWaitEvent(dev->side_stream, dev->ev_main_sync, 0);
 				dev->side_needs_sync = false;
@@ -578,6 +597,12 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	if(int rc = flush_clears(dev)) return rc;
 	dev->last_index_count = count;
 	if(count == 0) return MLV_OK;
+	for(mlv_buffer *b : { dev->vb, indexed ? dev->ib : (mlv_buffer *)nullptr }) { // uploads still in flight on the copy stream
+		if(!b || !b->ready_pending) continue;
+		CUDA_TRY(cudaStreamWaitEvent(dev->stream, b->ready, 0));
+		CUDA_TRY(cudaStreamWaitEvent(dev->side_stream, b->ready, 0));
+		b->ready_pending = false;
+	}
 
 	const uint32_t T = count / 3u;
 	if(T >= (1u << 28)) return fail(MLV_ERR_INVALID_ARGUMENT, "draw too large: triangle keys are (input_triangle << 3 | fan_index) in 32 bits");
