@@ -184,9 +184,34 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         gather = torch.as_tensor(_Raw(ptr, chunk * world), device=torch.device("cuda", local_rank))
         my_chunk = gather[rank * chunk:(rank + 1) * chunk]
 
+    # Exchange step: by default the fused peer-memory composite (each rank resolves its tiles straight into every rank's
+    # image over NVLink, include/malevich_b200.h); --composite nccl keeps pack -> ncclAllGather -> unpack. NCCL is always
+    # the transport for the one-off handle exchange, the barriers and the max/sum reductions of the measurements.
+    composite = "none"
+    if multi:
+        composite = args.composite
+        if composite == "p2p":
+            try:
+                mine = torch.frombuffer(bytearray(dev.composite_peer_export()), dtype=torch.uint8).cuda()
+                every = torch.empty(world * mine.numel(), dtype=torch.uint8, device="cuda")
+                dist.all_gather_into_tensor(every, mine)
+                blob = every.cpu().numpy().tobytes()
+                n = mine.numel()
+                dev.composite_peer_attach([blob[r * n:(r + 1) * n] for r in range(world)], same_process=False)
+                ok = torch.ones(1, device="cuda")
+            except Exception as e:  # noqa: BLE001 -- e.g. no peer access between the GPUs of this box
+                print(f"[bench] rank {rank}: peer-memory composite unavailable ({e}); using ncclAllGather", file=sys.stderr)
+                ok = torch.zeros(1, device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                composite = "nccl"
+
     def frame():
         scenes.render(dev, scene)
-        if multi:
+        if composite == "p2p":
+            dev.composite_broadcast()
+            dev.composite_wait()
+        elif composite == "nccl":
             dev.composite_pack()
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(gather, my_chunk)
@@ -332,7 +357,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "mtri_per_s": scene.input_triangles * fps / 1e6, "gpix_per_s": scene.width * scene.height * fps / 1e9,
             "config": {"workload": workload_name(args.config, scene), "input_triangles": scene.input_triangles, "draws": len(scene.objects),
                        "assembled_triangles": stats["assembled_triangle_count"], "tri_tile_pairs": stats["total_triangle_count_in_bins"],
-                       "tile_draws": stats["active_bin_count"], "parallelism": f"sort-first x{world}, stripe {stripe} tile rows" if multi else "single GPU",
+                       "tile_draws": stats["active_bin_count"], "parallelism": f"sort-first x{world}, stripe {stripe} tile rows, composite {composite}" if multi else "single GPU",
                        "l2": "no flush: per-frame working set (inputs + per-draw setup records) >> 126 MB L2" if args.config == 5 else "no flush"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes_per_launch,
@@ -360,6 +385,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--stripe", type=int, default=0, help="stripe height in tile rows for the sort-first split (0 = one contiguous band per rank)")
+    ap.add_argument("--composite", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange step: fused peer-memory broadcast (default) or pack + ncclAllGather + unpack")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -124,6 +124,12 @@ MLV_API int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data
 MLV_API void mlv_release_buffer(mlv_device *dev, mlv_buffer *buf);
 MLV_API int mlv_create_texture2d(mlv_device *dev, const void *texels, uint32_t width, uint32_t height, int format, mlv_texture **out);
 MLV_API void mlv_release_texture(mlv_device *dev, mlv_texture *tex);
+/* load_texture's `is_in_srgb` branch (main.c:546-558): every channel of every texel of an R8G8B8A8 texture -- alpha
+ * included -- goes through decode_u32_as_color (math.h:326-334), srgb_to_linear (math.h:386-395, double arithmetic)
+ * and encode_color_as_u32 (math.h:322-324, truncation), in place, on the device. */
+MLV_API int mlv_texture_srgb_to_linear(mlv_device *dev, mlv_texture *tex);
+/* copies the texels back (R8G8B8A8: 4 bytes, R32G32B32A32_FLOAT: 16 bytes per texel); synchronises */
+MLV_API int mlv_read_texture(mlv_device *dev, const mlv_texture *tex, void *out_texels);
 
 /* ---- pipeline state: graphics_pipeline.{ia,vs,rs,ps} main.c:71-115, written by render() main.c:1276-1294 */
 MLV_API int mlv_ia_set_vertex_buffer(mlv_device *dev, mlv_buffer *vb);       /* ia.p_vertex_buffer main.c:1292 */
@@ -156,7 +162,7 @@ MLV_API int mlv_reset_stats(mlv_device *dev);                /* memset(&stats,0)
 
 /* Device-resident resolve: tiled colour/depth -> row-major device buffers with 128-bit stores. */
 MLV_API int mlv_resolve(mlv_device *dev);
-MLV_API void *mlv_resolved_color_device_ptr(mlv_device *dev); /* W*H u32, valid after mlv_resolve */
+MLV_API void *mlv_resolved_color_device_ptr(mlv_device *dev); /* W*H u32, valid after mlv_resolve / mlv_composite_unpack / mlv_composite_wait (call it after those: the buffer alternates) */
 MLV_API void *mlv_resolved_depth_device_ptr(mlv_device *dev); /* W*H f32, valid after mlv_resolve */
 
 /* Sort-first compositing. The gather buffer holds num_ranks equal chunks; rank r's
@@ -167,6 +173,31 @@ MLV_API void *mlv_resolved_depth_device_ptr(mlv_device *dev); /* W*H f32, valid 
 MLV_API int mlv_composite_layout(mlv_device *dev, void **out_gather_device_ptr, size_t *out_chunk_bytes);
 MLV_API int mlv_composite_pack(mlv_device *dev);
 MLV_API int mlv_composite_unpack(mlv_device *dev);
+
+/* Peer-memory compositing: the fused form of the exchange above for GPUs that can address each other (NVLink /
+ * NVSwitch; cudaIpc between processes). mlv_composite_broadcast resolves this rank's tiles straight into the row-major
+ * image of EVERY rank and publishes a per-frame arrival word on each; mlv_composite_wait blocks the device stream (not
+ * the host) until the stripes of all ranks have arrived, after which mlv_resolved_color_device_ptr points at the complete
+ * image. No staging chunk, no collective call, no un-swizzle pass. Setup, once per device:
+ *   1. every rank: mlv_composite_peer_export(dev, &info)        (allocates two images + the arrival words)
+ *   2. the caller exchanges the mlv_peer_info structs (any transport: ncclAllGather, MPI, a pipe)
+ *   3. every rank: mlv_composite_peer_attach(dev, infos, same_process)
+ * Every mlv_composite_broadcast must be followed by mlv_composite_wait before the next one (a rank may run at most one
+ * frame ahead of the slowest; the images are double-buffered by frame parity). A peer that never arrives makes the
+ * wait give up after 10 s and the next read-back / mlv_get_stats return MLV_ERR_STATE. */
+#define MLV_MAX_PEERS 16
+typedef struct mlv_peer_info {
+	unsigned char ipc_color[2][64]; /* cudaIpcMemHandle_t of the two images */
+	unsigned char ipc_flags[64];    /* cudaIpcMemHandle_t of the arrival words */
+	void *color[2];                 /* the same allocations as plain device pointers (same_process != 0) */
+	void *flags;
+	int cuda_device;
+	int reserved;
+} mlv_peer_info;
+MLV_API int mlv_composite_peer_export(mlv_device *dev, mlv_peer_info *out);
+MLV_API int mlv_composite_peer_attach(mlv_device *dev, const mlv_peer_info *infos /* [num_ranks], in rank order */, int same_process);
+MLV_API int mlv_composite_broadcast(mlv_device *dev);
+MLV_API int mlv_composite_wait(mlv_device *dev);
 
 /* ---- debug read-back of the last draw (needs MLV_DEVICE_DEBUG_CAPTURE). Each synchronises.
  * Pass NULL data pointers to query the counts only. */

@@ -1382,6 +1382,26 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant
 // resolve / composite
 // =================================================================================================
 
+// load_texture's sRGB branch (main.c:546-558) as a byte transform over the texels. The curve has 256 possible inputs per
+// channel; the table is evaluated on the host with the reference's own double arithmetic (libm pow) and travels as a
+// kernel parameter, so the kernel is pure HBM work: 16 texels per thread-iteration through 128-bit accesses.
+struct SrgbTable {
+	uint8_t lin[256];
+};
+__global__ void __launch_bounds__(256) k_texture_srgb_to_linear(uint4 *__restrict__ texels, size_t count_u4, uint32_t *__restrict__ tail, uint32_t tail_count, const __grid_constant__ SrgbTable T) {
+	pdl_prologue();
+	__shared__ uint8_t s_lin[256];
+	s_lin[threadIdx.x] = T.lin[threadIdx.x];
+	__syncthreads();
+	auto conv = [&](uint32_t t) { return (uint32_t)s_lin[t & 0xffu] | ((uint32_t)s_lin[(t >> 8) & 0xffu] << 8) | ((uint32_t)s_lin[(t >> 16) & 0xffu] << 16) | ((uint32_t)s_lin[t >> 24] << 24); };
+	for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count_u4; i += (size_t)gridDim.x * blockDim.x) {
+		uint4 v = texels[i];
+		v.x = conv(v.x), v.y = conv(v.y), v.z = conv(v.z), v.w = conv(v.w);
+		texels[i] = v;
+	}
+	if(blockIdx.x == 0 && threadIdx.x < tail_count) tail[threadIdx.x] = conv(tail[threadIdx.x]);
+}
+
 // Tiled -> row-major. One thread per 4 horizontally adjacent pixels of rows y and y+4 of a tile: four 128-bit
 // loads (64 contiguous bytes, all of them used), two 128-bit colour stores (+ two 128-bit depth stores).
 struct Quad8 {
@@ -1454,6 +1474,62 @@ __global__ void __launch_bounds__(256) k_composite_unpack(const uint4 *__restric
 	const uint32_t ty = y >> 3;
 	const uint32_t owner = (ty / (uint32_t)stripe_h) % (uint32_t)num_ranks;
 	colors[q] = __ldg(gather + (size_t)owner * chunk_u4 + (size_t)chunk_row(ty, y & 7u, stripe_h, num_ranks) * qw + xq);
+}
+
+// Fused resolve + all-gather over peer memory: this rank's tiles go from the tiled framebuffer straight into the
+// row-major image of EVERY rank (its own included) with 128-bit stores -- local HBM for itself, NVLink for the
+// peers -- so there is no staging chunk, no collective call and no un-swizzle pass afterwards. When the last CTA
+// has fenced its stores, one thread publishes the frame's sequence number in every rank's arrival word for this rank.
+__global__ void __launch_bounds__(256) k_composite_broadcast(const uint4 *__restrict__ fb, const __grid_constant__ PeerTargets peers, int width, int height, Partition part, uint32_t seq,
+                                                             Counters *__restrict__ ctr) {
+	pdl_prologue();
+	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t wt = (uint32_t)width >> 3, ht = (uint32_t)height >> 3;
+	const uint32_t quads_per_row = wt * 2u;
+	const uint32_t rowgroup = w / quads_per_row;
+	if(rowgroup < ht * 4u) {
+		const uint32_t xq = w % quads_per_row, ty = rowgroup >> 2, row = rowgroup & 3u;
+		if(part.owns_row((int)ty)) {
+			const Quad8 q = load_quad8(fb, ty * wt + (xq >> 1), row, xq & 1u);
+			const size_t top = (size_t)(ty * 8u + row) * quads_per_row + xq;
+			for(int p = 0; p < part.num_ranks; ++p) {
+				uint4 *dst = peers.color[p];
+				dst[top] = q.c_top;
+				dst[top + 4u * quads_per_row] = q.c_bot;
+			}
+		}
+	}
+	__threadfence_system(); // my stores are visible to every GPU before my CTA is counted as done
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		const uint32_t done = atomicAdd(&ctr->bcast_done, 1u);
+		if(done == gridDim.x - 1u) {
+			ctr->bcast_done = 0u;
+			__threadfence_system();
+			for(int p = 0; p < part.num_ranks; ++p) *reinterpret_cast<volatile uint32_t *>(peers.flags[p] + part.rank) = seq;
+		}
+	}
+}
+
+// Waits until every rank's stripes of frame `seq` have arrived in this rank's image. Bounded: a peer that never
+// arrives sets MLV_FLAG_COMPOSITE_TIMEOUT instead of hanging the GPU.
+__global__ void __launch_bounds__(32) k_composite_wait(const uint32_t *flags, int num_ranks, uint32_t seq, Counters *__restrict__ ctr, unsigned long long timeout_ns) {
+	pdl_prologue();
+	if((int)threadIdx.x < num_ranks) {
+		const volatile uint32_t *f = flags + threadIdx.x;
+		unsigned long long t0;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+		while((int)(*f - seq) < 0) {
+			__nanosleep(100);
+			unsigned long long t1;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+			if(t1 - t0 > timeout_ns) {
+				atomicOr(&ctr->error_flags, MLV_FLAG_COMPOSITE_TIMEOUT);
+				break;
+			}
+		}
+	}
+	__threadfence_system();
 }
 
 } // namespace mlv

@@ -110,6 +110,16 @@ struct mlv_device {
 	float4 *resolved_depth;
 	uint4 *gather;
 	size_t chunk_bytes;
+	// peer-memory compositing (mlv_composite_peer_*)
+	uint4 *p2p_color[2];       // my two images (peers write their stripes into them)
+	uint32_t *p2p_flags;       // my arrival words, one per source rank
+	uint4 *peer_color[2][MLV_MAX_PEERS]; // every rank's images as mapped here ([.][rank] = my own)
+	uint32_t *peer_flags[MLV_MAX_PEERS];
+	void *ipc_opened[3 * MLV_MAX_PEERS];
+	int ipc_opened_count;
+	bool peers_attached, bcast_pending;
+	uint32_t p2p_seq;          // frame sequence number of the last broadcast
+	uint4 *present_color;      // what mlv_resolved_color_device_ptr hands out
 
 	// bound pipeline state (graphics_pipeline)
 	mlv_buffer *vb, *ib;
@@ -275,6 +285,7 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	CREATE_TRY(cudaMemsetAsync(dev->scan_state, 0, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long), dev->stream));
 	CREATE_TRY(cudaMalloc(&dev->rsqrt_lut, sizeof(k_rsqrt_lut_host)));
 	CREATE_TRY(cudaMalloc(&dev->resolved_color, (size_t)dev->W * dev->H * 4));
+	dev->present_color = dev->resolved_color;
 	CREATE_TRY(cudaMalloc(&dev->resolved_depth, (size_t)dev->W * dev->H * 4));
 	CREATE_TRY(cudaMemsetAsync(dev->fb, 0, nb * 32 * sizeof(uint4), dev->stream));
 	CREATE_TRY(cudaMemsetAsync(dev->tile_min, 0, nb * sizeof(float), dev->stream));
@@ -301,8 +312,9 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(dev->stream) cudaStreamSynchronize(dev->stream);
 	if(dev->side_stream) cudaStreamSynchronize(dev->side_stream);
 	if(dev->copy_stream) cudaStreamSynchronize(dev->copy_stream);
+	for(int i = 0; i < dev->ipc_opened_count; ++i) cudaIpcCloseMemHandle(dev->ipc_opened[i]);
 	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue, dev->vcache[0], dev->vcache[1], dev->chunk_live,
-		             dev->scan_state, dev->ctr, dev->stat_stripes, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather };
+		             dev->scan_state, dev->ctr, dev->stat_stripes, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather, dev->p2p_color[0], dev->p2p_color[1], dev->p2p_flags };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
 	if(dev->stream) cudaStreamDestroy(dev->stream);
@@ -394,6 +406,37 @@ int mlv_create_texture2d(mlv_device *dev, const void *texels, uint32_t width, ui
 		return fail(MLV_ERR_CUDA, "texture upload: %s", cudaGetErrorString(e));
 	}
 	*out = t;
+	return MLV_OK;
+}
+
+int mlv_texture_srgb_to_linear(mlv_device *dev, mlv_texture *tex) {
+	if(int rc = use_device(dev)) return rc;
+	if(!tex || tex->format != MLV_FORMAT_R8G8B8A8_UNORM) return fail(MLV_ERR_INVALID_ARGUMENT, "sRGB conversion wants an R8G8B8A8 texture (main.c:546-558)");
+	SrgbTable table;
+	for(int b = 0; b < 256; ++b) {
+		const float normalizer = (float)(1.0 / 255.0);            // math.h:328
+		const float v = (float)(uint32_t)b * normalizer;          // math.h:329
+		float lin;                                                 // srgb_to_linear math.h:386-395: double arithmetic, f32 result
+		if((double)v <= 0.04045) lin = (float)((double)v / 12.92);
+		else lin = (float)pow(((double)v + 0.055) / 1.055, 2.4);
+		table.lin[b] = (uint8_t)(uint32_t)(lin * 255.f);          // encode_color_as_u32 math.h:323 (truncation)
+	}
+	const size_t texel_count = (size_t)tex->width * tex->height;
+	const size_t count_u4 = texel_count / 4;
+	const uint32_t tail = (uint32_t)(texel_count % 4);
+	size_t blocks = (count_u4 + 255) / 256;
+	if(blocks > 148u * 8u) blocks = 148u * 8u;
+	if(blocks == 0) blocks = 1;
+	launch_pdl(k_texture_srgb_to_linear, (uint32_t)blocks, 256, dev->stream, (uint4 *)tex->d, count_u4, (uint32_t *)tex->d + count_u4 * 4, tail, table);
+	return check_launch(dev, "k_texture_srgb_to_linear");
+}
+
+int mlv_read_texture(mlv_device *dev, const mlv_texture *tex, void *out_texels) {
+	if(int rc = use_device(dev)) return rc;
+	if(!tex || !out_texels) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	const size_t bytes = (size_t)tex->width * tex->height * (tex->format == MLV_FORMAT_R8G8B8A8_UNORM ? 4 : 16);
+	CUDA_TRY(cudaMemcpyAsync(out_texels, tex->d, bytes, cudaMemcpyDeviceToHost, dev->stream));
+	CUDA_TRY(cudaStreamSynchronize(dev->stream));
 	return MLV_OK;
 }
 
@@ -855,6 +898,7 @@ int mlv_draw_indexed_ex(mlv_device *dev, uint32_t index_count, uint32_t start_in
 
 static int check_flags(mlv_device *dev, const Counters &c) {
 	if(c.error_flags & MLV_FLAG_TRI_OVERFLOW) return fail(MLV_ERR_CAPACITY, "a draw assembled more than T + max(2T,512) triangles (the reference's own buffer bound, main.c:739-740)");
+	if(c.error_flags & MLV_FLAG_COMPOSITE_TIMEOUT) return fail(MLV_ERR_STATE, "peer-memory compositing: a rank's stripes did not arrive within 10 s");
 	if(c.error_flags & MLV_FLAG_PAIR_OVERFLOW)
 		return fail(MLV_ERR_CAPACITY, "a draw produced more (triangle,tile) pairs than max_pairs_per_draw = %llu; that draw was skipped", (unsigned long long)dev->pair_capacity);
 	return MLV_OK;
@@ -866,10 +910,11 @@ int mlv_resolve(mlv_device *dev) {
 	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H; // 8 pixels (4 wide, rows y and y+4) per thread
 	prof_pre(dev, MLV_STAGE_RESOLVE);
 	launch_pdl(k_resolve, (items + 255) / 256, 256, dev->stream, dev->fb, dev->resolved_color, dev->resolved_depth, dev->W, dev->H);
+	dev->present_color = dev->resolved_color;
 	return check_launch(dev, "k_resolve");
 }
 
-void *mlv_resolved_color_device_ptr(mlv_device *dev) { return dev ? dev->resolved_color : nullptr; }
+void *mlv_resolved_color_device_ptr(mlv_device *dev) { return dev ? dev->present_color : nullptr; }
 void *mlv_resolved_depth_device_ptr(mlv_device *dev) { return dev ? dev->resolved_depth : nullptr; }
 
 int mlv_present_readback(mlv_device *dev, uint32_t *colors, float *depths) {
@@ -878,6 +923,7 @@ int mlv_present_readback(mlv_device *dev, uint32_t *colors, float *depths) {
 	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
 	prof_pre(dev, MLV_STAGE_RESOLVE);
 	launch_pdl(k_resolve, (items + 255) / 256, 256, dev->stream, dev->fb, dev->resolved_color, depths ? dev->resolved_depth : nullptr, dev->W, dev->H);
+	dev->present_color = dev->resolved_color;
 	if(int rc = check_launch(dev, "k_resolve")) return rc;
 	const size_t bytes = (size_t)dev->W * dev->H * 4;
 	if(colors) CUDA_TRY(cudaMemcpyAsync(colors, dev->resolved_color, bytes, cudaMemcpyDeviceToHost, dev->stream));
@@ -930,7 +976,110 @@ int mlv_composite_unpack(mlv_device *dev) {
 	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
 	prof_pre(dev, MLV_STAGE_COMPOSITE);
 	launch_pdl(k_composite_unpack, (quads + 255) / 256, 256, dev->stream, dev->gather, dev->resolved_color, dev->W, dev->H, dev->part.num_ranks, dev->part.stripe_h, dev->chunk_bytes / 16);
+	dev->present_color = dev->resolved_color;
 	return check_launch(dev, "k_composite_unpack");
+}
+
+// ---- peer-memory compositing ---------------------------------------------------------------------
+
+int mlv_composite_peer_export(mlv_device *dev, mlv_peer_info *out) {
+	if(int rc = use_device(dev)) return rc;
+	if(!out) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	if(dev->part.num_ranks <= 1) return fail(MLV_ERR_STATE, "device was created with a single rank");
+	if(dev->part.num_ranks > MLV_MAX_PEERS) return fail(MLV_ERR_INVALID_ARGUMENT, "peer-memory compositing supports up to %d ranks", MLV_MAX_PEERS);
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "mlv_peer_info carries 64-byte IPC handles");
+	const size_t image_bytes = (size_t)dev->W * dev->H * 4;
+	if(!dev->p2p_flags) {
+		CUDA_TRY(cudaMalloc(&dev->p2p_color[0], image_bytes));
+		CUDA_TRY(cudaMalloc(&dev->p2p_color[1], image_bytes));
+		CUDA_TRY(cudaMalloc(&dev->p2p_flags, MLV_MAX_PEERS * sizeof(uint32_t)));
+		CUDA_TRY(cudaMemsetAsync(dev->p2p_color[0], 0, image_bytes, dev->stream));
+		CUDA_TRY(cudaMemsetAsync(dev->p2p_color[1], 0, image_bytes, dev->stream));
+		CUDA_TRY(cudaMemsetAsync(dev->p2p_flags, 0, MLV_MAX_PEERS * sizeof(uint32_t), dev->stream));
+		CUDA_TRY(cudaStreamSynchronize(dev->stream)); // peers may write as soon as they have the handles
+	}
+	memset(out, 0, sizeof(*out));
+	cudaIpcMemHandle_t h;
+	for(int k = 0; k < 2; ++k) {
+		CUDA_TRY(cudaIpcGetMemHandle(&h, dev->p2p_color[k]));
+		memcpy(out->ipc_color[k], &h, 64);
+		out->color[k] = dev->p2p_color[k];
+	}
+	CUDA_TRY(cudaIpcGetMemHandle(&h, dev->p2p_flags));
+	memcpy(out->ipc_flags, &h, 64);
+	out->flags = dev->p2p_flags;
+	out->cuda_device = dev->cuda_dev;
+	return MLV_OK;
+}
+
+int mlv_composite_peer_attach(mlv_device *dev, const mlv_peer_info *infos, int same_process) {
+	if(int rc = use_device(dev)) return rc;
+	if(!infos) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	if(!dev->p2p_flags) return fail(MLV_ERR_STATE, "call mlv_composite_peer_export first");
+	if(dev->peers_attached) return fail(MLV_ERR_STATE, "peers already attached");
+	const int n = dev->part.num_ranks, me = dev->part.rank;
+	for(int p = 0; p < n; ++p) {
+		if(p == me) {
+			dev->peer_color[0][p] = dev->p2p_color[0];
+			dev->peer_color[1][p] = dev->p2p_color[1];
+			dev->peer_flags[p] = dev->p2p_flags;
+			continue;
+		}
+		if(same_process) {
+			if(infos[p].cuda_device != dev->cuda_dev) {
+				cudaError_t e = cudaDeviceEnablePeerAccess(infos[p].cuda_device, 0);
+				if(e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+				else if(e != cudaSuccess) return fail(MLV_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", infos[p].cuda_device, cudaGetErrorString(e));
+			}
+			dev->peer_color[0][p] = (uint4 *)infos[p].color[0];
+			dev->peer_color[1][p] = (uint4 *)infos[p].color[1];
+			dev->peer_flags[p] = (uint32_t *)infos[p].flags;
+			continue;
+		}
+		void *mapped[3];
+		const unsigned char *handles[3] = { infos[p].ipc_color[0], infos[p].ipc_color[1], infos[p].ipc_flags };
+		for(int k = 0; k < 3; ++k) {
+			cudaIpcMemHandle_t h;
+			memcpy(&h, handles[k], 64);
+			cudaError_t e = cudaIpcOpenMemHandle(&mapped[k], h, cudaIpcMemLazyEnablePeerAccess);
+			if(e != cudaSuccess) return fail(MLV_ERR_CUDA, "cudaIpcOpenMemHandle (rank %d): %s", p, cudaGetErrorString(e));
+			dev->ipc_opened[dev->ipc_opened_count++] = mapped[k];
+		}
+		dev->peer_color[0][p] = (uint4 *)mapped[0];
+		dev->peer_color[1][p] = (uint4 *)mapped[1];
+		dev->peer_flags[p] = (uint32_t *)mapped[2];
+	}
+	dev->peers_attached = true;
+	return MLV_OK;
+}
+
+int mlv_composite_broadcast(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	if(!dev->peers_attached) return fail(MLV_ERR_STATE, "call mlv_composite_peer_attach first");
+	if(dev->bcast_pending) return fail(MLV_ERR_STATE, "mlv_composite_wait must follow every mlv_composite_broadcast");
+	if(int rc = flush_clears(dev)) return rc;
+	const uint32_t seq = ++dev->p2p_seq;
+	PeerTargets t;
+	memset(&t, 0, sizeof(t));
+	for(int p = 0; p < dev->part.num_ranks; ++p) {
+		t.color[p] = dev->peer_color[seq & 1u][p];
+		t.flags[p] = dev->peer_flags[p];
+	}
+	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
+	prof_pre(dev, MLV_STAGE_COMPOSITE);
+	launch_pdl(k_composite_broadcast, (items + 255) / 256, 256, dev->stream, dev->fb, t, dev->W, dev->H, dev->part, seq, dev->ctr);
+	dev->bcast_pending = true;
+	return check_launch(dev, "k_composite_broadcast");
+}
+
+int mlv_composite_wait(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	if(!dev->bcast_pending) return fail(MLV_ERR_STATE, "no broadcast to wait for");
+	prof_pre(dev, MLV_STAGE_COMPOSITE);
+	launch_pdl(k_composite_wait, 1, 32, dev->stream, (const uint32_t *)dev->p2p_flags, dev->part.num_ranks, dev->p2p_seq, dev->ctr, 10000000000ull);
+	dev->bcast_pending = false;
+	dev->present_color = dev->p2p_color[dev->p2p_seq & 1u];
+	return check_launch(dev, "k_composite_wait");
 }
 
 // ---- debug read-back -------------------------------------------------------------------------------

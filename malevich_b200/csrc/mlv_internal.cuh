@@ -37,7 +37,7 @@ namespace mlv {
 #define MLV_TOUCHED 0x80000000u          /* bin_count flag: bin is non-empty in the reference's sense but (so far) holds only Hi-Z-rejected pairs */
 #define MLV_TILE_MIN_CLEARED 0x80000000u /* tile_min bit pattern (-0.0f) the depth clear writes: equals 0.0 in every comparison, marks "never refreshed" */
 
-enum { MLV_FLAG_TRI_OVERFLOW = 1u, MLV_FLAG_PAIR_OVERFLOW = 2u };
+enum { MLV_FLAG_TRI_OVERFLOW = 1u, MLV_FLAG_PAIR_OVERFLOW = 2u, MLV_FLAG_COMPOSITE_TIMEOUT = 4u };
 
 struct Counters {
 	uint32_t ovf_count;   // overflow slots taken by clipped triangles in the current draw (reset by k_tile)
@@ -52,7 +52,7 @@ struct Counters {
 	uint32_t draw_pairs_all;   // (triangle,tile) pairs of the current draw including Hi-Z-rejected ones (Stats)
 	uint32_t draw_active_bins; // non-empty bins of the current draw in the reference's sense (Stats)
 	uint32_t huge_count;  // triangles with more than MLV_HUGE_TILES tiles in the current draw (reset by k_tile)
-	uint32_t reserved0;
+	uint32_t bcast_done;  // CTAs of k_composite_broadcast that have finished their stores (reset by the last one)
 	uint32_t pad[3];
 	mlv_stats stats;      // accumulated like reference main.c:1228-1246
 };
@@ -60,6 +60,16 @@ struct Counters {
 struct Partition { // sort-first ownership
 	int num_ranks, rank, stripe_h;
 	__host__ __device__ __forceinline__ bool owns_row(int ty) const { return num_ranks <= 1 || ((ty / stripe_h) % num_ranks) == rank; }
+};
+
+// Peer-memory compositing (fused form): every rank keeps two row-major images and one arrival word
+// per source rank; peers write into them over NVLink (cudaIpc mappings, or plain pointers inside one process).
+#ifndef MLV_MAX_PEERS
+#define MLV_MAX_PEERS 16
+#endif
+struct PeerTargets {
+	uint4 *color[MLV_MAX_PEERS];    // the image of the current frame parity on rank p
+	uint32_t *flags[MLV_MAX_PEERS]; // rank p's arrival words, one per source rank
 };
 
 struct DebugOut {

@@ -46,9 +46,11 @@ VECTOR_WIDTH = 8  # main.c:26
 
 
 class Texture2D:
-    """Texture2D, common_shader_core.h:20-24. `p_data` is uint32 [h, w] (R8G8B8A8) or float32 [h, w, 4]."""
+    """Texture2D, common_shader_core.h:20-24. `p_data` is uint32 [h, w] (R8G8B8A8) or float32 [h, w, 4].
+    `is_in_srgb` is load_texture's argument (main.c:538): the device copy is re-quantised to linear on the GPU."""
 
-    def __init__(self, p_data: np.ndarray):
+    def __init__(self, p_data: np.ndarray, is_in_srgb: bool = False):
+        self.is_in_srgb = bool(is_in_srgb)
         if p_data.dtype == np.uint32 and p_data.ndim == 2:
             self.format = L.FORMAT_R8G8B8A8_UNORM
         elif p_data.dtype == np.float32 and p_data.ndim == 3 and p_data.shape[2] == 4:
@@ -172,8 +174,16 @@ class Device:
             return hit[1]
         h = C.c_void_p()
         L.check(self._lib.mlv_create_texture2d(self._h, tex.p_data.ctypes.data_as(C.c_void_p), tex.width, tex.height, tex.format, C.byref(h)))
+        if tex.is_in_srgb:
+            L.check(self._lib.mlv_texture_srgb_to_linear(self._h, h))
         self._textures[id(tex)] = (tex, h)
         return h
+
+    def read_texture(self, tex: Texture2D) -> np.ndarray:
+        """The device copy of a texture (after the sRGB re-quantisation, if any)."""
+        out = np.empty_like(tex.p_data)
+        L.check(self._lib.mlv_read_texture(self._h, self._texture(tex), out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def upload(self, *objs):
         """Optional: create device copies ahead of the first draw (keeps uploads out of a timed region)."""
@@ -341,6 +351,24 @@ class Device:
 
     def composite_unpack(self):
         L.check(self._lib.mlv_composite_unpack(self._h))
+
+    # peer-memory compositing (fused resolve + all-gather over NVLink; see include/malevich_b200.h)
+    def composite_peer_export(self) -> bytes:
+        """This rank's mlv_peer_info as bytes, to be exchanged between the ranks by any transport."""
+        info = L.PeerInfo()
+        L.check(self._lib.mlv_composite_peer_export(self._h, C.byref(info)))
+        return bytes(info)
+
+    def composite_peer_attach(self, infos, same_process: bool = False):
+        """`infos`: the exported bytes of every rank, in rank order."""
+        arr = (L.PeerInfo * len(infos))(*[L.PeerInfo.from_buffer_copy(b) for b in infos])
+        L.check(self._lib.mlv_composite_peer_attach(self._h, arr, 1 if same_process else 0))
+
+    def composite_broadcast(self):
+        L.check(self._lib.mlv_composite_broadcast(self._h))
+
+    def composite_wait(self):
+        L.check(self._lib.mlv_composite_wait(self._h))
 
     # ---- debug read-back of the last draw ------------------------------------------------------
     def debug_vs_out(self) -> np.ndarray:

@@ -9,6 +9,7 @@ BIT-EXACT; colour within 1/255 per channel on >= 99.9 % of pixels, none off by m
 import ctypes
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -288,6 +289,101 @@ def _check_partition(sc, combos):
                 d.close()
 
 
+def test_peer_memory_composite_in_one_process():
+    """mlv_composite_broadcast / mlv_composite_wait with every rank as a device object of this process on one GPU (plain
+    pointers instead of cudaIpc mappings): after two frames (both image parities, increasing sequence numbers) every rank
+    holds the complete image, bit-identical to the single-device one."""
+    from malevich_b200 import scenes
+    sc = cases.SMALL["ftm_320x200"]()
+    with _device(sc.width, sc.height) as dev:
+        scenes.render(dev, sc)
+        ref_col, _ = dev.present()
+    for world, stripe in ((2, 13), (4, 2), (8, 1), (3, 5)):
+        devs = [_device(sc.width, sc.height, num_ranks=world, rank=r, stripe_height_tiles=stripe) for r in range(world)]
+        try:
+            infos = [d.composite_peer_export() for d in devs]
+            for d in devs:
+                d.composite_peer_attach(infos, same_process=True)
+            for frame in range(2):
+                for d in devs:
+                    scenes.render(d, sc)
+                    d.composite_broadcast()
+                for d in devs:  # all stripes are on their way before anybody spins (the streams of one GPU may share a hardware queue)
+                    d.finish()
+                for d in devs:
+                    d.composite_wait()
+                    d.finish()
+                    out = _as_tensor(d.resolved_color_ptr(), sc.width * sc.height * 4).cpu().numpy().view(np.uint32).reshape(sc.height, sc.width)
+                    assert np.array_equal(out, ref_col), f"world {world} stripe {stripe} frame {frame}"
+                    d.stats()  # surfaces MLV_FLAG_COMPOSITE_TIMEOUT, if any
+            with pytest.raises(Exception):
+                devs[0].composite_wait()  # nothing to wait for
+        finally:
+            for d in devs:
+                d.close()
+
+
+def _ipc_rank(rank, world, conns, result_q):
+    """One process = one rank; all ranks share cuda:0 here (on the real machine each has its own GPU)."""
+    try:
+        import numpy as np
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import cases as cases_
+        from malevich_b200 import Device, scenes
+        sc = cases_.SMALL["toon_320x200"]()
+        with Device(sc.width, sc.height) as single:
+            scenes.render(single, sc)
+            ref_col, _ = single.present()
+        with Device(sc.width, sc.height, num_ranks=world, rank=rank, stripe_height_tiles=3) as dev:
+            mine = dev.composite_peer_export()
+            for c in conns:
+                c.send((rank, mine))
+            infos = {rank: mine}
+            for c in conns:
+                r, b = c.recv()
+                infos[r] = b
+            dev.composite_peer_attach([infos[r] for r in range(world)], same_process=False)
+            ok = True
+            for frame in range(3):
+                scenes.render(dev, sc)
+                dev.composite_broadcast()
+                dev.composite_wait()
+                dev.finish()
+                dev.stats()
+                import torch
+                out = _as_tensor(dev.resolved_color_ptr(), sc.width * sc.height * 4).cpu().numpy().view(np.uint32).reshape(sc.height, sc.width)
+                ok = ok and bool(np.array_equal(out, ref_col))
+            for c in conns:  # nobody unmaps while a peer may still be writing
+                c.send("done")
+            for c in conns:
+                c.recv()
+        result_q.put((rank, ok, ""))
+    except Exception as e:  # noqa: BLE001
+        result_q.put((rank, False, repr(e)))
+
+
+def test_peer_memory_composite_across_processes_with_cuda_ipc():
+    """Two processes, one rank each, exchanging mlv_peer_info over a pipe and writing into each other's images through
+    cudaIpc mappings -- the multi-GPU data path of bench.py --gpus N, exercised on a single GPU."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    a, b = ctx.Pipe()
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ipc_rank, args=(0, 2, [a], q)), ctx.Process(target=_ipc_rank, args=(1, 2, [b], q))]
+    for p in procs:
+        p.start()
+    try:
+        results = [q.get(timeout=240) for _ in procs]
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    for rank, ok, err in results:
+        assert ok, f"rank {rank}: {err or 'image differs from the single-device image'}"
+
+
 def _as_tensor(ptr, nbytes):
     import torch
 
@@ -295,6 +391,30 @@ def _as_tensor(ptr, nbytes):
         def __init__(self):
             self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
     return torch.as_tensor(_Raw(), device="cuda")
+
+
+def test_texture_srgb_to_linear_on_device_matches_reference_load_path():
+    """load_texture's is_in_srgb branch (main.c:546-558) run on the GPU: exhaustive over all 256 byte values in every
+    channel, a ragged size (texel count not a multiple of 4), and end to end -- TOON drawn with sRGB textures that the
+    device re-quantises itself must reproduce the golden frame made with host-converted textures."""
+    from malevich_b200 import Texture2D, assets, scenes
+    b = np.arange(256, dtype=np.uint32)
+    every_byte = (b | (b << 8) | (b << 16) | (b << 24)).reshape(16, 16)
+    rng = np.random.default_rng(7)
+    ragged = rng.integers(0, 2**32, size=(61, 127), dtype=np.uint32)
+    sc = cases.SMALL["toon_320x200"]()
+    with _device(sc.width, sc.height) as dev:
+        for arr in (every_byte, ragged, assets.standin_texture_srgb(3, 128)):
+            got = dev.read_texture(Texture2D(arr, is_in_srgb=True))
+            assert np.array_equal(got, assets.srgb_texture_to_linear(arr))
+            if have_ref(320, 200):
+                assert np.array_equal(got, _oracle(320, 200).texture_srgb_to_linear(arr))
+        for i, obj in enumerate(sc.objects):
+            obj.texture = Texture2D(assets.standin_texture_srgb(i), is_in_srgb=True)
+        scenes.render(dev, sc)
+        col, dep = dev.present()
+    frames = np.load(os.path.join(ROOT, "tests", "golden", "small_frames.npz"))
+    parity.assert_frames_match(col, dep, frames["toon_320x200/colors"], frames["toon_320x200/depths"], "toon with device-converted sRGB textures")
 
 
 def test_no_cpu_fallback_and_kernels_launch():
