@@ -157,6 +157,13 @@ MLV_API int mlv_draw(mlv_device *dev, uint32_t vertex_count);                   
  * With num_ranks > 1 only the tiles this rank owns are meaningful unless the caller composited
  * the ranks first (mlv_composite_*). */
 MLV_API int mlv_present_readback(mlv_device *dev, uint32_t *colors, float *depths);
+/* The same without blocking the host: resolve on the device stream, then the device-to-host copies on a read-back stream
+ * of their own, so the read-back of frame f overlaps the uploads and the rendering of frame f+1. `colors` / `depths`
+ * should be page-locked and must stay untouched until mlv_present_wait (or mlv_finish) returns; the next resolve waits
+ * for the copies on the device, so at most one read-back is in flight. Capacity errors of the frame are reported by the
+ * next synchronising call (mlv_get_stats, mlv_present_readback). */
+MLV_API int mlv_present_readback_async(mlv_device *dev, uint32_t *colors, float *depths);
+MLV_API int mlv_present_wait(mlv_device *dev);
 MLV_API int mlv_get_stats(mlv_device *dev, mlv_stats *out);  /* stats main.c:231,1268 */
 MLV_API int mlv_reset_stats(mlv_device *dev);                /* memset(&stats,0) main.c:1268 */
 

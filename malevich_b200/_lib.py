@@ -15,7 +15,7 @@ EXPORTED_SYMBOLS = [
     "mlv_vs_set_shader", "mlv_vs_set_constant_buffer", "mlv_vs_set_shader_resource", "mlv_rs_set_viewport",
     "mlv_ps_set_shader", "mlv_ps_set_shader_resource",
     "mlv_clear_render_target_view", "mlv_clear_depth_stencil_view", "mlv_draw_indexed", "mlv_draw_indexed_ex", "mlv_draw",
-    "mlv_present_readback", "mlv_get_stats", "mlv_reset_stats",
+    "mlv_present_readback", "mlv_present_readback_async", "mlv_present_wait", "mlv_get_stats", "mlv_reset_stats",
     "mlv_resolve", "mlv_resolved_color_device_ptr", "mlv_resolved_depth_device_ptr",
     "mlv_composite_peer_export", "mlv_composite_peer_attach", "mlv_composite_broadcast", "mlv_composite_wait", "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
     "mlv_debug_read_vs_out", "mlv_debug_read_triangles", "mlv_debug_read_bins", "mlv_debug_read_masks",
@@ -109,6 +109,8 @@ def load() -> C.CDLL:
         "mlv_draw_indexed_ex": (i32, [vp, u32, u32, C.c_int32]),
         "mlv_draw": (i32, [vp, u32]),
         "mlv_present_readback": (i32, [vp, vp, vp]),
+        "mlv_present_readback_async": (i32, [vp, vp, vp]),
+        "mlv_present_wait": (i32, [vp]),
         "mlv_get_stats": (i32, [vp, P(Stats)]),
         "mlv_reset_stats": (i32, [vp]),
         "mlv_resolve": (i32, [vp]),

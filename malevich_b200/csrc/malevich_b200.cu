@@ -88,7 +88,13 @@ struct mlv_device {
 	// Buffer uploads run on a copy stream: a draw waits only for the buffers it binds, so the upload of mesh k+1
 	// overlaps the draw of mesh k (a host that streams its geometry every frame is otherwise PCIe-then-render serial).
 	cudaStream_t copy_stream;
-	cudaEvent_t ev_copy_after_main;
+	cudaEvent_t ev_last_draw; // recorded after every draw: the next upload may overwrite a buffer only after the draws that read it
+	bool last_draw_recorded;
+	// Asynchronous present: the device-to-host copies run on their own stream, so the read-back of frame f overlaps the
+	// uploads (other PCIe direction) and the rendering of frame f+1.
+	cudaStream_t readback_stream;
+	cudaEvent_t ev_resolved, ev_readback_done;
+	bool readback_in_flight;
 	cudaEvent_t ev_vertex_done, ev_main_sync, ev_cache_free[2];
 	bool cache_free_recorded[2];
 	bool side_needs_sync; // the side stream has not yet been ordered after the device's creation-time work on the main stream
@@ -262,7 +268,10 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	CREATE_TRY(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
 	CREATE_TRY(cudaStreamCreateWithFlags(&dev->side_stream, cudaStreamNonBlocking));
 	CREATE_TRY(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
-	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_copy_after_main, cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_last_draw, cudaEventDisableTiming));
+	CREATE_TRY(cudaStreamCreateWithFlags(&dev->readback_stream, cudaStreamNonBlocking));
+	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_resolved, cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_readback_done, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_vertex_done, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_main_sync, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_cache_free[0], cudaEventDisableTiming));
@@ -320,7 +329,11 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(dev->stream) cudaStreamDestroy(dev->stream);
 	if(dev->side_stream) cudaStreamDestroy(dev->side_stream);
 	if(dev->copy_stream) cudaStreamDestroy(dev->copy_stream);
-	for(cudaEvent_t e : { dev->ev_copy_after_main, dev->ev_vertex_done, dev->ev_main_sync, dev->ev_cache_free[0], dev->ev_cache_free[1] })
+	if(dev->readback_stream) {
+		cudaStreamSynchronize(dev->readback_stream);
+		cudaStreamDestroy(dev->readback_stream);
+	}
+	for(cudaEvent_t e : { dev->ev_last_draw, dev->ev_resolved, dev->ev_readback_done, dev->ev_vertex_done, dev->ev_main_sync, dev->ev_cache_free[0], dev->ev_cache_free[1] })
 		if(e) cudaEventDestroy(e);
 	if(dev->prof_events) {
 		for(cudaEvent_t e : *dev->prof_events) cudaEventDestroy(e);
@@ -334,6 +347,8 @@ int mlv_finish(mlv_device *dev) {
 	if(int rc = use_device(dev)) return rc;
 	CUDA_TRY(cudaStreamSynchronize(dev->stream));
 	CUDA_TRY(cudaStreamSynchronize(dev->copy_stream)); // uploads no draw has consumed yet
+	CUDA_TRY(cudaStreamSynchronize(dev->readback_stream));
+	dev->readback_in_flight = false;
 	return MLV_OK;
 }
 
@@ -364,9 +379,9 @@ int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t
 	if(int rc = use_device(dev)) return rc;
 	if(!buf || !data || bytes > buf->bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer update");
 	// after every draw issued so far (any of them may read this buffer; each k_vertex on the side stream has already
-	// been joined into the main stream by its k_geom), before the first draw that binds it afterwards (bind_ready)
-	CUDA_TRY(cudaEventRecord(dev->ev_copy_after_main, dev->stream));
-	CUDA_TRY(cudaStreamWaitEvent(dev->copy_stream, dev->ev_copy_after_main, 0));
+	// been joined into the main stream by its k_geom), before the first draw that binds it afterwards. Only draws
+	// read buffers: a resolve or read-back issued since the last draw does not hold the upload back.
+	if(dev->last_draw_recorded) CUDA_TRY(cudaStreamWaitEvent(dev->copy_stream, dev->ev_last_draw, 0));
 	CUDA_TRY(cudaMemcpyAsync(buf->d, data, bytes, cudaMemcpyHostToDevice, dev->copy_stream));
 	CUDA_TRY(cudaEventRecord(buf->ready, dev->copy_stream));
 	buf->ready_pending = true;
@@ -883,7 +898,10 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 		case MLV_PS_BASIC: launch_pdl(k_tile<1>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
 		default: launch_pdl(k_tile<2>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
 	}
-	return check_launch(dev, "k_tile");
+	if(int rc = check_launch(dev, "k_tile")) return rc;
+	CUDA_TRY(cudaEventRecord(dev->ev_last_draw, dev->stream));
+	dev->last_draw_recorded = true;
+	return MLV_OK;
 }
 
 extern "C" {
@@ -907,6 +925,7 @@ static int check_flags(mlv_device *dev, const Counters &c) {
 int mlv_resolve(mlv_device *dev) {
 	if(int rc = use_device(dev)) return rc;
 	if(int rc = flush_clears(dev)) return rc;
+	if(dev->readback_in_flight) CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_readback_done, 0));
 	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H; // 8 pixels (4 wide, rows y and y+4) per thread
 	prof_pre(dev, MLV_STAGE_RESOLVE);
 	launch_pdl(k_resolve, (items + 255) / 256, 256, dev->stream, dev->fb, dev->resolved_color, dev->resolved_depth, dev->W, dev->H);
@@ -917,9 +936,37 @@ int mlv_resolve(mlv_device *dev) {
 void *mlv_resolved_color_device_ptr(mlv_device *dev) { return dev ? dev->present_color : nullptr; }
 void *mlv_resolved_depth_device_ptr(mlv_device *dev) { return dev ? dev->resolved_depth : nullptr; }
 
+int mlv_present_readback_async(mlv_device *dev, uint32_t *colors, float *depths) {
+	if(int rc = use_device(dev)) return rc;
+	if(int rc = flush_clears(dev)) return rc;
+	if(dev->readback_in_flight) CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_readback_done, 0)); // the resolved images are reused
+	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
+	prof_pre(dev, MLV_STAGE_RESOLVE);
+	launch_pdl(k_resolve, (items + 255) / 256, 256, dev->stream, dev->fb, dev->resolved_color, depths ? dev->resolved_depth : nullptr, dev->W, dev->H);
+	dev->present_color = dev->resolved_color;
+	if(int rc = check_launch(dev, "k_resolve")) return rc;
+	CUDA_TRY(cudaEventRecord(dev->ev_resolved, dev->stream));
+	CUDA_TRY(cudaStreamWaitEvent(dev->readback_stream, dev->ev_resolved, 0));
+	const size_t bytes = (size_t)dev->W * dev->H * 4;
+	if(colors) CUDA_TRY(cudaMemcpyAsync(colors, dev->resolved_color, bytes, cudaMemcpyDeviceToHost, dev->readback_stream));
+	if(depths) CUDA_TRY(cudaMemcpyAsync(depths, dev->resolved_depth, bytes, cudaMemcpyDeviceToHost, dev->readback_stream));
+	CUDA_TRY(cudaEventRecord(dev->ev_readback_done, dev->readback_stream));
+	dev->readback_in_flight = true;
+	return MLV_OK;
+}
+
+int mlv_present_wait(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	if(!dev->readback_in_flight) return MLV_OK;
+	CUDA_TRY(cudaEventSynchronize(dev->ev_readback_done));
+	dev->readback_in_flight = false;
+	return MLV_OK;
+}
+
 int mlv_present_readback(mlv_device *dev, uint32_t *colors, float *depths) {
 	if(int rc = use_device(dev)) return rc;
 	if(int rc = flush_clears(dev)) return rc;
+	if(dev->readback_in_flight) CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_readback_done, 0));
 	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
 	prof_pre(dev, MLV_STAGE_RESOLVE);
 	launch_pdl(k_resolve, (items + 255) / 256, 256, dev->stream, dev->fb, dev->resolved_color, depths ? dev->resolved_depth : nullptr, dev->W, dev->H);
@@ -974,6 +1021,7 @@ int mlv_composite_unpack(mlv_device *dev) {
 	if(int rc = use_device(dev)) return rc;
 	if(dev->part.num_ranks <= 1) return fail(MLV_ERR_STATE, "device was created with a single rank");
 	const uint32_t quads = (uint32_t)(dev->W / 4) * (uint32_t)dev->H;
+	if(dev->readback_in_flight) CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_readback_done, 0));
 	prof_pre(dev, MLV_STAGE_COMPOSITE);
 	launch_pdl(k_composite_unpack, (quads + 255) / 256, 256, dev->stream, dev->gather, dev->resolved_color, dev->W, dev->H, dev->part.num_ranks, dev->part.stripe_h, dev->chunk_bytes / 16);
 	dev->present_color = dev->resolved_color;

@@ -306,6 +306,14 @@ class Device:
         L.check(self._lib.mlv_present_readback(self._h, colors.ctypes.data_as(C.c_void_p),
                                                depths.ctypes.data_as(C.c_void_p) if depths is not None else None))
 
+    def present_async(self, colors: np.ndarray, depths: Optional[np.ndarray] = None):
+        """Non-blocking present into (page-locked) arrays; `present_wait` or `finish` says when they are complete."""
+        L.check(self._lib.mlv_present_readback_async(self._h, colors.ctypes.data_as(C.c_void_p),
+                                                     depths.ctypes.data_as(C.c_void_p) if depths is not None else None))
+
+    def present_wait(self):
+        L.check(self._lib.mlv_present_wait(self._h))
+
     def finish(self):
         L.check(self._lib.mlv_finish(self._h))
 

@@ -393,6 +393,32 @@ def _as_tensor(ptr, nbytes):
     return torch.as_tensor(_Raw(), device="cuda")
 
 
+def test_async_present_and_streamed_uploads_match_blocking_present():
+    """mlv_present_readback_async + mlv_present_wait deliver the image mlv_present_readback does, also when every buffer
+    is re-uploaded before every frame (uploads on the copy stream, read-back on its own stream, two frames in flight)."""
+    import ctypes as C
+    from malevich_b200 import _lib as L
+    from malevich_b200 import scenes
+    sc = cases.SMALL["ftm_320x200"]()
+    with _device(sc.width, sc.height) as dev:
+        scenes.render(dev, sc)
+        ref_col, ref_dep = dev.present()
+        bufs = [(np.zeros_like(ref_col), np.zeros_like(ref_dep)) for _ in range(2)]
+        for frame in range(4):
+            for obj in sc.objects:
+                for arr, kind in ((obj.vertex_buffer, L.BUFFER_VERTEX), (obj.index_buffer, L.BUFFER_INDEX)):
+                    L.check(dev._lib.mlv_update_buffer(dev._h, dev._buffer(arr, kind), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+            scenes.render(dev, sc)
+            dev.present_wait()
+            if frame:
+                col, dep = bufs[(frame - 1) % 2]
+                assert np.array_equal(col, ref_col) and np.array_equal(dep.view(np.uint32), ref_dep.view(np.uint32))
+                col[...] = 0
+            dev.present_async(*bufs[frame % 2])
+        dev.finish()
+        assert np.array_equal(bufs[1][0], ref_col)
+
+
 def test_texture_srgb_to_linear_on_device_matches_reference_load_path():
     """load_texture's is_in_srgb branch (main.c:546-558) run on the GPU: exhaustive over all 256 byte values in every
     channel, a ragged size (texel count not a multiple of 4), and end to end -- TOON drawn with sRGB textures that the
