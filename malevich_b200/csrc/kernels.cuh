@@ -551,6 +551,20 @@ __device__ __forceinline__ bool chunk_is_foreign(const GeomParams &P, uint32_t c
 // shader and the per-vertex part of primitive assembly once per UNIQUE vertex; k_geom<VCACHE> then gathers 32 bytes
 // per corner from an L2-resident table instead of fetching, transforming, dividing and snapping it again. Both are
 // pure functions of the vertex, so the values are the ones the reference computes per corner.
+// The per-vertex half of the cull / trivial-reject / trivial-accept tests (main.c:759-781), one bit per comparison so that
+// the per-triangle tests become three bitwise operations. NaN makes every comparison false, as in the reference:
+// bits 0-5  "outside":  x < -w, x > w, y < -w, y > w, z < 0, z > w   (rejected: some plane has all three vertices outside)
+// bits 6-11 "inside":   x >= -w, x <= w, y >= -w, y <= w, z >= 0, z <= w   (inside: every plane has all three inside)
+// bit 12    w == 0 (degenerate, main.c:759)
+#define MLV_CODE_OUT 0x3fu
+#define MLV_CODE_IN 0xfc0u
+#define MLV_CODE_W0 0x1000u
+__device__ __forceinline__ uint32_t clip_code(const float4 p) {
+	return (p.x < -p.w ? 1u : 0u) | (p.x > p.w ? 2u : 0u) | (p.y < -p.w ? 4u : 0u) | (p.y > p.w ? 8u : 0u) | (p.z < 0.0f ? 16u : 0u) | (p.z > p.w ? 32u : 0u) |
+	       (p.x >= -p.w ? 64u : 0u) | (p.x <= p.w ? 128u : 0u) | (p.y >= -p.w ? 256u : 0u) | (p.y <= p.w ? 512u : 0u) | (p.z >= 0.0f ? 1024u : 0u) | (p.z <= p.w ? 2048u : 0u) |
+	       (p.w == 0.0f ? MLV_CODE_W0 : 0u);
+}
+
 template <int VS>
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ GeomParams P, uint32_t vertex_count) {
 	pdl_prologue();
@@ -559,7 +573,7 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ GeomPara
 	const float4 pos = vs_position<VS>(__ldg(P.vb + 2 * (size_t)v), P.cb);
 	const ProjVertex pv = project_vertex(pos, P);
 	P.vcache[2 * (size_t)v] = pos;
-	P.vcache[2 * (size_t)v + 1] = make_float4(__int_as_float(pv.sx), __int_as_float(pv.sy), pv.s.z, pv.rw);
+	P.vcache[2 * (size_t)v + 1] = make_float4(__int_as_float(pv.sx), __int_as_float(pv.sy), pv.s.z, __uint_as_float(clip_code(pos)));
 }
 
 template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
@@ -614,10 +628,10 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 			vi2 = vi0 + 2u;
 		}
 		float4 a0, b0, c0, a, b, c, qa, qb, qc; // first half of each input vertex; clip-space positions; cached per-vertex projection
-		if(VCACHE) {
-			a = __ldg(P.vcache + 2 * (size_t)vi0), qa = __ldg(P.vcache + 2 * (size_t)vi0 + 1);
-			b = __ldg(P.vcache + 2 * (size_t)vi1), qb = __ldg(P.vcache + 2 * (size_t)vi1 + 1);
-			c = __ldg(P.vcache + 2 * (size_t)vi2), qc = __ldg(P.vcache + 2 * (size_t)vi2 + 1);
+		if(VCACHE) { // only the projected half of each entry: the clip-space positions are fetched for survivors
+			qa = __ldg(P.vcache + 2 * (size_t)vi0 + 1);
+			qb = __ldg(P.vcache + 2 * (size_t)vi1 + 1);
+			qc = __ldg(P.vcache + 2 * (size_t)vi2 + 1);
 		} else {
 			a0 = __ldg(P.vb + 2 * (size_t)vi0), b0 = __ldg(P.vb + 2 * (size_t)vi1), c0 = __ldg(P.vb + 2 * (size_t)vi2);
 			// ---- vertex shader, position part (main.c:698-734)
@@ -633,23 +647,31 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 			o[6] = v2.r0, o[7] = v2.r1, o[8] = make_float4(v2.r2x, 0.0f, 0.0f, 0.0f);
 		}
 		// ---- primitive assembly (main.c:750-908)
-		const bool degenerate = (a.w == 0.0f || b.w == 0.0f || c.w == 0.0f); // main.c:759
-		const bool rejected =                                                // main.c:764-772
-		    (a.x < -a.w && b.x < -b.w && c.x < -c.w) || (a.x > a.w && b.x > b.w && c.x > c.w) || (a.y < -a.w && b.y < -b.w && c.y < -c.w) ||
-		    (a.y > a.w && b.y > b.w && c.y > c.w) || (a.z < 0.0f && b.z < 0.0f && c.z < 0.0f) || (a.z > a.w && b.z > b.w && c.z > c.w);
-		bool direct = false;
-		if(!degenerate && !rejected) {
-			const bool inside = // main.c:775-781
+		bool degenerate, rejected, inside;
+		if(VCACHE) { // the comparisons were made per vertex by k_vertex (clip_code)
+			const uint32_t ca = __float_as_uint(qa.w), cb = __float_as_uint(qb.w), cc = __float_as_uint(qc.w);
+			degenerate = ((ca | cb | cc) & MLV_CODE_W0) != 0u;
+			rejected = (ca & cb & cc & MLV_CODE_OUT) != 0u;
+			inside = (ca & cb & cc & MLV_CODE_IN) == MLV_CODE_IN;
+		} else {
+			degenerate = (a.w == 0.0f || b.w == 0.0f || c.w == 0.0f); // main.c:759
+			rejected =                                                // main.c:764-772
+			    (a.x < -a.w && b.x < -b.w && c.x < -c.w) || (a.x > a.w && b.x > b.w && c.x > c.w) || (a.y < -a.w && b.y < -b.w && c.y < -c.w) ||
+			    (a.y > a.w && b.y > b.w && c.y > c.w) || (a.z < 0.0f && b.z < 0.0f && c.z < 0.0f) || (a.z > a.w && b.z > b.w && c.z > c.w);
+			inside = // main.c:775-781
 			    (a.x >= -a.w && b.x >= -b.w && c.x >= -c.w) && (a.x <= a.w && b.x <= b.w && c.x <= c.w) && (a.y >= -a.w && b.y >= -b.w && c.y >= -c.w) &&
 			    (a.y <= a.w && b.y <= b.w && c.y <= c.w) && (a.z >= 0.0f && b.z >= 0.0f && c.z >= 0.0f) && (a.z <= a.w && b.z <= b.w && c.z <= c.w);
+		}
+		bool direct = false;
+		if(!degenerate && !rejected) {
 			if(inside) {
 				TriSetup S;
 				bool kept;
 				if(VCACHE) {
 					ProjVertex pa, pb, pc; // s.x, s.y, s.w are not needed outside debug capture (which never uses the cache)
-					pa.s = make_float4(0.0f, 0.0f, qa.z, 0.0f), pa.rw = qa.w, pa.sx = __float_as_int(qa.x), pa.sy = __float_as_int(qa.y);
-					pb.s = make_float4(0.0f, 0.0f, qb.z, 0.0f), pb.rw = qb.w, pb.sx = __float_as_int(qb.x), pb.sy = __float_as_int(qb.y);
-					pc.s = make_float4(0.0f, 0.0f, qc.z, 0.0f), pc.rw = qc.w, pc.sx = __float_as_int(qc.x), pc.sy = __float_as_int(qc.y);
+					pa.s = make_float4(0.0f, 0.0f, qa.z, 0.0f), pa.rw = 0.0f, pa.sx = __float_as_int(qa.x), pa.sy = __float_as_int(qa.y);
+					pb.s = make_float4(0.0f, 0.0f, qb.z, 0.0f), pb.rw = 0.0f, pb.sx = __float_as_int(qb.x), pb.sy = __float_as_int(qb.y);
+					pc.s = make_float4(0.0f, 0.0f, qc.z, 0.0f), pc.rw = 0.0f, pc.sx = __float_as_int(qc.x), pc.sy = __float_as_int(qc.y);
 					kept = setup_from_projected(pa, pb, pc, P, S);
 				} else {
 					kept = setup_project(a, b, c, P, S);
@@ -667,7 +689,11 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 						// ---- vertex shader, attribute part
 						float4 r1a, r1b, r1c;
 						float r2a, r2b, r2c;
-						if(VCACHE) a0 = __ldg(P.vb + 2 * (size_t)vi0), b0 = __ldg(P.vb + 2 * (size_t)vi1), c0 = __ldg(P.vb + 2 * (size_t)vi2);
+						if(VCACHE) {
+							a0 = __ldg(P.vb + 2 * (size_t)vi0), b0 = __ldg(P.vb + 2 * (size_t)vi1), c0 = __ldg(P.vb + 2 * (size_t)vi2);
+							a = __ldg(P.vcache + 2 * (size_t)vi0), b = __ldg(P.vcache + 2 * (size_t)vi1), c = __ldg(P.vcache + 2 * (size_t)vi2);
+							S.rw[0] = 1.0f / a.w, S.rw[1] = 1.0f / b.w, S.rw[2] = 1.0f / c.w; // a_reciprocal_ws (project_vertex): the same correctly rounded divide
+						}
 						vs_attributes<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), a, P.cb, P.vs_tex, P.rsqrt_lut, r1a, r2a);
 						vs_attributes<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), b, P.cb, P.vs_tex, P.rsqrt_lut, r1b, r2b);
 						vs_attributes<VS>(c0, __ldg(P.vb + 2 * (size_t)vi2 + 1), c, P.cb, P.vs_tex, P.rsqrt_lut, r1c, r2c);

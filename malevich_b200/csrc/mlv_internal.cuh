@@ -112,7 +112,7 @@ struct GeomParams {
 	uint4 *tri_bounds;
 	const float4 *chunk_bounds; // sort-first chunk culling: 2 x float4 per k_geom CTA, or null
 	uint8_t *chunk_live;        // written by k_geom's cull test: 1 = this rank processed the chunk
-	float4 *vcache; // 2 x float4 per unique vertex: clip-space position, {snapped x, snapped y, screen z, 1/w}
+	float4 *vcache; // 2 x float4 per unique vertex: clip-space position, {snapped x, snapped y, screen z, clip_code bits}
 	uint32_t *clip_queue;
 	uint32_t *big_queue;
 	uint32_t *huge_queue;
