@@ -594,6 +594,8 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 	// rank's tile rows, so a foreign chunk costs one thread's cull test instead of a CTA (or a kernel of its own).
 	__shared__ uint8_t s_live[MLV_GEOM_THREADS];
 	const uint32_t num_chunks = (P.tri_count + MLV_GEOM_THREADS - 1u) / MLV_GEOM_THREADS;
+	uint32_t pf0 = 0, pf1 = 0, pf2 = 0; // prefetched vertex indices of the next chunk
+	bool pf_valid = false;
 	for(uint32_t first = blockIdx.x; first < num_chunks; first += gridDim.x * MLV_GEOM_THREADS) {
 	if(P.chunk_bounds) {
 		const uint32_t c = first + threadIdx.x * gridDim.x;
@@ -619,9 +621,22 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 		// that survive culling and Hi-Z (the reference shades all of them; the results are the same values).
 		uint32_t vi0, vi1, vi2;
 		if(INDEXED) {
-			vi0 = P.ix.fetch(3u * t);
-			vi1 = P.ix.fetch(3u * t + 1u);
-			vi2 = P.ix.fetch(3u * t + 2u);
+			if(pf_valid) {
+				vi0 = pf0, vi1 = pf1, vi2 = pf2;
+			} else {
+				vi0 = P.ix.fetch(3u * t);
+				vi1 = P.ix.fetch(3u * t + 1u);
+				vi2 = P.ix.fetch(3u * t + 2u);
+			}
+			// persistent grid: the indices of this thread's triangle in the CTA's NEXT chunk are requested now, so the
+			// first of the three dependent round trips (index -> vertex -> tile minimum) of that chunk is already over
+			const uint32_t tn = t + gridDim.x * MLV_GEOM_THREADS;
+			pf_valid = !P.chunk_bounds && tn < P.tri_count;
+			if(pf_valid) {
+				pf0 = P.ix.fetch(3u * tn);
+				pf1 = P.ix.fetch(3u * tn + 1u);
+				pf2 = P.ix.fetch(3u * tn + 2u);
+			}
 		} else {
 			vi0 = 3u * t;
 			vi1 = vi0 + 1u;

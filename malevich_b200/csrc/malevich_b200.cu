@@ -590,7 +590,7 @@ static TexDesc tex_desc(const mlv_texture *t) {
 template <int VS>
 static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed, uint32_t vcache_vertices) {
 	const bool debug = gp.keep_all;
-	if(gp.chunk_bounds && nblocks > 148u * 4u) nblocks = 148u * 4u; // sort-first: persistent grid, chunks culled inside k_geom
+	if(nblocks > 148u * 4u) nblocks = 148u * 4u; // persistent grid: 4 CTAs per SM stride over the chunks (sort-first: and cull them in place)
 	if(vcache_vertices) {
 		const int sel = dev->vcache_sel;
 		dev->vcache_sel ^= 1;
