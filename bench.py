@@ -119,7 +119,7 @@ def run_reference(args, rank: int):
     from oracle.ref_oracle import RefOracle, have
     scene = build_scene(args.config)
     base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
             "config": {"workload": workload_name(args.config, scene), "input_triangles": scene.input_triangles, "draws": len(scene.objects)}}
     if not have(scene.width, scene.height):
         base["unavailable"] = f"oracle/_ref/libmalevich_ref_{scene.width}x{scene.height}.so not built (needs /root/reference at build time)"
@@ -206,11 +206,22 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             if ok.item() == 0:
                 composite = "nccl"
 
+    # p2p: the exchange of frame f runs on the library's exchange stream underneath the drawing of frame f+1 (see
+    # mlv_composite_broadcast_async): frame() draws frame f+1, joins the exchange of frame f and starts that of frame
+    # f+1; drain() joins the last one. Every timed region ends with drain(), so K steps contain K complete exchanges.
+    pending = [False]
+
+    def drain():
+        if pending[0]:
+            dev.composite_join()
+            pending[0] = False
+
     def frame():
         scenes.render(dev, scene)
         if composite == "p2p":
-            dev.composite_broadcast()
-            dev.composite_wait()
+            drain()
+            dev.composite_broadcast_async()
+            pending[0] = True
         elif composite == "nccl":
             dev.composite_pack()
             with torch.cuda.stream(stream):
@@ -220,6 +231,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             dev.resolve()
 
     def barrier():
+        drain()
         dev.finish()
         torch.cuda.synchronize()
         if multi:
@@ -261,6 +273,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     e0.record(stream)
     for _ in range(args.steps):
         frame()
+    drain()
     e1.record(stream)
     barrier()
     launches = dev.kernel_launch_count - launches0
@@ -271,6 +284,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     dev.profile_begin()
     for _ in range(args.steps):
         frame()
+    drain()
     prof = dev.profile_end()
     stage_ms = {k: v[0] / args.steps for k, v in prof.items()}
     stage_launches = {k: v[1] // args.steps for k, v in prof.items()}
@@ -309,6 +323,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             L.check(lib.mlv_update_buffer(dev._h, h, p.ctypes.data_as(C.c_void_p), p.nbytes))
         if multi:
             frame()
+            drain()
             dev.finish()  # composite result is in the resolved image; read it back below
             _readback_multi()
         else:
@@ -413,6 +428,12 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", "29541",
                os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its version
+    # banner there) are pointed at stderr; the line itself goes to a private duplicate of the original stdout
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = json_out
     run_b200(args, rank, world, local_rank)
 
 

@@ -205,6 +205,19 @@ MLV_API int mlv_composite_peer_export(mlv_device *dev, mlv_peer_info *out);
 MLV_API int mlv_composite_peer_attach(mlv_device *dev, const mlv_peer_info *infos /* [num_ranks], in rank order */, int same_process);
 MLV_API int mlv_composite_broadcast(mlv_device *dev);
 MLV_API int mlv_composite_wait(mlv_device *dev);
+/* The same exchange off the critical path. mlv_composite_broadcast_async puts the broadcast and the wait of frame f on
+ * an exchange stream of their own (high priority, ordered after everything issued so far) and returns; the device
+ * goes on with frame f+1 at once -- a frame that starts with a colour + depth clear is drawn into the second tiled
+ * framebuffer of a pair, so it does not wait for the broadcast that still reads the first. mlv_composite_join makes the
+ * device stream wait for that exchange; afterwards mlv_resolved_color_device_ptr is the complete image of frame f. Rules:
+ * every _async is joined before the next broadcast of either kind, and whatever reads the joined image (work on
+ * mlv_get_stream(), or mlv_present_*) is issued before the next broadcast -- peers reuse the image two frames later,
+ * after this rank's next broadcast has run. The usual frame loop is
+ *     draw frame f+1;  mlv_composite_join (frame f);  consume frame f;  mlv_composite_broadcast_async (frame f+1)
+ * whose frame time is a rank's own rendering time: the NVLink transfer and the wait for the slowest rank overlap the next
+ * frame's geometry. */
+MLV_API int mlv_composite_broadcast_async(mlv_device *dev);
+MLV_API int mlv_composite_join(mlv_device *dev);
 
 /* ---- debug read-back of the last draw (needs MLV_DEVICE_DEBUG_CAPTURE). Each synchronises.
  * Pass NULL data pointers to query the counts only. */

@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = [
     "mlv_clear_render_target_view", "mlv_clear_depth_stencil_view", "mlv_draw_indexed", "mlv_draw_indexed_ex", "mlv_draw",
     "mlv_present_readback", "mlv_present_readback_async", "mlv_present_wait", "mlv_get_stats", "mlv_reset_stats",
     "mlv_resolve", "mlv_resolved_color_device_ptr", "mlv_resolved_depth_device_ptr",
-    "mlv_composite_peer_export", "mlv_composite_peer_attach", "mlv_composite_broadcast", "mlv_composite_wait", "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
+    "mlv_composite_peer_export", "mlv_composite_peer_attach", "mlv_composite_broadcast", "mlv_composite_wait", "mlv_composite_broadcast_async", "mlv_composite_join", "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
     "mlv_debug_read_vs_out", "mlv_debug_read_triangles", "mlv_debug_read_bins", "mlv_debug_read_masks",
     "mlv_debug_read_tile_min_depths", "mlv_profile_begin", "mlv_profile_end", "mlv_kernel_launch_count",
 ]
@@ -121,6 +121,8 @@ def load() -> C.CDLL:
         "mlv_composite_peer_attach": (i32, [vp, vp, i32]),
         "mlv_composite_broadcast": (i32, [vp]),
         "mlv_composite_wait": (i32, [vp]),
+        "mlv_composite_broadcast_async": (i32, [vp]),
+        "mlv_composite_join": (i32, [vp]),
         "mlv_composite_pack": (i32, [vp]),
         "mlv_composite_unpack": (i32, [vp]),
         "mlv_debug_read_vs_out": (i32, [vp, vp, P(u32)]),

@@ -1521,8 +1521,10 @@ __global__ void __launch_bounds__(256) k_composite_unpack(const uint4 *__restric
 // row-major image of EVERY rank (its own included) with 128-bit stores -- local HBM for itself, NVLink for the
 // peers -- so there is no staging chunk, no collective call and no un-swizzle pass afterwards. When the last CTA
 // has fenced its stores, one thread publishes the frame's sequence number in every rank's arrival word for this rank.
+// Targets are the ranks [target_lo, target_hi); `publish` = 0 leaves the arrival words alone (the copy-engine form of
+// the exchange resolves into this rank's own image only and publishes after its peer copies, k_composite_publish).
 __global__ void __launch_bounds__(256) k_composite_broadcast(const uint4 *__restrict__ fb, const __grid_constant__ PeerTargets peers, int width, int height, Partition part, uint32_t seq,
-                                                             Counters *__restrict__ ctr) {
+                                                             Counters *__restrict__ ctr, int target_lo, int target_hi, int publish) {
 	pdl_prologue();
 	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t wt = (uint32_t)width >> 3, ht = (uint32_t)height >> 3;
@@ -1533,13 +1535,14 @@ __global__ void __launch_bounds__(256) k_composite_broadcast(const uint4 *__rest
 		if(part.owns_row((int)ty)) {
 			const Quad8 q = load_quad8(fb, ty * wt + (xq >> 1), row, xq & 1u);
 			const size_t top = (size_t)(ty * 8u + row) * quads_per_row + xq;
-			for(int p = 0; p < part.num_ranks; ++p) {
+			for(int p = target_lo; p < target_hi; ++p) {
 				uint4 *dst = peers.color[p];
 				dst[top] = q.c_top;
 				dst[top + 4u * quads_per_row] = q.c_bot;
 			}
 		}
 	}
+	if(!publish) return;
 	__threadfence_system(); // my stores are visible to every GPU before my CTA is counted as done
 	__syncthreads();
 	if(threadIdx.x == 0) {
@@ -1549,6 +1552,16 @@ __global__ void __launch_bounds__(256) k_composite_broadcast(const uint4 *__rest
 			__threadfence_system();
 			for(int p = 0; p < part.num_ranks; ++p) *reinterpret_cast<volatile uint32_t *>(peers.flags[p] + part.rank) = seq;
 		}
+	}
+}
+
+// Copy-engine form of the exchange: after this rank's band has been copied into every peer's image (cudaMemcpyAsync on
+// the exchange stream, ordered before this launch), tell every rank that frame `seq` of this rank has arrived.
+__global__ void __launch_bounds__(32) k_composite_publish(const __grid_constant__ PeerTargets peers, int num_ranks, int rank, uint32_t seq) {
+	pdl_prologue();
+	if((int)threadIdx.x < num_ranks) {
+		__threadfence_system();
+		*reinterpret_cast<volatile uint32_t *>(peers.flags[threadIdx.x] + rank) = seq;
 	}
 }
 

@@ -69,7 +69,17 @@ struct mlv_device {
 	Partition part;
 
 	// persistent render state (reference: static frame_buffer/depth_buffer/a_tile_min_depths)
-	uint4 *fb;
+	uint4 *fb;                 // the tiled framebuffer draws go to (= fb_pair[fb_sel])
+	// Asynchronous exchange (mlv_composite_broadcast_async): the broadcast of frame f reads the tiled framebuffer on the
+	// exchange stream while frame f+1 is already being drawn, so a frame that starts with a full clear is drawn into
+	// the other framebuffer of the pair instead of waiting for the broadcast.
+	uint4 *fb_pair[2];
+	int fb_sel;
+	bool fb_busy[2];           // a broadcast on the exchange stream reads fb_pair[i]; ev_fb_free[i] fires when it is done
+	cudaEvent_t ev_fb_free[2];
+	cudaStream_t xchg_stream;
+	cudaEvent_t ev_frame_done, ev_xchg_done;
+	bool xchg_pending;         // mlv_composite_join has not yet been called for the last mlv_composite_broadcast_async
 	float *tile_min;
 	// per-draw arenas
 	uint32_t *bin_count, *bin_offset;
@@ -276,9 +286,19 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_main_sync, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_cache_free[0], cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_cache_free[1], cudaEventDisableTiming));
+	if(num_ranks > 1) {
+		int prio_lo = 0, prio_hi = 0; // the exchange is short and latency-critical: its CTAs go first when SM slots free up
+		CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		CREATE_TRY(cudaStreamCreateWithPriority(&dev->xchg_stream, cudaStreamNonBlocking, prio_hi));
+		CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_frame_done, cudaEventDisableTiming));
+		CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_xchg_done, cudaEventDisableTiming));
+		CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_fb_free[0], cudaEventDisableTiming));
+		CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_fb_free[1], cudaEventDisableTiming));
+	}
 	dev->side_needs_sync = true;
 	const size_t nb = dev->num_bins;
-	CREATE_TRY(cudaMalloc(&dev->fb, nb * 32 * sizeof(uint4)));
+	CREATE_TRY(cudaMalloc(&dev->fb_pair[0], nb * 32 * sizeof(uint4)));
+	dev->fb = dev->fb_pair[0];
 	CREATE_TRY(cudaMalloc(&dev->tile_min, nb * sizeof(float)));
 	CREATE_TRY(cudaMalloc(&dev->bin_count, nb * sizeof(uint32_t)));
 	CREATE_TRY(cudaMalloc(&dev->bin_offset, nb * sizeof(uint32_t)));
@@ -297,6 +317,10 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	dev->present_color = dev->resolved_color;
 	CREATE_TRY(cudaMalloc(&dev->resolved_depth, (size_t)dev->W * dev->H * 4));
 	CREATE_TRY(cudaMemsetAsync(dev->fb, 0, nb * 32 * sizeof(uint4), dev->stream));
+	if(num_ranks > 1) {
+		CREATE_TRY(cudaMalloc(&dev->fb_pair[1], nb * 32 * sizeof(uint4)));
+		CREATE_TRY(cudaMemsetAsync(dev->fb_pair[1], 0, nb * 32 * sizeof(uint4), dev->stream));
+	}
 	CREATE_TRY(cudaMemsetAsync(dev->tile_min, 0, nb * sizeof(float), dev->stream));
 	CREATE_TRY(cudaMemsetAsync(dev->bin_count, 0, nb * sizeof(uint32_t), dev->stream));
 	CREATE_TRY(cudaMemsetAsync(dev->ctr, 0, sizeof(Counters), dev->stream));
@@ -321,19 +345,21 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(dev->stream) cudaStreamSynchronize(dev->stream);
 	if(dev->side_stream) cudaStreamSynchronize(dev->side_stream);
 	if(dev->copy_stream) cudaStreamSynchronize(dev->copy_stream);
+	if(dev->xchg_stream) cudaStreamSynchronize(dev->xchg_stream);
 	for(int i = 0; i < dev->ipc_opened_count; ++i) cudaIpcCloseMemHandle(dev->ipc_opened[i]);
-	void *ptrs[] = { dev->fb, dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue, dev->vcache[0], dev->vcache[1], dev->chunk_live,
+	void *ptrs[] = { dev->fb_pair[0], dev->fb_pair[1], dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue, dev->vcache[0], dev->vcache[1], dev->chunk_live,
 		             dev->scan_state, dev->ctr, dev->stat_stripes, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather, dev->p2p_color[0], dev->p2p_color[1], dev->p2p_flags };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
 	if(dev->stream) cudaStreamDestroy(dev->stream);
 	if(dev->side_stream) cudaStreamDestroy(dev->side_stream);
 	if(dev->copy_stream) cudaStreamDestroy(dev->copy_stream);
+	if(dev->xchg_stream) cudaStreamDestroy(dev->xchg_stream);
 	if(dev->readback_stream) {
 		cudaStreamSynchronize(dev->readback_stream);
 		cudaStreamDestroy(dev->readback_stream);
 	}
-	for(cudaEvent_t e : { dev->ev_last_draw, dev->ev_resolved, dev->ev_readback_done, dev->ev_vertex_done, dev->ev_main_sync, dev->ev_cache_free[0], dev->ev_cache_free[1] })
+	for(cudaEvent_t e : { dev->ev_last_draw, dev->ev_resolved, dev->ev_readback_done, dev->ev_vertex_done, dev->ev_main_sync, dev->ev_cache_free[0], dev->ev_cache_free[1], dev->ev_frame_done, dev->ev_xchg_done, dev->ev_fb_free[0], dev->ev_fb_free[1] })
 		if(e) cudaEventDestroy(e);
 	if(dev->prof_events) {
 		for(cudaEvent_t e : *dev->prof_events) cudaEventDestroy(e);
@@ -349,6 +375,10 @@ int mlv_finish(mlv_device *dev) {
 	CUDA_TRY(cudaStreamSynchronize(dev->copy_stream)); // uploads no draw has consumed yet
 	CUDA_TRY(cudaStreamSynchronize(dev->readback_stream));
 	dev->readback_in_flight = false;
+	if(dev->xchg_stream) {
+		CUDA_TRY(cudaStreamSynchronize(dev->xchg_stream));
+		dev->fb_busy[0] = dev->fb_busy[1] = false;
+	}
 	return MLV_OK;
 }
 
@@ -538,9 +568,26 @@ int mlv_ps_set_shader_resource(mlv_device *dev, uint32_t slot, mlv_texture *tex)
 
 // ---- clears --------------------------------------------------------------------------------------
 
+// Called before anything on the main stream WRITES the tiled framebuffer (a clear, a draw): an asynchronous broadcast
+// may still be reading it on the exchange stream. A frame that starts with a full clear moves to the other framebuffer
+// of the pair (nothing of the old contents survives such a clear); anything else waits for the broadcast.
+static int acquire_framebuffer(mlv_device *dev, bool full_clear) {
+	if(!dev->xchg_stream || !(dev->fb_busy[0] || dev->fb_busy[1])) return MLV_OK;
+	if(full_clear && dev->fb_busy[dev->fb_sel]) {
+		dev->fb_sel ^= 1;
+		dev->fb = dev->fb_pair[dev->fb_sel];
+	}
+	if(dev->fb_busy[dev->fb_sel]) {
+		CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_fb_free[dev->fb_sel], 0));
+		dev->fb_busy[dev->fb_sel] = false;
+	}
+	return MLV_OK;
+}
+
 static int flush_clears(mlv_device *dev) {
-	if(!dev->pend_color && !dev->pend_depth) return MLV_OK;
+	if(!dev->pend_color && !dev->pend_depth) return acquire_framebuffer(dev, false);
 	const int mode = (dev->pend_color ? 1 : 0) | (dev->pend_depth ? 2 : 0);
+	if(int rc = acquire_framebuffer(dev, mode == 3)) return rc;
 	const uint32_t n = (dev->bin_end - dev->bin_begin) * 32u; // this rank's band only (nobody reads the tiles of other ranks)
 	if(n == 0) { // a rank without tile rows (more ranks than stripes)
 		dev->pend_color = dev->pend_depth = false;
@@ -1105,6 +1152,7 @@ int mlv_composite_broadcast(mlv_device *dev) {
 	if(int rc = use_device(dev)) return rc;
 	if(!dev->peers_attached) return fail(MLV_ERR_STATE, "call mlv_composite_peer_attach first");
 	if(dev->bcast_pending) return fail(MLV_ERR_STATE, "mlv_composite_wait must follow every mlv_composite_broadcast");
+	if(dev->xchg_pending) return fail(MLV_ERR_STATE, "mlv_composite_join must follow every mlv_composite_broadcast_async");
 	if(int rc = flush_clears(dev)) return rc;
 	const uint32_t seq = ++dev->p2p_seq;
 	PeerTargets t;
@@ -1115,9 +1163,75 @@ int mlv_composite_broadcast(mlv_device *dev) {
 	}
 	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
 	prof_pre(dev, MLV_STAGE_COMPOSITE);
-	launch_pdl(k_composite_broadcast, (items + 255) / 256, 256, dev->stream, dev->fb, t, dev->W, dev->H, dev->part, seq, dev->ctr);
+	launch_pdl(k_composite_broadcast, (items + 255) / 256, 256, dev->stream, dev->fb, t, dev->W, dev->H, dev->part, seq, dev->ctr, 0, dev->part.num_ranks, 1);
 	dev->bcast_pending = true;
 	return check_launch(dev, "k_composite_broadcast");
+}
+
+// The exchange of frame f off the critical path: broadcast + wait go to the exchange stream, ordered after everything
+// issued so far on the main stream, and the main stream carries on with frame f+1 at once (in the other tiled
+// framebuffer when that frame starts with a full clear, see acquire_framebuffer).
+int mlv_composite_broadcast_async(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	if(!dev->peers_attached) return fail(MLV_ERR_STATE, "call mlv_composite_peer_attach first");
+	if(dev->bcast_pending) return fail(MLV_ERR_STATE, "mlv_composite_wait must follow every mlv_composite_broadcast");
+	if(dev->xchg_pending) return fail(MLV_ERR_STATE, "mlv_composite_join must follow every mlv_composite_broadcast_async");
+	if(int rc = flush_clears(dev)) return rc;
+	const uint32_t seq = ++dev->p2p_seq;
+	PeerTargets t;
+	memset(&t, 0, sizeof(t));
+	for(int p = 0; p < dev->part.num_ranks; ++p) {
+		t.color[p] = dev->peer_color[seq & 1u][p];
+		t.flags[p] = dev->peer_flags[p];
+	}
+	// after the frame's draws -- and after every consumer of the previously joined image issued on the main stream:
+	// peers overwrite that image only once this rank's broadcast of the next frame has run (they wait for it)
+	CUDA_TRY(cudaEventRecord(dev->ev_frame_done, dev->stream));
+	CUDA_TRY(cudaStreamWaitEvent(dev->xchg_stream, dev->ev_frame_done, 0));
+	if(dev->readback_in_flight) CUDA_TRY(cudaStreamWaitEvent(dev->xchg_stream, dev->ev_readback_done, 0));
+	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
+	const int n = dev->part.num_ranks, me = dev->part.rank;
+	const bool band = (uint64_t)dev->part.stripe_h * (uint64_t)n >= (uint64_t)dev->ht; // one contiguous band of rows per rank
+	if(band) {
+		// Copy-engine form: a short kernel resolves this rank's band into its OWN row-major image, the band (one
+		// contiguous range of rows) then travels to every peer by DMA over NVLink -- no SM is busy with the transfer,
+		// which therefore really runs underneath the next frame's kernels -- and a one-warp kernel publishes the
+		// arrival. Peers are visited in ring order so that every image has one writer at a time.
+		launch_pdl(k_composite_broadcast, (items + 255) / 256, 256, dev->xchg_stream, dev->fb, t, dev->W, dev->H, dev->part, seq, dev->ctr, me, me + 1, 0);
+		CUDA_TRY(cudaEventRecord(dev->ev_fb_free[dev->fb_sel], dev->xchg_stream));
+		const uint32_t row_lo = (uint32_t)dev->part.stripe_h * (uint32_t)me;
+		uint32_t row_hi = row_lo + (uint32_t)dev->part.stripe_h;
+		if(row_hi > (uint32_t)dev->ht) row_hi = (uint32_t)dev->ht;
+		if(row_lo < row_hi) {
+			const size_t offset = (size_t)row_lo * 8u * (size_t)dev->W * 4u, bytes = (size_t)(row_hi - row_lo) * 8u * (size_t)dev->W * 4u;
+			for(int k = 1; k < n; ++k) {
+				const int p = (me + k) % n;
+				CUDA_TRY(cudaMemcpyAsync((char *)t.color[p] + offset, (const char *)t.color[me] + offset, bytes, cudaMemcpyDefault, dev->xchg_stream));
+			}
+		}
+		launch_pdl(k_composite_publish, 1, 32, dev->xchg_stream, t, n, me, seq);
+		dev->launches += 1;
+	} else {
+		launch_pdl(k_composite_broadcast, (items + 255) / 256, 256, dev->xchg_stream, dev->fb, t, dev->W, dev->H, dev->part, seq, dev->ctr, 0, n, 1);
+		CUDA_TRY(cudaEventRecord(dev->ev_fb_free[dev->fb_sel], dev->xchg_stream));
+	}
+	dev->fb_busy[dev->fb_sel] = true;
+	launch_pdl(k_composite_wait, 1, 32, dev->xchg_stream, (const uint32_t *)dev->p2p_flags, n, seq, dev->ctr, 10000000000ull);
+	CUDA_TRY(cudaEventRecord(dev->ev_xchg_done, dev->xchg_stream));
+	cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return fail(MLV_ERR_CUDA, "launch of k_composite_broadcast/k_composite_wait failed: %s", cudaGetErrorString(e));
+	dev->launches += 2;
+	dev->xchg_pending = true;
+	return MLV_OK;
+}
+
+int mlv_composite_join(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	if(!dev->xchg_pending) return fail(MLV_ERR_STATE, "no asynchronous broadcast to join");
+	CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_xchg_done, 0));
+	dev->xchg_pending = false;
+	dev->present_color = dev->p2p_color[dev->p2p_seq & 1u];
+	return MLV_OK;
 }
 
 int mlv_composite_wait(mlv_device *dev) {

@@ -378,6 +378,14 @@ class Device:
     def composite_wait(self):
         L.check(self._lib.mlv_composite_wait(self._h))
 
+    def composite_broadcast_async(self):
+        """Broadcast + wait of this frame on the exchange stream; the device carries on with the next frame."""
+        L.check(self._lib.mlv_composite_broadcast_async(self._h))
+
+    def composite_join(self):
+        """The device stream waits for the last composite_broadcast_async; resolved_color_ptr() is that frame."""
+        L.check(self._lib.mlv_composite_join(self._h))
+
     # ---- debug read-back of the last draw ------------------------------------------------------
     def debug_vs_out(self) -> np.ndarray:
         n = C.c_uint32()

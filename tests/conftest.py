@@ -4,6 +4,10 @@ import sys
 
 import pytest
 
+# Multi-rank tests keep several device objects (6 streams each) on ONE GPU; with the default of 8 hardware queues their
+# streams would alias and a rank's bounded spin-wait for a peer could sit in front of that peer's work.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -323,6 +323,70 @@ def test_peer_memory_composite_in_one_process():
                 d.close()
 
 
+def test_async_peer_memory_composite_in_one_process():
+    """mlv_composite_broadcast_async / mlv_composite_join, pipelined the way bench.py runs them: frame f+1 is drawn (into the
+    other tiled framebuffer of the pair) while frame f is still being exchanged; the joined image is always the complete
+    frame f. Two different scenes alternate so that a stale or half-exchanged image cannot pass."""
+    from malevich_b200 import scenes
+    scs = [cases.SMALL["ftm_320x200"](), cases.SMALL["toon_320x200"]()]
+    refs = []
+    for sc in scs:
+        with _device(sc.width, sc.height) as dev:
+            scenes.render(dev, sc)
+            refs.append(dev.present()[0])
+    W, H = scs[0].width, scs[0].height
+    for world, stripe in ((2, 13), (3, 2), (2, 1)):
+        devs = [_device(W, H, num_ranks=world, rank=r, stripe_height_tiles=stripe) for r in range(world)]
+        try:
+            infos = [d.composite_peer_export() for d in devs]
+            for d in devs:
+                d.composite_peer_attach(infos, same_process=True)
+            with pytest.raises(Exception):
+                devs[0].composite_join()  # nothing to join
+            # One host thread drives every rank here, so nothing that synchronises the whole GPU (cudaFree when an arena
+            # grows, a caching-allocator miss) may happen while a rank's wait kernel spins for a peer this thread has not
+            # issued yet: size the arenas and the result buffers first. (One process per GPU has no such coupling.)
+            import torch
+            for d in devs:
+                for sc in scs:
+                    scenes.render(d, sc)
+                d.finish()
+                d._got = torch.empty(W * H * 4, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            frames = 5
+            for f in range(frames + 1):
+                for d in devs:
+                    if f < frames:
+                        scenes.render(d, scs[f % 2])
+                    if f > 0:
+                        d.composite_join()  # exchange of frame f-1
+                        out = _as_tensor(d.resolved_color_ptr(), W * H * 4)
+                        with torch.cuda.stream(torch.cuda.ExternalStream(d.stream)):
+                            d._got.copy_(out)  # consumer on the device stream, issued before the next broadcast
+                    if f < frames:
+                        d.composite_broadcast_async()
+                if f > 0:
+                    for r, d in enumerate(devs):
+                        d.finish()
+                        got = d._got.cpu().numpy().view(np.uint32).reshape(H, W)
+                        assert np.array_equal(got, refs[(f - 1) % 2]), f"world {world} stripe {stripe} frame {f - 1} rank {r}"
+            for d in devs:
+                d.stats()  # surfaces MLV_FLAG_COMPOSITE_TIMEOUT, if any
+            # the synchronous form still works afterwards, and a frame without a full clear waits for the exchange
+            for d in devs:
+                scenes.render(d, scs[0])
+                d.composite_broadcast_async()
+                scenes.render(d, scs[1], clear=False)  # draws on top of frame 0 in the SAME framebuffer
+                d.composite_join()
+            for d in devs:
+                d.finish()
+                out = _as_tensor(d.resolved_color_ptr(), W * H * 4).cpu().numpy().view(np.uint32).reshape(H, W)
+                assert np.array_equal(out, refs[0])
+        finally:
+            for d in devs:
+                d.close()
+
+
 def _ipc_rank(rank, world, conns, result_q):
     """One process = one rank; all ranks share cuda:0 here (on the real machine each has its own GPU)."""
     try:
@@ -354,6 +418,25 @@ def _ipc_rank(rank, world, conns, result_q):
                 import torch
                 out = _as_tensor(dev.resolved_color_ptr(), sc.width * sc.height * 4).cpu().numpy().view(np.uint32).reshape(sc.height, sc.width)
                 ok = ok and bool(np.array_equal(out, ref_col))
+            # the pipelined form: draw frame f+1, join + consume frame f, start the exchange of frame f+1
+            sc2 = cases_.SMALL["ftm_320x200"]()
+            with Device(sc2.width, sc2.height) as single:
+                scenes.render(single, sc2)
+                ref2, _ = single.present()
+            pair, refs2, got = [sc, sc2], [ref_col, ref2], []
+            for frame in range(5):
+                if frame < 4:
+                    scenes.render(dev, pair[frame % 2])
+                if frame > 0:
+                    dev.composite_join()
+                    with torch.cuda.stream(torch.cuda.ExternalStream(dev.stream)):
+                        got.append(_as_tensor(dev.resolved_color_ptr(), sc.width * sc.height * 4).clone())
+                if frame < 4:
+                    dev.composite_broadcast_async()
+            dev.finish()
+            dev.stats()
+            for frame, g in enumerate(got):
+                ok = ok and bool(np.array_equal(g.cpu().numpy().view(np.uint32).reshape(sc.height, sc.width), refs2[frame % 2]))
             for c in conns:  # nobody unmaps while a peer may still be writing
                 c.send("done")
             for c in conns:
