@@ -173,6 +173,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     stripe = args.stripe if args.stripe > 0 else max(1, -(-(scene.height // 8) // world))
     dev = Device(scene.width, scene.height, cuda_device=local_rank, num_ranks=world, rank=rank, stripe_height_tiles=stripe)
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local_rank))
+    def shard_bytes(nbytes: int) -> int:  # equal shards of a buffer, 16-byte granules, for the in-place all-gather of sharded uploads
+        return -(-(-(-nbytes // world)) // 16) * 16
+
+    if multi:  # buffers padded to world x shard so that every rank's shard has the same size
+        from malevich_b200 import _lib as L0
+        for o in scene.objects:
+            for arr, kind in ((o.vertex_buffer, L0.BUFFER_VERTEX), (o.index_buffer, L0.BUFFER_INDEX)):
+                dev.adopt_buffer(arr, kind, shard_bytes(arr.nbytes) * world)
     scenes.upload(dev, scene)
 
     gather = None
@@ -318,7 +326,45 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     colors_host2 = pinned_like(colors_host)
     e2e_step = [0]
 
+    # N > 1: the geometry is replicated, so every byte crosses PCIe ONCE per frame: rank r uploads shard r of every
+    # buffer over its own link, an in-place ncclAllGather on a side stream replicates the shards over NVLink, and the
+    # buffer is marked complete on that stream (draws that bind it wait for exactly that). The composited frame is read
+    # back by rank 0 on the read-back stream, one frame behind (the exchange of frame f overlaps frame f+1).
+    if multi and composite == "p2p":
+        class _RawBuf:
+            def __init__(self, ptr, nbytes):
+                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+        cuda_dev = torch.device("cuda", local_rank)
+        copy_stream = torch.cuda.ExternalStream(dev.copy_stream, device=cuda_dev)
+        ag_stream = torch.cuda.Stream(device=cuda_dev)
+        sharded = []
+        for h, p in host_inputs:
+            sb = shard_bytes(p.nbytes)
+            full = torch.as_tensor(_RawBuf(int(lib.mlv_buffer_device_ptr(h)), sb * world), device=cuda_dev)
+            lo, hi = min(rank * sb, p.nbytes), min((rank + 1) * sb, p.nbytes)
+            sharded.append((h, p.ctypes.data + lo, lo, hi - lo, full, full[rank * sb:(rank + 1) * sb], torch.cuda.Event()))
+
+    def frame_e2e_sharded():
+        for h, host_ptr, lo, n, full, mine, ev in sharded:
+            L.check(lib.mlv_update_buffer_range(dev._h, h, lo, C.c_void_p(host_ptr), n))
+            ev.record(copy_stream)
+            ag_stream.wait_event(ev)
+            with torch.cuda.stream(ag_stream):
+                dist.all_gather_into_tensor(full, mine)
+            L.check(lib.mlv_buffer_mark_updated(dev._h, h, C.c_void_p(ag_stream.cuda_stream)))
+        scenes.render(dev, scene)
+        had = pending[0]
+        drain()  # join the exchange of the previous frame
+        if had and rank == 0:
+            dev.present_wait()
+            dev.composite_readback_async(colors_host if e2e_step[0] % 2 == 0 else colors_host2)
+            e2e_step[0] += 1
+        dev.composite_broadcast_async()
+        pending[0] = True
+
     def frame_e2e():
+        if multi and composite == "p2p":
+            return frame_e2e_sharded()
         for h, p in host_inputs:
             L.check(lib.mlv_update_buffer(dev._h, h, p.ctypes.data_as(C.c_void_p), p.nbytes))
         if multi:
@@ -349,8 +395,22 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         frame_e2e()
+    if multi and composite == "p2p":  # deliver the last frame too: K steps = K frames uploaded, drawn, exchanged and read back
+        drain()
+        if rank == 0:
+            dev.present_wait()
+            dev.composite_readback_async(colors_host if e2e_step[0] % 2 == 0 else colors_host2)
+            last_e2e_image = colors_host if e2e_step[0] % 2 == 0 else colors_host2
     barrier()
     e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3 / args.steps)
+    e2e_check = None
+    if multi and composite == "p2p":
+        frame()   # every rank takes part in the exchange
+        barrier()
+    if multi and composite == "p2p" and rank == 0:
+        # the frame delivered end to end (sharded uploads, asynchronous exchange) is the frame the resident path renders
+        ref_img = torch.as_tensor(_RawBuf(dev.resolved_color_ptr(), scene.width * scene.height * 4), device=cuda_dev).cpu().numpy().view(np.uint32).reshape(scene.height, scene.width)
+        e2e_check = bool(np.array_equal(ref_img, last_e2e_image))
     tex_bytes = sum(p.nbytes for _, p in tex_seen.values())
 
     if rank == 0:
@@ -391,7 +451,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                "frac": b_alg / (ms * 1e-3) / 1e9 / world / peak, "bytes_by_stage": b_stage},
             "stage_ms_per_step": {k: round(v, 4) for k, v in stage_ms.items()},
             "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d - tex_bytes), "d2h_bytes_per_step": int(d2h),
-                    "note": "every vertex/index buffer + constant buffer re-uploaded from pinned host memory each frame; framebuffer read back to pinned host memory each frame (double-buffered: the host collects frame f-1 while frame f is queued); textures stay resident"},
+                    "note": ("every vertex/index buffer + constant buffer re-uploaded from pinned host memory each frame; framebuffer read back to pinned host memory each frame (double-buffered: the host collects frame f-1 while frame f is queued); textures stay resident"
+                             if not (multi and composite == "p2p") else
+                             "whole job: every vertex/index buffer crosses PCIe once per frame -- rank r uploads shard r of each buffer from pinned host memory, an in-place ncclAllGather replicates it over NVLink -- and rank 0 reads the composited frame back to pinned host memory (one frame behind: the exchange of frame f overlaps frame f+1); textures stay resident"),
+                    **({"image_matches_resident_path": e2e_check} if e2e_check is not None else {})},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if not multi and not args.no_cpu_baseline:

@@ -122,6 +122,16 @@ MLV_API int mlv_create_buffer(mlv_device *dev, const void *data, size_t bytes, i
  * valid until mlv_finish / mlv_present_readback returns when it points to page-locked memory. */
 MLV_API int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t bytes);
 MLV_API void mlv_release_buffer(mlv_device *dev, mlv_buffer *buf);
+/* Sharded uploads for replicated geometry (sort-first): every rank holds the same host buffers, so rank r
+ * uploads only bytes [offset, offset + bytes) over its own PCIe link (mlv_update_buffer_range), the ranks exchange the
+ * shards in place over NVLink (the caller's collective, e.g. ncclAllGather on mlv_buffer_device_ptr, ordered after the
+ * upload on mlv_get_copy_stream) and mlv_buffer_mark_updated tells the library on which stream the buffer becomes
+ * complete: later draws that bind it wait for that point. Create the buffer with mlv_create_buffer(dev, NULL, capacity,
+ * kind) when the collective wants a padded size. */
+MLV_API int mlv_update_buffer_range(mlv_device *dev, mlv_buffer *buf, size_t offset, const void *data, size_t bytes);
+MLV_API void *mlv_buffer_device_ptr(mlv_buffer *buf);
+MLV_API void *mlv_get_copy_stream(mlv_device *dev);
+MLV_API int mlv_buffer_mark_updated(mlv_device *dev, mlv_buffer *buf, void *cuda_stream /* NULL = the copy stream */);
 MLV_API int mlv_create_texture2d(mlv_device *dev, const void *texels, uint32_t width, uint32_t height, int format, mlv_texture **out);
 MLV_API void mlv_release_texture(mlv_device *dev, mlv_texture *tex);
 /* load_texture's `is_in_srgb` branch (main.c:546-558): every channel of every texel of an R8G8B8A8 texture -- alpha
@@ -217,6 +227,9 @@ MLV_API int mlv_composite_wait(mlv_device *dev);
  * whose frame time is a rank's own rendering time: the NVLink transfer and the wait for the slowest rank overlap the next
  * frame's geometry. */
 MLV_API int mlv_composite_broadcast_async(mlv_device *dev);
+/* Device-to-host copy of the composited image on the read-back stream (like mlv_present_readback_async, which reads this
+ * rank's own tiles); completed by mlv_present_wait / mlv_finish. Call it after mlv_composite_wait / mlv_composite_join. */
+MLV_API int mlv_composite_readback_async(mlv_device *dev, uint32_t *colors);
 MLV_API int mlv_composite_join(mlv_device *dev);
 
 /* ---- debug read-back of the last draw (needs MLV_DEVICE_DEBUG_CAPTURE). Each synchronises.

@@ -10,14 +10,14 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmalevich_b200.so")
 # every symbol include/malevich_b200.h declares (tests check the library exports each of them)
 EXPORTED_SYMBOLS = [
     "mlv_last_error_string", "mlv_create_device", "mlv_destroy_device", "mlv_finish", "mlv_get_stream",
-    "mlv_create_buffer", "mlv_update_buffer", "mlv_release_buffer", "mlv_create_texture2d", "mlv_release_texture", "mlv_texture_srgb_to_linear", "mlv_read_texture",
+    "mlv_create_buffer", "mlv_update_buffer", "mlv_update_buffer_range", "mlv_buffer_device_ptr", "mlv_get_copy_stream", "mlv_buffer_mark_updated", "mlv_release_buffer", "mlv_create_texture2d", "mlv_release_texture", "mlv_texture_srgb_to_linear", "mlv_read_texture",
     "mlv_ia_set_vertex_buffer", "mlv_ia_set_index_buffer", "mlv_ia_set_index_format", "mlv_ia_set_input_layout", "mlv_ia_set_primitive_topology",
     "mlv_vs_set_shader", "mlv_vs_set_constant_buffer", "mlv_vs_set_shader_resource", "mlv_rs_set_viewport",
     "mlv_ps_set_shader", "mlv_ps_set_shader_resource",
     "mlv_clear_render_target_view", "mlv_clear_depth_stencil_view", "mlv_draw_indexed", "mlv_draw_indexed_ex", "mlv_draw",
     "mlv_present_readback", "mlv_present_readback_async", "mlv_present_wait", "mlv_get_stats", "mlv_reset_stats",
     "mlv_resolve", "mlv_resolved_color_device_ptr", "mlv_resolved_depth_device_ptr",
-    "mlv_composite_peer_export", "mlv_composite_peer_attach", "mlv_composite_broadcast", "mlv_composite_wait", "mlv_composite_broadcast_async", "mlv_composite_join", "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
+    "mlv_composite_peer_export", "mlv_composite_peer_attach", "mlv_composite_broadcast", "mlv_composite_wait", "mlv_composite_broadcast_async", "mlv_composite_join", "mlv_composite_readback_async", "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
     "mlv_debug_read_vs_out", "mlv_debug_read_triangles", "mlv_debug_read_bins", "mlv_debug_read_masks",
     "mlv_debug_read_tile_min_depths", "mlv_profile_begin", "mlv_profile_end", "mlv_kernel_launch_count",
 ]
@@ -87,6 +87,10 @@ def load() -> C.CDLL:
         "mlv_get_stream": (vp, [vp]),
         "mlv_create_buffer": (i32, [vp, vp, sz, i32, P(vp)]),
         "mlv_update_buffer": (i32, [vp, vp, vp, sz]),
+        "mlv_update_buffer_range": (i32, [vp, vp, sz, vp, sz]),
+        "mlv_buffer_device_ptr": (vp, [vp]),
+        "mlv_get_copy_stream": (vp, [vp]),
+        "mlv_buffer_mark_updated": (i32, [vp, vp, vp]),
         "mlv_release_buffer": (None, [vp, vp]),
         "mlv_create_texture2d": (i32, [vp, vp, u32, u32, i32, P(vp)]),
         "mlv_release_texture": (None, [vp, vp]),
@@ -123,6 +127,7 @@ def load() -> C.CDLL:
         "mlv_composite_wait": (i32, [vp]),
         "mlv_composite_broadcast_async": (i32, [vp]),
         "mlv_composite_join": (i32, [vp]),
+        "mlv_composite_readback_async": (i32, [vp, vp]),
         "mlv_composite_pack": (i32, [vp]),
         "mlv_composite_unpack": (i32, [vp]),
         "mlv_debug_read_vs_out": (i32, [vp, vp, P(u32)]),

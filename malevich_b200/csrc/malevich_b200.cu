@@ -419,6 +419,29 @@ int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t
 	return MLV_OK;
 }
 
+int mlv_update_buffer_range(mlv_device *dev, mlv_buffer *buf, size_t offset, const void *data, size_t bytes) {
+	if(int rc = use_device(dev)) return rc;
+	if(!buf || !data || offset > buf->bytes || bytes > buf->bytes - offset) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer range update");
+	if(dev->last_draw_recorded) CUDA_TRY(cudaStreamWaitEvent(dev->copy_stream, dev->ev_last_draw, 0));
+	if(bytes) CUDA_TRY(cudaMemcpyAsync((char *)buf->d + offset, data, bytes, cudaMemcpyHostToDevice, dev->copy_stream));
+	CUDA_TRY(cudaEventRecord(buf->ready, dev->copy_stream));
+	buf->ready_pending = true;
+	buf->version++;
+	return MLV_OK;
+}
+
+void *mlv_buffer_device_ptr(mlv_buffer *buf) { return buf ? buf->d : nullptr; }
+void *mlv_get_copy_stream(mlv_device *dev) { return dev ? (void *)dev->copy_stream : nullptr; }
+
+int mlv_buffer_mark_updated(mlv_device *dev, mlv_buffer *buf, void *stream) {
+	if(int rc = use_device(dev)) return rc;
+	if(!buf) return fail(MLV_ERR_INVALID_ARGUMENT, "null buffer");
+	CUDA_TRY(cudaEventRecord(buf->ready, stream ? (cudaStream_t)stream : dev->copy_stream));
+	buf->ready_pending = true;
+	buf->version++;
+	return MLV_OK;
+}
+
 void mlv_release_buffer(mlv_device *dev, mlv_buffer *buf) {
 	if(!dev || !buf) return;
 	cudaSetDevice(dev->cuda_dev);
@@ -1231,6 +1254,20 @@ int mlv_composite_join(mlv_device *dev) {
 	CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_xchg_done, 0));
 	dev->xchg_pending = false;
 	dev->present_color = dev->p2p_color[dev->p2p_seq & 1u];
+	return MLV_OK;
+}
+
+// Read-back of the composited image (the one mlv_composite_wait / mlv_composite_join handed out) on the read-back stream.
+int mlv_composite_readback_async(mlv_device *dev, uint32_t *colors) {
+	if(int rc = use_device(dev)) return rc;
+	if(!colors) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	if(dev->part.num_ranks <= 1) return fail(MLV_ERR_STATE, "device was created with a single rank");
+	if(dev->bcast_pending || dev->xchg_pending) return fail(MLV_ERR_STATE, "call mlv_composite_wait / mlv_composite_join first");
+	CUDA_TRY(cudaEventRecord(dev->ev_resolved, dev->stream)); // after the wait / join
+	CUDA_TRY(cudaStreamWaitEvent(dev->readback_stream, dev->ev_resolved, 0));
+	CUDA_TRY(cudaMemcpyAsync(colors, dev->present_color, (size_t)dev->W * dev->H * 4, cudaMemcpyDeviceToHost, dev->readback_stream));
+	CUDA_TRY(cudaEventRecord(dev->ev_readback_done, dev->readback_stream));
+	dev->readback_in_flight = true;
 	return MLV_OK;
 }
 

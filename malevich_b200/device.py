@@ -168,6 +168,24 @@ class Device:
         self._buffers[key] = (arr, h)
         return h
 
+    def adopt_buffer(self, arr: np.ndarray, kind: int, capacity_bytes: int):
+        """Device copy of `arr` in an allocation of `capacity_bytes` >= arr.nbytes (a padded size for in-place collectives
+        over the buffer, see mlv_update_buffer_range). Later draws that bind `arr` use it."""
+        a = np.ascontiguousarray(arr)
+        h = C.c_void_p()
+        L.check(self._lib.mlv_create_buffer(self._h, None, max(int(capacity_bytes), a.nbytes), kind, C.byref(h)))
+        L.check(self._lib.mlv_update_buffer(self._h, h, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        self._buffers[(id(arr), kind)] = (arr, h)
+        return h
+
+    @property
+    def copy_stream(self) -> int:
+        return int(self._lib.mlv_get_copy_stream(self._h) or 0)
+
+    def composite_readback_async(self, colors: np.ndarray):
+        """Non-blocking read-back of the composited image (after composite_wait / composite_join) into a page-locked array."""
+        L.check(self._lib.mlv_composite_readback_async(self._h, colors.ctypes.data_as(C.c_void_p)))
+
     def _texture(self, tex: Texture2D):
         hit = self._textures.get(id(tex))
         if hit is not None and hit[0] is tex:
