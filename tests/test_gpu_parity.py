@@ -476,6 +476,68 @@ def _as_tensor(ptr, nbytes):
     return torch.as_tensor(_Raw(), device="cuda")
 
 
+def test_range_uploads_marked_on_a_caller_stream_and_composite_readback():
+    """The sharded-upload entry points of the sort-first path, on one GPU: a buffer created with a padded capacity and
+    filled by mlv_update_buffer_range in three pieces, declared complete on a caller's stream with
+    mlv_buffer_mark_updated, draws the same frame; mlv_composite_readback_async delivers the composited image."""
+    import ctypes as C
+    import torch
+    from malevich_b200 import _lib as L, scenes
+    lib = L.load()
+    sc = cases.SMALL["toon_320x200"]()
+    with _device(sc.width, sc.height) as dev:
+        scenes.render(dev, sc)
+        ref_col, ref_dep = dev.present()
+    with _device(sc.width, sc.height) as dev:
+        side = torch.cuda.Stream()
+        keep = []
+        for o in sc.objects:
+            for arr, kind in ((o.vertex_buffer, L.BUFFER_VERTEX), (o.index_buffer, L.BUFFER_INDEX)):
+                h = C.c_void_p()
+                L.check(lib.mlv_create_buffer(dev._h, None, arr.nbytes + 4096, kind, C.byref(h)))  # capacity only, no contents
+                dev._buffers[(id(arr), kind)] = (arr, h)
+                raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+                keep.append(raw)
+                cuts = [0, raw.nbytes // 3 // 16 * 16, raw.nbytes // 2 // 16 * 16, raw.nbytes]
+                for lo, hi in zip(cuts[:-1], cuts[1:]):
+                    L.check(lib.mlv_update_buffer_range(dev._h, h, lo, C.c_void_p(raw.ctypes.data + lo), hi - lo))
+                assert int(lib.mlv_buffer_device_ptr(h)) != 0
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.ExternalStream(dev.copy_stream))
+                side.wait_event(ev)
+                L.check(lib.mlv_buffer_mark_updated(dev._h, h, C.c_void_p(side.cuda_stream)))
+                assert lib.mlv_update_buffer_range(dev._h, h, arr.nbytes + 4096 - 8, C.c_void_p(raw.ctypes.data), 16) == L.MLV_ERR_INVALID_ARGUMENT
+        scenes.render(dev, sc)
+        col, dep = dev.present()
+        assert np.array_equal(col, ref_col) and np.array_equal(dep, ref_dep)
+        with pytest.raises(Exception):
+            dev.composite_readback_async(col)  # single-rank device
+    devs = [_device(sc.width, sc.height, num_ranks=2, rank=r, stripe_height_tiles=13) for r in range(2)]
+    try:
+        infos = [d.composite_peer_export() for d in devs]
+        for d in devs:
+            d.composite_peer_attach(infos, same_process=True)
+        for d in devs:
+            scenes.render(d, sc)
+            d.finish()
+        out = [torch.empty(sc.width * sc.height, dtype=torch.int32, pin_memory=True) for _ in devs]
+        for d in devs:
+            scenes.render(d, sc)
+            d.composite_broadcast()
+        for d in devs:
+            d.finish()
+        for d, o in zip(devs, out):
+            with pytest.raises(Exception):
+                d.composite_readback_async(o.numpy())  # exchange not complete yet
+            d.composite_wait()
+            d.composite_readback_async(o.numpy())
+            d.present_wait()
+            assert np.array_equal(o.numpy().view(np.uint32).reshape(sc.height, sc.width), ref_col)
+    finally:
+        for d in devs:
+            d.close()
+
+
 def test_async_present_and_streamed_uploads_match_blocking_present():
     """mlv_present_readback_async + mlv_present_wait deliver the image mlv_present_readback does, also when every buffer
     is re-uploaded before every frame (uploads on the copy stream, read-back on its own stream, two frames in flight)."""
