@@ -49,7 +49,9 @@ enum { MLV_VS_PASSTHROUGH = 0,     /* passthrough_vs.c:16-25 */
 enum { MLV_PS_PASSTHROUGH = 0,  /* passthrough_ps.c:13-20 */
        MLV_PS_BASIC = 1,        /* basic_ps.c:16-27 */
        MLV_PS_ENV_LIGHTING = 2, /* env_lighting_ps.c:13-24 */
-       MLV_PS_COUNT = 3 };
+       MLV_PS_BASIC_TRILINEAR = 3, /* EXTENSION: basic_ps.c:16-27 with SRV0 sampled trilinearly from the mip chain
+                                    * mlv_texture_generate_mips built; the reference samples level 0 only (common_shader_core.h:195-199) */
+       MLV_PS_COUNT = 4 };
 /* Texture2D, common_shader_core.h:20-24: the reference infers the texel type from the sampler used
  * (get_texel_u_x8 :30 vs get_texel_f_x8 :42); here it is explicit. */
 enum { MLV_FORMAT_R8G8B8A8_UNORM = 0, MLV_FORMAT_R32G32B32A32_FLOAT = 1 };
@@ -138,6 +140,13 @@ MLV_API void mlv_release_texture(mlv_device *dev, mlv_texture *tex);
  * included -- goes through decode_u32_as_color (math.h:326-334), srgb_to_linear (math.h:386-395, double arithmetic)
  * and encode_color_as_u32 (math.h:322-324, truncation), in place, on the device. */
 MLV_API int mlv_texture_srgb_to_linear(mlv_device *dev, mlv_texture *tex);
+/* EXTENSION (the reference has no mips): builds the full mip chain of an R8G8B8A8 texture on the device, level
+ * l = max(1, extent >> l), each level a 2x2 box filter of the one above per channel ((a+b+c+d+2)>>2; an odd extent repeats its
+ * last row / column). Call it after mlv_texture_srgb_to_linear so that the filter works on linear values. Without a chain
+ * MLV_PS_BASIC_TRILINEAR samples level 0 only and equals MLV_PS_BASIC. */
+MLV_API int mlv_texture_generate_mips(mlv_device *dev, mlv_texture *tex);
+MLV_API int mlv_texture_mip_levels(const mlv_texture *tex, uint32_t *out_levels); /* 1 = level 0 only */
+MLV_API int mlv_read_texture_mip(mlv_device *dev, const mlv_texture *tex, uint32_t level, void *out_texels); /* synchronises */
 /* copies the texels back (R8G8B8A8: 4 bytes, R32G32B32A32_FLOAT: 16 bytes per texel); synchronises */
 MLV_API int mlv_read_texture(mlv_device *dev, const mlv_texture *tex, void *out_texels);
 

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmalevich_b200.so")
 # every symbol include/malevich_b200.h declares (tests check the library exports each of them)
 EXPORTED_SYMBOLS = [
     "mlv_last_error_string", "mlv_create_device", "mlv_destroy_device", "mlv_finish", "mlv_get_stream",
-    "mlv_create_buffer", "mlv_update_buffer", "mlv_update_buffer_range", "mlv_buffer_device_ptr", "mlv_get_copy_stream", "mlv_buffer_mark_updated", "mlv_release_buffer", "mlv_create_texture2d", "mlv_release_texture", "mlv_texture_srgb_to_linear", "mlv_read_texture",
+    "mlv_create_buffer", "mlv_update_buffer", "mlv_update_buffer_range", "mlv_buffer_device_ptr", "mlv_get_copy_stream", "mlv_buffer_mark_updated", "mlv_release_buffer", "mlv_create_texture2d", "mlv_release_texture", "mlv_texture_srgb_to_linear", "mlv_texture_generate_mips", "mlv_texture_mip_levels", "mlv_read_texture_mip", "mlv_read_texture",
     "mlv_ia_set_vertex_buffer", "mlv_ia_set_index_buffer", "mlv_ia_set_index_format", "mlv_ia_set_input_layout", "mlv_ia_set_primitive_topology",
     "mlv_vs_set_shader", "mlv_vs_set_constant_buffer", "mlv_vs_set_shader_resource", "mlv_rs_set_viewport",
     "mlv_ps_set_shader", "mlv_ps_set_shader_resource",
@@ -27,7 +27,7 @@ MLV_OK = 0
 MLV_ERR_INVALID_ARGUMENT, MLV_ERR_CUDA, MLV_ERR_OUT_OF_MEMORY, MLV_ERR_CAPACITY, MLV_ERR_STATE = 1, 2, 3, 4, 5
 PRIMITIVE_TOPOLOGY_UNDEFINED, PRIMITIVE_TOPOLOGY_TRIANGLELIST = 0, 1
 VS_PASSTHROUGH, VS_BASIC, VS_VERTEX_LIGHTING, VS_FULLSCREEN = 0, 1, 2, 3
-PS_PASSTHROUGH, PS_BASIC, PS_ENV_LIGHTING = 0, 1, 2
+PS_PASSTHROUGH, PS_BASIC, PS_ENV_LIGHTING, PS_BASIC_TRILINEAR = 0, 1, 2, 3
 FORMAT_R8G8B8A8_UNORM, FORMAT_R32G32B32A32_FLOAT = 0, 1
 BUFFER_VERTEX, BUFFER_INDEX = 0, 1
 INDEX_U32, INDEX_U16 = 0, 1
@@ -96,6 +96,9 @@ def load() -> C.CDLL:
         "mlv_release_texture": (None, [vp, vp]),
         "mlv_texture_srgb_to_linear": (i32, [vp, vp]),
         "mlv_read_texture": (i32, [vp, vp, vp]),
+        "mlv_texture_generate_mips": (i32, [vp, vp]),
+        "mlv_texture_mip_levels": (i32, [vp, P(u32)]),
+        "mlv_read_texture_mip": (i32, [vp, vp, u32, vp]),
         "mlv_ia_set_vertex_buffer": (i32, [vp, vp]),
         "mlv_ia_set_index_buffer": (i32, [vp, vp]),
         "mlv_ia_set_index_format": (i32, [vp, i32]),

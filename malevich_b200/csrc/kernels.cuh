@@ -1242,6 +1242,21 @@ __device__ __forceinline__ uint32_t slot_of_key(const TileParams &P, uint32_t ke
 	return (c2.z == MLV_REDIRECT) ? (P.direct_slots + c2.x + (key & 7u)) : t;
 }
 
+// perspective-correct barycentrics of the pixel whose edge functions are E1, E2 (main.c:1089-1115)
+__device__ __forceinline__ void perspective_barycentrics(uint32_t E1, uint32_t E2, float ooa, const float4 &s1, float &pbx, float &pby) {
+	float bx, by;
+	barycentrics(E1, E2, ooa, bx, by);
+	float denom = 1.0f - (bx + by);
+	denom = denom * s1.x;
+	denom = denom + bx * s1.y;
+	denom = denom + by * s1.z;
+	denom = 1.0f / denom;
+	pbx = (bx * s1.y) * denom;
+	pby = (by * s1.z) * denom;
+}
+
+#define MLV_PS_ID_BASIC_TRILINEAR 3
+
 template <int PS>
 __device__ __forceinline__ uint32_t shade_pixel(const TileParams &P, uint32_t key, uint32_t X, uint32_t Y) {
 	const uint32_t slot = slot_of_key(P, key);
@@ -1252,20 +1267,22 @@ __device__ __forceinline__ uint32_t shade_pixel(const TileParams &P, uint32_t ke
 	const uint32_t E2 = c1.z * X + c1.w * Y + c2x;
 	const float4 *sh = reinterpret_cast<const float4 *>(P.tri_shade + (size_t)slot * MLV_TRI_SHADE_U4);
 	const float4 s0 = __ldg(sh), s1 = __ldg(sh + 1), r1a = __ldg(sh + 2), r1b = __ldg(sh + 3), r1c = __ldg(sh + 4), s5 = __ldg(sh + 5);
-	float bx, by;
-	barycentrics(E1, E2, s0.x, bx, by);
-	// perspective correction (main.c:1106-1115)
-	float denom = 1.0f - (bx + by);
-	denom = denom * s1.x;
-	denom = denom + bx * s1.y;
-	denom = denom + by * s1.z;
-	denom = 1.0f / denom;
-	const float pbx = (bx * s1.y) * denom;
-	const float pby = (by * s1.z) * denom;
+	float pbx, pby;
+	perspective_barycentrics(E1, E2, s0.x, s1, pbx, pby);
+	if(PS == MLV_PS_ID_BASIC_TRILINEAR) {
+		// Screen-space derivatives of UV, analytically: the same triangle's interpolation one pixel to the right
+		// (E + 16a) and one pixel down (E + 16b) -- exact plane extrapolation, also outside the triangle.
+		float qx, qy, rx, ry;
+		perspective_barycentrics(E1 + (c0.w << 4), E2 + (c1.z << 4), s0.x, s1, qx, qy);
+		perspective_barycentrics(E1 + (c1.x << 4), E2 + (c1.w << 4), s0.x, s1, rx, ry);
+		const float u = interp(r1a.w, r1b.w, r1c.w, pbx, pby), v = interp(s1.w, s5.x, s5.y, pbx, pby);
+		return encode_color(run_ps_basic_trilinear(u, v, interp(r1a.w, r1b.w, r1c.w, qx, qy), interp(s1.w, s5.x, s5.y, qx, qy), interp(r1a.w, r1b.w, r1c.w, rx, ry),
+		                                           interp(s1.w, s5.x, s5.y, rx, ry), P.ps_tex));
+	}
 	const float4 r1 = make_float4(interp(r1a.x, r1b.x, r1c.x, pbx, pby), interp(r1a.y, r1b.y, r1c.y, pbx, pby), interp(r1a.z, r1b.z, r1c.z, pbx, pby),
 	                              interp(r1a.w, r1b.w, r1c.w, pbx, pby));
 	const float r2x = interp(s1.w, s5.x, s5.y, pbx, pby);
-	return encode_color(run_ps<PS>(r1, r2x, P.ps_tex, P.rsqrt_lut));
+	return encode_color(run_ps<(PS == MLV_PS_ID_BASIC_TRILINEAR ? 1 : PS)>(r1, r2x, P.ps_tex, P.rsqrt_lut));
 }
 
 #define MLV_TILE_THREADS 256
@@ -1441,6 +1458,22 @@ __global__ void __launch_bounds__(256) k_texture_srgb_to_linear(uint4 *__restric
 		texels[i] = v;
 	}
 	if(blockIdx.x == 0 && threadIdx.x < tail_count) tail[threadIdx.x] = conv(tail[threadIdx.x]);
+}
+
+// One level of the mip chain of an R8G8B8A8 texture (mlv_texture_generate_mips): 2x2 box filter per channel with
+// round-to-nearest ((a+b+c+d+2)>>2); an odd source extent repeats its last row / column. One thread per destination texel.
+__global__ void __launch_bounds__(256) k_mip_downsample(const uint32_t *__restrict__ src, int sw, int sh, uint32_t *__restrict__ dst, int dw, int dh) {
+	pdl_prologue();
+	const size_t n = (size_t)dw * (size_t)dh;
+	for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const int x = (int)(i % (size_t)dw), y = (int)(i / (size_t)dw);
+		const int x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1), y0 = min(2 * y, sh - 1), y1 = min(2 * y + 1, sh - 1);
+		const uint32_t a = __ldg(src + (size_t)y0 * sw + x0), b = __ldg(src + (size_t)y0 * sw + x1), c = __ldg(src + (size_t)y1 * sw + x0), d = __ldg(src + (size_t)y1 * sw + x1);
+		uint32_t out = 0;
+#pragma unroll
+		for(int sft = 0; sft < 32; sft += 8) out |= ((((a >> sft) & 0xffu) + ((b >> sft) & 0xffu) + ((c >> sft) & 0xffu) + ((d >> sft) & 0xffu) + 2u) >> 2) << sft;
+		dst[i] = out;
+	}
 }
 
 // Tiled -> row-major. One thread per 4 horizontally adjacent pixels of rows y and y+4 of a tile: four 128-bit

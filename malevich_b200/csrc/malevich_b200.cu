@@ -58,6 +58,8 @@ struct mlv_texture {
 	void *d;
 	uint32_t width, height;
 	int format;
+	void *mips;          // levels 1 .. mip_levels-1 (mlv_texture_generate_mips), null = level 0 only
+	uint32_t mip_levels; // including level 0
 };
 
 struct mlv_device {
@@ -465,6 +467,8 @@ int mlv_create_texture2d(mlv_device *dev, const void *texels, uint32_t width, ui
 	t->width = width;
 	t->height = height;
 	t->format = format;
+	t->mips = nullptr;
+	t->mip_levels = 1;
 	const size_t bytes = (size_t)width * height * (format == MLV_FORMAT_R8G8B8A8_UNORM ? 4 : 16);
 	cudaError_t e = cudaMalloc(&t->d, bytes);
 	if(e == cudaSuccess) e = cudaMemcpyAsync(t->d, texels, bytes, cudaMemcpyHostToDevice, dev->stream);
@@ -499,6 +503,62 @@ int mlv_texture_srgb_to_linear(mlv_device *dev, mlv_texture *tex) {
 	return check_launch(dev, "k_texture_srgb_to_linear");
 }
 
+static uint32_t mip_extent_host(uint32_t e, uint32_t level) {
+	const uint32_t v = e >> level;
+	return v ? v : 1u;
+}
+
+int mlv_texture_generate_mips(mlv_device *dev, mlv_texture *tex) {
+	if(int rc = use_device(dev)) return rc;
+	if(!tex || tex->format != MLV_FORMAT_R8G8B8A8_UNORM) return fail(MLV_ERR_INVALID_ARGUMENT, "mip chains are built for R8G8B8A8 textures");
+	uint32_t levels = 1;
+	size_t texels = 0;
+	while(mip_extent_host(tex->width, levels - 1) > 1u || mip_extent_host(tex->height, levels - 1) > 1u) {
+		texels += (size_t)mip_extent_host(tex->width, levels) * mip_extent_host(tex->height, levels);
+		++levels;
+	}
+	if(levels == 1) return MLV_OK; // a 1x1 texture is its own chain
+	if(!tex->mips) {
+		cudaError_t e = cudaMalloc(&tex->mips, texels * 4);
+		if(e != cudaSuccess) {
+			tex->mips = nullptr;
+			return fail(MLV_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu): %s", texels * 4, cudaGetErrorString(e));
+		}
+	}
+	tex->mip_levels = levels;
+	const uint32_t *src = (const uint32_t *)tex->d;
+	uint32_t *dst = (uint32_t *)tex->mips;
+	for(uint32_t l = 1; l < levels; ++l) {
+		const uint32_t sw = mip_extent_host(tex->width, l - 1), sh = mip_extent_host(tex->height, l - 1), dw = mip_extent_host(tex->width, l), dh = mip_extent_host(tex->height, l);
+		size_t blocks = ((size_t)dw * dh + 255) / 256;
+		if(blocks > 148u * 8u) blocks = 148u * 8u;
+		launch_pdl(k_mip_downsample, (uint32_t)blocks, 256, dev->stream, src, (int)sw, (int)sh, dst, (int)dw, (int)dh);
+		if(int rc = check_launch(dev, "k_mip_downsample")) return rc;
+		src = dst;
+		dst += (size_t)dw * dh;
+	}
+	return MLV_OK;
+}
+
+int mlv_texture_mip_levels(const mlv_texture *tex, uint32_t *out_levels) {
+	if(!tex || !out_levels) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	*out_levels = tex->mips ? tex->mip_levels : 1u;
+	return MLV_OK;
+}
+
+int mlv_read_texture_mip(mlv_device *dev, const mlv_texture *tex, uint32_t level, void *out_texels) {
+	if(int rc = use_device(dev)) return rc;
+	if(!tex || !out_texels) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	if(level == 0) return mlv_read_texture(dev, tex, out_texels);
+	if(!tex->mips || level >= tex->mip_levels) return fail(MLV_ERR_INVALID_ARGUMENT, "texture has no mip level %u", level);
+	size_t offset = 0;
+	for(uint32_t l = 1; l < level; ++l) offset += (size_t)mip_extent_host(tex->width, l) * mip_extent_host(tex->height, l);
+	const size_t bytes = (size_t)mip_extent_host(tex->width, level) * mip_extent_host(tex->height, level) * 4;
+	CUDA_TRY(cudaMemcpyAsync(out_texels, (const uint32_t *)tex->mips + offset, bytes, cudaMemcpyDeviceToHost, dev->stream));
+	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	return MLV_OK;
+}
+
 int mlv_read_texture(mlv_device *dev, const mlv_texture *tex, void *out_texels) {
 	if(int rc = use_device(dev)) return rc;
 	if(!tex || !out_texels) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
@@ -517,6 +577,7 @@ void mlv_release_texture(mlv_device *dev, mlv_texture *tex) {
 		if(dev->ps_srv[i] == tex) dev->ps_srv[i] = nullptr;
 	}
 	cudaFree(tex->d);
+	if(tex->mips) cudaFree(tex->mips);
 	delete tex;
 }
 
@@ -654,6 +715,8 @@ static TexDesc tex_desc(const mlv_texture *t) {
 	d.width = t ? (int)t->width : 0;
 	d.height = t ? (int)t->height : 0;
 	d.format = t ? t->format : 0;
+	d.mips = t ? t->mips : nullptr;
+	d.mip_levels = (t && t->mips) ? (int)t->mip_levels : 1;
 	return d;
 }
 
@@ -718,7 +781,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	if(dev->vs_id != MLV_VS_PASSTHROUGH && dev->cb_bytes[0] < 192) return fail(MLV_ERR_STATE, "constant buffer slot 0 must hold the 192-byte PerFrameCB (main.c:169-173)");
 	if(dev->vs_id == MLV_VS_VERTEX_LIGHTING && !(dev->vs_srv[0] && dev->vs_srv[0]->format == MLV_FORMAT_R32G32B32A32_FLOAT))
 		return fail(MLV_ERR_STATE, "vertex_lighting_vs needs an RGBA32F panorama in VS resource slot 0");
-	if(dev->ps_id == MLV_PS_BASIC && !(dev->ps_srv[0] && dev->ps_srv[0]->format == MLV_FORMAT_R8G8B8A8_UNORM))
+	if((dev->ps_id == MLV_PS_BASIC || dev->ps_id == MLV_PS_BASIC_TRILINEAR) && !(dev->ps_srv[0] && dev->ps_srv[0]->format == MLV_FORMAT_R8G8B8A8_UNORM))
 		return fail(MLV_ERR_STATE, "basic_ps needs an R8G8B8A8 texture in PS resource slot 0");
 	if(dev->ps_id == MLV_PS_ENV_LIGHTING && !(dev->ps_srv[0] && dev->ps_srv[0]->format == MLV_FORMAT_R32G32B32A32_FLOAT))
 		return fail(MLV_ERR_STATE, "env_lighting_ps needs an RGBA32F panorama in PS resource slot 0");
@@ -966,6 +1029,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	switch(dev->ps_id) {
 		case MLV_PS_PASSTHROUGH: launch_pdl(k_tile<0>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
 		case MLV_PS_BASIC: launch_pdl(k_tile<1>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
+		case MLV_PS_BASIC_TRILINEAR: launch_pdl(k_tile<MLV_PS_ID_BASIC_TRILINEAR>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
 		default: launch_pdl(k_tile<2>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
 	}
 	if(int rc = check_launch(dev, "k_tile")) return rc;

@@ -18,6 +18,8 @@ struct TexDesc {
 	int width;
 	int height;
 	int format;
+	const void *mips; // levels 1 .. mip_levels-1, tightly packed one after the other (mlv_texture_generate_mips); null = none
+	int mip_levels;   // including level 0; 1 = no mip chain
 };
 
 // VS output registers actually consumed downstream: r0 = SV_POSITION, r1 = (NORMAL|COLOR|VIEW_DIR).xyz + UV.x,
@@ -149,6 +151,41 @@ __device__ __forceinline__ float4 bilinear_f(const TexDesc &tex, float u, float 
 	const float4 t11 = __ldg(p + t1 * tex.width + s1);
 	const float4 t0111 = lerp4(t01, t11, b.frac_s);
 	return lerp4(t0010, t0111, b.frac_t);
+}
+
+// ---- mip-mapped trilinear sampling: an EXTENSION. The reference samples level 0 bilinearly and nothing
+// else (sample_2D_u_x8 common_shader_core.h:195-199). Built from the reference's own bilinear_u_x8 per level, so that a
+// texture that is not minified anywhere renders bit-identically to basic_ps.
+__device__ __forceinline__ int mip_extent(int e, int level) {
+	const int v = e >> level;
+	return v > 0 ? v : 1;
+}
+__device__ __forceinline__ TexDesc mip_level_desc(const TexDesc &tex, int level) {
+	if(level <= 0) return tex;
+	size_t texels = 0;
+	for(int l = 1; l < level; ++l) texels += (size_t)mip_extent(tex.width, l) * (size_t)mip_extent(tex.height, l);
+	TexDesc d = tex;
+	d.data = (const uint32_t *)tex.mips + texels;
+	d.width = mip_extent(tex.width, level);
+	d.height = mip_extent(tex.height, level);
+	return d;
+}
+// (u,v) at the pixel, at its right neighbour and at the pixel below -> level of detail the way D3D11 defines it:
+// rho = the longer of the two screen-space derivatives measured in texels, lod = log2(rho) clamped to the chain.
+__device__ __forceinline__ float4 trilinear_u(const TexDesc &tex, float u, float v, float u_dx, float v_dx, float u_dy, float v_dy) {
+	const float w = (float)tex.width, h = (float)tex.height;
+	const float ax = (u_dx - u) * w, ay = (v_dx - v) * h, bx = (u_dy - u) * w, by = (v_dy - v) * h;
+	const float rho2 = fmaxf(ax * ax + ay * ay, bx * bx + by * by);
+	float lod = 0.5f * log2f(rho2);                               // log2(sqrt(rho2)); rho2 == 0 -> -inf -> clamped to 0
+	const float max_lod = (float)(tex.mip_levels - 1);
+	lod = (lod > 0.0f) ? lod : 0.0f;                              // also maps NaN to 0
+	lod = (lod < max_lod) ? lod : max_lod;
+	const int l0 = (int)lod;
+	const float f = lod - (float)l0;
+	const float4 c0 = bilinear_u(mip_level_desc(tex, l0), u, v);
+	if(f == 0.0f) return c0;                                      // magnification: exactly the reference's bilinear sample
+	const float4 c1 = bilinear_u(mip_level_desc(tex, l0 + 1), u, v); // f > 0 implies l0 + 1 <= mip_levels - 1
+	return lerp4(c0, c1, f);
 }
 
 // sample_2D_latlon_x8 (common_shader_core.h:226-244). The three axes go through v3f256_normalize, so
@@ -287,6 +324,13 @@ __device__ __forceinline__ float3 run_ps<2>(float4 r1, float, const TexDesc &tex
 	normalize3(nx, ny, nz, lut);
 	const float4 c = sample_latlon(tex, nx, ny, nz, lut);
 	return make_float3(tone_map(c.x), tone_map(c.y), tone_map(c.z));
+}
+
+// basic_ps with mip-mapped trilinear filtering of SRV0 (extension, see trilinear_u): UV = (r1.w, r2.x) at the pixel, at the
+// pixel to its right and at the pixel below it
+__device__ __forceinline__ float3 run_ps_basic_trilinear(float u, float v, float u_dx, float v_dx, float u_dy, float v_dy, const TexDesc &tex) {
+	const float4 c = trilinear_u(tex, u, v, u_dx, v_dx, u_dy, v_dy);
+	return make_float3(srgb_from_linear_approx(c.x), srgb_from_linear_approx(c.y), srgb_from_linear_approx(c.z));
 }
 
 // Output merger encode (main.c:1176-1178): i32 adds of shifted RNE conversions, no clamp, alpha 0.

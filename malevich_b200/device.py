@@ -41,6 +41,8 @@ fullscreen_vs = VertexShader(256, 384, L.VS_FULLSCREEN)
 passthrough_ps = PixelShader(L.PS_PASSTHROUGH)
 basic_ps = PixelShader(L.PS_BASIC)
 env_lighting_ps = PixelShader(L.PS_ENV_LIGHTING)
+# extension: basic_ps with SRV0 sampled trilinearly from a device-built mip chain
+basic_trilinear_ps = PixelShader(L.PS_BASIC_TRILINEAR)
 
 VECTOR_WIDTH = 8  # main.c:26
 
@@ -49,8 +51,9 @@ class Texture2D:
     """Texture2D, common_shader_core.h:20-24. `p_data` is uint32 [h, w] (R8G8B8A8) or float32 [h, w, 4].
     `is_in_srgb` is load_texture's argument (main.c:538): the device copy is re-quantised to linear on the GPU."""
 
-    def __init__(self, p_data: np.ndarray, is_in_srgb: bool = False):
+    def __init__(self, p_data: np.ndarray, is_in_srgb: bool = False, generate_mips: bool = False):
         self.is_in_srgb = bool(is_in_srgb)
+        self.generate_mips = bool(generate_mips)  # extension: mlv_texture_generate_mips after the upload
         if p_data.dtype == np.uint32 and p_data.ndim == 2:
             self.format = L.FORMAT_R8G8B8A8_UNORM
         elif p_data.dtype == np.float32 and p_data.ndim == 3 and p_data.shape[2] == 4:
@@ -194,6 +197,8 @@ class Device:
         L.check(self._lib.mlv_create_texture2d(self._h, tex.p_data.ctypes.data_as(C.c_void_p), tex.width, tex.height, tex.format, C.byref(h)))
         if tex.is_in_srgb:
             L.check(self._lib.mlv_texture_srgb_to_linear(self._h, h))
+        if tex.generate_mips:
+            L.check(self._lib.mlv_texture_generate_mips(self._h, h))
         self._textures[id(tex)] = (tex, h)
         return h
 
@@ -201,6 +206,18 @@ class Device:
         """The device copy of a texture (after the sRGB re-quantisation, if any)."""
         out = np.empty_like(tex.p_data)
         L.check(self._lib.mlv_read_texture(self._h, self._texture(tex), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def read_texture_mips(self, tex: Texture2D) -> list:
+        """Every level of the device's mip chain of `tex` (level 0 first) as uint32 [h, w] arrays."""
+        h = self._texture(tex)
+        n = C.c_uint32()
+        L.check(self._lib.mlv_texture_mip_levels(h, C.byref(n)))
+        out = []
+        for level in range(n.value):
+            a = np.empty((max(1, tex.height >> level), max(1, tex.width >> level)), dtype=np.uint32)
+            L.check(self._lib.mlv_read_texture_mip(self._h, h, level, a.ctypes.data_as(C.c_void_p)))
+            out.append(a)
         return out
 
     def upload(self, *objs):
