@@ -266,6 +266,11 @@ enum { MLV_STAGE_CLEAR = 0,      /* k_clear */
        MLV_STAGE_COUNT = 10 };
 MLV_API int mlv_profile_begin(mlv_device *dev);
 MLV_API int mlv_profile_end(mlv_device *dev, double *out_ms, uint32_t *out_launches);
+/* The same region launch by launch -- the timeline Remotery's viewer draws (external/Remotery/vis): stage, start relative
+ * to the first launch of the region, duration. Valid after mlv_profile_end; out == NULL queries the count.
+ * tools/trace_frame.py turns it into a Chrome/Perfetto trace with the reference's scope names. */
+typedef struct mlv_profile_event { int32_t stage; float start_ms; float duration_ms; } mlv_profile_event;
+MLV_API int mlv_profile_read_events(mlv_device *dev, mlv_profile_event *out, uint32_t capacity, uint32_t *out_count);
 
 /* how many kernels this device has launched since creation (bench.py's gpu_launches) */
 MLV_API uint64_t mlv_kernel_launch_count(mlv_device *dev);

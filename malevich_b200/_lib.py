@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "mlv_resolve", "mlv_resolved_color_device_ptr", "mlv_resolved_depth_device_ptr",
     "mlv_composite_peer_export", "mlv_composite_peer_attach", "mlv_composite_broadcast", "mlv_composite_wait", "mlv_composite_broadcast_async", "mlv_composite_join", "mlv_composite_readback_async", "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
     "mlv_debug_read_vs_out", "mlv_debug_read_triangles", "mlv_debug_read_bins", "mlv_debug_read_masks",
-    "mlv_debug_read_tile_min_depths", "mlv_profile_begin", "mlv_profile_end", "mlv_kernel_launch_count",
+    "mlv_debug_read_tile_min_depths", "mlv_profile_begin", "mlv_profile_end", "mlv_profile_read_events", "mlv_kernel_launch_count",
 ]
 STAGE_NAMES = ["clear", "geometry", "bin_count", "bin_scan", "bin_fill", "tile", "resolve", "composite", "vertex_cache", "clip"]
 
@@ -32,6 +32,10 @@ FORMAT_R8G8B8A8_UNORM, FORMAT_R32G32B32A32_FLOAT = 0, 1
 BUFFER_VERTEX, BUFFER_INDEX = 0, 1
 INDEX_U32, INDEX_U16 = 0, 1
 DEVICE_DEBUG_CAPTURE = 1
+
+
+class ProfileEvent(C.Structure):
+    _fields_ = [("stage", C.c_int32), ("start_ms", C.c_float), ("duration_ms", C.c_float)]
 
 
 class Viewport(C.Structure):
@@ -140,6 +144,7 @@ def load() -> C.CDLL:
         "mlv_debug_read_tile_min_depths": (i32, [vp, vp]),
         "mlv_profile_begin": (i32, [vp]),
         "mlv_profile_end": (i32, [vp, P(C.c_double), P(u32)]),
+        "mlv_profile_read_events": (i32, [vp, vp, u32, P(u32)]),
         "mlv_kernel_launch_count": (C.c_uint64, [vp]),
     }
     assert sorted(sig) == sorted(EXPORTED_SYMBOLS)

@@ -1484,6 +1484,25 @@ int mlv_profile_end(mlv_device *dev, double *out_ms, uint32_t *out_launches) {
 	return MLV_OK;
 }
 
+// Per-launch records of the last profiled region (valid after mlv_profile_end until the next mlv_profile_begin).
+int mlv_profile_read_events(mlv_device *dev, mlv_profile_event *out, uint32_t capacity, uint32_t *out_count) {
+	if(int rc = use_device(dev)) return rc;
+	if(!out_count) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	if(dev->prof_on) return fail(MLV_ERR_STATE, "call mlv_profile_end first");
+	const size_t n = dev->prof_stages->size();
+	*out_count = (uint32_t)n;
+	if(!out) return MLV_OK;
+	for(size_t k = 0; k < n && k < capacity; ++k) {
+		float start = 0.f, dur = 0.f;
+		CUDA_TRY(cudaEventElapsedTime(&start, (*dev->prof_events)[0], (*dev->prof_events)[2 * k]));
+		CUDA_TRY(cudaEventElapsedTime(&dur, (*dev->prof_events)[2 * k], (*dev->prof_events)[2 * k + 1]));
+		out[k].stage = (*dev->prof_stages)[k];
+		out[k].start_ms = start;
+		out[k].duration_ms = dur;
+	}
+	return MLV_OK;
+}
+
 uint64_t mlv_kernel_launch_count(mlv_device *dev) { return dev ? dev->launches : 0; }
 
 } // extern "C"

@@ -378,6 +378,14 @@ class Device:
         L.check(self._lib.mlv_profile_end(self._h, ms, n))
         return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(L.STAGE_NAMES)}
 
+    def profile_events(self) -> list:
+        """Launch-by-launch records of the last profiled region: [(stage name, start ms, duration ms)]."""
+        n = C.c_uint32()
+        L.check(self._lib.mlv_profile_read_events(self._h, None, 0, C.byref(n)))
+        ev = (L.ProfileEvent * max(n.value, 1))()
+        L.check(self._lib.mlv_profile_read_events(self._h, ev, n.value, C.byref(n)))
+        return [(L.STAGE_NAMES[e.stage], float(e.start_ms), float(e.duration_ms)) for e in ev[:n.value]]
+
     def resolve(self):
         L.check(self._lib.mlv_resolve(self._h))
 
