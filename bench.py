@@ -173,8 +173,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     stripe = args.stripe if args.stripe > 0 else max(1, -(-(scene.height // 8) // world))
     dev = Device(scene.width, scene.height, cuda_device=local_rank, num_ranks=world, rank=rank, stripe_height_tiles=stripe)
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local_rank))
+    from malevich_b200 import partition
+
     def shard_bytes(nbytes: int) -> int:  # equal shards of a buffer, 16-byte granules, for the in-place all-gather of sharded uploads
-        return -(-(-(-nbytes // world)) // 16) * 16
+        return partition.shard_bytes(nbytes, world)
 
     if multi:  # buffers padded to world x shard so that every rank's shard has the same size
         from malevich_b200 import _lib as L0
@@ -341,8 +343,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         for h, p in host_inputs:
             sb = shard_bytes(p.nbytes)
             full = torch.as_tensor(_RawBuf(int(lib.mlv_buffer_device_ptr(h)), sb * world), device=cuda_dev)
-            lo, hi = min(rank * sb, p.nbytes), min((rank + 1) * sb, p.nbytes)
-            sharded.append((h, p.ctypes.data + lo, lo, hi - lo, full, full[rank * sb:(rank + 1) * sb], torch.cuda.Event()))
+            lo, count = partition.shard_range(p.nbytes, world, rank)
+            sharded.append((h, p.ctypes.data + lo, lo, count, full, full[rank * sb:(rank + 1) * sb], torch.cuda.Event()))
 
     def frame_e2e_sharded():
         for h, host_ptr, lo, n, full, mine, ev in sharded:

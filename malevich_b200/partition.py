@@ -50,3 +50,21 @@ def unpack(chunks: np.ndarray, height: int, num_ranks: int, stripe_h: int) -> np
     for y in range(height):
         out[y] = chunks[owner_of_tile_row(y // TILE, num_ranks, stripe_h), chunk_row_of(y, num_ranks, stripe_h)]
     return out
+
+
+# ---- sharded uploads of replicated geometry (bench.py e2e at N > 1; include/malevich_b200.h mlv_update_buffer_range) ----
+SHARD_GRANULE = 16  # bytes; device buffers are 16-byte aligned and the kernels read them through 128-bit loads
+
+
+def shard_bytes(nbytes: int, num_ranks: int) -> int:
+    """Size of one rank's shard: equal for all ranks (in-place all-gather), a multiple of 16 bytes."""
+    per = -(-nbytes // num_ranks)
+    return -(-per // SHARD_GRANULE) * SHARD_GRANULE
+
+
+def shard_range(nbytes: int, num_ranks: int, rank: int):
+    """(offset, count) of the bytes of an nbytes-long host buffer that rank uploads itself; count may be 0 for the last
+    ranks of a small buffer. The device buffer has capacity shard_bytes * num_ranks; what lies beyond nbytes is padding."""
+    sb = shard_bytes(nbytes, num_ranks)
+    lo, hi = min(rank * sb, nbytes), min((rank + 1) * sb, nbytes)
+    return lo, hi - lo

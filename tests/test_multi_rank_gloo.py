@@ -71,3 +71,46 @@ def test_gloo_composite_reproduces_the_full_frame(world, stripe_h, tmp_path):
     mp.spawn(_worker, args=(world, port, stripe_h, frame_path, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / f"rank{r}.txt").read() == "OK"
+
+
+def _shard_worker(rank, world, port, sizes, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = True
+        for n in sizes:
+            host = np.random.default_rng(n).integers(0, 256, n, dtype=np.uint8)  # the replicated host buffer (same on every rank)
+            sb = partition.shard_bytes(n, world)
+            device = torch.full((sb * world,), 0xEE, dtype=torch.uint8)        # stands for the padded device buffer
+            lo, count = partition.shard_range(n, world, rank)
+            device[lo:lo + count] = torch.from_numpy(host[lo:lo + count])       # mlv_update_buffer_range: this rank's shard only
+            dist.all_gather_into_tensor(device, device[rank * sb:(rank + 1) * sb].clone())  # NVLink replication (NCCL in bench.py)
+            ok = ok and np.array_equal(device.numpy()[:n], host)
+        with open(os.path.join(out_dir, f"shard{rank}.txt"), "w") as f:
+            f.write("OK" if ok else "MISMATCH")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_ranges_tile_the_buffer():
+    for n in (1, 15, 16, 17, 4096, 20056032, 15000000):
+        for world in (1, 2, 3, 4, 8):
+            sb = partition.shard_bytes(n, world)
+            assert sb % 16 == 0 and sb * world >= n
+            pos = 0
+            for r in range(world):
+                lo, count = partition.shard_range(n, world, r)
+                assert lo == min(pos, n) and lo % 16 == 0 or count == 0
+                assert lo >= r * sb or count == 0
+                pos = lo + count
+            assert pos == n
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_sharded_upload_replicates_the_buffer(world, tmp_path):
+    """The e2e upload path of bench.py at N > 1 with gloo standing in for NCCL: every rank contributes 1/N of each buffer."""
+    mp.spawn(_shard_worker, args=(world, 29700 + world, (1, 17, 4096, 100003, 1200000), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"shard{r}.txt").read() == "OK"
