@@ -270,6 +270,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     dev.reset_stats()
     frame()
     stats_local = dev.stats()
+    work = reduce_sum_dict(dev.work_counters())  # what the kernels really processed in that frame (Hi-Z at binning time removes the rest)
     # per-rank shares (a triangle is counted by the rank that owns its first tile row); the sum is the reference's Stats
     stats = reduce_sum_dict({k: stats_local[k] for k in ("assembled_triangle_count", "active_bin_count", "total_triangle_count_in_bins")})
 
@@ -425,13 +426,24 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                      "k_bin_scan": stage_ms["bin_scan"], "k_bin_fill": stage_ms["bin_fill"]}
         kernel_launches = {"k_geom": stage_launches["geometry"], "k_tile": stage_launches["tile"], "k_geom_clip": stage_launches["clip"], "k_vertex": stage_launches["vertex_cache"],
                            "k_bin_scan": stage_launches["bin_scan"], "k_bin_fill": stage_launches["bin_fill"]}
-        kernel_bytes = {"k_geom": b_stage["geometry"], "k_tile": b_stage["tile"] / world, "k_geom_clip": 0, "k_vertex": 0, "k_bin_scan": 16 * (scene.width // 8) * (scene.height // 8) * len(scene.objects) / world,
-                        "k_bin_fill": 8 * stats["total_triangle_count_in_bins"] / world}
+        # Algorithmic bytes of a kernel = SURVEY.md 8d's per-unit figures x the units the kernel REALLY processed (device work
+        # counters): Stats count every assembled triangle and pair like the reference, but a triangle that Hi-Z rejects at
+        # binning time writes no record and a tile without surviving pairs is not visited, so those units move no bytes.
+        idx_bytes = 4 * sum(o.index_count for o in scene.objects)
+        vtx_bytes = 32 * sum(o.vertex_buffer.shape[0] for o in scene.objects)
+        kernel_bytes = {"k_geom": (idx_bytes + vtx_bytes + 216 * work["records_written"]) / world,        # inputs once + record write
+                        "k_tile": (216 * work["records_written"] + 1032 * work["tiles_visited"] + 4 * work["pairs_listed"]) / world,  # record read + tile read/write + list read
+                        "k_geom_clip": 0, "k_vertex": vtx_bytes / world, "k_bin_scan": 16 * (scene.width // 8) * (scene.height // 8) * len(scene.objects) / world,
+                        "k_bin_fill": (16 * stats["assembled_triangle_count"] + 4 * work["pairs_listed"]) / world}
         dom = max(("k_geom", "k_tile"), key=kernel_ms.get)  # the two kernels that carry the record stream; the others move < 5 % of the bytes
-        dom_launches = kernel_launches[dom]
-        dom_ms_per_launch = kernel_ms[dom] / max(dom_launches, 1)
-        dom_bytes_per_launch = kernel_bytes[dom] / max(dom_launches, 1)
-        achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9 if dom_ms_per_launch > 0 else 0.0
+
+        def kernel_roofline(k):
+            n = max(kernel_launches[k], 1)
+            ms_l, b_l = kernel_ms[k] / n, kernel_bytes[k] / n
+            a = b_l / (ms_l * 1e-3) / 1e9 if ms_l > 0 else 0.0
+            return {"achieved": a, "frac": a / peak, "algorithmic_bytes_per_launch": b_l, "ms_per_launch": ms_l, "launches_per_step": kernel_launches[k]}
+        dom_r = kernel_roofline(dom)
+        achieved, dom_bytes_per_launch, dom_ms_per_launch, dom_launches = dom_r["achieved"], dom_r["algorithmic_bytes_per_launch"], dom_r["ms_per_launch"], dom_r["launches_per_step"]
         # measured DRAM bytes per launch of that kernel from the committed ncu capture (same workload, 1 GPU), else null
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_traffic_config5_n1.json")
@@ -448,9 +460,15 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                        "l2": "no flush: per-frame working set (inputs + per-draw setup records) >> 126 MB L2" if args.config == 5 else "no flush"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes_per_launch,
-                         "ms_per_launch": dom_ms_per_launch, "launches_per_step": dom_launches},
+                         "ms_per_launch": dom_ms_per_launch, "launches_per_step": dom_launches,
+                         "units_per_step": {"records_written": work["records_written"], "tiles_visited": work["tiles_visited"], "pairs_listed": work["pairs_listed"]},
+                         "note": "algorithmic bytes = SURVEY 8d per-unit figures x the units the kernel really processed (mlv_work_counters), averaged over its launches of a frame; "
+                                 "the launch time is its CUDA-event bracket (no overlap with neighbours)"},
+            "roofline_kernels": {k: kernel_roofline(k) for k in ("k_geom", "k_tile", "k_vertex", "k_bin_fill")},
             "roofline_frame": {"algorithmic_bytes_per_frame": b_alg, "achieved": b_alg / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
-                               "frac": b_alg / (ms * 1e-3) / 1e9 / world / peak, "bytes_by_stage": b_stage},
+                               "frac": b_alg / (ms * 1e-3) / 1e9 / world / peak, "bytes_by_stage": b_stage,
+                               "note": "B_alg of the REFERENCE algorithm for this frame (SURVEY 8d: every assembled triangle's record written and read, every touched tile-draw loaded and "
+                                       "stored) over the measured frame time: delivered work per second, not DRAM throughput -- it exceeds the peak when Hi-Z at binning time removes work"},
             "stage_ms_per_step": {k: round(v, 4) for k, v in stage_ms.items()},
             "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d - tex_bytes), "d2h_bytes_per_step": int(d2h),
                     "note": ("every vertex/index buffer + constant buffer re-uploaded from pinned host memory each frame; framebuffer read back to pinned host memory each frame (double-buffered: the host collects frame f-1 while frame f is queued); textures stay resident"

@@ -79,6 +79,15 @@ typedef struct mlv_stats {
 	uint32_t total_triangle_count_in_bins;
 } mlv_stats;
 
+/* What the device really processed since the last mlv_reset_stats -- unlike Stats, which count every assembled triangle and
+ * every (triangle, tile) pair like the reference does, these exclude what Hi-Z at binning time removed before it cost memory
+ * traffic. bench.py derives the per-kernel algorithmic bytes (SURVEY.md 8d per-unit figures) from them. */
+typedef struct mlv_work_counters {
+	uint64_t records_written; /* assembled triangles that survived Hi-Z in at least one tile: setup records written, later read by k_tile */
+	uint64_t pairs_listed;    /* (triangle, tile) pairs stored in the per-tile lists */
+	uint64_t tiles_visited;   /* tile-draws k_tile loaded and stored (work-list bins) */
+} mlv_work_counters;
+
 /* Replaces the compile-time WIDTH/HEIGHT (main.c:21-22) and adds the sort-first partition
  * (SURVEY.md 8e): rank r of num_ranks owns the 8-pixel tile rows ty with (ty / stripe_height_tiles)
  * % num_ranks == r. width and height must be multiples of 8 (WIDTH_IN_TILES main.c:28-29). */
@@ -185,6 +194,7 @@ MLV_API int mlv_present_readback_async(mlv_device *dev, uint32_t *colors, float 
 MLV_API int mlv_present_wait(mlv_device *dev);
 MLV_API int mlv_get_stats(mlv_device *dev, mlv_stats *out);  /* stats main.c:231,1268 */
 MLV_API int mlv_reset_stats(mlv_device *dev);                /* memset(&stats,0) main.c:1268 */
+MLV_API int mlv_get_work_counters(mlv_device *dev, mlv_work_counters *out); /* synchronises; reset by mlv_reset_stats */
 
 /* Device-resident resolve: tiled colour/depth -> row-major device buffers with 128-bit stores. */
 MLV_API int mlv_resolve(mlv_device *dev);

@@ -15,7 +15,7 @@ EXPORTED_SYMBOLS = [
     "mlv_vs_set_shader", "mlv_vs_set_constant_buffer", "mlv_vs_set_shader_resource", "mlv_rs_set_viewport",
     "mlv_ps_set_shader", "mlv_ps_set_shader_resource",
     "mlv_clear_render_target_view", "mlv_clear_depth_stencil_view", "mlv_draw_indexed", "mlv_draw_indexed_ex", "mlv_draw",
-    "mlv_present_readback", "mlv_present_readback_async", "mlv_present_wait", "mlv_get_stats", "mlv_reset_stats",
+    "mlv_present_readback", "mlv_present_readback_async", "mlv_present_wait", "mlv_get_stats", "mlv_reset_stats", "mlv_get_work_counters",
     "mlv_resolve", "mlv_resolved_color_device_ptr", "mlv_resolved_depth_device_ptr",
     "mlv_composite_peer_export", "mlv_composite_peer_attach", "mlv_composite_broadcast", "mlv_composite_wait", "mlv_composite_broadcast_async", "mlv_composite_join", "mlv_composite_readback_async", "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
     "mlv_debug_read_vs_out", "mlv_debug_read_triangles", "mlv_debug_read_bins", "mlv_debug_read_masks",
@@ -32,6 +32,10 @@ FORMAT_R8G8B8A8_UNORM, FORMAT_R32G32B32A32_FLOAT = 0, 1
 BUFFER_VERTEX, BUFFER_INDEX = 0, 1
 INDEX_U32, INDEX_U16 = 0, 1
 DEVICE_DEBUG_CAPTURE = 1
+
+
+class WorkCounters(C.Structure):
+    _fields_ = [("records_written", C.c_uint64), ("pairs_listed", C.c_uint64), ("tiles_visited", C.c_uint64)]
 
 
 class ProfileEvent(C.Structure):
@@ -124,6 +128,7 @@ def load() -> C.CDLL:
         "mlv_present_wait": (i32, [vp]),
         "mlv_get_stats": (i32, [vp, P(Stats)]),
         "mlv_reset_stats": (i32, [vp]),
+        "mlv_get_work_counters": (i32, [vp, P(WorkCounters)]),
         "mlv_resolve": (i32, [vp]),
         "mlv_resolved_color_device_ptr": (vp, [vp]),
         "mlv_resolved_depth_device_ptr": (vp, [vp]),

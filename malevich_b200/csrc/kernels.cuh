@@ -379,6 +379,7 @@ __device__ __forceinline__ uint32_t emit_triangle(const GeomParams &P, uint32_t 
 	const uint2 pb = pack_bounds(S);
 	P.tri_bounds[slot] = tally.live ? make_uint4(pb.x, pb.y, __float_as_uint(S.max_depth), key) : make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, key);
 	if(tally.live) {
+		atomicAdd(P.stat_stripes + (size_t)(blockIdx.x % MLV_STAT_STRIPES) * 16u + 1u, 1ull); // work counter: records_written
 		TriRecord R;
 		make_record(R, S, pb, r1a, r1b, r1c, r2a, r2b, r2c);
 		uint4 *cov = P.tri_cov + (size_t)slot * MLV_TRI_COV_U4;
@@ -460,6 +461,15 @@ __device__ __forceinline__ void tally_stats(unsigned long long *stripes, uint32_
 	if(lane_id() == 0 && (emitted | pairs)) {
 		const uint32_t stripe = (blockIdx.x * 8u + (threadIdx.x >> 5)) % MLV_STAT_STRIPES;
 		atomicAdd(stripes + stripe * 16u, ((unsigned long long)emitted << 32) | pairs);
+	}
+}
+
+// Work counter (mlv_work_counters.records_written): second word of the warp's stripe; warp-uniform count, nothing to do
+// for a draw that wrote no records.
+__device__ __forceinline__ void tally_records(unsigned long long *stripes, uint32_t records) {
+	if(lane_id() == 0 && records) {
+		const uint32_t stripe = (blockIdx.x * 8u + (threadIdx.x >> 5)) % MLV_STAT_STRIPES;
+		atomicAdd(stripes + stripe * 16u + 1u, (unsigned long long)records);
 	}
 }
 
@@ -584,7 +594,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 	// coalesced 128-bit stores instead of 32 scattered 16-byte pieces per instruction.
 	__shared__ uint4 s_stage[MLV_GEOM_THREADS / 32][32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)];
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-	uint32_t emitted = 0, pairs = 0;
+	uint32_t emitted = 0, pairs = 0, records = 0;
 	if(blockIdx.x == 0 && threadIdx.x == 0) { // Stats (main.c:1228-1232)
 		P.ctr->stats.vertex_count += P.index_count;
 		P.ctr->stats.input_triangle_count += P.tri_count;
@@ -757,6 +767,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 	__syncwarp();
 	const uint32_t valid = __ballot_sync(0xffffffffu, staged);
 	if(valid) {
+		records += (uint32_t)__popc(valid);
 		const uint4 *st = s_stage[warp];
 		const size_t slot0 = (size_t)(t - lane);
 		uint4 *cov = P.tri_cov + slot0 * MLV_TRI_COV_U4;
@@ -777,6 +788,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 	if(P.chunk_bounds) __syncthreads(); // s_live is rewritten by the next round
 	}
 	tally_stats(P.stat_stripes, emitted, pairs);
+	tally_records(P.stat_stripes, records);
 }
 
 #define MLV_CLIP_SPLIT 4u
@@ -1293,21 +1305,29 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	if(blockIdx.x == 0 && threadIdx.x < 32) { // every earlier kernel of this draw is done with these: fold them into Stats, re-arm for the next draw
-		uint32_t tris = 0, pairs = 0;
+		uint32_t tris = 0, pairs = 0, records = 0;
 #pragma unroll
 		for(uint32_t i = lane; i < MLV_STAT_STRIPES; i += 32u) {
 			const unsigned long long v = P.stat_stripes[i * 16u];
 			P.stat_stripes[i * 16u] = 0ull;
 			tris += (uint32_t)(v >> 32);
 			pairs += (uint32_t)v;
+			records += (uint32_t)P.stat_stripes[i * 16u + 1u];
+			P.stat_stripes[i * 16u + 1u] = 0ull;
 		}
 #pragma unroll
 		for(int d = 16; d > 0; d >>= 1) {
 			tris += __shfl_xor_sync(0xffffffffu, tris, d);
 			pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
+			records += __shfl_xor_sync(0xffffffffu, records, d);
 		}
 		if(lane == 0) {
 			Counters *c = P.ctr;
+			c->work.records_written += records;
+			if(c->pair_total <= pair_capacity) {
+				c->work.pairs_listed += c->pair_total;
+				c->work.tiles_visited += c->n_cbins;
+			}
 			c->stats.assembled_triangle_count += tris;
 			c->stats.total_triangle_count_in_bins += pairs;
 			c->stats.active_bin_count += c->draw_active_bins;

@@ -1125,8 +1125,19 @@ int mlv_get_stats(mlv_device *dev, mlv_stats *out) {
 	return check_flags(dev, c);
 }
 
+int mlv_get_work_counters(mlv_device *dev, mlv_work_counters *out) {
+	if(int rc = use_device(dev)) return rc;
+	if(!out) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	Counters c;
+	CUDA_TRY(cudaMemcpyAsync(&c, dev->ctr, sizeof(c), cudaMemcpyDeviceToHost, dev->stream));
+	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	*out = c.work;
+	return check_flags(dev, c);
+}
+
 int mlv_reset_stats(mlv_device *dev) {
 	if(int rc = use_device(dev)) return rc;
+	CUDA_TRY(cudaMemsetAsync((char *)dev->ctr + offsetof(Counters, work), 0, sizeof(mlv_work_counters), dev->stream));
 	CUDA_TRY(cudaMemsetAsync((char *)dev->ctr + offsetof(Counters, stats), 0, sizeof(mlv_stats), dev->stream));
 	CUDA_TRY(cudaMemsetAsync((char *)dev->ctr + offsetof(Counters, error_flags), 0, sizeof(uint32_t), dev->stream));
 	return MLV_OK;

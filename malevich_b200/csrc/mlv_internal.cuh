@@ -55,6 +55,7 @@ struct Counters {
 	uint32_t bcast_done;  // CTAs of k_composite_broadcast that have finished their stores (reset by the last one)
 	uint32_t pad[3];
 	mlv_stats stats;      // accumulated like reference main.c:1228-1246
+	mlv_work_counters work; // what the kernels really processed (Hi-Z at binning time removes work the reference's Stats still count)
 };
 
 struct Partition { // sort-first ownership

@@ -357,6 +357,12 @@ class Device:
         L.check(self._lib.mlv_get_stats(self._h, C.byref(s)))
         return s.as_dict()
 
+    def work_counters(self) -> dict:
+        """What the kernels really processed since reset_stats (Stats count the reference's work, hidden or not)."""
+        w = L.WorkCounters()
+        L.check(self._lib.mlv_get_work_counters(self._h, C.byref(w)))
+        return {"records_written": int(w.records_written), "pairs_listed": int(w.pairs_listed), "tiles_visited": int(w.tiles_visited)}
+
     def reset_stats(self):  # memset(&stats, 0) main.c:1268
         L.check(self._lib.mlv_reset_stats(self._h))
 

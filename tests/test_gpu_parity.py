@@ -476,6 +476,28 @@ def _as_tensor(ptr, nbytes):
     return torch.as_tensor(_Raw(), device="cuda")
 
 
+def test_work_counters_equal_stats_without_hiz_and_shrink_with_it():
+    """mlv_work_counters: with Hi-Z at binning time disabled (debug capture keeps every pair, like the reference) every assembled
+    triangle writes a record and every counted pair is listed, so the counters equal Stats; with it, hidden layers drop out."""
+    from malevich_b200 import scenes
+    sc = scenes.synthetic(1280, 720, layers=3, nx=400, ny=200)
+    with _device(sc.width, sc.height, debug_capture=True) as dev:
+        scenes.render(dev, sc)
+        st, w = dev.stats(), dev.work_counters()
+        assert w["records_written"] == st["assembled_triangle_count"]
+        assert w["pairs_listed"] == st["total_triangle_count_in_bins"]
+        assert w["tiles_visited"] == st["active_bin_count"]
+    with _device(sc.width, sc.height) as dev:
+        scenes.render(dev, sc)
+        st2, w2 = dev.stats(), dev.work_counters()
+        assert st2 == st
+        assert 0 < w2["records_written"] < st["assembled_triangle_count"] * 0.6   # layers 2 and 3 lie behind layer 1
+        assert 0 < w2["pairs_listed"] < st["total_triangle_count_in_bins"] * 0.6
+        assert (sc.width // 8) * (sc.height // 8) <= w2["tiles_visited"] <= st["active_bin_count"]
+        dev.reset_stats()
+        assert dev.work_counters() == {"records_written": 0, "pairs_listed": 0, "tiles_visited": 0}
+
+
 def test_range_uploads_marked_on_a_caller_stream_and_composite_readback():
     """The sharded-upload entry points of the sort-first path, on one GPU: a buffer created with a padded capacity and
     filled by mlv_update_buffer_range in three pieces, declared complete on a caller's stream with
