@@ -1299,8 +1299,27 @@ __device__ __forceinline__ uint32_t shade_pixel(const TileParams &P, uint32_t ke
 
 #define MLV_TILE_THREADS 256
 
+// Coverage by (triangle, row) items. With lanes over triangles (coverage() above) a batch costs what its TALLEST bounding
+// box costs and the lanes beyond the list's length idle -- at BASELINE config 5 (21 pixel-sized triangles per tile, boxes of
+// ~4 x 5 pixels) that loop was a third of k_tile's instructions. Here every lane publishes its triangle's edge values at the
+// top-left pixel of (bounds & tile) and the steps, a warp scan numbers the rows of all boxes, and lane i evaluates row item
+// i: same wrapping arithmetic, same bits, ~3 rounds of one row each instead of ~8 rows per lane. Row masks are assembled as
+// bytes of the reference's 64-bit fragment mask (bit 8*row + col) in shared memory. Batches of tall boxes (more than
+// MLV_ROWCOV_MAX_ITEMS rows in all) keep the per-triangle loop, which has less overhead per row.
+#define MLV_ROWCOV_MAX_ITEMS 160
+struct RowCovWarp {
+	uint32_t e[3][32];      // edge functions at the box's top-left pixel
+	uint32_t sx[3][32];     // step per pixel to the right (a << 4)
+	uint32_t sy[3][32];     // step per row down (b << 4)
+	uint32_t box[32];       // x0 | x1 << 4 | y0 << 8 (tile-relative)
+	uint32_t first[32];     // number of the triangle's first row item
+	uint2 mask[32];         // fragment mask under construction: .x rows 0-3, .y rows 4-7
+	uint8_t item_tri[256];  // row item -> lane of its triangle
+};
+
 template <int PS>
-__global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant__ TileParams P, uint32_t pair_capacity) {
+__global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_constant__ TileParams P, uint32_t pair_capacity) {
+	__shared__ RowCovWarp s_rowcov[MLV_TILE_THREADS / 32];
 	pdl_prologue();
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -1374,27 +1393,80 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS) k_tile(const __grid_constant
 			uint32_t key = 0, lo = 0, hi = 0;
 			uint32_t a1 = 0, b1 = 0, e1 = 0, a2 = 0, b2 = 0, e2 = 0; // E1/E2 of this lane's triangle: coefficients and value at the tile origin
 			float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f);
+			uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;
+			uint32_t c2x = 0u, slot = 0u;
+			int x0 = 0, x1 = -1, y0 = 0, y1 = -1; // (bounds & tile) of a triangle that passes Hi-Z; empty otherwise
 			if(k < n) {
 				key = ids[k];
-				const uint32_t slot = slot_of_key(P, key);
+				slot = slot_of_key(P, key);
 				const uint4 *cov = P.tri_cov + (size_t)slot * MLV_TRI_COV_U4;
 				const uint4 c2 = __ldg(cov + 2);
 				const float max_depth = __uint_as_float(c2.y);
 				if(!(max_depth < tile_min_old)) { // Hi-Z (main.c:1005-1010)
-					const uint4 c0 = __ldg(cov), c1 = __ldg(cov + 1);
-					int x0 = 0, x1 = 7, y0 = 0, y1 = 7;
+					c0 = __ldg(cov), c1 = __ldg(cov + 1), c2x = c2.x;
+					x0 = 0, x1 = 7, y0 = 0, y1 = 7;
 					if(c2.z & MLV_NOWRAP_BIT) {
 						x0 = max((int)(c2.z & 0xffffu) - tile_x, 0);
 						y0 = max((int)((c2.z >> 16) & 0x7fffu) - tile_y, 0);
 						x1 = min((int)(short)(c2.w & 0xffffu) - tile_x, 7);
 						y1 = min((int)(short)(c2.w >> 16) - tile_y, 7);
 					}
-					coverage(c0, c1, c2.x, X0, Y0, x0, x1, y0, y1, lo, hi);
-					if(lo | hi) {
-						a1 = c0.w, b1 = c1.x, e1 = c0.w * X0 + c1.x * Y0 + c1.y;
-						a2 = c1.z, b2 = c1.w, e2 = c1.z * X0 + c1.w * Y0 + c2.x;
-						s0 = __ldg(reinterpret_cast<const float4 *>(P.tri_shade + (size_t)slot * MLV_TRI_SHADE_U4));
+				}
+			}
+			{
+				const uint32_t rows = (x1 >= x0 && y1 >= y0) ? (uint32_t)(y1 - y0 + 1) : 0u;
+				uint32_t incl = rows;
+#pragma unroll
+				for(int d = 1; d < 32; d <<= 1) {
+					const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+					if(lane >= (uint32_t)d) incl += o;
+				}
+				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+				if(total > MLV_ROWCOV_MAX_ITEMS) { // tall boxes: per-triangle loop
+					if(rows) coverage(c0, c1, c2x, X0, Y0, x0, x1, y0, y1, lo, hi);
+				} else if(total) {
+					RowCovWarp &R = s_rowcov[threadIdx.x >> 5];
+					const uint32_t first = incl - rows;
+					if(rows) {
+						const uint32_t Xs = X0 + ((uint32_t)x0 << 4), Ys = Y0 + ((uint32_t)y0 << 4);
+						R.e[0][lane] = c0.x * Xs + c0.y * Ys + c0.z, R.sx[0][lane] = c0.x << 4, R.sy[0][lane] = c0.y << 4;
+						R.e[1][lane] = c0.w * Xs + c1.x * Ys + c1.y, R.sx[1][lane] = c0.w << 4, R.sy[1][lane] = c1.x << 4;
+						R.e[2][lane] = c1.z * Xs + c1.w * Ys + c2x, R.sx[2][lane] = c1.z << 4, R.sy[2][lane] = c1.w << 4;
+						R.box[lane] = (uint32_t)x0 | ((uint32_t)x1 << 4) | ((uint32_t)y0 << 8);
+						for(uint32_t r = 0; r < rows; ++r) R.item_tri[first + r] = (uint8_t)lane;
 					}
+					R.first[lane] = first;
+					R.mask[lane] = make_uint2(0u, 0u);
+					__syncwarp();
+					for(uint32_t it = 0; it < total; it += 32u) {
+						const uint32_t i = it + lane;
+						if(i < total) {
+							const uint32_t j = R.item_tri[i];
+							const uint32_t r = i - R.first[j], box = R.box[j];
+							const uint32_t bx0 = box & 15u, bx1 = (box >> 4) & 15u, by = ((box >> 8) & 15u) + r;
+							const uint32_t sx0 = R.sx[0][j], sx1 = R.sx[1][j], sx2 = R.sx[2][j];
+							uint32_t r0 = R.e[0][j] + r * R.sy[0][j], r1 = R.e[1][j] + r * R.sy[1][j], r2 = R.e[2][j] + r * R.sy[2][j];
+							uint32_t row = 0u;
+							for(uint32_t x = bx0; x <= bx1; ++x) {
+								row |= ((int)(r0 | r1 | r2) > 0) ? (1u << x) : 0u;
+								r0 += sx0;
+								r1 += sx1;
+								r2 += sx2;
+							}
+							reinterpret_cast<uint8_t *>(&R.mask[j])[by] = (uint8_t)row;
+						}
+					}
+					__syncwarp();
+					const uint2 m = R.mask[lane];
+					lo = m.x, hi = m.y;
+					__syncwarp(); // the next batch rewrites the warp's rows
+				}
+			}
+			if(k < n) {
+				if(lo | hi) {
+					a1 = c0.w, b1 = c1.x, e1 = c0.w * X0 + c1.x * Y0 + c1.y;
+					a2 = c1.z, b2 = c1.w, e2 = c1.z * X0 + c1.w * Y0 + c2x;
+					s0 = __ldg(reinterpret_cast<const float4 *>(P.tri_shade + (size_t)slot * MLV_TRI_SHADE_U4));
 				}
 				if(P.dbg.infos) {
 					mlv_ref_tile_info ti;
