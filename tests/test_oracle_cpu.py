@@ -174,6 +174,45 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} not exported by {L.LIB_PATH}"
 
 
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The header is the contract: compile it with the C compiler and compare sizeof / offsetof of every plain-data struct with
+    the ctypes mirrors in malevich_b200/_lib.py and the numpy record dtypes in device.py (an ABI drift would otherwise only
+    show up as garbage on the GPU box)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from malevich_b200 import _lib as L, device as D
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"mlv_viewport": L.Viewport, "mlv_stats": L.Stats, "mlv_device_desc": L.DeviceDesc, "mlv_peer_info": L.PeerInfo,
+               "mlv_work_counters": L.WorkCounters, "mlv_profile_event": L.ProfileEvent}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "malevich_b200.h"', "int main(void) {"]
+    for cname, ct in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    for cname in ("mlv_ref_triangle", "mlv_ref_compacted_bin", "mlv_ref_tile_info"):
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+    lines.append('printf("MLV_PS_COUNT %d\\nMLV_VS_COUNT %d\\nMLV_STAGE_COUNT %d\\nMLV_MAX_PEERS %d\\n", MLV_PS_COUNT, MLV_VS_COUNT, MLV_STAGE_COUNT, MLV_MAX_PEERS);')
+    lines += ["return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)  # the header is plain C
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
+    assert int(got["mlv_ref_triangle"]) == D.REF_TRIANGLE_DTYPE.itemsize == 80        # Triangle main.c:134-139
+    assert int(got["mlv_ref_compacted_bin"]) == D.REF_COMPACTED_BIN_DTYPE.itemsize == 12  # CompactedBin main.c:146-150
+    assert int(got["mlv_ref_tile_info"]) == D.REF_TILE_INFO_DTYPE.itemsize == 16        # TileInfo main.c:159-162
+    assert int(got["MLV_STAGE_COUNT"]) == len(L.STAGE_NAMES)
+    assert int(got["MLV_PS_COUNT"]) == 1 + max(L.PS_PASSTHROUGH, L.PS_BASIC, L.PS_ENV_LIGHTING, L.PS_BASIC_TRILINEAR)
+    assert int(got["MLV_VS_COUNT"]) == 1 + max(L.VS_PASSTHROUGH, L.VS_BASIC, L.VS_VERTEX_LIGHTING, L.VS_FULLSCREEN)
+
+
 def test_c_abi_argument_errors_without_gpu():
     lib = L.load()
     h = ctypes.c_void_p()
