@@ -257,7 +257,14 @@ MLV_API int mlv_debug_read_vs_out(mlv_device *dev, float *out12_per_vertex, uint
 MLV_API int mlv_debug_read_triangles(mlv_device *dev, mlv_ref_triangle *tris, float *attributes36, uint32_t *out_count); /* primitive_assembly_stage outputs main.c:877-906 */
 MLV_API int mlv_debug_read_bins(mlv_device *dev, uint32_t *triangle_ids, uint32_t *out_pair_count, mlv_ref_compacted_bin *bins, uint32_t *out_bin_count); /* binner outputs main.c:947-978 */
 MLV_API int mlv_debug_read_masks(mlv_device *dev, mlv_ref_tile_info *infos, uint32_t *out_pair_count);          /* rasterizer output main.c:986-1041 */
-MLV_API int mlv_debug_read_tile_min_depths(mlv_device *dev, float *out_bins);                                    /* a_tile_min_depths main.c:230 */
+MLV_API int mlv_debug_read_tile_min_depths(mlv_device *dev, float *out_bins);                                    /* a_tile_min_depths main.c:230 (works without debug capture) */
+/* keys[i] = the device's order-preserving key of the reference's assembled triangle id i of the last draw (ascending) */
+MLV_API int mlv_debug_read_keys(mlv_device *dev, uint32_t *keys, uint32_t *out_count);
+/* The per-tile lists of the last draw as the PRODUCTION path built them (no debug capture needed): device keys in arrival
+ * order with the pairs Hi-Z rejects at binning time (main.c:1003-1010) already removed, and the work list of bins
+ * (num_triangles_self may be 0: a touched bin visited only for write_tile's tile-minimum refresh, main.c:589-603).
+ * Sorting each list and adding the rejected pairs back gives the reference's triangle_ids (main.c:950-962). Synchronises. */
+MLV_API int mlv_read_bin_lists(mlv_device *dev, uint32_t *keys, uint32_t *out_pair_count, mlv_ref_compacted_bin *bins, uint32_t *out_bin_count);
 
 /* Per-stage device timing (replaces the reference's Remotery scopes, rmt_BeginCPUSample main.c:663,699,737,916,
  * 984,1047,1192,1205): between mlv_profile_begin and mlv_profile_end every kernel launch is bracketed by CUDA events
@@ -284,6 +291,8 @@ MLV_API int mlv_profile_read_events(mlv_device *dev, mlv_profile_event *out, uin
 
 /* how many kernels this device has launched since creation (bench.py's gpu_launches) */
 MLV_API uint64_t mlv_kernel_launch_count(mlv_device *dev);
+/* word-wise 64-bit FNV-1a over u32 words: the frame hash used by tests/golden/golden.json and bench.py (host-side helper) */
+MLV_API uint64_t mlv_fnv64_words(const uint32_t *words, size_t count);
 
 #ifdef __cplusplus
 }

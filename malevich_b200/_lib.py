@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "mlv_resolve", "mlv_resolved_color_device_ptr", "mlv_resolved_depth_device_ptr",
     "mlv_composite_peer_export", "mlv_composite_peer_attach", "mlv_composite_broadcast", "mlv_composite_wait", "mlv_composite_broadcast_async", "mlv_composite_join", "mlv_composite_readback_async", "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
     "mlv_debug_read_vs_out", "mlv_debug_read_triangles", "mlv_debug_read_bins", "mlv_debug_read_masks",
-    "mlv_debug_read_tile_min_depths", "mlv_profile_begin", "mlv_profile_end", "mlv_profile_read_events", "mlv_kernel_launch_count",
+    "mlv_debug_read_tile_min_depths", "mlv_debug_read_keys", "mlv_read_bin_lists", "mlv_fnv64_words", "mlv_profile_begin", "mlv_profile_end", "mlv_profile_read_events", "mlv_kernel_launch_count",
 ]
 STAGE_NAMES = ["clear", "geometry", "bin_count", "bin_scan", "bin_fill", "tile", "resolve", "composite", "vertex_cache", "clip"]
 
@@ -147,6 +147,9 @@ def load() -> C.CDLL:
         "mlv_debug_read_bins": (i32, [vp, vp, P(u32), vp, P(u32)]),
         "mlv_debug_read_masks": (i32, [vp, vp, P(u32)]),
         "mlv_debug_read_tile_min_depths": (i32, [vp, vp]),
+        "mlv_debug_read_keys": (i32, [vp, vp, P(u32)]),
+        "mlv_read_bin_lists": (i32, [vp, vp, P(u32), vp, P(u32)]),
+        "mlv_fnv64_words": (C.c_uint64, [vp, sz]),
         "mlv_profile_begin": (i32, [vp]),
         "mlv_profile_end": (i32, [vp, P(C.c_double), P(u32)]),
         "mlv_profile_read_events": (i32, [vp, vp, u32, P(u32)]),
@@ -164,3 +167,10 @@ def load() -> C.CDLL:
 def check(code: int) -> None:
     if code != MLV_OK:
         raise MalevichError(code, load().mlv_last_error_string().decode("utf-8", "replace"))
+
+
+def fnv64_words(a) -> str:
+    """Frame hash (word-wise 64-bit FNV-1a over u32 words) as 16 hex digits -- the format of tests/golden/golden.json."""
+    import numpy as np
+    w = np.ascontiguousarray(a).view(np.uint32).ravel()
+    return "%016x" % load().mlv_fnv64_words(w.ctypes.data_as(C.c_void_p), w.size)

@@ -80,8 +80,11 @@ __device__ __forceinline__ void set_edge(int *e, int signed_area, int x0, int y0
 }
 
 // main.c:843-848: floor(x * (1 << 4) + 0.5) -- float multiply, double add, double floor, C conversion to i32
+// The C conversion is x86 cvttsd2si: NaN and everything outside [-2^31, 2^31) give the "integer indefinite" 0x80000000
+// (CUDA's conversion would saturate, and map NaN to 0).
 __device__ __forceinline__ int snap(float v) {
 	const double d = floor((double)(v * 16.0f) + 0.5);
+	if(!(d >= -2147483648.0 && d < 2147483648.0)) return (int)0x80000000;
 	return __double2int_rz(d);
 }
 
@@ -944,7 +947,7 @@ __device__ __forceinline__ void fill_small_rect(const BinParams &P, const SlotBo
 __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinParams P, uint32_t pair_capacity) {
 	pdl_prologue();
 	if(P.ctr->pair_total > pair_capacity || P.ctr->pair_total == 0u) return; // draw skipped (MLV_FLAG_PAIR_OVERFLOW is set) / nothing survived Hi-Z
-	const uint32_t n = P.direct_slots + P.ctr->ovf_count;
+	const uint32_t n = P.direct_slots + min(P.ctr->ovf_count, P.ovf_capacity); // (a draw that ran out of overflow slots is skipped as a whole: k_bin_scan poisons pair_total)
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	for(uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < n; base += warps * 32u) {
@@ -1099,7 +1102,10 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 		if(tile == P.num_blocks - 1 && lane == 0) {
 			const uint32_t total = excl + block_total;
 			if(warp == 0) {
-				P.ctr->pair_total = total;
+				// A draw whose clipped triangles ran out of overflow slots (MLV_FLAG_TRI_OVERFLOW) is skipped as a whole,
+				// like one whose pairs do not fit: k_bin_fill and k_tile return when pair_total exceeds the capacity.
+				const bool tri_overflow = P.ctr->ovf_count > P.ovf_capacity;
+				P.ctr->pair_total = tri_overflow ? 0xffffffffu : total;
 				if(total > P.pair_capacity) atomicOr(&P.ctr->error_flags, MLV_FLAG_PAIR_OVERFLOW);
 			} else {
 				P.ctr->n_cbins = total; // k_tile ignores it when the pair arena overflowed
@@ -1318,7 +1324,7 @@ struct RowCovWarp {
 };
 
 template <int PS>
-__global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_constant__ TileParams P, uint32_t pair_capacity) {
+__global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_constant__ TileParams P, uint32_t pair_capacity, uint32_t ovf_capacity) {
 	__shared__ RowCovWarp s_rowcov[MLV_TILE_THREADS / 32];
 	pdl_prologue();
 	const uint32_t lane = lane_id();
@@ -1350,7 +1356,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_const
 			c->stats.assembled_triangle_count += tris;
 			c->stats.total_triangle_count_in_bins += pairs;
 			c->stats.active_bin_count += c->draw_active_bins;
-			c->last_ovf_count = c->ovf_count;
+			c->last_ovf_count = min(c->ovf_count, ovf_capacity);
 			c->draw_active_bins = 0u;
 			c->ovf_count = c->clip_count = c->big_count = c->huge_count = 0u;
 		}

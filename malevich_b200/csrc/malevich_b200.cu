@@ -42,13 +42,14 @@ struct mlv_buffer {
 	void *d;
 	size_t bytes;
 	int kind;
+	uint64_t uid;              // unique per buffer object for the life of the process (a freed buffer's address can come back)
 	uint64_t version;          // bumped by every update
 	cudaEvent_t ready;         // recorded on the copy stream after the last upload
 	bool ready_pending;        // no draw has waited on `ready` yet
 	// sort-first chunk bounds cached with the buffer that defines the triangle list (index buffer, or vertex buffer for mlv_draw)
 	float4 *chunk_bounds;
 	uint32_t chunk_capacity, chunk_count;
-	const mlv_buffer *chunk_vb;
+	uint64_t chunk_vb_uid;
 	uint64_t chunk_vb_version, chunk_self_version;
 	int chunk_indexed;
 	uint32_t chunk_start_index, chunk_index16;
@@ -68,6 +69,7 @@ struct mlv_device {
 	cudaStream_t stream;
 	int W, H, wt, ht;
 	uint32_t num_bins;
+	uint32_t sm_count; // cudaDevAttrMultiProcessorCount: persistent grids are sized in multiples of it
 	Partition part;
 
 	// persistent render state (reference: static frame_buffer/depth_buffer/a_tile_min_depths)
@@ -242,6 +244,7 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	memset(dev, 0, sizeof(*dev));
 	dev->desc = *desc;
 	dev->cuda_dev = cuda_dev;
+	dev->sm_count = prop.multiProcessorCount > 0 ? (uint32_t)prop.multiProcessorCount : 148u;
 	dev->W = (int)desc->width;
 	dev->H = (int)desc->height;
 	dev->wt = dev->W / 8;
@@ -396,6 +399,8 @@ int mlv_create_buffer(mlv_device *dev, const void *data, size_t bytes, int kind,
 	memset(b, 0, sizeof(*b));
 	b->bytes = bytes;
 	b->kind = kind;
+	static uint64_t next_uid = 0;
+	b->uid = __atomic_add_fetch(&next_uid, 1, __ATOMIC_RELAXED);
 	cudaError_t e = cudaMalloc(&b->d, (bytes + 15) & ~(size_t)15);
 	if(e == cudaSuccess && (e = cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming)) != cudaSuccess) cudaFree(b->d);
 	if(e != cudaSuccess) {
@@ -497,7 +502,7 @@ int mlv_texture_srgb_to_linear(mlv_device *dev, mlv_texture *tex) {
 	const size_t count_u4 = texel_count / 4;
 	const uint32_t tail = (uint32_t)(texel_count % 4);
 	size_t blocks = (count_u4 + 255) / 256;
-	if(blocks > 148u * 8u) blocks = 148u * 8u;
+	if(blocks > dev->sm_count * 8u) blocks = dev->sm_count * 8u;
 	if(blocks == 0) blocks = 1;
 	launch_pdl(k_texture_srgb_to_linear, (uint32_t)blocks, 256, dev->stream, (uint4 *)tex->d, count_u4, (uint32_t *)tex->d + count_u4 * 4, tail, table);
 	return check_launch(dev, "k_texture_srgb_to_linear");
@@ -531,7 +536,7 @@ int mlv_texture_generate_mips(mlv_device *dev, mlv_texture *tex) {
 	for(uint32_t l = 1; l < levels; ++l) {
 		const uint32_t sw = mip_extent_host(tex->width, l - 1), sh = mip_extent_host(tex->height, l - 1), dw = mip_extent_host(tex->width, l), dh = mip_extent_host(tex->height, l);
 		size_t blocks = ((size_t)dw * dh + 255) / 256;
-		if(blocks > 148u * 8u) blocks = 148u * 8u;
+		if(blocks > dev->sm_count * 8u) blocks = dev->sm_count * 8u;
 		launch_pdl(k_mip_downsample, (uint32_t)blocks, 256, dev->stream, src, (int)sw, (int)sh, dst, (int)dw, (int)dh);
 		if(int rc = check_launch(dev, "k_mip_downsample")) return rc;
 		src = dst;
@@ -723,7 +728,7 @@ static TexDesc tex_desc(const mlv_texture *t) {
 template <int VS>
 static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed, uint32_t vcache_vertices) {
 	const bool debug = gp.keep_all;
-	if(nblocks > 148u * 4u) nblocks = 148u * 4u; // persistent grid: 4 CTAs per SM stride over the chunks (sort-first: and cull them in place)
+	if(nblocks > dev->sm_count * 4u) nblocks = dev->sm_count * 4u; // persistent grid: 4 CTAs per SM stride over the chunks (sort-first: and cull them in place)
 	if(vcache_vertices) {
 		const int sel = dev->vcache_sel;
 		dev->vcache_sel ^= 1;
@@ -797,9 +802,11 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 
 	const uint32_t T = count / 3u;
 	if(T >= (1u << 28)) return fail(MLV_ERR_INVALID_ARGUMENT, "draw too large: triangle keys are (input_triangle << 3 | fan_index) in 32 bits");
-	// Slot capacity = the reference's own output capacity T + max(2T, 512) (main.c:739-740): T direct slots plus
-	// max(2T, 512) overflow slots for the fan triangles of clipped input triangles.
-	const uint32_t ovf_cap = (2u * T > 512u ? 2u * T : 512u);
+	// The reference bounds the triangles that SURVIVE culling by T + max(2T, 512) (main.c:739-740). Here a clipped input
+	// triangle leaves its direct slot empty and takes one overflow slot per fan triangle before they are culled, so the
+	// overflow arena holds max(3T, 512) slots: whatever fits the reference's bound fits here (e.g. every triangle of the
+	// draw clipped into a fan of three).
+	const uint32_t ovf_cap = (3u * T > 512u ? 3u * T : 512u);
 	const uint32_t need_slots = T + ovf_cap;
 	const uint32_t nblocks = (T + MLV_GEOM_THREADS - 1) / MLV_GEOM_THREADS;
 	const bool debug = (dev->desc.flags & MLV_DEVICE_DEBUG_CAPTURE) != 0;
@@ -885,7 +892,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	if(dev->part.num_ranks > 1 && !debug && (dev->vs_id == MLV_VS_BASIC || dev->vs_id == MLV_VS_VERTEX_LIGHTING)) {
 		mlv_buffer *owner = indexed ? dev->ib : dev->vb;
 		const bool valid = owner->chunk_bounds && owner->chunk_count == nblocks && owner->chunk_indexed == (indexed ? 1 : 0) && owner->chunk_self_version == owner->version &&
-		                   owner->chunk_vb == dev->vb && owner->chunk_vb_version == dev->vb->version && owner->chunk_start_index == start_index &&
+		                   owner->chunk_vb_uid == dev->vb->uid && owner->chunk_vb_version == dev->vb->version && owner->chunk_start_index == start_index &&
 		                   owner->chunk_base_vertex == base_vertex && owner->chunk_index16 == gp.ix.index16;
 		if(!valid) {
 			if(nblocks > owner->chunk_capacity) {
@@ -900,7 +907,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 			owner->chunk_count = nblocks;
 			owner->chunk_indexed = indexed ? 1 : 0;
 			owner->chunk_self_version = owner->version;
-			owner->chunk_vb = dev->vb;
+			owner->chunk_vb_uid = dev->vb->uid;
 			owner->chunk_vb_version = dev->vb->version;
 			owner->chunk_start_index = start_index;
 			owner->chunk_base_vertex = base_vertex;
@@ -942,7 +949,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 		// one thread per queued triangle: the clipper is a long dependent chain per triangle, so the queue is spread over
 		// as many warps as it has entries (concentrating it on fewer CTAs was measured slower: 28 vs 20 us)
 		uint32_t cb = (T * MLV_CLIP_SPLIT + MLV_CLIP_THREADS - 1u) / MLV_CLIP_THREADS;
-		if(cb > 148u * 4u) cb = 148u * 4u;
+		if(cb > dev->sm_count * 4u) cb = dev->sm_count * 4u;
 		prof_pre(dev, MLV_STAGE_CLIP);
 		switch(dev->vs_id) {
 			case MLV_VS_PASSTHROUGH: launch_geom_clip<0>(dev, gp, cb, indexed); break;
@@ -966,13 +973,14 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	bp.ctr = dev->ctr;
 	bp.stat_stripes = dev->stat_stripes;
 	bp.direct_slots = T;
+	bp.ovf_capacity = ovf_cap;
 	bp.num_bins = dev->num_bins;
 	bp.wt = dev->wt;
 	bp.ht = dev->ht;
 	bp.part = dev->part;
 	bp.keep_all = debug;
 	uint32_t big_blocks = (T + 7u) / 8u; // one warp per queued triangle, grid-stride
-	if(big_blocks > 148u * 4u) big_blocks = 148u * 4u;
+	if(big_blocks > dev->sm_count * 4u) big_blocks = dev->sm_count * 4u;
 	prof_pre(dev, MLV_STAGE_BIN_COUNT);
 	launch_pdl(k_bin_big, big_blocks, 256, dev->stream, bp);
 	if(int rc = check_launch(dev, "k_bin_big")) return rc;
@@ -989,6 +997,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	sp.bin_begin = dev->bin_begin;
 	sp.bin_end = dev->bin_end;
 	sp.pair_capacity = (uint32_t)dev->pair_capacity;
+	sp.ovf_capacity = ovf_cap;
 	sp.ticket_base = dev->ticket_base;
 	sp.epoch = dev->epoch;
 	sp.num_blocks = dev->scan_blocks;
@@ -998,7 +1007,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	if(int rc = check_launch(dev, "k_bin_scan")) return rc;
 
 	uint32_t bin_blocks = (need_slots + 255u) / 256u;
-	if(bin_blocks > 148u * 16u) bin_blocks = 148u * 16u;
+	if(bin_blocks > dev->sm_count * 16u) bin_blocks = dev->sm_count * 16u;
 	prof_pre(dev, MLV_STAGE_BIN_FILL);
 	launch_pdl(k_bin_fill, bin_blocks, 256, dev->stream, bp, (uint32_t)dev->pair_capacity);
 	if(int rc = check_launch(dev, "k_bin_fill")) return rc;
@@ -1023,14 +1032,14 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	tp.wt = dev->wt;
 	tp.sort_lists = debug;
 	uint32_t tile_blocks = (dev->num_bins + 7u) / 8u;
-	if(tile_blocks > 148u * 8u) tile_blocks = 148u * 8u;
+	if(tile_blocks > dev->sm_count * 8u) tile_blocks = dev->sm_count * 8u;
 	const uint32_t pcap = (uint32_t)dev->pair_capacity;
 	prof_pre(dev, MLV_STAGE_TILE);
 	switch(dev->ps_id) {
-		case MLV_PS_PASSTHROUGH: launch_pdl(k_tile<0>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
-		case MLV_PS_BASIC: launch_pdl(k_tile<1>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
-		case MLV_PS_BASIC_TRILINEAR: launch_pdl(k_tile<MLV_PS_ID_BASIC_TRILINEAR>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
-		default: launch_pdl(k_tile<2>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap); break;
+		case MLV_PS_PASSTHROUGH: launch_pdl(k_tile<0>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap, ovf_cap); break;
+		case MLV_PS_BASIC: launch_pdl(k_tile<1>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap, ovf_cap); break;
+		case MLV_PS_BASIC_TRILINEAR: launch_pdl(k_tile<MLV_PS_ID_BASIC_TRILINEAR>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap, ovf_cap); break;
+		default: launch_pdl(k_tile<2>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap, ovf_cap); break;
 	}
 	if(int rc = check_launch(dev, "k_tile")) return rc;
 	CUDA_TRY(cudaEventRecord(dev->ev_last_draw, dev->stream));
@@ -1049,7 +1058,7 @@ int mlv_draw_indexed_ex(mlv_device *dev, uint32_t index_count, uint32_t start_in
 // ---- results -------------------------------------------------------------------------------------
 
 static int check_flags(mlv_device *dev, const Counters &c) {
-	if(c.error_flags & MLV_FLAG_TRI_OVERFLOW) return fail(MLV_ERR_CAPACITY, "a draw assembled more than T + max(2T,512) triangles (the reference's own buffer bound, main.c:739-740)");
+	if(c.error_flags & MLV_FLAG_TRI_OVERFLOW) return fail(MLV_ERR_CAPACITY, "a draw clipped its triangles into more than max(3T,512) fan triangles (the reference bounds its output by T + max(2T,512), main.c:739-740); that draw was skipped");
 	if(c.error_flags & MLV_FLAG_COMPOSITE_TIMEOUT) return fail(MLV_ERR_STATE, "peer-memory compositing: a rank's stripes did not arrive within 10 s");
 	if(c.error_flags & MLV_FLAG_PAIR_OVERFLOW)
 		return fail(MLV_ERR_CAPACITY, "a draw produced more (triangle,tile) pairs than max_pairs_per_draw = %llu; that draw was skipped", (unsigned long long)dev->pair_capacity);
@@ -1252,6 +1261,8 @@ int mlv_composite_broadcast(mlv_device *dev) {
 	if(dev->bcast_pending) return fail(MLV_ERR_STATE, "mlv_composite_wait must follow every mlv_composite_broadcast");
 	if(dev->xchg_pending) return fail(MLV_ERR_STATE, "mlv_composite_join must follow every mlv_composite_broadcast_async");
 	if(int rc = flush_clears(dev)) return rc;
+	// peers overwrite the image a read-back may still be copying only after this broadcast has run (they wait for it)
+	if(dev->readback_in_flight) CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_readback_done, 0));
 	const uint32_t seq = ++dev->p2p_seq;
 	PeerTargets t;
 	memset(&t, 0, sizeof(t));
@@ -1458,6 +1469,38 @@ int mlv_debug_read_masks(mlv_device *dev, mlv_ref_tile_info *infos, uint32_t *ou
 	return MLV_OK;
 }
 
+// The key of every assembled triangle of the last draw in ascending order, i.e. keys[i] = device key of the reference's
+// triangle id i (mlv_internal.cuh "Triangle identity").
+int mlv_debug_read_keys(mlv_device *dev, uint32_t *keys, uint32_t *out_count) {
+	Counters c;
+	if(int rc = debug_counters(dev, &c)) return rc;
+	if(dev->last_index_count == 0) {
+		if(out_count) *out_count = 0;
+		return MLV_OK;
+	}
+	DebugMap m;
+	if(int rc = build_debug_map(dev, c, m)) return rc;
+	if(out_count) *out_count = (uint32_t)m.keys.size();
+	if(keys && !m.keys.empty()) memcpy(keys, m.keys.data(), m.keys.size() * sizeof(uint32_t));
+	return MLV_OK;
+}
+
+// The per-tile lists of the last draw exactly as k_tile consumed them -- device keys, in arrival order, Hi-Z-rejected
+// pairs already removed -- and the work list of bins. Works WITHOUT debug capture: this is the production data path.
+int mlv_read_bin_lists(mlv_device *dev, uint32_t *keys, uint32_t *out_pair_count, mlv_ref_compacted_bin *bins, uint32_t *out_bin_count) {
+	if(int rc = use_device(dev)) return rc;
+	Counters c;
+	CUDA_TRY(cudaMemcpyAsync(&c, dev->ctr, sizeof(c), cudaMemcpyDeviceToHost, dev->stream));
+	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	const bool skipped = c.pair_total > dev->pair_capacity || dev->last_index_count == 0;
+	const uint32_t pairs = skipped ? 0u : c.pair_total, nb = skipped ? 0u : c.n_cbins;
+	if(out_pair_count) *out_pair_count = pairs;
+	if(out_bin_count) *out_bin_count = nb;
+	if(keys && pairs) CUDA_TRY(cudaMemcpy(keys, dev->pair_ids, (size_t)pairs * 4, cudaMemcpyDeviceToHost));
+	if(bins && nb) CUDA_TRY(cudaMemcpy(bins, dev->cbins, (size_t)nb * sizeof(mlv_ref_compacted_bin), cudaMemcpyDeviceToHost));
+	return check_flags(dev, c);
+}
+
 int mlv_debug_read_tile_min_depths(mlv_device *dev, float *out_bins) {
 	if(int rc = use_device(dev)) return rc;
 	if(!out_bins) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
@@ -1515,5 +1558,13 @@ int mlv_profile_read_events(mlv_device *dev, mlv_profile_event *out, uint32_t ca
 }
 
 uint64_t mlv_kernel_launch_count(mlv_device *dev) { return dev ? dev->launches : 0; }
+
+// Word-wise 64-bit FNV-1a over u32 words (h = 0xcbf29ce484222325; h ^= w; h *= 0x100000001b3): the frame hash of
+// tests/golden/golden.json, so that a host can compare a read-back frame with the committed one without Python loops.
+uint64_t mlv_fnv64_words(const uint32_t *words, size_t count) {
+	uint64_t h = 0xcbf29ce484222325ull;
+	for(size_t i = 0; i < count; ++i) h = (h ^ (uint64_t)words[i]) * 0x100000001b3ull;
+	return h;
+}
 
 } // extern "C"

@@ -138,6 +138,7 @@ struct BinParams {
 	Counters *ctr;
 	unsigned long long *stat_stripes;
 	uint32_t direct_slots; // T
+	uint32_t ovf_capacity;
 	uint32_t num_bins;
 	int wt, ht;
 	Partition part;
@@ -153,6 +154,7 @@ struct ScanParams {
 	const float *tile_min;
 	uint32_t bin_begin, bin_end; // this rank's bins (the whole render target unless it owns one contiguous band)
 	uint32_t pair_capacity;
+	uint32_t ovf_capacity;
 	uint32_t ticket_base, epoch, num_blocks;
 };
 

@@ -466,6 +466,23 @@ class Device:
         L.check(self._lib.mlv_debug_read_masks(self._h, infos.ctypes.data_as(C.c_void_p), C.byref(n)))
         return infos
 
+    def debug_keys(self) -> np.ndarray:
+        """keys[i] = device key of the reference's assembled triangle id i of the last draw (debug capture)."""
+        n = C.c_uint32()
+        L.check(self._lib.mlv_debug_read_keys(self._h, None, C.byref(n)))
+        keys = np.empty(n.value, dtype=np.uint32)
+        L.check(self._lib.mlv_debug_read_keys(self._h, keys.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return keys
+
+    def bin_lists(self):
+        """(keys, bins) of the last draw as the production path built them: Hi-Z-rejected pairs removed, arrival order."""
+        npairs, nbins = C.c_uint32(), C.c_uint32()
+        L.check(self._lib.mlv_read_bin_lists(self._h, None, C.byref(npairs), None, C.byref(nbins)))
+        keys = np.empty(npairs.value, dtype=np.uint32)
+        bins = np.empty(nbins.value, dtype=REF_COMPACTED_BIN_DTYPE)
+        L.check(self._lib.mlv_read_bin_lists(self._h, keys.ctypes.data_as(C.c_void_p), C.byref(npairs), bins.ctypes.data_as(C.c_void_p), C.byref(nbins)))
+        return keys, bins
+
     def debug_tile_min_depths(self) -> np.ndarray:
         out = np.empty((self.height // 8) * (self.width // 8), dtype=np.float32)
         L.check(self._lib.mlv_debug_read_tile_min_depths(self._h, out.ctypes.data_as(C.c_void_p)))

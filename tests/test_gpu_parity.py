@@ -618,3 +618,177 @@ def test_no_cpu_fallback_and_kernels_launch():
         scenes.render(dev, sc)
         dev.present()
         assert dev.kernel_launch_count - n0 == 1 + 7 + 1  # fused clear + (vertex cache, geom, clip, big-count, scan, fill, tile) + resolve
+
+
+# ---- production path (no debug capture): the kernels bench.py times --------------------------------------------------
+
+def _render_production_draw_by_draw(dev, orc, sc, per_draw):
+    """Same frame on the production device (Hi-Z at binning time, unsorted lists, vertex cache, no record for hidden
+    triangles) and on the live reference, draw by draw; `per_draw(i, obj, tile_min_before)` runs after each pair of draws."""
+    from malevich_b200 import scenes as S
+    import malevich_b200._lib as L
+    dev.clear_render_target_view(S.CLEAR_COLOR)
+    dev.clear_depth_stencil_view(S.CLEAR_DEPTH)
+    orc.begin_frame(sc.per_frame_cb, S.CLEAR_COLOR, S.CLEAR_DEPTH)
+    dev.reset_stats()
+    gp = dev.graphics_pipeline
+    gp.ia.primitive_topology = L.PRIMITIVE_TOPOLOGY_TRIANGLELIST
+    gp.rs.viewport.width, gp.rs.viewport.height = float(sc.width), float(sc.height)
+    gp.rs.viewport.top_left_x = gp.rs.viewport.top_left_y = 0.0
+    gp.rs.viewport.min_depth, gp.rs.viewport.max_depth = 0.0, 1.0
+    gp.vs.p_constant_buffers[0] = sc.per_frame_cb
+    for i, o in enumerate(sc.objects):
+        tile_min_before = orc.tile_min_depths()
+        gp.ia.input_layout = o.vertex_shader.in_vertex_size // 8
+        gp.vs.output_register_count = o.vertex_shader.out_vertex_size // 128
+        gp.vs.shader, gp.ps.shader = o.vertex_shader, o.pixel_shader
+        gp.ia.p_index_buffer, gp.ia.p_vertex_buffer = o.index_buffer, o.vertex_buffer
+        gp.vs.p_shader_resource_views[0] = gp.ps.p_shader_resource_views[0] = o.texture
+        dev.draw_indexed(o.index_count)
+        orc.draw(o.vertex_buffer, o.index_buffer, o.vertex_shader.vs_main, o.pixel_shader.ps_main, o.texture, staged=True)
+        per_draw(i, o, tile_min_before)
+
+
+@pytest.mark.parametrize("name", sorted(cases.FULL))
+def test_production_path_full_size_against_live_reference(name):
+    """BASELINE configs 1-4 (+ SUPREMATISM, the screenshot scene) at full resolution through the PRODUCTION kernels --
+    debug_capture off, i.e. exactly what bench.py times -- compared with the live reference after EVERY draw: depth
+    bit-exact, tile minima equal, colour within tolerance, and at the end Stats + the committed depth hash."""
+    sc = cases.FULL[name]()
+    if not have_ref(sc.width, sc.height):
+        pytest.skip("oracle/_ref not available for this resolution")
+    orc = _oracle(sc.width, sc.height)
+    if not parity.host_vrsqrtps_matches_table(orc):
+        pytest.skip("host vrsqrtps differs from the committed Intel table")
+    with _device(sc.width, sc.height) as dev:
+        def check(i, o, _):
+            col, dep = dev.present()
+            parity.assert_frames_match(col, dep, orc.colors(), orc.depths(), f"{name} after draw {i} ({o.name})")
+            assert np.array_equal(dev.debug_tile_min_depths(), orc.tile_min_depths()), f"{name}: tile minima differ after draw {i}"
+        _render_production_draw_by_draw(dev, orc, sc, check)
+        col, dep = dev.present()
+        assert dev.stats() == orc.stats() == GOLDEN[name]["stats"]
+    assert _fnv(dep) == GOLDEN[name]["depth_fnv"]
+    from malevich_b200._lib import fnv64_words
+    assert fnv64_words(dep) == GOLDEN[name]["depth_fnv"]  # the library's own hash helper (what bench.py prints) agrees
+
+
+@pytest.mark.parametrize("name", sorted(cases.SMALL) + ["config1_toon_1280x720", "config2_ftm_1920x1080"])
+def test_production_bin_lists_equal_reference_lists_minus_hiz_rejected_pairs(name):
+    """The per-tile lists k_tile consumes in production (fused counting in k_geom / k_geom_clip / k_bin_big, scan, unordered
+    fill, Hi-Z at binning time) are, per bin and as sorted sets, the reference's triangle_ids (main.c:950-962) minus the
+    pairs its rasterizer rejects by Hi-Z (tri.max_depth < a_tile_min_depths[bin], main.c:1003-1010); a bin is on the
+    work list iff it has a surviving pair (or is visited for write_tile's tile-minimum refresh only). Keys are mapped to the
+    reference's ids through a debug-capture device rendering the same frame."""
+    sc = {**cases.SMALL, **cases.FULL}[name]()
+    if not have_ref(sc.width, sc.height):
+        pytest.skip("oracle/_ref not available for this resolution")
+    orc = _oracle(sc.width, sc.height)
+    if not parity.host_vrsqrtps_matches_table(orc):
+        pytest.skip("host vrsqrtps differs from the committed Intel table")
+    # pass 1: key of every reference id, per draw (debug capture)
+    keys_by_id = []
+    with _device(sc.width, sc.height, debug_capture=True) as dbg:
+        _render_production_draw_by_draw(dbg, orc, sc, lambda i, o, tm: keys_by_id.append(dbg.debug_keys()))
+    # pass 2: production lists
+    with _device(sc.width, sc.height) as dev:
+        def check(i, o, tile_min_before):
+            tris, _ = orc.staged_triangles()
+            ids, rbins = orc.staged_bins()
+            keys, gbins = dev.bin_lists()
+            kmap = keys_by_id[i]
+            assert len(kmap) == len(tris)
+            got = {int(b["bin_index"]): np.sort(keys[int(b["num_triangles_upto"]):int(b["num_triangles_upto"]) + int(b["num_triangles_self"])]) for b in gbins}
+            assert len(got) == len(gbins), "a bin is listed twice"
+            assert np.all(np.diff(gbins["bin_index"].astype(np.int64)) > 0), "work list not in ascending bin order"
+            ref_bins = set()
+            for b in rbins:
+                bi = int(b["bin_index"])
+                ref_bins.add(bi)
+                lst = ids[int(b["num_triangles_upto"]):int(b["num_triangles_upto"]) + int(b["num_triangles_self"])]
+                keep = ~(tris["max_depth"][lst] < tile_min_before[bi])
+                want = kmap[lst[keep]]
+                if want.size:
+                    assert bi in got and np.array_equal(got[bi], want), f"{name} draw {i} bin {bi}: list differs"
+                else:
+                    assert bi not in got or got[bi].size == 0, f"{name} draw {i} bin {bi}: pairs that Hi-Z rejects are listed"
+            assert set(got) <= ref_bins, f"{name} draw {i}: bins on the work list that the reference leaves empty"
+            assert int(sum(g.size for g in got.values())) == len(keys)
+        _render_production_draw_by_draw(dev, orc, sc, check)
+        assert dev.stats() == orc.stats()
+
+
+def test_every_triangle_clipped_into_a_fan_of_three():
+    """a draw whose triangles ALL cross two frustum planes (fan of 3 each) fills 3T overflow slots. The
+    reference renders it (3T surviving triangles <= T + max(2T, 512), main.c:739-740); so must the device, bit-exact."""
+    from malevich_b200 import scenes
+    from malevich_b200.device import passthrough_ps, passthrough_vs
+    W, H = 320, 200
+    if not have_ref(W, H):
+        pytest.skip("oracle/_ref not available")
+    n = 512  # triangles (index count 1536: divisible by 8 and 3)
+    rng = np.random.default_rng(11)
+    vb = np.zeros((3 * n, 8), np.float32)
+    for t in range(n):
+        # passthrough_vs maps x,y in [0,1] to clip [-1,1] (w = 1): one vertex inside, two beyond the right AND the top plane,
+        # clockwise/counter-clockwise chosen so that the triangle survives back-face culling (signed_area <= 0)
+        cx, cy = rng.uniform(0.55, 0.9, 2)
+        p = np.array([[cx, cy], [cx + 0.5, cy + 0.05], [cx + 0.05, cy + 0.5]], np.float32)
+        z = np.float32(rng.uniform(0.2, 0.8))
+        vb[3 * t:3 * t + 3, 0:2] = p
+        vb[3 * t:3 * t + 3, 2] = z
+        vb[3 * t:3 * t + 3, 3] = 1.0
+        vb[3 * t:3 * t + 3, 4:7] = rng.uniform(0, 1, (3, 3)).astype(np.float32)
+    ib = np.arange(3 * n, dtype=np.uint32)
+    sc = scenes.Scene("fan3", W, H, [scenes.SceneObject(vb, ib, passthrough_vs, passthrough_ps, None, "fan3")], np.zeros((3, 4, 4), np.float32))
+    orc = _oracle(W, H)
+    orc.render(sc)
+    st_ref = orc.stats()
+    assert st_ref["assembled_triangle_count"] > 2 * n, f"test geometry no longer clips into fans of three: {st_ref}"
+    for debug in (False, True):
+        with _device(W, H, debug_capture=debug) as dev:
+            scenes.render(dev, sc)
+            col, dep = dev.present()
+            assert dev.stats() == st_ref
+        parity.assert_frames_match(col, dep, orc.colors(), orc.depths(), f"fan3 debug={debug}")
+
+
+def test_out_of_range_and_infinite_vertices_snap_like_x86():
+    """the reference's (i32) casts of the snapped coordinates are x86 cvttsd2si -- 0x80000000 for NaN and for
+    anything outside the i32 range (huge x/w, w = Inf) -- and such triangles are assembled, bounded and binned from those
+    values. Staged comparison against the live reference on vertices that provoke every case."""
+    from malevich_b200 import scenes
+    from malevich_b200.device import passthrough_ps, passthrough_vs
+    W, H = 320, 200
+    if not have_ref(W, H):
+        pytest.skip("oracle/_ref not available")
+    big, inf = np.float32(3.0e7), np.float32(np.inf)
+    tris = [
+        [(0.2, 0.2, 0.5, 1.0), (0.8, 0.3, 0.5, 1.0), (0.4, 0.9, 0.5, 1.0)],          # ordinary (control)
+        [(0.5, 0.5, 0.5, inf), (0.6, 0.5, 0.5, 1.0), (0.5, 0.6, 0.5, 1.0)],           # w = Inf: rw = 0, x*rw = 0
+        [(0.5 * big, 0.5, 0.5, big), (0.6, 0.5, 0.5, 1.0), (0.5, 0.7, 0.5, 1.0)],      # huge but consistent
+        [(0.3, 0.3, 0.5, 1e-30), (0.3, 0.3, 0.5, 1e-30), (0.3, 0.3, 0.5, 1e-30)],      # x/w far outside the i32 range
+        [(inf, 0.5, 0.5, inf), (0.6, 0.5, 0.5, 1.0), (0.5, 0.7, 0.5, 1.0)],            # Inf * 0 = NaN
+        [(0.1, 0.1, 0.5, 1.0), (0.1, 0.1, 0.5, 1.0), (0.1, 0.1, 0.5, 1.0)],            # degenerate point
+        [(0.7, 0.2, 0.25, 1.0), (0.9, 0.2, 0.25, 1.0), (0.8, 0.4, 0.25, 1.0)],
+        [(0.2, 0.7, 0.75, 1.0), (0.4, 0.7, 0.75, 1.0), (0.3, 0.9, 0.75, 1.0)],
+    ]
+    vb = np.zeros((24, 8), np.float32)
+    for t, tri in enumerate(tris):
+        for k, v in enumerate(tri):
+            vb[3 * t + k, 0:4] = v
+            vb[3 * t + k, 4:7] = (0.25 * k + 0.1, 0.5, 0.125 * t)
+    sc = scenes.Scene("snap", W, H, [scenes.SceneObject(vb, np.arange(24, dtype=np.uint32), passthrough_vs, passthrough_ps, None, "snap")], np.zeros((3, 4, 4), np.float32))
+    orc = _oracle(W, H)
+    with np.errstate(all="ignore"):
+        with _device(W, H, debug_capture=True) as dev:
+            for draw_name, res in parity.render_both_staged(dev, orc, sc):
+                assert parity.staged_ok(res), f"{draw_name}: {res}"
+            col, dep = dev.present()
+            assert dev.stats() == orc.stats()
+        parity.assert_frames_match(col, dep, orc.colors(), orc.depths(), "snap")
+        with _device(W, H) as dev:
+            scenes.render(dev, sc)
+            col, dep = dev.present()
+            assert dev.stats() == orc.stats()
+        parity.assert_frames_match(col, dep, orc.colors(), orc.depths(), "snap production")
