@@ -179,6 +179,25 @@ MLV_API int mlv_draw_indexed(mlv_device *dev, uint32_t index_count);            
 MLV_API int mlv_draw_indexed_ex(mlv_device *dev, uint32_t index_count, uint32_t start_index_location, int32_t base_vertex_location); /* ID3D11DeviceContext::DrawIndexed in full: the reference's TODO at main.c:1219 */
 MLV_API int mlv_draw(mlv_device *dev, uint32_t vertex_count);                   /* draw_indexed with identity indices (all shipped meshes) */
 
+/* ---- command lists: the frame recorded once, replayed with one launch ------------------------------------------------
+ * D3D11's deferred-context pattern (ID3D11DeviceContext::FinishCommandList / ExecuteCommandList), which the reference --
+ * an immediate-mode CPU renderer whose render() (main.c:1265-1299) re-issues every call every frame -- has no analogue of.
+ * Between mlv_begin_command_list and mlv_finish_command_list the state setters, clears, draws, mlv_resolve,
+ * mlv_reset_stats and mlv_composite_pack are RECORDED (captured into a CUDA graph) instead of executed; everything that
+ * synchronises, reads back or exchanges with peers fails with MLV_ERR_STATE. mlv_execute_command_list replays the recording:
+ * one launch instead of ~7 per draw. The recording binds buffer and texture OBJECTS, not their contents: mlv_update_buffer
+ * between executions is honoured (the execution waits for it). The vertex-shader constant buffer is recorded by value;
+ * mlv_command_list_set_constants replaces it (for one draw or MLV_ALL_DRAWS) without re-recording -- what update()
+ * (main.c:1480-1562) changes per frame. Buffers, textures and the list must outlive its executions. */
+typedef struct mlv_command_list mlv_command_list;
+#define MLV_ALL_DRAWS 0xffffffffu
+MLV_API int mlv_begin_command_list(mlv_device *dev);
+MLV_API int mlv_finish_command_list(mlv_device *dev, mlv_command_list **out_list);
+MLV_API int mlv_execute_command_list(mlv_device *dev, mlv_command_list *list);
+MLV_API int mlv_command_list_set_constants(mlv_device *dev, mlv_command_list *list, uint32_t draw_index, const void *data, size_t bytes);
+MLV_API int mlv_command_list_info(const mlv_command_list *list, uint32_t *out_draws, uint64_t *out_kernel_launches);
+MLV_API void mlv_release_command_list(mlv_device *dev, mlv_command_list *list);
+
 /* ---- results ---------------------------------------------------------------------------------- */
 /* Replaces the GDI blit of frame_buffer (paint_window main.c:286-357): row-major y*W+x, colour
  * 0x00RRGGBB from the PS path, depth f32 reversed-Z. Either pointer may be NULL. Synchronises.

@@ -7,5 +7,5 @@ fails loudly when the CUDA extension is missing or no B200 is visible.
 """
 from . import _lib  # noqa: F401
 from ._lib import MalevichError  # noqa: F401
-from .device import (Device, PixelShader, Texture2D, VertexShader, basic_ps, basic_trilinear_ps, basic_vs, env_lighting_ps,  # noqa: F401
+from .device import (CommandList, Device, PixelShader, Texture2D, VertexShader, basic_ps, basic_trilinear_ps, basic_vs, env_lighting_ps,  # noqa: F401
                      fullscreen_vs, passthrough_ps, passthrough_vs, vertex_lighting_vs)

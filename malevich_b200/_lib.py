@@ -15,6 +15,7 @@ EXPORTED_SYMBOLS = [
     "mlv_vs_set_shader", "mlv_vs_set_constant_buffer", "mlv_vs_set_shader_resource", "mlv_rs_set_viewport",
     "mlv_ps_set_shader", "mlv_ps_set_shader_resource",
     "mlv_clear_render_target_view", "mlv_clear_depth_stencil_view", "mlv_draw_indexed", "mlv_draw_indexed_ex", "mlv_draw",
+    "mlv_begin_command_list", "mlv_finish_command_list", "mlv_execute_command_list", "mlv_command_list_set_constants", "mlv_command_list_info", "mlv_release_command_list",
     "mlv_present_readback", "mlv_present_readback_async", "mlv_present_wait", "mlv_get_stats", "mlv_reset_stats", "mlv_get_work_counters",
     "mlv_resolve", "mlv_resolved_color_device_ptr", "mlv_resolved_depth_device_ptr",
     "mlv_composite_peer_export", "mlv_composite_peer_attach", "mlv_composite_broadcast", "mlv_composite_wait", "mlv_composite_broadcast_async", "mlv_composite_join", "mlv_composite_readback_async", "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
@@ -32,6 +33,7 @@ FORMAT_R8G8B8A8_UNORM, FORMAT_R32G32B32A32_FLOAT = 0, 1
 BUFFER_VERTEX, BUFFER_INDEX = 0, 1
 INDEX_U32, INDEX_U16 = 0, 1
 DEVICE_DEBUG_CAPTURE = 1
+ALL_DRAWS = 0xFFFFFFFF
 
 
 class WorkCounters(C.Structure):
@@ -123,6 +125,12 @@ def load() -> C.CDLL:
         "mlv_draw_indexed": (i32, [vp, u32]),
         "mlv_draw_indexed_ex": (i32, [vp, u32, u32, C.c_int32]),
         "mlv_draw": (i32, [vp, u32]),
+        "mlv_begin_command_list": (i32, [vp]),
+        "mlv_finish_command_list": (i32, [vp, P(vp)]),
+        "mlv_execute_command_list": (i32, [vp, vp]),
+        "mlv_command_list_set_constants": (i32, [vp, vp, u32, vp, sz]),
+        "mlv_command_list_info": (i32, [vp, P(u32), P(C.c_uint64)]),
+        "mlv_release_command_list": (None, [vp, vp]),
         "mlv_present_readback": (i32, [vp, vp, vp]),
         "mlv_present_readback_async": (i32, [vp, vp, vp]),
         "mlv_present_wait": (i32, [vp]),

@@ -1038,9 +1038,12 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 	__shared__ uint32_t s_sum[32], s_nz[32];
 	__shared__ uint32_t s_excl[2];
 	// CTAs take their logical position from a ticket so that every predecessor a CTA may wait on has started
-	if(threadIdx.x == 0) s_tile = atomicAdd(&P.ctr->ticket, 1u) - P.ticket_base;
+	// (the ticket counter is re-armed and the epoch advanced by k_tile at the end of every draw: nothing per draw comes from
+	// the host, so a recorded frame -- a CUDA graph, mlv_execute_command_list -- replays unchanged)
+	if(threadIdx.x == 0) s_tile = atomicAdd(&P.ctr->ticket, 1u);
 	__syncthreads();
 	const uint32_t tile = s_tile;
+	const uint32_t epoch = P.ctr->epoch;
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 	const uint32_t base = P.bin_begin + (tile * MLV_SCAN_THREADS + threadIdx.x) * MLV_SCAN_ITEMS; // 4 consecutive bins per thread, 16-byte accesses
 	uint32_t raw[MLV_SCAN_ITEMS], c[MLV_SCAN_ITEMS];
@@ -1095,7 +1098,7 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 			if(lane >= (uint32_t)d) wincl += o;
 		}
 		const uint32_t block_total = __shfl_sync(0xffffffffu, wincl, 31);
-		const uint32_t excl = lookback_exclusive(warp == 0 ? P.state_sum : P.state_nz, tile, P.epoch, block_total);
+		const uint32_t excl = lookback_exclusive(warp == 0 ? P.state_sum : P.state_nz, tile, epoch, block_total);
 		if(warp == 0) s_sum[lane] = wincl - v;
 		else s_nz[lane] = wincl - v;
 		if(lane == 0) s_excl[warp] = excl;
@@ -1359,7 +1362,18 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_const
 			c->last_ovf_count = min(c->ovf_count, ovf_capacity);
 			c->draw_active_bins = 0u;
 			c->ovf_count = c->clip_count = c->big_count = c->huge_count = 0u;
+			c->ticket = 0u;
 		}
+		// the epoch tags the look-back words of the next draw's scan; when its 30 bits wrap (after 2^30 draws) every
+		// published scan entry is invalidated
+		uint32_t next_epoch = 0u;
+		if(lane == 0) next_epoch = (P.ctr->epoch + 1u) & 0x3fffffffu;
+		next_epoch = __shfl_sync(0xffffffffu, next_epoch, 0);
+		if(next_epoch == 0u) {
+			for(uint32_t i = lane; i < P.scan_words; i += 32u) P.scan_state[i] = 0ull;
+			next_epoch = 1u;
+		}
+		if(lane == 0) P.ctr->epoch = next_epoch;
 	}
 	if(P.ctr->pair_total > pair_capacity) return; // draw skipped, MLV_FLAG_PAIR_OVERFLOW is set
 	const uint32_t n_cbins = P.ctr->n_cbins;

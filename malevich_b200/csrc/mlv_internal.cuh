@@ -44,7 +44,7 @@ struct Counters {
 	uint32_t pair_total;  // (triangle,tile) pairs of the current draw
 	uint32_t n_cbins;     // non-empty bins of the current draw (0 if the pair arena overflowed)
 	uint32_t error_flags; // sticky MLV_FLAG_*
-	uint32_t ticket;      // monotonically increasing block ticket (look-back scans)
+	uint32_t ticket;      // block ticket of the current draw's look-back scan (reset by k_tile)
 	uint32_t draw_tris;   // assembled triangles of the current draw
 	uint32_t last_ovf_count; // ovf_count of the last finished draw (debug read-back)
 	uint32_t clip_count;  // input triangles queued for k_geom_clip in the current draw (reset by k_tile)
@@ -53,7 +53,8 @@ struct Counters {
 	uint32_t draw_active_bins; // non-empty bins of the current draw in the reference's sense (Stats)
 	uint32_t huge_count;  // triangles with more than MLV_HUGE_TILES tiles in the current draw (reset by k_tile)
 	uint32_t bcast_done;  // CTAs of k_composite_broadcast that have finished their stores (reset by the last one)
-	uint32_t pad[3];
+	uint32_t epoch;       // draw epoch tagging the scan's look-back words (advanced by k_tile; never 0)
+	uint32_t pad[2];
 	mlv_stats stats;      // accumulated like reference main.c:1228-1246
 	mlv_work_counters work; // what the kernels really processed (Hi-Z at binning time removes work the reference's Stats still count)
 };
@@ -124,6 +125,7 @@ struct GeomParams {
 	Counters *ctr;
 	unsigned long long *stat_stripes;
 	uint32_t index_count;
+	uint32_t draw_ordinal; // position of the draw inside a recorded command list (identifies the kernel nodes whose constants are updated)
 };
 
 struct BinParams {
@@ -155,7 +157,7 @@ struct ScanParams {
 	uint32_t bin_begin, bin_end; // this rank's bins (the whole render target unless it owns one contiguous band)
 	uint32_t pair_capacity;
 	uint32_t ovf_capacity;
-	uint32_t ticket_base, epoch, num_blocks;
+	uint32_t num_blocks;
 };
 
 struct TileParams {
@@ -171,6 +173,8 @@ struct TileParams {
 	TexDesc ps_tex;
 	const uint32_t *rsqrt_lut;
 	DebugOut dbg;
+	unsigned long long *scan_state; // look-back words of k_bin_scan (cleared when the epoch wraps)
+	uint32_t scan_words;
 	uint32_t direct_slots; // T
 	uint32_t key_bits;
 	int wt;

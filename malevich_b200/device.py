@@ -328,6 +328,32 @@ class Device:
         self._bind(False)
         L.check(self._lib.mlv_draw(self._h, int(vertex_count)))
 
+    # ---- command lists (D3D11 deferred-context pattern; one CUDA-graph launch per frame) ---------
+    def begin_command_list(self):
+        """Start recording: clears / draws / resolve issued from now on are captured instead of executed."""
+        L.check(self._lib.mlv_begin_command_list(self._h))
+
+    def finish_command_list(self) -> "CommandList":
+        h = C.c_void_p()
+        L.check(self._lib.mlv_finish_command_list(self._h, C.byref(h)))
+        return CommandList(self, h)
+
+    def record(self, fn) -> "CommandList":
+        """Records whatever `fn()` issues on this device into a command list."""
+        self.begin_command_list()
+        try:
+            fn()
+        except Exception:
+            try:
+                self.finish_command_list().release()
+            except Exception:
+                pass
+            raise
+        return self.finish_command_list()
+
+    def execute_command_list(self, cl: "CommandList"):
+        L.check(self._lib.mlv_execute_command_list(self._h, cl._h))
+
     # ---- results ---------------------------------------------------------------------------------
     def present(self, want_depth: bool = True):
         """-> (colors uint32 [H, W], depths float32 [H, W] or None); replaces the GDI blit (main.c:286-357)."""
@@ -487,3 +513,29 @@ class Device:
         out = np.empty((self.height // 8) * (self.width // 8), dtype=np.float32)
         L.check(self._lib.mlv_debug_read_tile_min_depths(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
+
+
+class CommandList:
+    """A recorded frame (mlv_command_list). `set_constants` replaces the vertex-shader constant buffer of one draw or of
+    all of them without re-recording -- the per-frame camera update of the reference's loop (main.c:1480-1562, 1595-1597)."""
+
+    def __init__(self, dev: Device, handle):
+        self._dev, self._h = dev, handle
+
+    def execute(self):
+        self._dev.execute_command_list(self)
+
+    def set_constants(self, cb: np.ndarray, draw_index: int = L.ALL_DRAWS):
+        raw = np.ascontiguousarray(cb, dtype=np.float32)
+        L.check(self._dev._lib.mlv_command_list_set_constants(self._dev._h, self._h, int(draw_index), raw.ctypes.data_as(C.c_void_p), raw.nbytes))
+
+    @property
+    def info(self) -> dict:
+        d, k = C.c_uint32(), C.c_uint64()
+        L.check(self._dev._lib.mlv_command_list_info(self._h, C.byref(d), C.byref(k)))
+        return {"draws": int(d.value), "kernel_launches": int(k.value)}
+
+    def release(self):
+        if self._h and self._dev._h:
+            self._dev._lib.mlv_release_command_list(self._dev._h, self._h)
+        self._h = None

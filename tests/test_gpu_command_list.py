@@ -1,0 +1,170 @@
+"""GPU tests (`-m gpu`) of command lists (mlv_begin/finish/execute_command_list): a recorded frame replayed with one CUDA-graph
+launch must give exactly the frame the immediate calls give -- image, depth, Stats -- also across constant-buffer updates,
+buffer uploads between executions, arenas that grow while recording, and sort-first ranks."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _device(*a, **k):
+    from malevich_b200 import Device
+    return Device(*a, **k)
+
+
+def _immediate(sc):
+    from malevich_b200 import scenes
+    with _device(sc.width, sc.height) as dev:
+        dev.reset_stats()
+        scenes.render(dev, sc)
+        col, dep = dev.present()
+        return col, dep, dev.stats()
+
+
+@pytest.mark.parametrize("name", ["toon_320x200", "ftm_320x200", "emily_320x200", "synth_320x200"])
+def test_recorded_frame_replays_bit_identically(name):
+    from malevich_b200 import scenes
+    sc = cases.SMALL[name]()
+    ref_col, ref_dep, ref_stats = _immediate(sc)
+    with _device(sc.width, sc.height) as dev:  # fresh device: every arena grows WHILE recording
+        def frame():
+            dev.reset_stats()
+            scenes.render(dev, sc)
+            dev.resolve()
+        cl = dev.record(frame)
+        info = cl.info
+        assert info["draws"] == len(sc.objects) and info["kernel_launches"] >= 6 * len(sc.objects) + 2
+        n0 = dev.kernel_launch_count
+        for _ in range(3):
+            cl.execute()
+            col, dep = dev.present()
+            assert np.array_equal(col, ref_col) and np.array_equal(dep.view(np.uint32), ref_dep.view(np.uint32))
+            assert dev.stats() == ref_stats  # reset_stats is part of the recording, like memset(&stats, 0) in render() (main.c:1268)
+        assert dev.kernel_launch_count - n0 == 3 * (info["kernel_launches"] + 1)  # + the resolve of each present()
+        # immediate mode still works after executions (vertex cache side stream re-joins) ...
+        dev.reset_stats()
+        scenes.render(dev, sc)
+        col, dep = dev.present()
+        assert np.array_equal(col, ref_col) and np.array_equal(dep.view(np.uint32), ref_dep.view(np.uint32)) and dev.stats() == ref_stats
+        # ... and so does the list after immediate frames
+        cl.execute()
+        col, dep = dev.present()
+        assert np.array_equal(col, ref_col) and dev.stats() == ref_stats
+        cl.release()
+
+
+def test_constants_of_a_recorded_list_follow_the_camera():
+    """update() rewrites the PerFrameCB every frame (main.c:1595-1597): mlv_command_list_set_constants replaces it in the
+    recorded geometry kernels; the replay equals an immediate frame with that camera."""
+    from malevich_b200 import camera, scenes
+    sc = cases.SMALL["ftm_320x200"]()
+    poses = [((-8.0, 5.0, 1.2), -2.8, 0.1), ((-2.0, 1.5, 1.0), -2.0, 0.3), scenes.FTM_SCREENSHOT_POSE]
+    with _device(sc.width, sc.height) as dev:
+        cl = dev.record(lambda: scenes.render(dev, sc))
+        for pose in poses:
+            cb = camera.per_frame_cb(sc.width, sc.height, *pose)
+            want_col, want_dep, _ = _immediate(scenes.ftm(sc.width, sc.height, cb=cb))
+            cl.set_constants(cb)
+            cl.execute()
+            col, dep = dev.present()
+            assert np.array_equal(col, want_col) and np.array_equal(dep.view(np.uint32), want_dep.view(np.uint32)), str(pose)
+        # one draw only: the sky (last draw) rendered with another camera than the rest
+        cb_a, cb_b = camera.per_frame_cb(sc.width, sc.height, *poses[0]), camera.per_frame_cb(sc.width, sc.height, *poses[1])
+        cl.set_constants(cb_a)
+        cl.set_constants(cb_b, draw_index=len(sc.objects) - 1)
+        cl.execute()
+        col, dep = dev.present()
+        with _device(sc.width, sc.height) as imm:
+            sa = scenes.ftm(sc.width, sc.height, cb=cb_a)
+            scenes.render(imm, scenes.Scene(sa.name, sa.width, sa.height, sa.objects[:-1], sa.per_frame_cb))
+            sb = scenes.ftm(sc.width, sc.height, cb=cb_b)
+            scenes.render(imm, scenes.Scene(sb.name, sb.width, sb.height, sb.objects[-1:], sb.per_frame_cb), clear=False)
+            want_col, want_dep = imm.present()
+        assert np.array_equal(col, want_col) and np.array_equal(dep.view(np.uint32), want_dep.view(np.uint32))
+        with pytest.raises(Exception):
+            cl.set_constants(cb_a, draw_index=len(sc.objects))
+        cl.release()
+
+
+def test_buffer_uploads_between_executions_and_recording_rules():
+    import ctypes as C
+    from malevich_b200 import _lib as L, scenes
+    sc = cases.SMALL["toon_320x200"]()
+    ref_col, ref_dep, _ = _immediate(sc)
+    with _device(sc.width, sc.height) as dev:
+        scenes.upload(dev, sc)
+        dev.begin_command_list()
+        scenes.render(dev, sc)
+        for bad in (dev.present, dev.stats, dev.finish, dev.begin_command_list, lambda: dev.present_async(ref_col.copy())):
+            with pytest.raises(Exception):
+                bad()  # nothing that synchronises or reads back can be recorded
+        cl = dev.finish_command_list()
+        with pytest.raises(Exception):
+            dev.finish_command_list()  # nothing is being recorded
+        cl.execute()
+        col, dep = dev.present()
+        assert np.array_equal(col, ref_col) and np.array_equal(dep.view(np.uint32), ref_dep.view(np.uint32))
+        # new contents for the first object's vertex buffer (shifted a little): the recording binds the object, not the bytes
+        o = sc.objects[0]
+        moved = o.vertex_buffer.copy()
+        moved[:, 2] += 0.05
+        h = dev._buffer(o.vertex_buffer, L.BUFFER_VERTEX)
+        L.check(dev._lib.mlv_update_buffer(dev._h, h, moved.ctypes.data_as(C.c_void_p), moved.nbytes))
+        cl.execute()
+        col2, dep2 = dev.present()
+        sc2 = scenes.Scene(sc.name, sc.width, sc.height, [scenes.SceneObject(moved, o.index_buffer, o.vertex_shader, o.pixel_shader, o.texture)] + sc.objects[1:], sc.per_frame_cb)
+        want_col, want_dep, _ = _immediate(sc2)
+        assert np.array_equal(col2, want_col) and np.array_equal(dep2.view(np.uint32), want_dep.view(np.uint32))
+        assert not np.array_equal(col2, ref_col)
+        cl.release()
+
+
+def test_command_lists_of_sort_first_ranks_compose_to_the_single_device_image():
+    """Every rank of a sort-first split replays its own recorded frame (the exchange stays immediate: pack, gather, unpack)."""
+    import torch
+    from malevich_b200 import scenes
+    from test_gpu_parity import _as_tensor
+    sc = cases.SMALL["synth_320x200"]()
+    ref_col, _, ref_stats = _immediate(sc)
+    for world, stripe in ((2, 13), (4, 1)):
+        devs = [_device(sc.width, sc.height, num_ranks=world, rank=r, stripe_height_tiles=stripe) for r in range(world)]
+        try:
+            lists = []
+            for d in devs:
+                def frame(d=d):
+                    d.reset_stats()
+                    scenes.render(d, sc)
+                    d.composite_pack()
+                lists.append(d.record(frame))
+            for rep in range(2):
+                sums = {"assembled_triangle_count": 0, "active_bin_count": 0, "total_triangle_count_in_bins": 0}
+                for d, cl in zip(devs, lists):
+                    cl.execute()
+                    d.finish()
+                    st = d.stats()
+                    for k in sums:
+                        sums[k] += st[k]
+                assert sums == {k: ref_stats[k] for k in sums}
+                _, chunk = devs[0].composite_layout()
+                for r, d in enumerate(devs):
+                    src_ptr, _ = d.composite_layout()
+                    src = _as_tensor(src_ptr + r * chunk, chunk)
+                    for d2 in devs:
+                        dst_ptr, _ = d2.composite_layout()
+                        _as_tensor(dst_ptr + r * chunk, chunk).copy_(src)
+                torch.cuda.synchronize()
+                for d in devs:
+                    d.composite_unpack()
+                    d.finish()
+                    out = _as_tensor(d.resolved_color_ptr(), sc.width * sc.height * 4).cpu().numpy().view(np.uint32).reshape(sc.height, sc.width)
+                    assert np.array_equal(out, ref_col), f"world {world} stripe {stripe} rep {rep}"
+            for cl in lists:
+                cl.release()
+        finally:
+            for d in devs:
+                d.close()
