@@ -422,20 +422,22 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         fps = 1e3 / ms
         # dominant kernel = the kernel with the largest summed time over the step; its algorithmic bytes (SURVEY.md 8d per-unit
         # figures x the units it processed) over its own CUDA-event time
-        kernel_ms = {"k_geom": stage_ms["geometry"], "k_tile": stage_ms["tile"], "k_geom_clip": stage_ms["clip"], "k_vertex": stage_ms["vertex_cache"],
+        kernel_ms = {"k_front": stage_ms["geometry"], "k_back": stage_ms["geometry_back"], "k_tile": stage_ms["tile"], "k_front_clip": stage_ms["clip"], "k_vertex": stage_ms["vertex_cache"],
                      "k_bin_scan": stage_ms["bin_scan"], "k_bin_fill": stage_ms["bin_fill"]}
-        kernel_launches = {"k_geom": stage_launches["geometry"], "k_tile": stage_launches["tile"], "k_geom_clip": stage_launches["clip"], "k_vertex": stage_launches["vertex_cache"],
+        kernel_launches = {"k_front": stage_launches["geometry"], "k_back": stage_launches["geometry_back"], "k_tile": stage_launches["tile"], "k_front_clip": stage_launches["clip"], "k_vertex": stage_launches["vertex_cache"],
                            "k_bin_scan": stage_launches["bin_scan"], "k_bin_fill": stage_launches["bin_fill"]}
         # Algorithmic bytes of a kernel = SURVEY.md 8d's per-unit figures x the units the kernel REALLY processed (device work
         # counters): Stats count every assembled triangle and pair like the reference, but a triangle that Hi-Z rejects at
         # binning time writes no record and a tile without surviving pairs is not visited, so those units move no bytes.
         idx_bytes = 4 * sum(o.index_count for o in scene.objects)
         vtx_bytes = 32 * sum(o.vertex_buffer.shape[0] for o in scene.objects)
-        kernel_bytes = {"k_geom": (idx_bytes + vtx_bytes + 216 * work["records_written"]) / world,        # inputs once + record write
+        tri_in = sum(o.index_count // 3 for o in scene.objects)
+        kernel_bytes = {"k_front": (idx_bytes + vtx_bytes + 16 * tri_in) / world,                           # inputs once + 16 B of bounds per input triangle
+                        "k_back": (16 * tri_in + 216 * work["records_written"]) / world,                    # bounds read + record write
                         "k_tile": (216 * work["records_written"] + 1032 * work["tiles_visited"] + 4 * work["pairs_listed"]) / world,  # record read + tile read/write + list read
-                        "k_geom_clip": 0, "k_vertex": vtx_bytes / world, "k_bin_scan": 16 * (scene.width // 8) * (scene.height // 8) * len(scene.objects) / world,
+                        "k_front_clip": 0, "k_vertex": vtx_bytes / world, "k_bin_scan": 16 * (scene.width // 8) * (scene.height // 8) * len(scene.objects) / world,
                         "k_bin_fill": (16 * stats["assembled_triangle_count"] + 4 * work["pairs_listed"]) / world}
-        dom = max(("k_geom", "k_tile"), key=kernel_ms.get)  # the two kernels that carry the record stream; the others move < 5 % of the bytes
+        dom = max(("k_front", "k_back", "k_tile"), key=kernel_ms.get)  # the kernels that carry the geometry and record streams; the others move < 5 % of the bytes
 
         def kernel_roofline(k):
             n = max(kernel_launches[k], 1)
@@ -464,7 +466,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                          "units_per_step": {"records_written": work["records_written"], "tiles_visited": work["tiles_visited"], "pairs_listed": work["pairs_listed"]},
                          "note": "algorithmic bytes = SURVEY 8d per-unit figures x the units the kernel really processed (mlv_work_counters), averaged over its launches of a frame; "
                                  "the launch time is its CUDA-event bracket (no overlap with neighbours)"},
-            "roofline_kernels": {k: kernel_roofline(k) for k in ("k_geom", "k_tile", "k_vertex", "k_bin_fill")},
+            "roofline_kernels": {k: kernel_roofline(k) for k in ("k_front", "k_back", "k_tile", "k_vertex", "k_bin_fill")},
             "roofline_frame": {"algorithmic_bytes_per_frame": b_alg, "achieved": b_alg / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
                                "frac": b_alg / (ms * 1e-3) / 1e9 / world / peak, "bytes_by_stage": b_stage,
                                "note": "B_alg of the REFERENCE algorithm for this frame (SURVEY 8d: every assembled triangle's record written and read, every touched tile-draw loaded and "

@@ -290,7 +290,7 @@ MLV_API int mlv_read_bin_lists(mlv_device *dev, uint32_t *keys, uint32_t *out_pa
  * on the device's stream. mlv_profile_end synchronises and returns, per stage, the summed kernel time in
  * milliseconds and the number of launches. Arrays have MLV_STAGE_COUNT entries. */
 enum { MLV_STAGE_CLEAR = 0,      /* k_clear */
-       MLV_STAGE_GEOMETRY = 1,   /* k_geom (+ k_chunk_bounds when the sort-first chunk bounds are (re)built) */
+       MLV_STAGE_GEOMETRY = 1,   /* k_front: the front half of geometry (+ k_chunk_bounds when the sort-first chunk bounds are (re)built) */
        MLV_STAGE_BIN_COUNT = 2,  /* k_bin_big */
        MLV_STAGE_BIN_SCAN = 3,   /* k_bin_scan */
        MLV_STAGE_BIN_FILL = 4,   /* k_bin_fill */
@@ -298,8 +298,9 @@ enum { MLV_STAGE_CLEAR = 0,      /* k_clear */
        MLV_STAGE_RESOLVE = 6,    /* k_resolve */
        MLV_STAGE_COMPOSITE = 7,  /* k_composite_pack / k_composite_unpack */
        MLV_STAGE_VERTEX = 8,     /* k_vertex (post-transform vertex cache) */
-       MLV_STAGE_CLIP = 9,       /* k_geom_clip */
-       MLV_STAGE_COUNT = 10 };
+       MLV_STAGE_CLIP = 9,       /* k_front_clip */
+       MLV_STAGE_BACK = 10,      /* k_back: Hi-Z + binner pass 1 + setup records of the survivors */
+       MLV_STAGE_COUNT = 11 };
 MLV_API int mlv_profile_begin(mlv_device *dev);
 MLV_API int mlv_profile_end(mlv_device *dev, double *out_ms, uint32_t *out_launches);
 /* The same region launch by launch -- the timeline Remotery's viewer draws (external/Remotery/vis): stage, start relative

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "mlv_debug_read_vs_out", "mlv_debug_read_triangles", "mlv_debug_read_bins", "mlv_debug_read_masks",
     "mlv_debug_read_tile_min_depths", "mlv_debug_read_keys", "mlv_read_bin_lists", "mlv_fnv64_words", "mlv_profile_begin", "mlv_profile_end", "mlv_profile_read_events", "mlv_kernel_launch_count",
 ]
-STAGE_NAMES = ["clear", "geometry", "bin_count", "bin_scan", "bin_fill", "tile", "resolve", "composite", "vertex_cache", "clip"]
+STAGE_NAMES = ["clear", "geometry", "bin_count", "bin_scan", "bin_fill", "tile", "resolve", "composite", "vertex_cache", "clip", "geometry_back"]
 
 MLV_OK = 0
 MLV_ERR_INVALID_ARGUMENT, MLV_ERR_CUDA, MLV_ERR_OUT_OF_MEMORY, MLV_ERR_CAPACITY, MLV_ERR_STATE = 1, 2, 3, 4, 5

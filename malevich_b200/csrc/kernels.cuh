@@ -1,10 +1,12 @@
 // kernels.cuh -- the draw pipeline as hand-written sm_100a kernels.
 //
 //   k_clear      clear_render_target_view + clear_depth_stencil_view      (reference main.c:1191-1217)
-//   k_geom<VS>   input assembler + vertex shader + primitive assembly     (main.c:662-913)
-//                fused, one thread per input triangle, no inter-thread dependency: triangles are named by
-//                order-preserving keys instead of compacted ids (see mlv_internal.cuh)
-//   k_bin_big / k_bin_fill  binner passes 1 and 2 (pass 1 of small triangles is fused into k_geom) (main.c:924-962)
+//   k_front<VS> / k_front_clip<VS>  input assembler + vertex shader + primitive assembly (main.c:662-913), the half
+//                that does not depend on the render target: one thread per input triangle, no inter-thread dependency
+//                (triangles are named by order-preserving keys instead of compacted ids, see mlv_internal.cuh);
+//                runs ahead of the draw-to-draw chain on a stream of its own
+//   k_back<VS>   Hi-Z + binner pass 1 per triangle, setup records for the survivors
+//   k_bin_big / k_bin_fill  binner passes 1 and 2 (pass 1 of small triangles is fused into k_back) (main.c:924-962)
 //   k_bin_scan   binner exclusive scan + compaction of non-empty bins     (main.c:937-974), multi-CTA
 //                single pass with decoupled look-back
 //   k_tile<PS>   rasterizer + Hi-Z + early-Z + pixel shader + output merger (main.c:983-1189)
@@ -305,21 +307,21 @@ __device__ __forceinline__ void count_small_rect(const GeomParams &P, const Tile
 	}
 }
 
-__device__ __forceinline__ BinTally count_bins(const GeomParams &P, const TriSetup &S) {
+__device__ __forceinline__ BinTally count_bins(const GeomParams &P, int minx, int miny, int maxx, int maxy, float max_depth) {
 	BinTally r = { 0u, false, false, false };
-	const TileRect tr = tile_rect(S.minx, S.miny, S.maxx, S.maxy, P.wt, P.ht);
+	const TileRect tr = tile_rect(minx, miny, maxx, maxy, P.wt, P.ht);
 	const int cnt = tr.w() * tr.h();
 	if(cnt <= 0) return r;
 	if(cnt > 8) {
-		for(int ty = tr.ty0; ty <= tr.ty1 && !r.live; ++ty) r.live = P.part.owns_row(ty);
+		r.live = P.part.owned_rows(tr.ty0, tr.ty1) > 0;
 		r.big = r.live && cnt <= MLV_HUGE_TILES;
 		r.huge = r.live && cnt > MLV_HUGE_TILES;
 		return r;
 	}
 	// dense meshes of pixel-sized triangles (BASELINE config 5: 2.2 tiles per triangle) almost never need more than
-	// four steps; the eight-step walk costs a third of the geometry kernel's instructions when every lane pays for it
-	if(cnt <= 4) count_small_rect<4>(P, tr, cnt, S.max_depth, r);
-	else count_small_rect<8>(P, tr, cnt, S.max_depth, r);
+	// four steps; the eight-step walk costs a third of the kernel's instructions when every lane pays for it
+	if(cnt <= 4) count_small_rect<4>(P, tr, cnt, max_depth, r);
+	else count_small_rect<8>(P, tr, cnt, max_depth, r);
 	return r;
 }
 
@@ -375,29 +377,6 @@ __device__ __forceinline__ void emit_debug(const GeomParams &P, uint32_t slot, u
 	P.dbg.slot_key[slot] = key;
 }
 
-// Straight (uncoalesced) emission, used by the clipping pass only. Returns the pairs counted for Stats.
-__device__ __forceinline__ uint32_t emit_triangle(const GeomParams &P, uint32_t slot, uint32_t key, const TriSetup &S, const float4 &r1a, const float4 &r1b, const float4 &r1c,
-                                                  float r2a, float r2b, float r2c) {
-	const BinTally tally = count_bins(P, S);
-	const uint2 pb = pack_bounds(S);
-	P.tri_bounds[slot] = tally.live ? make_uint4(pb.x, pb.y, __float_as_uint(S.max_depth), key) : make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, key);
-	if(tally.live) {
-		atomicAdd(P.stat_stripes + (size_t)(blockIdx.x % MLV_STAT_STRIPES) * 16u + 1u, 1ull); // work counter: records_written
-		TriRecord R;
-		make_record(R, S, pb, r1a, r1b, r1c, r2a, r2b, r2c);
-		uint4 *cov = P.tri_cov + (size_t)slot * MLV_TRI_COV_U4;
-		float4 *sh = reinterpret_cast<float4 *>(P.tri_shade + (size_t)slot * MLV_TRI_SHADE_U4);
-#pragma unroll
-		for(int i = 0; i < MLV_TRI_COV_U4; ++i) cov[i] = R.cov[i];
-#pragma unroll
-		for(int i = 0; i < MLV_TRI_SHADE_U4; ++i) sh[i] = R.shade[i];
-		if(tally.big) P.big_queue[atomicAdd(&P.ctr->big_count, 1u)] = slot;
-		if(tally.huge) P.huge_queue[atomicAdd(&P.ctr->huge_count, 1u)] = slot;
-	}
-	if(P.dbg.tris) emit_debug(P, slot, key, S, r1a, r1b, r1c, r2a, r2b, r2c);
-	return tally.pairs;
-}
-
 // Clipper (main.c:649-660): returns the vertex count of the clipped polygon left in poly[].
 __device__ __forceinline__ int clip_polygon(const GeomParams &P, const VsOut &v0, const VsOut &v1, const VsOut &v2, float *&cur, float *&other) {
 	poly_store(cur, 0, v0);
@@ -428,27 +407,6 @@ __device__ __forceinline__ int clip_polygon(const GeomParams &P, const VsOut &v0
 		}
 	}
 	return n;
-}
-
-// Fan triangulation (main.c:797) of a clipped polygon into the consecutive overflow slots T + base + j; slot t
-// becomes a redirect to them. Returns the number of assembled triangles, adds the pairs to `pairs`.
-__device__ __forceinline__ uint32_t emit_fan(const GeomParams &P, uint32_t t, const float *poly, int fan, uint32_t base, uint32_t &pairs, int j_first, int j_step) {
-	if(j_first == 0) P.tri_cov[(size_t)t * MLV_TRI_COV_U4 + 2] = make_uint4(base, 0u, MLV_REDIRECT, 0u);
-	uint32_t emitted = 0;
-	for(int j = j_first; j < fan; j += j_step) {
-		const uint32_t slot = P.tri_count + base + (uint32_t)j;
-		const uint32_t key = (t << 3) | (uint32_t)j;
-		TriSetup S;
-		const VsOut p0 = poly_load(poly, 0), p1 = poly_load(poly, j + 1), p2 = poly_load(poly, j + 2);
-		if(setup_triangle(p0.r0, p1.r0, p2.r0, P, S)) {
-			pairs += emit_triangle(P, slot, key, S, p0.r1, p1.r1, p2.r1, p0.r2x, p1.r2x, p2.r2x);
-			if(P.part.owns_row(S.miny / 8)) ++emitted;
-		} else {
-			P.tri_bounds[slot] = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, key);
-			if(P.dbg.slot_key) P.dbg.slot_key[slot] = 0xffffffffu;
-		}
-	}
-	return emitted;
 }
 
 // Per-draw Stats contributions (main.c:1228-1246): one atomic per warp and counter.
@@ -590,21 +548,35 @@ __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ GeomPara
 }
 
 template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
-__global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_constant__ GeomParams P) {
-	pdl_prologue();
-	// Records are staged per warp in shared memory and written out as contiguous 512-byte rows: the 32 direct
-	// slots of a warp are adjacent in HBM, so the warp stores 1536 B of TriCov and 3072 B of TriShade with fully
-	// coalesced 128-bit stores instead of 32 scattered 16-byte pieces per instruction.
-	__shared__ uint4 s_stage[MLV_GEOM_THREADS / 32][32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)];
-	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-	uint32_t emitted = 0, pairs = 0, records = 0;
-	if(blockIdx.x == 0 && threadIdx.x == 0) { // Stats (main.c:1228-1232)
-		P.ctr->stats.vertex_count += P.index_count;
-		P.ctr->stats.input_triangle_count += P.tri_count;
+__device__ __forceinline__ void fetch_indices(const GeomParams &P, uint32_t t, uint32_t &vi0, uint32_t &vi1, uint32_t &vi2) {
+	if(INDEXED) {
+		vi0 = P.ix.fetch(3u * t);
+		vi1 = P.ix.fetch(3u * t + 1u);
+		vi2 = P.ix.fetch(3u * t + 2u);
+	} else {
+		vi0 = 3u * t;
+		vi1 = vi0 + 1u;
+		vi2 = vi0 + 2u;
 	}
-	// Single GPU: CTA b processes chunk b (the loops below run once). Sort-first: a persistent grid strides over the
-	// chunks; each round, thread k of the CTA tests the cached object-space bounds of the CTA's k-th chunk against this
-	// rank's tile rows, so a foreign chunk costs one thread's cull test instead of a CTA (or a kernel of its own).
+}
+
+// =================================================================================================
+// geometry, FRONT half: everything of input assembly + vertex shader + primitive assembly that does not depend on the
+// render target's state (main.c:662-898 minus the Hi-Z test): index and vertex fetch, position part of the vertex shader,
+// cull / trivial reject / clip test, projection, snap, signed area, face cull, bounds, Stats. Output per input triangle:
+// 16 bytes of bounds {min, max, max_depth, key} (MLV_BOUNDS_EMPTY when it bins nothing on this rank) and a queue of the
+// triangles that need the clipper. It reads nothing a previous draw writes, so the front halves of the draws of a frame run
+// ahead on a stream of their own, underneath the tile kernels of earlier draws; only the BACK half (Hi-Z, binning, records
+// for the survivors) sits on the draw-to-draw dependency chain.
+// =================================================================================================
+template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
+__global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_constant__ GeomParams P) {
+	pdl_prologue();
+	const uint32_t lane = lane_id();
+	uint32_t emitted = 0, pairs = 0;
+	// Single GPU: CTA b processes chunk b, b + grid, ... Sort-first: each round, thread k of the CTA tests the cached
+	// object-space bounds of the CTA's k-th chunk against this rank's tile rows, so a foreign chunk costs one thread's cull
+	// test instead of a CTA (or a kernel of its own).
 	__shared__ uint8_t s_live[MLV_GEOM_THREADS];
 	const uint32_t num_chunks = (P.tri_count + MLV_GEOM_THREADS - 1u) / MLV_GEOM_THREADS;
 	uint32_t pf0 = 0, pf1 = 0, pf2 = 0; // prefetched vertex indices of the next chunk
@@ -615,7 +587,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 		bool live = false;
 		if(c < num_chunks) {
 			live = !chunk_is_foreign(P, c);
-			P.chunk_live[c] = live ? 1 : 0; // k_bin_fill skips the stale bounds of the chunks nobody rewrote
+			P.chunk_live[c] = live ? 1 : 0; // the back half and k_bin_fill skip the stale bounds of the chunks nobody rewrote
 		}
 		s_live[threadIdx.x] = live ? 1 : 0;
 		__syncthreads();
@@ -625,38 +597,25 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 	if(chunk >= num_chunks) break;
 	if(P.chunk_bounds && !s_live[k]) continue;
 	const uint32_t t = chunk * MLV_GEOM_THREADS + threadIdx.x;
-	bool needs_clip = false, is_big = false;
-	bool staged = false; // this lane has a record for its direct slot t
-	uint4 bounds = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, t << 3);
+	bool needs_clip = false;
 	if(t < P.tri_count) {
-		// ---- input assembler (main.c:662-696): index fetch + vertex fetch. Work is done lazily: positions for every
-		// triangle, the second half of each vertex and the attribute part of the vertex shader only for triangles
-		// that survive culling and Hi-Z (the reference shades all of them; the results are the same values).
+		uint4 bounds = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, t << 3);
+		// ---- input assembler (main.c:662-696): index fetch + first half of each vertex (or its cache entry)
 		uint32_t vi0, vi1, vi2;
+		if(INDEXED && pf_valid) {
+			vi0 = pf0, vi1 = pf1, vi2 = pf2;
+		} else {
+			fetch_indices<VS, INDEXED, DEBUG, VCACHE>(P, t, vi0, vi1, vi2);
+		}
 		if(INDEXED) {
-			if(pf_valid) {
-				vi0 = pf0, vi1 = pf1, vi2 = pf2;
-			} else {
-				vi0 = P.ix.fetch(3u * t);
-				vi1 = P.ix.fetch(3u * t + 1u);
-				vi2 = P.ix.fetch(3u * t + 2u);
-			}
 			// persistent grid: the indices of this thread's triangle in the CTA's NEXT chunk are requested now, so the
-			// first of the three dependent round trips (index -> vertex -> tile minimum) of that chunk is already over
+			// first of the dependent round trips (index -> vertex) of that chunk is already over
 			const uint32_t tn = t + gridDim.x * MLV_GEOM_THREADS;
 			pf_valid = !P.chunk_bounds && tn < P.tri_count;
-			if(pf_valid) {
-				pf0 = P.ix.fetch(3u * tn);
-				pf1 = P.ix.fetch(3u * tn + 1u);
-				pf2 = P.ix.fetch(3u * tn + 2u);
-			}
-		} else {
-			vi0 = 3u * t;
-			vi1 = vi0 + 1u;
-			vi2 = vi0 + 2u;
+			if(pf_valid) fetch_indices<VS, INDEXED, DEBUG, VCACHE>(P, tn, pf0, pf1, pf2);
 		}
-		float4 a0, b0, c0, a, b, c, qa, qb, qc; // first half of each input vertex; clip-space positions; cached per-vertex projection
-		if(VCACHE) { // only the projected half of each entry: the clip-space positions are fetched for survivors
+		float4 a0, b0, c0, a, b, c, qa, qb, qc;
+		if(VCACHE) {
 			qa = __ldg(P.vcache + 2 * (size_t)vi0 + 1);
 			qb = __ldg(P.vcache + 2 * (size_t)vi1 + 1);
 			qc = __ldg(P.vcache + 2 * (size_t)vi2 + 1);
@@ -674,7 +633,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 			o[3] = v1.r0, o[4] = v1.r1, o[5] = make_float4(v1.r2x, 0.0f, 0.0f, 0.0f);
 			o[6] = v2.r0, o[7] = v2.r1, o[8] = make_float4(v2.r2x, 0.0f, 0.0f, 0.0f);
 		}
-		// ---- primitive assembly (main.c:750-908)
+		// ---- primitive assembly (main.c:750-898)
 		bool degenerate, rejected, inside;
 		if(VCACHE) { // the comparisons were made per vertex by k_vertex (clip_code)
 			const uint32_t ca = __float_as_uint(qa.w), cb = __float_as_uint(qb.w), cc = __float_as_uint(qc.w);
@@ -694,51 +653,25 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 		if(!degenerate && !rejected) {
 			if(inside) {
 				TriSetup S;
-				bool kept;
 				if(VCACHE) {
-					ProjVertex pa, pb, pc; // s.x, s.y, s.w are not needed outside debug capture (which never uses the cache)
+					ProjVertex pa, pb, pc; // s.x, s.y, s.w, rw are not needed for the bounds
 					pa.s = make_float4(0.0f, 0.0f, qa.z, 0.0f), pa.rw = 0.0f, pa.sx = __float_as_int(qa.x), pa.sy = __float_as_int(qa.y);
 					pb.s = make_float4(0.0f, 0.0f, qb.z, 0.0f), pb.rw = 0.0f, pb.sx = __float_as_int(qb.x), pb.sy = __float_as_int(qb.y);
 					pc.s = make_float4(0.0f, 0.0f, qc.z, 0.0f), pc.rw = 0.0f, pc.sx = __float_as_int(qc.x), pc.sy = __float_as_int(qc.y);
-					kept = setup_from_projected(pa, pb, pc, P, S);
+					direct = setup_from_projected(pa, pb, pc, P, S);
 				} else {
-					kept = setup_project(a, b, c, P, S);
+					direct = setup_project(a, b, c, P, S);
 				}
-				if(kept) {
-					direct = true;
+				if(direct) {
 					emitted += P.part.owns_row(S.miny / 8) ? 1u : 0u; // counted once across ranks: by the owner of its first tile row
-					// ---- binner pass 1 + Hi-Z for this triangle; a triangle hidden in every tile it touches writes no record
-					const BinTally tally = count_bins(P, S);
-					pairs += tally.pairs;
-					is_big = tally.big;
-					if(tally.huge) P.huge_queue[atomicAdd(&P.ctr->huge_count, 1u)] = t; // rare: sky domes, full-screen quads
-					if(tally.live || DEBUG) {
-						setup_edges(P, S);
-						// ---- vertex shader, attribute part
-						float4 r1a, r1b, r1c;
-						float r2a, r2b, r2c;
-						if(VCACHE) {
-							a0 = __ldg(P.vb + 2 * (size_t)vi0), b0 = __ldg(P.vb + 2 * (size_t)vi1), c0 = __ldg(P.vb + 2 * (size_t)vi2);
-							a = __ldg(P.vcache + 2 * (size_t)vi0), b = __ldg(P.vcache + 2 * (size_t)vi1), c = __ldg(P.vcache + 2 * (size_t)vi2);
-							S.rw[0] = 1.0f / a.w, S.rw[1] = 1.0f / b.w, S.rw[2] = 1.0f / c.w; // a_reciprocal_ws (project_vertex): the same correctly rounded divide
-						}
-						vs_attributes<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), a, P.cb, P.vs_tex, P.rsqrt_lut, r1a, r2a);
-						vs_attributes<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), b, P.cb, P.vs_tex, P.rsqrt_lut, r1b, r2b);
-						vs_attributes<VS>(c0, __ldg(P.vb + 2 * (size_t)vi2 + 1), c, P.cb, P.vs_tex, P.rsqrt_lut, r1c, r2c);
-						if(tally.live) {
-							const uint2 pb = pack_bounds(S);
-							bounds = make_uint4(pb.x, pb.y, __float_as_uint(S.max_depth), t << 3);
-							staged = true;
-							TriRecord R;
-							make_record(R, S, pb, r1a, r1b, r1c, r2a, r2b, r2c);
-							uint4 *st = s_stage[warp];
-#pragma unroll
-							for(int i = 0; i < MLV_TRI_COV_U4; ++i) st[lane * MLV_TRI_COV_U4 + i] = R.cov[i];
-#pragma unroll
-							for(int i = 0; i < MLV_TRI_SHADE_U4; ++i)
-								st[32 * MLV_TRI_COV_U4 + lane * MLV_TRI_SHADE_U4 + i] = make_uint4(__float_as_uint(R.shade[i].x), __float_as_uint(R.shade[i].y), __float_as_uint(R.shade[i].z), __float_as_uint(R.shade[i].w));
-						}
-						if(DEBUG) emit_debug(P, t, t << 3, S, r1a, r1b, r1c, r2a, r2b, r2c);
+					// (triangle, tile) pairs on this rank (Stats, main.c:1246): every tile of the bounds rectangle (main.c:927-936)
+					const TileRect tr = tile_rect(S.minx, S.miny, S.maxx, S.maxy, P.wt, P.ht);
+					const uint32_t np = (uint32_t)(tr.w() * P.part.owned_rows(tr.ty0, tr.ty1));
+					pairs += np;
+					if(np || DEBUG) {
+						S.nowrap = false;
+						const uint2 pb = pack_bounds(S);
+						bounds = make_uint4(pb.x, pb.y, __float_as_uint(S.max_depth), t << 3);
 					}
 				}
 			} else {
@@ -748,60 +681,69 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_geom(const __grid_const
 		if(DEBUG && !direct) P.dbg.slot_key[t] = 0xffffffffu;
 		P.tri_bounds[t] = bounds;
 	}
-	// ---- triangles that need the clipper are queued for k_geom_clip, triangles with large tile rectangles for
-	// k_bin_big (one warp-aggregated atomic each): either slow path would otherwise stall the 31 other lanes
+	// ---- triangles that need the clipper are queued for k_front_clip (one warp-aggregated atomic): the slow path would
+	// otherwise stall the 31 other lanes
 	{
 		const uint32_t cmask = __ballot_sync(0xffffffffu, needs_clip);
 		if(cmask) {
 			uint32_t base = 0;
-			if(lane == 0) base = atomicAdd(&P.ctr->clip_count, (uint32_t)__popc(cmask));
+			if(lane == 0) base = atomicAdd(&P.dctr->clip_count, (uint32_t)__popc(cmask));
 			base = __shfl_sync(0xffffffffu, base, 0);
 			if(needs_clip) P.clip_queue[base + __popc(cmask & ((1u << lane) - 1u))] = t;
 		}
-		const uint32_t bmask = __ballot_sync(0xffffffffu, is_big);
-		if(bmask) {
-			uint32_t base = 0;
-			if(lane == 0) base = atomicAdd(&P.ctr->big_count, (uint32_t)__popc(bmask));
-			base = __shfl_sync(0xffffffffu, base, 0);
-			if(is_big) P.big_queue[base + __popc(bmask & ((1u << lane) - 1u))] = t;
-		}
 	}
-	// ---- coalesced write-out of the staged records
-	__syncwarp();
-	const uint32_t valid = __ballot_sync(0xffffffffu, staged);
-	if(valid) {
-		records += (uint32_t)__popc(valid);
-		const uint4 *st = s_stage[warp];
-		const size_t slot0 = (size_t)(t - lane);
-		uint4 *cov = P.tri_cov + slot0 * MLV_TRI_COV_U4;
-		uint4 *sh = P.tri_shade + slot0 * MLV_TRI_SHADE_U4;
-#pragma unroll
-		for(int i = 0; i < MLV_TRI_COV_U4; ++i) {
-			const uint32_t chunk = i * 32 + lane;
-			if((valid >> (chunk / MLV_TRI_COV_U4)) & 1u) cov[chunk] = st[chunk];
-		}
-#pragma unroll
-		for(int i = 0; i < MLV_TRI_SHADE_U4; ++i) {
-			const uint32_t chunk = i * 32 + lane;
-			if((valid >> (chunk / MLV_TRI_SHADE_U4)) & 1u) sh[chunk] = st[32 * MLV_TRI_COV_U4 + chunk];
-		}
-	}
-	__syncwarp(); // the staging rows are reused by the next chunk of a persistent CTA
 	}
 	if(P.chunk_bounds) __syncthreads(); // s_live is rewritten by the next round
 	}
 	tally_stats(P.stat_stripes, emitted, pairs);
-	tally_records(P.stat_stripes, records);
+}
+
+// Fan triangulation (main.c:797) of a clipped polygon into the consecutive overflow slots T + base + j: bounds for the back
+// half and -- always, the clipped attributes exist only here -- the 144-byte record in the draw's overflow arena.
+// Returns the number of assembled triangles, adds the pairs to `pairs`.
+__device__ __forceinline__ uint32_t emit_fan(const GeomParams &P, uint32_t t, const float *poly, int fan, uint32_t base, uint32_t &pairs, int j_first, int j_step) {
+	uint32_t emitted = 0;
+	for(int j = j_first; j < fan; j += j_step) {
+		const uint32_t ovf = base + (uint32_t)j, slot = P.tri_count + ovf;
+		const uint32_t key = (t << 3) | (uint32_t)j;
+		TriSetup S;
+		const VsOut p0 = poly_load(poly, 0), p1 = poly_load(poly, j + 1), p2 = poly_load(poly, j + 2);
+		uint4 bounds = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, key);
+		if(setup_triangle(p0.r0, p1.r0, p2.r0, P, S)) {
+			if(P.part.owns_row(S.miny / 8)) ++emitted;
+			const TileRect tr = tile_rect(S.minx, S.miny, S.maxx, S.maxy, P.wt, P.ht);
+			const uint32_t np = (uint32_t)(tr.w() * P.part.owned_rows(tr.ty0, tr.ty1));
+			pairs += np;
+			if(np || P.dbg.tris) {
+				const uint2 pb = pack_bounds(S);
+				bounds = make_uint4(pb.x & ~MLV_NOWRAP_BIT, pb.y, __float_as_uint(S.max_depth), key);
+				TriRecord R;
+				make_record(R, S, pb, p0.r1, p1.r1, p2.r1, p0.r2x, p1.r2x, p2.r2x);
+				uint4 *cov = P.ovf_cov + (size_t)ovf * MLV_TRI_COV_U4;
+				float4 *sh = reinterpret_cast<float4 *>(P.ovf_shade + (size_t)ovf * MLV_TRI_SHADE_U4);
+#pragma unroll
+				for(int i = 0; i < MLV_TRI_COV_U4; ++i) cov[i] = R.cov[i];
+#pragma unroll
+				for(int i = 0; i < MLV_TRI_SHADE_U4; ++i) sh[i] = R.shade[i];
+			}
+			if(P.dbg.tris) emit_debug(P, slot, key, S, p0.r1, p1.r1, p2.r1, p0.r2x, p1.r2x, p2.r2x);
+		} else if(P.dbg.slot_key) {
+			P.dbg.slot_key[slot] = 0xffffffffu;
+		}
+		P.tri_bounds[slot] = bounds;
+	}
+	return emitted;
 }
 
 #define MLV_CLIP_SPLIT 4u
-// Clipping pass over the queued input triangles (dense, unlike the sparse occurrences inside k_geom's warps).
-// Re-runs input assembly + vertex shader for the triangle, clips, and emits the fan into overflow slots.
+// Clipping pass of the front half over the queued input triangles (dense, unlike the sparse occurrences inside k_front's
+// warps). Re-runs input assembly + vertex shader for the triangle, clips, sets up the fan and writes bounds + records into
+// the draw's overflow slots.
 template <int VS, bool INDEXED>
-__global__ void __launch_bounds__(MLV_CLIP_THREADS) k_geom_clip(const __grid_constant__ GeomParams P) {
+__global__ void __launch_bounds__(MLV_CLIP_THREADS) k_front_clip(const __grid_constant__ GeomParams P) {
 	__shared__ float s_poly[2][MLV_CLIP_MAXV * 9 * MLV_CLIP_THREADS];
 	pdl_prologue();
-	const uint32_t n = P.ctr->clip_count;
+	const uint32_t n = P.dctr->clip_count;
 	const uint32_t lane = lane_id();
 	uint32_t emitted = 0, pairs = 0;
 	// MLV_CLIP_SPLIT consecutive lanes work on the same queued triangle: each repeats the (cheap, deterministic) vertex
@@ -816,12 +758,8 @@ __global__ void __launch_bounds__(MLV_CLIP_THREADS) k_geom_clip(const __grid_con
 		uint32_t t = 0;
 		if(i < n) {
 			t = P.clip_queue[i];
-			uint32_t vi0 = 3u * t, vi1 = 3u * t + 1u, vi2 = 3u * t + 2u;
-			if(INDEXED) {
-				vi0 = P.ix.fetch(vi0);
-				vi1 = P.ix.fetch(vi1);
-				vi2 = P.ix.fetch(vi2);
-			}
+			uint32_t vi0, vi1, vi2;
+			fetch_indices<VS, INDEXED, false, false>(P, t, vi0, vi1, vi2);
 			const VsOut v0 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi0), __ldg(P.vb + 2 * (size_t)vi0 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
 			const VsOut v1 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi1), __ldg(P.vb + 2 * (size_t)vi1 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
 			const VsOut v2 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi2), __ldg(P.vb + 2 * (size_t)vi2 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
@@ -840,7 +778,7 @@ __global__ void __launch_bounds__(MLV_CLIP_THREADS) k_geom_clip(const __grid_con
 		}
 		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
 		uint32_t base = 0;
-		if(lane == 0 && total) base = atomicAdd(&P.ctr->ovf_count, total);
+		if(lane == 0 && total) base = atomicAdd(&P.dctr->ovf_count, total);
 		base = __shfl_sync(0xffffffffu, base, 0) + incl - ((sub == 0u) ? (uint32_t)fan : 0u);
 		base = __shfl_sync(0xffffffffu, base, (int)(lane - sub)); // the group shares the base of its first lane
 		if(fan > 0) {
@@ -849,6 +787,138 @@ __global__ void __launch_bounds__(MLV_CLIP_THREADS) k_geom_clip(const __grid_con
 		}
 	}
 	tally_stats(P.stat_stripes, emitted, pairs);
+}
+
+// =================================================================================================
+// geometry, BACK half: the part of a draw that depends on what earlier draws left in the render target. Per slot with
+// non-empty bounds (direct slots of k_front, overflow slots of k_front_clip): binner pass 1 with the Hi-Z test
+// (main.c:924-936, 1003-1010); a DIRECT slot that survives in at least one tile fetches its vertices again, runs the
+// attribute part of the vertex shader, builds the edge functions and writes its 144-byte record -- staged per warp in
+// shared memory and written as contiguous 512-byte rows. A triangle hidden in every tile it touches costs 16 bytes of
+// bounds and its tile-minimum look-ups, and writes nothing.
+// =================================================================================================
+template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
+__global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_back(const __grid_constant__ GeomParams P) {
+	pdl_prologue();
+	__shared__ uint4 s_stage[MLV_GEOM_THREADS / 32][32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)];
+	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+	const uint32_t n_slots = P.tri_count + min(P.dctr->ovf_count, P.ovf_capacity);
+	const uint32_t num_chunks = (n_slots + MLV_GEOM_THREADS - 1u) / MLV_GEOM_THREADS;
+	uint32_t records = 0;
+	// Sort-first: direct slots of chunks the front half skipped on this rank hold stale bounds from an earlier draw. Each
+	// round, thread k of the CTA looks up the liveness of the CTA's k-th chunk, so a foreign chunk costs no round trip of its own.
+	__shared__ uint8_t s_live[MLV_GEOM_THREADS]; // bit 0: the chunk holds slots to process, bit 1: its direct slots are live
+	for(uint32_t first = blockIdx.x; first < num_chunks; first += gridDim.x * MLV_GEOM_THREADS) {
+	if(P.chunk_live) {
+		const uint32_t c = first + threadIdx.x * gridDim.x;
+		uint8_t code = 0;
+		if(c < num_chunks) {
+			const bool has_direct = c * MLV_GEOM_THREADS < P.tri_count, has_ovf = (c + 1u) * MLV_GEOM_THREADS > P.tri_count;
+			const bool direct_live = has_direct && __ldg(P.chunk_live + c) != 0;
+			code = (uint8_t)(((direct_live || has_ovf) ? 1 : 0) | (direct_live ? 2 : 0));
+		}
+		s_live[threadIdx.x] = code;
+		__syncthreads();
+	}
+	for(uint32_t k = 0; k < MLV_GEOM_THREADS; ++k) {
+		const uint32_t chunk = first + k * gridDim.x;
+		if(chunk >= num_chunks) break;
+		if(P.chunk_live && !(s_live[k] & 1)) continue;
+		const uint32_t slot = chunk * MLV_GEOM_THREADS + threadIdx.x;
+		bool staged = false, is_big = false, is_huge = false;
+		const bool mine = slot < n_slots && (slot >= P.tri_count || !P.chunk_live || (s_live[k] & 2));
+		if(mine) {
+			const uint4 b = P.tri_bounds[slot];
+			if((b.x & 0xffffu) != MLV_BOUNDS_EMPTY) {
+				const int minx = (int)(b.x & 0xffffu), miny = (int)((b.x >> 16) & 0x7fffu), maxx = (int)(short)(b.y & 0xffffu), maxy = (int)(short)(b.y >> 16);
+				// ---- binner pass 1 + Hi-Z for this triangle
+				const BinTally tally = count_bins(P, minx, miny, maxx, maxy, __uint_as_float(b.z));
+				is_big = tally.big, is_huge = tally.huge;
+				if(tally.live) ++records;
+				else reinterpret_cast<uint32_t *>(P.tri_bounds + slot)[0] = MLV_BOUNDS_EMPTY; // k_bin_fill skips it
+				if(slot < P.tri_count && (tally.live || DEBUG)) {
+					// ---- the record of a surviving direct triangle: input assembler + vertex shader + setup again (pure functions
+					// of the same inputs: the values k_front computed), now including attributes and edge functions
+					const uint32_t t = slot;
+					uint32_t vi0, vi1, vi2;
+					fetch_indices<VS, INDEXED, DEBUG, VCACHE>(P, t, vi0, vi1, vi2);
+					float4 a0 = __ldg(P.vb + 2 * (size_t)vi0), b0 = __ldg(P.vb + 2 * (size_t)vi1), c0 = __ldg(P.vb + 2 * (size_t)vi2);
+					float4 a, bq, c;
+					TriSetup S;
+					if(VCACHE) {
+						const float4 qa = __ldg(P.vcache + 2 * (size_t)vi0 + 1), qb = __ldg(P.vcache + 2 * (size_t)vi1 + 1), qc = __ldg(P.vcache + 2 * (size_t)vi2 + 1);
+						a = __ldg(P.vcache + 2 * (size_t)vi0), bq = __ldg(P.vcache + 2 * (size_t)vi1), c = __ldg(P.vcache + 2 * (size_t)vi2);
+						ProjVertex pa, pb, pc; // s.x, s.y, s.w are not needed outside debug capture (which never uses the cache)
+						pa.s = make_float4(0.0f, 0.0f, qa.z, 0.0f), pa.sx = __float_as_int(qa.x), pa.sy = __float_as_int(qa.y);
+						pb.s = make_float4(0.0f, 0.0f, qb.z, 0.0f), pb.sx = __float_as_int(qb.x), pb.sy = __float_as_int(qb.y);
+						pc.s = make_float4(0.0f, 0.0f, qc.z, 0.0f), pc.sx = __float_as_int(qc.x), pc.sy = __float_as_int(qc.y);
+						pa.rw = 1.0f / a.w, pb.rw = 1.0f / bq.w, pc.rw = 1.0f / c.w; // a_reciprocal_ws (project_vertex): the same correctly rounded divide
+						setup_from_projected(pa, pb, pc, P, S);
+					} else {
+						a = vs_position<VS>(a0, P.cb), bq = vs_position<VS>(b0, P.cb), c = vs_position<VS>(c0, P.cb);
+						setup_project(a, bq, c, P, S);
+					}
+					setup_edges(P, S);
+					// ---- vertex shader, attribute part
+					float4 r1a, r1b, r1c;
+					float r2a, r2b, r2c;
+					vs_attributes<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), a, P.cb, P.vs_tex, P.rsqrt_lut, r1a, r2a);
+					vs_attributes<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), bq, P.cb, P.vs_tex, P.rsqrt_lut, r1b, r2b);
+					vs_attributes<VS>(c0, __ldg(P.vb + 2 * (size_t)vi2 + 1), c, P.cb, P.vs_tex, P.rsqrt_lut, r1c, r2c);
+					if(tally.live) {
+						staged = true;
+						TriRecord R;
+						make_record(R, S, pack_bounds(S), r1a, r1b, r1c, r2a, r2b, r2c);
+						uint4 *st = s_stage[warp];
+#pragma unroll
+						for(int i = 0; i < MLV_TRI_COV_U4; ++i) st[lane * MLV_TRI_COV_U4 + i] = R.cov[i];
+#pragma unroll
+						for(int i = 0; i < MLV_TRI_SHADE_U4; ++i)
+							st[32 * MLV_TRI_COV_U4 + lane * MLV_TRI_SHADE_U4 + i] = make_uint4(__float_as_uint(R.shade[i].x), __float_as_uint(R.shade[i].y), __float_as_uint(R.shade[i].z), __float_as_uint(R.shade[i].w));
+					}
+					if(DEBUG) emit_debug(P, t, t << 3, S, r1a, r1b, r1c, r2a, r2b, r2c);
+				}
+			}
+		}
+		// ---- triangles with large tile rectangles are queued for k_bin_big (one warp-aggregated atomic)
+		{
+			const uint32_t bmask = __ballot_sync(0xffffffffu, is_big);
+			if(bmask) {
+				uint32_t base = 0;
+				if(lane == 0) base = atomicAdd(&P.ctr->big_count, (uint32_t)__popc(bmask));
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if(is_big) P.big_queue[base + __popc(bmask & ((1u << lane) - 1u))] = slot;
+			}
+			if(is_huge) P.huge_queue[atomicAdd(&P.ctr->huge_count, 1u)] = slot; // rare: sky domes, full-screen quads
+		}
+		// ---- coalesced write-out of the staged records: the direct slots of a warp are adjacent in HBM, so the warp stores
+		// 1536 B of TriCov and 3072 B of TriShade with 128-bit stores instead of 32 scattered 16-byte pieces per instruction
+		__syncwarp();
+		const uint32_t valid = __ballot_sync(0xffffffffu, staged);
+		if(valid) {
+			const uint4 *st = s_stage[warp];
+			const size_t slot0 = (size_t)(slot - lane);
+			uint4 *cov = P.tri_cov + slot0 * MLV_TRI_COV_U4;
+			uint4 *sh = P.tri_shade + slot0 * MLV_TRI_SHADE_U4;
+#pragma unroll
+			for(int i = 0; i < MLV_TRI_COV_U4; ++i) {
+				const uint32_t piece = i * 32 + lane;
+				if((valid >> (piece / MLV_TRI_COV_U4)) & 1u) cov[piece] = st[piece];
+			}
+#pragma unroll
+			for(int i = 0; i < MLV_TRI_SHADE_U4; ++i) {
+				const uint32_t piece = i * 32 + lane;
+				if((valid >> (piece / MLV_TRI_SHADE_U4)) & 1u) sh[piece] = st[32 * MLV_TRI_COV_U4 + piece];
+			}
+		}
+		__syncwarp(); // the staging rows are reused by the next chunk of a persistent CTA
+	}
+	if(P.chunk_live) __syncthreads(); // s_live is rewritten by the next round
+	}
+	// work counter (mlv_work_counters.records_written): second word of the warp's stripe
+#pragma unroll
+	for(int d = 16; d > 0; d >>= 1) records += __shfl_xor_sync(0xffffffffu, records, d);
+	tally_records(P.stat_stripes, records);
 }
 
 // =================================================================================================
@@ -879,7 +949,6 @@ __global__ void __launch_bounds__(256) k_bin_big(const __grid_constant__ BinPara
 	const uint32_t n = P.ctr->big_count;
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-	uint32_t pairs = 0;
 	for(uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
 		const SlotBounds s = load_bounds(P.tri_bounds, P.big_queue[i], P.wt, P.ht);
 		const int w = s.tr.w(), cnt = w * s.tr.h();
@@ -887,7 +956,6 @@ __global__ void __launch_bounds__(256) k_bin_big(const __grid_constant__ BinPara
 			const int ty = s.tr.ty0 + k / w, tx = s.tr.tx0 + k % w;
 			if(!P.part.owns_row(ty)) continue;
 			const uint32_t bin = (uint32_t)(ty * P.wt + tx);
-			++pairs;
 			if(hiz_rejects(s.max_depth, P.tile_min, bin, P.keep_all)) atomicOr(P.bin_count + bin, MLV_TOUCHED);
 			else atomicAdd(P.bin_count + bin, 1u);
 		}
@@ -900,29 +968,28 @@ __global__ void __launch_bounds__(256) k_bin_big(const __grid_constant__ BinPara
 			const int ty = s.tr.ty0 + k / w, tx = s.tr.tx0 + k % w;
 			if(!P.part.owns_row(ty)) continue;
 			const uint32_t bin = (uint32_t)(ty * P.wt + tx);
-			++pairs;
 			if(hiz_rejects(s.max_depth, P.tile_min, bin, P.keep_all)) atomicOr(P.bin_count + bin, MLV_TOUCHED);
 			else atomicAdd(P.bin_count + bin, 1u);
 		}
 	}
-	tally_stats(P.stat_stripes, 0u, pairs);
+	// (the pairs were counted for Stats by the front half: tiles of the rectangle x owned rows)
 }
 
 // Pass 2 of the binner (main.c:950-962): every surviving (triangle, tile) pair takes the next position of its
 // bin's list (atomic on the running offset the scan left in bin_offset). One lane per triangle slot; rectangles
 // of more than 8 tiles are expanded cooperatively by the warp (four independent atomics in flight per lane),
 // huge ones by the whole grid. The per-bin order this leaves is arbitrary; k_tile does not depend on it.
-__device__ __forceinline__ void fill_one(const BinParams &P, int k, int cnt, int w, int tx0, int ty0, float max_depth, uint32_t key) {
+__device__ __forceinline__ void fill_one(const BinParams &P, int k, int cnt, int w, int tx0, int ty0, float max_depth, uint32_t slot) {
 	if(k >= cnt) return;
 	const int ty = ty0 + k / w, tx = tx0 + k % w;
 	if(!P.part.owns_row(ty)) return;
 	const uint32_t bin = (uint32_t)(ty * P.wt + tx);
-	if(!hiz_rejects(max_depth, P.tile_min, bin, P.keep_all)) P.pair_ids[atomicAdd(P.bin_offset + bin, 1u)] = key;
+	if(!hiz_rejects(max_depth, P.tile_min, bin, P.keep_all)) P.pair_ids[atomicAdd(P.bin_offset + bin, 1u)] = slot;
 }
 
 // unrolled, predicated walk over a rectangle of at most N tiles: all tile-minimum loads, then all atomics, then all stores
 template <int N>
-__device__ __forceinline__ void fill_small_rect(const BinParams &P, const SlotBounds &s, int cnt) {
+__device__ __forceinline__ void fill_small_rect(const BinParams &P, const SlotBounds &s, int cnt, uint32_t slot) {
 	uint32_t bins[N], pos[N];
 	bool ok[N];
 	int tx = s.tr.tx0, ty = s.tr.ty0;
@@ -941,13 +1008,13 @@ __device__ __forceinline__ void fill_small_rect(const BinParams &P, const SlotBo
 	for(int k = 0; k < N; ++k) pos[k] = ok[k] ? atomicAdd(P.bin_offset + bins[k], 1u) : 0u;
 #pragma unroll
 	for(int k = 0; k < N; ++k)
-		if(ok[k]) P.pair_ids[pos[k]] = s.key;
+		if(ok[k]) P.pair_ids[pos[k]] = slot;
 }
 
 __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinParams P, uint32_t pair_capacity) {
 	pdl_prologue();
 	if(P.ctr->pair_total > pair_capacity || P.ctr->pair_total == 0u) return; // draw skipped (MLV_FLAG_PAIR_OVERFLOW is set) / nothing survived Hi-Z
-	const uint32_t n = P.direct_slots + min(P.ctr->ovf_count, P.ovf_capacity); // (a draw that ran out of overflow slots is skipped as a whole: k_bin_scan poisons pair_total)
+	const uint32_t n = P.direct_slots + min(P.dctr->ovf_count, P.ovf_capacity); // (a draw that ran out of overflow slots is skipped as a whole: k_bin_scan poisons pair_total)
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	for(uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < n; base += warps * 32u) {
@@ -958,25 +1025,27 @@ __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinPar
 		const bool live_chunk = !P.chunk_live || slot >= P.direct_slots || __ldg(P.chunk_live + slot / MLV_GEOM_THREADS) != 0;
 		if(slot < n && live_chunk) s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
 		const int w = s.empty ? 0 : s.tr.w(), cnt = s.empty ? 0 : w * s.tr.h();
-		if(cnt > 0 && cnt <= 4) fill_small_rect<4>(P, s, cnt);
-		else if(cnt > 0 && cnt <= 8) fill_small_rect<8>(P, s, cnt);
+		if(cnt > 0 && cnt <= 4) fill_small_rect<4>(P, s, cnt, slot);
+		else if(cnt > 0 && cnt <= 8) fill_small_rect<8>(P, s, cnt, slot);
 	}
 	const uint32_t nbig = P.ctr->big_count;
 	for(uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nbig; i += warps) { // 9..MLV_HUGE_TILES tiles: one warp per triangle
-		const SlotBounds s = load_bounds(P.tri_bounds, P.big_queue[i], P.wt, P.ht);
+		const uint32_t slot = P.big_queue[i];
+		const SlotBounds s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
 		const int w = s.tr.w(), cnt = w * s.tr.h();
 		for(int k = (int)lane; k < cnt; k += 128) {
-			fill_one(P, k, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, s.key);
-			fill_one(P, k + 32, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, s.key);
-			fill_one(P, k + 64, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, s.key);
-			fill_one(P, k + 96, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, s.key);
+			fill_one(P, k, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, slot);
+			fill_one(P, k + 32, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, slot);
+			fill_one(P, k + 64, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, slot);
+			fill_one(P, k + 96, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, slot);
 		}
 	}
 	const uint32_t nhuge = P.ctr->huge_count;
 	for(uint32_t i = 0; i < nhuge; ++i) { // huge rectangles, grid-cooperative
-		const SlotBounds s = load_bounds(P.tri_bounds, P.huge_queue[i], P.wt, P.ht);
+		const uint32_t slot = P.huge_queue[i];
+		const SlotBounds s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
 		const int w = s.tr.w(), cnt = w * s.tr.h();
-		for(int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < cnt; k += (int)(gridDim.x * blockDim.x)) fill_one(P, k, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, s.key);
+		for(int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < cnt; k += (int)(gridDim.x * blockDim.x)) fill_one(P, k, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, slot);
 	}
 }
 
@@ -1107,7 +1176,7 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 			if(warp == 0) {
 				// A draw whose clipped triangles ran out of overflow slots (MLV_FLAG_TRI_OVERFLOW) is skipped as a whole,
 				// like one whose pairs do not fit: k_bin_fill and k_tile return when pair_total exceeds the capacity.
-				const bool tri_overflow = P.ctr->ovf_count > P.ovf_capacity;
+				const bool tri_overflow = P.dctr->ovf_count > P.ovf_capacity;
 				P.ctr->pair_total = tri_overflow ? 0xffffffffu : total;
 				if(total > P.pair_capacity) atomicOr(&P.ctr->error_flags, MLV_FLAG_PAIR_OVERFLOW);
 			} else {
@@ -1141,24 +1210,36 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 // tile: rasterizer + Hi-Z + early-Z + pixel shader + output merger
 // =================================================================================================
 
-// Restores ascending-key order inside one bin list (the order the reference's serial fill produces,
-// main.c:950-962). n <= 32: bitonic network in registers. Larger lists: stable LSD radix split, one bit
-// per pass, ping-ponging between the list and a scratch segment of the same extent.
-__device__ __forceinline__ void sort_bin_ids(uint32_t *ids, uint32_t *tmp, uint32_t n, uint32_t key_bits) {
+// record / key of a slot (mlv_internal.cuh "Triangle identity")
+__device__ __forceinline__ const uint4 *cov_of(const TileParams &P, uint32_t slot) {
+	return slot < P.direct_slots ? P.tri_cov + (size_t)slot * MLV_TRI_COV_U4 : P.ovf_cov + (size_t)(slot - P.direct_slots) * MLV_TRI_COV_U4;
+}
+__device__ __forceinline__ const float4 *shade_of(const TileParams &P, uint32_t slot) {
+	return reinterpret_cast<const float4 *>(slot < P.direct_slots ? P.tri_shade + (size_t)slot * MLV_TRI_SHADE_U4 : P.ovf_shade + (size_t)(slot - P.direct_slots) * MLV_TRI_SHADE_U4);
+}
+__device__ __forceinline__ uint32_t key_of(const TileParams &P, uint32_t slot) {
+	return slot < P.direct_slots ? (slot << 3) : __ldg(reinterpret_cast<const uint32_t *>(P.tri_bounds + slot) + 3);
+}
+
+// Debug capture only: restores ascending-KEY order inside one bin list of slots (the order the reference's serial fill
+// produces, main.c:950-962). n <= 32: bitonic network in registers. Larger lists: stable LSD radix split on the key, one
+// bit per pass, ping-ponging between the list and a scratch segment of the same extent.
+__device__ __forceinline__ void sort_bin_ids(const TileParams &P, uint32_t *ids, uint32_t *tmp, uint32_t n, uint32_t key_bits) {
 	const uint32_t lane = lane_id();
 	if(n <= 32u) {
-		uint32_t v = (lane < n) ? ids[lane] : 0xffffffffu;
+		const uint32_t slot = (lane < n) ? ids[lane] : 0xffffffffu;
+		unsigned long long v = (lane < n) ? (((unsigned long long)key_of(P, slot) << 32) | slot) : ~0ull;
 #pragma unroll
 		for(int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
 			for(int j = k >> 1; j > 0; j >>= 1) {
-				const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+				const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
 				const bool up = ((lane & k) == 0);
 				const bool lower = ((lane & j) == 0);
 				v = (lower == up) ? min(v, o) : max(v, o);
 			}
 		}
-		if(lane < n) ids[lane] = v;
+		if(lane < n) ids[lane] = (uint32_t)v;
 		__syncwarp();
 		return;
 	}
@@ -1169,7 +1250,7 @@ __device__ __forceinline__ void sort_bin_ids(uint32_t *ids, uint32_t *tmp, uint3
 		uint32_t zeros = 0;
 		for(uint32_t i0 = 0; i0 < n; i0 += 32u) {
 			const uint32_t i = i0 + lane;
-			const bool isz = (i < n) && !((src[i] >> bit) & 1u);
+			const bool isz = (i < n) && !((key_of(P, src[i]) >> bit) & 1u);
 			zeros += __popc(__ballot_sync(0xffffffffu, isz));
 		}
 		if(zeros == 0u || zeros == n) continue; // this bit does not discriminate
@@ -1178,7 +1259,7 @@ __device__ __forceinline__ void sort_bin_ids(uint32_t *ids, uint32_t *tmp, uint3
 			const uint32_t i = i0 + lane;
 			const bool valid = i < n;
 			const uint32_t val = valid ? src[i] : 0u;
-			const bool isz = valid && !((val >> bit) & 1u);
+			const bool isz = valid && !((key_of(P, val) >> bit) & 1u);
 			const uint32_t bz = __ballot_sync(0xffffffffu, isz);
 			const uint32_t bo = __ballot_sync(0xffffffffu, valid && !isz);
 			if(isz) dst[zpos + __popc(bz & lt)] = val;
@@ -1256,13 +1337,6 @@ __device__ __forceinline__ float interp(float v0, float v1, float v2, float u, f
 	return t;
 }
 
-// key -> record slot (follows the redirect of a clipped input triangle)
-__device__ __forceinline__ uint32_t slot_of_key(const TileParams &P, uint32_t key) {
-	const uint32_t t = key >> 3;
-	const uint4 c2 = __ldg(P.tri_cov + (size_t)t * MLV_TRI_COV_U4 + 2);
-	return (c2.z == MLV_REDIRECT) ? (P.direct_slots + c2.x + (key & 7u)) : t;
-}
-
 // perspective-correct barycentrics of the pixel whose edge functions are E1, E2 (main.c:1089-1115)
 __device__ __forceinline__ void perspective_barycentrics(uint32_t E1, uint32_t E2, float ooa, const float4 &s1, float &pbx, float &pby) {
 	float bx, by;
@@ -1279,14 +1353,13 @@ __device__ __forceinline__ void perspective_barycentrics(uint32_t E1, uint32_t E
 #define MLV_PS_ID_BASIC_TRILINEAR 3
 
 template <int PS>
-__device__ __forceinline__ uint32_t shade_pixel(const TileParams &P, uint32_t key, uint32_t X, uint32_t Y) {
-	const uint32_t slot = slot_of_key(P, key);
-	const uint4 *cov = P.tri_cov + (size_t)slot * MLV_TRI_COV_U4;
+__device__ __forceinline__ uint32_t shade_pixel(const TileParams &P, uint32_t slot, uint32_t X, uint32_t Y) {
+	const uint4 *cov = cov_of(P, slot);
 	const uint4 c0 = __ldg(cov), c1 = __ldg(cov + 1);
 	const uint32_t c2x = __ldg(reinterpret_cast<const uint32_t *>(cov + 2));
 	const uint32_t E1 = c0.w * X + c1.x * Y + c1.y;
 	const uint32_t E2 = c1.z * X + c1.w * Y + c2x;
-	const float4 *sh = reinterpret_cast<const float4 *>(P.tri_shade + (size_t)slot * MLV_TRI_SHADE_U4);
+	const float4 *sh = shade_of(P, slot);
 	const float4 s0 = __ldg(sh), s1 = __ldg(sh + 1), r1a = __ldg(sh + 2), r1b = __ldg(sh + 3), r1c = __ldg(sh + 4), s5 = __ldg(sh + 5);
 	float pbx, pby;
 	perspective_barycentrics(E1, E2, s0.x, s1, pbx, pby);
@@ -1356,12 +1429,15 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_const
 				c->work.pairs_listed += c->pair_total;
 				c->work.tiles_visited += c->n_cbins;
 			}
+			c->stats.vertex_count += P.index_count;             // main.c:1228-1232
+			c->stats.input_triangle_count += P.direct_slots;
 			c->stats.assembled_triangle_count += tris;
 			c->stats.total_triangle_count_in_bins += pairs;
 			c->stats.active_bin_count += c->draw_active_bins;
-			c->last_ovf_count = min(c->ovf_count, ovf_capacity);
+			c->last_ovf_count = min(P.dctr->ovf_count, ovf_capacity);
 			c->draw_active_bins = 0u;
-			c->ovf_count = c->clip_count = c->big_count = c->huge_count = 0u;
+			c->big_count = c->huge_count = 0u;
+			P.dctr->ovf_count = P.dctr->clip_count = 0u; // the draw context is free for the front half of a later draw
 			c->ticket = 0u;
 		}
 		// the epoch tags the look-back words of the next draw's scan; when its 30 bits wrap (after 2^30 draws) every
@@ -1389,7 +1465,8 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_const
 		// read_tile (main.c:577-587)
 		uint4 pix = P.fb[(size_t)b * 32u + lane];
 		float d0 = __uint_as_float(pix.z), d1 = __uint_as_float(pix.w);
-		uint32_t win0 = MLV_NO_WINNER, win1 = MLV_NO_WINNER;
+		uint32_t win0 = MLV_NO_WINNER, win1 = MLV_NO_WINNER; // keys of the fragments that hold the pixels (depth ties go to the greater key)
+		uint32_t wslot0 = 0u, wslot1 = 0u;
 		const float tile_min_old = P.tile_min[b]; // get_tile_minimum_depth: previous draws only (N3)
 
 		if(n == 0u) { // touched bin whose pairs were all Hi-Z-rejected at binning time: write_tile's tile-minimum refresh only
@@ -1405,7 +1482,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_const
 		// reference's result in any visiting order, and the list k_bin_fill left in arrival order needs no sorting.
 		// Debug capture sorts it anyway so that mlv_debug_read_bins shows the reference's per-tile order.
 		uint32_t *ids = P.pair_ids + off;
-		if(P.sort_lists) sort_bin_ids(ids, P.pair_tmp + off, n, P.key_bits);
+		if(P.sort_lists) sort_bin_ids(P, ids, P.pair_tmp + off, n, P.key_bits);
 
 		for(uint32_t base = 0; base < n; base += 32u) {
 			// ---- rasterizer, lanes over triangles (main.c:996-1041)
@@ -1417,9 +1494,9 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_const
 			uint32_t c2x = 0u, slot = 0u;
 			int x0 = 0, x1 = -1, y0 = 0, y1 = -1; // (bounds & tile) of a triangle that passes Hi-Z; empty otherwise
 			if(k < n) {
-				key = ids[k];
-				slot = slot_of_key(P, key);
-				const uint4 *cov = P.tri_cov + (size_t)slot * MLV_TRI_COV_U4;
+				slot = ids[k];
+				key = key_of(P, slot);
+				const uint4 *cov = cov_of(P, slot);
 				const uint4 c2 = __ldg(cov + 2);
 				const float max_depth = __uint_as_float(c2.y);
 				if(!(max_depth < tile_min_old)) { // Hi-Z (main.c:1005-1010)
@@ -1486,7 +1563,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_const
 				if(lo | hi) {
 					a1 = c0.w, b1 = c1.x, e1 = c0.w * X0 + c1.x * Y0 + c1.y;
 					a2 = c1.z, b2 = c1.w, e2 = c1.z * X0 + c1.w * Y0 + c2x;
-					s0 = __ldg(reinterpret_cast<const float4 *>(P.tri_shade + (size_t)slot * MLV_TRI_SHADE_U4));
+					s0 = __ldg(shade_of(P, slot));
 				}
 				if(P.dbg.infos) {
 					mlv_ref_tile_info ti;
@@ -1509,7 +1586,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_const
 				const uint32_t ta2 = __shfl_sync(0xffffffffu, a2, j), tb2 = __shfl_sync(0xffffffffu, b2, j), te2 = __shfl_sync(0xffffffffu, e2, j);
 				const float ooa = __shfl_sync(0xffffffffu, s0.x, j), z0 = __shfl_sync(0xffffffffu, s0.y, j);
 				const float z1 = __shfl_sync(0xffffffffu, s0.z, j), z2 = __shfl_sync(0xffffffffu, s0.w, j);
-				const uint32_t tkey = __shfl_sync(0xffffffffu, key, j);
+				const uint32_t tkey = __shfl_sync(0xffffffffu, key, j), tslot = __shfl_sync(0xffffffffu, slot, j);
 				const uint32_t E1 = ta1 * (px << 4) + tb1 * (py << 4) + te1;
 				const uint32_t E2 = ta2 * (px << 4) + tb2 * (py << 4) + te2;
 				if(set0 & bitj) {
@@ -1519,6 +1596,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_const
 					if(z > d0 || (z == d0 && (win0 == MLV_NO_WINNER || tkey > win0))) { // z >= depth in id order (main.c:1166), see above; false on NaN
 						d0 = z;
 						win0 = tkey;
+						wslot0 = tslot;
 					}
 				}
 				if(set1 & bitj) {
@@ -1528,14 +1606,15 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_const
 					if(z > d1 || (z == d1 && (win1 == MLV_NO_WINNER || tkey > win1))) {
 						d1 = z;
 						win1 = tkey;
+						wslot1 = tslot;
 					}
 				}
 			}
 		}
 
 		// ---- pixel shader + output merger, once per pixel on the last fragment that passed (main.c:1170-1181)
-		if(win0 != MLV_NO_WINNER) pix.x = shade_pixel<PS>(P, win0, X, Y);
-		if(win1 != MLV_NO_WINNER) pix.y = shade_pixel<PS>(P, win1, X, Y + 64u);
+		if(win0 != MLV_NO_WINNER) pix.x = shade_pixel<PS>(P, wslot0, X, Y);
+		if(win1 != MLV_NO_WINNER) pix.y = shade_pixel<PS>(P, wslot1, X, Y + 64u);
 		pix.z = __float_as_uint(d0);
 		pix.w = __float_as_uint(d1);
 

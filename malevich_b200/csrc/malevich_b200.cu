@@ -84,7 +84,24 @@ struct mlv_command_list {
 	std::vector<const void *> *geom_funcs; // kernels whose first parameter is a GeomParams
 	std::vector<const void *> *vertex_funcs; // ... and that take a second u32 (k_vertex)
 	std::vector<GeomNode *> *geom_nodes;
-	std::vector<void *> *graveyard;        // arenas that grew while recording: earlier nodes still address the old allocation
+};
+
+#define MLV_DRAW_CONTEXTS 8 /* draws whose front half may run ahead; MAX_OBJECT_COUNT_PER_SCENE of the reference is 8 (main.c:44) */
+struct DrawCtx {
+	uint4 *tri_bounds;
+	uint32_t slot_capacity;
+	uint32_t *clip_queue;
+	uint32_t queue_capacity;
+	uint4 *ovf_cov, *ovf_shade;
+	uint32_t ovf_capacity;
+	float4 *vcache; // post-transform vertex cache (k_vertex): read by the front half and, for the survivors, by the back half
+	uint32_t vcache_capacity;
+	uint8_t *chunk_live;
+	uint32_t chunk_capacity;
+	DrawCounters *dctr;
+	unsigned long long *stat_stripes; // Stats contributions of the draw, folded into Stats by its k_tile (main-stream order)
+	cudaEvent_t front_done, free_ev;
+	bool free_recorded;
 };
 
 struct mlv_device {
@@ -114,15 +131,22 @@ struct mlv_device {
 	mlv_ref_compacted_bin *cbins;
 	uint32_t *pair_ids, *pair_tmp;
 	uint64_t pair_capacity;
-	uint4 *tri_cov, *tri_shade;
-	uint4 *tri_bounds;
-	uint32_t *clip_queue, *big_queue, *huge_queue;
-	// Post-transform vertex cache, double-buffered: k_vertex of draw d+1 depends on nothing draw d produces, so it runs
-	// on a second stream underneath draw d's binning and tile kernels and joins the main stream before k_geom.
-	float4 *vcache[2];
-	uint32_t vcache_capacity;
-	int vcache_sel;
-	cudaStream_t side_stream;
+	uint4 *tri_cov, *tri_shade;      // records of the direct slots
+	uint32_t *big_queue, *huge_queue;
+	uint32_t queue_capacity;
+	// Draw contexts: what the FRONT half of a draw (its own stream, running ahead) hands to its BACK half (main stream).
+	DrawCtx ctxs[MLV_DRAW_CONTEXTS];
+	uint32_t num_ctx;                // 1 under debug capture (the reference-layout capture arrays exist once)
+	uint64_t draw_seq;
+	DrawCtx *last_ctx;
+	cudaStream_t front_streams[MLV_DRAW_CONTEXTS]; // context i runs its front half on stream i % num_front_streams: independent latency chains overlap
+	uint32_t num_front_streams;
+	bool front_needs_sync[MLV_DRAW_CONTEXTS];      // per front stream: not yet ordered after what the main stream held when reset_front_order ran (creation, a graph execution)
+	bool front_touched[MLV_DRAW_CONTEXTS];         // per front stream: has joined the capture of the command list being recorded
+	cudaEvent_t ev_front_join[MLV_DRAW_CONTEXTS];
+	int knob_no_pdl_tile, knob_no_pdl_back;           // the front stream has not yet been ordered after what the main stream holds (creation, a graph execution)
+	std::vector<void *> *graveyard;  // arenas replaced while command lists that address them exist
+	uint32_t lists_alive;
 	// Buffer uploads run on a copy stream: a draw waits only for the buffers it binds, so the upload of mesh k+1
 	// overlaps the draw of mesh k (a host that streams its geometry every frame is otherwise PCIe-then-render serial).
 	cudaStream_t copy_stream;
@@ -133,17 +157,12 @@ struct mlv_device {
 	cudaStream_t readback_stream;
 	cudaEvent_t ev_resolved, ev_readback_done;
 	bool readback_in_flight;
-	cudaEvent_t ev_vertex_done, ev_main_sync, ev_cache_free[2];
-	bool cache_free_recorded[2];
-	bool side_needs_sync; // the side stream has not yet been ordered after the device's creation-time work on the main stream
-	uint8_t *chunk_live;
-	uint32_t chunk_live_capacity;
+	cudaEvent_t ev_main_sync;
 	uint32_t bin_begin, bin_end; // bins this rank can touch: everything, or one contiguous band
 	uint32_t tri_capacity; // slots (direct + overflow)
 	unsigned long long *scan_state; // 2 x scan_blocks look-back words
 	uint32_t scan_blocks;
 	Counters *ctr;
-	unsigned long long *stat_stripes;
 	uint32_t *rsqrt_lut;
 	// debug capture
 	DebugOut dbg;
@@ -192,7 +211,17 @@ struct mlv_device {
 	size_t prof_used;
 };
 
+// Events recorded inside / outside a capture cannot order work on the other side: the next draw's front half starts from
+// a fork of the main stream instead of the per-context events.
+static void reset_front_order(mlv_device *dev) {
+	cudaEventRecord(dev->ev_main_sync, dev->stream); // the fork point: front halves issued from now on come after everything the main stream holds now
+	for(bool &b : dev->front_needs_sync) b = true;
+	for(bool &b : dev->front_touched) b = false;
+	for(DrawCtx &c : dev->ctxs) c.free_recorded = false;
+}
+
 // Every kernel goes through here: launched with programmatic stream serialisation (see pdl_prologue in kernels.cuh).
+static thread_local int g_pdl = 1; // 0: the next launches are plain stream-ordered launches
 template <typename... KArgs, typename... Args>
 static void launch_pdl(void (*kernel)(KArgs...), uint32_t grid, uint32_t block, cudaStream_t stream, Args &&...args) {
 	cudaLaunchConfig_t cfg;
@@ -202,7 +231,7 @@ static void launch_pdl(void (*kernel)(KArgs...), uint32_t grid, uint32_t block, 
 	cfg.stream = stream;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	attr[0].val.programmaticStreamSerializationAllowed = g_pdl;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
 	cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
@@ -243,6 +272,12 @@ static int check_launch(mlv_device *dev, const char *what) {
 		cudaEventRecord((*dev->prof_events)[dev->prof_used + 1], dev->stream);
 		dev->prof_used += 2;
 	}
+	return MLV_OK;
+}
+
+static int check_launch_only(mlv_device *, const char *what) {
+	cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return fail(MLV_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
 	return MLV_OK;
 }
 
@@ -312,16 +347,37 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	} while(0)
 
 	CREATE_TRY(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
-	CREATE_TRY(cudaStreamCreateWithFlags(&dev->side_stream, cudaStreamNonBlocking));
+	dev->graveyard = new std::vector<void *>();
+	dev->num_ctx = (desc->flags & MLV_DEVICE_DEBUG_CAPTURE) ? 1u : MLV_DRAW_CONTEXTS;
+	{
+		const char *e = getenv("MLV_FRONT_STREAMS");
+		uint32_t n = e ? (uint32_t)atoi(e) : dev->num_ctx;
+		if(n < 1) n = 1;
+		if(n > dev->num_ctx) n = dev->num_ctx;
+		dev->num_front_streams = n;
+		int prio_lo = 0, prio_hi = 0;
+		CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		const char *p = getenv("MLV_FRONT_PRIORITY");
+		const int prio = (p && atoi(p)) ? prio_hi : prio_lo;
+		for(uint32_t i = 0; i < n; ++i) CREATE_TRY(cudaStreamCreateWithPriority(&dev->front_streams[i], cudaStreamNonBlocking, prio));
+		dev->knob_no_pdl_tile = getenv("MLV_NO_PDL_TILE") ? atoi(getenv("MLV_NO_PDL_TILE")) : 0;
+		dev->knob_no_pdl_back = getenv("MLV_NO_PDL_BACK") ? atoi(getenv("MLV_NO_PDL_BACK")) : 0;
+	}
 	CREATE_TRY(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_last_draw, cudaEventDisableTiming));
 	CREATE_TRY(cudaStreamCreateWithFlags(&dev->readback_stream, cudaStreamNonBlocking));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_resolved, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_readback_done, cudaEventDisableTiming));
-	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_vertex_done, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_main_sync, cudaEventDisableTiming));
-	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_cache_free[0], cudaEventDisableTiming));
-	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_cache_free[1], cudaEventDisableTiming));
+	for(uint32_t i = 0; i < dev->num_ctx; ++i) {
+		DrawCtx &c = dev->ctxs[i];
+		CREATE_TRY(cudaEventCreateWithFlags(&c.front_done, cudaEventDisableTiming));
+		CREATE_TRY(cudaEventCreateWithFlags(&c.free_ev, cudaEventDisableTiming));
+		CREATE_TRY(cudaMalloc(&c.dctr, sizeof(DrawCounters)));
+		CREATE_TRY(cudaMalloc(&c.stat_stripes, MLV_STAT_STRIPES * 128));
+		CREATE_TRY(cudaMemsetAsync(c.dctr, 0, sizeof(DrawCounters), dev->stream));
+		CREATE_TRY(cudaMemsetAsync(c.stat_stripes, 0, MLV_STAT_STRIPES * 128, dev->stream));
+	}
 	if(num_ranks > 1) {
 		int prio_lo = 0, prio_hi = 0; // the exchange is short and latency-critical: its CTAs go first when SM slots free up
 		CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -331,7 +387,6 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 		CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_fb_free[0], cudaEventDisableTiming));
 		CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_fb_free[1], cudaEventDisableTiming));
 	}
-	dev->side_needs_sync = true;
 	const size_t nb = dev->num_bins;
 	CREATE_TRY(cudaMalloc(&dev->fb_pair[0], nb * 32 * sizeof(uint4)));
 	dev->fb = dev->fb_pair[0];
@@ -340,10 +395,8 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	CREATE_TRY(cudaMalloc(&dev->bin_offset, nb * sizeof(uint32_t)));
 	CREATE_TRY(cudaMalloc(&dev->cbins, nb * sizeof(mlv_ref_compacted_bin)));
 	CREATE_TRY(cudaMalloc(&dev->pair_ids, dev->pair_capacity * sizeof(uint32_t)));
-	CREATE_TRY(cudaMalloc(&dev->pair_tmp, dev->pair_capacity * sizeof(uint32_t)));
+	// (pair_tmp, the scratch of the debug-capture list sort, is allocated with the first debug draw)
 	CREATE_TRY(cudaMalloc(&dev->ctr, sizeof(Counters)));
-	CREATE_TRY(cudaMalloc(&dev->stat_stripes, MLV_STAT_STRIPES * 128));
-	CREATE_TRY(cudaMemsetAsync(dev->stat_stripes, 0, MLV_STAT_STRIPES * 128, dev->stream));
 	dev->scan_blocks = (dev->bin_end - dev->bin_begin + MLV_SCAN_THREADS * MLV_SCAN_ITEMS - 1) / (MLV_SCAN_THREADS * MLV_SCAN_ITEMS);
 	if(dev->scan_blocks == 0) dev->scan_blocks = 1;
 	CREATE_TRY(cudaMalloc(&dev->scan_state, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long)));
@@ -374,6 +427,8 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 		CREATE_TRY(cudaMemsetAsync(dev->gather, 0, dev->chunk_bytes * num_ranks, dev->stream));
 	}
 	CREATE_TRY(cudaStreamSynchronize(dev->stream));
+	for(uint32_t i = 0; i < dev->num_front_streams; ++i) CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_front_join[i], cudaEventDisableTiming));
+	reset_front_order(dev);
 #undef CREATE_TRY
 	*out_device = dev;
 	return MLV_OK;
@@ -393,23 +448,37 @@ void mlv_destroy_device(mlv_device *dev) {
 		cudaGetLastError();
 	}
 	if(dev->stream) cudaStreamSynchronize(dev->stream);
-	if(dev->side_stream) cudaStreamSynchronize(dev->side_stream);
+	for(cudaStream_t fs : dev->front_streams)
+		if(fs) cudaStreamSynchronize(fs);
 	if(dev->copy_stream) cudaStreamSynchronize(dev->copy_stream);
 	if(dev->xchg_stream) cudaStreamSynchronize(dev->xchg_stream);
 	for(int i = 0; i < dev->ipc_opened_count; ++i) cudaIpcCloseMemHandle(dev->ipc_opened[i]);
-	void *ptrs[] = { dev->fb_pair[0], dev->fb_pair[1], dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->tri_bounds, dev->clip_queue, dev->big_queue, dev->huge_queue, dev->vcache[0], dev->vcache[1], dev->chunk_live,
-		             dev->scan_state, dev->ctr, dev->stat_stripes, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather, dev->p2p_color[0], dev->p2p_color[1], dev->p2p_flags };
+	void *ptrs[] = { dev->fb_pair[0], dev->fb_pair[1], dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->big_queue, dev->huge_queue,
+		             dev->scan_state, dev->ctr, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather, dev->p2p_color[0], dev->p2p_color[1], dev->p2p_flags };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
+	for(cudaEvent_t e : dev->ev_front_join)
+		if(e) cudaEventDestroy(e);
+	for(DrawCtx &c : dev->ctxs) {
+		for(void *p : { (void *)c.tri_bounds, (void *)c.clip_queue, (void *)c.ovf_cov, (void *)c.ovf_shade, (void *)c.vcache, (void *)c.chunk_live, (void *)c.dctr, (void *)c.stat_stripes })
+			if(p) cudaFree(p);
+		if(c.front_done) cudaEventDestroy(c.front_done);
+		if(c.free_ev) cudaEventDestroy(c.free_ev);
+	}
+	if(dev->graveyard) {
+		for(void *p : *dev->graveyard) cudaFree(p);
+		delete dev->graveyard;
+	}
 	if(dev->stream) cudaStreamDestroy(dev->stream);
-	if(dev->side_stream) cudaStreamDestroy(dev->side_stream);
+	for(cudaStream_t fs : dev->front_streams)
+		if(fs) cudaStreamDestroy(fs);
 	if(dev->copy_stream) cudaStreamDestroy(dev->copy_stream);
 	if(dev->xchg_stream) cudaStreamDestroy(dev->xchg_stream);
 	if(dev->readback_stream) {
 		cudaStreamSynchronize(dev->readback_stream);
 		cudaStreamDestroy(dev->readback_stream);
 	}
-	for(cudaEvent_t e : { dev->ev_last_draw, dev->ev_resolved, dev->ev_readback_done, dev->ev_vertex_done, dev->ev_main_sync, dev->ev_cache_free[0], dev->ev_cache_free[1], dev->ev_frame_done, dev->ev_xchg_done, dev->ev_fb_free[0], dev->ev_fb_free[1] })
+	for(cudaEvent_t e : { dev->ev_last_draw, dev->ev_resolved, dev->ev_readback_done, dev->ev_main_sync, dev->ev_frame_done, dev->ev_xchg_done, dev->ev_fb_free[0], dev->ev_fb_free[1] })
 		if(e) cudaEventDestroy(e);
 	if(dev->prof_events) {
 		for(cudaEvent_t e : *dev->prof_events) cudaEventDestroy(e);
@@ -423,6 +492,7 @@ int mlv_finish(mlv_device *dev) {
 	if(int rc = immediate_only(dev, "mlv_finish")) return rc;
 	if(int rc = use_device(dev)) return rc;
 	CUDA_TRY(cudaStreamSynchronize(dev->stream));
+	for(uint32_t i = 0; i < dev->num_front_streams; ++i) CUDA_TRY(cudaStreamSynchronize(dev->front_streams[i]));
 	CUDA_TRY(cudaStreamSynchronize(dev->copy_stream)); // uploads no draw has consumed yet
 	CUDA_TRY(cudaStreamSynchronize(dev->readback_stream));
 	dev->readback_in_flight = false;
@@ -500,6 +570,7 @@ void mlv_release_buffer(mlv_device *dev, mlv_buffer *buf) {
 	if(!dev || !buf) return;
 	cudaSetDevice(dev->cuda_dev);
 	cudaStreamSynchronize(dev->stream);
+	for(uint32_t i = 0; i < dev->num_front_streams; ++i) cudaStreamSynchronize(dev->front_streams[i]);
 	cudaStreamSynchronize(dev->copy_stream);
 	if(dev->vb == buf) dev->vb = nullptr;
 	if(dev->ib == buf) dev->ib = nullptr;
@@ -779,8 +850,7 @@ static cudaError_t regrow(T **p, size_t count) {
 	*p = nullptr;
 	return cudaMalloc((void **)p, count * sizeof(T));
 }
-// cudaStreamSynchronize is illegal on a capturing stream; nothing is executing then anyway
-static cudaError_t sync_unless_recording(mlv_device *dev, cudaStream_t s) { return dev->recording ? cudaSuccess : cudaStreamSynchronize(s); }
+
 
 static TexDesc tex_desc(const mlv_texture *t) {
 	TexDesc d;
@@ -799,58 +869,66 @@ static void note_geom_func(mlv_device *dev, const void *func, bool is_vertex) {
 	if(std::find(v->begin(), v->end(), func) == v->end()) v->push_back(func);
 }
 
+// The three geometry kernels of a draw for one vertex shader (template dispatch on indexed / debug capture / vertex cache).
 template <int VS>
-static void launch_geom(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed, uint32_t vcache_vertices) {
+static void launch_front(mlv_device *dev, cudaStream_t fs, const GeomParams &gp, uint32_t nblocks, bool indexed, uint32_t vcache_vertices) {
 	const bool debug = gp.keep_all;
 	if(nblocks > dev->sm_count * 4u) nblocks = dev->sm_count * 4u; // persistent grid: 4 CTAs per SM stride over the chunks (sort-first: and cull them in place)
 	if(vcache_vertices) {
-		const int sel = dev->vcache_sel;
-		dev->vcache_sel ^= 1;
-		// Per-stage profiling brackets every kernel with events on the main stream, so it keeps k_vertex there.
-		cudaStream_t vs_stream = dev->prof_on ? dev->stream : dev->side_stream;
-		if(!dev->prof_on) {
-			if(dev->side_needs_sync) { // first use: everything issued on the main stream so far comes first
-				cudaEventRecord(dev->ev_main_sync, dev->stream);
-				cudaStreamWaitEvent(dev->side_stream, dev->ev_main_sync, 0);
-				dev->side_needs_sync = false;
-			} else if(dev->cache_free_recorded[sel]) { // the k_geom that read this half of the cache two draws ago
-				cudaStreamWaitEvent(dev->side_stream, dev->ev_cache_free[sel], 0);
-			}
-		}
 		prof_pre(dev, MLV_STAGE_VERTEX);
 		note_geom_func(dev, (const void *)k_vertex<VS>, true);
-		note_geom_func(dev, (const void *)k_geom<VS, true, false, true>, false);
-		launch_pdl(k_vertex<VS>, (vcache_vertices + 255u) / 256u, 256, vs_stream, gp, vcache_vertices);
+		launch_pdl(k_vertex<VS>, (vcache_vertices + 255u) / 256u, 256, fs, gp, vcache_vertices);
 		check_launch(dev, "k_vertex");
-		if(!dev->prof_on) {
-			cudaEventRecord(dev->ev_vertex_done, dev->side_stream);
-			cudaStreamWaitEvent(dev->stream, dev->ev_vertex_done, 0);
-		}
-		prof_pre(dev, MLV_STAGE_GEOMETRY);
-		launch_pdl(k_geom<VS, true, false, true>, nblocks, MLV_GEOM_THREADS, dev->stream, gp);
-		// (recorded before check_launch's profiling event so the GEOMETRY bracket still closes on the kernel)
-		cudaEventRecord(dev->ev_cache_free[sel], dev->stream);
-		dev->cache_free_recorded[sel] = true;
-		return;
 	}
 	prof_pre(dev, MLV_STAGE_GEOMETRY);
-	note_geom_func(dev, indexed ? (debug ? (const void *)k_geom<VS, true, true, false> : (const void *)k_geom<VS, true, false, false>)
-	                            : (debug ? (const void *)k_geom<VS, false, true, false> : (const void *)k_geom<VS, false, false, false>), false);
-	if(indexed && debug) launch_pdl(k_geom<VS, true, true, false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp);
-	else if(indexed) launch_pdl(k_geom<VS, true, false, false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp);
-	else if(debug) launch_pdl(k_geom<VS, false, true, false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp);
-	else launch_pdl(k_geom<VS, false, false, false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp);
+	const void *f;
+	if(vcache_vertices) { f = (const void *)k_front<VS, true, false, true>; launch_pdl(k_front<VS, true, false, true>, nblocks, MLV_GEOM_THREADS, fs, gp); }
+	else if(indexed && debug) { f = (const void *)k_front<VS, true, true, false>; launch_pdl(k_front<VS, true, true, false>, nblocks, MLV_GEOM_THREADS, fs, gp); }
+	else if(indexed) { f = (const void *)k_front<VS, true, false, false>; launch_pdl(k_front<VS, true, false, false>, nblocks, MLV_GEOM_THREADS, fs, gp); }
+	else if(debug) { f = (const void *)k_front<VS, false, true, false>; launch_pdl(k_front<VS, false, true, false>, nblocks, MLV_GEOM_THREADS, fs, gp); }
+	else { f = (const void *)k_front<VS, false, false, false>; launch_pdl(k_front<VS, false, false, false>, nblocks, MLV_GEOM_THREADS, fs, gp); }
+	note_geom_func(dev, f, false);
+	check_launch(dev, "k_front");
+	{ // clipping pass over the (device-side) queue; most draws queue few or no triangles. One group of MLV_CLIP_SPLIT lanes per
+		// queued triangle: the clipper is a long dependent chain per triangle, so the queue is spread over as many warps as it
+		// has entries (concentrating it on fewer CTAs was measured slower: 28 vs 20 us)
+		uint32_t cb = (gp.tri_count * MLV_CLIP_SPLIT + MLV_CLIP_THREADS - 1u) / MLV_CLIP_THREADS;
+		if(cb > dev->sm_count * 4u) cb = dev->sm_count * 4u;
+		prof_pre(dev, MLV_STAGE_CLIP);
+		if(indexed) { f = (const void *)k_front_clip<VS, true>; launch_pdl(k_front_clip<VS, true>, cb, MLV_CLIP_THREADS, fs, gp); }
+		else { f = (const void *)k_front_clip<VS, false>; launch_pdl(k_front_clip<VS, false>, cb, MLV_CLIP_THREADS, fs, gp); }
+		note_geom_func(dev, f, false);
+		check_launch(dev, "k_front_clip");
+	}
 }
+
 template <int VS>
-static void launch_geom_clip(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed) {
-	note_geom_func(dev, indexed ? (const void *)k_geom_clip<VS, true> : (const void *)k_geom_clip<VS, false>, false);
-	if(indexed) launch_pdl(k_geom_clip<VS, true>, nblocks, MLV_CLIP_THREADS, dev->stream, gp);
-	else launch_pdl(k_geom_clip<VS, false>, nblocks, MLV_CLIP_THREADS, dev->stream, gp);
+static void launch_back(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed, bool vcache) {
+	const bool debug = gp.keep_all;
+	if(nblocks > dev->sm_count * 4u) nblocks = dev->sm_count * 4u;
+	prof_pre(dev, MLV_STAGE_BACK);
+	const void *f;
+	g_pdl = dev->knob_no_pdl_back ? 0 : 1;
+	if(vcache) { f = (const void *)k_back<VS, true, false, true>; launch_pdl(k_back<VS, true, false, true>, nblocks, MLV_GEOM_THREADS, dev->stream, gp); }
+	else if(indexed && debug) { f = (const void *)k_back<VS, true, true, false>; launch_pdl(k_back<VS, true, true, false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp); }
+	else if(indexed) { f = (const void *)k_back<VS, true, false, false>; launch_pdl(k_back<VS, true, false, false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp); }
+	else if(debug) { f = (const void *)k_back<VS, false, true, false>; launch_pdl(k_back<VS, false, true, false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp); }
+	else { f = (const void *)k_back<VS, false, false, false>; launch_pdl(k_back<VS, false, false, false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp); }
+	note_geom_func(dev, f, false);
+	g_pdl = 1;
+}
+
+// Both streams of a draw are idle (nothing recorded: nothing is executing): called before an arena is replaced.
+static cudaError_t quiesce(mlv_device *dev) {
+	if(dev->recording) return cudaSuccess;
+	cudaError_t e = cudaStreamSynchronize(dev->stream);
+	for(uint32_t i = 0; i < dev->num_front_streams && e == cudaSuccess; ++i) e = cudaStreamSynchronize(dev->front_streams[i]);
+	return e;
 }
 
 static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t start_index = 0, int32_t base_vertex = 0) {
 	if(int rc = use_device(dev)) return rc;
-	g_graveyard = dev->recording ? dev->recording->graveyard : nullptr;
+	g_graveyard = (dev->recording || dev->lists_alive) ? dev->graveyard : nullptr;
 	if(dev->recording && dev->prof_on) return fail(MLV_ERR_STATE, "per-stage profiling brackets launches with events and cannot be recorded");
 	// the reference's asserts (main.c:666,670,1230) become argument errors
 	if(dev->topology != MLV_PRIMITIVE_TOPOLOGY_TRIANGLELIST) return fail(MLV_ERR_STATE, "primitive topology must be TRIANGLELIST (main.c:666)");
@@ -874,18 +952,6 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	if(int rc = flush_clears(dev)) return rc;
 	dev->last_index_count = count;
 	if(count == 0) return MLV_OK;
-	for(mlv_buffer *b : { dev->vb, indexed ? dev->ib : (mlv_buffer *)nullptr }) { // uploads still in flight on the copy stream
-		if(!b) continue;
-		if(dev->recording && std::find(dev->recording->buffers->begin(), dev->recording->buffers->end(), b) == dev->recording->buffers->end()) dev->recording->buffers->push_back(b);
-		if(!b->ready_pending) continue;
-		if(dev->recording) { // a capturing stream cannot wait for an event recorded outside the capture: the host waits instead
-			CUDA_TRY(cudaEventSynchronize(b->ready));
-		} else {
-			CUDA_TRY(cudaStreamWaitEvent(dev->stream, b->ready, 0));
-			CUDA_TRY(cudaStreamWaitEvent(dev->side_stream, b->ready, 0));
-		}
-		b->ready_pending = false;
-	}
 
 	const uint32_t T = count / 3u;
 	if(T >= (1u << 28)) return fail(MLV_ERR_INVALID_ARGUMENT, "draw too large: triangle keys are (input_triangle << 3 | fan_index) in 32 bits");
@@ -897,33 +963,111 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	const uint32_t need_slots = T + ovf_cap;
 	const uint32_t nblocks = (T + MLV_GEOM_THREADS - 1) / MLV_GEOM_THREADS;
 	const bool debug = (dev->desc.flags & MLV_DEVICE_DEBUG_CAPTURE) != 0;
-	if(need_slots > dev->tri_capacity || (debug && (need_slots > dev->dbg_tri_capacity || count > dev->dbg_vertex_capacity || !dev->dbg.infos))) {
-		CUDA_TRY(sync_unless_recording(dev, dev->stream));
-		if(need_slots > dev->tri_capacity) {
-			const uint32_t cap = need_slots + need_slots / 4;
+	// Stream of the front half. Per-stage profiling brackets every kernel with events on the main stream, so it keeps
+	// everything there.
+	const uint32_t ctx_index = (uint32_t)(dev->draw_seq % dev->num_ctx), fs_index = ctx_index % dev->num_front_streams;
+	cudaStream_t fs = dev->prof_on ? dev->stream : dev->front_streams[fs_index];
+	DrawCtx *ctx = &dev->ctxs[ctx_index];
+	dev->draw_seq++;
+
+	// ---- arenas shared by all draws (used by the back half / tile kernels, which run one draw at a time)
+	if(T > dev->tri_capacity || need_slots > dev->queue_capacity || (debug && (need_slots > dev->dbg_tri_capacity || count > dev->dbg_vertex_capacity || !dev->dbg.infos))) {
+		CUDA_TRY(quiesce(dev));
+		if(T > dev->tri_capacity) {
+			const uint32_t cap = T + T / 4;
 			CUDA_TRY(regrow(&dev->tri_cov, (size_t)cap * MLV_TRI_COV_U4));
 			CUDA_TRY(regrow(&dev->tri_shade, (size_t)cap * MLV_TRI_SHADE_U4));
-			CUDA_TRY(regrow(&dev->tri_bounds, (size_t)cap));
-			CUDA_TRY(regrow(&dev->clip_queue, (size_t)cap));
+			dev->tri_capacity = cap;
+		}
+		if(need_slots > dev->queue_capacity) {
+			const uint32_t cap = need_slots + need_slots / 4;
 			CUDA_TRY(regrow(&dev->big_queue, (size_t)cap));
 			CUDA_TRY(regrow(&dev->huge_queue, (size_t)cap));
-			dev->tri_capacity = cap;
+			dev->queue_capacity = cap;
 		}
 		if(debug) {
 			if(need_slots > dev->dbg_tri_capacity) {
-				CUDA_TRY(regrow(&dev->dbg.tris, (size_t)dev->tri_capacity));
-				CUDA_TRY(regrow(&dev->dbg.attrs, (size_t)dev->tri_capacity * 36));
-				CUDA_TRY(regrow(&dev->dbg.slot_key, (size_t)dev->tri_capacity));
-				dev->dbg_tri_capacity = dev->tri_capacity;
+				const uint32_t cap = need_slots + need_slots / 4;
+				CUDA_TRY(regrow(&dev->dbg.tris, (size_t)cap));
+				CUDA_TRY(regrow(&dev->dbg.attrs, (size_t)cap * 36));
+				CUDA_TRY(regrow(&dev->dbg.slot_key, (size_t)cap));
+				dev->dbg_tri_capacity = cap;
 			}
 			if(count > dev->dbg_vertex_capacity) {
 				CUDA_TRY(regrow(&dev->dbg.vs_out, (size_t)count * 12));
 				dev->dbg_vertex_capacity = count;
 			}
 			if(!dev->dbg.infos) CUDA_TRY(regrow(&dev->dbg.infos, (size_t)dev->pair_capacity));
+			if(!dev->pair_tmp) CUDA_TRY(regrow(&dev->pair_tmp, (size_t)dev->pair_capacity));
+		}
+	}
+	// ---- the draw context: what the front half hands to the back half
+	uint32_t vcache_vertices = 0;
+	const bool chunk_cull = dev->part.num_ranks > 1 && !debug && (dev->vs_id == MLV_VS_BASIC || dev->vs_id == MLV_VS_VERTEX_LIGHTING);
+	// Post-transform vertex cache: worth it when the index buffer references each vertex of the buffer about twice or
+	// more (the bound vertex buffer's size is the only vertex count a D3D11-style draw call has).
+	if(indexed && !debug && !chunk_cull) { // (with chunk culling a rank touches ~1/N of the vertices; transforming all of them would cost more)
+		const uint64_t vb_vertices = dev->vb->bytes / 32;
+		if(vb_vertices > 0 && vb_vertices <= 0x7fffffffull && (uint64_t)count >= 2 * vb_vertices) vcache_vertices = (uint32_t)vb_vertices;
+	}
+	if(need_slots > ctx->slot_capacity || T > ctx->queue_capacity || ovf_cap > ctx->ovf_capacity || vcache_vertices > ctx->vcache_capacity || (chunk_cull && nblocks > ctx->chunk_capacity)) {
+		// every context grows to the same size: draws rotate through the contexts, so each of them meets the largest draw sooner or later
+		CUDA_TRY(quiesce(dev));
+		for(uint32_t i = 0; i < dev->num_ctx; ++i) {
+			DrawCtx *c = &dev->ctxs[i];
+			if(need_slots > c->slot_capacity) {
+				const uint32_t cap = need_slots + need_slots / 4;
+				CUDA_TRY(regrow(&c->tri_bounds, (size_t)cap));
+				c->slot_capacity = cap;
+			}
+			if(T > c->queue_capacity) {
+				const uint32_t cap = T + T / 4;
+				CUDA_TRY(regrow(&c->clip_queue, (size_t)cap));
+				c->queue_capacity = cap;
+			}
+			if(ovf_cap > c->ovf_capacity) {
+				const uint32_t cap = ovf_cap + ovf_cap / 4;
+				CUDA_TRY(regrow(&c->ovf_cov, (size_t)cap * MLV_TRI_COV_U4));
+				CUDA_TRY(regrow(&c->ovf_shade, (size_t)cap * MLV_TRI_SHADE_U4));
+				c->ovf_capacity = cap;
+			}
+			if(vcache_vertices > c->vcache_capacity) {
+				CUDA_TRY(regrow(&c->vcache, (size_t)vcache_vertices * 2));
+				c->vcache_capacity = vcache_vertices;
+			}
+			if(chunk_cull && nblocks > c->chunk_capacity) {
+				CUDA_TRY(regrow(&c->chunk_live, (size_t)nblocks));
+				c->chunk_capacity = nblocks;
+			}
 		}
 	}
 	dev->last_direct_slots = T;
+	dev->last_ctx = ctx;
+
+	// ---- stream order. The front half reads the bound buffers and writes its draw context; it waits for (1) uploads of
+	// those buffers still in flight, (2) the draw that used this context last (its k_tile re-arms the context), and -- the
+	// first time after anything that is not ordered by (2) -- everything issued on the main stream so far.
+	for(mlv_buffer *b : { dev->vb, indexed ? dev->ib : (mlv_buffer *)nullptr }) { // uploads still in flight on the copy stream
+		if(!b) continue;
+		if(dev->recording && std::find(dev->recording->buffers->begin(), dev->recording->buffers->end(), b) == dev->recording->buffers->end()) dev->recording->buffers->push_back(b);
+		if(!b->ready_pending) continue;
+		if(dev->recording) { // a capturing stream cannot wait for an event recorded outside the capture: the host waits instead
+			CUDA_TRY(cudaEventSynchronize(b->ready));
+		} else {
+			CUDA_TRY(cudaStreamWaitEvent(dev->stream, b->ready, 0));
+			for(uint32_t i = 0; i < dev->num_front_streams; ++i) CUDA_TRY(cudaStreamWaitEvent(dev->front_streams[i], b->ready, 0));
+		}
+		b->ready_pending = false;
+	}
+	if(!dev->prof_on) {
+		if(dev->front_needs_sync[fs_index]) { // fork from the point of the main stream reset_front_order marked
+			CUDA_TRY(cudaStreamWaitEvent(fs, dev->ev_main_sync, 0));
+			dev->front_needs_sync[fs_index] = false;
+			dev->front_touched[fs_index] = true;
+		} else if(ctx->free_recorded) {
+			CUDA_TRY(cudaStreamWaitEvent(fs, ctx->free_ev, 0));
+		}
+	}
 
 	GeomParams gp;
 	memset(&gp, 0, sizeof(gp));
@@ -957,8 +1101,11 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	gp.part = dev->part;
 	gp.tri_cov = dev->tri_cov;
 	gp.tri_shade = dev->tri_shade;
-	gp.tri_bounds = dev->tri_bounds;
-	gp.clip_queue = dev->clip_queue;
+	gp.tri_bounds = ctx->tri_bounds;
+	gp.ovf_cov = ctx->ovf_cov;
+	gp.ovf_shade = ctx->ovf_shade;
+	gp.dctr = ctx->dctr;
+	gp.clip_queue = ctx->clip_queue;
 	gp.big_queue = dev->big_queue;
 	gp.huge_queue = dev->huge_queue;
 	gp.bin_count = dev->bin_count;
@@ -966,26 +1113,36 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	gp.keep_all = debug;
 	if(debug) gp.dbg = dev->dbg;
 	gp.ctr = dev->ctr;
-	gp.stat_stripes = dev->stat_stripes;
+	gp.stat_stripes = ctx->stat_stripes;
 	gp.index_count = count;
 	gp.draw_ordinal = dev->recording ? dev->recording->draws : 0u;
+	if(vcache_vertices) gp.vcache = ctx->vcache;
 
 	// Sort-first chunk culling (multi-GPU): object-space chunk bounds cached with the buffer that defines the triangle list.
-	if(dev->part.num_ranks > 1 && !debug && (dev->vs_id == MLV_VS_BASIC || dev->vs_id == MLV_VS_VERTEX_LIGHTING)) {
+	if(chunk_cull) {
 		mlv_buffer *owner = indexed ? dev->ib : dev->vb;
 		const bool valid = owner->chunk_bounds && owner->chunk_count == nblocks && owner->chunk_indexed == (indexed ? 1 : 0) && owner->chunk_self_version == owner->version &&
 		                   owner->chunk_vb_uid == dev->vb->uid && owner->chunk_vb_version == dev->vb->version && owner->chunk_start_index == start_index &&
 		                   owner->chunk_base_vertex == base_vertex && owner->chunk_index16 == gp.ix.index16;
 		if(!valid) {
 			if(nblocks > owner->chunk_capacity) {
-				CUDA_TRY(sync_unless_recording(dev, dev->stream));
+				CUDA_TRY(quiesce(dev));
 				CUDA_TRY(regrow(&owner->chunk_bounds, (size_t)nblocks * 2));
 				owner->chunk_capacity = nblocks;
 			}
 			prof_pre(dev, MLV_STAGE_GEOMETRY);
-			if(indexed) launch_pdl(k_chunk_bounds<true>, nblocks, MLV_GEOM_THREADS, dev->stream, gp.ix, gp.vb, T, owner->chunk_bounds);
-			else launch_pdl(k_chunk_bounds<false>, nblocks, MLV_GEOM_THREADS, dev->stream, gp.ix, gp.vb, T, owner->chunk_bounds);
+			if(indexed) launch_pdl(k_chunk_bounds<true>, nblocks, MLV_GEOM_THREADS, fs, gp.ix, gp.vb, T, owner->chunk_bounds);
+			else launch_pdl(k_chunk_bounds<false>, nblocks, MLV_GEOM_THREADS, fs, gp.ix, gp.vb, T, owner->chunk_bounds);
 			if(int rc = check_launch(dev, "k_chunk_bounds")) return rc;
+			// the bounds are cached with the buffer: later draws (on other front streams) use them too
+			if(!dev->prof_on) {
+				CUDA_TRY(cudaEventRecord(ctx->front_done, fs));
+				for(uint32_t i = 0; i < dev->num_front_streams; ++i) {
+					if(i == fs_index) continue;
+					CUDA_TRY(cudaStreamWaitEvent(dev->front_streams[i], ctx->front_done, 0));
+					if(dev->recording) dev->front_touched[i] = true;
+				}
+			}
 			owner->chunk_count = nblocks;
 			owner->chunk_indexed = indexed ? 1 : 0;
 			owner->chunk_self_version = owner->version;
@@ -995,56 +1152,37 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 			owner->chunk_base_vertex = base_vertex;
 			owner->chunk_index16 = gp.ix.index16;
 		}
-		if(nblocks > dev->chunk_live_capacity) {
-			CUDA_TRY(sync_unless_recording(dev, dev->stream));
-			CUDA_TRY(regrow(&dev->chunk_live, (size_t)nblocks));
-			dev->chunk_live_capacity = nblocks;
-		}
 		gp.chunk_bounds = owner->chunk_bounds;
-		gp.chunk_live = dev->chunk_live;
+		gp.chunk_live = ctx->chunk_live;
 	}
-	// Post-transform vertex cache: worth it when the index buffer references each vertex of the buffer about twice or
-	// more (the bound vertex buffer's size is the only vertex count a D3D11-style draw call has).
-	uint32_t vcache_vertices = 0;
-	if(indexed && !debug && !gp.chunk_bounds) { // (with chunk culling a rank touches ~1/N of the vertices; transforming all of them would cost more)
-		const uint64_t vb_vertices = dev->vb->bytes / 32;
-		if(vb_vertices > 0 && vb_vertices <= 0x7fffffffull && (uint64_t)count >= 2 * vb_vertices) {
-			vcache_vertices = (uint32_t)vb_vertices;
-			if(vcache_vertices > dev->vcache_capacity) {
-				CUDA_TRY(sync_unless_recording(dev, dev->stream));
-				CUDA_TRY(sync_unless_recording(dev, dev->side_stream));
-				CUDA_TRY(regrow(&dev->vcache[0], (size_t)vcache_vertices * 2));
-				CUDA_TRY(regrow(&dev->vcache[1], (size_t)vcache_vertices * 2));
-				dev->vcache_capacity = vcache_vertices;
-			}
-			gp.vcache = dev->vcache[dev->vcache_sel];
-		}
-	}
+
+	// ---- front half (its own stream): k_vertex, k_front, k_front_clip
 	switch(dev->vs_id) {
-		case MLV_VS_PASSTHROUGH: launch_geom<0>(dev, gp, nblocks, indexed, vcache_vertices); break;
-		case MLV_VS_BASIC: launch_geom<1>(dev, gp, nblocks, indexed, vcache_vertices); break;
-		case MLV_VS_VERTEX_LIGHTING: launch_geom<2>(dev, gp, nblocks, indexed, vcache_vertices); break;
-		default: launch_geom<3>(dev, gp, nblocks, indexed, vcache_vertices); break;
+		case MLV_VS_PASSTHROUGH: launch_front<0>(dev, fs, gp, nblocks, indexed, vcache_vertices); break;
+		case MLV_VS_BASIC: launch_front<1>(dev, fs, gp, nblocks, indexed, vcache_vertices); break;
+		case MLV_VS_VERTEX_LIGHTING: launch_front<2>(dev, fs, gp, nblocks, indexed, vcache_vertices); break;
+		default: launch_front<3>(dev, fs, gp, nblocks, indexed, vcache_vertices); break;
 	}
-	if(int rc = check_launch(dev, "k_geom")) return rc;
-	{ // clipping pass over the (device-side) queue; a modest persistent grid, most draws queue few or no triangles
-		// one thread per queued triangle: the clipper is a long dependent chain per triangle, so the queue is spread over
-		// as many warps as it has entries (concentrating it on fewer CTAs was measured slower: 28 vs 20 us)
-		uint32_t cb = (T * MLV_CLIP_SPLIT + MLV_CLIP_THREADS - 1u) / MLV_CLIP_THREADS;
-		if(cb > dev->sm_count * 4u) cb = dev->sm_count * 4u;
-		prof_pre(dev, MLV_STAGE_CLIP);
-		switch(dev->vs_id) {
-			case MLV_VS_PASSTHROUGH: launch_geom_clip<0>(dev, gp, cb, indexed); break;
-			case MLV_VS_BASIC: launch_geom_clip<1>(dev, gp, cb, indexed); break;
-			case MLV_VS_VERTEX_LIGHTING: launch_geom_clip<2>(dev, gp, cb, indexed); break;
-			default: launch_geom_clip<3>(dev, gp, cb, indexed); break;
-		}
-		if(int rc = check_launch(dev, "k_geom_clip")) return rc;
+	if(int rc = check_launch_only(dev, "front half")) return rc;
+	if(!dev->prof_on) {
+		CUDA_TRY(cudaEventRecord(ctx->front_done, fs));
+		CUDA_TRY(cudaStreamWaitEvent(dev->stream, ctx->front_done, 0));
 	}
+
+	// ---- back half (main stream: ordered after the previous draw's k_tile through the tile minima)
+	const uint32_t back_blocks = (need_slots + MLV_GEOM_THREADS - 1) / MLV_GEOM_THREADS;
+	switch(dev->vs_id) {
+		case MLV_VS_PASSTHROUGH: launch_back<0>(dev, gp, back_blocks, indexed, vcache_vertices != 0); break;
+		case MLV_VS_BASIC: launch_back<1>(dev, gp, back_blocks, indexed, vcache_vertices != 0); break;
+		case MLV_VS_VERTEX_LIGHTING: launch_back<2>(dev, gp, back_blocks, indexed, vcache_vertices != 0); break;
+		default: launch_back<3>(dev, gp, back_blocks, indexed, vcache_vertices != 0); break;
+	}
+	if(int rc = check_launch(dev, "k_back")) return rc;
 
 	BinParams bp;
 	memset(&bp, 0, sizeof(bp));
-	bp.tri_bounds = dev->tri_bounds;
+	bp.tri_bounds = ctx->tri_bounds;
+	bp.dctr = ctx->dctr;
 	bp.big_queue = dev->big_queue;
 	bp.huge_queue = dev->huge_queue;
 	bp.chunk_live = gp.chunk_live;
@@ -1053,7 +1191,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	bp.bin_offset = dev->bin_offset;
 	bp.pair_ids = dev->pair_ids;
 	bp.ctr = dev->ctr;
-	bp.stat_stripes = dev->stat_stripes;
+	bp.stat_stripes = ctx->stat_stripes;
 	bp.direct_slots = T;
 	bp.ovf_capacity = ovf_cap;
 	bp.num_bins = dev->num_bins;
@@ -1073,6 +1211,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	sp.bin_offset = dev->bin_offset;
 	sp.cbins = dev->cbins;
 	sp.ctr = dev->ctr;
+	sp.dctr = ctx->dctr;
 	sp.state_sum = dev->scan_state;
 	sp.state_nz = dev->scan_state + dev->scan_blocks;
 	sp.tile_min = dev->tile_min;
@@ -1098,16 +1237,21 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	tp.pair_tmp = dev->pair_tmp;
 	tp.tri_cov = dev->tri_cov;
 	tp.tri_shade = dev->tri_shade;
+	tp.ovf_cov = ctx->ovf_cov;
+	tp.ovf_shade = ctx->ovf_shade;
+	tp.tri_bounds = ctx->tri_bounds;
+	tp.dctr = ctx->dctr;
 	tp.fb = dev->fb;
 	tp.tile_min = dev->tile_min;
 	tp.ctr = dev->ctr;
-	tp.stat_stripes = dev->stat_stripes;
+	tp.stat_stripes = ctx->stat_stripes;
 	tp.ps_tex = tex_desc(dev->ps_srv[0]);
 	tp.rsqrt_lut = dev->rsqrt_lut;
 	if(debug) tp.dbg = dev->dbg;
 	tp.scan_state = dev->scan_state;
 	tp.scan_words = dev->scan_blocks * 2u;
 	tp.direct_slots = T;
+	tp.index_count = count;
 	tp.key_bits = 3u;
 	while(tp.key_bits < 32u && (T >> (tp.key_bits - 3u)) != 0u) tp.key_bits++;
 	tp.wt = dev->wt;
@@ -1116,13 +1260,19 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	if(tile_blocks > dev->sm_count * 8u) tile_blocks = dev->sm_count * 8u;
 	const uint32_t pcap = (uint32_t)dev->pair_capacity;
 	prof_pre(dev, MLV_STAGE_TILE);
+	g_pdl = dev->knob_no_pdl_tile ? 0 : 1;
 	switch(dev->ps_id) {
 		case MLV_PS_PASSTHROUGH: launch_pdl(k_tile<0>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap, ovf_cap); break;
 		case MLV_PS_BASIC: launch_pdl(k_tile<1>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap, ovf_cap); break;
 		case MLV_PS_BASIC_TRILINEAR: launch_pdl(k_tile<MLV_PS_ID_BASIC_TRILINEAR>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap, ovf_cap); break;
 		default: launch_pdl(k_tile<2>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap, ovf_cap); break;
 	}
+	g_pdl = 1;
 	if(int rc = check_launch(dev, "k_tile")) return rc;
+	if(!dev->prof_on) { // the context is free again once this draw's k_tile has re-armed it
+		CUDA_TRY(cudaEventRecord(ctx->free_ev, dev->stream));
+		ctx->free_recorded = true;
+	}
 	if(dev->recording) {
 		dev->recording->draws++;
 		return MLV_OK; // (mlv_execute_command_list records ev_last_draw after the whole list)
@@ -1151,15 +1301,13 @@ static void free_command_list(mlv_command_list *list) {
 	if(!list) return;
 	if(list->exec) cudaGraphExecDestroy(list->exec);
 	if(list->graph) cudaGraphDestroy(list->graph);
-	if(list->graveyard)
-		for(void *p : *list->graveyard) cudaFree(p);
+	if(list->owner && list->owner->lists_alive) list->owner->lists_alive--;
 	if(list->geom_nodes)
 		for(GeomNode *n : *list->geom_nodes) delete n;
 	delete list->buffers;
 	delete list->geom_funcs;
 	delete list->vertex_funcs;
 	delete list->geom_nodes;
-	delete list->graveyard;
 	delete list;
 }
 
@@ -1176,7 +1324,7 @@ int mlv_begin_command_list(mlv_device *dev) {
 	list->geom_funcs = new std::vector<const void *>();
 	list->vertex_funcs = new std::vector<const void *>();
 	list->geom_nodes = new std::vector<GeomNode *>();
-	list->graveyard = new std::vector<void *>();
+	dev->lists_alive++; // from now on a replaced arena is kept until the device is destroyed: recorded nodes may address it
 	list->fb_sel = dev->fb_sel;
 	cudaError_t e = cudaStreamBeginCapture(dev->stream, cudaStreamCaptureModeRelaxed);
 	if(e != cudaSuccess) {
@@ -1185,8 +1333,7 @@ int mlv_begin_command_list(mlv_device *dev) {
 	}
 	dev->recording = list;
 	// events recorded outside the capture cannot be waited for inside it: the side stream forks from the main stream again
-	dev->side_needs_sync = true;
-	dev->cache_free_recorded[0] = dev->cache_free_recorded[1] = false;
+	reset_front_order(dev);
 	return MLV_OK;
 }
 
@@ -1196,14 +1343,17 @@ int mlv_finish_command_list(mlv_device *dev, mlv_command_list **out_list) {
 	if(!out_list) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
 	*out_list = nullptr;
 	int rc = flush_clears(dev); // a clear recorded after the last draw
+	for(uint32_t i = 0; i < dev->num_front_streams; ++i) { // every stream that joined the capture re-joins the main stream
+		if(!dev->front_touched[i]) continue;
+		cudaEventRecord(dev->ev_front_join[i], dev->front_streams[i]);
+		cudaStreamWaitEvent(dev->stream, dev->ev_front_join[i], 0);
+	}
 	mlv_command_list *list = dev->recording;
 	const uint64_t launches_before = list->launches; // (set by begin: dev->launches at that time)
 	(void)launches_before;
 	cudaError_t e = cudaStreamEndCapture(dev->stream, &list->graph);
 	dev->recording = nullptr;
-	g_graveyard = nullptr;
-	dev->side_needs_sync = true; // the captured events mean nothing outside the graph
-	dev->cache_free_recorded[0] = dev->cache_free_recorded[1] = false;
+	reset_front_order(dev); // the captured events mean nothing outside the graph
 	if(rc != MLV_OK || e != cudaSuccess || !list->graph) {
 		free_command_list(list);
 		if(rc != MLV_OK) return rc;
@@ -1273,8 +1423,7 @@ int mlv_execute_command_list(mlv_device *dev, mlv_command_list *list) {
 	if(list->has_resolve) dev->present_color = dev->resolved_color;
 	CUDA_TRY(cudaEventRecord(dev->ev_last_draw, dev->stream));
 	dev->last_draw_recorded = true;
-	dev->side_needs_sync = true; // the graph used the vertex cache on its own branch; the side stream re-joins the main stream first
-	dev->cache_free_recorded[0] = dev->cache_free_recorded[1] = false;
+	reset_front_order(dev); // the graph ran the front halves on branches of its own; the front stream re-joins the main stream first
 	return MLV_OK;
 }
 
@@ -1658,6 +1807,7 @@ int mlv_debug_read_vs_out(mlv_device *dev, float *out12_per_vertex, uint32_t *ou
 struct DebugMap {
 	std::vector<uint32_t> keys;  // ascending
 	std::vector<uint32_t> slots; // slot of keys[i]
+	std::vector<uint32_t> slot_rank; // reference id of a slot
 	uint32_t rank(uint32_t key) const { return (uint32_t)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin()); }
 };
 
@@ -1671,9 +1821,11 @@ static int build_debug_map(mlv_device *dev, const Counters &c, DebugMap &m) {
 	std::sort(ks.begin(), ks.end());
 	m.keys.resize(ks.size());
 	m.slots.resize(ks.size());
+	m.slot_rank.assign(n_slots, 0xffffffffu);
 	for(size_t i = 0; i < ks.size(); ++i) {
 		m.keys[i] = ks[i].first;
 		m.slots[i] = ks[i].second;
+		m.slot_rank[ks[i].second] = (uint32_t)i;
 	}
 	return MLV_OK;
 }
@@ -1715,8 +1867,8 @@ int mlv_debug_read_bins(mlv_device *dev, uint32_t *triangle_ids, uint32_t *out_p
 	if(triangle_ids && pairs) {
 		DebugMap m;
 		if(int rc = build_debug_map(dev, c, m)) return rc;
-		CUDA_TRY(cudaMemcpy(triangle_ids, dev->pair_ids, (size_t)pairs * 4, cudaMemcpyDeviceToHost));
-		for(uint32_t i = 0; i < pairs; ++i) triangle_ids[i] = m.rank(triangle_ids[i]);
+		CUDA_TRY(cudaMemcpy(triangle_ids, dev->pair_ids, (size_t)pairs * 4, cudaMemcpyDeviceToHost)); // the lists hold slots
+		for(uint32_t i = 0; i < pairs; ++i) triangle_ids[i] = triangle_ids[i] < m.slot_rank.size() ? m.slot_rank[triangle_ids[i]] : 0xffffffffu;
 	}
 	if(bins && nb) CUDA_TRY(cudaMemcpy(bins, dev->cbins, (size_t)nb * sizeof(mlv_ref_compacted_bin), cudaMemcpyDeviceToHost));
 	return MLV_OK;
@@ -1765,7 +1917,16 @@ int mlv_read_bin_lists(mlv_device *dev, uint32_t *keys, uint32_t *out_pair_count
 	const uint32_t pairs = skipped ? 0u : c.pair_total, nb = skipped ? 0u : c.n_cbins;
 	if(out_pair_count) *out_pair_count = pairs;
 	if(out_bin_count) *out_bin_count = nb;
-	if(keys && pairs) CUDA_TRY(cudaMemcpy(keys, dev->pair_ids, (size_t)pairs * 4, cudaMemcpyDeviceToHost));
+	if(keys && pairs) {
+		CUDA_TRY(cudaMemcpy(keys, dev->pair_ids, (size_t)pairs * 4, cudaMemcpyDeviceToHost)); // slots: direct slot t has key t << 3,
+		const uint32_t T = dev->last_direct_slots, n_ovf = c.last_ovf_count;                      // an overflow slot's key is word 3 of its bounds entry
+		std::vector<uint4> ovf(n_ovf);
+		if(n_ovf && dev->last_ctx) CUDA_TRY(cudaMemcpy(ovf.data(), dev->last_ctx->tri_bounds + T, (size_t)n_ovf * sizeof(uint4), cudaMemcpyDeviceToHost));
+		for(uint32_t i = 0; i < pairs; ++i) {
+			const uint32_t slot = keys[i];
+			keys[i] = slot < T ? (slot << 3) : (slot - T < n_ovf ? ovf[slot - T].w : 0xffffffffu);
+		}
+	}
 	if(bins && nb) CUDA_TRY(cudaMemcpy(bins, dev->cbins, (size_t)nb * sizeof(mlv_ref_compacted_bin), cudaMemcpyDeviceToHost));
 	return check_flags(dev, c);
 }

@@ -18,17 +18,15 @@ namespace mlv {
 // Triangle identity. The reference numbers assembled triangles in single-thread output order (input order,
 // fan order inside a clipped triangle). Here a triangle is named by the order-preserving
 // KEY = (input_triangle << 3) | fan_index, so no ordered compaction (scan) is needed: ascending key ==
-// ascending reference id. Records live in SLOTS: an unclipped input triangle t uses slot t; the fan
-// triangles of a clipped input triangle use consecutive overflow slots T + base + fan_index, found through a
-// redirect stored in slot t.
+// ascending reference id. Records live in SLOTS: an unclipped input triangle t uses direct slot t (key = t << 3); the
+// fan triangles of a clipped input triangle use consecutive overflow slots T + base + fan_index, whose key is word 3 of
+// their bounds entry. The per-tile lists hold SLOTS; keys are only needed to break depth ties (main.c:1166).
 //   TriCov   48 B  { a0,b0,c0,a1 | b1,c1,a2,b2 | c2, max_depth, minx|flags_miny<<16, maxx|maxy<<16 }  coverage + Hi-Z
-//                  redirect:  word 10 == MLV_REDIRECT, word 8 = overflow base
 //   TriShade 96 B  { ooa,z0,z1,z2 | rw0,rw1,rw2,r2x_v0 | r1_v0 | r1_v1 | r1_v2 | r2x_v1,r2x_v2,0,0 }  depth + attributes
 //   bounds   16 B  { minx | (miny|nowrap<<15)<<16, maxx | maxy<<16, max_depth, key } int16 pixel bounds (main.c:888-898);
 //                  minx == 0x7fff: bins nothing (culled, redirected, not on this rank, or hidden by Hi-Z in every tile)
 #define MLV_TRI_COV_U4 3
 #define MLV_TRI_SHADE_U4 6
-#define MLV_REDIRECT 0x7ffe7ffeu
 #define MLV_BOUNDS_EMPTY 0x00007fffu
 #define MLV_NOWRAP_BIT 0x80000000u /* bit 15 of miny inside word 10 */
 
@@ -39,15 +37,22 @@ namespace mlv {
 
 enum { MLV_FLAG_TRI_OVERFLOW = 1u, MLV_FLAG_PAIR_OVERFLOW = 2u, MLV_FLAG_COMPOSITE_TIMEOUT = 4u };
 
+// Per-draw counters the FRONT half of a draw hands to its BACK half (one set per draw context, reset by the draw's k_tile).
+struct DrawCounters {
+	uint32_t clip_count; // input triangles queued for k_front_clip
+	uint32_t ovf_count;  // overflow slots taken by the fan triangles of clipped input triangles (may exceed the capacity: the draw is skipped)
+	uint32_t pad[2];
+};
+
 struct Counters {
-	uint32_t ovf_count;   // overflow slots taken by clipped triangles in the current draw (reset by k_tile)
+	uint32_t reserved0;
 	uint32_t pair_total;  // (triangle,tile) pairs of the current draw
 	uint32_t n_cbins;     // non-empty bins of the current draw (0 if the pair arena overflowed)
 	uint32_t error_flags; // sticky MLV_FLAG_*
 	uint32_t ticket;      // block ticket of the current draw's look-back scan (reset by k_tile)
 	uint32_t draw_tris;   // assembled triangles of the current draw
 	uint32_t last_ovf_count; // ovf_count of the last finished draw (debug read-back)
-	uint32_t clip_count;  // input triangles queued for k_geom_clip in the current draw (reset by k_tile)
+	uint32_t reserved1;
 	uint32_t big_count;   // triangles queued for k_bin_big in the current draw (reset by k_tile)
 	uint32_t draw_pairs_all;   // (triangle,tile) pairs of the current draw including Hi-Z-rejected ones (Stats)
 	uint32_t draw_active_bins; // non-empty bins of the current draw in the reference's sense (Stats)
@@ -62,6 +67,19 @@ struct Counters {
 struct Partition { // sort-first ownership
 	int num_ranks, rank, stripe_h;
 	__host__ __device__ __forceinline__ bool owns_row(int ty) const { return num_ranks <= 1 || ((ty / stripe_h) % num_ranks) == rank; }
+	// number of tile rows in [0, x) this rank owns: full periods of num_ranks stripes + the part of the last period inside this rank's stripe
+	__host__ __device__ __forceinline__ int owned_below(int x) const {
+		const int period = num_ranks * stripe_h, q = x / period, rem = x % period;
+		int in = rem - rank * stripe_h;
+		in = in < 0 ? 0 : (in > stripe_h ? stripe_h : in);
+		return q * stripe_h + in;
+	}
+	// number of tile rows in [ty0, ty1] this rank owns
+	__host__ __device__ __forceinline__ int owned_rows(int ty0, int ty1) const {
+		if(ty1 < ty0) return 0;
+		if(num_ranks <= 1) return ty1 - ty0 + 1;
+		return owned_below(ty1 + 1) - owned_below(ty0);
+	}
 };
 
 // Peer-memory compositing (fused form): every rank keeps two row-major images and one arrival word
@@ -109,11 +127,15 @@ struct GeomParams {
 	int wt, ht;     // WIDTH_IN_TILES / HEIGHT_IN_TILES
 	float clip_k;   // component of the host-normalised clip-plane normals (main.c:652-657)
 	Partition part;
-	uint4 *tri_cov;
+	uint4 *tri_cov;   // records of the direct slots (shared by all draws: written by k_back, read by the same draw's k_tile)
 	uint4 *tri_shade;
-	uint4 *tri_bounds;
-	const float4 *chunk_bounds; // sort-first chunk culling: 2 x float4 per k_geom CTA, or null
-	uint8_t *chunk_live;        // written by k_geom's cull test: 1 = this rank processed the chunk
+	// ---- the draw context: what the front half of THIS draw produces for its back half
+	uint4 *tri_bounds;          // 16 B per slot (direct + overflow)
+	uint4 *ovf_cov;             // records of the overflow slots (fan triangles of clipped input triangles)
+	uint4 *ovf_shade;
+	DrawCounters *dctr;
+	const float4 *chunk_bounds; // sort-first chunk culling: 2 x float4 per 256-triangle chunk, or null
+	uint8_t *chunk_live;        // written by k_front's cull test: 1 = this rank processed the chunk
 	float4 *vcache; // 2 x float4 per unique vertex: clip-space position, {snapped x, snapped y, screen z, clip_code bits}
 	uint32_t *clip_queue;
 	uint32_t *big_queue;
@@ -130,6 +152,7 @@ struct GeomParams {
 
 struct BinParams {
 	const uint4 *tri_bounds;
+	const DrawCounters *dctr;
 	const uint32_t *big_queue;
 	const uint32_t *huge_queue;
 	const uint8_t *chunk_live;
@@ -152,6 +175,7 @@ struct ScanParams {
 	uint32_t *bin_offset;
 	mlv_ref_compacted_bin *cbins;
 	Counters *ctr;
+	const DrawCounters *dctr;
 	unsigned long long *state_sum, *state_nz;
 	const float *tile_min;
 	uint32_t bin_begin, bin_end; // this rank's bins (the whole render target unless it owns one contiguous band)
@@ -166,6 +190,10 @@ struct TileParams {
 	uint32_t *pair_tmp;
 	const uint4 *tri_cov;
 	const uint4 *tri_shade;
+	const uint4 *ovf_cov;    // records of the slots >= direct_slots
+	const uint4 *ovf_shade;
+	const uint4 *tri_bounds; // word 3 of an overflow slot's entry is its key
+	DrawCounters *dctr;      // re-armed at the end of the draw
 	uint4 *fb;
 	float *tile_min;
 	Counters *ctr;
@@ -176,6 +204,7 @@ struct TileParams {
 	unsigned long long *scan_state; // look-back words of k_bin_scan (cleared when the epoch wraps)
 	uint32_t scan_words;
 	uint32_t direct_slots; // T
+	uint32_t index_count;  // Stats (main.c:1228-1232)
 	uint32_t key_bits;
 	int wt;
 	bool sort_lists; // debug capture: restore ascending-key order inside every bin list

@@ -1,18 +1,25 @@
-import csv,sys
-rows=list(csv.reader(open(sys.argv[1])))
-for i,r in enumerate(rows):
-    if 'Kernel Name' in r: h=r; start=i; break
-ki=h.index('Kernel Name'); mi=h.index('Metric Name'); vi=h.index('Metric Value'); idi=h.index('ID')
+#!/usr/bin/env python3
+"""Per-launch table of an ncu --csv launch list: kernel, time, DRAM bytes, warp instructions.
+Usage: python tools/launches.py <launches.csv> [first_launch] [count]"""
+import csv, sys
 from collections import OrderedDict
-d=OrderedDict()
-for r in rows[start+1:]:
-    if len(r)<=vi: continue
-    d.setdefault((r[idi],r[ki].split('(')[0][-28:]),{})[r[mi]]=r[vi]
-agg={}
-for (i,k),m in d.items():
-    t=float(m.get('gpu__time_duration.sum',0)); rd=float(m.get('dram__bytes_read.sum',0) or 0); wr=float(m.get('dram__bytes_write.sum',0) or 0)
-    a=agg.setdefault(k,[0,0,0,0,[]]); a[0]+=1; a[1]+=t; a[2]+=rd; a[3]+=wr; a[4].append(round(t/1000,1))
-tot=sum(a[1] for a in agg.values())
-print('total us',tot/1000)
-for k,a in sorted(agg.items(), key=lambda x:-x[1][1]):
-    print('%-30s n=%3d  sum %8.1f us (%4.1f%%)  rd %7.1f MB wr %7.1f MB  per-launch %s'%(k,a[0],a[1]/1000,100*a[1]/tot,a[2]/1e6,a[3]/1e6,a[4][:9]))
+lines = open(sys.argv[1]).read().splitlines()
+start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
+rows = list(csv.reader(lines[start:]))
+h = rows[0]
+ki, mi, vi, idi = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("ID")
+per = OrderedDict()
+for r in rows[1:]:
+    if len(r) > vi:
+        per.setdefault((int(r[idi]), r[ki].split("(")[0].replace("void ", "").replace("mlv::", "")), {})[r[mi]] = float(r[vi].replace(",", "") or 0)
+first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+count = int(sys.argv[3]) if len(sys.argv) > 3 else 10**9
+tot = 0.0
+for (i, k), m in per.items():
+    if i < first or i >= first + count:
+        continue
+    t = m.get("gpu__time_duration.sum", 0) / 1e3
+    tot += t
+    print("%4d %-44s %8.1f us  rd %7.2f MB wr %7.2f MB  inst %9.0f k  regs %3d grid %6d" % (i, k[:44], t, m.get("dram__bytes_read.sum", 0) / 1e6, m.get("dram__bytes_write.sum", 0) / 1e6,
+          m.get("smsp__inst_executed.sum", 0) / 1e3, m.get("launch__registers_per_thread", 0), m.get("launch__grid_size", 0)))
+print("total %.1f us" % tot)
