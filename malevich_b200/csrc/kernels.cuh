@@ -6,9 +6,9 @@
 //                (triangles are named by order-preserving keys instead of compacted ids, see mlv_internal.cuh);
 //                runs ahead of the draw-to-draw chain on a stream of its own
 //   k_back<VS>   Hi-Z + binner pass 1 per triangle, setup records for the survivors
-//   k_bin_big / k_bin_fill  binner passes 1 and 2 (pass 1 of small triangles is fused into k_back) (main.c:924-962)
 //   k_bin_scan   binner exclusive scan + compaction of non-empty bins     (main.c:937-974), multi-CTA
 //                single pass with decoupled look-back
+//   k_fill       binner pass 2                                            (main.c:950-962)
 //   k_tile<PS>   rasterizer + Hi-Z + early-Z + pixel shader + output merger (main.c:983-1189)
 //                one warp per non-empty bin: lanes over triangles for coverage (64-bit masks), a 32x32 bit
 //                transpose turns them into per-pixel cover sets, lanes over pixels for depth, pixel shader
@@ -261,18 +261,38 @@ __device__ __forceinline__ bool hiz_rejects(float max_depth, const float *__rest
 	return !keep_all && (max_depth < __ldg(tile_min + bin));
 }
 
-// Pass 1 of the binner (main.c:924-936) for one triangle with a small tile rectangle, fused into geometry.
-// Returns: pairs = (triangle, tile) pairs on this rank, live = at least one pair survives Hi-Z,
-// big = more than 8 tiles, left to k_bin_big (cooperative expansion).
+// Pass 1 of the binner (main.c:924-936) for one triangle, fused into the back half of geometry.
+//   live  = at least one pair survives Hi-Z (big rectangles: decided by the warp-cooperative expansion; huge ones: owns a tile)
+//   first = bins this thread touched FIRST in this draw (Stats: active_bin_count, main.c:1245)
+//   wake  = a bin without surviving pairs still needs its k_tail visit (write_tile refreshes the tile minimum of every
+//           non-empty bin, main.c:589-603; only a bin whose minimum still carries the clear tag would change)
 struct BinTally {
-	uint32_t pairs;
-	bool live, big, huge;
+	bool live, big, huge, wake;
+	uint32_t survivors;
 };
-// Rectangles of at most N tiles: walk them with fully unrolled, predicated steps so that the tile-minimum and counter
+
+// One (triangle, tile) pair. A bin is "touched in this draw" when bin_touch[bin] holds the draw's epoch -- raised by
+// whoever finds it missing, nothing to wait for and nothing to reset afterwards: a draw whose pairs are all rejected
+// leaves nothing behind for the binning kernels to clean up. The draw's last kernel counts the touched bins
+// (Stats: active_bin_count, main.c:1245). tm / touch are the values loaded from tile_min[bin] / bin_touch[bin].
+template <typename Params>
+__device__ __forceinline__ void count_pair(const Params &P, uint32_t bin, float tm, uint32_t touch, float max_depth, uint32_t epoch, BinTally &r) {
+	const bool rejected = !P.keep_all && (max_depth < tm); // Hi-Z (main.c:1006)
+	if(touch != epoch) atomicMax(P.bin_touch + bin, epoch); // (result unused: a reduction nobody waits for; plain stores were slower)
+	if(!rejected) {
+		atomicAdd(P.bin_count + bin, 1u);
+		r.live = true;
+		++r.survivors;
+	} else if(__float_as_uint(tm) == MLV_TILE_MIN_CLEARED) {
+		r.wake = true; // (see k_bin_scan)
+	}
+}
+
+// Rectangles of at most N tiles: walk them with fully unrolled, predicated steps so that the tile-minimum and touch
 // loads of all tiles are independent and in flight together (they were a chain of dependent L2 round trips), then
-// issue the atomics. A bin already flagged as touched needs no second atomicOr (a stale read only repeats it).
+// issue the atomics.
 template <int N>
-__device__ __forceinline__ void count_small_rect(const GeomParams &P, const TileRect &tr, int cnt, float max_depth, BinTally &r) {
+__device__ __forceinline__ void count_small_rect(const GeomParams &P, const TileRect &tr, int cnt, float max_depth, uint32_t epoch, BinTally &r) {
 	uint32_t bins[N];
 	bool ok[N];
 	{
@@ -288,31 +308,22 @@ __device__ __forceinline__ void count_small_rect(const GeomParams &P, const Tile
 		}
 	}
 	float tm[N];
-	uint32_t bc[N];
+	uint32_t tc[N];
 #pragma unroll
 	for(int k = 0; k < N; ++k) {
 		tm[k] = ok[k] ? __ldg(P.tile_min + bins[k]) : 0.0f;
-		bc[k] = (ok[k] && !P.keep_all) ? __ldcg(P.bin_count + bins[k]) : 0u;
+		tc[k] = ok[k] ? __ldcg(P.bin_touch + bins[k]) : epoch;
 	}
 #pragma unroll
-	for(int k = 0; k < N; ++k) {
-		if(!ok[k]) continue;
-		++r.pairs;
-		if(!P.keep_all && max_depth < tm[k]) { // Hi-Z (main.c:1006), see hiz_rejects
-			if(!(bc[k] & MLV_TOUCHED)) atomicOr(P.bin_count + bins[k], MLV_TOUCHED);
-		} else {
-			atomicAdd(P.bin_count + bins[k], 1u);
-			r.live = true;
-		}
-	}
+	for(int k = 0; k < N; ++k)
+		if(ok[k]) count_pair(P, bins[k], tm[k], tc[k], max_depth, epoch, r);
 }
 
-__device__ __forceinline__ BinTally count_bins(const GeomParams &P, int minx, int miny, int maxx, int maxy, float max_depth) {
-	BinTally r = { 0u, false, false, false };
-	const TileRect tr = tile_rect(minx, miny, maxx, maxy, P.wt, P.ht);
+__device__ __forceinline__ BinTally count_bins(const GeomParams &P, const TileRect &tr, float max_depth, uint32_t epoch) {
+	BinTally r = { false, false, false, false, 0u };
 	const int cnt = tr.w() * tr.h();
 	if(cnt <= 0) return r;
-	if(cnt > 8) {
+	if(cnt > 8) { // counted by k_bin_big: a warp per rectangle, the whole grid for a huge one
 		r.live = P.part.owned_rows(tr.ty0, tr.ty1) > 0;
 		r.big = r.live && cnt <= MLV_HUGE_TILES;
 		r.huge = r.live && cnt > MLV_HUGE_TILES;
@@ -320,8 +331,8 @@ __device__ __forceinline__ BinTally count_bins(const GeomParams &P, int minx, in
 	}
 	// dense meshes of pixel-sized triangles (BASELINE config 5: 2.2 tiles per triangle) almost never need more than
 	// four steps; the eight-step walk costs a third of the kernel's instructions when every lane pays for it
-	if(cnt <= 4) count_small_rect<4>(P, tr, cnt, max_depth, r);
-	else count_small_rect<8>(P, tr, cnt, max_depth, r);
+	if(cnt <= 4) count_small_rect<4>(P, tr, cnt, max_depth, epoch, r);
+	else count_small_rect<8>(P, tr, cnt, max_depth, epoch, r);
 	return r;
 }
 
@@ -435,6 +446,7 @@ __device__ __forceinline__ void tally_records(unsigned long long *stripes, uint3
 }
 
 #define MLV_GEOM_THREADS 256
+#define MLV_TILE_THREADS 256
 
 // ---- sort-first chunk culling (multi-GPU only) -------------------------------------------
 // A chunk = the MLV_GEOM_THREADS input triangles of one k_geom CTA. k_chunk_bounds computes the object-space AABB of
@@ -569,6 +581,19 @@ __device__ __forceinline__ void fetch_indices(const GeomParams &P, uint32_t t, u
 // ahead on a stream of their own, underneath the tile kernels of earlier draws; only the BACK half (Hi-Z, binning, records
 // for the survivors) sits on the draw-to-draw dependency chain.
 // =================================================================================================
+// (warp-collective) queues the slots whose tile rectangle holds more than 8 tiles: big_class 1 -> big queue, 2 -> huge queue
+__device__ __forceinline__ void queue_big(const GeomParams &P, int big_class, uint32_t slot) {
+	const uint32_t lane = lane_id();
+	const uint32_t bmask = __ballot_sync(0xffffffffu, big_class == 1);
+	if(bmask) {
+		uint32_t base = 0;
+		if(lane == 0) base = atomicAdd(&P.dctr->big_count, (uint32_t)__popc(bmask));
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if(big_class == 1) P.big_queue[base + __popc(bmask & ((1u << lane) - 1u))] = slot;
+	}
+	if(big_class == 2) P.huge_queue[atomicAdd(&P.dctr->huge_count, 1u)] = slot; // rare: sky domes, full-screen quads
+}
+
 template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
 __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_constant__ GeomParams P) {
 	pdl_prologue();
@@ -587,7 +612,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_cons
 		bool live = false;
 		if(c < num_chunks) {
 			live = !chunk_is_foreign(P, c);
-			P.chunk_live[c] = live ? 1 : 0; // the back half and k_bin_fill skip the stale bounds of the chunks nobody rewrote
+			P.chunk_live[c] = live ? 1 : 0; // the back half and the fill phase skip the stale bounds of the chunks nobody rewrote
 		}
 		s_live[threadIdx.x] = live ? 1 : 0;
 		__syncthreads();
@@ -598,6 +623,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_cons
 	if(P.chunk_bounds && !s_live[k]) continue;
 	const uint32_t t = chunk * MLV_GEOM_THREADS + threadIdx.x;
 	bool needs_clip = false;
+	int big_class = 0; // 1: tile rectangle of 9 .. MLV_HUGE_TILES tiles, 2: larger
 	if(t < P.tri_count) {
 		uint4 bounds = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, t << 3);
 		// ---- input assembler (main.c:662-696): index fetch + first half of each vertex (or its cache entry)
@@ -673,6 +699,8 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_cons
 						const uint2 pb = pack_bounds(S);
 						bounds = make_uint4(pb.x, pb.y, __float_as_uint(S.max_depth), t << 3);
 					}
+					const int cnt = tr.w() * tr.h();
+					if(np && cnt > 8) big_class = cnt > MLV_HUGE_TILES ? 2 : 1;
 				}
 			} else {
 				needs_clip = true;
@@ -682,7 +710,8 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_cons
 		P.tri_bounds[t] = bounds;
 	}
 	// ---- triangles that need the clipper are queued for k_front_clip (one warp-aggregated atomic): the slow path would
-	// otherwise stall the 31 other lanes
+	// otherwise stall the 31 other lanes. Triangles with large tile rectangles are queued for the back half, which expands
+	// them with a warp each, spread over its whole grid.
 	{
 		const uint32_t cmask = __ballot_sync(0xffffffffu, needs_clip);
 		if(cmask) {
@@ -691,6 +720,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_cons
 			base = __shfl_sync(0xffffffffu, base, 0);
 			if(needs_clip) P.clip_queue[base + __popc(cmask & ((1u << lane) - 1u))] = t;
 		}
+		queue_big(P, big_class, t);
 	}
 	}
 	if(P.chunk_bounds) __syncthreads(); // s_live is rewritten by the next round
@@ -714,6 +744,13 @@ __device__ __forceinline__ uint32_t emit_fan(const GeomParams &P, uint32_t t, co
 			const TileRect tr = tile_rect(S.minx, S.miny, S.maxx, S.maxy, P.wt, P.ht);
 			const uint32_t np = (uint32_t)(tr.w() * P.part.owned_rows(tr.ty0, tr.ty1));
 			pairs += np;
+			{
+				const int cnt = tr.w() * tr.h();
+				if(np && cnt > 8) { // (lanes diverge here: plain atomics)
+					if(cnt > MLV_HUGE_TILES) P.huge_queue[atomicAdd(&P.dctr->huge_count, 1u)] = slot;
+					else P.big_queue[atomicAdd(&P.dctr->big_count, 1u)] = slot;
+				}
+			}
 			if(np || P.dbg.tris) {
 				const uint2 pb = pack_bounds(S);
 				bounds = make_uint4(pb.x & ~MLV_NOWRAP_BIT, pb.y, __float_as_uint(S.max_depth), key);
@@ -795,135 +832,14 @@ __global__ void __launch_bounds__(MLV_CLIP_THREADS) k_front_clip(const __grid_co
 // (main.c:924-936, 1003-1010); a DIRECT slot that survives in at least one tile fetches its vertices again, runs the
 // attribute part of the vertex shader, builds the edge functions and writes its 144-byte record -- staged per warp in
 // shared memory and written as contiguous 512-byte rows. A triangle hidden in every tile it touches costs 16 bytes of
-// bounds and its tile-minimum look-ups, and writes nothing.
+// bounds and its tile-minimum look-ups, and writes nothing. The chunk loop is software-pipelined (the bounds of the CTA's
+// next chunk are in flight while the current one is processed): at one chunk per round trip chain the kernel was
+// latency-bound at every size.
 // =================================================================================================
-template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
-__global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_back(const __grid_constant__ GeomParams P) {
-	pdl_prologue();
-	__shared__ uint4 s_stage[MLV_GEOM_THREADS / 32][32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)];
-	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-	const uint32_t n_slots = P.tri_count + min(P.dctr->ovf_count, P.ovf_capacity);
-	const uint32_t num_chunks = (n_slots + MLV_GEOM_THREADS - 1u) / MLV_GEOM_THREADS;
-	uint32_t records = 0;
-	// Sort-first: direct slots of chunks the front half skipped on this rank hold stale bounds from an earlier draw. Each
-	// round, thread k of the CTA looks up the liveness of the CTA's k-th chunk, so a foreign chunk costs no round trip of its own.
-	__shared__ uint8_t s_live[MLV_GEOM_THREADS]; // bit 0: the chunk holds slots to process, bit 1: its direct slots are live
-	for(uint32_t first = blockIdx.x; first < num_chunks; first += gridDim.x * MLV_GEOM_THREADS) {
-	if(P.chunk_live) {
-		const uint32_t c = first + threadIdx.x * gridDim.x;
-		uint8_t code = 0;
-		if(c < num_chunks) {
-			const bool has_direct = c * MLV_GEOM_THREADS < P.tri_count, has_ovf = (c + 1u) * MLV_GEOM_THREADS > P.tri_count;
-			const bool direct_live = has_direct && __ldg(P.chunk_live + c) != 0;
-			code = (uint8_t)(((direct_live || has_ovf) ? 1 : 0) | (direct_live ? 2 : 0));
-		}
-		s_live[threadIdx.x] = code;
-		__syncthreads();
-	}
-	for(uint32_t k = 0; k < MLV_GEOM_THREADS; ++k) {
-		const uint32_t chunk = first + k * gridDim.x;
-		if(chunk >= num_chunks) break;
-		if(P.chunk_live && !(s_live[k] & 1)) continue;
-		const uint32_t slot = chunk * MLV_GEOM_THREADS + threadIdx.x;
-		bool staged = false, is_big = false, is_huge = false;
-		const bool mine = slot < n_slots && (slot >= P.tri_count || !P.chunk_live || (s_live[k] & 2));
-		if(mine) {
-			const uint4 b = P.tri_bounds[slot];
-			if((b.x & 0xffffu) != MLV_BOUNDS_EMPTY) {
-				const int minx = (int)(b.x & 0xffffu), miny = (int)((b.x >> 16) & 0x7fffu), maxx = (int)(short)(b.y & 0xffffu), maxy = (int)(short)(b.y >> 16);
-				// ---- binner pass 1 + Hi-Z for this triangle
-				const BinTally tally = count_bins(P, minx, miny, maxx, maxy, __uint_as_float(b.z));
-				is_big = tally.big, is_huge = tally.huge;
-				if(tally.live) ++records;
-				else reinterpret_cast<uint32_t *>(P.tri_bounds + slot)[0] = MLV_BOUNDS_EMPTY; // k_bin_fill skips it
-				if(slot < P.tri_count && (tally.live || DEBUG)) {
-					// ---- the record of a surviving direct triangle: input assembler + vertex shader + setup again (pure functions
-					// of the same inputs: the values k_front computed), now including attributes and edge functions
-					const uint32_t t = slot;
-					uint32_t vi0, vi1, vi2;
-					fetch_indices<VS, INDEXED, DEBUG, VCACHE>(P, t, vi0, vi1, vi2);
-					float4 a0 = __ldg(P.vb + 2 * (size_t)vi0), b0 = __ldg(P.vb + 2 * (size_t)vi1), c0 = __ldg(P.vb + 2 * (size_t)vi2);
-					float4 a, bq, c;
-					TriSetup S;
-					if(VCACHE) {
-						const float4 qa = __ldg(P.vcache + 2 * (size_t)vi0 + 1), qb = __ldg(P.vcache + 2 * (size_t)vi1 + 1), qc = __ldg(P.vcache + 2 * (size_t)vi2 + 1);
-						a = __ldg(P.vcache + 2 * (size_t)vi0), bq = __ldg(P.vcache + 2 * (size_t)vi1), c = __ldg(P.vcache + 2 * (size_t)vi2);
-						ProjVertex pa, pb, pc; // s.x, s.y, s.w are not needed outside debug capture (which never uses the cache)
-						pa.s = make_float4(0.0f, 0.0f, qa.z, 0.0f), pa.sx = __float_as_int(qa.x), pa.sy = __float_as_int(qa.y);
-						pb.s = make_float4(0.0f, 0.0f, qb.z, 0.0f), pb.sx = __float_as_int(qb.x), pb.sy = __float_as_int(qb.y);
-						pc.s = make_float4(0.0f, 0.0f, qc.z, 0.0f), pc.sx = __float_as_int(qc.x), pc.sy = __float_as_int(qc.y);
-						pa.rw = 1.0f / a.w, pb.rw = 1.0f / bq.w, pc.rw = 1.0f / c.w; // a_reciprocal_ws (project_vertex): the same correctly rounded divide
-						setup_from_projected(pa, pb, pc, P, S);
-					} else {
-						a = vs_position<VS>(a0, P.cb), bq = vs_position<VS>(b0, P.cb), c = vs_position<VS>(c0, P.cb);
-						setup_project(a, bq, c, P, S);
-					}
-					setup_edges(P, S);
-					// ---- vertex shader, attribute part
-					float4 r1a, r1b, r1c;
-					float r2a, r2b, r2c;
-					vs_attributes<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), a, P.cb, P.vs_tex, P.rsqrt_lut, r1a, r2a);
-					vs_attributes<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), bq, P.cb, P.vs_tex, P.rsqrt_lut, r1b, r2b);
-					vs_attributes<VS>(c0, __ldg(P.vb + 2 * (size_t)vi2 + 1), c, P.cb, P.vs_tex, P.rsqrt_lut, r1c, r2c);
-					if(tally.live) {
-						staged = true;
-						TriRecord R;
-						make_record(R, S, pack_bounds(S), r1a, r1b, r1c, r2a, r2b, r2c);
-						uint4 *st = s_stage[warp];
-#pragma unroll
-						for(int i = 0; i < MLV_TRI_COV_U4; ++i) st[lane * MLV_TRI_COV_U4 + i] = R.cov[i];
-#pragma unroll
-						for(int i = 0; i < MLV_TRI_SHADE_U4; ++i)
-							st[32 * MLV_TRI_COV_U4 + lane * MLV_TRI_SHADE_U4 + i] = make_uint4(__float_as_uint(R.shade[i].x), __float_as_uint(R.shade[i].y), __float_as_uint(R.shade[i].z), __float_as_uint(R.shade[i].w));
-					}
-					if(DEBUG) emit_debug(P, t, t << 3, S, r1a, r1b, r1c, r2a, r2b, r2c);
-				}
-			}
-		}
-		// ---- triangles with large tile rectangles are queued for k_bin_big (one warp-aggregated atomic)
-		{
-			const uint32_t bmask = __ballot_sync(0xffffffffu, is_big);
-			if(bmask) {
-				uint32_t base = 0;
-				if(lane == 0) base = atomicAdd(&P.ctr->big_count, (uint32_t)__popc(bmask));
-				base = __shfl_sync(0xffffffffu, base, 0);
-				if(is_big) P.big_queue[base + __popc(bmask & ((1u << lane) - 1u))] = slot;
-			}
-			if(is_huge) P.huge_queue[atomicAdd(&P.ctr->huge_count, 1u)] = slot; // rare: sky domes, full-screen quads
-		}
-		// ---- coalesced write-out of the staged records: the direct slots of a warp are adjacent in HBM, so the warp stores
-		// 1536 B of TriCov and 3072 B of TriShade with 128-bit stores instead of 32 scattered 16-byte pieces per instruction
-		__syncwarp();
-		const uint32_t valid = __ballot_sync(0xffffffffu, staged);
-		if(valid) {
-			const uint4 *st = s_stage[warp];
-			const size_t slot0 = (size_t)(slot - lane);
-			uint4 *cov = P.tri_cov + slot0 * MLV_TRI_COV_U4;
-			uint4 *sh = P.tri_shade + slot0 * MLV_TRI_SHADE_U4;
-#pragma unroll
-			for(int i = 0; i < MLV_TRI_COV_U4; ++i) {
-				const uint32_t piece = i * 32 + lane;
-				if((valid >> (piece / MLV_TRI_COV_U4)) & 1u) cov[piece] = st[piece];
-			}
-#pragma unroll
-			for(int i = 0; i < MLV_TRI_SHADE_U4; ++i) {
-				const uint32_t piece = i * 32 + lane;
-				if((valid >> (piece / MLV_TRI_SHADE_U4)) & 1u) sh[piece] = st[32 * MLV_TRI_COV_U4 + piece];
-			}
-		}
-		__syncwarp(); // the staging rows are reused by the next chunk of a persistent CTA
-	}
-	if(P.chunk_live) __syncthreads(); // s_live is rewritten by the next round
-	}
-	// work counter (mlv_work_counters.records_written): second word of the warp's stripe
-#pragma unroll
-	for(int d = 16; d > 0; d >>= 1) records += __shfl_xor_sync(0xffffffffu, records, d);
-	tally_records(P.stat_stripes, records);
-}
-
-// =================================================================================================
-// binner
-// =================================================================================================
+struct BackState {
+	uint32_t records, survivors;
+	bool wake;
+};
 
 struct SlotBounds {
 	TileRect tr;
@@ -941,45 +857,214 @@ __device__ __forceinline__ SlotBounds load_bounds(const uint4 *__restrict__ tri_
 	return s;
 }
 
-// Pass 1 of the binner (main.c:924-936) for the triangles whose tile rectangle holds more than 8 tiles (queued by
-// the geometry kernels). Rectangles of up to MLV_HUGE_TILES tiles: one warp per triangle, lanes stride over the
-// rectangle. Larger ones (sky domes, full-screen quads): the whole grid strides over the rectangle.
-__global__ void __launch_bounds__(256) k_bin_big(const __grid_constant__ BinParams P) {
-	pdl_prologue();
-	const uint32_t n = P.ctr->big_count;
+// Pass 1 of the binner (main.c:924-936) for the triangles whose tile rectangle holds more than 8 tiles (queued by the
+// front half). Rectangles of up to MLV_HUGE_TILES tiles: one warp per triangle, lanes stride over the rectangle with four
+// tiles in flight. Larger ones (sky domes, full-screen quads): the whole grid strides over the rectangle.
+__device__ __forceinline__ void count_big_rects(const GeomParams &P, uint32_t epoch, BackState &st) {
+	const uint32_t n = P.dctr->big_count, nhuge = P.dctr->huge_count;
+	if((n | nhuge) == 0u) return;
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-	for(uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
-		const SlotBounds s = load_bounds(P.tri_bounds, P.big_queue[i], P.wt, P.ht);
-		const int w = s.tr.w(), cnt = w * s.tr.h();
-		for(int k = (int)lane; k < cnt; k += 32) {
+	BinTally r = { false, false, false, false, 0u };
+	auto one = [&](int k, int cnt, int w, const SlotBounds &s, float &tm, uint32_t &tc, uint32_t &bin, bool &ok) {
+		ok = k < cnt;
+		if(ok) {
 			const int ty = s.tr.ty0 + k / w, tx = s.tr.tx0 + k % w;
-			if(!P.part.owns_row(ty)) continue;
-			const uint32_t bin = (uint32_t)(ty * P.wt + tx);
-			if(hiz_rejects(s.max_depth, P.tile_min, bin, P.keep_all)) atomicOr(P.bin_count + bin, MLV_TOUCHED);
-			else atomicAdd(P.bin_count + bin, 1u);
+			ok = P.part.owns_row(ty);
+			bin = (uint32_t)(ty * P.wt + tx);
+			if(ok) tm = __ldg(P.tile_min + bin), tc = __ldcg(P.bin_touch + bin);
 		}
-	}
-	const uint32_t nhuge = P.ctr->huge_count;
-	for(uint32_t i = 0; i < nhuge; ++i) { // huge rectangles, grid-cooperative
-		const SlotBounds s = load_bounds(P.tri_bounds, P.huge_queue[i], P.wt, P.ht);
+	};
+	auto expand = [&](const SlotBounds &s, int first, int stride) {
+		if(s.empty) return;
 		const int w = s.tr.w(), cnt = w * s.tr.h();
-		for(int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < cnt; k += (int)(gridDim.x * blockDim.x)) {
-			const int ty = s.tr.ty0 + k / w, tx = s.tr.tx0 + k % w;
-			if(!P.part.owns_row(ty)) continue;
-			const uint32_t bin = (uint32_t)(ty * P.wt + tx);
-			if(hiz_rejects(s.max_depth, P.tile_min, bin, P.keep_all)) atomicOr(P.bin_count + bin, MLV_TOUCHED);
-			else atomicAdd(P.bin_count + bin, 1u);
+		for(int k = first; k < cnt; k += 4 * stride) {
+			float tm[4];
+			uint32_t tc[4], bin[4];
+			bool ok[4];
+#pragma unroll
+			for(int u = 0; u < 4; ++u) one(k + u * stride, cnt, w, s, tm[u], tc[u], bin[u], ok[u]);
+#pragma unroll
+			for(int u = 0; u < 4; ++u)
+				if(ok[u]) {
+					count_pair(P, bin[u], tm[u], tc[u], s.max_depth, epoch, r);
+				}
 		}
-	}
-	// (the pairs were counted for Stats by the front half: tiles of the rectangle x owned rows)
+	};
+	for(uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) expand(load_bounds(P.tri_bounds, P.big_queue[i], P.wt, P.ht), (int)lane, 32);
+	for(uint32_t i = 0; i < nhuge; ++i) expand(load_bounds(P.tri_bounds, P.huge_queue[i], P.wt, P.ht), (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)(gridDim.x * blockDim.x));
+	st.survivors += r.survivors;
+	st.wake = st.wake || r.wake;
 }
+
+template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
+__device__ __forceinline__ void back_process(const GeomParams &P, uint4 (*s_stage)[32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)], uint32_t slot, uint4 b, uint32_t epoch, BackState &st) {
+	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+	bool staged = false, live = false, present = false;
+	TileRect tr = { 0, 0, -1, -1 };
+	float max_depth = 0.0f;
+	if((b.x & 0xffffu) != MLV_BOUNDS_EMPTY) {
+		present = true;
+		const int minx = (int)(b.x & 0xffffu), miny = (int)((b.x >> 16) & 0x7fffu), maxx = (int)(short)(b.y & 0xffffu), maxy = (int)(short)(b.y >> 16);
+		max_depth = __uint_as_float(b.z);
+		tr = tile_rect(minx, miny, maxx, maxy, P.wt, P.ht);
+		// ---- binner pass 1 + Hi-Z for this triangle
+		const BinTally tally = count_bins(P, tr, max_depth, epoch);
+		live = tally.live; // (rectangles of more than 8 tiles: counted below by a warp each, from the front half's queue)
+		st.survivors += tally.survivors;
+		st.wake = st.wake || tally.wake;
+	}
+	if(present) {
+		if(!live && !DEBUG) reinterpret_cast<uint32_t *>(P.tri_bounds + slot)[0] = MLV_BOUNDS_EMPTY; // the fill phase skips it
+		if(live) ++st.records;
+		if(slot < P.tri_count && (live || DEBUG)) {
+			// ---- the record of a surviving direct triangle: input assembler + vertex shader + setup again (pure functions
+			// of the same inputs: the values k_front computed), now including attributes and edge functions
+			const uint32_t t = slot;
+			uint32_t vi0, vi1, vi2;
+			fetch_indices<VS, INDEXED, DEBUG, VCACHE>(P, t, vi0, vi1, vi2);
+			float4 a0 = __ldg(P.vb + 2 * (size_t)vi0), b0 = __ldg(P.vb + 2 * (size_t)vi1), c0 = __ldg(P.vb + 2 * (size_t)vi2);
+			float4 a, bq, c;
+			TriSetup S;
+			if(VCACHE) {
+				const float4 qa = __ldg(P.vcache + 2 * (size_t)vi0 + 1), qb = __ldg(P.vcache + 2 * (size_t)vi1 + 1), qc = __ldg(P.vcache + 2 * (size_t)vi2 + 1);
+				a = __ldg(P.vcache + 2 * (size_t)vi0), bq = __ldg(P.vcache + 2 * (size_t)vi1), c = __ldg(P.vcache + 2 * (size_t)vi2);
+				ProjVertex pa, pb, pc; // s.x, s.y, s.w are not needed outside debug capture (which never uses the cache)
+				pa.s = make_float4(0.0f, 0.0f, qa.z, 0.0f), pa.sx = __float_as_int(qa.x), pa.sy = __float_as_int(qa.y);
+				pb.s = make_float4(0.0f, 0.0f, qb.z, 0.0f), pb.sx = __float_as_int(qb.x), pb.sy = __float_as_int(qb.y);
+				pc.s = make_float4(0.0f, 0.0f, qc.z, 0.0f), pc.sx = __float_as_int(qc.x), pc.sy = __float_as_int(qc.y);
+				pa.rw = 1.0f / a.w, pb.rw = 1.0f / bq.w, pc.rw = 1.0f / c.w; // a_reciprocal_ws (project_vertex): the same correctly rounded divide
+				setup_from_projected(pa, pb, pc, P, S);
+			} else {
+				a = vs_position<VS>(a0, P.cb), bq = vs_position<VS>(b0, P.cb), c = vs_position<VS>(c0, P.cb);
+				setup_project(a, bq, c, P, S);
+			}
+			setup_edges(P, S);
+			// ---- vertex shader, attribute part
+			float4 r1a, r1b, r1c;
+			float r2a, r2b, r2c;
+			vs_attributes<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), a, P.cb, P.vs_tex, P.rsqrt_lut, r1a, r2a);
+			vs_attributes<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), bq, P.cb, P.vs_tex, P.rsqrt_lut, r1b, r2b);
+			vs_attributes<VS>(c0, __ldg(P.vb + 2 * (size_t)vi2 + 1), c, P.cb, P.vs_tex, P.rsqrt_lut, r1c, r2c);
+			if(live) {
+				staged = true;
+				TriRecord R;
+				make_record(R, S, pack_bounds(S), r1a, r1b, r1c, r2a, r2b, r2c);
+				uint4 *stg = s_stage[warp];
+#pragma unroll
+				for(int i = 0; i < MLV_TRI_COV_U4; ++i) stg[lane * MLV_TRI_COV_U4 + i] = R.cov[i];
+#pragma unroll
+				for(int i = 0; i < MLV_TRI_SHADE_U4; ++i)
+					stg[32 * MLV_TRI_COV_U4 + lane * MLV_TRI_SHADE_U4 + i] = make_uint4(__float_as_uint(R.shade[i].x), __float_as_uint(R.shade[i].y), __float_as_uint(R.shade[i].z), __float_as_uint(R.shade[i].w));
+			}
+			if(DEBUG) emit_debug(P, t, t << 3, S, r1a, r1b, r1c, r2a, r2b, r2c);
+		}
+	}
+	// ---- coalesced write-out of the staged records: the direct slots of a warp are adjacent in HBM, so the warp stores
+	// 1536 B of TriCov and 3072 B of TriShade with 128-bit stores instead of 32 scattered 16-byte pieces per instruction
+	__syncwarp();
+	const uint32_t valid = __ballot_sync(0xffffffffu, staged);
+	if(valid) {
+		const uint4 *stg = s_stage[warp];
+		const size_t slot0 = (size_t)(slot - lane);
+		uint4 *cov = P.tri_cov + slot0 * MLV_TRI_COV_U4;
+		uint4 *sh = P.tri_shade + slot0 * MLV_TRI_SHADE_U4;
+#pragma unroll
+		for(int i = 0; i < MLV_TRI_COV_U4; ++i) {
+			const uint32_t piece = i * 32 + lane;
+			if((valid >> (piece / MLV_TRI_COV_U4)) & 1u) cov[piece] = stg[piece];
+		}
+#pragma unroll
+		for(int i = 0; i < MLV_TRI_SHADE_U4; ++i) {
+			const uint32_t piece = i * 32 + lane;
+			if((valid >> (piece / MLV_TRI_SHADE_U4)) & 1u) sh[piece] = stg[32 * MLV_TRI_COV_U4 + piece];
+		}
+	}
+	__syncwarp(); // the staging rows are reused by the next chunk
+}
+
+template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
+__global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_back(const __grid_constant__ GeomParams P) {
+	pdl_prologue();
+	__shared__ uint4 s_stage[MLV_GEOM_THREADS / 32][32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)];
+	__shared__ uint32_t s_list[MLV_GEOM_THREADS]; // the live chunks of this round, compacted
+	__shared__ uint32_t s_warp_count[MLV_GEOM_THREADS / 32];
+	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+	const uint32_t epoch = P.ctr->epoch;        // both loads are in flight with the first chunk's bounds;
+	const uint32_t ovf_raw = P.dctr->ovf_count; // the overflow count is only needed after the direct slots
+	const uint32_t direct_chunks = (P.tri_count + MLV_GEOM_THREADS - 1u) / MLV_GEOM_THREADS;
+	BackState st = { 0u, 0u, false };
+	for(uint32_t first = blockIdx.x; first < direct_chunks; first += gridDim.x * MLV_GEOM_THREADS) {
+		// Thread k looks up the k-th chunk of this CTA's round. Sort-first: chunks the front half skipped on this rank hold
+		// stale bounds from an earlier draw -- they are dropped here, at the cost of one load for the whole round.
+		const uint32_t cand = first + threadIdx.x * gridDim.x;
+		const bool live_chunk = cand < direct_chunks && (!P.chunk_live || __ldg(P.chunk_live + cand) != 0);
+		const uint32_t m = __ballot_sync(0xffffffffu, live_chunk);
+		if(lane == 0) s_warp_count[warp] = (uint32_t)__popc(m);
+		__syncthreads();
+		uint32_t before = 0, total = 0;
+#pragma unroll
+		for(uint32_t w = 0; w < MLV_GEOM_THREADS / 32; ++w) {
+			const uint32_t cnt = s_warp_count[w];
+			before += (w < warp) ? cnt : 0u;
+			total += cnt;
+		}
+		if(live_chunk) s_list[before + (uint32_t)__popc(m & ((1u << lane) - 1u))] = cand;
+		__syncthreads();
+		const uint4 empty = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, 0u);
+		uint4 b_next = empty;
+		if(total) {
+			const uint32_t s0 = s_list[0] * MLV_GEOM_THREADS + threadIdx.x;
+			if(s0 < P.tri_count) b_next = P.tri_bounds[s0];
+		}
+		for(uint32_t i = 0; i < total; ++i) {
+			const uint32_t slot = s_list[i] * MLV_GEOM_THREADS + threadIdx.x;
+			const uint4 b = b_next;
+			b_next = empty;
+			if(i + 1u < total) {
+				const uint32_t sn = s_list[i + 1u] * MLV_GEOM_THREADS + threadIdx.x;
+				if(sn < P.tri_count) b_next = P.tri_bounds[sn];
+			}
+			back_process<VS, INDEXED, DEBUG, VCACHE>(P, s_stage, slot, b, epoch, st);
+		}
+		__syncthreads(); // s_list is rewritten by the next round
+	}
+	// overflow slots: the fan triangles of clipped input triangles (their records exist already)
+	const uint32_t n_ovf = min(ovf_raw, P.ovf_capacity);
+	for(uint32_t base = blockIdx.x * MLV_GEOM_THREADS; base < n_ovf; base += gridDim.x * MLV_GEOM_THREADS) {
+		const uint32_t o = base + threadIdx.x;
+		const uint4 b = (o < n_ovf) ? P.tri_bounds[P.tri_count + o] : make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, 0u);
+		back_process<VS, INDEXED, DEBUG, VCACHE>(P, s_stage, P.tri_count + o, b, epoch, st);
+	}
+	// ---- rectangles of more than 8 tiles (the front half queued them): a warp each, spread over the whole grid
+	count_big_rects(P, epoch, st);
+	// ---- per-draw tallies: records written (work counter, one atomic per warp); "a pair survived Hi-Z" (the scan, the fill
+	// pass and the tile kernel return at once otherwise)
+#pragma unroll
+	for(int d = 16; d > 0; d >>= 1) {
+		st.records += __shfl_xor_sync(0xffffffffu, st.records, d);
+		st.survivors += __shfl_xor_sync(0xffffffffu, st.survivors, d);
+	}
+	const bool wake = __any_sync(0xffffffffu, st.wake);
+	if(lane == 0) {
+		const uint32_t stripe = (blockIdx.x * 8u + warp) % MLV_STAT_STRIPES;
+		if(st.records) atomicAdd(P.stat_stripes + stripe * 16u + 1u, (unsigned long long)st.records);
+		if(st.survivors) P.ctr->draw_alive = 1u; // (the exact total is the scan's)
+		if(wake) P.ctr->n_wake = 1u;
+	}
+}
+
+// =================================================================================================
+// binner: k_bin_scan (exclusive scan of the per-bin counts pass 1 left + work list), k_fill (pass 2). All of them, and
+// k_tile, return at once for a draw whose pairs were all rejected by Hi-Z (nothing is left behind by such a draw: bins
+// are marked as touched by the draw's epoch, not by flags that would need resetting).
+// =================================================================================================
 
 // Pass 2 of the binner (main.c:950-962): every surviving (triangle, tile) pair takes the next position of its
 // bin's list (atomic on the running offset the scan left in bin_offset). One lane per triangle slot; rectangles
 // of more than 8 tiles are expanded cooperatively by the warp (four independent atomics in flight per lane),
 // huge ones by the whole grid. The per-bin order this leaves is arbitrary; k_tile does not depend on it.
-__device__ __forceinline__ void fill_one(const BinParams &P, int k, int cnt, int w, int tx0, int ty0, float max_depth, uint32_t slot) {
+__device__ __forceinline__ void fill_one(const TailParams &P, int k, int cnt, int w, int tx0, int ty0, float max_depth, uint32_t slot) {
 	if(k >= cnt) return;
 	const int ty = ty0 + k / w, tx = tx0 + k % w;
 	if(!P.part.owns_row(ty)) return;
@@ -989,7 +1074,7 @@ __device__ __forceinline__ void fill_one(const BinParams &P, int k, int cnt, int
 
 // unrolled, predicated walk over a rectangle of at most N tiles: all tile-minimum loads, then all atomics, then all stores
 template <int N>
-__device__ __forceinline__ void fill_small_rect(const BinParams &P, const SlotBounds &s, int cnt, uint32_t slot) {
+__device__ __forceinline__ void fill_small_rect(const TailParams &P, const SlotBounds &s, int cnt, uint32_t slot) {
 	uint32_t bins[N], pos[N];
 	bool ok[N];
 	int tx = s.tr.tx0, ty = s.tr.ty0;
@@ -1011,27 +1096,30 @@ __device__ __forceinline__ void fill_small_rect(const BinParams &P, const SlotBo
 		if(ok[k]) P.pair_ids[pos[k]] = slot;
 }
 
-__global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinParams P, uint32_t pair_capacity) {
+__global__ void __launch_bounds__(256) k_fill(const __grid_constant__ TailParams P) {
 	pdl_prologue();
-	if(P.ctr->pair_total > pair_capacity || P.ctr->pair_total == 0u) return; // draw skipped (MLV_FLAG_PAIR_OVERFLOW is set) / nothing survived Hi-Z
-	const uint32_t n = P.direct_slots + min(P.dctr->ovf_count, P.ovf_capacity); // (a draw that ran out of overflow slots is skipped as a whole: k_bin_scan poisons pair_total)
+	const uint32_t total = P.ctr->pair_total;
+	// draw skipped (pair arena or overflow slots exhausted: k_tile raises the flag) / nothing survived Hi-Z
+	if(total == 0u || total > P.pair_capacity || P.dctr->ovf_count > P.ovf_capacity) return;
+	const uint32_t n = P.direct_slots + min(P.dctr->ovf_count, P.ovf_capacity);
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	for(uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < n; base += warps * 32u) {
 		const uint32_t slot = base + lane;
 		SlotBounds s;
 		s.empty = true;
-		// slots of chunks k_geom skipped on this rank hold stale bounds from an earlier draw
+		// slots of chunks the front half skipped on this rank hold stale bounds from an earlier draw
 		const bool live_chunk = !P.chunk_live || slot >= P.direct_slots || __ldg(P.chunk_live + slot / MLV_GEOM_THREADS) != 0;
 		if(slot < n && live_chunk) s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
 		const int w = s.empty ? 0 : s.tr.w(), cnt = s.empty ? 0 : w * s.tr.h();
 		if(cnt > 0 && cnt <= 4) fill_small_rect<4>(P, s, cnt, slot);
 		else if(cnt > 0 && cnt <= 8) fill_small_rect<8>(P, s, cnt, slot);
 	}
-	const uint32_t nbig = P.ctr->big_count;
+	const uint32_t nbig = P.dctr->big_count;
 	for(uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nbig; i += warps) { // 9..MLV_HUGE_TILES tiles: one warp per triangle
 		const uint32_t slot = P.big_queue[i];
 		const SlotBounds s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
+		if(s.empty) continue;
 		const int w = s.tr.w(), cnt = w * s.tr.h();
 		for(int k = (int)lane; k < cnt; k += 128) {
 			fill_one(P, k, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, slot);
@@ -1040,10 +1128,11 @@ __global__ void __launch_bounds__(256) k_bin_fill(const __grid_constant__ BinPar
 			fill_one(P, k + 96, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, slot);
 		}
 	}
-	const uint32_t nhuge = P.ctr->huge_count;
+	const uint32_t nhuge = P.dctr->huge_count;
 	for(uint32_t i = 0; i < nhuge; ++i) { // huge rectangles, grid-cooperative
 		const uint32_t slot = P.huge_queue[i];
 		const SlotBounds s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
+		if(s.empty) continue;
 		const int w = s.tr.w(), cnt = w * s.tr.h();
 		for(int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < cnt; k += (int)(gridDim.x * blockDim.x)) fill_one(P, k, cnt, w, s.tr.tx0, s.tr.ty0, s.max_depth, slot);
 	}
@@ -1101,8 +1190,9 @@ __device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long lo
 // would rewrite the value already stored).
 #define MLV_SCAN_THREADS 1024
 #define MLV_SCAN_ITEMS 4
-__global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_constant__ ScanParams P) {
+__global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_constant__ TailParams P) {
 	pdl_prologue();
+	if(P.ctr->draw_alive == 0u && P.ctr->n_wake == 0u) return; // nothing survived Hi-Z in this draw: there is nothing to lay out (k_fill and k_tile return as well)
 	__shared__ uint32_t s_tile;
 	__shared__ uint32_t s_sum[32], s_nz[32];
 	__shared__ uint32_t s_excl[2];
@@ -1112,7 +1202,7 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 	if(threadIdx.x == 0) s_tile = atomicAdd(&P.ctr->ticket, 1u);
 	__syncthreads();
 	const uint32_t tile = s_tile;
-	const uint32_t epoch = P.ctr->epoch;
+	const uint32_t epoch = P.ctr->epoch, n_wake = P.ctr->n_wake;
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 	const uint32_t base = P.bin_begin + (tile * MLV_SCAN_THREADS + threadIdx.x) * MLV_SCAN_ITEMS; // 4 consecutive bins per thread, 16-byte accesses
 	uint32_t raw[MLV_SCAN_ITEMS], c[MLV_SCAN_ITEMS];
@@ -1125,17 +1215,17 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 #pragma unroll
 		for(int k = 0; k < MLV_SCAN_ITEMS; ++k) raw[k] = (base + k < P.bin_end) ? P.bin_count[base + k] : 0u;
 	}
-	uint32_t tsum = 0, twork = 0, tne = 0;
+	uint32_t tsum = 0, twork = 0;
 #pragma unroll
 	for(int k = 0; k < MLV_SCAN_ITEMS; ++k) {
-		c[k] = raw[k] & ~MLV_TOUCHED;
-		const bool nonempty = raw[k] != 0u;
-		work[k] = c[k] != 0u || (nonempty && __float_as_uint(P.tile_min[base + k]) == MLV_TILE_MIN_CLEARED);
+		c[k] = raw[k];
+		// (a touched bin without surviving pairs whose tile minimum still carries the clear tag is visited for write_tile's
+		// refresh, main.c:589-603; it takes a pair with negative depth, the back half counts such bins in n_wake)
+		work[k] = c[k] != 0u || (n_wake != 0u && base + k < P.bin_end && P.bin_touch[base + k] == epoch && __float_as_uint(P.tile_min[base + k]) == MLV_TILE_MIN_CLEARED);
 		tsum += c[k];
 		twork += work[k] ? 1u : 0u;
-		tne += nonempty ? 1u : 0u;
 	}
-	if(tne) { // counters back to zero for the next draw
+	if(twork) { // counters back to zero for the next draw
 		if(full) *reinterpret_cast<uint4 *>(P.bin_count + base) = make_uint4(0u, 0u, 0u, 0u);
 		else
 			for(int k = 0; k < MLV_SCAN_ITEMS; ++k)
@@ -1150,13 +1240,10 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 			wincl_work += o2;
 		}
 	}
-#pragma unroll
-	for(int d = 16; d > 0; d >>= 1) tne += __shfl_xor_sync(0xffffffffu, tne, d);
 	if(lane == 31) {
 		s_sum[warp] = incl;
 		s_nz[warp] = wincl_work;
 	}
-	if(lane == 0 && tne) atomicAdd(&P.ctr->draw_active_bins, tne);
 	__syncthreads();
 	if(warp < 2) {
 		const uint32_t v = (warp == 0) ? s_sum[lane] : s_nz[lane];
@@ -1171,17 +1258,10 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 		if(warp == 0) s_sum[lane] = wincl - v;
 		else s_nz[lane] = wincl - v;
 		if(lane == 0) s_excl[warp] = excl;
-		if(tile == P.num_blocks - 1 && lane == 0) {
+		if(tile == P.scan_blocks - 1 && lane == 0) {
 			const uint32_t total = excl + block_total;
-			if(warp == 0) {
-				// A draw whose clipped triangles ran out of overflow slots (MLV_FLAG_TRI_OVERFLOW) is skipped as a whole,
-				// like one whose pairs do not fit: k_bin_fill and k_tile return when pair_total exceeds the capacity.
-				const bool tri_overflow = P.dctr->ovf_count > P.ovf_capacity;
-				P.ctr->pair_total = tri_overflow ? 0xffffffffu : total;
-				if(total > P.pair_capacity) atomicOr(&P.ctr->error_flags, MLV_FLAG_PAIR_OVERFLOW);
-			} else {
-				P.ctr->n_cbins = total; // k_tile ignores it when the pair arena overflowed
-			}
+			if(warp == 0) P.ctr->pair_total = total; // (k_fill and k_tile skip a draw whose pairs or overflow slots do not fit)
+			else P.ctr->n_cbins = total;
 		}
 	}
 	__syncthreads();
@@ -1211,20 +1291,20 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 // =================================================================================================
 
 // record / key of a slot (mlv_internal.cuh "Triangle identity")
-__device__ __forceinline__ const uint4 *cov_of(const TileParams &P, uint32_t slot) {
+__device__ __forceinline__ const uint4 *cov_of(const TailParams &P, uint32_t slot) {
 	return slot < P.direct_slots ? P.tri_cov + (size_t)slot * MLV_TRI_COV_U4 : P.ovf_cov + (size_t)(slot - P.direct_slots) * MLV_TRI_COV_U4;
 }
-__device__ __forceinline__ const float4 *shade_of(const TileParams &P, uint32_t slot) {
+__device__ __forceinline__ const float4 *shade_of(const TailParams &P, uint32_t slot) {
 	return reinterpret_cast<const float4 *>(slot < P.direct_slots ? P.tri_shade + (size_t)slot * MLV_TRI_SHADE_U4 : P.ovf_shade + (size_t)(slot - P.direct_slots) * MLV_TRI_SHADE_U4);
 }
-__device__ __forceinline__ uint32_t key_of(const TileParams &P, uint32_t slot) {
+__device__ __forceinline__ uint32_t key_of(const TailParams &P, uint32_t slot) {
 	return slot < P.direct_slots ? (slot << 3) : __ldg(reinterpret_cast<const uint32_t *>(P.tri_bounds + slot) + 3);
 }
 
 // Debug capture only: restores ascending-KEY order inside one bin list of slots (the order the reference's serial fill
 // produces, main.c:950-962). n <= 32: bitonic network in registers. Larger lists: stable LSD radix split on the key, one
 // bit per pass, ping-ponging between the list and a scratch segment of the same extent.
-__device__ __forceinline__ void sort_bin_ids(const TileParams &P, uint32_t *ids, uint32_t *tmp, uint32_t n, uint32_t key_bits) {
+__device__ __forceinline__ void sort_bin_ids(const TailParams &P, uint32_t *ids, uint32_t *tmp, uint32_t n, uint32_t key_bits) {
 	const uint32_t lane = lane_id();
 	if(n <= 32u) {
 		const uint32_t slot = (lane < n) ? ids[lane] : 0xffffffffu;
@@ -1353,7 +1433,7 @@ __device__ __forceinline__ void perspective_barycentrics(uint32_t E1, uint32_t E
 #define MLV_PS_ID_BASIC_TRILINEAR 3
 
 template <int PS>
-__device__ __forceinline__ uint32_t shade_pixel(const TileParams &P, uint32_t slot, uint32_t X, uint32_t Y) {
+__device__ __forceinline__ uint32_t shade_pixel(const TailParams &P, uint32_t slot, uint32_t X, uint32_t Y) {
 	const uint4 *cov = cov_of(P, slot);
 	const uint4 c0 = __ldg(cov), c1 = __ldg(cov + 1);
 	const uint32_t c2x = __ldg(reinterpret_cast<const uint32_t *>(cov + 2));
@@ -1379,7 +1459,6 @@ __device__ __forceinline__ uint32_t shade_pixel(const TileParams &P, uint32_t sl
 	return encode_color(run_ps<(PS == MLV_PS_ID_BASIC_TRILINEAR ? 1 : PS)>(r1, r2x, P.ps_tex, P.rsqrt_lut));
 }
 
-#define MLV_TILE_THREADS 256
 
 // Coverage by (triangle, row) items. With lanes over triangles (coverage() above) a batch costs what its TALLEST bounding
 // box costs and the lanes beyond the list's length idle -- at BASELINE config 5 (21 pixel-sized triangles per tile, boxes of
@@ -1400,59 +1479,9 @@ struct RowCovWarp {
 };
 
 template <int PS>
-__global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_constant__ TileParams P, uint32_t pair_capacity, uint32_t ovf_capacity) {
-	__shared__ RowCovWarp s_rowcov[MLV_TILE_THREADS / 32];
-	pdl_prologue();
+__device__ __forceinline__ void tile_phase(const TailParams &P, RowCovWarp *s_rowcov, const uint32_t n_cbins) {
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-	if(blockIdx.x == 0 && threadIdx.x < 32) { // every earlier kernel of this draw is done with these: fold them into Stats, re-arm for the next draw
-		uint32_t tris = 0, pairs = 0, records = 0;
-#pragma unroll
-		for(uint32_t i = lane; i < MLV_STAT_STRIPES; i += 32u) {
-			const unsigned long long v = P.stat_stripes[i * 16u];
-			P.stat_stripes[i * 16u] = 0ull;
-			tris += (uint32_t)(v >> 32);
-			pairs += (uint32_t)v;
-			records += (uint32_t)P.stat_stripes[i * 16u + 1u];
-			P.stat_stripes[i * 16u + 1u] = 0ull;
-		}
-#pragma unroll
-		for(int d = 16; d > 0; d >>= 1) {
-			tris += __shfl_xor_sync(0xffffffffu, tris, d);
-			pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
-			records += __shfl_xor_sync(0xffffffffu, records, d);
-		}
-		if(lane == 0) {
-			Counters *c = P.ctr;
-			c->work.records_written += records;
-			if(c->pair_total <= pair_capacity) {
-				c->work.pairs_listed += c->pair_total;
-				c->work.tiles_visited += c->n_cbins;
-			}
-			c->stats.vertex_count += P.index_count;             // main.c:1228-1232
-			c->stats.input_triangle_count += P.direct_slots;
-			c->stats.assembled_triangle_count += tris;
-			c->stats.total_triangle_count_in_bins += pairs;
-			c->stats.active_bin_count += c->draw_active_bins;
-			c->last_ovf_count = min(P.dctr->ovf_count, ovf_capacity);
-			c->draw_active_bins = 0u;
-			c->big_count = c->huge_count = 0u;
-			P.dctr->ovf_count = P.dctr->clip_count = 0u; // the draw context is free for the front half of a later draw
-			c->ticket = 0u;
-		}
-		// the epoch tags the look-back words of the next draw's scan; when its 30 bits wrap (after 2^30 draws) every
-		// published scan entry is invalidated
-		uint32_t next_epoch = 0u;
-		if(lane == 0) next_epoch = (P.ctr->epoch + 1u) & 0x3fffffffu;
-		next_epoch = __shfl_sync(0xffffffffu, next_epoch, 0);
-		if(next_epoch == 0u) {
-			for(uint32_t i = lane; i < P.scan_words; i += 32u) P.scan_state[i] = 0ull;
-			next_epoch = 1u;
-		}
-		if(lane == 0) P.ctr->epoch = next_epoch;
-	}
-	if(P.ctr->pair_total > pair_capacity) return; // draw skipped, MLV_FLAG_PAIR_OVERFLOW is set
-	const uint32_t n_cbins = P.ctr->n_cbins;
 	const uint32_t px = lane & 7u, py = lane >> 3; // this lane's pixels: (px, py) and (px, py + 4)
 
 	for(uint32_t cb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; cb < n_cbins; cb += warps) {
@@ -1479,7 +1508,7 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_const
 		// The reference walks a bin's list in ascending triangle id and lets a fragment through when z >= depth
 		// (main.c:1166), so the surviving fragment of a pixel is the one with the greatest z and, among equal z, the
 		// greatest id -- a property of the SET of fragments. Taking the maximum over (z, key) therefore gives the
-		// reference's result in any visiting order, and the list k_bin_fill left in arrival order needs no sorting.
+		// reference's result in any visiting order, and the list the fill phase left in arrival order needs no sorting.
 		// Debug capture sorts it anyway so that mlv_debug_read_bins shows the reference's per-tile order.
 		uint32_t *ids = P.pair_ids + off;
 		if(P.sort_lists) sort_bin_ids(P, ids, P.pair_tmp + off, n, P.key_bits);
@@ -1625,6 +1654,96 @@ __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_const
 		for(int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, d));
 		if(lane == 0) P.tile_min[b] = m;
 	}
+}
+
+// One warp of the last CTA of a draw's last kernel: fold the draw's Stats contributions (main.c:1228-1246), re-arm the
+// counters and the draw context for the next draw.
+__device__ __forceinline__ void finish_draw(const TailParams &P, bool skipped, bool pair_overflow) {
+	const uint32_t lane = lane_id();
+	uint32_t tris = 0, pairs = 0, records = 0;
+#pragma unroll
+	for(uint32_t i = lane; i < MLV_STAT_STRIPES; i += 32u) {
+		const unsigned long long v = P.stat_stripes[i * 16u];
+		P.stat_stripes[i * 16u] = 0ull;
+		tris += (uint32_t)(v >> 32);
+		pairs += (uint32_t)v;
+		records += (uint32_t)P.stat_stripes[i * 16u + 1u];
+		P.stat_stripes[i * 16u + 1u] = 0ull;
+	}
+#pragma unroll
+	for(int d = 16; d > 0; d >>= 1) {
+		tris += __shfl_xor_sync(0xffffffffu, tris, d);
+		pairs += __shfl_xor_sync(0xffffffffu, pairs, d);
+		records += __shfl_xor_sync(0xffffffffu, records, d);
+	}
+	// the epoch tags this draw's touches in bin_touch and the look-back words of its scan; when its 30 bits wrap (after 2^30
+	// draws) every tag is invalidated
+	uint32_t next_epoch = 0u;
+	if(lane == 0) next_epoch = (P.ctr->epoch + 1u) & 0x3fffffffu;
+	next_epoch = __shfl_sync(0xffffffffu, next_epoch, 0);
+	if(next_epoch == 0u) {
+		for(uint32_t i = lane; i < 2u * P.scan_blocks; i += 32u) P.state_sum[i] = 0ull; // (state_nz follows state_sum)
+		for(uint32_t i = lane; i < P.num_bins; i += 32u) P.bin_touch[i] = 0u;
+		next_epoch = 1u;
+	}
+	if(lane == 0) {
+		Counters *c = P.ctr;
+		c->work.records_written += records;
+		if(!skipped) {
+			c->work.pairs_listed += c->pair_total;
+			c->work.tiles_visited += c->n_cbins;
+		}
+		if(pair_overflow) atomicOr(&c->error_flags, MLV_FLAG_PAIR_OVERFLOW);
+		// what the read-backs of the last draw's lists see (mlv_read_bin_lists, mlv_debug_read_bins)
+		c->last_pair_total = skipped ? 0xffffffffu : c->pair_total;
+		c->last_n_cbins = skipped ? 0u : c->n_cbins;
+		c->stats.vertex_count += P.index_count;             // main.c:1228-1232
+		c->stats.input_triangle_count += P.direct_slots;
+		c->stats.assembled_triangle_count += tris;
+		c->stats.total_triangle_count_in_bins += pairs;
+		c->stats.active_bin_count += c->draw_active_bins;   // non-empty bins in the reference's sense: Hi-Z-rejected pairs count (main.c:1245)
+		c->draw_active_bins = 0u;
+		c->last_ovf_count = min(P.dctr->ovf_count, P.ovf_capacity);
+		c->pair_total = c->n_cbins = c->ticket = c->n_wake = c->draw_alive = 0u;
+		c->epoch = next_epoch;
+		P.dctr->ovf_count = P.dctr->clip_count = P.dctr->big_count = P.dctr->huge_count = 0u; // the draw context is free for the front half of a later draw
+	}
+}
+
+template <int PS>
+__global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_constant__ TailParams P) {
+	__shared__ RowCovWarp s_rowcov[MLV_TILE_THREADS / 32];
+	pdl_prologue();
+	Counters *c = P.ctr;
+	const uint32_t total = c->pair_total, n_cbins = c->n_cbins;
+	const bool skipped = total > P.pair_capacity || P.dctr->ovf_count > P.ovf_capacity; // MLV_FLAG_PAIR_OVERFLOW / MLV_FLAG_TRI_OVERFLOW: the draw is skipped as a whole
+	const uint32_t epoch = c->epoch;
+	// Stats: the bins this draw touched (every thread of the grid looks at its share: one load, in flight with the ones above)
+	uint32_t touched = 0;
+	for(uint32_t b = P.bin_begin + blockIdx.x * blockDim.x + threadIdx.x; b < P.bin_end; b += gridDim.x * blockDim.x) touched += (__ldcg(P.bin_touch + b) == epoch) ? 1u : 0u;
+	if(!skipped && n_cbins) tile_phase<PS>(P, s_rowcov, n_cbins);
+	// The LAST CTA to get here folds the draw's Stats and re-arms the per-draw counters: CTAs of this grid that start late
+	// (the grid may exceed what is resident at once) must still find pair_total / n_cbins as the scan left them. One 64-bit
+	// atomic per CTA: arrivals in the low word, touched bins in the high word.
+	__shared__ uint32_t s_touched[MLV_TILE_THREADS / 32];
+	__shared__ bool s_last;
+#pragma unroll
+	for(int d = 16; d > 0; d >>= 1) touched += __shfl_xor_sync(0xffffffffu, touched, d);
+	if(lane_id() == 0) s_touched[threadIdx.x >> 5] = touched;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		touched = 0;
+		for(uint32_t w = 0; w < blockDim.x / 32u; ++w) touched += s_touched[w];
+		__threadfence();
+		const unsigned long long before = atomicAdd(&c->tile_done, ((unsigned long long)touched << 32) | 1ull);
+		s_last = (uint32_t)before == gridDim.x - 1u;
+		if(s_last) {
+			c->draw_active_bins = (uint32_t)(before >> 32) + touched;
+			c->tile_done = 0ull;
+		}
+	}
+	__syncthreads();
+	if(s_last && threadIdx.x < 32) finish_draw(P, skipped, total > P.pair_capacity);
 }
 
 // =================================================================================================

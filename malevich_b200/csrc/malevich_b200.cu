@@ -14,6 +14,8 @@
 #include <utility>
 #include <vector>
 
+#include <cuda.h> // driver-API types only: the entry points are fetched through cudaGetDriverEntryPoint, libcuda is not linked
+
 #include "kernels.cuh"
 
 using namespace mlv;
@@ -89,6 +91,7 @@ struct mlv_command_list {
 #define MLV_DRAW_CONTEXTS 8 /* draws whose front half may run ahead; MAX_OBJECT_COUNT_PER_SCENE of the reference is 8 (main.c:44) */
 struct DrawCtx {
 	uint4 *tri_bounds;
+	uint32_t *big_queue, *huge_queue; // slots with large tile rectangles (capacity: every slot)
 	uint32_t slot_capacity;
 	uint32_t *clip_queue;
 	uint32_t queue_capacity;
@@ -127,13 +130,14 @@ struct mlv_device {
 	bool xchg_pending;         // mlv_composite_join has not yet been called for the last mlv_composite_broadcast_async
 	float *tile_min;
 	// per-draw arenas
-	uint32_t *bin_count, *bin_offset;
+	uint32_t *bin_count, *bin_offset, *bin_touch;
+	unsigned long long *scan_state; // 2 x scan_blocks look-back words
+	uint32_t scan_blocks;
 	mlv_ref_compacted_bin *cbins;
 	uint32_t *pair_ids, *pair_tmp;
 	uint64_t pair_capacity;
 	uint4 *tri_cov, *tri_shade;      // records of the direct slots
-	uint32_t *big_queue, *huge_queue;
-	uint32_t queue_capacity;
+
 	// Draw contexts: what the FRONT half of a draw (its own stream, running ahead) hands to its BACK half (main stream).
 	DrawCtx ctxs[MLV_DRAW_CONTEXTS];
 	uint32_t num_ctx;                // 1 under debug capture (the reference-layout capture arrays exist once)
@@ -160,8 +164,6 @@ struct mlv_device {
 	cudaEvent_t ev_main_sync;
 	uint32_t bin_begin, bin_end; // bins this rank can touch: everything, or one contiguous band
 	uint32_t tri_capacity; // slots (direct + overflow)
-	unsigned long long *scan_state; // 2 x scan_blocks look-back words
-	uint32_t scan_blocks;
 	Counters *ctr;
 	uint32_t *rsqrt_lut;
 	// debug capture
@@ -241,6 +243,35 @@ static int use_device(mlv_device *dev) {
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	CUDA_TRY(cudaSetDevice(dev->cuda_dev));
 	return MLV_OK;
+}
+
+// Waits on `st` until every rank's arrival word has reached `seq` (cyclic comparison, like k_composite_wait). A stream
+// memory operation (cuStreamWaitValue32) when the driver offers it: the wait then occupies no SM -- a spinning kernel would
+// sit resident next to the cooperative k_tail launches of the next frame, which need every CTA slot they were sized for.
+// Fallback (MLV_COMPOSITE_WAIT_KERNEL=1 forces it): the bounded spin kernel.
+typedef CUresult (*mlv_pfn_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static bool wait_flags_on_stream(mlv_device *dev, cudaStream_t st, uint32_t seq) {
+	static mlv_pfn_wait32 fn = nullptr;
+	static bool resolved = false;
+	if(!resolved) {
+		resolved = true;
+		const char *force = getenv("MLV_COMPOSITE_WAIT_KERNEL");
+		if(!(force && atoi(force))) {
+			void *p = nullptr;
+			cudaDriverEntryPointQueryResult q;
+			if(cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (mlv_pfn_wait32)p;
+			cudaGetLastError();
+		}
+	}
+	if(fn) {
+		bool ok = true;
+		for(int p = 0; p < dev->part.num_ranks && ok; ++p)
+			ok = fn((CUstream)st, (CUdeviceptr)(uintptr_t)(dev->p2p_flags + p), (cuuint32_t)seq, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS;
+		if(ok) return true;
+		fn = nullptr; // e.g. not supported on this device: use the kernel from now on
+	}
+	launch_pdl(k_composite_wait, 1, 32, st, (const uint32_t *)dev->p2p_flags, dev->part.num_ranks, seq, dev->ctr, 10000000000ull);
+	return false;
 }
 
 // Entry points that synchronise, read back or use other streams cannot be part of a recorded command list.
@@ -351,7 +382,7 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	dev->num_ctx = (desc->flags & MLV_DEVICE_DEBUG_CAPTURE) ? 1u : MLV_DRAW_CONTEXTS;
 	{
 		const char *e = getenv("MLV_FRONT_STREAMS");
-		uint32_t n = e ? (uint32_t)atoi(e) : dev->num_ctx;
+		uint32_t n = e ? (uint32_t)atoi(e) : 2u; // measured: two independent front chains overlap best with the draw-to-draw chain (1: 0.727, 2: 0.721, 4: 0.749 ms per config-5 frame)
 		if(n < 1) n = 1;
 		if(n > dev->num_ctx) n = dev->num_ctx;
 		dev->num_front_streams = n;
@@ -397,6 +428,8 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	CREATE_TRY(cudaMalloc(&dev->pair_ids, dev->pair_capacity * sizeof(uint32_t)));
 	// (pair_tmp, the scratch of the debug-capture list sort, is allocated with the first debug draw)
 	CREATE_TRY(cudaMalloc(&dev->ctr, sizeof(Counters)));
+	CREATE_TRY(cudaMalloc(&dev->bin_touch, nb * sizeof(uint32_t)));
+	CREATE_TRY(cudaMemsetAsync(dev->bin_touch, 0, nb * sizeof(uint32_t), dev->stream));
 	dev->scan_blocks = (dev->bin_end - dev->bin_begin + MLV_SCAN_THREADS * MLV_SCAN_ITEMS - 1) / (MLV_SCAN_THREADS * MLV_SCAN_ITEMS);
 	if(dev->scan_blocks == 0) dev->scan_blocks = 1;
 	CREATE_TRY(cudaMalloc(&dev->scan_state, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long)));
@@ -453,14 +486,14 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(dev->copy_stream) cudaStreamSynchronize(dev->copy_stream);
 	if(dev->xchg_stream) cudaStreamSynchronize(dev->xchg_stream);
 	for(int i = 0; i < dev->ipc_opened_count; ++i) cudaIpcCloseMemHandle(dev->ipc_opened[i]);
-	void *ptrs[] = { dev->fb_pair[0], dev->fb_pair[1], dev->tile_min, dev->bin_count, dev->bin_offset, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade, dev->big_queue, dev->huge_queue,
-		             dev->scan_state, dev->ctr, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather, dev->p2p_color[0], dev->p2p_color[1], dev->p2p_flags };
+	void *ptrs[] = { dev->fb_pair[0], dev->fb_pair[1], dev->tile_min, dev->bin_count, dev->bin_offset, dev->bin_touch, dev->scan_state, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade,
+		             dev->ctr, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather, dev->p2p_color[0], dev->p2p_color[1], dev->p2p_flags };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
 	for(cudaEvent_t e : dev->ev_front_join)
 		if(e) cudaEventDestroy(e);
 	for(DrawCtx &c : dev->ctxs) {
-		for(void *p : { (void *)c.tri_bounds, (void *)c.clip_queue, (void *)c.ovf_cov, (void *)c.ovf_shade, (void *)c.vcache, (void *)c.chunk_live, (void *)c.dctr, (void *)c.stat_stripes })
+		for(void *p : { (void *)c.tri_bounds, (void *)c.big_queue, (void *)c.huge_queue, (void *)c.clip_queue, (void *)c.ovf_cov, (void *)c.ovf_shade, (void *)c.vcache, (void *)c.chunk_live, (void *)c.dctr, (void *)c.stat_stripes })
 			if(p) cudaFree(p);
 		if(c.front_done) cudaEventDestroy(c.front_done);
 		if(c.free_ev) cudaEventDestroy(c.free_ev);
@@ -971,19 +1004,13 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	dev->draw_seq++;
 
 	// ---- arenas shared by all draws (used by the back half / tile kernels, which run one draw at a time)
-	if(T > dev->tri_capacity || need_slots > dev->queue_capacity || (debug && (need_slots > dev->dbg_tri_capacity || count > dev->dbg_vertex_capacity || !dev->dbg.infos))) {
+	if(T > dev->tri_capacity || (debug && (need_slots > dev->dbg_tri_capacity || count > dev->dbg_vertex_capacity || !dev->dbg.infos))) {
 		CUDA_TRY(quiesce(dev));
 		if(T > dev->tri_capacity) {
 			const uint32_t cap = T + T / 4;
 			CUDA_TRY(regrow(&dev->tri_cov, (size_t)cap * MLV_TRI_COV_U4));
 			CUDA_TRY(regrow(&dev->tri_shade, (size_t)cap * MLV_TRI_SHADE_U4));
 			dev->tri_capacity = cap;
-		}
-		if(need_slots > dev->queue_capacity) {
-			const uint32_t cap = need_slots + need_slots / 4;
-			CUDA_TRY(regrow(&dev->big_queue, (size_t)cap));
-			CUDA_TRY(regrow(&dev->huge_queue, (size_t)cap));
-			dev->queue_capacity = cap;
 		}
 		if(debug) {
 			if(need_slots > dev->dbg_tri_capacity) {
@@ -1018,6 +1045,8 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 			if(need_slots > c->slot_capacity) {
 				const uint32_t cap = need_slots + need_slots / 4;
 				CUDA_TRY(regrow(&c->tri_bounds, (size_t)cap));
+				CUDA_TRY(regrow(&c->big_queue, (size_t)cap));
+				CUDA_TRY(regrow(&c->huge_queue, (size_t)cap));
 				c->slot_capacity = cap;
 			}
 			if(T > c->queue_capacity) {
@@ -1106,9 +1135,10 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	gp.ovf_shade = ctx->ovf_shade;
 	gp.dctr = ctx->dctr;
 	gp.clip_queue = ctx->clip_queue;
-	gp.big_queue = dev->big_queue;
-	gp.huge_queue = dev->huge_queue;
+	gp.big_queue = ctx->big_queue;
+	gp.huge_queue = ctx->huge_queue;
 	gp.bin_count = dev->bin_count;
+	gp.bin_touch = dev->bin_touch;
 	gp.tile_min = dev->tile_min;
 	gp.keep_all = debug;
 	if(debug) gp.dbg = dev->dbg;
@@ -1179,93 +1209,64 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	}
 	if(int rc = check_launch(dev, "k_back")) return rc;
 
-	BinParams bp;
-	memset(&bp, 0, sizeof(bp));
-	bp.tri_bounds = ctx->tri_bounds;
-	bp.dctr = ctx->dctr;
-	bp.big_queue = dev->big_queue;
-	bp.huge_queue = dev->huge_queue;
-	bp.chunk_live = gp.chunk_live;
-	bp.tile_min = dev->tile_min;
-	bp.bin_count = dev->bin_count;
-	bp.bin_offset = dev->bin_offset;
-	bp.pair_ids = dev->pair_ids;
-	bp.ctr = dev->ctr;
-	bp.stat_stripes = ctx->stat_stripes;
-	bp.direct_slots = T;
-	bp.ovf_capacity = ovf_cap;
-	bp.num_bins = dev->num_bins;
-	bp.wt = dev->wt;
-	bp.ht = dev->ht;
-	bp.part = dev->part;
-	bp.keep_all = debug;
-	uint32_t big_blocks = (T + 7u) / 8u; // one warp per queued triangle, grid-stride
-	if(big_blocks > dev->sm_count * 4u) big_blocks = dev->sm_count * 4u;
-	prof_pre(dev, MLV_STAGE_BIN_COUNT);
-	launch_pdl(k_bin_big, big_blocks, 256, dev->stream, bp);
-	if(int rc = check_launch(dev, "k_bin_big")) return rc;
-
-	ScanParams sp;
-	memset(&sp, 0, sizeof(sp));
-	sp.bin_count = dev->bin_count;
-	sp.bin_offset = dev->bin_offset;
-	sp.cbins = dev->cbins;
-	sp.ctr = dev->ctr;
-	sp.dctr = ctx->dctr;
-	sp.state_sum = dev->scan_state;
-	sp.state_nz = dev->scan_state + dev->scan_blocks;
-	sp.tile_min = dev->tile_min;
-	sp.bin_begin = dev->bin_begin;
-	sp.bin_end = dev->bin_end;
-	sp.pair_capacity = (uint32_t)dev->pair_capacity;
-	sp.ovf_capacity = ovf_cap;
-	sp.num_blocks = dev->scan_blocks;
-	prof_pre(dev, MLV_STAGE_BIN_SCAN);
-	launch_pdl(k_bin_scan, dev->scan_blocks, MLV_SCAN_THREADS, dev->stream, sp);
-	if(int rc = check_launch(dev, "k_bin_scan")) return rc;
-
-	uint32_t bin_blocks = (need_slots + 255u) / 256u;
-	if(bin_blocks > dev->sm_count * 16u) bin_blocks = dev->sm_count * 16u;
-	prof_pre(dev, MLV_STAGE_BIN_FILL);
-	launch_pdl(k_bin_fill, bin_blocks, 256, dev->stream, bp, (uint32_t)dev->pair_capacity);
-	if(int rc = check_launch(dev, "k_bin_fill")) return rc;
-
-	TileParams tp;
+	TailParams tp;
 	memset(&tp, 0, sizeof(tp));
-	tp.cbins = dev->cbins;
+	tp.tri_bounds = ctx->tri_bounds;
+	tp.dctr = ctx->dctr;
+	tp.big_queue = ctx->big_queue;
+	tp.huge_queue = ctx->huge_queue;
+	tp.chunk_live = gp.chunk_live;
+	tp.tile_min = dev->tile_min;
+	tp.bin_count = dev->bin_count;
+	tp.bin_touch = dev->bin_touch;
+	tp.bin_offset = dev->bin_offset;
 	tp.pair_ids = dev->pair_ids;
 	tp.pair_tmp = dev->pair_tmp;
+	tp.cbins = dev->cbins;
+	tp.state_sum = dev->scan_state;
+	tp.state_nz = dev->scan_state + dev->scan_blocks;
+	tp.scan_blocks = dev->scan_blocks;
+	tp.ctr = dev->ctr;
+	tp.stat_stripes = ctx->stat_stripes;
+	tp.direct_slots = T;
+	tp.ovf_capacity = ovf_cap;
+	tp.pair_capacity = (uint32_t)dev->pair_capacity;
+	tp.num_bins = dev->num_bins;
+	tp.bin_begin = dev->bin_begin;
+	tp.bin_end = dev->bin_end;
+	tp.wt = dev->wt;
+	tp.ht = dev->ht;
+	tp.part = dev->part;
+	tp.keep_all = debug;
+	tp.sort_lists = debug;
 	tp.tri_cov = dev->tri_cov;
 	tp.tri_shade = dev->tri_shade;
 	tp.ovf_cov = ctx->ovf_cov;
 	tp.ovf_shade = ctx->ovf_shade;
-	tp.tri_bounds = ctx->tri_bounds;
-	tp.dctr = ctx->dctr;
 	tp.fb = dev->fb;
-	tp.tile_min = dev->tile_min;
-	tp.ctr = dev->ctr;
-	tp.stat_stripes = ctx->stat_stripes;
 	tp.ps_tex = tex_desc(dev->ps_srv[0]);
 	tp.rsqrt_lut = dev->rsqrt_lut;
 	if(debug) tp.dbg = dev->dbg;
-	tp.scan_state = dev->scan_state;
-	tp.scan_words = dev->scan_blocks * 2u;
-	tp.direct_slots = T;
 	tp.index_count = count;
 	tp.key_bits = 3u;
 	while(tp.key_bits < 32u && (T >> (tp.key_bits - 3u)) != 0u) tp.key_bits++;
-	tp.wt = dev->wt;
-	tp.sort_lists = debug;
+	prof_pre(dev, MLV_STAGE_BIN_SCAN);
+	launch_pdl(k_bin_scan, dev->scan_blocks, MLV_SCAN_THREADS, dev->stream, tp);
+	if(int rc = check_launch(dev, "k_bin_scan")) return rc;
+	uint32_t fill_blocks = (need_slots + 255u) / 256u;
+	if(fill_blocks > dev->sm_count * 6u) fill_blocks = dev->sm_count * 6u; // persistent: what is resident at once (40 registers)
+	prof_pre(dev, MLV_STAGE_BIN_FILL);
+	launch_pdl(k_fill, fill_blocks, 256, dev->stream, tp);
+	if(int rc = check_launch(dev, "k_fill")) return rc;
 	uint32_t tile_blocks = (dev->num_bins + 7u) / 8u;
-	if(tile_blocks > dev->sm_count * 8u) tile_blocks = dev->sm_count * 8u;
-	const uint32_t pcap = (uint32_t)dev->pair_capacity;
+	if(tile_blocks > dev->sm_count * 4u) tile_blocks = dev->sm_count * 4u; // persistent: what is resident at once (__launch_bounds__(256, 4))
 	prof_pre(dev, MLV_STAGE_TILE);
 	g_pdl = dev->knob_no_pdl_tile ? 0 : 1;
 	switch(dev->ps_id) {
-		case MLV_PS_PASSTHROUGH: launch_pdl(k_tile<0>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap, ovf_cap); break;
-		case MLV_PS_BASIC: launch_pdl(k_tile<1>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap, ovf_cap); break;
-		case MLV_PS_BASIC_TRILINEAR: launch_pdl(k_tile<MLV_PS_ID_BASIC_TRILINEAR>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap, ovf_cap); break;
-		default: launch_pdl(k_tile<2>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp, pcap, ovf_cap); break;
+		case MLV_PS_PASSTHROUGH: launch_pdl(k_tile<0>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp); break;
+		case MLV_PS_BASIC: launch_pdl(k_tile<1>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp); break;
+		case MLV_PS_BASIC_TRILINEAR: launch_pdl(k_tile<MLV_PS_ID_BASIC_TRILINEAR>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp); break;
+		default: launch_pdl(k_tile<2>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp); break;
 	}
 	g_pdl = 1;
 	if(int rc = check_launch(dev, "k_tile")) return rc;
@@ -1738,7 +1739,7 @@ int mlv_composite_broadcast_async(mlv_device *dev) {
 		CUDA_TRY(cudaEventRecord(dev->ev_fb_free[dev->fb_sel], dev->xchg_stream));
 	}
 	dev->fb_busy[dev->fb_sel] = true;
-	launch_pdl(k_composite_wait, 1, 32, dev->xchg_stream, (const uint32_t *)dev->p2p_flags, n, seq, dev->ctr, 10000000000ull);
+	wait_flags_on_stream(dev, dev->xchg_stream, seq);
 	CUDA_TRY(cudaEventRecord(dev->ev_xchg_done, dev->xchg_stream));
 	cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return fail(MLV_ERR_CUDA, "launch of k_composite_broadcast/k_composite_wait failed: %s", cudaGetErrorString(e));
@@ -1777,7 +1778,7 @@ int mlv_composite_wait(mlv_device *dev) {
 	if(int rc = use_device(dev)) return rc;
 	if(!dev->bcast_pending) return fail(MLV_ERR_STATE, "no broadcast to wait for");
 	prof_pre(dev, MLV_STAGE_COMPOSITE);
-	launch_pdl(k_composite_wait, 1, 32, dev->stream, (const uint32_t *)dev->p2p_flags, dev->part.num_ranks, dev->p2p_seq, dev->ctr, 10000000000ull);
+	wait_flags_on_stream(dev, dev->stream, dev->p2p_seq);
 	dev->bcast_pending = false;
 	dev->present_color = dev->p2p_color[dev->p2p_seq & 1u];
 	return check_launch(dev, "k_composite_wait");
@@ -1799,6 +1800,33 @@ int mlv_debug_read_vs_out(mlv_device *dev, float *out12_per_vertex, uint32_t *ou
 	if(int rc = debug_counters(dev, &c)) return rc;
 	if(out_vertex_count) *out_vertex_count = dev->last_index_count;
 	if(out12_per_vertex && dev->last_index_count) CUDA_TRY(cudaMemcpy(out12_per_vertex, dev->dbg.vs_out, (size_t)dev->last_index_count * 48, cudaMemcpyDeviceToHost));
+	return MLV_OK;
+}
+
+// The per-tile lists of the last draw, marshalled into the reference's layout: bins in ascending bin index, every list
+// segment placed where the reference's exclusive scan (main.c:937-942) puts it. On the device the segments lie in
+// allocation order (k_fill) and the work list is unordered.
+static int read_sorted_lists(mlv_device *dev, const Counters &c, std::vector<uint32_t> &slots, std::vector<mlv_ref_compacted_bin> &bins, std::vector<uint32_t> *src = nullptr) {
+	slots.clear();
+	bins.clear();
+	if(src) src->clear();
+	if(dev->last_index_count == 0 || c.last_pair_total == 0xffffffffu) return MLV_OK;
+	const uint32_t pairs = c.last_pair_total, nb = c.last_n_cbins;
+	std::vector<uint32_t> raw(pairs);
+	std::vector<mlv_ref_compacted_bin> cb(nb);
+	if(pairs) CUDA_TRY(cudaMemcpy(raw.data(), dev->pair_ids, (size_t)pairs * 4, cudaMemcpyDeviceToHost));
+	if(nb) CUDA_TRY(cudaMemcpy(cb.data(), dev->cbins, (size_t)nb * sizeof(mlv_ref_compacted_bin), cudaMemcpyDeviceToHost));
+	std::sort(cb.begin(), cb.end(), [](const mlv_ref_compacted_bin &a, const mlv_ref_compacted_bin &b) { return a.bin_index < b.bin_index; });
+	slots.reserve(pairs);
+	for(mlv_ref_compacted_bin &b : cb) {
+		const uint32_t base = b.num_triangles_upto;
+		b.num_triangles_upto = (uint32_t)slots.size();
+		for(uint32_t k = 0; k < b.num_triangles_self; ++k) {
+			slots.push_back(base + k < pairs ? raw[base + k] : 0xffffffffu);
+			if(src) src->push_back(base + k);
+		}
+	}
+	bins.swap(cb);
 	return MLV_OK;
 }
 
@@ -1860,31 +1888,40 @@ int mlv_debug_read_triangles(mlv_device *dev, mlv_ref_triangle *tris, float *att
 int mlv_debug_read_bins(mlv_device *dev, uint32_t *triangle_ids, uint32_t *out_pair_count, mlv_ref_compacted_bin *bins, uint32_t *out_bin_count) {
 	Counters c;
 	if(int rc = debug_counters(dev, &c)) return rc;
-	const bool skipped = c.pair_total > dev->pair_capacity || dev->last_index_count == 0;
-	const uint32_t pairs = skipped ? 0u : c.pair_total, nb = skipped ? 0u : c.n_cbins;
+	std::vector<uint32_t> slots;
+	std::vector<mlv_ref_compacted_bin> cb;
+	if(int rc = read_sorted_lists(dev, c, slots, cb)) return rc;
+	const uint32_t pairs = (uint32_t)slots.size(), nb = (uint32_t)cb.size();
 	if(out_pair_count) *out_pair_count = pairs;
 	if(out_bin_count) *out_bin_count = nb;
 	if(triangle_ids && pairs) {
 		DebugMap m;
 		if(int rc = build_debug_map(dev, c, m)) return rc;
-		CUDA_TRY(cudaMemcpy(triangle_ids, dev->pair_ids, (size_t)pairs * 4, cudaMemcpyDeviceToHost)); // the lists hold slots
-		for(uint32_t i = 0; i < pairs; ++i) triangle_ids[i] = triangle_ids[i] < m.slot_rank.size() ? m.slot_rank[triangle_ids[i]] : 0xffffffffu;
+		for(uint32_t i = 0; i < pairs; ++i) triangle_ids[i] = slots[i] < m.slot_rank.size() ? m.slot_rank[slots[i]] : 0xffffffffu; // the lists hold slots
 	}
-	if(bins && nb) CUDA_TRY(cudaMemcpy(bins, dev->cbins, (size_t)nb * sizeof(mlv_ref_compacted_bin), cudaMemcpyDeviceToHost));
+	if(bins && nb) memcpy(bins, cb.data(), (size_t)nb * sizeof(mlv_ref_compacted_bin));
 	return MLV_OK;
 }
 
 int mlv_debug_read_masks(mlv_device *dev, mlv_ref_tile_info *infos, uint32_t *out_pair_count) {
 	Counters c;
 	if(int rc = debug_counters(dev, &c)) return rc;
-	const bool skipped = c.pair_total > dev->pair_capacity || dev->last_index_count == 0;
-	const uint32_t pairs = skipped ? 0u : c.pair_total;
+	std::vector<uint32_t> slots;
+	std::vector<mlv_ref_compacted_bin> cb;
+	std::vector<uint32_t> src; // position of every marshalled pair in the device arrays
+	if(int rc = read_sorted_lists(dev, c, slots, cb, &src)) return rc;
+	const uint32_t pairs = (uint32_t)slots.size();
 	if(out_pair_count) *out_pair_count = pairs;
 	if(infos && pairs) {
 		DebugMap m;
 		if(int rc = build_debug_map(dev, c, m)) return rc;
-		CUDA_TRY(cudaMemcpy(infos, dev->dbg.infos, (size_t)pairs * sizeof(mlv_ref_tile_info), cudaMemcpyDeviceToHost));
-		for(uint32_t i = 0; i < pairs; ++i) infos[i].triangle_id = m.rank(infos[i].triangle_id);
+		const uint32_t raw_pairs = c.last_pair_total;
+		std::vector<mlv_ref_tile_info> raw(raw_pairs);
+		CUDA_TRY(cudaMemcpy(raw.data(), dev->dbg.infos, (size_t)raw_pairs * sizeof(mlv_ref_tile_info), cudaMemcpyDeviceToHost));
+		for(uint32_t i = 0; i < pairs; ++i) {
+			infos[i] = raw[src[i]];
+			infos[i].triangle_id = m.rank(infos[i].triangle_id);
+		}
 	}
 	return MLV_OK;
 }
@@ -1913,21 +1950,19 @@ int mlv_read_bin_lists(mlv_device *dev, uint32_t *keys, uint32_t *out_pair_count
 	Counters c;
 	CUDA_TRY(cudaMemcpyAsync(&c, dev->ctr, sizeof(c), cudaMemcpyDeviceToHost, dev->stream));
 	CUDA_TRY(cudaStreamSynchronize(dev->stream));
-	const bool skipped = c.pair_total > dev->pair_capacity || dev->last_index_count == 0;
-	const uint32_t pairs = skipped ? 0u : c.pair_total, nb = skipped ? 0u : c.n_cbins;
+	std::vector<uint32_t> slots;
+	std::vector<mlv_ref_compacted_bin> cb;
+	if(int rc = read_sorted_lists(dev, c, slots, cb)) return rc;
+	const uint32_t pairs = (uint32_t)slots.size(), nb = (uint32_t)cb.size();
 	if(out_pair_count) *out_pair_count = pairs;
 	if(out_bin_count) *out_bin_count = nb;
-	if(keys && pairs) {
-		CUDA_TRY(cudaMemcpy(keys, dev->pair_ids, (size_t)pairs * 4, cudaMemcpyDeviceToHost)); // slots: direct slot t has key t << 3,
-		const uint32_t T = dev->last_direct_slots, n_ovf = c.last_ovf_count;                      // an overflow slot's key is word 3 of its bounds entry
+	if(keys && pairs) { // slots -> keys: direct slot t has key t << 3, an overflow slot's key is word 3 of its bounds entry
+		const uint32_t T = dev->last_direct_slots, n_ovf = c.last_ovf_count;
 		std::vector<uint4> ovf(n_ovf);
 		if(n_ovf && dev->last_ctx) CUDA_TRY(cudaMemcpy(ovf.data(), dev->last_ctx->tri_bounds + T, (size_t)n_ovf * sizeof(uint4), cudaMemcpyDeviceToHost));
-		for(uint32_t i = 0; i < pairs; ++i) {
-			const uint32_t slot = keys[i];
-			keys[i] = slot < T ? (slot << 3) : (slot - T < n_ovf ? ovf[slot - T].w : 0xffffffffu);
-		}
+		for(uint32_t i = 0; i < pairs; ++i) keys[i] = slots[i] < T ? (slots[i] << 3) : (slots[i] - T < n_ovf ? ovf[slots[i] - T].w : 0xffffffffu);
 	}
-	if(bins && nb) CUDA_TRY(cudaMemcpy(bins, dev->cbins, (size_t)nb * sizeof(mlv_ref_compacted_bin), cudaMemcpyDeviceToHost));
+	if(bins && nb) memcpy(bins, cb.data(), (size_t)nb * sizeof(mlv_ref_compacted_bin));
 	return check_flags(dev, c);
 }
 

@@ -32,7 +32,6 @@ namespace mlv {
 
 #define MLV_NO_WINNER 0xffffffffu
 #define MLV_STAT_STRIPES 64u
-#define MLV_TOUCHED 0x80000000u          /* bin_count flag: bin is non-empty in the reference's sense but (so far) holds only Hi-Z-rejected pairs */
 #define MLV_TILE_MIN_CLEARED 0x80000000u /* tile_min bit pattern (-0.0f) the depth clear writes: equals 0.0 in every comparison, marks "never refreshed" */
 
 enum { MLV_FLAG_TRI_OVERFLOW = 1u, MLV_FLAG_PAIR_OVERFLOW = 2u, MLV_FLAG_COMPOSITE_TIMEOUT = 4u };
@@ -41,7 +40,8 @@ enum { MLV_FLAG_TRI_OVERFLOW = 1u, MLV_FLAG_PAIR_OVERFLOW = 2u, MLV_FLAG_COMPOSI
 struct DrawCounters {
 	uint32_t clip_count; // input triangles queued for k_front_clip
 	uint32_t ovf_count;  // overflow slots taken by the fan triangles of clipped input triangles (may exceed the capacity: the draw is skipped)
-	uint32_t pad[2];
+	uint32_t big_count;  // slots whose tile rectangle holds 9 .. MLV_HUGE_TILES tiles (counted by a warp each in the back half)
+	uint32_t huge_count; // ... more than MLV_HUGE_TILES tiles (counted by the whole grid)
 };
 
 struct Counters {
@@ -49,17 +49,20 @@ struct Counters {
 	uint32_t pair_total;  // (triangle,tile) pairs of the current draw
 	uint32_t n_cbins;     // non-empty bins of the current draw (0 if the pair arena overflowed)
 	uint32_t error_flags; // sticky MLV_FLAG_*
-	uint32_t ticket;      // block ticket of the current draw's look-back scan (reset by k_tile)
+	uint32_t ticket;      // block ticket of the current draw's look-back scan (reset at the end of the draw)
 	uint32_t draw_tris;   // assembled triangles of the current draw
 	uint32_t last_ovf_count; // ovf_count of the last finished draw (debug read-back)
 	uint32_t reserved1;
-	uint32_t big_count;   // triangles queued for k_bin_big in the current draw (reset by k_tile)
+	uint32_t draw_alive;  // a pair of the current draw survived Hi-Z (set by the back half): the scan, the fill pass and k_tile have work
 	uint32_t draw_pairs_all;   // (triangle,tile) pairs of the current draw including Hi-Z-rejected ones (Stats)
-	uint32_t draw_active_bins; // non-empty bins of the current draw in the reference's sense (Stats)
-	uint32_t huge_count;  // triangles with more than MLV_HUGE_TILES tiles in the current draw (reset by k_tile)
+	uint32_t draw_active_bins; // bins the current draw touched (counted by its k_tile)
+	uint32_t reserved2;
 	uint32_t bcast_done;  // CTAs of k_composite_broadcast that have finished their stores (reset by the last one)
-	uint32_t epoch;       // draw epoch tagging the scan's look-back words (advanced by k_tile; never 0)
-	uint32_t pad[2];
+	uint32_t epoch;       // draw epoch tagging this draw's touches in bin_touch (advanced at the end of every draw; never 0)
+	uint32_t n_wake;      // entries of wake_bins in the current draw
+	uint32_t last_pair_total, last_n_cbins; // pair_total / n_cbins of the last finished draw (read-backs); pair_total 0xffffffff: it was skipped
+	uint32_t pad[3];
+	unsigned long long tile_done; // low word: CTAs of the current k_tile that have finished (the last one folds the draw's Stats); high word: bins they counted as touched
 	mlv_stats stats;      // accumulated like reference main.c:1228-1246
 	mlv_work_counters work; // what the kernels really processed (Hi-Z at binning time removes work the reference's Stats still count)
 };
@@ -141,6 +144,7 @@ struct GeomParams {
 	uint32_t *big_queue;
 	uint32_t *huge_queue;
 	uint32_t *bin_count;
+	uint32_t *bin_touch;
 	const float *tile_min;
 	bool keep_all; // debug capture: no Hi-Z at binning time, lists hold every pair like the reference's
 	DebugOut dbg;
@@ -150,64 +154,45 @@ struct GeomParams {
 	uint32_t draw_ordinal; // position of the draw inside a recorded command list (identifies the kernel nodes whose constants are updated)
 };
 
-struct BinParams {
-	const uint4 *tri_bounds;
-	const DrawCounters *dctr;
+// Everything the tail kernel of a draw needs (scan | fill | tile).
+struct TailParams {
+	// binning
+	const uint4 *tri_bounds;   // the draw context's bounds (word 3 of an overflow slot's entry is its key)
+	DrawCounters *dctr;        // re-armed at the end of the draw
 	const uint32_t *big_queue;
 	const uint32_t *huge_queue;
 	const uint8_t *chunk_live;
-	const float *tile_min;
-	uint32_t *bin_count;
-	uint32_t *bin_offset;
+	float *tile_min;
+	uint32_t *bin_count;       // surviving pairs per bin (zero outside a draw's back half .. scan)
+	uint32_t *bin_touch;       // epoch of the draw that touched the bin last
+	uint32_t *bin_offset;      // start of the bin's list (the scan), then the running fill position (k_fill)
+	unsigned long long *state_sum, *state_nz; // look-back words of the scan, tagged with the draw epoch
+	uint32_t scan_blocks;
 	uint32_t *pair_ids;
+	uint32_t *pair_tmp;
+	mlv_ref_compacted_bin *cbins;
 	Counters *ctr;
 	unsigned long long *stat_stripes;
-	uint32_t direct_slots; // T
+	uint32_t direct_slots;     // T
 	uint32_t ovf_capacity;
+	uint32_t pair_capacity;
 	uint32_t num_bins;
+	uint32_t bin_begin, bin_end; // this rank's bins (the whole render target unless it owns one contiguous band)
 	int wt, ht;
 	Partition part;
 	bool keep_all;
-};
-
-struct ScanParams {
-	uint32_t *bin_count;
-	uint32_t *bin_offset;
-	mlv_ref_compacted_bin *cbins;
-	Counters *ctr;
-	const DrawCounters *dctr;
-	unsigned long long *state_sum, *state_nz;
-	const float *tile_min;
-	uint32_t bin_begin, bin_end; // this rank's bins (the whole render target unless it owns one contiguous band)
-	uint32_t pair_capacity;
-	uint32_t ovf_capacity;
-	uint32_t num_blocks;
-};
-
-struct TileParams {
-	const mlv_ref_compacted_bin *cbins;
-	uint32_t *pair_ids;
-	uint32_t *pair_tmp;
+	bool sort_lists;           // debug capture: restore ascending-key order inside every bin list
+	// tile phase
 	const uint4 *tri_cov;
 	const uint4 *tri_shade;
-	const uint4 *ovf_cov;    // records of the slots >= direct_slots
+	const uint4 *ovf_cov;      // records of the slots >= direct_slots
 	const uint4 *ovf_shade;
-	const uint4 *tri_bounds; // word 3 of an overflow slot's entry is its key
-	DrawCounters *dctr;      // re-armed at the end of the draw
 	uint4 *fb;
-	float *tile_min;
-	Counters *ctr;
-	unsigned long long *stat_stripes;
 	TexDesc ps_tex;
 	const uint32_t *rsqrt_lut;
 	DebugOut dbg;
-	unsigned long long *scan_state; // look-back words of k_bin_scan (cleared when the epoch wraps)
-	uint32_t scan_words;
-	uint32_t direct_slots; // T
-	uint32_t index_count;  // Stats (main.c:1228-1232)
+	uint32_t index_count;      // Stats (main.c:1228-1232)
 	uint32_t key_bits;
-	int wt;
-	bool sort_lists; // debug capture: restore ascending-key order inside every bin list
 };
 
 } // namespace mlv

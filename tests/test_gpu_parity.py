@@ -617,7 +617,7 @@ def test_no_cpu_fallback_and_kernels_launch():
         n0 = dev.kernel_launch_count
         scenes.render(dev, sc)
         dev.present()
-        assert dev.kernel_launch_count - n0 == 1 + 8 + 1  # fused clear + (vertex cache, front, front clip, back, big-count, scan, fill, tile) + resolve
+        assert dev.kernel_launch_count - n0 == 1 + 7 + 1  # fused clear + (vertex cache, front, front clip, back, scan, fill, tile) + resolve
 
 
 # ---- production path (no debug capture): the kernels bench.py times --------------------------------------------------
