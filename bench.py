@@ -2,7 +2,7 @@
 """bench.py -- frames/s of the draw pipeline (clear -> draw_indexed x N -> framebuffer) on 1..8 B200.
 
 A "step" is ONE FRAME of the workload: colour+depth clear, every draw_indexed of the scene, resolve to
-the row-major framebuffer (+ sort-first composite over NCCL when --gpus > 1).
+the row-major framebuffer (+ sort-first composite over NVLink when --gpus > 1).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config 5]        # this repo's CUDA path
   python bench.py --impl reference ...                                    # the reference's own CPU pipeline (oracle/_ref)
@@ -12,8 +12,11 @@ Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for how every field i
 from __future__ import annotations
 
 import argparse
+import csv
+import hashlib
 import json
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -37,7 +40,7 @@ def load_peaks():
 
 
 def algorithmic_bytes(scene, stats, num_draws):
-    """SURVEY.md 8d per-unit table -> bytes per frame, split per stage."""
+    """SURVEY.md 8d per-unit table -> bytes per frame of the REFERENCE algorithm, split per stage."""
     px = scene.width * scene.height
     bins = (scene.width // 8) * (scene.height // 8)
     idx = sum(o.index_count for o in scene.objects)
@@ -106,9 +109,32 @@ def build_scene(config: int):
     return scenes.CONFIGS[config]()
 
 
-def workload_name(config: int, scene) -> str:
-    return {1: "config1 TOON", 2: "config2 FTM", 3: "config3 EMILY(stand-in sphere)+fullscreen radiance", 4: "config4 LOCOMOTIVE(stand-in torus knot)",
-            5: "config5 synthetic 10M-triangle grid, 8 draws"}[config] + f" {scene.width}x{scene.height}"
+WORKLOADS = {1: "config1 TOON", 2: "config2 FTM", 3: "config3 EMILY(stand-in sphere)+fullscreen radiance", 4: "config4 LOCOMOTIVE(stand-in torus knot)",
+             5: "config5 synthetic 10M-triangle grid, 8 draws"}
+GOLDEN_KEYS = {1: "config1_toon_1280x720", 2: "config2_ftm_1920x1080", 3: "config3_emily_1920x1080", 4: "config4_locomotive_3840x2160", 5: "config5_synthetic_3840x2160"}
+
+
+def workload_config(config: int, scene) -> dict:
+    """The `config` object: identical for this repo's arm and the reference arm (what was rendered, nothing derived)."""
+    return {"workload": f"{WORKLOADS[config]} {scene.width}x{scene.height}", "input_triangles": scene.input_triangles, "draws": len(scene.objects),
+            "width": scene.width, "height": scene.height}
+
+
+def golden_hashes(config: int) -> dict:
+    """Committed frame hashes of the workload: the reference's depth image (tests/golden/golden.json, made from oracle/_ref) and
+    this repo's own colour image (tests/golden/gpu_frames.json: written on a GPU box by tools/make_gpu_golden.py only after
+    the frame passed the colour tolerance against the live reference; colour is <= 1/255, not bit-exact, so the reference's
+    own colour hash cannot be matched)."""
+    out = {"depth_fnv": None, "color_fnv": None}
+    try:
+        out["depth_fnv"] = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))[GOLDEN_KEYS[config]]["depth_fnv"]
+    except Exception:
+        pass
+    try:
+        out["color_fnv"] = json.load(open(os.path.join(ROOT, "tests", "golden", "gpu_frames.json")))[GOLDEN_KEYS[config]]["color_fnv"]
+    except Exception:
+        pass
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -119,8 +145,7 @@ def run_reference(args, rank: int):
     from oracle.ref_oracle import RefOracle, have
     scene = build_scene(args.config)
     base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, scene), "input_triangles": scene.input_triangles, "draws": len(scene.objects)}}
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic", "config": workload_config(args.config, scene)}
     if not have(scene.width, scene.height):
         base["unavailable"] = f"oracle/_ref/libmalevich_ref_{scene.width}x{scene.height}.so not built (needs /root/reference at build time)"
         print(json.dumps(base), flush=True)
@@ -158,48 +183,86 @@ def cpu_baseline_sample(scene, frames: int = 2):
             "sample": f"best of {frames} full frames (after 1 warm-up) of the same workload on the host cores, reference render() compiled from its own sources"}
 
 
+def measure_traffic(config: int, kernel: str, timeout_s: int = 150):
+    """DRAM bytes per launch of `kernel` (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the launches of ONE frame
+    of the workload on one GPU), measured now by a child process under ncu. Never a timing: only byte counters are read.
+    Returns (bytes_per_launch or None, how)."""
+    ncu = shutil.which("ncu")
+    if ncu is None:
+        return None, "ncu not on PATH"
+    with tempfile.TemporaryDirectory() as tmp:
+        log = os.path.join(tmp, "traffic.csv")
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", f"regex:^{kernel}", "--csv", "--log-file", log,
+               sys.executable, os.path.join(ROOT, "tools", "profile_rank.py"), "1", "0", "2", str(config)]
+        try:
+            r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout_s)
+            if r.returncode != 0 or not os.path.exists(log):
+                return None, f"ncu exit code {r.returncode}"
+            lines = open(log).read().splitlines()
+            start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
+            rows = list(csv.reader(lines[start:]))
+            h = rows[0]
+            idi, vi = h.index("ID"), h.index("Metric Value")
+            per = {}
+            for row in rows[1:]:
+                if len(row) > vi:
+                    per[row[idi]] = per.get(row[idi], 0.0) + float(row[vi].replace(",", "") or 0)
+            ids = sorted(per, key=int)
+            if not ids:
+                return None, "no launch of the kernel captured"
+            frame = ids[len(ids) // 2:]  # the child renders two frames: the second one (warm arenas)
+            return sum(per[i] for i in frame) / len(frame), f"ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the {len(frame)} launches of one frame (child process, measured in this run)"
+        except Exception as e:  # noqa: BLE001
+            return None, f"ncu capture failed: {type(e).__name__}"
+
+
+def kernels_source_hash() -> str:
+    h = hashlib.sha256()
+    for name in ("kernels.cuh", "shaders.cuh", "mlv_internal.cuh", "malevich_b200.cu"):
+        h.update(open(os.path.join(ROOT, "malevich_b200", "csrc", name), "rb").read())
+    return h.hexdigest()[:16]
+
+
 # ------------------------------------------------------------------------------------------------
 def run_b200(args, rank: int, world: int, local_rank: int):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
-    from malevich_b200 import Device, scenes
+    from malevich_b200 import Device, partition, scenes
+    from malevich_b200 import _lib as L
 
     torch.cuda.set_device(local_rank)
+    cuda_dev = torch.device("cuda", local_rank)
     multi = world > 1
     if multi:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=cuda_dev)
     scene = build_scene(args.config)
+    lib = L.load()
     # sort-first split: by default one contiguous band of tile rows per rank (lets a rank skip geometry chunks outside its band)
     stripe = args.stripe if args.stripe > 0 else max(1, -(-(scene.height // 8) // world))
     dev = Device(scene.width, scene.height, cuda_device=local_rank, num_ranks=world, rank=rank, stripe_height_tiles=stripe)
-    stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local_rank))
-    from malevich_b200 import partition
+    stream = torch.cuda.ExternalStream(dev.stream, device=cuda_dev)
 
-    def shard_bytes(nbytes: int) -> int:  # equal shards of a buffer, 16-byte granules, for the in-place all-gather of sharded uploads
-        return partition.shard_bytes(nbytes, world)
+    class _Raw:  # CUDA array interface over library-owned device memory (no copy)
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
 
-    if multi:  # buffers padded to world x shard so that every rank's shard has the same size
-        from malevich_b200 import _lib as L0
-        for o in scene.objects:
-            for arr, kind in ((o.vertex_buffer, L0.BUFFER_VERTEX), (o.index_buffer, L0.BUFFER_INDEX)):
-                dev.adopt_buffer(arr, kind, shard_bytes(arr.nbytes) * world)
+    def as_tensor(ptr, nbytes):
+        return torch.as_tensor(_Raw(ptr, nbytes), device=cuda_dev)
+
     scenes.upload(dev, scene)
 
-    gather = None
-    if multi:
-        class _Raw:  # CUDA array interface over the library-owned gather buffer (no copy)
-            def __init__(self, ptr, nbytes):
-                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
-        ptr, chunk = dev.composite_layout()
-        gather = torch.as_tensor(_Raw(ptr, chunk * world), device=torch.device("cuda", local_rank))
-        my_chunk = gather[rank * chunk:(rank + 1) * chunk]
-
-    # Exchange step: by default the fused peer-memory composite (each rank resolves its tiles straight into every rank's
-    # image over NVLink, include/malevich_b200.h); --composite nccl keeps pack -> ncclAllGather -> unpack. NCCL is always
-    # the transport for the one-off handle exchange, the barriers and the max/sum reductions of the measurements.
+    # ---- exchange step: by default the asynchronous peer-memory composite (each rank's band travels into every rank's image
+    # over NVLink underneath the next frame, include/malevich_b200.h); --composite nccl keeps pack -> ncclAllGather -> unpack.
+    # NCCL is always the transport for the one-off handle exchange, the barriers and the reductions of the measurements.
     composite = "none"
+    gather = my_chunk = None
     if multi:
         composite = args.composite
+        ptr, chunk = dev.composite_layout()
+        gather = as_tensor(ptr, chunk * world)
+        my_chunk = gather[rank * chunk:(rank + 1) * chunk]
         if composite == "p2p":
             try:
                 mine = torch.frombuffer(bytearray(dev.composite_peer_export()), dtype=torch.uint8).cuda()
@@ -216,18 +279,40 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             if ok.item() == 0:
                 composite = "nccl"
 
-    # p2p: the exchange of frame f runs on the library's exchange stream underneath the drawing of frame f+1 (see
-    # mlv_composite_broadcast_async): frame() draws frame f+1, joins the exchange of frame f and starts that of frame
-    # f+1; drain() joins the last one. Every timed region ends with drain(), so K steps contain K complete exchanges.
-    pending = [False]
+    # ---- the frame, recorded once (D3D11 deferred-context pattern: mlv_begin/finish/execute_command_list). Replaying it is one
+    # CUDA-graph launch; `--immediate` issues the calls one by one instead (what round 1 measured).
+    def record_frame():
+        dev.reset_stats()
+        scenes.render(dev, scene)
+        if not multi:
+            dev.resolve()
+    scenes.render(dev, scene)  # sizes every arena before the recording
+    dev.finish()
+    frame_list = None if args.immediate else dev.record(record_frame)
+    # the same frame without the device-resident resolve: what the end-to-end loops replay (the present resolves and copies
+    # on its own, and a recording that writes the resolved image has to wait for a read-back of that image still in flight)
+    def record_draws():
+        dev.reset_stats()
+        scenes.render(dev, scene)
+    draws_list = None if args.immediate else (frame_list if multi else dev.record(record_draws))
+
+    pending = [False]  # p2p: an exchange has been started and not yet joined
 
     def drain():
         if pending[0]:
             dev.composite_join()
             pending[0] = False
 
+    def render_frame():
+        if frame_list is not None:
+            frame_list.execute()
+        else:
+            record_frame()
+
     def frame():
-        scenes.render(dev, scene)
+        """clear + all draws + resolve (N = 1) / + exchange (N > 1). p2p: the exchange of frame f runs on the library's exchange
+        stream underneath frame f+1; every timed region ends with drain(), so K steps contain K complete exchanges."""
+        render_frame()
         if composite == "p2p":
             drain()
             dev.composite_broadcast_async()
@@ -237,8 +322,6 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(gather, my_chunk)
             dev.composite_unpack()
-        else:
-            dev.resolve()
 
     def barrier():
         drain()
@@ -263,20 +346,35 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return {k: int(v) for k, v in zip(keys, t.tolist())}
 
-    # ---- warm-up, stats of one frame (work counts for the algorithmic-bytes model)
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         frame()
-    dev.finish()
-    dev.reset_stats()
+    barrier()
+    # work counts of one frame (the recording resets Stats at its start, like memset(&stats, 0) in render(), main.c:1268)
     frame()
+    drain()
     stats_local = dev.stats()
     work = reduce_sum_dict(dev.work_counters())  # what the kernels really processed in that frame (Hi-Z at binning time removes the rest)
     # per-rank shares (a triangle is counted by the rank that owns its first tile row); the sum is the reference's Stats
     stats = reduce_sum_dict({k: stats_local[k] for k in ("assembled_triangle_count", "active_bin_count", "total_triangle_count_in_bins")})
 
+    # ---- the frame the timed path renders, hashed (outside every timed region) and compared with the committed frames
+    hashes = None
+    colors = np.empty((scene.height, scene.width), np.uint32)
+    if rank == 0:
+        if multi:
+            colors[...] = as_tensor(dev.resolved_color_ptr(), colors.nbytes).cpu().numpy().view(np.uint32).reshape(colors.shape)
+            depth_fnv = None  # depth is not exchanged between the ranks
+        else:
+            depths = np.empty((scene.height, scene.width), np.float32)
+            dev.present_into(colors, depths)
+            depth_fnv = L.fnv64_words(depths)
+        want = golden_hashes(args.config)
+        hashes = {"color": L.fnv64_words(colors), "depth": depth_fnv, "golden_color": want["color_fnv"], "golden_depth": want["depth_fnv"]}
+    barrier()
+
     # ---- timed region: device-resident inputs, CUDA events on the launching stream, max over ranks
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
     launches0 = dev.kernel_launch_count
@@ -291,144 +389,179 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     clocks = sampler.stop() if rank == 0 else None
     ms = reduce_max(e0.elapsed_time(e1) / args.steps)
 
-    # ---- per-stage kernel times (CUDA events around every launch, same stream)
+    # ---- per-stage kernel times (immediate mode: CUDA events around every launch, all on one stream, nothing overlaps)
     dev.profile_begin()
     for _ in range(args.steps):
-        frame()
-    drain()
+        record_frame()
+        if multi:
+            dev.composite_pack()
     prof = dev.profile_end()
     stage_ms = {k: v[0] / args.steps for k, v in prof.items()}
     stage_launches = {k: v[1] // args.steps for k, v in prof.items()}
 
-    # ---- end to end through the public API with HOST buffers: every frame uploads every vertex/index buffer,
-    # texture and the constant buffer from pinned host memory, renders, and reads the framebuffer back to the host
+    # ---- end to end through the public API with HOST buffers, two ways:
+    # (1) `e2e`: the reference's own frame loop (main.c:1587-1602): geometry and textures are loaded once (init(), main.c:1317-1420),
+    #     every frame update() rewrites the 192-byte PerFrameCB (main.c:1595-1597), render() draws, the frame is presented. Here:
+    #     the constant buffer of every draw is replaced from host memory (mlv_command_list_set_constants), the recorded frame is
+    #     replayed, the framebuffer is read back to pinned host memory.
+    # (2) `e2e_streaming`: a host that streams its geometry -- every vertex and index byte re-uploaded from pinned host memory each
+    #     frame (one vertex slab + one index slab addressed with start index / base vertex; at N > 1 each rank uploads its shard
+    #     over its own PCIe link and an in-place ncclAllGather replicates it over NVLink), plus the same read-back.
+    keep = []
+
     def pinned_like(a: np.ndarray) -> np.ndarray:
         t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
         out = t.numpy().view(a.dtype).reshape(a.shape)
         out[...] = a
-        out_keep.append(t)
+        keep.append(t)
         return out
-    out_keep = []
-    import ctypes as C
-    from malevich_b200 import _lib as L
-    lib = L.load()
-    host_inputs = []
-    h2d = 0
-    for o in scene.objects:
-        for arr, kind in ((o.vertex_buffer, L.BUFFER_VERTEX), (o.index_buffer, L.BUFFER_INDEX)):
-            host_inputs.append((dev._buffer(arr, kind), pinned_like(arr)))
-            h2d += arr.nbytes
-    tex_seen = {}
-    for o in scene.objects:
-        if o.texture is not None and id(o.texture) not in tex_seen:
-            tex_seen[id(o.texture)] = (dev._texture(o.texture), pinned_like(o.texture.p_data))
-    h2d += sum(p.nbytes for _, p in tex_seen.values()) + 192
-    colors_host = pinned_like(np.zeros((scene.height, scene.width), np.uint32))
-    d2h = colors_host.nbytes
+    host_frames = [pinned_like(np.zeros((scene.height, scene.width), np.uint32)) for _ in range(2)]
+    d2h = host_frames[0].nbytes
+    e2e_n = [0]
+    cb_host = np.ascontiguousarray(scene.per_frame_cb, dtype=np.float32)
 
-    colors_host2 = pinned_like(colors_host)
-    e2e_step = [0]
+    def deliver():  # hand the finished frame to the host: double-buffered, the copy of frame f overlaps frame f+1
+        if multi:
+            had = pending[0]
+            drain()  # join the exchange of the previous frame
+            if had and rank == 0:
+                dev.present_wait()
+                dev.composite_readback_async(host_frames[e2e_n[0] % 2])
+                e2e_n[0] += 1
+            dev.composite_broadcast_async()
+            pending[0] = True
+        else:
+            dev.present_wait()
+            dev.present_async(host_frames[e2e_n[0] % 2])
+            e2e_n[0] += 1
 
-    # N > 1: the geometry is replicated, so every byte crosses PCIe ONCE per frame: rank r uploads shard r of every
-    # buffer over its own link, an in-place ncclAllGather on a side stream replicates the shards over NVLink, and the
-    # buffer is marked complete on that stream (draws that bind it wait for exactly that). The composited frame is read
-    # back by rank 0 on the read-back stream, one frame behind (the exchange of frame f overlaps frame f+1).
-    if multi and composite == "p2p":
-        class _RawBuf:
-            def __init__(self, ptr, nbytes):
-                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
-        cuda_dev = torch.device("cuda", local_rank)
+    def flush_e2e():  # deliver the last frame too: K steps = K frames drawn, exchanged and read back
+        if multi:
+            had = pending[0]
+            drain()
+            if had and rank == 0:
+                dev.present_wait()
+                dev.composite_readback_async(host_frames[e2e_n[0] % 2])
+                e2e_n[0] += 1
+        dev.finish()
+
+    def last_delivered():
+        return host_frames[(e2e_n[0] - 1) % 2]
+
+    def frame_e2e_static():
+        if draws_list is not None:
+            draws_list.set_constants(cb_host)  # update(): the camera of this frame
+            draws_list.execute()
+        else:
+            record_draws()  # (the Python mirror sends the constant buffer with every draw)
+        deliver()
+
+    def time_e2e(step):
+        for _ in range(2):
+            step()
+        flush_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        flush_e2e()
+        barrier()
+        return reduce_max((time.perf_counter() - t0) * 1e3 / args.steps)
+
+    e2e_streaming = None
+    if not multi or composite == "p2p":
+        e2e_static_ms = time_e2e(frame_e2e_static)
+        static_ok = bool(np.array_equal(last_delivered(), colors)) if rank == 0 else None
+        e2e = {"value": 1e3 / e2e_static_ms, "unit": UNIT, "ms_per_step": e2e_static_ms, "h2d_bytes_per_step": 192 * len(scene.objects), "d2h_bytes_per_step": int(d2h),
+               "image_matches_resident_path": static_ok,
+               "note": "the reference's frame loop (main.c:1587-1602): geometry and textures resident (loaded once by init()), per frame the PerFrameCB of every draw replaced from host memory "
+                       "(update(), main.c:1595-1597), the recorded frame replayed, the framebuffer read back to pinned host memory (double-buffered: the host collects frame f-1 while frame f is queued"
+                       + ("; rank 0 reads the composited frame)" if multi else ")")}
+
+        # ---- streaming geometry: slabs
+        vtx_counts = [o.vertex_buffer.shape[0] for o in scene.objects]
+        base_vertex = np.concatenate([[0], np.cumsum(vtx_counts)[:-1]]).astype(np.int64)
+        start_index = np.concatenate([[0], np.cumsum([o.index_count for o in scene.objects])[:-1]]).astype(np.int64)
+        vb_slab = pinned_like(np.concatenate([np.ascontiguousarray(o.vertex_buffer, dtype=np.float32) for o in scene.objects]))
+        ib_slab = pinned_like(np.concatenate([np.ascontiguousarray(o.index_buffer, dtype=np.uint32) for o in scene.objects]))
+        slabs = []
+        for arr, kind in ((vb_slab, L.BUFFER_VERTEX), (ib_slab, L.BUFFER_INDEX)):
+            sb = partition.shard_bytes(arr.nbytes, world)
+            h = dev.adopt_buffer(arr, kind, sb * world)
+            lo, count = partition.shard_range(arr.nbytes, world, rank)
+            full = as_tensor(int(lib.mlv_buffer_device_ptr(h)), sb * world)
+            slabs.append((h, arr, lo, count, full, full[rank * sb:(rank + 1) * sb], torch.cuda.Event()))
         copy_stream = torch.cuda.ExternalStream(dev.copy_stream, device=cuda_dev)
         ag_stream = torch.cuda.Stream(device=cuda_dev)
-        sharded = []
-        for h, p in host_inputs:
-            sb = shard_bytes(p.nbytes)
-            full = torch.as_tensor(_RawBuf(int(lib.mlv_buffer_device_ptr(h)), sb * world), device=cuda_dev)
-            lo, count = partition.shard_range(p.nbytes, world, rank)
-            sharded.append((h, p.ctypes.data + lo, lo, count, full, full[rank * sb:(rank + 1) * sb], torch.cuda.Event()))
 
-    def frame_e2e_sharded():
-        for h, host_ptr, lo, n, full, mine, ev in sharded:
-            L.check(lib.mlv_update_buffer_range(dev._h, h, lo, C.c_void_p(host_ptr), n))
-            ev.record(copy_stream)
-            ag_stream.wait_event(ev)
-            with torch.cuda.stream(ag_stream):
-                dist.all_gather_into_tensor(full, mine)
-            L.check(lib.mlv_buffer_mark_updated(dev._h, h, C.c_void_p(ag_stream.cuda_stream)))
-        scenes.render(dev, scene)
-        had = pending[0]
-        drain()  # join the exchange of the previous frame
-        if had and rank == 0:
-            dev.present_wait()
-            dev.composite_readback_async(colors_host if e2e_step[0] % 2 == 0 else colors_host2)
-            e2e_step[0] += 1
-        dev.composite_broadcast_async()
-        pending[0] = True
+        def record_slab_frame():
+            dev.reset_stats()
+            dev.clear_render_target_view(scenes.CLEAR_COLOR)
+            dev.clear_depth_stencil_view(scenes.CLEAR_DEPTH)
+            gp = dev.graphics_pipeline
+            gp.vs.p_constant_buffers[0] = scene.per_frame_cb
+            gp.ia.p_vertex_buffer, gp.ia.p_index_buffer = vb_slab, ib_slab
+            for o, s0, b0 in zip(scene.objects, start_index, base_vertex):
+                gp.vs.shader, gp.ps.shader = o.vertex_shader, o.pixel_shader
+                gp.vs.p_shader_resource_views[0] = gp.ps.p_shader_resource_views[0] = o.texture
+                dev.draw_indexed(o.index_count, start_index_location=int(s0), base_vertex_location=int(b0))
+        record_slab_frame()  # sizes the arenas for the slab draws
+        dev.finish()
+        slab_list = None if args.immediate else dev.record(record_slab_frame)
 
-    def frame_e2e():
-        if multi and composite == "p2p":
-            return frame_e2e_sharded()
-        for h, p in host_inputs:
-            L.check(lib.mlv_update_buffer(dev._h, h, p.ctypes.data_as(C.c_void_p), p.nbytes))
-        if multi:
+        def frame_e2e_streaming():
+            for h, arr, lo, count, full, mine, ev in slabs:
+                if multi:
+                    L.check(lib.mlv_update_buffer_range(dev._h, h, lo, C.c_void_p(arr.ctypes.data + lo), count))
+                    ev.record(copy_stream)
+                    ag_stream.wait_event(ev)
+                    with torch.cuda.stream(ag_stream):
+                        dist.all_gather_into_tensor(full, mine)
+                    L.check(lib.mlv_buffer_mark_updated(dev._h, h, C.c_void_p(ag_stream.cuda_stream)))
+                else:
+                    L.check(lib.mlv_update_buffer(dev._h, h, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+            if slab_list is not None:
+                slab_list.execute()
+            else:
+                record_slab_frame()
+            deliver()
+        e2e_streaming_ms = time_e2e(frame_e2e_streaming)
+        streaming_ok = bool(np.array_equal(last_delivered(), colors)) if rank == 0 else None
+        e2e_streaming = {"value": 1e3 / e2e_streaming_ms, "unit": UNIT, "ms_per_step": e2e_streaming_ms, "h2d_bytes_per_step": int(vb_slab.nbytes + ib_slab.nbytes + 192 * len(scene.objects)),
+                         "d2h_bytes_per_step": int(d2h), "image_matches_resident_path": streaming_ok,
+                         "note": "a host that streams its geometry: one vertex slab + one index slab (draws address them with start index / base vertex) re-uploaded from pinned host memory every frame"
+                                 + (", each rank uploading its shard over its own PCIe link and an in-place ncclAllGather replicating it over NVLink (2 collectives per frame)" if multi else "")
+                                 + "; same read-back as e2e; textures stay resident"}
+    else:
+        # --composite nccl: e2e = static geometry with a blocking read-back by rank 0
+        def frame_e2e_nccl():
+            if frame_list is not None:
+                frame_list.set_constants(cb_host)
             frame()
-            drain()
-            dev.finish()  # composite result is in the resolved image; read it back below
-            _readback_multi()
-        else:
-            # double-buffered present: the host takes delivery of frame f-1 while frame f is already queued, and the
-            # device-to-host copy of frame f overlaps the uploads of frame f+1 (PCIe is full duplex)
-            scenes.render(dev, scene)
-            dev.present_wait()
-            dev.present_async(colors_host if e2e_step[0] % 2 == 0 else colors_host2)
-            e2e_step[0] += 1
-
-    def _readback_multi():
-        torch.cuda.synchronize()
-        n = scene.width * scene.height * 4
-        class _Raw2:
-            def __init__(self, ptr, nbytes):
-                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
-        src = torch.as_tensor(_Raw2(dev.resolved_color_ptr(), n), device=torch.device("cuda", local_rank))
-        torch.from_numpy(colors_host.view(np.uint8).reshape(-1)).copy_(src, non_blocking=False)
-
-    for _ in range(2):
-        frame_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        frame_e2e()
-    if multi and composite == "p2p":  # deliver the last frame too: K steps = K frames uploaded, drawn, exchanged and read back
-        drain()
-        if rank == 0:
-            dev.present_wait()
-            dev.composite_readback_async(colors_host if e2e_step[0] % 2 == 0 else colors_host2)
-            last_e2e_image = colors_host if e2e_step[0] % 2 == 0 else colors_host2
-    barrier()
-    e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3 / args.steps)
-    e2e_check = None
-    if multi and composite == "p2p":
-        frame()   # every rank takes part in the exchange
+            dev.finish()
+            if rank == 0:
+                torch.from_numpy(host_frames[0].view(np.uint8).reshape(-1)).copy_(as_tensor(dev.resolved_color_ptr(), d2h))
+        for _ in range(2):
+            frame_e2e_nccl()
         barrier()
-    if multi and composite == "p2p" and rank == 0:
-        # the frame delivered end to end (sharded uploads, asynchronous exchange) is the frame the resident path renders
-        ref_img = torch.as_tensor(_RawBuf(dev.resolved_color_ptr(), scene.width * scene.height * 4), device=cuda_dev).cpu().numpy().view(np.uint32).reshape(scene.height, scene.width)
-        e2e_check = bool(np.array_equal(ref_img, last_e2e_image))
-    tex_bytes = sum(p.nbytes for _, p in tex_seen.values())
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            frame_e2e_nccl()
+        barrier()
+        e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3 / args.steps)
+        e2e = {"value": 1e3 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 192 * len(scene.objects), "d2h_bytes_per_step": int(d2h),
+               "note": "static geometry, per-frame constant buffer, pack + ncclAllGather + unpack, blocking read-back by rank 0"}
 
     if rank == 0:
         peak, peak_src = load_peaks()
         b_alg, b_stage = algorithmic_bytes(scene, stats, len(scene.objects))
         fps = 1e3 / ms
-        # dominant kernel = the kernel with the largest summed time over the step; its algorithmic bytes (SURVEY.md 8d per-unit
-        # figures x the units it processed) over its own CUDA-event time
-        kernel_ms = {"k_front": stage_ms["geometry"], "k_back": stage_ms["geometry_back"], "k_tile": stage_ms["tile"], "k_front_clip": stage_ms["clip"], "k_vertex": stage_ms["vertex_cache"],
-                     "k_bin_scan": stage_ms["bin_scan"], "k_bin_fill": stage_ms["bin_fill"]}
-        kernel_launches = {"k_front": stage_launches["geometry"], "k_back": stage_launches["geometry_back"], "k_tile": stage_launches["tile"], "k_front_clip": stage_launches["clip"], "k_vertex": stage_launches["vertex_cache"],
-                           "k_bin_scan": stage_launches["bin_scan"], "k_bin_fill": stage_launches["bin_fill"]}
-        # Algorithmic bytes of a kernel = SURVEY.md 8d's per-unit figures x the units the kernel REALLY processed (device work
-        # counters): Stats count every assembled triangle and pair like the reference, but a triangle that Hi-Z rejects at
-        # binning time writes no record and a tile without surviving pairs is not visited, so those units move no bytes.
+        # Per-kernel roofline: algorithmic bytes = SURVEY.md 8d's per-unit figures x the units the kernel REALLY processed (device
+        # work counters: Stats count every assembled triangle and pair like the reference, but a triangle that Hi-Z rejects at
+        # binning time writes no record and a tile without surviving pairs is not visited), over the kernel's own CUDA-event time.
+        kstage = {"k_front": "geometry", "k_back": "geometry_back", "k_tile": "tile", "k_front_clip": "clip", "k_vertex": "vertex_cache", "k_bin_scan": "bin_scan", "k_fill": "bin_fill"}
+        kernel_ms = {k: stage_ms[s] for k, s in kstage.items()}
+        kernel_launches = {k: stage_launches[s] for k, s in kstage.items()}
         idx_bytes = 4 * sum(o.index_count for o in scene.objects)
         vtx_bytes = 32 * sum(o.vertex_buffer.shape[0] for o in scene.objects)
         tri_in = sum(o.index_count // 3 for o in scene.objects)
@@ -436,7 +569,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                         "k_back": (16 * tri_in + 216 * work["records_written"]) / world,                    # bounds read + record write
                         "k_tile": (216 * work["records_written"] + 1032 * work["tiles_visited"] + 4 * work["pairs_listed"]) / world,  # record read + tile read/write + list read
                         "k_front_clip": 0, "k_vertex": vtx_bytes / world, "k_bin_scan": 16 * (scene.width // 8) * (scene.height // 8) * len(scene.objects) / world,
-                        "k_bin_fill": (16 * stats["assembled_triangle_count"] + 4 * work["pairs_listed"]) / world}
+                        "k_fill": (16 * stats["assembled_triangle_count"] + 4 * work["pairs_listed"]) / world}
         dom = max(("k_front", "k_back", "k_tile"), key=kernel_ms.get)  # the kernels that carry the geometry and record streams; the others move < 5 % of the bytes
 
         def kernel_roofline(k):
@@ -445,38 +578,36 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             a = b_l / (ms_l * 1e-3) / 1e9 if ms_l > 0 else 0.0
             return {"achieved": a, "frac": a / peak, "algorithmic_bytes_per_launch": b_l, "ms_per_launch": ms_l, "launches_per_step": kernel_launches[k]}
         dom_r = kernel_roofline(dom)
-        achieved, dom_bytes_per_launch, dom_ms_per_launch, dom_launches = dom_r["achieved"], dom_r["algorithmic_bytes_per_launch"], dom_r["ms_per_launch"], dom_r["launches_per_step"]
-        # measured DRAM bytes per launch of that kernel from the committed ncu capture (same workload, 1 GPU), else null
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic_config5_n1.json")
-        if args.config == 5 and world == 1 and os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f)["kernels"].get(dom, {}).get("dram_bytes_per_launch")
+        traffic, traffic_how = (None, "not measured (--no-traffic, or more than one GPU)")
+        if not multi and not args.no_traffic:
+            traffic, traffic_how = measure_traffic(args.config, dom)
         out = {
-            "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
             "mtri_per_s": scene.input_triangles * fps / 1e6, "gpix_per_s": scene.width * scene.height * fps / 1e9,
-            "config": {"workload": workload_name(args.config, scene), "input_triangles": scene.input_triangles, "draws": len(scene.objects),
-                       "assembled_triangles": stats["assembled_triangle_count"], "tri_tile_pairs": stats["total_triangle_count_in_bins"],
-                       "tile_draws": stats["active_bin_count"], "parallelism": f"sort-first x{world}, stripe {stripe} tile rows, composite {composite}" if multi else "single GPU",
-                       "l2": "no flush: per-frame working set (inputs + per-draw setup records) >> 126 MB L2" if args.config == 5 else "no flush"},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes_per_launch,
-                         "ms_per_launch": dom_ms_per_launch, "launches_per_step": dom_launches,
+            "config": workload_config(args.config, scene),
+            "run": {"parallelism": f"sort-first x{world}, stripe {stripe} tile rows, composite {composite}" if multi else "single GPU",
+                    "issue": "immediate calls" if args.immediate else "recorded command list (one CUDA-graph launch per frame)",
+                    "assembled_triangles": stats["assembled_triangle_count"], "tri_tile_pairs": stats["total_triangle_count_in_bins"], "tile_draws": stats["active_bin_count"],
+                    "l2": "no flush: per-frame working set (inputs + per-draw setup records) >> 126 MB L2" if args.config == 5 else "no flush", "kernels_source_sha256_16": kernels_source_hash()},
+            "frame_fnv": {"color": hashes["color"], "depth": hashes["depth"]},
+            "matches_golden": {"color": (hashes["color"] == hashes["golden_color"]) if hashes["golden_color"] else None,
+                               "depth": (hashes["depth"] == hashes["golden_depth"]) if (hashes["depth"] and hashes["golden_depth"]) else None,
+                               "note": "depth: the reference's own depth image (tests/golden/golden.json, bit-exact); colour: this repo's frame as committed after passing the <= 1/255 "
+                                       "tolerance against the live reference (tests/golden/gpu_frames.json); depth is not exchanged between ranks, so it is hashed at N = 1 only"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_r["achieved"], "peak": peak, "unit": "GB/s",
+                         "frac": dom_r["achieved"] / peak, "traffic": traffic, "traffic_source": traffic_how, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": dom_r["algorithmic_bytes_per_launch"], "ms_per_launch": dom_r["ms_per_launch"], "launches_per_step": dom_r["launches_per_step"],
                          "units_per_step": {"records_written": work["records_written"], "tiles_visited": work["tiles_visited"], "pairs_listed": work["pairs_listed"]},
                          "note": "algorithmic bytes = SURVEY 8d per-unit figures x the units the kernel really processed (mlv_work_counters), averaged over its launches of a frame; "
-                                 "the launch time is its CUDA-event bracket (no overlap with neighbours)"},
-            "roofline_kernels": {k: kernel_roofline(k) for k in ("k_front", "k_back", "k_tile", "k_vertex", "k_bin_fill")},
+                                 "the launch time is its CUDA-event bracket in immediate mode (no overlap with neighbours)"},
+            "roofline_kernels": {k: kernel_roofline(k) for k in ("k_front", "k_back", "k_tile", "k_vertex", "k_fill")},
             "roofline_frame": {"algorithmic_bytes_per_frame": b_alg, "achieved": b_alg / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
                                "frac": b_alg / (ms * 1e-3) / 1e9 / world / peak, "bytes_by_stage": b_stage,
                                "note": "B_alg of the REFERENCE algorithm for this frame (SURVEY 8d: every assembled triangle's record written and read, every touched tile-draw loaded and "
-                                       "stored) over the measured frame time: delivered work per second, not DRAM throughput -- it exceeds the peak when Hi-Z at binning time removes work"},
+                                       "stored) over the measured frame time: delivered reference work per second, NOT a DRAM-throughput fraction -- it exceeds the peak when Hi-Z at binning time removes work"},
             "stage_ms_per_step": {k: round(v, 4) for k, v in stage_ms.items()},
-            "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d - tex_bytes), "d2h_bytes_per_step": int(d2h),
-                    "note": ("every vertex/index buffer + constant buffer re-uploaded from pinned host memory each frame; framebuffer read back to pinned host memory each frame (double-buffered: the host collects frame f-1 while frame f is queued); textures stay resident"
-                             if not (multi and composite == "p2p") else
-                             "whole job: every vertex/index buffer crosses PCIe once per frame -- rank r uploads shard r of each buffer from pinned host memory, an in-place ncclAllGather replicates it over NVLink -- and rank 0 reads the composited frame back to pinned host memory (one frame behind: the exchange of frame f overlaps frame f+1); textures stay resident"),
-                    **({"image_matches_resident_path": e2e_check} if e2e_check is not None else {})},
+            "e2e": e2e, "e2e_streaming": e2e_streaming,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if not multi and not args.no_cpu_baseline:
@@ -495,17 +626,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--stripe", type=int, default=0, help="stripe height in tile rows for the sort-first split (0 = one contiguous band per rank)")
-    ap.add_argument("--composite", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange step: fused peer-memory broadcast (default) or pack + ncclAllGather + unpack")
+    ap.add_argument("--composite", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange step: asynchronous peer-memory broadcast (default) or pack + ncclAllGather + unpack")
+    ap.add_argument("--immediate", action="store_true", help="issue every call every frame instead of replaying a recorded command list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child process that measures roofline.traffic")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        if args.steps > 10:
-            args.steps = 10  # bounded: a config-5 frame is seconds of CPU work
-        if args.warmup > 2:
-            args.warmup = 2
         run_reference(args, rank)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:

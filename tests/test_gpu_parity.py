@@ -792,3 +792,28 @@ def test_out_of_range_and_infinite_vertices_snap_like_x86():
             col, dep = dev.present()
             assert dev.stats() == orc.stats()
         parity.assert_frames_match(col, dep, orc.colors(), orc.depths(), "snap production")
+
+
+def test_committed_gpu_frame_hashes_are_the_production_frames():
+    """tests/golden/gpu_frames.json (what bench.py's `matches_golden.color` compares with, at every GPU count) holds the hashes
+    of the frames the production path renders for the five BASELINE configs; tools/make_gpu_golden.py wrote them only after the
+    frames passed the parity bars against the live reference. Here: the hashes still are those frames', and (where the reference
+    is available) the frames still pass."""
+    from malevich_b200 import scenes
+    from malevich_b200._lib import fnv64_words
+    committed = json.load(open(os.path.join(ROOT, "tests", "golden", "gpu_frames.json")))
+    for cfg, key in ((1, "config1_toon_1280x720"), (2, "config2_ftm_1920x1080"), (3, "config3_emily_1920x1080"), (4, "config4_locomotive_3840x2160"), (5, "config5_synthetic_3840x2160")):
+        sc = scenes.CONFIGS[cfg]()
+        with _device(sc.width, sc.height) as dev:
+            cl = dev.record(lambda: (dev.reset_stats(), scenes.render(dev, sc)))  # the way bench.py issues the frame
+            cl.execute()
+            col, dep = dev.present()
+            assert dev.stats() == GOLDEN[key]["stats"]
+            cl.release()
+        assert fnv64_words(dep) == committed[key]["depth_fnv"] == GOLDEN[key]["depth_fnv"], key
+        assert fnv64_words(col) == committed[key]["color_fnv"], key
+        if cfg != 5 and have_ref(sc.width, sc.height):  # (config 5 against the live reference: test_config5_full_size_against_live_reference)
+            orc = _oracle(sc.width, sc.height)
+            if parity.host_vrsqrtps_matches_table(orc):
+                orc.render(sc)
+                parity.assert_frames_match(col, dep, orc.colors(), orc.depths(), key)

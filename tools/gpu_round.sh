@@ -1,8 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log | cut -c1-250
-for wr in "1 0" "8 3" "8 0" "2 0" "4 1"; do timeout 120 python tools/issue_time.py $wr 20 5 | grep "command list"; done > gpurun_out/issue_time.txt 2>&1
-for c in 1 2 3 4; do timeout 120 python tools/issue_time.py 1 0 20 $c| grep "command list"; done >> gpurun_out/issue_time.txt 2>&1
-cat gpurun_out/issue_time.txt
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,launch__registers_per_thread,launch__grid_size --clock-control none --csv --log-file gpurun_out/launches_w1_r0.csv python tools/profile_rank.py 1 0 2 5 > gpurun_out/ncu_w1.log 2>&1
+python tools/make_gpu_golden.py > gpurun_out/make_gpu_golden.log 2>&1; tail -3 gpurun_out/make_gpu_golden.log
+cp gpurun_out/gpu_frames.json tests/golden/gpu_frames.json
+for c in 5 1 2 3 4; do
+  timeout 400 python bench.py --config $c --steps 20 --warmup 3 > gpurun_out/bench_c${c}.json 2> gpurun_out/bench_c${c}.err
+  tail -3 gpurun_out/bench_c${c}.err
+done
+timeout 300 python bench.py --impl reference --config 5 --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
