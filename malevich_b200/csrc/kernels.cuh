@@ -502,15 +502,24 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS) k_chunk_bounds(const IndexSt
 	}
 }
 
+// The vertex-shader constant buffer of the draw (PerFrameCB, main.c:169-173) in shared memory: from the kernel parameters
+// (immediate draws) or from the device copy a recorded command list keeps per draw (so that the constants of a replay can
+// be replaced without touching the recording, mlv_command_list_set_constants).
+__device__ __forceinline__ const float *stage_constants(const GeomParams &P, float *s_cb) {
+	if(threadIdx.x < 48u) s_cb[threadIdx.x] = P.cbp ? __ldg(P.cbp + threadIdx.x) : P.cb[threadIdx.x];
+	__syncthreads();
+	return s_cb;
+}
+
 // true when the chunk certainly bins nothing on this rank
-__device__ __forceinline__ bool chunk_is_foreign(const GeomParams &P, uint32_t chunk) {
+__device__ __forceinline__ bool chunk_is_foreign(const GeomParams &P, const float *cb, uint32_t chunk) {
 	const float4 lo = __ldg(P.chunk_bounds + 2 * (size_t)chunk), hi = __ldg(P.chunk_bounds + 2 * (size_t)chunk + 1);
 	if(lo.w != 0.0f) return false; // the chunk holds a NaN / Inf position
 	float ymin = INFINITY, ymax = -INFINITY;
 #pragma unroll
 	for(int k = 0; k < 8; ++k) {
 		const float4 corner = make_float4((k & 1) ? hi.x : lo.x, (k & 2) ? hi.y : lo.y, (k & 4) ? hi.z : lo.z, 1.0f);
-		const float4 cs = mul_m4_v4_pairwise(P.cb, corner);
+		const float4 cs = mul_m4_v4_pairwise(cb, corner);
 		// behind or near the eye plane the projection of the box is unbounded: keep the chunk
 		if(!(cs.w > 1e-6f && fabsf(cs.y) <= 3.0e38f)) return false;
 		const float ys = P.vp_m11 * (cs.y / cs.w) + P.vp_m13; // screen y of the corner (the exact path adds rounding of a few ulp)
@@ -551,9 +560,11 @@ __device__ __forceinline__ uint32_t clip_code(const float4 p) {
 template <int VS>
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ GeomParams P, uint32_t vertex_count) {
 	pdl_prologue();
+	__shared__ float s_cb[48];
+	const float *cb = stage_constants(P, s_cb);
 	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
 	if(v >= vertex_count) return;
-	const float4 pos = vs_position<VS>(__ldg(P.vb + 2 * (size_t)v), P.cb);
+	const float4 pos = vs_position<VS>(__ldg(P.vb + 2 * (size_t)v), cb);
 	const ProjVertex pv = project_vertex(pos, P);
 	P.vcache[2 * (size_t)v] = pos;
 	P.vcache[2 * (size_t)v + 1] = make_float4(__int_as_float(pv.sx), __int_as_float(pv.sy), pv.s.z, __uint_as_float(clip_code(pos)));
@@ -597,6 +608,8 @@ __device__ __forceinline__ void queue_big(const GeomParams &P, int big_class, ui
 template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
 __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_constant__ GeomParams P) {
 	pdl_prologue();
+	__shared__ float s_cb[48];
+	const float *cb = stage_constants(P, s_cb);
 	const uint32_t lane = lane_id();
 	uint32_t emitted = 0, pairs = 0;
 	// Single GPU: CTA b processes chunk b, b + grid, ... Sort-first: each round, thread k of the CTA tests the cached
@@ -611,7 +624,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_cons
 		const uint32_t c = first + threadIdx.x * gridDim.x;
 		bool live = false;
 		if(c < num_chunks) {
-			live = !chunk_is_foreign(P, c);
+			live = !chunk_is_foreign(P, cb, c);
 			P.chunk_live[c] = live ? 1 : 0; // the back half and the fill phase skip the stale bounds of the chunks nobody rewrote
 		}
 		s_live[threadIdx.x] = live ? 1 : 0;
@@ -648,12 +661,12 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_cons
 		} else {
 			a0 = __ldg(P.vb + 2 * (size_t)vi0), b0 = __ldg(P.vb + 2 * (size_t)vi1), c0 = __ldg(P.vb + 2 * (size_t)vi2);
 			// ---- vertex shader, position part (main.c:698-734)
-			a = vs_position<VS>(a0, P.cb), b = vs_position<VS>(b0, P.cb), c = vs_position<VS>(c0, P.cb);
+			a = vs_position<VS>(a0, cb), b = vs_position<VS>(b0, cb), c = vs_position<VS>(c0, cb);
 		}
 		if(DEBUG) {
-			const VsOut v0 = run_vs<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
-			const VsOut v1 = run_vs<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
-			const VsOut v2 = run_vs<VS>(c0, __ldg(P.vb + 2 * (size_t)vi2 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
+			const VsOut v0 = run_vs<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), cb, P.vs_tex, P.rsqrt_lut);
+			const VsOut v1 = run_vs<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), cb, P.vs_tex, P.rsqrt_lut);
+			const VsOut v2 = run_vs<VS>(c0, __ldg(P.vb + 2 * (size_t)vi2 + 1), cb, P.vs_tex, P.rsqrt_lut);
 			float4 *o = reinterpret_cast<float4 *>(P.dbg.vs_out + (size_t)(3u * t) * 12);
 			o[0] = v0.r0, o[1] = v0.r1, o[2] = make_float4(v0.r2x, 0.0f, 0.0f, 0.0f);
 			o[3] = v1.r0, o[4] = v1.r1, o[5] = make_float4(v1.r2x, 0.0f, 0.0f, 0.0f);
@@ -779,7 +792,9 @@ __device__ __forceinline__ uint32_t emit_fan(const GeomParams &P, uint32_t t, co
 template <int VS, bool INDEXED>
 __global__ void __launch_bounds__(MLV_CLIP_THREADS) k_front_clip(const __grid_constant__ GeomParams P) {
 	__shared__ float s_poly[2][MLV_CLIP_MAXV * 9 * MLV_CLIP_THREADS];
+	__shared__ float s_cb[48];
 	pdl_prologue();
+	const float *cb = stage_constants(P, s_cb);
 	const uint32_t n = P.dctr->clip_count;
 	const uint32_t lane = lane_id();
 	uint32_t emitted = 0, pairs = 0;
@@ -797,9 +812,9 @@ __global__ void __launch_bounds__(MLV_CLIP_THREADS) k_front_clip(const __grid_co
 			t = P.clip_queue[i];
 			uint32_t vi0, vi1, vi2;
 			fetch_indices<VS, INDEXED, false, false>(P, t, vi0, vi1, vi2);
-			const VsOut v0 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi0), __ldg(P.vb + 2 * (size_t)vi0 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
-			const VsOut v1 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi1), __ldg(P.vb + 2 * (size_t)vi1 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
-			const VsOut v2 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi2), __ldg(P.vb + 2 * (size_t)vi2 + 1), P.cb, P.vs_tex, P.rsqrt_lut);
+			const VsOut v0 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi0), __ldg(P.vb + 2 * (size_t)vi0 + 1), cb, P.vs_tex, P.rsqrt_lut);
+			const VsOut v1 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi1), __ldg(P.vb + 2 * (size_t)vi1 + 1), cb, P.vs_tex, P.rsqrt_lut);
+			const VsOut v2 = run_vs<VS>(__ldg(P.vb + 2 * (size_t)vi2), __ldg(P.vb + 2 * (size_t)vi2 + 1), cb, P.vs_tex, P.rsqrt_lut);
 			fan = clip_polygon(P, v0, v1, v2, poly, scratch) - 2;
 			if(fan > 8) { // cannot happen for a convex clip of a triangle by six planes (<= 9 vertices)
 				atomicOr(&P.ctr->error_flags, MLV_FLAG_TRI_OVERFLOW);
@@ -898,7 +913,7 @@ __device__ __forceinline__ void count_big_rects(const GeomParams &P, uint32_t ep
 }
 
 template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
-__device__ __forceinline__ void back_process(const GeomParams &P, uint4 (*s_stage)[32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)], uint32_t slot, uint4 b, uint32_t epoch, BackState &st) {
+__device__ __forceinline__ void back_process(const GeomParams &P, uint4 (*s_stage)[32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)], uint32_t slot, uint4 b, uint32_t epoch, const float *cb, BackState &st) {
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 	bool staged = false, live = false, present = false;
 	TileRect tr = { 0, 0, -1, -1 };
@@ -936,16 +951,16 @@ __device__ __forceinline__ void back_process(const GeomParams &P, uint4 (*s_stag
 				pa.rw = 1.0f / a.w, pb.rw = 1.0f / bq.w, pc.rw = 1.0f / c.w; // a_reciprocal_ws (project_vertex): the same correctly rounded divide
 				setup_from_projected(pa, pb, pc, P, S);
 			} else {
-				a = vs_position<VS>(a0, P.cb), bq = vs_position<VS>(b0, P.cb), c = vs_position<VS>(c0, P.cb);
+				a = vs_position<VS>(a0, cb), bq = vs_position<VS>(b0, cb), c = vs_position<VS>(c0, cb);
 				setup_project(a, bq, c, P, S);
 			}
 			setup_edges(P, S);
 			// ---- vertex shader, attribute part
 			float4 r1a, r1b, r1c;
 			float r2a, r2b, r2c;
-			vs_attributes<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), a, P.cb, P.vs_tex, P.rsqrt_lut, r1a, r2a);
-			vs_attributes<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), bq, P.cb, P.vs_tex, P.rsqrt_lut, r1b, r2b);
-			vs_attributes<VS>(c0, __ldg(P.vb + 2 * (size_t)vi2 + 1), c, P.cb, P.vs_tex, P.rsqrt_lut, r1c, r2c);
+			vs_attributes<VS>(a0, __ldg(P.vb + 2 * (size_t)vi0 + 1), a, cb, P.vs_tex, P.rsqrt_lut, r1a, r2a);
+			vs_attributes<VS>(b0, __ldg(P.vb + 2 * (size_t)vi1 + 1), bq, cb, P.vs_tex, P.rsqrt_lut, r1b, r2b);
+			vs_attributes<VS>(c0, __ldg(P.vb + 2 * (size_t)vi2 + 1), c, cb, P.vs_tex, P.rsqrt_lut, r1c, r2c);
 			if(live) {
 				staged = true;
 				TriRecord R;
@@ -989,6 +1004,8 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_back(const __grid_const
 	__shared__ uint4 s_stage[MLV_GEOM_THREADS / 32][32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)];
 	__shared__ uint32_t s_list[MLV_GEOM_THREADS]; // the live chunks of this round, compacted
 	__shared__ uint32_t s_warp_count[MLV_GEOM_THREADS / 32];
+	__shared__ float s_cb[48];
+	const float *cb = stage_constants(P, s_cb);
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 	const uint32_t epoch = P.ctr->epoch;        // both loads are in flight with the first chunk's bounds;
 	const uint32_t ovf_raw = P.dctr->ovf_count; // the overflow count is only needed after the direct slots
@@ -1025,7 +1042,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_back(const __grid_const
 				const uint32_t sn = s_list[i + 1u] * MLV_GEOM_THREADS + threadIdx.x;
 				if(sn < P.tri_count) b_next = P.tri_bounds[sn];
 			}
-			back_process<VS, INDEXED, DEBUG, VCACHE>(P, s_stage, slot, b, epoch, st);
+			back_process<VS, INDEXED, DEBUG, VCACHE>(P, s_stage, slot, b, epoch, cb, st);
 		}
 		__syncthreads(); // s_list is rewritten by the next round
 	}
@@ -1034,7 +1051,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_back(const __grid_const
 	for(uint32_t base = blockIdx.x * MLV_GEOM_THREADS; base < n_ovf; base += gridDim.x * MLV_GEOM_THREADS) {
 		const uint32_t o = base + threadIdx.x;
 		const uint4 b = (o < n_ovf) ? P.tri_bounds[P.tri_count + o] : make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, 0u);
-		back_process<VS, INDEXED, DEBUG, VCACHE>(P, s_stage, P.tri_count + o, b, epoch, st);
+		back_process<VS, INDEXED, DEBUG, VCACHE>(P, s_stage, P.tri_count + o, b, epoch, cb, st);
 	}
 	// ---- rectangles of more than 8 tiles (the front half queued them): a warp each, spread over the whole grid
 	count_big_rects(P, epoch, st);

@@ -86,7 +86,15 @@ struct mlv_command_list {
 	std::vector<const void *> *geom_funcs; // kernels whose first parameter is a GeomParams
 	std::vector<const void *> *vertex_funcs; // ... and that take a second u32 (k_vertex)
 	std::vector<GeomNode *> *geom_nodes;
+	// The PerFrameCB of the first MLV_LIST_CONSTANT_DRAWS recorded draws lives in a device arena (64 floats per draw) the
+	// geometry kernels read through GeomParams::cbp: mlv_command_list_set_constants rewrites the host shadow and the next
+	// execution uploads it with ONE small copy ahead of the graph launch -- no graph node is touched. (Replacing the
+	// by-value constants of every geometry node cost ~35 cudaGraphExecKernelNodeSetParams per config-5 frame and made the
+	// driver upload the graph again.) Draws beyond the arena keep by-value constants and the node path.
+	float *d_constants, *h_constants;
+	bool constants_dirty;
 };
+#define MLV_LIST_CONSTANT_DRAWS 256u
 
 #define MLV_DRAW_CONTEXTS 8 /* draws whose front half may run ahead; MAX_OBJECT_COUNT_PER_SCENE of the reference is 8 (main.c:44) */
 struct DrawCtx {
@@ -1108,6 +1116,11 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	gp.tri_count = T;
 	gp.ovf_capacity = ovf_cap;
 	memcpy(gp.cb, dev->cb[0], 192);
+	if(dev->recording && dev->recording->draws < MLV_LIST_CONSTANT_DRAWS) { // replaceable per execution, see mlv_command_list
+		gp.cbp = dev->recording->d_constants + (size_t)dev->recording->draws * 64;
+		memcpy(dev->recording->h_constants + (size_t)dev->recording->draws * 64, dev->cb[0], 192);
+		dev->recording->constants_dirty = true;
+	}
 	gp.vs_tex = tex_desc(dev->vs_srv[0]);
 	gp.rsqrt_lut = dev->rsqrt_lut;
 	{ // screen_from_ndc initialiser (main.c:825-830): double arithmetic rounded to f32 per entry
@@ -1305,6 +1318,8 @@ static void free_command_list(mlv_command_list *list) {
 	if(list->owner && list->owner->lists_alive) list->owner->lists_alive--;
 	if(list->geom_nodes)
 		for(GeomNode *n : *list->geom_nodes) delete n;
+	if(list->d_constants) cudaFree(list->d_constants);
+	free(list->h_constants);
 	delete list->buffers;
 	delete list->geom_funcs;
 	delete list->vertex_funcs;
@@ -1327,7 +1342,13 @@ int mlv_begin_command_list(mlv_device *dev) {
 	list->geom_nodes = new std::vector<GeomNode *>();
 	dev->lists_alive++; // from now on a replaced arena is kept until the device is destroyed: recorded nodes may address it
 	list->fb_sel = dev->fb_sel;
-	cudaError_t e = cudaStreamBeginCapture(dev->stream, cudaStreamCaptureModeRelaxed);
+	list->h_constants = (float *)calloc((size_t)MLV_LIST_CONSTANT_DRAWS * 64, sizeof(float));
+	cudaError_t e = list->h_constants ? cudaMalloc(&list->d_constants, (size_t)MLV_LIST_CONSTANT_DRAWS * 64 * sizeof(float)) : cudaErrorMemoryAllocation;
+	if(e != cudaSuccess) {
+		free_command_list(list);
+		return fail(MLV_ERR_OUT_OF_MEMORY, "command-list constants arena: %s", cudaGetErrorString(e));
+	}
+	e = cudaStreamBeginCapture(dev->stream, cudaStreamCaptureModeRelaxed);
 	if(e != cudaSuccess) {
 		free_command_list(list);
 		return fail(MLV_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
@@ -1378,6 +1399,7 @@ int mlv_finish_command_list(mlv_device *dev, mlv_command_list **out_list) {
 		const bool is_vertex = std::find(list->vertex_funcs->begin(), list->vertex_funcs->end(), (const void *)kp.func) != list->vertex_funcs->end();
 		const bool is_geom = std::find(list->geom_funcs->begin(), list->geom_funcs->end(), (const void *)kp.func) != list->geom_funcs->end();
 		if(!is_vertex && !is_geom) continue;
+		if(((const GeomParams *)kp.kernelParams[0])->cbp) continue; // constants in the list's device arena
 		GeomNode *g = new GeomNode();
 		g->node = nodes[i];
 		g->params = kp;
@@ -1417,6 +1439,11 @@ int mlv_execute_command_list(mlv_device *dev, mlv_command_list *list) {
 		CUDA_TRY(cudaStreamWaitEvent(dev->stream, b->ready, 0));
 		b->ready_pending = false;
 	}
+	if(list->constants_dirty) { // (pageable source: staged by the driver before the call returns, the shadow may be rewritten at once)
+		const uint32_t n = list->draws < MLV_LIST_CONSTANT_DRAWS ? list->draws : MLV_LIST_CONSTANT_DRAWS;
+		CUDA_TRY(cudaMemcpyAsync(list->d_constants, list->h_constants, (size_t)n * 64 * sizeof(float), cudaMemcpyHostToDevice, dev->stream));
+		list->constants_dirty = false;
+	}
 	CUDA_TRY(cudaGraphLaunch(list->exec, dev->stream));
 	dev->launches += list->launches;
 	dev->last_index_count = list->last_index_count;
@@ -1433,7 +1460,13 @@ int mlv_command_list_set_constants(mlv_device *dev, mlv_command_list *list, uint
 	if(!list || list->owner != dev || !data || bytes > sizeof(((GeomParams *)0)->cb)) return fail(MLV_ERR_INVALID_ARGUMENT, "bad command-list constants");
 	if(draw_index != MLV_ALL_DRAWS && draw_index >= list->draws) return fail(MLV_ERR_INVALID_ARGUMENT, "draw %u out of range (%u draws recorded)", draw_index, list->draws);
 	uint32_t touched = 0;
-	for(GeomNode *g : *list->geom_nodes) {
+	for(uint32_t d = 0; d < list->draws && d < MLV_LIST_CONSTANT_DRAWS; ++d) {
+		if(draw_index != MLV_ALL_DRAWS && d != draw_index) continue;
+		memcpy(list->h_constants + (size_t)d * 64, data, bytes);
+		list->constants_dirty = true;
+		++touched;
+	}
+	for(GeomNode *g : *list->geom_nodes) { // draws beyond the arena
 		if(draw_index != MLV_ALL_DRAWS && g->gp.draw_ordinal != draw_index) continue;
 		memcpy(g->gp.cb, data, bytes);
 		cudaError_t e = cudaGraphExecKernelNodeSetParams(list->exec, g->node, &g->params);

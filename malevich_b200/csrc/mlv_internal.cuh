@@ -122,6 +122,7 @@ struct GeomParams {
 	uint32_t tri_count;    // T: input triangles == number of direct slots
 	uint32_t ovf_capacity; // overflow slots available
 	float cb[48];
+	const float *cbp; // non-null: the constants live here (a recorded command list's per-draw device copy), cb[] is ignored
 	TexDesc vs_tex;
 	const uint32_t *rsqrt_lut;
 	// screen_from_ndc (main.c:825-830), computed on the host in double like the reference's initialiser
