@@ -309,6 +309,21 @@ MLV_API int mlv_profile_end(mlv_device *dev, double *out_ms, uint32_t *out_launc
 typedef struct mlv_profile_event { int32_t stage; float start_ms; float duration_ms; } mlv_profile_event;
 MLV_API int mlv_profile_read_events(mlv_device *dev, mlv_profile_event *out, uint32_t capacity, uint32_t *out_count);
 
+/* Device-side timeline: the frame as it really overlaps, INSIDE a recorded command list and across the library's streams
+ * (the event brackets above serialise the launches and cannot be recorded). Every geometry / binning / tile launch issued
+ * or recorded between mlv_timeline_begin and mlv_timeline_end carries a slot into which its CTAs stamp %globaltimer:
+ * first CTA resident, first CTA past the wait for the previous kernel of its stream, last CTA done. mlv_timeline_reset
+ * (stream-ordered on the device stream, not recordable) re-arms the slots before the execution to be looked at;
+ * mlv_timeline_read synchronises and returns one event per slot in issue order, microseconds relative to the earliest
+ * stamp (-1: the launch has not run since the reset). The stamps cost two atomics per CTA; launches issued while the
+ * timeline is off carry no slot. tools/timeline_frame.py writes a Chrome/Perfetto trace under the reference's Remotery
+ * scope names (main.c:663,699,737,916,984,1047). */
+typedef struct mlv_timeline_event { int32_t stage; int32_t draw; double resident_us, start_us, end_us; } mlv_timeline_event;
+MLV_API int mlv_timeline_begin(mlv_device *dev);
+MLV_API int mlv_timeline_end(mlv_device *dev);
+MLV_API int mlv_timeline_reset(mlv_device *dev);
+MLV_API int mlv_timeline_read(mlv_device *dev, mlv_timeline_event *out, uint32_t capacity, uint32_t *out_count);
+
 /* how many kernels this device has launched since creation (bench.py's gpu_launches) */
 MLV_API uint64_t mlv_kernel_launch_count(mlv_device *dev);
 /* word-wise 64-bit FNV-1a over u32 words: the frame hash used by tests/golden/golden.json and bench.py (host-side helper) */

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmalevich_b200.so")
+LIB_PATH = os.environ.get("MLV_LIB_PATH") or os.path.join(_HERE, "csrc", "libmalevich_b200.so")  # (the override serves kernel experiments: variant builds side by side)
 
 # every symbol include/malevich_b200.h declares (tests check the library exports each of them)
 EXPORTED_SYMBOLS = [
@@ -21,6 +21,7 @@ EXPORTED_SYMBOLS = [
     "mlv_composite_peer_export", "mlv_composite_peer_attach", "mlv_composite_broadcast", "mlv_composite_wait", "mlv_composite_broadcast_async", "mlv_composite_join", "mlv_composite_readback_async", "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
     "mlv_debug_read_vs_out", "mlv_debug_read_triangles", "mlv_debug_read_bins", "mlv_debug_read_masks",
     "mlv_debug_read_tile_min_depths", "mlv_debug_read_keys", "mlv_read_bin_lists", "mlv_fnv64_words", "mlv_profile_begin", "mlv_profile_end", "mlv_profile_read_events", "mlv_kernel_launch_count",
+    "mlv_timeline_begin", "mlv_timeline_end", "mlv_timeline_reset", "mlv_timeline_read",
 ]
 STAGE_NAMES = ["clear", "geometry", "bin_count", "bin_scan", "bin_fill", "tile", "resolve", "composite", "vertex_cache", "clip", "geometry_back"]
 
@@ -42,6 +43,10 @@ class WorkCounters(C.Structure):
 
 class ProfileEvent(C.Structure):
     _fields_ = [("stage", C.c_int32), ("start_ms", C.c_float), ("duration_ms", C.c_float)]
+
+
+class TimelineEvent(C.Structure):
+    _fields_ = [("stage", C.c_int32), ("draw", C.c_int32), ("resident_us", C.c_double), ("start_us", C.c_double), ("end_us", C.c_double)]
 
 
 class Viewport(C.Structure):
@@ -161,6 +166,10 @@ def load() -> C.CDLL:
         "mlv_profile_begin": (i32, [vp]),
         "mlv_profile_end": (i32, [vp, P(C.c_double), P(u32)]),
         "mlv_profile_read_events": (i32, [vp, vp, u32, P(u32)]),
+        "mlv_timeline_begin": (i32, [vp]),
+        "mlv_timeline_end": (i32, [vp]),
+        "mlv_timeline_reset": (i32, [vp]),
+        "mlv_timeline_read": (i32, [vp, vp, u32, P(u32)]),
         "mlv_kernel_launch_count": (C.c_uint64, [vp]),
     }
     assert sorted(sig) == sorted(EXPORTED_SYMBOLS)

@@ -30,6 +30,32 @@ __device__ __forceinline__ void pdl_prologue() {
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// Device-side timeline (mlv_timeline_*): a launch that carries a slot stamps %globaltimer into it -- [0] the first CTA
+// resident, [1] the first CTA past griddepcontrol.wait (the previous kernel of its stream has completed), [2] the last CTA
+// done, stored inverted so that all three are atomicMin over words preset to ~0. Unlike event brackets this works inside a
+// recorded command list and across streams: it shows the frame as it really overlaps.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+struct TimelineScope {
+	unsigned long long *slot;
+	__device__ __forceinline__ explicit TimelineScope(unsigned long long *s) : slot(s) {
+		if(slot && threadIdx.x == 0) atomicMin(slot, globaltimer_ns());
+	}
+	__device__ __forceinline__ void started() const {
+		if(slot && threadIdx.x == 0) atomicMin(slot + 1, globaltimer_ns());
+	}
+	__device__ __forceinline__ ~TimelineScope() {
+		if(slot && threadIdx.x == 0) atomicMin(slot + 2, ~globaltimer_ns());
+	}
+};
+#define MLV_KERNEL_PROLOGUE(slot_ptr) \
+	TimelineScope timeline_scope_(slot_ptr); \
+	pdl_prologue(); \
+	timeline_scope_.started()
+
 // =================================================================================================
 // clear
 // =================================================================================================
@@ -271,14 +297,47 @@ struct BinTally {
 	uint32_t survivors;
 };
 
-// One (triangle, tile) pair. A bin is "touched in this draw" when bin_touch[bin] holds the draw's epoch -- raised by
-// whoever finds it missing, nothing to wait for and nothing to reset afterwards: a draw whose pairs are all rejected
-// leaves nothing behind for the binning kernels to clean up. The draw's last kernel counts the touched bins
-// (Stats: active_bin_count, main.c:1245). tm / touch are the values loaded from tile_min[bin] / bin_touch[bin].
+// "Touched in this draw" (Stats: active_bin_count counts the bins that received a pair, Hi-Z-rejected or not, main.c:1245)
+// is one BYTE per bin in the DRAW CONTEXT's touch map: it depends on nothing an earlier draw leaves behind, so the FRONT
+// half raises the bytes (for rectangles of at most 8 tiles; larger ones are expanded by the back half, which raises theirs)
+// and a triangle hidden by Hi-Z costs the back half nothing for it. Plain idempotent byte stores: no read-modify-write,
+// the lanes of a warp that store to the same bin merge in the load/store unit (one bit per bin with atomicOr serialised
+// on the 32 bins sharing a word: 100 us per draw). The draw's k_tile counts the bytes and clears the map.
+// `seen` is the value loaded from touch[bin] (L2: a stale 0 only repeats the store).
+__device__ __forceinline__ void touch_bin(uint8_t *touch, uint32_t bin, uint32_t seen) {
+	if(!seen) touch[bin] = 1;
+}
+template <int N>
+__device__ __forceinline__ void touch_small_rect(uint8_t *touch_bits, const Partition &part, int wt, const TileRect &tr, int cnt) {
+	uint32_t bins[N], word[N];
+	bool ok[N];
+	int tx = tr.tx0, ty = tr.ty0;
+#pragma unroll
+	for(int k = 0; k < N; ++k) {
+		ok[k] = k < cnt && part.owns_row(ty);
+		bins[k] = (uint32_t)(ty * wt + tx);
+		if(++tx > tr.tx1) {
+			tx = tr.tx0;
+			++ty;
+		}
+	}
+#pragma unroll
+	for(int k = 0; k < N; ++k) word[k] = ok[k] ? (uint32_t)__ldcg(touch_bits + bins[k]) : 1u;
+#pragma unroll
+	for(int k = 0; k < N; ++k)
+		if(ok[k]) touch_bin(touch_bits, bins[k], word[k]);
+}
+// (front half) the touch bits of a triangle whose tile rectangle holds 1..8 tiles
+__device__ __forceinline__ void touch_rect(uint8_t *touch_bits, const Partition &part, int wt, const TileRect &tr, int cnt) {
+	if(cnt <= 0 || cnt > 8) return;
+	if(cnt <= 4) touch_small_rect<4>(touch_bits, part, wt, tr, cnt);
+	else touch_small_rect<8>(touch_bits, part, wt, tr, cnt);
+}
+
+// One (triangle, tile) pair of the back half. tm is the value loaded from tile_min[bin].
 template <typename Params>
-__device__ __forceinline__ void count_pair(const Params &P, uint32_t bin, float tm, uint32_t touch, float max_depth, uint32_t epoch, BinTally &r) {
+__device__ __forceinline__ void count_pair(const Params &P, uint32_t bin, float tm, float max_depth, BinTally &r) {
 	const bool rejected = !P.keep_all && (max_depth < tm); // Hi-Z (main.c:1006)
-	if(touch != epoch) atomicMax(P.bin_touch + bin, epoch); // (result unused: a reduction nobody waits for; plain stores were slower)
 	if(!rejected) {
 		atomicAdd(P.bin_count + bin, 1u);
 		r.live = true;
@@ -292,7 +351,7 @@ __device__ __forceinline__ void count_pair(const Params &P, uint32_t bin, float 
 // loads of all tiles are independent and in flight together (they were a chain of dependent L2 round trips), then
 // issue the atomics.
 template <int N>
-__device__ __forceinline__ void count_small_rect(const GeomParams &P, const TileRect &tr, int cnt, float max_depth, uint32_t epoch, BinTally &r) {
+__device__ __forceinline__ void count_small_rect(const GeomParams &P, const TileRect &tr, int cnt, float max_depth, BinTally &r) {
 	uint32_t bins[N];
 	bool ok[N];
 	{
@@ -308,18 +367,14 @@ __device__ __forceinline__ void count_small_rect(const GeomParams &P, const Tile
 		}
 	}
 	float tm[N];
-	uint32_t tc[N];
 #pragma unroll
-	for(int k = 0; k < N; ++k) {
-		tm[k] = ok[k] ? __ldg(P.tile_min + bins[k]) : 0.0f;
-		tc[k] = ok[k] ? __ldcg(P.bin_touch + bins[k]) : epoch;
-	}
+	for(int k = 0; k < N; ++k) tm[k] = ok[k] ? __ldg(P.tile_min + bins[k]) : 0.0f;
 #pragma unroll
 	for(int k = 0; k < N; ++k)
-		if(ok[k]) count_pair(P, bins[k], tm[k], tc[k], max_depth, epoch, r);
+		if(ok[k]) count_pair(P, bins[k], tm[k], max_depth, r);
 }
 
-__device__ __forceinline__ BinTally count_bins(const GeomParams &P, const TileRect &tr, float max_depth, uint32_t epoch) {
+__device__ __forceinline__ BinTally count_bins(const GeomParams &P, const TileRect &tr, float max_depth) {
 	BinTally r = { false, false, false, false, 0u };
 	const int cnt = tr.w() * tr.h();
 	if(cnt <= 0) return r;
@@ -331,8 +386,8 @@ __device__ __forceinline__ BinTally count_bins(const GeomParams &P, const TileRe
 	}
 	// dense meshes of pixel-sized triangles (BASELINE config 5: 2.2 tiles per triangle) almost never need more than
 	// four steps; the eight-step walk costs a third of the kernel's instructions when every lane pays for it
-	if(cnt <= 4) count_small_rect<4>(P, tr, cnt, max_depth, epoch, r);
-	else count_small_rect<8>(P, tr, cnt, max_depth, epoch, r);
+	if(cnt <= 4) count_small_rect<4>(P, tr, cnt, max_depth, r);
+	else count_small_rect<8>(P, tr, cnt, max_depth, r);
 	return r;
 }
 
@@ -559,7 +614,7 @@ __device__ __forceinline__ uint32_t clip_code(const float4 p) {
 
 template <int VS>
 __global__ void __launch_bounds__(256) k_vertex(const __grid_constant__ GeomParams P, uint32_t vertex_count) {
-	pdl_prologue();
+	MLV_KERNEL_PROLOGUE(P.timeline);
 	__shared__ float s_cb[48];
 	const float *cb = stage_constants(P, s_cb);
 	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -605,9 +660,49 @@ __device__ __forceinline__ void queue_big(const GeomParams &P, int big_class, ui
 	if(big_class == 2) P.huge_queue[atomicAdd(&P.dctr->huge_count, 1u)] = slot; // rare: sky domes, full-screen quads
 }
 
+// WARP SUMMARY of 32 consecutive direct slots, 16 bytes {tx0 | ty0 << 16, tx1 | ty1 << 16, max of max_depth, flags}: the
+// union of the tile rectangles and the nearest depth bound of the slots that bin something on this rank through a
+// rectangle of at most 8 tiles. The back half tests the summary against the tile minima first: when the nearest depth of
+// the 32 triangles lies behind every tile of the union, each of their (triangle, tile) pairs fails the Hi-Z test
+// (max_depth <= summary depth < tile_min, main.c:1006) and none of them needs its bounds, its tile look-ups or a record
+// -- a draw hidden behind earlier ones costs the draw-to-draw chain one 16-byte load and a few tile minima per 32 triangles.
+// flags == 0: nothing to bin in these slots.
+#define MLV_WS_SMALL 1u /* the rectangle / depth words are valid */
+#define MLV_WS_FINE 2u  /* a slot needs the per-triangle path whatever the coarse test says */
+__device__ __forceinline__ void write_warp_summary(const GeomParams &P, uint32_t t, uint32_t flags, uint32_t tx0, uint32_t ty0, uint32_t tx1, uint32_t ty1, uint32_t depth_bits) {
+	const uint32_t f = __reduce_or_sync(0xffffffffu, flags);
+	uint4 ws = make_uint4(0u, 0u, 0u, f);
+	if(f & MLV_WS_SMALL) {
+		const uint32_t wx0 = __reduce_min_sync(0xffffffffu, tx0), wy0 = __reduce_min_sync(0xffffffffu, ty0);
+		const uint32_t wx1 = __reduce_max_sync(0xffffffffu, tx1), wy1 = __reduce_max_sync(0xffffffffu, ty1);
+		ws.x = wx0 | (wy0 << 16);
+		ws.y = wx1 | (wy1 << 16);
+		ws.z = __reduce_max_sync(0xffffffffu, depth_bits); // non-negative floats order like their bit patterns
+		// ---- the touch bytes of these triangles (touch_bin): neighbours in mesh order share their bins, so the warp merges the
+		// rectangles of its lanes into one mask over the union and raises every bin once -- one predicated byte store per warp
+		// instead of a look-up and a store per (triangle, tile) pair (22 us per 1.25 M-triangle draw)
+		const uint32_t w = wx1 - wx0 + 1u, cnt = w * (wy1 - wy0 + 1u);
+		if(cnt <= 32u) {
+			uint32_t mask = 0u;
+			if(flags & MLV_WS_SMALL) {
+				const uint32_t row = (1u << (tx1 - tx0 + 1u)) - 1u; // at most 8 tiles wide
+				for(uint32_t ty = ty0; ty <= ty1; ++ty)
+					if(P.part.owns_row((int)ty)) mask |= row << ((ty - wy0) * w + (tx0 - wx0));
+			}
+			mask = __reduce_or_sync(0xffffffffu, mask);
+			const uint32_t lane = lane_id();
+			if((mask >> lane) & 1u) P.touch_bits[(wy0 + lane / w) * (uint32_t)P.wt + wx0 + lane % w] = 1;
+		} else if(flags & MLV_WS_SMALL) { // a scattered mesh order
+			const TileRect tr = { (int)tx0, (int)ty0, (int)tx1, (int)ty1 };
+			touch_rect(P.touch_bits, P.part, P.wt, tr, tr.w() * tr.h());
+		}
+	}
+	if(lane_id() == 0 && t < P.tri_count) P.warp_sum[t >> 5] = ws;
+}
+
 template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
 __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_constant__ GeomParams P) {
-	pdl_prologue();
+	MLV_KERNEL_PROLOGUE(P.timeline);
 	__shared__ float s_cb[48];
 	const float *cb = stage_constants(P, s_cb);
 	const uint32_t lane = lane_id();
@@ -625,7 +720,11 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_cons
 		bool live = false;
 		if(c < num_chunks) {
 			live = !chunk_is_foreign(P, cb, c);
-			P.chunk_live[c] = live ? 1 : 0; // the back half and the fill phase skip the stale bounds of the chunks nobody rewrote
+			P.chunk_live[c] = live ? 1 : 0; // the fill phase skips the stale bounds of the chunks nobody rewrote
+			if(!live) { // ... and the back half their warp summaries
+				const uint32_t n_ws = (P.tri_count + 31u) / 32u;
+				for(uint32_t i = c * (MLV_GEOM_THREADS / 32u); i < min((c + 1u) * (MLV_GEOM_THREADS / 32u), n_ws); ++i) reinterpret_cast<uint32_t *>(P.warp_sum + i)[3] = 0u;
+			}
 		}
 		s_live[threadIdx.x] = live ? 1 : 0;
 		__syncthreads();
@@ -637,6 +736,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_cons
 	const uint32_t t = chunk * MLV_GEOM_THREADS + threadIdx.x;
 	bool needs_clip = false;
 	int big_class = 0; // 1: tile rectangle of 9 .. MLV_HUGE_TILES tiles, 2: larger
+	uint32_t ws_flags = 0u, ws_tx0 = 0xffffu, ws_ty0 = 0xffffu, ws_tx1 = 0u, ws_ty1 = 0u, ws_depth = 0u; // this lane's share of the warp summary
 	if(t < P.tri_count) {
 		uint4 bounds = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, t << 3);
 		// ---- input assembler (main.c:662-696): index fetch + first half of each vertex (or its cache entry)
@@ -714,6 +814,13 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_cons
 					}
 					const int cnt = tr.w() * tr.h();
 					if(np && cnt > 8) big_class = cnt > MLV_HUGE_TILES ? 2 : 1;
+					if(np || DEBUG) {
+						// rectangles of more than 8 tiles get their record whatever Hi-Z says (count_bins); a negative or NaN depth
+						// bound does not order like its bit pattern: both make the back half look at the triangles of this warp
+						if(DEBUG || cnt > 8 || !(S.max_depth >= 0.0f)) ws_flags = MLV_WS_FINE;
+						else ws_flags = MLV_WS_SMALL, ws_tx0 = (uint32_t)tr.tx0, ws_ty0 = (uint32_t)tr.ty0, ws_tx1 = (uint32_t)tr.tx1, ws_ty1 = (uint32_t)tr.ty1, ws_depth = __float_as_uint(S.max_depth);
+					}
+					if(np && ws_flags != MLV_WS_SMALL) touch_rect(P.touch_bits, P.part, P.wt, tr, cnt); // (the warp raises the touch bytes of its MLV_WS_SMALL lanes together, write_warp_summary)
 				}
 			} else {
 				needs_clip = true;
@@ -735,6 +842,7 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_front(const __grid_cons
 		}
 		queue_big(P, big_class, t);
 	}
+	write_warp_summary(P, t, ws_flags, ws_tx0, ws_ty0, ws_tx1, ws_ty1, ws_depth);
 	}
 	if(P.chunk_bounds) __syncthreads(); // s_live is rewritten by the next round
 	}
@@ -759,6 +867,7 @@ __device__ __forceinline__ uint32_t emit_fan(const GeomParams &P, uint32_t t, co
 			pairs += np;
 			{
 				const int cnt = tr.w() * tr.h();
+				if(np) touch_rect(P.touch_bits, P.part, P.wt, tr, cnt);
 				if(np && cnt > 8) { // (lanes diverge here: plain atomics)
 					if(cnt > MLV_HUGE_TILES) P.huge_queue[atomicAdd(&P.dctr->huge_count, 1u)] = slot;
 					else P.big_queue[atomicAdd(&P.dctr->big_count, 1u)] = slot;
@@ -793,7 +902,7 @@ template <int VS, bool INDEXED>
 __global__ void __launch_bounds__(MLV_CLIP_THREADS) k_front_clip(const __grid_constant__ GeomParams P) {
 	__shared__ float s_poly[2][MLV_CLIP_MAXV * 9 * MLV_CLIP_THREADS];
 	__shared__ float s_cb[48];
-	pdl_prologue();
+	MLV_KERNEL_PROLOGUE(P.timeline);
 	const float *cb = stage_constants(P, s_cb);
 	const uint32_t n = P.dctr->clip_count;
 	const uint32_t lane = lane_id();
@@ -875,8 +984,7 @@ __device__ __forceinline__ SlotBounds load_bounds(const uint4 *__restrict__ tri_
 // Pass 1 of the binner (main.c:924-936) for the triangles whose tile rectangle holds more than 8 tiles (queued by the
 // front half). Rectangles of up to MLV_HUGE_TILES tiles: one warp per triangle, lanes stride over the rectangle with four
 // tiles in flight. Larger ones (sky domes, full-screen quads): the whole grid strides over the rectangle.
-__device__ __forceinline__ void count_big_rects(const GeomParams &P, uint32_t epoch, BackState &st) {
-	const uint32_t n = P.dctr->big_count, nhuge = P.dctr->huge_count;
+__device__ __forceinline__ void count_big_rects(const GeomParams &P, BackState &st, uint32_t n, uint32_t nhuge) {
 	if((n | nhuge) == 0u) return;
 	const uint32_t lane = lane_id();
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -887,7 +995,7 @@ __device__ __forceinline__ void count_big_rects(const GeomParams &P, uint32_t ep
 			const int ty = s.tr.ty0 + k / w, tx = s.tr.tx0 + k % w;
 			ok = P.part.owns_row(ty);
 			bin = (uint32_t)(ty * P.wt + tx);
-			if(ok) tm = __ldg(P.tile_min + bin), tc = __ldcg(P.bin_touch + bin);
+			if(ok) tm = __ldg(P.tile_min + bin), tc = (uint32_t)__ldcg(P.touch_bits + bin);
 		}
 	};
 	auto expand = [&](const SlotBounds &s, int first, int stride) {
@@ -902,7 +1010,8 @@ __device__ __forceinline__ void count_big_rects(const GeomParams &P, uint32_t ep
 #pragma unroll
 			for(int u = 0; u < 4; ++u)
 				if(ok[u]) {
-					count_pair(P, bin[u], tm[u], tc[u], s.max_depth, epoch, r);
+					touch_bin(P.touch_bits, bin[u], tc[u]);
+					count_pair(P, bin[u], tm[u], s.max_depth, r);
 				}
 		}
 	};
@@ -913,7 +1022,7 @@ __device__ __forceinline__ void count_big_rects(const GeomParams &P, uint32_t ep
 }
 
 template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
-__device__ __forceinline__ void back_process(const GeomParams &P, uint4 (*s_stage)[32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)], uint32_t slot, uint4 b, uint32_t epoch, const float *cb, BackState &st) {
+__device__ __forceinline__ void back_process(const GeomParams &P, uint4 (*s_stage)[32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)], uint32_t slot, uint4 b, const float *cb, BackState &st) {
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 	bool staged = false, live = false, present = false;
 	TileRect tr = { 0, 0, -1, -1 };
@@ -924,7 +1033,7 @@ __device__ __forceinline__ void back_process(const GeomParams &P, uint4 (*s_stag
 		max_depth = __uint_as_float(b.z);
 		tr = tile_rect(minx, miny, maxx, maxy, P.wt, P.ht);
 		// ---- binner pass 1 + Hi-Z for this triangle
-		const BinTally tally = count_bins(P, tr, max_depth, epoch);
+		const BinTally tally = count_bins(P, tr, max_depth);
 		live = tally.live; // (rectangles of more than 8 tiles: counted below by a warp each, from the front half's queue)
 		st.survivors += tally.survivors;
 		st.wake = st.wake || tally.wake;
@@ -998,51 +1107,99 @@ __device__ __forceinline__ void back_process(const GeomParams &P, uint4 (*s_stag
 	__syncwarp(); // the staging rows are reused by the next chunk
 }
 
+// Coarse Hi-Z of one warp summary (see write_warp_summary) by TWO adjacent lanes, each looking at up to 16 tiles of the
+// union rectangle, so that all tile minima of a summary are requested at once: true when the 32 slots need the
+// per-triangle path (the same answer in both lanes).
+#define MLV_BACK_GROUP 128u /* warp summaries a CTA tests per round (4096 triangles) */
+__device__ __forceinline__ bool summary_needs_triangles(const GeomParams &P, uint32_t wsi, bool in_range, uint32_t sub) {
+	uint4 ws = make_uint4(0u, 0u, 0u, 0u);
+	if(in_range) ws = __ldcg(P.warp_sum + wsi);
+	// ws.w == 0: nothing to bin in these slots (or: a chunk the front half culled on this rank)
+	bool need = ws.w != 0u, test = false;
+	int hidden = 1;
+	if(need && !(ws.w & MLV_WS_FINE) && !P.keep_all) {
+		const int tx0 = (int)(ws.x & 0xffffu), ty0 = (int)(ws.x >> 16), tx1 = (int)(ws.y & 0xffffu), ty1 = (int)(ws.y >> 16);
+		const int w = tx1 - tx0 + 1, cnt = w * (ty1 - ty0 + 1);
+		if(cnt <= 32) { // (more: a scattered mesh order, the union says little)
+			test = true;
+			const float nearest = __uint_as_float(ws.z);
+			const int k0 = (int)sub * 16;
+			int tx = tx0 + k0 % w, ty = ty0 + k0 / w;
+			float tm[16];
+			bool ok[16];
+#pragma unroll
+			for(int u = 0; u < 16; ++u) {
+				// (sort-first: rows of other ranks inside the union are tested like owned ones -- their minima still carry the
+				// clear tag here, so a warp that straddles a band border takes the per-triangle path; asking owns_row per tile
+				// cost 32 integer divisions per lane, 3 us of the kernel)
+				ok[u] = k0 + u < cnt;
+				tm[u] = ok[u] ? __ldg(P.tile_min + (uint32_t)(ty * P.wt + tx)) : 0.0f;
+				if(++tx > tx1) {
+					tx = tx0;
+					++ty;
+				}
+			}
+#pragma unroll
+			for(int u = 0; u < 16; ++u) // count_pair's test with the nearest depth of the 32 triangles; a tile that still carries the clear tag hides nothing (wake logic)
+				if(ok[u] && !((nearest < tm[u]) && __float_as_uint(tm[u]) != MLV_TILE_MIN_CLEARED)) hidden = 0;
+		}
+	}
+	// the two lanes of a summary agree on everything but `hidden`
+	hidden &= __shfl_xor_sync(0xffffffffu, hidden, 1);
+	if(test) {
+		need = hidden == 0;
+		if(hidden && sub == 0u) reinterpret_cast<uint32_t *>(P.warp_sum + wsi)[3] = 0u; // the fill pass skips these slots as well
+	}
+	return need;
+}
+
 template <int VS, bool INDEXED, bool DEBUG, bool VCACHE>
 __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_back(const __grid_constant__ GeomParams P) {
-	pdl_prologue();
+	MLV_KERNEL_PROLOGUE(P.timeline);
 	__shared__ uint4 s_stage[MLV_GEOM_THREADS / 32][32 * (MLV_TRI_COV_U4 + MLV_TRI_SHADE_U4)];
-	__shared__ uint32_t s_list[MLV_GEOM_THREADS]; // the live chunks of this round, compacted
+	__shared__ uint32_t s_list[MLV_BACK_GROUP]; // the warp summaries of this round that need their triangles, compacted
 	__shared__ uint32_t s_warp_count[MLV_GEOM_THREADS / 32];
 	__shared__ float s_cb[48];
 	const float *cb = stage_constants(P, s_cb);
 	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-	const uint32_t epoch = P.ctr->epoch;        // both loads are in flight with the first chunk's bounds;
-	const uint32_t ovf_raw = P.dctr->ovf_count; // the overflow count is only needed after the direct slots
-	const uint32_t direct_chunks = (P.tri_count + MLV_GEOM_THREADS - 1u) / MLV_GEOM_THREADS;
+	const uint32_t ovf_raw = P.dctr->ovf_count, n_big = P.dctr->big_count, n_huge = P.dctr->huge_count; // (in flight with the first summaries; only needed after the direct slots)
+	// CTA g takes the summaries j * gridDim.x + g: every CTA samples the whole draw (sort-first: a rank's live triangles are
+	// one contiguous run of the mesh order; contiguous groups would leave most CTAs without work), MLV_BACK_GROUP of them
+	// per round -- one round for draws of up to gridDim.x * 4096 triangles (2.4 M on a B200).
+	const uint32_t n_ws = (P.tri_count + 31u) / 32u, per_cta = (n_ws + gridDim.x - 1u) / gridDim.x;
 	BackState st = { 0u, 0u, false };
-	for(uint32_t first = blockIdx.x; first < direct_chunks; first += gridDim.x * MLV_GEOM_THREADS) {
-		// Thread k looks up the k-th chunk of this CTA's round. Sort-first: chunks the front half skipped on this rank hold
-		// stale bounds from an earlier draw -- they are dropped here, at the cost of one load for the whole round.
-		const uint32_t cand = first + threadIdx.x * gridDim.x;
-		const bool live_chunk = cand < direct_chunks && (!P.chunk_live || __ldg(P.chunk_live + cand) != 0);
-		const uint32_t m = __ballot_sync(0xffffffffu, live_chunk);
+	for(uint32_t j0 = 0; j0 < per_cta; j0 += MLV_BACK_GROUP) {
+		// ---- phase 1, two lanes per warp summary: coarse Hi-Z. The front half cleared the summaries of the chunks it culled.
+		const uint32_t wsi = (j0 + (threadIdx.x >> 1)) * gridDim.x + blockIdx.x, sub = threadIdx.x & 1u;
+		const bool fine = summary_needs_triangles(P, wsi, wsi < n_ws, sub) && sub == 0u;
+		const uint32_t m = __ballot_sync(0xffffffffu, fine);
 		if(lane == 0) s_warp_count[warp] = (uint32_t)__popc(m);
 		__syncthreads();
 		uint32_t before = 0, total = 0;
 #pragma unroll
-		for(uint32_t w = 0; w < MLV_GEOM_THREADS / 32; ++w) {
+		for(uint32_t w = 0; w < MLV_GEOM_THREADS / 32u; ++w) {
 			const uint32_t cnt = s_warp_count[w];
 			before += (w < warp) ? cnt : 0u;
 			total += cnt;
 		}
-		if(live_chunk) s_list[before + (uint32_t)__popc(m & ((1u << lane) - 1u))] = cand;
+		if(fine) s_list[before + (uint32_t)__popc(m & ((1u << lane) - 1u))] = wsi;
 		__syncthreads();
+		// ---- phase 2, one warp per listed summary: the per-triangle path, the bounds of the warp's next item in flight
 		const uint4 empty = make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, 0u);
 		uint4 b_next = empty;
-		if(total) {
-			const uint32_t s0 = s_list[0] * MLV_GEOM_THREADS + threadIdx.x;
+		if(warp < total) {
+			const uint32_t s0 = s_list[warp] * 32u + lane;
 			if(s0 < P.tri_count) b_next = P.tri_bounds[s0];
 		}
-		for(uint32_t i = 0; i < total; ++i) {
-			const uint32_t slot = s_list[i] * MLV_GEOM_THREADS + threadIdx.x;
+		for(uint32_t i = warp; i < total; i += MLV_GEOM_THREADS / 32u) {
+			const uint32_t slot = s_list[i] * 32u + lane;
 			const uint4 b = b_next;
 			b_next = empty;
-			if(i + 1u < total) {
-				const uint32_t sn = s_list[i + 1u] * MLV_GEOM_THREADS + threadIdx.x;
+			if(i + MLV_GEOM_THREADS / 32u < total) {
+				const uint32_t sn = s_list[i + MLV_GEOM_THREADS / 32u] * 32u + lane;
 				if(sn < P.tri_count) b_next = P.tri_bounds[sn];
 			}
-			back_process<VS, INDEXED, DEBUG, VCACHE>(P, s_stage, slot, b, epoch, cb, st);
+			back_process<VS, INDEXED, DEBUG, VCACHE>(P, s_stage, slot, b, cb, st);
 		}
 		__syncthreads(); // s_list is rewritten by the next round
 	}
@@ -1051,10 +1208,10 @@ __global__ void __launch_bounds__(MLV_GEOM_THREADS, 4) k_back(const __grid_const
 	for(uint32_t base = blockIdx.x * MLV_GEOM_THREADS; base < n_ovf; base += gridDim.x * MLV_GEOM_THREADS) {
 		const uint32_t o = base + threadIdx.x;
 		const uint4 b = (o < n_ovf) ? P.tri_bounds[P.tri_count + o] : make_uint4(MLV_BOUNDS_EMPTY, 0u, 0u, 0u);
-		back_process<VS, INDEXED, DEBUG, VCACHE>(P, s_stage, P.tri_count + o, b, epoch, cb, st);
+		back_process<VS, INDEXED, DEBUG, VCACHE>(P, s_stage, P.tri_count + o, b, cb, st);
 	}
 	// ---- rectangles of more than 8 tiles (the front half queued them): a warp each, spread over the whole grid
-	count_big_rects(P, epoch, st);
+	count_big_rects(P, st, n_big, n_huge);
 	// ---- per-draw tallies: records written (work counter, one atomic per warp); "a pair survived Hi-Z" (the scan, the fill
 	// pass and the tile kernel return at once otherwise)
 #pragma unroll
@@ -1114,7 +1271,7 @@ __device__ __forceinline__ void fill_small_rect(const TailParams &P, const SlotB
 }
 
 __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ TailParams P) {
-	pdl_prologue();
+	MLV_KERNEL_PROLOGUE(P.timeline ? P.timeline + 4 : nullptr);
 	const uint32_t total = P.ctr->pair_total;
 	// draw skipped (pair arena or overflow slots exhausted: k_tile raises the flag) / nothing survived Hi-Z
 	if(total == 0u || total > P.pair_capacity || P.dctr->ovf_count > P.ovf_capacity) return;
@@ -1127,7 +1284,9 @@ __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ TailParams
 		s.empty = true;
 		// slots of chunks the front half skipped on this rank hold stale bounds from an earlier draw
 		const bool live_chunk = !P.chunk_live || slot >= P.direct_slots || __ldg(P.chunk_live + slot / MLV_GEOM_THREADS) != 0;
-		if(slot < n && live_chunk) s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
+		// 32 direct slots whose warp summary says "nothing to bin" (the front half) or "hidden by Hi-Z" (the back half's coarse test)
+		const bool summarised_out = base + 32u <= P.direct_slots && live_chunk && __ldg(P.warp_sum + (base >> 5) * 4u + 3u) == 0u;
+		if(slot < n && live_chunk && !summarised_out) s = load_bounds(P.tri_bounds, slot, P.wt, P.ht);
 		const int w = s.empty ? 0 : s.tr.w(), cnt = s.empty ? 0 : w * s.tr.h();
 		if(cnt > 0 && cnt <= 4) fill_small_rect<4>(P, s, cnt, slot);
 		else if(cnt > 0 && cnt <= 8) fill_small_rect<8>(P, s, cnt, slot);
@@ -1208,7 +1367,7 @@ __device__ __forceinline__ uint32_t lookback_exclusive(volatile unsigned long lo
 #define MLV_SCAN_THREADS 1024
 #define MLV_SCAN_ITEMS 4
 __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_constant__ TailParams P) {
-	pdl_prologue();
+	MLV_KERNEL_PROLOGUE(P.timeline);
 	if(P.ctr->draw_alive == 0u && P.ctr->n_wake == 0u) return; // nothing survived Hi-Z in this draw: there is nothing to lay out (k_fill and k_tile return as well)
 	__shared__ uint32_t s_tile;
 	__shared__ uint32_t s_sum[32], s_nz[32];
@@ -1238,7 +1397,7 @@ __global__ void __launch_bounds__(MLV_SCAN_THREADS) k_bin_scan(const __grid_cons
 		c[k] = raw[k];
 		// (a touched bin without surviving pairs whose tile minimum still carries the clear tag is visited for write_tile's
 		// refresh, main.c:589-603; it takes a pair with negative depth, the back half counts such bins in n_wake)
-		work[k] = c[k] != 0u || (n_wake != 0u && base + k < P.bin_end && P.bin_touch[base + k] == epoch && __float_as_uint(P.tile_min[base + k]) == MLV_TILE_MIN_CLEARED);
+		work[k] = c[k] != 0u || (n_wake != 0u && base + k < P.bin_end && P.touch_bits[base + k] != 0 && __float_as_uint(P.tile_min[base + k]) == MLV_TILE_MIN_CLEARED);
 		tsum += c[k];
 		twork += work[k] ? 1u : 0u;
 	}
@@ -1700,7 +1859,6 @@ __device__ __forceinline__ void finish_draw(const TailParams &P, bool skipped, b
 	next_epoch = __shfl_sync(0xffffffffu, next_epoch, 0);
 	if(next_epoch == 0u) {
 		for(uint32_t i = lane; i < 2u * P.scan_blocks; i += 32u) P.state_sum[i] = 0ull; // (state_nz follows state_sum)
-		for(uint32_t i = lane; i < P.num_bins; i += 32u) P.bin_touch[i] = 0u;
 		next_epoch = 1u;
 	}
 	if(lane == 0) {
@@ -1730,14 +1888,20 @@ __device__ __forceinline__ void finish_draw(const TailParams &P, bool skipped, b
 template <int PS>
 __global__ void __launch_bounds__(MLV_TILE_THREADS, 4) k_tile(const __grid_constant__ TailParams P) {
 	__shared__ RowCovWarp s_rowcov[MLV_TILE_THREADS / 32];
-	pdl_prologue();
+	MLV_KERNEL_PROLOGUE(P.timeline ? P.timeline + 8 : nullptr);
 	Counters *c = P.ctr;
 	const uint32_t total = c->pair_total, n_cbins = c->n_cbins;
 	const bool skipped = total > P.pair_capacity || P.dctr->ovf_count > P.ovf_capacity; // MLV_FLAG_PAIR_OVERFLOW / MLV_FLAG_TRI_OVERFLOW: the draw is skipped as a whole
-	const uint32_t epoch = c->epoch;
 	// Stats: the bins this draw touched (every thread of the grid looks at its share: one load, in flight with the ones above)
 	uint32_t touched = 0;
-	for(uint32_t b = P.bin_begin + blockIdx.x * blockDim.x + threadIdx.x; b < P.bin_end; b += gridDim.x * blockDim.x) touched += (__ldcg(P.bin_touch + b) == epoch) ? 1u : 0u;
+	for(uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < (P.num_bins + 3u) / 4u; w += gridDim.x * blockDim.x) { // (the map is padded to a multiple of 4 bytes)
+		uint32_t *word = reinterpret_cast<uint32_t *>(P.touch_bits) + w;
+		const uint32_t bytes = __ldcg(word);
+		if(bytes) {
+			touched += (uint32_t)__popc(bytes & 0x01010101u);
+			*word = 0u; // the context's map is clean again for the front half of a later draw
+		}
+	}
 	if(!skipped && n_cbins) tile_phase<PS>(P, s_rowcov, n_cbins);
 	// The LAST CTA to get here folds the draw's Stats and re-arms the per-draw counters: CTAs of this grid that start late
 	// (the grid may exceed what is resident at once) must still find pair_total / n_cbins as the scan left them. One 64-bit

@@ -109,6 +109,8 @@ struct DrawCtx {
 	uint32_t vcache_capacity;
 	uint8_t *chunk_live;
 	uint32_t chunk_capacity;
+	uint8_t *touch_bits;  // one byte per bin: raised by the front half (and the back half's large rectangles), counted + cleared by k_tile
+	uint4 *warp_sum;      // 16 B per 32 direct slots (slot_capacity / 32 + 1 entries)
 	DrawCounters *dctr;
 	unsigned long long *stat_stripes; // Stats contributions of the draw, folded into Stats by its k_tile (main-stream order)
 	cudaEvent_t front_done, free_ev;
@@ -138,7 +140,7 @@ struct mlv_device {
 	bool xchg_pending;         // mlv_composite_join has not yet been called for the last mlv_composite_broadcast_async
 	float *tile_min;
 	// per-draw arenas
-	uint32_t *bin_count, *bin_offset, *bin_touch;
+	uint32_t *bin_count, *bin_offset;
 	unsigned long long *scan_state; // 2 x scan_blocks look-back words
 	uint32_t scan_blocks;
 	mlv_ref_compacted_bin *cbins;
@@ -156,6 +158,7 @@ struct mlv_device {
 	bool front_needs_sync[MLV_DRAW_CONTEXTS];      // per front stream: not yet ordered after what the main stream held when reset_front_order ran (creation, a graph execution)
 	bool front_touched[MLV_DRAW_CONTEXTS];         // per front stream: has joined the capture of the command list being recorded
 	cudaEvent_t ev_front_join[MLV_DRAW_CONTEXTS];
+	int prio_chain, prio_front, knob_explicit_priority; // launch priorities of the draw-to-draw chain and of the front halves
 	int knob_no_pdl_tile, knob_no_pdl_back;           // the front stream has not yet been ordered after what the main stream holds (creation, a graph execution)
 	std::vector<void *> *graveyard;  // arenas replaced while command lists that address them exist
 	uint32_t lists_alive;
@@ -214,6 +217,12 @@ struct mlv_device {
 	// command-list recording (mlv_begin_command_list .. mlv_finish_command_list): the device stream is in CUDA stream capture
 	mlv_command_list *recording;
 
+	// device-side timeline (mlv_timeline_*): 4 words per launch issued or recorded while it is on
+	bool timeline_on;
+	unsigned long long *timeline;
+	uint32_t timeline_used;
+	std::vector<int> *timeline_stages; // stage << 16 | draw ordinal of the frame
+	uint32_t timeline_draw;
 	// per-stage profiling (mlv_profile_begin/end)
 	bool prof_on;
 	std::vector<cudaEvent_t> *prof_events; // pairs (start, end)
@@ -232,18 +241,38 @@ static void reset_front_order(mlv_device *dev) {
 
 // Every kernel goes through here: launched with programmatic stream serialisation (see pdl_prologue in kernels.cuh).
 static thread_local int g_pdl = 1; // 0: the next launches are plain stream-ordered launches
+static thread_local int g_launch_priority = 0;
+static thread_local bool g_launch_priority_set = false;
 template <typename... KArgs, typename... Args>
 static void launch_pdl(void (*kernel)(KArgs...), uint32_t grid, uint32_t block, cudaStream_t stream, Args &&...args) {
+	{ // One shared-memory carve-out for every kernel of the library. An SM changes its L1 / shared split only when it is
+		// idle, so a kernel whose CTAs need another split than the resident ones waits for whole SMs to drain: with the
+		// driver's per-kernel choice (k_front ~1 KB, k_tile 62 KB, k_back 150 KB of shared memory per SM) the back half of
+		// the visible draw became resident 50 us after its inputs were ready -- when the front halves running ahead had
+		// drained -- whatever the stream priorities said (device timeline, profiles/).
+		static std::vector<const void *> seen;
+		static const int carveout = getenv("MLV_SMEM_CARVEOUT") ? atoi(getenv("MLV_SMEM_CARVEOUT")) : 72; // percent of the maximum: 164 KB
+		const void *fn = (const void *)kernel;
+		if(carveout > 0 && std::find(seen.begin(), seen.end(), fn) == seen.end()) {
+			cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+			seen.push_back(fn);
+		}
+	}
 	cudaLaunchConfig_t cfg;
 	memset(&cfg, 0, sizeof(cfg));
 	cfg.gridDim = dim3(grid, 1, 1);
 	cfg.blockDim = dim3(block, 1, 1);
 	cfg.stream = stream;
-	cudaLaunchAttribute attr[1];
+	cudaLaunchAttribute attr[2];
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	attr[0].val.programmaticStreamSerializationAllowed = g_pdl;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
+	if(g_launch_priority_set) { // explicit per launch: recorded with the kernel node of a command list
+		attr[1].id = cudaLaunchAttributePriority;
+		attr[1].val.priority = g_launch_priority;
+		cfg.numAttrs = 2;
+	}
 	cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -300,6 +329,14 @@ static void prof_pre(mlv_device *dev, int stage) {
 	}
 	dev->prof_stages->push_back(stage);
 	cudaEventRecord((*dev->prof_events)[dev->prof_used], dev->stream);
+}
+
+// The next launch's slot of the device-side timeline (null when it is off or full).
+#define MLV_TIMELINE_CAPACITY 4096u
+static unsigned long long *timeline_slot(mlv_device *dev, int stage) {
+	if(!dev->timeline_on || dev->timeline_used >= MLV_TIMELINE_CAPACITY) return nullptr;
+	dev->timeline_stages->push_back((stage << 16) | (int)(dev->timeline_draw & 0xffffu));
+	return dev->timeline + 4 * (size_t)dev->timeline_used++;
 }
 
 static int check_launch(mlv_device *dev, const char *what) {
@@ -385,7 +422,18 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 		}                                         \
 	} while(0)
 
-	CREATE_TRY(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+	{ // The device stream carries the draw-to-draw dependency chain (back half, binning, tile kernel): its CTAs go first when
+		// SM slots free up. At equal priority the front halves running ahead on their own streams kept the chain's next kernel
+		// waiting for slots (device timeline, config 5: the visible draw's back half became resident 50 us after its inputs
+		// were ready, the first hidden draw's 37 us after the tile kernel before it had finished).
+		int prio_lo = 0, prio_hi = 0;
+		CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		const char *p = getenv("MLV_MAIN_PRIORITY");
+		CREATE_TRY(cudaStreamCreateWithPriority(&dev->stream, cudaStreamNonBlocking, (p && !atoi(p)) ? prio_lo : prio_hi));
+		dev->prio_chain = prio_hi;
+		dev->prio_front = prio_lo;
+		dev->knob_explicit_priority = getenv("MLV_EXPLICIT_PRIORITY") ? atoi(getenv("MLV_EXPLICIT_PRIORITY")) : 1;
+	}
 	dev->graveyard = new std::vector<void *>();
 	dev->num_ctx = (desc->flags & MLV_DEVICE_DEBUG_CAPTURE) ? 1u : MLV_DRAW_CONTEXTS;
 	{
@@ -416,6 +464,9 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 		CREATE_TRY(cudaMalloc(&c.stat_stripes, MLV_STAT_STRIPES * 128));
 		CREATE_TRY(cudaMemsetAsync(c.dctr, 0, sizeof(DrawCounters), dev->stream));
 		CREATE_TRY(cudaMemsetAsync(c.stat_stripes, 0, MLV_STAT_STRIPES * 128, dev->stream));
+		const size_t touch_bytes = ((size_t)dev->num_bins + 15) / 16 * 16;
+		CREATE_TRY(cudaMalloc(&c.touch_bits, touch_bytes));
+		CREATE_TRY(cudaMemsetAsync(c.touch_bits, 0, touch_bytes, dev->stream));
 	}
 	if(num_ranks > 1) {
 		int prio_lo = 0, prio_hi = 0; // the exchange is short and latency-critical: its CTAs go first when SM slots free up
@@ -436,8 +487,6 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	CREATE_TRY(cudaMalloc(&dev->pair_ids, dev->pair_capacity * sizeof(uint32_t)));
 	// (pair_tmp, the scratch of the debug-capture list sort, is allocated with the first debug draw)
 	CREATE_TRY(cudaMalloc(&dev->ctr, sizeof(Counters)));
-	CREATE_TRY(cudaMalloc(&dev->bin_touch, nb * sizeof(uint32_t)));
-	CREATE_TRY(cudaMemsetAsync(dev->bin_touch, 0, nb * sizeof(uint32_t), dev->stream));
 	dev->scan_blocks = (dev->bin_end - dev->bin_begin + MLV_SCAN_THREADS * MLV_SCAN_ITEMS - 1) / (MLV_SCAN_THREADS * MLV_SCAN_ITEMS);
 	if(dev->scan_blocks == 0) dev->scan_blocks = 1;
 	CREATE_TRY(cudaMalloc(&dev->scan_state, (size_t)dev->scan_blocks * 2 * sizeof(unsigned long long)));
@@ -494,14 +543,14 @@ void mlv_destroy_device(mlv_device *dev) {
 	if(dev->copy_stream) cudaStreamSynchronize(dev->copy_stream);
 	if(dev->xchg_stream) cudaStreamSynchronize(dev->xchg_stream);
 	for(int i = 0; i < dev->ipc_opened_count; ++i) cudaIpcCloseMemHandle(dev->ipc_opened[i]);
-	void *ptrs[] = { dev->fb_pair[0], dev->fb_pair[1], dev->tile_min, dev->bin_count, dev->bin_offset, dev->bin_touch, dev->scan_state, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade,
+	void *ptrs[] = { dev->fb_pair[0], dev->fb_pair[1], dev->tile_min, dev->bin_count, dev->bin_offset, dev->scan_state, dev->cbins, dev->pair_ids, dev->pair_tmp, dev->tri_cov, dev->tri_shade,
 		             dev->ctr, dev->rsqrt_lut, dev->dbg.tris, dev->dbg.attrs, dev->dbg.slot_key, dev->dbg.vs_out, dev->dbg.infos, dev->resolved_color, dev->resolved_depth, dev->gather, dev->p2p_color[0], dev->p2p_color[1], dev->p2p_flags };
 	for(void *p : ptrs)
 		if(p) cudaFree(p);
 	for(cudaEvent_t e : dev->ev_front_join)
 		if(e) cudaEventDestroy(e);
 	for(DrawCtx &c : dev->ctxs) {
-		for(void *p : { (void *)c.tri_bounds, (void *)c.big_queue, (void *)c.huge_queue, (void *)c.clip_queue, (void *)c.ovf_cov, (void *)c.ovf_shade, (void *)c.vcache, (void *)c.chunk_live, (void *)c.dctr, (void *)c.stat_stripes })
+		for(void *p : { (void *)c.tri_bounds, (void *)c.big_queue, (void *)c.huge_queue, (void *)c.clip_queue, (void *)c.ovf_cov, (void *)c.ovf_shade, (void *)c.vcache, (void *)c.chunk_live, (void *)c.touch_bits, (void *)c.warp_sum, (void *)c.dctr, (void *)c.stat_stripes })
 			if(p) cudaFree(p);
 		if(c.front_done) cudaEventDestroy(c.front_done);
 		if(c.free_ev) cudaEventDestroy(c.free_ev);
@@ -526,6 +575,8 @@ void mlv_destroy_device(mlv_device *dev) {
 		delete dev->prof_events;
 	}
 	delete dev->prof_stages;
+	if(dev->timeline) cudaFree(dev->timeline);
+	delete dev->timeline_stages;
 	delete dev;
 }
 
@@ -912,16 +963,22 @@ static void note_geom_func(mlv_device *dev, const void *func, bool is_vertex) {
 
 // The three geometry kernels of a draw for one vertex shader (template dispatch on indexed / debug capture / vertex cache).
 template <int VS>
-static void launch_front(mlv_device *dev, cudaStream_t fs, const GeomParams &gp, uint32_t nblocks, bool indexed, uint32_t vcache_vertices) {
+static void launch_front(mlv_device *dev, cudaStream_t fs, const GeomParams &gp_in, uint32_t nblocks, bool indexed, uint32_t vcache_vertices) {
+	GeomParams gp = gp_in; // (a copy per launch: each carries its own timeline slot)
 	const bool debug = gp.keep_all;
-	if(nblocks > dev->sm_count * 4u) nblocks = dev->sm_count * 4u; // persistent grid: 4 CTAs per SM stride over the chunks (sort-first: and cull them in place)
+	{ // persistent grid: CTAs stride over the chunks (sort-first: and cull them in place)
+		static const uint32_t per_sm = getenv("MLV_FRONT_CTAS_PER_SM") ? (uint32_t)atoi(getenv("MLV_FRONT_CTAS_PER_SM")) : 4u;
+		if(nblocks > dev->sm_count * per_sm) nblocks = dev->sm_count * per_sm;
+	}
 	if(vcache_vertices) {
 		prof_pre(dev, MLV_STAGE_VERTEX);
 		note_geom_func(dev, (const void *)k_vertex<VS>, true);
+		gp.timeline = timeline_slot(dev, MLV_STAGE_VERTEX);
 		launch_pdl(k_vertex<VS>, (vcache_vertices + 255u) / 256u, 256, fs, gp, vcache_vertices);
 		check_launch(dev, "k_vertex");
 	}
 	prof_pre(dev, MLV_STAGE_GEOMETRY);
+	gp.timeline = timeline_slot(dev, MLV_STAGE_GEOMETRY);
 	const void *f;
 	if(vcache_vertices) { f = (const void *)k_front<VS, true, false, true>; launch_pdl(k_front<VS, true, false, true>, nblocks, MLV_GEOM_THREADS, fs, gp); }
 	else if(indexed && debug) { f = (const void *)k_front<VS, true, true, false>; launch_pdl(k_front<VS, true, true, false>, nblocks, MLV_GEOM_THREADS, fs, gp); }
@@ -936,6 +993,7 @@ static void launch_front(mlv_device *dev, cudaStream_t fs, const GeomParams &gp,
 		uint32_t cb = (gp.tri_count * MLV_CLIP_SPLIT + MLV_CLIP_THREADS - 1u) / MLV_CLIP_THREADS;
 		if(cb > dev->sm_count * 4u) cb = dev->sm_count * 4u;
 		prof_pre(dev, MLV_STAGE_CLIP);
+		gp.timeline = timeline_slot(dev, MLV_STAGE_CLIP);
 		if(indexed) { f = (const void *)k_front_clip<VS, true>; launch_pdl(k_front_clip<VS, true>, cb, MLV_CLIP_THREADS, fs, gp); }
 		else { f = (const void *)k_front_clip<VS, false>; launch_pdl(k_front_clip<VS, false>, cb, MLV_CLIP_THREADS, fs, gp); }
 		note_geom_func(dev, f, false);
@@ -944,7 +1002,9 @@ static void launch_front(mlv_device *dev, cudaStream_t fs, const GeomParams &gp,
 }
 
 template <int VS>
-static void launch_back(mlv_device *dev, const GeomParams &gp, uint32_t nblocks, bool indexed, bool vcache) {
+static void launch_back(mlv_device *dev, const GeomParams &gp_in, uint32_t nblocks, bool indexed, bool vcache) {
+	GeomParams gp = gp_in;
+	gp.timeline = timeline_slot(dev, MLV_STAGE_BACK);
 	const bool debug = gp.keep_all;
 	if(nblocks > dev->sm_count * 4u) nblocks = dev->sm_count * 4u;
 	prof_pre(dev, MLV_STAGE_BACK);
@@ -1055,6 +1115,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 				CUDA_TRY(regrow(&c->tri_bounds, (size_t)cap));
 				CUDA_TRY(regrow(&c->big_queue, (size_t)cap));
 				CUDA_TRY(regrow(&c->huge_queue, (size_t)cap));
+				CUDA_TRY(regrow(&c->warp_sum, (size_t)cap / 32 + 1));
 				c->slot_capacity = cap;
 			}
 			if(T > c->queue_capacity) {
@@ -1151,7 +1212,8 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	gp.big_queue = ctx->big_queue;
 	gp.huge_queue = ctx->huge_queue;
 	gp.bin_count = dev->bin_count;
-	gp.bin_touch = dev->bin_touch;
+	gp.touch_bits = ctx->touch_bits;
+	gp.warp_sum = ctx->warp_sum;
 	gp.tile_min = dev->tile_min;
 	gp.keep_all = debug;
 	if(debug) gp.dbg = dev->dbg;
@@ -1200,6 +1262,8 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	}
 
 	// ---- front half (its own stream): k_vertex, k_front, k_front_clip
+	g_launch_priority_set = dev->knob_explicit_priority != 0;
+	g_launch_priority = dev->prio_front;
 	switch(dev->vs_id) {
 		case MLV_VS_PASSTHROUGH: launch_front<0>(dev, fs, gp, nblocks, indexed, vcache_vertices); break;
 		case MLV_VS_BASIC: launch_front<1>(dev, fs, gp, nblocks, indexed, vcache_vertices); break;
@@ -1213,6 +1277,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	}
 
 	// ---- back half (main stream: ordered after the previous draw's k_tile through the tile minima)
+	g_launch_priority = dev->prio_chain;
 	const uint32_t back_blocks = (need_slots + MLV_GEOM_THREADS - 1) / MLV_GEOM_THREADS;
 	switch(dev->vs_id) {
 		case MLV_VS_PASSTHROUGH: launch_back<0>(dev, gp, back_blocks, indexed, vcache_vertices != 0); break;
@@ -1231,7 +1296,8 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	tp.chunk_live = gp.chunk_live;
 	tp.tile_min = dev->tile_min;
 	tp.bin_count = dev->bin_count;
-	tp.bin_touch = dev->bin_touch;
+	tp.touch_bits = ctx->touch_bits;
+	tp.warp_sum = reinterpret_cast<const uint32_t *>(ctx->warp_sum);
 	tp.bin_offset = dev->bin_offset;
 	tp.pair_ids = dev->pair_ids;
 	tp.pair_tmp = dev->pair_tmp;
@@ -1263,6 +1329,12 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	tp.index_count = count;
 	tp.key_bits = 3u;
 	while(tp.key_bits < 32u && (T >> (tp.key_bits - 3u)) != 0u) tp.key_bits++;
+	if(dev->timeline_on && dev->timeline_used + 3u <= MLV_TIMELINE_CAPACITY) { // three consecutive slots
+		tp.timeline = timeline_slot(dev, MLV_STAGE_BIN_SCAN);
+		timeline_slot(dev, MLV_STAGE_BIN_FILL);
+		timeline_slot(dev, MLV_STAGE_TILE);
+	}
+	dev->timeline_draw++;
 	prof_pre(dev, MLV_STAGE_BIN_SCAN);
 	launch_pdl(k_bin_scan, dev->scan_blocks, MLV_SCAN_THREADS, dev->stream, tp);
 	if(int rc = check_launch(dev, "k_bin_scan")) return rc;
@@ -1282,6 +1354,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 		default: launch_pdl(k_tile<2>, tile_blocks, MLV_TILE_THREADS, dev->stream, tp); break;
 	}
 	g_pdl = 1;
+	g_launch_priority_set = false;
 	if(int rc = check_launch(dev, "k_tile")) return rc;
 	if(!dev->prof_on) { // the context is free again once this draw's k_tile has re-armed it
 		CUDA_TRY(cudaEventRecord(ctx->free_ev, dev->stream));
@@ -1381,7 +1454,8 @@ int mlv_finish_command_list(mlv_device *dev, mlv_command_list **out_list) {
 		if(rc != MLV_OK) return rc;
 		return fail(MLV_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
 	}
-	e = cudaGraphInstantiate(&list->exec, list->graph, 0);
+	// (per-node priorities: the chain kernels were recorded with the highest launch priority, the front halves with the lowest)
+	e = cudaGraphInstantiateWithFlags(&list->exec, list->graph, dev->knob_explicit_priority ? cudaGraphInstantiateFlagUseNodePriority : 0);
 	if(e != cudaSuccess) {
 		free_command_list(list);
 		return fail(MLV_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
@@ -2054,6 +2128,56 @@ int mlv_profile_read_events(mlv_device *dev, mlv_profile_event *out, uint32_t ca
 		out[k].stage = (*dev->prof_stages)[k];
 		out[k].start_ms = start;
 		out[k].duration_ms = dur;
+	}
+	return MLV_OK;
+}
+
+int mlv_timeline_begin(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	if(!dev->timeline) {
+		CUDA_TRY(cudaMalloc(&dev->timeline, (size_t)MLV_TIMELINE_CAPACITY * 4 * sizeof(unsigned long long)));
+		dev->timeline_stages = new std::vector<int>();
+	}
+	dev->timeline_stages->clear();
+	dev->timeline_used = 0;
+	dev->timeline_draw = 0;
+	dev->timeline_on = true;
+	return mlv_timeline_reset(dev);
+}
+
+int mlv_timeline_end(mlv_device *dev) {
+	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	dev->timeline_on = false;
+	return MLV_OK;
+}
+
+int mlv_timeline_reset(mlv_device *dev) {
+	if(int rc = use_device(dev)) return rc;
+	if(!dev->timeline) return fail(MLV_ERR_STATE, "call mlv_timeline_begin first");
+	if(dev->recording) return fail(MLV_ERR_STATE, "mlv_timeline_reset cannot be recorded");
+	CUDA_TRY(cudaMemsetAsync(dev->timeline, 0xff, (size_t)MLV_TIMELINE_CAPACITY * 4 * sizeof(unsigned long long), dev->stream));
+	return MLV_OK;
+}
+
+int mlv_timeline_read(mlv_device *dev, mlv_timeline_event *out, uint32_t capacity, uint32_t *out_count) {
+	if(int rc = use_device(dev)) return rc;
+	if(!dev->timeline || !out_count) return fail(MLV_ERR_STATE, "call mlv_timeline_begin first");
+	*out_count = dev->timeline_used;
+	if(!out) return MLV_OK;
+	if(capacity < dev->timeline_used) return fail(MLV_ERR_INVALID_ARGUMENT, "capacity %u < %u timeline events", capacity, dev->timeline_used);
+	CUDA_TRY(cudaDeviceSynchronize());
+	std::vector<unsigned long long> raw((size_t)dev->timeline_used * 4);
+	CUDA_TRY(cudaMemcpy(raw.data(), dev->timeline, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	unsigned long long t0 = ~0ull;
+	for(uint32_t i = 0; i < dev->timeline_used; ++i) t0 = std::min(t0, raw[4 * (size_t)i]);
+	for(uint32_t i = 0; i < dev->timeline_used; ++i) {
+		const unsigned long long *r = &raw[4 * (size_t)i];
+		out[i].stage = (*dev->timeline_stages)[i] >> 16;
+		out[i].draw = (*dev->timeline_stages)[i] & 0xffff;
+		const bool ran = r[0] != ~0ull; // (a launch that did not execute since the last reset)
+		out[i].resident_us = ran ? (double)(r[0] - t0) * 1e-3 : -1.0;
+		out[i].start_us = ran && r[1] != ~0ull ? (double)(r[1] - t0) * 1e-3 : -1.0;
+		out[i].end_us = ran && r[2] != ~0ull ? (double)(~r[2] - t0) * 1e-3 : -1.0;
 	}
 	return MLV_OK;
 }

@@ -58,7 +58,7 @@ struct Counters {
 	uint32_t draw_active_bins; // bins the current draw touched (counted by its k_tile)
 	uint32_t reserved2;
 	uint32_t bcast_done;  // CTAs of k_composite_broadcast that have finished their stores (reset by the last one)
-	uint32_t epoch;       // draw epoch tagging this draw's touches in bin_touch (advanced at the end of every draw; never 0)
+	uint32_t epoch;       // draw epoch tagging the look-back words of this draw's scan (advanced at the end of every draw; never 0)
 	uint32_t n_wake;      // entries of wake_bins in the current draw
 	uint32_t last_pair_total, last_n_cbins; // pair_total / n_cbins of the last finished draw (read-backs); pair_total 0xffffffff: it was skipped
 	uint32_t pad[3];
@@ -145,7 +145,8 @@ struct GeomParams {
 	uint32_t *big_queue;
 	uint32_t *huge_queue;
 	uint32_t *bin_count;
-	uint32_t *bin_touch;
+	uint8_t *touch_bits;        // the draw context's "bin received a pair" map (Stats: active_bin_count), one byte per bin
+	uint4 *warp_sum;            // the draw context's warp summaries, 16 B per 32 direct slots (kernels.cuh, write_warp_summary)
 	const float *tile_min;
 	bool keep_all; // debug capture: no Hi-Z at binning time, lists hold every pair like the reference's
 	DebugOut dbg;
@@ -153,6 +154,7 @@ struct GeomParams {
 	unsigned long long *stat_stripes;
 	uint32_t index_count;
 	uint32_t draw_ordinal; // position of the draw inside a recorded command list (identifies the kernel nodes whose constants are updated)
+	unsigned long long *timeline; // this launch's slot of the device-side timeline (4 words), or null
 };
 
 // Everything the tail kernel of a draw needs (scan | fill | tile).
@@ -165,7 +167,8 @@ struct TailParams {
 	const uint8_t *chunk_live;
 	float *tile_min;
 	uint32_t *bin_count;       // surviving pairs per bin (zero outside a draw's back half .. scan)
-	uint32_t *bin_touch;       // epoch of the draw that touched the bin last
+	uint8_t *touch_bits;       // the draw context's touch map: counted and cleared by k_tile
+	const uint32_t *warp_sum;  // the draw context's warp summaries as words (word 3 of an entry == 0: the fill pass skips the 32 slots)
 	uint32_t *bin_offset;      // start of the bin's list (the scan), then the running fill position (k_fill)
 	unsigned long long *state_sum, *state_nz; // look-back words of the scan, tagged with the draw epoch
 	uint32_t scan_blocks;
@@ -194,6 +197,7 @@ struct TailParams {
 	DebugOut dbg;
 	uint32_t index_count;      // Stats (main.c:1228-1232)
 	uint32_t key_bits;
+	unsigned long long *timeline; // three consecutive slots of the device-side timeline (scan, fill, tile), or null
 };
 
 } // namespace mlv

@@ -418,6 +418,24 @@ class Device:
         L.check(self._lib.mlv_profile_read_events(self._h, ev, n.value, C.byref(n)))
         return [(L.STAGE_NAMES[e.stage], float(e.start_ms), float(e.duration_ms)) for e in ev[:n.value]]
 
+    def timeline_begin(self):
+        """Launches issued or recorded from now on stamp %globaltimer into their slot (works inside command lists)."""
+        L.check(self._lib.mlv_timeline_begin(self._h))
+
+    def timeline_end(self):
+        L.check(self._lib.mlv_timeline_end(self._h))
+
+    def timeline_reset(self):
+        L.check(self._lib.mlv_timeline_reset(self._h))
+
+    def timeline_read(self) -> list:
+        """[(stage name, draw, resident us, start us, end us)] per slot in issue order, relative to the earliest stamp."""
+        n = C.c_uint32()
+        L.check(self._lib.mlv_timeline_read(self._h, None, 0, C.byref(n)))
+        ev = (L.TimelineEvent * max(n.value, 1))()
+        L.check(self._lib.mlv_timeline_read(self._h, ev, n.value, C.byref(n)))
+        return [(L.STAGE_NAMES[e.stage], int(e.draw), float(e.resident_us), float(e.start_us), float(e.end_us)) for e in ev[:n.value]]
+
     def resolve(self):
         L.check(self._lib.mlv_resolve(self._h))
 

@@ -186,7 +186,7 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     if cc is None:
         pytest.skip("no C compiler")
     structs = {"mlv_viewport": L.Viewport, "mlv_stats": L.Stats, "mlv_device_desc": L.DeviceDesc, "mlv_peer_info": L.PeerInfo,
-               "mlv_work_counters": L.WorkCounters, "mlv_profile_event": L.ProfileEvent}
+               "mlv_work_counters": L.WorkCounters, "mlv_profile_event": L.ProfileEvent, "mlv_timeline_event": L.TimelineEvent}
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "malevich_b200.h"', "int main(void) {"]
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
