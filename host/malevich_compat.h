@@ -87,6 +87,10 @@ extern PixelShader passthrough_ps, basic_ps, env_lighting_ps;
  * before the first clear or draw. Returns 0 on success. */
 int malevich_gpu_init(unsigned width, unsigned height);
 void malevich_gpu_shutdown(void);
+/* The device copies of vertex / index buffers and textures are cached by host pointer (the reference never frees or
+ * rewrites an asset). A host that rewrites one in place, or frees it and reuses the address, says so here; the next draw
+ * that binds the pointer uploads it again. */
+void malevich_gpu_invalidate(const void *host_pointer);
 
 void clear_render_target_view(const f32 *p_clear_color); /* main.c:1191 */
 void clear_depth_stencil_view(const f32 depth);          /* main.c:1204 */

@@ -99,9 +99,23 @@ typedef struct mlv_device_desc {
 	uint32_t stripe_height_tiles; /* 0 = default (1) */
 	uint64_t max_pairs_per_draw;  /* capacity of the (triangle,tile) list arena; 0 = default */
 	uint32_t flags;               /* MLV_DEVICE_* */
-	uint32_t reserved;
+	uint32_t num_gpus;            /* 0 or 1 = this device only. N > 1 = a device GROUP: one host thread, CUDA devices cuda_device ..
+	                               * cuda_device + N - 1 in this process, one sort-first rank each (num_ranks / rank must be 0) */
 } mlv_device_desc;
-enum { MLV_DEVICE_DEBUG_CAPTURE = 1 /* keep reference-layout intermediates of the last draw for mlv_debug_read_* */ };
+enum { MLV_DEVICE_DEBUG_CAPTURE = 1, /* keep reference-layout intermediates of the last draw for mlv_debug_read_* */
+       MLV_DEVICE_GROUP_SAME_GPU = 2, /* device group: every rank on cuda_device (tests on a single-GPU box) */
+       MLV_DEVICE_GROUP_NCCL = 4 };   /* device group: compose the frame with pack + in-place ncclAllGather + unpack (libnccl.so.2,
+                                       * loaded on demand) instead of the asynchronous peer-memory exchange */
+/* DEVICE GROUPS. With num_gpus = N the multi-GPU fan-out lives behind the same calls: the handle returned by
+ * mlv_create_device stands for N per-GPU devices -- geometry, textures and pipeline state replicated, rank i rasterising the
+ * tile rows (ty / stripe_height_tiles) % N == i (default: one contiguous band per GPU) -- and the entry points a renderer
+ * needs fan out to them: buffers and textures (create / update / release, sRGB, mips), every state setter, both clears, the
+ * three draws, command lists (one recording per GPU, one graph launch per GPU per frame), mlv_present_readback[_async] /
+ * mlv_present_wait (exchange of the stripes over peer memory or NCCL, then rank 0's image; depth rows are collected from
+ * their owners on the host), mlv_get_stats / mlv_get_work_counters (sums of the ranks' shares = the reference's Stats),
+ * mlv_reset_stats, mlv_finish, mlv_kernel_launch_count, mlv_destroy_device. Every other entry point returns
+ * MLV_ERR_STATE for a group. host/malevich_compat.c creates a group when MLV_NUM_GPUS is set, so the reference's
+ * render() runs on N GPUs unchanged. */
 
 typedef struct mlv_device mlv_device;
 typedef struct mlv_buffer mlv_buffer;

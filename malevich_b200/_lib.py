@@ -33,7 +33,7 @@ PS_PASSTHROUGH, PS_BASIC, PS_ENV_LIGHTING, PS_BASIC_TRILINEAR = 0, 1, 2, 3
 FORMAT_R8G8B8A8_UNORM, FORMAT_R32G32B32A32_FLOAT = 0, 1
 BUFFER_VERTEX, BUFFER_INDEX = 0, 1
 INDEX_U32, INDEX_U16 = 0, 1
-DEVICE_DEBUG_CAPTURE = 1
+DEVICE_DEBUG_CAPTURE, DEVICE_GROUP_SAME_GPU, DEVICE_GROUP_NCCL = 1, 2, 4
 ALL_DRAWS = 0xFFFFFFFF
 
 
@@ -71,7 +71,7 @@ class PeerInfo(C.Structure):  # mlv_peer_info
 class DeviceDesc(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("cuda_device", C.c_int32), ("num_ranks", C.c_uint32),
                 ("rank", C.c_uint32), ("stripe_height_tiles", C.c_uint32), ("max_pairs_per_draw", C.c_uint64),
-                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32), ("num_gpus", C.c_uint32)]
 
 
 class MalevichError(RuntimeError):

@@ -68,6 +68,29 @@ def read_octrn_image(path: str):
     return data, width, height, fmt
 
 
+def write_octrn_image(path: str, texels: np.ndarray) -> None:
+    """Writes an image asset the readers here and in host/octrn.c accept: float32 [h, w, 4] as R32G32B32A32_FLOAT,
+    uint32 [h, w] as a 4-byte-per-texel format. (Stand-ins for the missing *_tex.octrn files go to disk this way when the
+    C host loads a scene through the reference's own init() table.)"""
+    t = np.ascontiguousarray(texels)
+    fmt = FORMAT_R32G32B32A32_FLOAT if t.dtype == np.float32 else 0x1C01
+    h, w = t.shape[0], t.shape[1]
+    with open(path, "wb") as f:
+        f.write(OCTRN_MAGIC + struct.pack("<II", OCTRN_TYPE_IMAGE, 0))
+        f.write(struct.pack("<QIHHHHHH", t.nbytes, fmt, w, h, 1, 1, 1, 0))
+        f.write(t.tobytes())
+
+
+def write_octrn_mesh(path: str, vb: np.ndarray, ib: np.ndarray) -> None:
+    v = np.ascontiguousarray(vb, dtype=np.float32).reshape(-1, 8)
+    i = np.ascontiguousarray(ib, dtype=np.uint32)
+    with open(path, "wb") as f:
+        f.write(OCTRN_MAGIC + struct.pack("<II", OCTRN_TYPE_MESH, 0))
+        f.write(struct.pack("<III", v.nbytes + i.nbytes, v.shape[0], i.shape[0]))
+        f.write(v.tobytes())
+        f.write(i.tobytes())
+
+
 def load_mesh(name: str):
     return read_octrn_mesh(os.path.join(ASSET_DIR, name + ".octrn"))
 

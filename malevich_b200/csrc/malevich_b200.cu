@@ -16,6 +16,9 @@
 
 #include <cuda.h> // driver-API types only: the entry points are fetched through cudaGetDriverEntryPoint, libcuda is not linked
 
+#include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
+
 #include "kernels.cuh"
 
 using namespace mlv;
@@ -25,6 +28,14 @@ static const uint32_t k_rsqrt_lut_host[2048] = {
 };
 
 static thread_local char g_last_error[512] = "";
+
+// NVTX ranges under the names of the reference's Remotery scopes (rmt_BeginCPUSample, main.c:663, 699, 737, 916, 984,
+// 1047, 1192, 1205, 1220, 1302): a timeline tool (Nsight Systems) shows the host side of every entry point and correlates
+// the kernels launched inside each range. Header-only NVTX 3: a no-op costing one pointer test when no tool is attached.
+struct NvtxScope {
+	explicit NvtxScope(const char *name) { nvtxRangePushA(name); }
+	~NvtxScope() { nvtxRangePop(); }
+};
 
 static int fail(int code, const char *fmt, ...) {
 	va_list ap;
@@ -41,6 +52,7 @@ static int fail(int code, const char *fmt, ...) {
 	} while(0)
 
 struct mlv_buffer {
+	std::vector<mlv_buffer *> *children; // buffer of a device group (num_gpus > 1): one replica per GPU, nothing else is used
 	void *d;
 	size_t bytes;
 	int kind;
@@ -58,6 +70,7 @@ struct mlv_buffer {
 	int32_t chunk_base_vertex;
 };
 struct mlv_texture {
+	std::vector<mlv_texture *> *children; // texture of a device group: one replica per GPU
 	void *d;
 	uint32_t width, height;
 	int format;
@@ -74,6 +87,7 @@ struct GeomNode { // a geometry kernel node of a recorded command list (its cons
 };
 
 struct mlv_command_list {
+	std::vector<mlv_command_list *> *children; // command list of a device group: one recording per GPU
 	mlv_device *owner;
 	cudaGraph_t graph;
 	cudaGraphExec_t exec;
@@ -118,6 +132,11 @@ struct DrawCtx {
 };
 
 struct mlv_device {
+	// A device GROUP (mlv_device_desc.num_gpus > 1) is only a list of per-GPU devices, one sort-first rank each, driven by one
+	// host thread: the entry points a renderer needs fan out to them (group_* below), every other one refuses a group.
+	std::vector<mlv_device *> *children;
+	uint32_t *group_scratch_color; // host staging for the depth images of the ranks (mlv_present_readback with depths)
+	void *group_nccl;              // GroupNccl: communicators of the ncclAllGather exchange (MLV_DEVICE_GROUP_NCCL), loaded on demand
 	mlv_device_desc desc;
 	int cuda_dev;
 	cudaStream_t stream;
@@ -278,6 +297,7 @@ static void launch_pdl(void (*kernel)(KArgs...), uint32_t grid, uint32_t block, 
 
 static int use_device(mlv_device *dev) {
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
+	if(dev->children) return fail(MLV_ERR_STATE, "this entry point is not available on a device group (mlv_device_desc.num_gpus > 1)");
 	CUDA_TRY(cudaSetDevice(dev->cuda_dev));
 	return MLV_OK;
 }
@@ -361,7 +381,25 @@ extern "C" {
 
 const char *mlv_last_error_string(void) { return g_last_error; }
 
+// ---- device groups: fan-out helpers ------------------------------------------------------------------
+#define GROUP_EACH(dev, expr)                                                      \
+	if((dev) && (dev)->children) {                                                 \
+		for(size_t gi = 0; gi < (dev)->children->size(); ++gi) {                   \
+			mlv_device *c = (*(dev)->children)[gi];                                \
+			(void)c;                                                               \
+			if(int rc = (expr)) return rc;                                         \
+		}                                                                          \
+		return MLV_OK;                                                             \
+	}
+#define GROUP_CHILD(obj) ((obj) ? ((obj)->children ? (*(obj)->children)[gi] : (obj)) : nullptr)
+static int group_create(const mlv_device_desc *desc, mlv_device **out_device);
+static void group_destroy(mlv_device *dev);
+static int group_present(mlv_device *dev, uint32_t *colors, float *depths, bool wait);
+static int group_present_wait(mlv_device *dev);
+static int mlv_present_copy_async(mlv_device *dev, uint32_t *colors);
+
 int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
+	if(desc && out_device && desc->num_gpus > 1) return group_create(desc, out_device);
 	if(!desc || !out_device) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
 	*out_device = nullptr;
 	if(desc->width == 0 || desc->height == 0 || (desc->width % 8) || (desc->height % 8))
@@ -527,6 +565,7 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 static void free_command_list(mlv_command_list *list);
 
 void mlv_destroy_device(mlv_device *dev) {
+	if(dev && dev->children) return group_destroy(dev);
 	if(!dev) return;
 	cudaSetDevice(dev->cuda_dev);
 	if(dev->recording) { // abandon a recording in progress
@@ -581,6 +620,7 @@ void mlv_destroy_device(mlv_device *dev) {
 }
 
 int mlv_finish(mlv_device *dev) {
+	GROUP_EACH(dev, mlv_finish(c));
 	if(int rc = immediate_only(dev, "mlv_finish")) return rc;
 	if(int rc = use_device(dev)) return rc;
 	CUDA_TRY(cudaStreamSynchronize(dev->stream));
@@ -600,6 +640,23 @@ void *mlv_get_stream(mlv_device *dev) { return dev ? (void *)dev->stream : nullp
 // ---- resources -----------------------------------------------------------------------------------
 
 int mlv_create_buffer(mlv_device *dev, const void *data, size_t bytes, int kind, mlv_buffer **out) {
+	if(dev && dev->children) {
+		if(!out) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer arguments");
+		mlv_buffer *g = new mlv_buffer();
+		memset(g, 0, sizeof(*g));
+		g->children = new std::vector<mlv_buffer *>();
+		g->bytes = bytes, g->kind = kind;
+		for(mlv_device *c : *dev->children) {
+			mlv_buffer *b = nullptr;
+			if(int rc = mlv_create_buffer(c, data, bytes, kind, &b)) {
+				mlv_release_buffer(dev, g);
+				return rc;
+			}
+			g->children->push_back(b);
+		}
+		*out = g;
+		return MLV_OK;
+	}
 	if(int rc = use_device(dev)) return rc;
 	if(!out || bytes == 0 || (kind != MLV_BUFFER_VERTEX && kind != MLV_BUFFER_INDEX)) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer arguments");
 	mlv_buffer *b = new(std::nothrow) mlv_buffer();
@@ -621,6 +678,7 @@ int mlv_create_buffer(mlv_device *dev, const void *data, size_t bytes, int kind,
 }
 
 int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t bytes) {
+	GROUP_EACH(dev, mlv_update_buffer(c, GROUP_CHILD(buf), data, bytes));
 	if(int rc = use_device(dev)) return rc;
 	if(!buf || !data || bytes > buf->bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer update");
 	// after every draw issued so far (any of them may read this buffer; each k_vertex on the side stream has already
@@ -635,6 +693,7 @@ int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t
 }
 
 int mlv_update_buffer_range(mlv_device *dev, mlv_buffer *buf, size_t offset, const void *data, size_t bytes) {
+	GROUP_EACH(dev, mlv_update_buffer_range(c, GROUP_CHILD(buf), offset, data, bytes));
 	if(int rc = use_device(dev)) return rc;
 	if(!buf || !data || offset > buf->bytes || bytes > buf->bytes - offset) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer range update");
 	if(dev->last_draw_recorded) CUDA_TRY(cudaStreamWaitEvent(dev->copy_stream, dev->ev_last_draw, 0));
@@ -658,6 +717,15 @@ int mlv_buffer_mark_updated(mlv_device *dev, mlv_buffer *buf, void *stream) {
 }
 
 void mlv_release_buffer(mlv_device *dev, mlv_buffer *buf) {
+	if(dev && dev->children) {
+		if(!buf) return;
+		if(buf->children) {
+			for(size_t gi = 0; gi < buf->children->size(); ++gi) mlv_release_buffer((*dev->children)[gi], (*buf->children)[gi]);
+			delete buf->children;
+		}
+		delete buf;
+		return;
+	}
 	if(immediate_only(dev, "mlv_release_buffer")) return;
 	if(!dev || !buf) return;
 	cudaSetDevice(dev->cuda_dev);
@@ -673,6 +741,23 @@ void mlv_release_buffer(mlv_device *dev, mlv_buffer *buf) {
 }
 
 int mlv_create_texture2d(mlv_device *dev, const void *texels, uint32_t width, uint32_t height, int format, mlv_texture **out) {
+	if(dev && dev->children) {
+		if(!out) return fail(MLV_ERR_INVALID_ARGUMENT, "bad texture arguments");
+		mlv_texture *g = new mlv_texture();
+		memset(g, 0, sizeof(*g));
+		g->children = new std::vector<mlv_texture *>();
+		g->width = width, g->height = height, g->format = format;
+		for(mlv_device *c : *dev->children) {
+			mlv_texture *t = nullptr;
+			if(int rc = mlv_create_texture2d(c, texels, width, height, format, &t)) {
+				mlv_release_texture(dev, g);
+				return rc;
+			}
+			g->children->push_back(t);
+		}
+		*out = g;
+		return MLV_OK;
+	}
 	if(int rc = use_device(dev)) return rc;
 	if(!out || !texels || width == 0 || height == 0 || (format != MLV_FORMAT_R8G8B8A8_UNORM && format != MLV_FORMAT_R32G32B32A32_FLOAT))
 		return fail(MLV_ERR_INVALID_ARGUMENT, "bad texture arguments");
@@ -704,6 +789,7 @@ int mlv_create_texture2d(mlv_device *dev, const void *texels, uint32_t width, ui
 }
 
 int mlv_texture_srgb_to_linear(mlv_device *dev, mlv_texture *tex) {
+	GROUP_EACH(dev, mlv_texture_srgb_to_linear(c, GROUP_CHILD(tex)));
 	if(int rc = immediate_only(dev, "mlv_texture_srgb_to_linear")) return rc;
 	if(int rc = use_device(dev)) return rc;
 	if(!tex || tex->format != MLV_FORMAT_R8G8B8A8_UNORM) return fail(MLV_ERR_INVALID_ARGUMENT, "sRGB conversion wants an R8G8B8A8 texture (main.c:546-558)");
@@ -732,6 +818,7 @@ static uint32_t mip_extent_host(uint32_t e, uint32_t level) {
 }
 
 int mlv_texture_generate_mips(mlv_device *dev, mlv_texture *tex) {
+	GROUP_EACH(dev, mlv_texture_generate_mips(c, GROUP_CHILD(tex)));
 	if(int rc = immediate_only(dev, "mlv_texture_generate_mips")) return rc;
 	if(int rc = use_device(dev)) return rc;
 	if(!tex || tex->format != MLV_FORMAT_R8G8B8A8_UNORM) return fail(MLV_ERR_INVALID_ARGUMENT, "mip chains are built for R8G8B8A8 textures");
@@ -795,6 +882,15 @@ int mlv_read_texture(mlv_device *dev, const mlv_texture *tex, void *out_texels) 
 }
 
 void mlv_release_texture(mlv_device *dev, mlv_texture *tex) {
+	if(dev && dev->children) {
+		if(!tex) return;
+		if(tex->children) {
+			for(size_t gi = 0; gi < tex->children->size(); ++gi) mlv_release_texture((*dev->children)[gi], (*tex->children)[gi]);
+			delete tex->children;
+		}
+		delete tex;
+		return;
+	}
 	if(immediate_only(dev, "mlv_release_texture")) return;
 	if(!dev || !tex) return;
 	cudaSetDevice(dev->cuda_dev);
@@ -811,41 +907,48 @@ void mlv_release_texture(mlv_device *dev, mlv_texture *tex) {
 // ---- pipeline state ------------------------------------------------------------------------------
 
 int mlv_ia_set_vertex_buffer(mlv_device *dev, mlv_buffer *vb) {
+	GROUP_EACH(dev, mlv_ia_set_vertex_buffer(c, GROUP_CHILD(vb)));
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	if(vb && vb->kind != MLV_BUFFER_VERTEX) return fail(MLV_ERR_INVALID_ARGUMENT, "buffer is not a vertex buffer");
 	dev->vb = vb;
 	return MLV_OK;
 }
 int mlv_ia_set_index_buffer(mlv_device *dev, mlv_buffer *ib) {
+	GROUP_EACH(dev, mlv_ia_set_index_buffer(c, GROUP_CHILD(ib)));
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	if(ib && ib->kind != MLV_BUFFER_INDEX) return fail(MLV_ERR_INVALID_ARGUMENT, "buffer is not an index buffer");
 	dev->ib = ib;
 	return MLV_OK;
 }
 int mlv_ia_set_index_format(mlv_device *dev, int format) {
+	GROUP_EACH(dev, mlv_ia_set_index_format(c, format));
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	if(format != MLV_INDEX_U32 && format != MLV_INDEX_U16) return fail(MLV_ERR_INVALID_ARGUMENT, "unknown index format %d", format);
 	dev->index_format = format;
 	return MLV_OK;
 }
 int mlv_ia_set_input_layout(mlv_device *dev, uint32_t bytes_per_vertex) {
+	GROUP_EACH(dev, mlv_ia_set_input_layout(c, bytes_per_vertex));
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	if(bytes_per_vertex != 32) return fail(MLV_ERR_INVALID_ARGUMENT, "input layout %u: every reference shader consumes 32-byte vertices (in_vertex_size/VECTOR_WIDTH main.c:1286)", bytes_per_vertex);
 	dev->input_layout = bytes_per_vertex;
 	return MLV_OK;
 }
 int mlv_ia_set_primitive_topology(mlv_device *dev, int topology) {
+	GROUP_EACH(dev, mlv_ia_set_primitive_topology(c, topology));
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	dev->topology = topology;
 	return MLV_OK;
 }
 int mlv_vs_set_shader(mlv_device *dev, int vs_id) {
+	GROUP_EACH(dev, mlv_vs_set_shader(c, vs_id));
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	if(vs_id < 0 || vs_id >= MLV_VS_COUNT) return fail(MLV_ERR_INVALID_ARGUMENT, "unknown vertex shader id %d", vs_id);
 	dev->vs_id = vs_id;
 	return MLV_OK;
 }
 int mlv_vs_set_constant_buffer(mlv_device *dev, uint32_t slot, const void *data, size_t bytes) {
+	GROUP_EACH(dev, mlv_vs_set_constant_buffer(c, slot, data, bytes));
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	if(slot >= MLV_CONSTANT_BUFFER_SLOT_COUNT || !data || bytes > sizeof(dev->cb[0])) return fail(MLV_ERR_INVALID_ARGUMENT, "bad constant buffer (slot %u, %zu bytes)", slot, bytes);
 	memcpy(dev->cb[slot], data, bytes);
@@ -853,11 +956,13 @@ int mlv_vs_set_constant_buffer(mlv_device *dev, uint32_t slot, const void *data,
 	return MLV_OK;
 }
 int mlv_vs_set_shader_resource(mlv_device *dev, uint32_t slot, mlv_texture *tex) {
+	GROUP_EACH(dev, mlv_vs_set_shader_resource(c, slot, GROUP_CHILD(tex)));
 	if(!dev || slot >= MLV_SHADER_RESOURCE_SLOT_COUNT) return fail(MLV_ERR_INVALID_ARGUMENT, "bad shader resource slot");
 	dev->vs_srv[slot] = tex;
 	return MLV_OK;
 }
 int mlv_rs_set_viewport(mlv_device *dev, const mlv_viewport *vp) {
+	GROUP_EACH(dev, mlv_rs_set_viewport(c, vp));
 	if(!dev || !vp) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
 	if((int)vp->width != dev->W || (int)vp->height != dev->H)
 		return fail(MLV_ERR_INVALID_ARGUMENT, "viewport %gx%g must equal the render target %dx%d (reference tile pitch main.c:582,590)", vp->width, vp->height, dev->W, dev->H);
@@ -866,12 +971,14 @@ int mlv_rs_set_viewport(mlv_device *dev, const mlv_viewport *vp) {
 	return MLV_OK;
 }
 int mlv_ps_set_shader(mlv_device *dev, int ps_id) {
+	GROUP_EACH(dev, mlv_ps_set_shader(c, ps_id));
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	if(ps_id < 0 || ps_id >= MLV_PS_COUNT) return fail(MLV_ERR_INVALID_ARGUMENT, "unknown pixel shader id %d", ps_id);
 	dev->ps_id = ps_id;
 	return MLV_OK;
 }
 int mlv_ps_set_shader_resource(mlv_device *dev, uint32_t slot, mlv_texture *tex) {
+	GROUP_EACH(dev, mlv_ps_set_shader_resource(c, slot, GROUP_CHILD(tex)));
 	if(!dev || slot >= MLV_SHADER_RESOURCE_SLOT_COUNT) return fail(MLV_ERR_INVALID_ARGUMENT, "bad shader resource slot");
 	dev->ps_srv[slot] = tex;
 	return MLV_OK;
@@ -912,6 +1019,8 @@ static int flush_clears(mlv_device *dev) {
 }
 
 int mlv_clear_render_target_view(mlv_device *dev, const float rgba[4]) {
+	GROUP_EACH(dev, mlv_clear_render_target_view(c, rgba));
+	NvtxScope nvtx("clear_render_target_view");
 	if(!dev || !rgba) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
 	// encode_color_as_u32 (math.h:322-324): truncation, R in the low byte -- not the PS path's channel order (App. C 4)
 	dev->clear_color = (((uint32_t)(rgba[3] * 255.f)) << 24) + (((uint32_t)(rgba[2] * 255.f)) << 16) + (((uint32_t)(rgba[1] * 255.f)) << 8) + (((uint32_t)(rgba[0] * 255.f)));
@@ -920,6 +1029,8 @@ int mlv_clear_render_target_view(mlv_device *dev, const float rgba[4]) {
 }
 
 int mlv_clear_depth_stencil_view(mlv_device *dev, float depth) {
+	GROUP_EACH(dev, mlv_clear_depth_stencil_view(c, depth));
+	NvtxScope nvtx("clear_depth_stencil_view");
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	dev->clear_depth = depth;
 	dev->pend_depth = true;
@@ -1028,6 +1139,7 @@ static cudaError_t quiesce(mlv_device *dev) {
 }
 
 static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t start_index = 0, int32_t base_vertex = 0) {
+	NvtxScope nvtx("draw_indexed");
 	if(int rc = use_device(dev)) return rc;
 	g_graveyard = (dev->recording || dev->lists_alive) ? dev->graveyard : nullptr;
 	if(dev->recording && dev->prof_on) return fail(MLV_ERR_STATE, "per-stage profiling brackets launches with events and cannot be recorded");
@@ -1262,6 +1374,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	}
 
 	// ---- front half (its own stream): k_vertex, k_front, k_front_clip
+	nvtxRangePushA("input_assambler_stage+vertex_shader_stage+primitive_assembly_stage"); // (sic, main.c:663)
 	g_launch_priority_set = dev->knob_explicit_priority != 0;
 	g_launch_priority = dev->prio_front;
 	switch(dev->vs_id) {
@@ -1270,6 +1383,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 		case MLV_VS_VERTEX_LIGHTING: launch_front<2>(dev, fs, gp, nblocks, indexed, vcache_vertices); break;
 		default: launch_front<3>(dev, fs, gp, nblocks, indexed, vcache_vertices); break;
 	}
+	nvtxRangePop();
 	if(int rc = check_launch_only(dev, "front half")) return rc;
 	if(!dev->prof_on) {
 		CUDA_TRY(cudaEventRecord(ctx->front_done, fs));
@@ -1277,6 +1391,7 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	}
 
 	// ---- back half (main stream: ordered after the previous draw's k_tile through the tile minima)
+	NvtxScope nvtx_tail("binner+rasterizer_stage+pixel_shader_stage");
 	g_launch_priority = dev->prio_chain;
 	const uint32_t back_blocks = (need_slots + MLV_GEOM_THREADS - 1) / MLV_GEOM_THREADS;
 	switch(dev->vs_id) {
@@ -1371,9 +1486,16 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 
 extern "C" {
 
-int mlv_draw_indexed(mlv_device *dev, uint32_t index_count) { return draw_common(dev, index_count, true); }
-int mlv_draw(mlv_device *dev, uint32_t vertex_count) { return draw_common(dev, vertex_count, false); }
+int mlv_draw_indexed(mlv_device *dev, uint32_t index_count) {
+	GROUP_EACH(dev, draw_common(c, index_count, true));
+	return draw_common(dev, index_count, true);
+}
+int mlv_draw(mlv_device *dev, uint32_t vertex_count) {
+	GROUP_EACH(dev, draw_common(c, vertex_count, false));
+	return draw_common(dev, vertex_count, false);
+}
 int mlv_draw_indexed_ex(mlv_device *dev, uint32_t index_count, uint32_t start_index_location, int32_t base_vertex_location) {
+	GROUP_EACH(dev, draw_common(c, index_count, true, start_index_location, base_vertex_location));
 	return draw_common(dev, index_count, true, start_index_location, base_vertex_location);
 }
 
@@ -1401,6 +1523,7 @@ static void free_command_list(mlv_command_list *list) {
 }
 
 int mlv_begin_command_list(mlv_device *dev) {
+	GROUP_EACH(dev, mlv_begin_command_list(c));
 	if(int rc = use_device(dev)) return rc;
 	if(dev->recording) return fail(MLV_ERR_STATE, "a command list is already being recorded");
 	if(dev->prof_on) return fail(MLV_ERR_STATE, "call mlv_profile_end before recording a command list");
@@ -1433,6 +1556,29 @@ int mlv_begin_command_list(mlv_device *dev) {
 }
 
 int mlv_finish_command_list(mlv_device *dev, mlv_command_list **out_list) {
+	if(dev && dev->children) {
+		if(!out_list) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+		mlv_command_list *g = new mlv_command_list();
+		memset(g, 0, sizeof(*g));
+		g->owner = dev;
+		g->children = new std::vector<mlv_command_list *>();
+		int first_rc = MLV_OK;
+		for(mlv_device *c : *dev->children) { // every rank leaves the recording state, whatever happens to one of them
+			mlv_command_list *l = nullptr;
+			const int rc = mlv_finish_command_list(c, &l);
+			if(rc && !first_rc) first_rc = rc;
+			g->children->push_back(l);
+		}
+		if(first_rc) {
+			mlv_release_command_list(dev, g);
+			*out_list = nullptr;
+			return first_rc;
+		}
+		g->draws = (*g->children)[0]->draws;
+		for(mlv_command_list *l : *g->children) g->launches += l->launches;
+		*out_list = g;
+		return MLV_OK;
+	}
 	if(int rc = use_device(dev)) return rc;
 	if(!dev->recording) return fail(MLV_ERR_STATE, "no command list is being recorded");
 	if(!out_list) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
@@ -1493,6 +1639,8 @@ int mlv_finish_command_list(mlv_device *dev, mlv_command_list **out_list) {
 }
 
 int mlv_execute_command_list(mlv_device *dev, mlv_command_list *list) {
+	GROUP_EACH(dev, (list && list->children && list->owner == dev) ? mlv_execute_command_list(c, (*list->children)[gi]) : fail(MLV_ERR_INVALID_ARGUMENT, "command list does not belong to this device"));
+	NvtxScope nvtx("render (recorded command list)");
 	if(int rc = use_device(dev)) return rc;
 	if(int rc = immediate_only(dev, "mlv_execute_command_list")) return rc;
 	if(!list || list->owner != dev) return fail(MLV_ERR_INVALID_ARGUMENT, "command list does not belong to this device");
@@ -1530,6 +1678,7 @@ int mlv_execute_command_list(mlv_device *dev, mlv_command_list *list) {
 }
 
 int mlv_command_list_set_constants(mlv_device *dev, mlv_command_list *list, uint32_t draw_index, const void *data, size_t bytes) {
+	GROUP_EACH(dev, (list && list->children && list->owner == dev) ? mlv_command_list_set_constants(c, (*list->children)[gi], draw_index, data, bytes) : fail(MLV_ERR_INVALID_ARGUMENT, "bad command-list constants"));
 	if(int rc = use_device(dev)) return rc;
 	if(!list || list->owner != dev || !data || bytes > sizeof(((GeomParams *)0)->cb)) return fail(MLV_ERR_INVALID_ARGUMENT, "bad command-list constants");
 	if(draw_index != MLV_ALL_DRAWS && draw_index >= list->draws) return fail(MLV_ERR_INVALID_ARGUMENT, "draw %u out of range (%u draws recorded)", draw_index, list->draws);
@@ -1559,6 +1708,16 @@ int mlv_command_list_info(const mlv_command_list *list, uint32_t *out_draws, uin
 }
 
 void mlv_release_command_list(mlv_device *dev, mlv_command_list *list) {
+	if(dev && dev->children) {
+		if(!list) return;
+		if(list->children) {
+			for(size_t gi = 0; gi < list->children->size(); ++gi)
+				if((*list->children)[gi]) mlv_release_command_list((*dev->children)[gi], (*list->children)[gi]);
+			delete list->children;
+		}
+		delete list;
+		return;
+	}
 	if(!dev || !list) return;
 	cudaSetDevice(dev->cuda_dev);
 	cudaStreamSynchronize(dev->stream); // an execution may still be in flight
@@ -1591,6 +1750,8 @@ void *mlv_resolved_color_device_ptr(mlv_device *dev) { return dev ? dev->present
 void *mlv_resolved_depth_device_ptr(mlv_device *dev) { return dev ? dev->resolved_depth : nullptr; }
 
 int mlv_present_readback_async(mlv_device *dev, uint32_t *colors, float *depths) {
+	if(dev && dev->children) return group_present(dev, colors, depths, false);
+	NvtxScope nvtx("present");
 	if(int rc = immediate_only(dev, "mlv_present_readback_async")) return rc;
 	if(int rc = use_device(dev)) return rc;
 	if(int rc = flush_clears(dev)) return rc;
@@ -1611,6 +1772,7 @@ int mlv_present_readback_async(mlv_device *dev, uint32_t *colors, float *depths)
 }
 
 int mlv_present_wait(mlv_device *dev) {
+	if(dev && dev->children) return group_present_wait(dev);
 	if(int rc = immediate_only(dev, "mlv_present_wait")) return rc;
 	if(int rc = use_device(dev)) return rc;
 	if(!dev->readback_in_flight) return MLV_OK;
@@ -1620,6 +1782,8 @@ int mlv_present_wait(mlv_device *dev) {
 }
 
 int mlv_present_readback(mlv_device *dev, uint32_t *colors, float *depths) {
+	if(dev && dev->children) return group_present(dev, colors, depths, true);
+	NvtxScope nvtx("present");
 	if(int rc = immediate_only(dev, "mlv_present_readback")) return rc;
 	if(int rc = use_device(dev)) return rc;
 	if(int rc = flush_clears(dev)) return rc;
@@ -1639,6 +1803,19 @@ int mlv_present_readback(mlv_device *dev, uint32_t *colors, float *depths) {
 }
 
 int mlv_get_stats(mlv_device *dev, mlv_stats *out) {
+	if(dev && dev->children) { // every rank counts its share (a triangle: the owner of its first tile row): the sum is the reference's Stats
+		if(!out) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+		memset(out, 0, sizeof(*out));
+		for(size_t gi = 0; gi < dev->children->size(); ++gi) {
+			mlv_stats s;
+			if(int rc = mlv_get_stats((*dev->children)[gi], &s)) return rc;
+			if(gi == 0) out->vertex_count = s.vertex_count, out->input_triangle_count = s.input_triangle_count; // (replicated inputs)
+			out->assembled_triangle_count += s.assembled_triangle_count;
+			out->active_bin_count += s.active_bin_count;
+			out->total_triangle_count_in_bins += s.total_triangle_count_in_bins;
+		}
+		return MLV_OK;
+	}
 	if(int rc = immediate_only(dev, "mlv_get_stats")) return rc;
 	if(int rc = use_device(dev)) return rc;
 	if(!out) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
@@ -1650,6 +1827,16 @@ int mlv_get_stats(mlv_device *dev, mlv_stats *out) {
 }
 
 int mlv_get_work_counters(mlv_device *dev, mlv_work_counters *out) {
+	if(dev && dev->children) {
+		if(!out) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+		memset(out, 0, sizeof(*out));
+		for(mlv_device *c : *dev->children) {
+			mlv_work_counters w;
+			if(int rc = mlv_get_work_counters(c, &w)) return rc;
+			out->records_written += w.records_written, out->pairs_listed += w.pairs_listed, out->tiles_visited += w.tiles_visited;
+		}
+		return MLV_OK;
+	}
 	if(int rc = immediate_only(dev, "mlv_get_work_counters")) return rc;
 	if(int rc = use_device(dev)) return rc;
 	if(!out) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
@@ -1661,6 +1848,7 @@ int mlv_get_work_counters(mlv_device *dev, mlv_work_counters *out) {
 }
 
 int mlv_reset_stats(mlv_device *dev) {
+	GROUP_EACH(dev, mlv_reset_stats(c));
 	if(int rc = use_device(dev)) return rc;
 	CUDA_TRY(cudaMemsetAsync((char *)dev->ctr + offsetof(Counters, work), 0, sizeof(mlv_work_counters), dev->stream));
 	CUDA_TRY(cudaMemsetAsync((char *)dev->ctr + offsetof(Counters, stats), 0, sizeof(mlv_stats), dev->stream));
@@ -1873,6 +2061,18 @@ int mlv_composite_readback_async(mlv_device *dev, uint32_t *colors) {
 	if(dev->part.num_ranks <= 1) return fail(MLV_ERR_STATE, "device was created with a single rank");
 	if(dev->bcast_pending || dev->xchg_pending) return fail(MLV_ERR_STATE, "call mlv_composite_wait / mlv_composite_join first");
 	CUDA_TRY(cudaEventRecord(dev->ev_resolved, dev->stream)); // after the wait / join
+	CUDA_TRY(cudaStreamWaitEvent(dev->readback_stream, dev->ev_resolved, 0));
+	CUDA_TRY(cudaMemcpyAsync(colors, dev->present_color, (size_t)dev->W * dev->H * 4, cudaMemcpyDeviceToHost, dev->readback_stream));
+	CUDA_TRY(cudaEventRecord(dev->ev_readback_done, dev->readback_stream));
+	dev->readback_in_flight = true;
+	return MLV_OK;
+}
+
+// (device groups, NCCL exchange) the image mlv_composite_unpack left, to the host on the read-back stream
+static int mlv_present_copy_async(mlv_device *dev, uint32_t *colors) {
+	if(int rc = use_device(dev)) return rc;
+	if(dev->readback_in_flight) CUDA_TRY(cudaEventSynchronize(dev->ev_readback_done));
+	CUDA_TRY(cudaEventRecord(dev->ev_resolved, dev->stream));
 	CUDA_TRY(cudaStreamWaitEvent(dev->readback_stream, dev->ev_resolved, 0));
 	CUDA_TRY(cudaMemcpyAsync(colors, dev->present_color, (size_t)dev->W * dev->H * 4, cudaMemcpyDeviceToHost, dev->readback_stream));
 	CUDA_TRY(cudaEventRecord(dev->ev_readback_done, dev->readback_stream));
@@ -2182,7 +2382,14 @@ int mlv_timeline_read(mlv_device *dev, mlv_timeline_event *out, uint32_t capacit
 	return MLV_OK;
 }
 
-uint64_t mlv_kernel_launch_count(mlv_device *dev) { return dev ? dev->launches : 0; }
+uint64_t mlv_kernel_launch_count(mlv_device *dev) {
+	if(dev && dev->children) {
+		uint64_t n = 0;
+		for(mlv_device *c : *dev->children) n += c->launches;
+		return n;
+	}
+	return dev ? dev->launches : 0;
+}
 
 // Word-wise 64-bit FNV-1a over u32 words (h = 0xcbf29ce484222325; h ^= w; h *= 0x100000001b3): the frame hash of
 // tests/golden/golden.json, so that a host can compare a read-back frame with the committed one without Python loops.
@@ -2190,6 +2397,179 @@ uint64_t mlv_fnv64_words(const uint32_t *words, size_t count) {
 	uint64_t h = 0xcbf29ce484222325ull;
 	for(size_t i = 0; i < count; ++i) h = (h ^ (uint64_t)words[i]) * 0x100000001b3ull;
 	return h;
+}
+
+// ---- device groups (mlv_device_desc.num_gpus > 1) -----------------------------------------------------
+// One host thread, N CUDA devices in one process: rank i of the sort-first split lives on CUDA device cuda_device + i
+// (MLV_DEVICE_GROUP_SAME_GPU: all on one device, for tests on a single-GPU box). Geometry, textures and state are
+// replicated by the fan-out above; the frame is composed by the asynchronous peer-memory exchange over plain peer pointers
+// (mlv_composite_peer_attach, same process: no IPC handles) or, with MLV_DEVICE_GROUP_NCCL, by pack + in-place
+// ncclAllGather + unpack inside one NCCL group call. NCCL is loaded on demand (libnccl.so.2): the library has no
+// load-time dependency on it and the peer-memory path needs none.
+struct GroupNccl {
+	void *lib;
+	std::vector<void *> comms;
+	int (*CommInitAll)(void **, int, const int *);
+	int (*CommDestroy)(void *);
+	int (*GroupStart)();
+	int (*GroupEnd)();
+	int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t);
+	const char *(*GetErrorString)(int);
+};
+
+static int group_nccl_init(mlv_device *dev) {
+	GroupNccl *g = new GroupNccl();
+	g->lib = nullptr;
+	for(const char *name : { "libnccl.so.2", "libnccl.so" })
+		if((g->lib = dlopen(name, RTLD_NOW | RTLD_LOCAL))) break;
+	if(!g->lib) {
+		delete g;
+		return fail(MLV_ERR_STATE, "MLV_DEVICE_GROUP_NCCL: cannot load libnccl.so.2 (%s)", dlerror());
+	}
+	g->CommInitAll = (int (*)(void **, int, const int *))dlsym(g->lib, "ncclCommInitAll");
+	g->CommDestroy = (int (*)(void *))dlsym(g->lib, "ncclCommDestroy");
+	g->GroupStart = (int (*)())dlsym(g->lib, "ncclGroupStart");
+	g->GroupEnd = (int (*)())dlsym(g->lib, "ncclGroupEnd");
+	g->AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(g->lib, "ncclAllGather");
+	g->GetErrorString = (const char *(*)(int))dlsym(g->lib, "ncclGetErrorString");
+	if(!g->CommInitAll || !g->CommDestroy || !g->GroupStart || !g->GroupEnd || !g->AllGather || !g->GetErrorString) {
+		dlclose(g->lib);
+		delete g;
+		return fail(MLV_ERR_STATE, "MLV_DEVICE_GROUP_NCCL: libnccl lacks an expected symbol");
+	}
+	std::vector<int> devs;
+	for(mlv_device *c : *dev->children) devs.push_back(c->cuda_dev);
+	g->comms.assign(devs.size(), nullptr);
+	const int rc = g->CommInitAll(g->comms.data(), (int)devs.size(), devs.data());
+	if(rc != 0) {
+		const int code = fail(MLV_ERR_CUDA, "ncclCommInitAll over %zu devices: %s", devs.size(), g->GetErrorString(rc));
+		dlclose(g->lib);
+		delete g;
+		return code;
+	}
+	dev->group_nccl = g;
+	return MLV_OK;
+}
+
+static void group_destroy(mlv_device *dev) {
+	if(dev->group_nccl) {
+		GroupNccl *g = (GroupNccl *)dev->group_nccl;
+		for(size_t i = 0; i < g->comms.size(); ++i) {
+			cudaSetDevice((*dev->children)[i]->cuda_dev);
+			if(g->comms[i]) g->CommDestroy(g->comms[i]);
+		}
+		dlclose(g->lib);
+		delete g;
+	}
+	for(mlv_device *c : *dev->children) mlv_finish(c); // nobody writes into a peer's images any more
+	for(mlv_device *c : *dev->children) mlv_destroy_device(c);
+	delete dev->children;
+	free(dev->group_scratch_color);
+	delete dev;
+}
+
+static int group_create(const mlv_device_desc *desc, mlv_device **out_device) {
+	*out_device = nullptr;
+	const uint32_t n = desc->num_gpus;
+	if(n > MLV_MAX_PEERS) return fail(MLV_ERR_INVALID_ARGUMENT, "num_gpus %u: at most %d", n, MLV_MAX_PEERS);
+	if(desc->num_ranks > 1) return fail(MLV_ERR_INVALID_ARGUMENT, "num_gpus and num_ranks exclude each other: a group creates its own ranks");
+	if(desc->flags & MLV_DEVICE_DEBUG_CAPTURE) return fail(MLV_ERR_INVALID_ARGUMENT, "debug capture is per device, not per group");
+	int first = desc->cuda_device, count = 0;
+	if(first < 0 && cudaGetDevice(&first) != cudaSuccess) return fail(MLV_ERR_CUDA, "no CUDA device");
+	const bool same = (desc->flags & MLV_DEVICE_GROUP_SAME_GPU) != 0;
+	if(cudaGetDeviceCount(&count) != cudaSuccess || (!same && first + (int)n > count)) return fail(MLV_ERR_CUDA, "num_gpus %u from device %d: only %d CUDA devices are visible", n, first, count);
+	mlv_device *g = new(std::nothrow) mlv_device();
+	if(!g) return fail(MLV_ERR_OUT_OF_MEMORY, "host allocation failed");
+	memset((void *)g, 0, sizeof(*g));
+	g->desc = *desc;
+	g->W = (int)desc->width, g->H = (int)desc->height;
+	g->children = new std::vector<mlv_device *>();
+	// one contiguous band of tile rows per GPU unless the caller chose a stripe height (interleaved stripes balance scenes
+	// whose cost varies down the screen)
+	const uint32_t ht = desc->height / 8u;
+	mlv_device_desc cd = *desc;
+	cd.num_gpus = 0;
+	cd.num_ranks = n;
+	cd.flags = desc->flags & ~(uint32_t)(MLV_DEVICE_GROUP_SAME_GPU | MLV_DEVICE_GROUP_NCCL);
+	cd.stripe_height_tiles = desc->stripe_height_tiles ? desc->stripe_height_tiles : (ht + n - 1u) / n;
+	std::vector<mlv_peer_info> infos(n);
+	for(uint32_t i = 0; i < n; ++i) {
+		cd.rank = i;
+		cd.cuda_device = same ? first : first + (int)i;
+		mlv_device *c = nullptr;
+		int rc = mlv_create_device(&cd, &c);
+		if(rc == MLV_OK) {
+			g->children->push_back(c);
+			rc = mlv_composite_peer_export(c, &infos[i]);
+		}
+		if(rc != MLV_OK) {
+			group_destroy(g);
+			return rc;
+		}
+	}
+	for(mlv_device *c : *g->children)
+		if(int rc = mlv_composite_peer_attach(c, infos.data(), 1)) {
+			group_destroy(g);
+			return rc;
+		}
+	if(desc->flags & MLV_DEVICE_GROUP_NCCL)
+		if(int rc = group_nccl_init(g)) {
+			group_destroy(g);
+			return rc;
+		}
+	*out_device = g;
+	return MLV_OK;
+}
+
+// The frame of a group: exchange the ranks' stripes, read rank 0's composed image back. Depth is not exchanged between
+// the ranks (nothing on the device needs it): when the caller wants it, every rank resolves its own depth image and the
+// host keeps the rows each rank owns.
+static int group_present(mlv_device *dev, uint32_t *colors, float *depths, bool wait) {
+	std::vector<mlv_device *> &ch = *dev->children;
+	if(dev->group_nccl) {
+		GroupNccl *g = (GroupNccl *)dev->group_nccl;
+		for(mlv_device *c : ch)
+			if(int rc = mlv_composite_pack(c)) return rc;
+		int rc = g->GroupStart();
+		for(size_t i = 0; i < ch.size() && rc == 0; ++i) {
+			cudaSetDevice(ch[i]->cuda_dev);
+			rc = g->AllGather((const char *)ch[i]->gather + i * ch[i]->chunk_bytes, ch[i]->gather, ch[i]->chunk_bytes, /* ncclChar */ 0, g->comms[i], ch[i]->stream);
+		}
+		const int rc_end = g->GroupEnd();
+		if(rc != 0 || rc_end != 0) return fail(MLV_ERR_CUDA, "ncclAllGather: %s", g->GetErrorString(rc ? rc : rc_end));
+		if(int rc2 = mlv_composite_unpack(ch[0])) return rc2; // (only the rank that is read back needs the row-major image)
+	} else {
+		for(mlv_device *c : ch)
+			if(int rc = mlv_composite_broadcast_async(c)) return rc;
+		for(mlv_device *c : ch)
+			if(int rc = mlv_composite_join(c)) return rc;
+	}
+	if(colors)
+		if(int rc = dev->group_nccl ? mlv_present_copy_async(ch[0], colors) : mlv_composite_readback_async(ch[0], colors)) return rc;
+	if(depths) {
+		const size_t pixels = (size_t)dev->W * dev->H;
+		if(!dev->group_scratch_color && !(dev->group_scratch_color = (uint32_t *)malloc(pixels * 4))) return fail(MLV_ERR_OUT_OF_MEMORY, "host allocation failed");
+		float *scratch = (float *)dev->group_scratch_color;
+		for(mlv_device *c : ch) {
+			if(int rc = mlv_resolve(c)) return rc;
+			cudaSetDevice(c->cuda_dev);
+			CUDA_TRY(cudaMemcpyAsync(scratch, c->resolved_depth, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+			CUDA_TRY(cudaStreamSynchronize(c->stream));
+			for(int ty = 0; ty < c->ht; ++ty)
+				if(c->part.owns_row(ty)) memcpy(depths + (size_t)ty * 8 * dev->W, scratch + (size_t)ty * 8 * dev->W, (size_t)8 * dev->W * 4);
+		}
+	}
+	return wait ? group_present_wait(dev) : MLV_OK;
+}
+
+static int group_present_wait(mlv_device *dev) {
+	mlv_device *c0 = (*dev->children)[0];
+	cudaSetDevice(c0->cuda_dev);
+	if(c0->readback_in_flight) {
+		CUDA_TRY(cudaEventSynchronize(c0->ev_readback_done));
+		c0->readback_in_flight = false;
+	}
+	return MLV_OK;
 }
 
 } // extern "C"

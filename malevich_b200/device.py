@@ -121,13 +121,18 @@ class Device:
     """One B200 running the draw pipeline for a width x height render target."""
 
     def __init__(self, width: int, height: int, cuda_device: int = -1, num_ranks: int = 1, rank: int = 0,
-                 stripe_height_tiles: int = 1, debug_capture: bool = False, max_pairs_per_draw: int = 0):
+                 stripe_height_tiles: int = 1, debug_capture: bool = False, max_pairs_per_draw: int = 0,
+                 num_gpus: int = 0, group_same_gpu: bool = False, group_nccl: bool = False):
+        """num_gpus > 1: a device GROUP -- one host thread, num_gpus CUDA devices in this process, the sort-first fan-out
+        and the exchange of the stripes behind the same calls (include/malevich_b200.h, DEVICE GROUPS); stripe_height_tiles
+        0 = one contiguous band per GPU. group_same_gpu puts every rank on one CUDA device (tests on a single-GPU box)."""
         self._lib = L.load()
         self.width, self.height = int(width), int(height)
         self.num_ranks, self.rank, self.stripe_height_tiles = num_ranks, rank, stripe_height_tiles
         desc = L.DeviceDesc(width=width, height=height, cuda_device=cuda_device, num_ranks=num_ranks, rank=rank,
                             stripe_height_tiles=stripe_height_tiles, max_pairs_per_draw=max_pairs_per_draw,
-                            flags=L.DEVICE_DEBUG_CAPTURE if debug_capture else 0)
+                            flags=(L.DEVICE_DEBUG_CAPTURE if debug_capture else 0) | (L.DEVICE_GROUP_SAME_GPU if group_same_gpu else 0) |
+                            (L.DEVICE_GROUP_NCCL if group_nccl else 0), num_gpus=num_gpus)
         self._h = C.c_void_p()
         L.check(self._lib.mlv_create_device(C.byref(desc), C.byref(self._h)))
         self.graphics_pipeline = Pipeline()

@@ -50,6 +50,88 @@ def test_c_host_builds_and_links_the_c_abi():
         assert name in syms
 
 
+def _fnv64(data: bytes) -> int:
+    h = 0xCBF29CE484222325
+    for b in np.frombuffer(data, dtype=np.uint8).tolist():
+        h = ((h ^ b) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def test_c_octrn_reader_agrees_with_the_python_reader(tmp_path):
+    """host/octrn.c (the reference's octarine_*_read_from_file, main.c:526-559) over the committed assets and over files
+    written by the Python writer: extents and payload hashes equal what malevich_b200.assets reads."""
+    import shutil
+    from malevich_b200 import assets
+    subprocess.run(["make", "-C", HOST_DIR], check=True, capture_output=True)
+    d = tmp_path / "assets"
+    d.mkdir()
+    names = ["toon_sky_mesh", "ftm_ground_mesh", "ninomaru_teien_panorama_irradiance"]
+    for n in names:
+        shutil.copy(os.path.join(assets.ASSET_DIR, n + ".octrn"), d / (n + ".octrn"))
+    tex = assets.standin_texture_srgb(1, size=64)
+    assets.write_octrn_image(str(d / "standin_tex.octrn"), tex)
+    vb, ib = assets.suprematist_scene()
+    assets.write_octrn_mesh(str(d / "sup_mesh.octrn"), vb, ib)
+    names += ["standin_tex", "sup_mesh"]
+    out = subprocess.run([HOST_BIN, "--list-assets", str(d)] + names, check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {l.split()[1]: l.split() for l in out if l}
+    for n in names:
+        path = str(d / (n + ".octrn"))
+        if got[n][0] == "mesh":
+            v, i = assets.read_octrn_mesh(path)
+            assert [int(got[n][2]), int(got[n][3])] == [v.shape[0], i.shape[0]]
+            assert int(got[n][4], 16) == _fnv64(v.tobytes() + i.tobytes())
+        else:
+            t, w, h, fmt = assets.read_octrn_image(path)
+            assert [int(got[n][2]), int(got[n][3]), int(got[n][4])] == [w, h, fmt]
+            assert int(got[n][5], 16) == _fnv64(t.tobytes())
+    assert got["sup_mesh"][0] == "mesh" and got["standin_tex"][0] == "image"
+    # a truncated file is refused, not read past its end
+    blob = open(d / "toon_sky_mesh.octrn", "rb").read()
+    open(d / "bad_mesh.octrn", "wb").write(blob[:-5])
+    r = subprocess.run([HOST_BIN, "--list-assets", str(d), "bad_mesh"], capture_output=True, text=True)
+    assert r.returncode != 0 and "bad_mesh.octrn" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["toon", "suprematism"])
+def test_c_host_loads_the_reference_scene_table(name, tmp_path):
+    """render_host in the reference's own start-up form: init()'s scene table filled by load_mesh / load_texture from
+    .octrn files (the stand-in sRGB textures are written to disk first; load_texture linearises them like main.c:546-558),
+    the PerFrameCB supplied as bytes so that the frame can be compared with the committed golden frame; the PPM
+    (replacement of the GDI blit) holds the same pixels."""
+    import json
+    import shutil
+    from malevich_b200 import assets, camera
+    subprocess.run(["make", "-C", HOST_DIR], check=True, capture_output=True)
+    d = tmp_path / "assets"
+    d.mkdir()
+    for i, part in enumerate(["house", "sky"]):
+        shutil.copy(os.path.join(assets.ASSET_DIR, f"toon_{part}_mesh.octrn"), d / f"toon_{part}_mesh.octrn")
+        assets.write_octrn_image(str(d / f"toon_{part}_tex.octrn"), assets.standin_texture_srgb(i))
+    cb_path, out_path, ppm_path = str(tmp_path / "cb.bin"), str(tmp_path / "out.bin"), str(tmp_path / "frame.ppm")
+    camera.per_frame_cb(320, 200).astype(np.float32).tofile(cb_path)
+    r = subprocess.run([HOST_BIN, "--assets", str(d), "--scene", name, "--size", "320x200", "--cb", cb_path, "--ppm", ppm_path, out_path, "2"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    col, dep, st = read_frame(out_path)
+    key = {"toon": "toon_320x200", "suprematism": "sup_320x200"}[name]
+    frames = np.load(os.path.join(ROOT, "tests", "golden", "small_frames.npz"))
+    parity.assert_frames_match(col, dep, frames[key + "/colors"], frames[key + "/depths"], key)
+    assert st == json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))[key]["stats"]
+    ppm = open(ppm_path, "rb").read()
+    head = b"P6\n320 200\n255\n"
+    assert ppm.startswith(head) and len(ppm) == len(head) + 320 * 200 * 3
+    rgb = np.frombuffer(ppm, dtype=np.uint8, offset=len(head)).reshape(200, 320, 3)
+    assert np.array_equal(rgb[..., 0], (col >> 16) & 0xFF) and np.array_equal(rgb[..., 1], (col >> 8) & 0xFF) and np.array_equal(rgb[..., 2], col & 0xFF)
+    # the camera of init() + update() computed in C (no --cb) draws the same triangles
+    r = subprocess.run([HOST_BIN, "--assets", str(d), "--scene", name, "--size", "320x200", out_path], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    col2, dep2, st2 = read_frame(out_path)
+    assert st2["input_triangle_count"] == st["input_triangle_count"] and abs(st2["assembled_triangle_count"] - st["assembled_triangle_count"]) <= 2
+    assert np.mean(col2 == col) > 0.99
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["sup_320x200", "toon_320x200", "emily_320x200", "loco_320x200"])
 def test_c_host_renders_like_the_reference(name, tmp_path):
