@@ -1459,7 +1459,10 @@ static int draw_common(mlv_device *dev, uint32_t count, bool indexed, uint32_t s
 	launch_pdl(k_fill, fill_blocks, 256, dev->stream, tp);
 	if(int rc = check_launch(dev, "k_fill")) return rc;
 	uint32_t tile_blocks = (dev->num_bins + 7u) / 8u;
-	if(tile_blocks > dev->sm_count * 4u) tile_blocks = dev->sm_count * 4u; // persistent: what is resident at once (__launch_bounds__(256, 4))
+	{ // persistent: what is resident at once (__launch_bounds__(256, 4)), or fewer to leave room for the front halves of later draws
+		static const uint32_t per_sm = getenv("MLV_TILE_CTAS_PER_SM") ? (uint32_t)atoi(getenv("MLV_TILE_CTAS_PER_SM")) : 4u;
+		if(tile_blocks > dev->sm_count * per_sm) tile_blocks = dev->sm_count * per_sm;
+	}
 	prof_pre(dev, MLV_STAGE_TILE);
 	g_pdl = dev->knob_no_pdl_tile ? 0 : 1;
 	switch(dev->ps_id) {

@@ -52,7 +52,7 @@ __device__ __forceinline__ float x86_rsqrt(float x, const uint32_t *__restrict__
 // _mm256_cvtps_epi32 (main.c:1176-1178, common_shader_core.h:106-107): round-to-nearest-even, and the
 // x86 "integer indefinite" 0x80000000 for NaN / out-of-range instead of CUDA's saturation (App. C 11).
 __device__ __forceinline__ int x86_cvt_rne(float f) {
-	if(!(f >= -2147483648.0f && f < 2147483648.0f)) return (int)0x80000000;
+	if(!(fabsf(f) < 2147483648.0f)) return (int)0x80000000; // (one compare: -2^31 itself converts to the same bit pattern)
 	return __float2int_rn(f);
 }
 

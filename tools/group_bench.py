@@ -1,0 +1,46 @@
+#!/usr/bin/env python3
+"""A device GROUP on real GPUs: ONE process, one host thread, N CUDA devices behind the single-device calls
+(mlv_device_desc.num_gpus, include/malevich_b200.h "DEVICE GROUPS"). Renders a BASELINE config as a recorded command list
+per GPU, composes the frame over peer memory (default) or ncclAllGather (--nccl), checks colour AND depth hashes of the
+composed frame against the committed golden frames and prints one JSON line.
+Usage: python tools/group_bench.py <num_gpus> [--config K] [--nccl] [--stripe S] [--frames F] [--same-gpu]"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from malevich_b200 import Device, scenes, _lib as L
+
+ap = argparse.ArgumentParser()
+ap.add_argument("num_gpus", type=int)
+ap.add_argument("--config", type=int, default=5)
+ap.add_argument("--nccl", action="store_true")
+ap.add_argument("--stripe", type=int, default=0)
+ap.add_argument("--frames", type=int, default=40)
+ap.add_argument("--same-gpu", action="store_true")
+a = ap.parse_args()
+KEYS = {1: "config1_toon_1280x720", 2: "config2_ftm_1920x1080", 3: "config3_emily_1920x1080", 4: "config4_locomotive_3840x2160", 5: "config5_synthetic_3840x2160"}
+golden = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "gpu_frames.json")))[KEYS[a.config]]
+sc = scenes.CONFIGS[a.config]()
+with Device(sc.width, sc.height, cuda_device=0, num_gpus=a.num_gpus, group_same_gpu=a.same_gpu, group_nccl=a.nccl, stripe_height_tiles=a.stripe) as dev:
+    scenes.upload(dev, sc)
+    scenes.render(dev, sc)
+    col, dep = dev.present()
+    stats = dev.stats()
+    cl = dev.record(lambda: scenes.render(dev, sc))
+    colors = np.empty((sc.height, sc.width), dtype=np.uint32)
+    def frame():
+        cl.execute()
+        dev.present_into(colors)
+    for _ in range(5):
+        frame()
+    dev.finish()
+    t0 = time.perf_counter()
+    for _ in range(a.frames):
+        frame()
+    dev.finish()
+    ms = 1e3 * (time.perf_counter() - t0) / a.frames
+    cl.release()
+print(json.dumps({"tool": "group_bench", "num_gpus": a.num_gpus, "config": KEYS[a.config], "exchange": "ncclAllGather" if a.nccl else "peer memory",
+                  "stripe_height_tiles": a.stripe or "one band per GPU", "ms_per_frame_incl_readback": round(ms, 4), "frames_per_s": round(1e3 / ms, 1),
+                  "color_fnv": L.fnv64_words(col), "depth_fnv": L.fnv64_words(dep), "matches_golden": {"color": L.fnv64_words(col) == golden["color_fnv"], "depth": L.fnv64_words(dep) == golden["depth_fnv"]},
+                  "replayed_frame_matches": L.fnv64_words(colors) == golden["color_fnv"], "stats": stats,
+                  "note": "one process, one host thread; each frame = one graph launch per GPU + exchange + read-back of the composed 4-byte image to host memory (blocking)"}))

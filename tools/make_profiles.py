@@ -6,7 +6,7 @@ from collections import OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 launch_csv, rep, bench_json = sys.argv[1:4]
-tag = sys.argv[4] if len(sys.argv) > 4 else "r01"
+tag = sys.argv[4] if len(sys.argv) > 4 else "r02"
 out = lambda name: os.path.join(ROOT, "profiles", f"{tag}_{name}")
 
 # ---- launch list: verbatim copy (minus ncu's banner lines) + per-kernel summary + per-launch DRAM traffic
@@ -47,11 +47,30 @@ cols = [raw[0].index(w) for w in want if w in raw[0]]
 with open(out("ncu_full_raw_selected.csv"), "w", newline="") as f:
     csv.writer(f).writerows([[r[c] for c in cols] for r in raw])
 with open(out("ncu_source_hotspots.txt"), "w") as f:
-    for title, kern, extra in (("k_tile, visible draw", "k_tile", ["--launch-count", "1"]), ("k_geom, visible draw (launch 1)", "k_geom$", ["--launch-count", "1"]),
-                               ("k_geom, hidden draw (launch 2)", "k_geom$", ["--launch-skip", "1", "--launch-count", "1"])):
+    for title, kern, extra in (("k_tile, visible draw", "k_tile", ["--launch-count", "1"]), ("k_back, visible draw (launch 1)", "k_back", ["--launch-count", "1"]),
+                               ("k_back, hidden draw (launch 2)", "k_back", ["--launch-skip", "1", "--launch-count", "1"]),
+                               ("k_front (the same work for every draw)", "k_front<", ["--launch-count", "1"])):
         f.write(f"==== {title}: CUDA source lines ranked by warp instructions executed (ncu --page source)\n")
         f.write(subprocess.run([sys.executable, os.path.join(tools, "ncu_lines.py"), rep, kern, "30"] + extra, capture_output=True, text=True).stdout + "\n")
 
-# ---- the bench line
+# ---- the bench line(s): config 5 = the headline; every other bench_*.json / timeline / table found next to it travels too
 json.dump(json.loads(open(bench_json).read().strip().splitlines()[-1]), open(out("bench_config5_n1.json"), "w"), indent=1)
+src_dir = os.path.dirname(os.path.abspath(bench_json))
+import shutil
+for name, dst in [(f"bench_c{c}.json", f"bench_config{c}_n1.json") for c in (1, 2, 3, 4)] + [("bench_ref.json", "bench_reference_arm_config5.json")] + \
+                 [(f"bench_n{n}.json", f"bench_config5_n{n}.json") for n in (2, 4, 8)] + [(f"bench_n{n}_nccl.json", f"bench_config5_n{n}_nccl.json") for n in (2, 4, 8)] + \
+                 [(f"group_n{n}_{m}.json", f"group_config5_n{n}_{m}.json") for n in (2, 4, 8) for m in ("peer", "nccl")]:
+    path = os.path.join(src_dir, name)
+    if os.path.exists(path) and open(path).read().strip():
+        json.dump(json.loads(open(path).read().strip().splitlines()[-1]), open(out(dst), "w"), indent=1)
+for name in ("timeline_config5_n1.json", "timeline_config5_n1.txt", "timeline_config5_rank3of8.json", "timeline_config5_rank3of8.txt", "timeline_config2_n1.json", "timeline_config2_n1.txt",
+             "launch_table_config5_n1.txt", "trace_config5.json", "sanitizer_memcheck.log", "sanitizer_racecheck.log", "sanitizer_synccheck.log"):
+    path = os.path.join(src_dir, name)
+    if os.path.exists(path):
+        shutil.copy(path, out(name))
+w8 = os.path.join(src_dir, "launches_w8_r3.csv")
+if os.path.exists(w8):
+    l8 = open(w8).read().splitlines()
+    s8 = next(i for i, l in enumerate(l8) if l.startswith('"ID"'))
+    open(out("launches_config5_rank3of8.csv"), "w").write("\n".join(l8[s8:]) + "\n")
 print("wrote", sorted(x for x in os.listdir(os.path.join(ROOT, "profiles")) if x.startswith(tag)))
