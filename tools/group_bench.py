@@ -26,21 +26,34 @@ with Device(sc.width, sc.height, cuda_device=0, num_gpus=a.num_gpus, group_same_
     col, dep = dev.present()
     stats = dev.stats()
     cl = dev.record(lambda: scenes.render(dev, sc))
-    colors = np.empty((sc.height, sc.width), dtype=np.uint32)
-    def frame():
+    # pinned host memory (through torch, when present) and a read-back one frame behind: the host collects frame f-1 while the
+    # GPUs render frame f -- what bench.py's e2e does with one process per GPU
+    try:
+        import torch
+        bufs = [torch.empty((sc.height, sc.width), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32) for _ in range(2)]
+        pinned = True
+    except Exception:
+        bufs = [np.empty((sc.height, sc.width), dtype=np.uint32) for _ in range(2)]
+        pinned = False
+    colors = bufs[0]
+    def frame(f):
         cl.execute()
-        dev.present_into(colors)
-    for _ in range(5):
-        frame()
+        dev.present_wait()            # frame f-1 has arrived in bufs[(f-1) & 1]
+        dev.present_async(bufs[f & 1])
+    for f in range(6):
+        frame(f)
+    dev.present_wait()
     dev.finish()
     t0 = time.perf_counter()
-    for _ in range(a.frames):
-        frame()
+    for f in range(a.frames):
+        frame(f)
+    dev.present_wait()
     dev.finish()
     ms = 1e3 * (time.perf_counter() - t0) / a.frames
+    colors = bufs[(a.frames - 1) & 1]
     cl.release()
 print(json.dumps({"tool": "group_bench", "num_gpus": a.num_gpus, "config": KEYS[a.config], "exchange": "ncclAllGather" if a.nccl else "peer memory",
                   "stripe_height_tiles": a.stripe or "one band per GPU", "ms_per_frame_incl_readback": round(ms, 4), "frames_per_s": round(1e3 / ms, 1),
                   "color_fnv": L.fnv64_words(col), "depth_fnv": L.fnv64_words(dep), "matches_golden": {"color": L.fnv64_words(col) == golden["color_fnv"], "depth": L.fnv64_words(dep) == golden["depth_fnv"]},
                   "replayed_frame_matches": L.fnv64_words(colors) == golden["color_fnv"], "stats": stats,
-                  "note": "one process, one host thread; each frame = one graph launch per GPU + exchange + read-back of the composed 4-byte image to host memory (blocking)"}))
+                  "pinned_host_memory": pinned, "note": "one process, one host thread; each frame = one graph launch per GPU + exchange + read-back of the composed 4-byte-per-pixel image to host memory, one frame behind"}))
