@@ -114,6 +114,18 @@ struct IndexStream {
 		const uint32_t raw = index16 ? (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(ib) + start_index + i) : __ldg(reinterpret_cast<const uint32_t *>(ib) + start_index + i);
 		return raw + (uint32_t)base_vertex;
 	}
+	// the three indices of triangle t: one decision about the index width and one address computation per triangle
+	__device__ __forceinline__ void fetch3(uint32_t t, uint32_t &i0, uint32_t &i1, uint32_t &i2) const {
+		const size_t first = (size_t)start_index + 3u * (size_t)t;
+		if(index16) {
+			const unsigned short *p = reinterpret_cast<const unsigned short *>(ib) + first;
+			i0 = __ldg(p), i1 = __ldg(p + 1), i2 = __ldg(p + 2);
+		} else {
+			const uint32_t *p = reinterpret_cast<const uint32_t *>(ib) + first;
+			i0 = __ldg(p), i1 = __ldg(p + 1), i2 = __ldg(p + 2);
+		}
+		i0 += (uint32_t)base_vertex, i1 += (uint32_t)base_vertex, i2 += (uint32_t)base_vertex;
+	}
 };
 
 struct GeomParams {
