@@ -420,32 +420,76 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     e2e_n = [0]
     cb_host = np.ascontiguousarray(scene.per_frame_cb, dtype=np.float32)
 
+    # N > 1: the frame is composed IN HOST MEMORY (args.e2e_composite == "host", default). Its destination is the host, so the
+    # ranks exchange nothing: every rank copies the rows it owns into ONE shared pinned frame (a /dev/shm mapping page-locked by
+    # each rank, malevich_b200/hostframe.py) over its own PCIe link -- N links carry the 33 MB instead of rank 0's alone. Rank 0
+    # is the consumer (the process that would blit it, main.c:1301-1306): it takes frame f once every rank has published its rows
+    # of f, one frame behind the frame being queued. "device": compose on the device with the peer-memory exchange and let rank
+    # 0 read the whole image back (what this bench measured before; kept for comparison).
+    shared = None
+    e2e_composite = "single GPU"
+    if multi:
+        e2e_composite = args.e2e_composite if composite == "p2p" else "device"
+        if e2e_composite == "host":
+            from malevich_b200.hostframe import SharedHostFrames
+            ok = torch.ones(1, device="cuda")
+            try:
+                name = f"mlv_frames_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
+                if rank == 0:
+                    shared = SharedHostFrames(name, scene.height, scene.width, world, rank, slots=2, create=True)
+                dist.barrier()
+                if rank != 0:
+                    shared = SharedHostFrames(name, scene.height, scene.width, world, rank, slots=2)
+                dev.register_host_memory(shared.address, shared.nbytes)
+                shared.reset()
+            except Exception as e:  # noqa: BLE001 -- e.g. no /dev/shm, or the mapping cannot be page-locked
+                print(f"[bench] rank {rank}: shared host frame unavailable ({e}); rank 0 reads the composited frame back", file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                e2e_composite = "device"
+    taken = [None]
+
     def deliver():  # hand the finished frame to the host: double-buffered, the copy of frame f overlaps frame f+1
-        if multi:
-            had = pending[0]
-            drain()  # join the exchange of the previous frame
-            if had and rank == 0:
-                dev.present_wait()
-                dev.composite_readback_async(host_frames[e2e_n[0] % 2])
-                e2e_n[0] += 1
+        f = e2e_n[0]
+        if multi and e2e_composite == "host":
+            if f > 0:
+                dev.present_wait()       # this rank's rows of frame f-1 are in host memory
+                shared.publish(f)
+                if rank == 0:
+                    taken[0] = shared.take(f - 1)  # ... and so are everybody else's: frame f-1 is whole
+            dev.present_owned_rows_async(shared.slot_for_next())
+        elif multi:
+            # exchange and read-back of THIS frame right behind its draws: the next frame's draws (the other tiled framebuffer of
+            # the pair) are queued while rank 0's 33 MB copy is in flight, so the period is max(render, read-back) + exchange.
+            drain()
             dev.composite_broadcast_async()
-            pending[0] = True
+            dev.composite_join()
+            if rank == 0:
+                dev.present_wait()  # the previous frame has arrived in the other host buffer
+                dev.composite_readback_async(host_frames[f % 2])
         else:
             dev.present_wait()
-            dev.present_async(host_frames[e2e_n[0] % 2])
-            e2e_n[0] += 1
+            dev.present_async(host_frames[f % 2])
+        e2e_n[0] += 1
 
-    def flush_e2e():  # deliver the last frame too: K steps = K frames drawn, exchanged and read back
-        if multi:
-            had = pending[0]
-            drain()
-            if had and rank == 0:
+    def flush_e2e():  # deliver the last frame too: K steps = K frames drawn, composed and in host memory
+        f = e2e_n[0]
+        if multi and e2e_composite == "host":
+            if f > 0:
                 dev.present_wait()
-                dev.composite_readback_async(host_frames[e2e_n[0] % 2])
-                e2e_n[0] += 1
+                shared.publish(f)
+                if rank == 0:
+                    taken[0] = shared.take(f - 1)
+        elif multi:
+            drain()
+            if rank == 0:
+                dev.present_wait()
         dev.finish()
 
     def last_delivered():
+        if multi and e2e_composite == "host":
+            return taken[0]
         return host_frames[(e2e_n[0] - 1) % 2]
 
     def frame_e2e_static():
@@ -476,7 +520,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                "image_matches_resident_path": static_ok,
                "note": "the reference's frame loop (main.c:1587-1602): geometry and textures resident (loaded once by init()), per frame the PerFrameCB of every draw replaced from host memory "
                        "(update(), main.c:1595-1597), the recorded frame replayed, the framebuffer read back to pinned host memory (double-buffered: the host collects frame f-1 while frame f is queued"
-                       + ("; rank 0 reads the composited frame)" if multi else ")")}
+                       + ("; composed in host memory: every rank copies the rows it owns into one shared pinned frame over its own PCIe link, rank 0 takes the frame when all rows have arrived)" if e2e_composite == "host"
+                          else "; composed on the device, rank 0 reads the composited frame)" if multi else ")"),
+               "composite": e2e_composite}
 
         # ---- streaming geometry: slabs
         vtx_counts = [o.vertex_buffer.shape[0] for o in scene.objects]
@@ -613,8 +659,22 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         if not multi and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample(scene)
         print(json.dumps(out), flush=True)
+    if shared is not None:
+        dev.finish()
+        try:
+            dev.unregister_host_memory(shared.address)
+        except Exception:  # noqa: BLE001
+            pass
+        taken[0] = None
+        shared.close(unlink=False)
     dev.close()
     if multi:
+        dist.barrier()
+        if shared is not None and rank == 0:
+            try:
+                os.unlink(shared.path)
+            except OSError:
+                pass
         dist.destroy_process_group()
 
 
@@ -627,6 +687,8 @@ def main():
     ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--stripe", type=int, default=0, help="stripe height in tile rows for the sort-first split (0 = one contiguous band per rank)")
     ap.add_argument("--composite", default="p2p", choices=["p2p", "nccl"], help="multi-GPU exchange step: asynchronous peer-memory broadcast (default) or pack + ncclAllGather + unpack")
+    ap.add_argument("--e2e-composite", default="host", choices=["host", "device"], help="N > 1, end-to-end loops: compose the frame in host memory (every rank delivers the rows it owns over its own PCIe link; default) "
+                    "or on the device (peer-memory exchange, rank 0 reads the whole image back)")
     ap.add_argument("--immediate", action="store_true", help="issue every call every frame instead of replaying a recorded command list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child process that measures roofline.traffic")

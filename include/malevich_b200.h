@@ -104,15 +104,18 @@ typedef struct mlv_device_desc {
 } mlv_device_desc;
 enum { MLV_DEVICE_DEBUG_CAPTURE = 1, /* keep reference-layout intermediates of the last draw for mlv_debug_read_* */
        MLV_DEVICE_GROUP_SAME_GPU = 2, /* device group: every rank on cuda_device (tests on a single-GPU box) */
-       MLV_DEVICE_GROUP_NCCL = 4 };   /* device group: compose the frame with pack + in-place ncclAllGather + unpack (libnccl.so.2,
-                                       * loaded on demand) instead of the asynchronous peer-memory exchange */
+       MLV_DEVICE_GROUP_NCCL = 4,     /* device group: compose the frame on the device with pack + in-place ncclAllGather + unpack
+                                       * (libnccl.so.2, loaded on demand), then read rank 0's image back */
+       MLV_DEVICE_GROUP_PEER_EXCHANGE = 8 }; /* device group: compose it on the device with the asynchronous peer-memory exchange over
+                                       * NVLink, then read rank 0's image back. Default (neither flag): the frame is composed IN HOST
+                                       * MEMORY -- every GPU copies the rows it owns over its own PCIe link (mlv_present_owned_rows_async) */
 /* DEVICE GROUPS. With num_gpus = N the multi-GPU fan-out lives behind the same calls: the handle returned by
  * mlv_create_device stands for N per-GPU devices -- geometry, textures and pipeline state replicated, rank i rasterising the
  * tile rows (ty / stripe_height_tiles) % N == i (default: one contiguous band per GPU) -- and the entry points a renderer
  * needs fan out to them: buffers and textures (create / update / release, sRGB, mips), every state setter, both clears, the
  * three draws, command lists (one recording per GPU, one graph launch per GPU per frame), mlv_present_readback[_async] /
- * mlv_present_wait (exchange of the stripes over peer memory or NCCL, then rank 0's image; depth rows are collected from
- * their owners on the host), mlv_get_stats / mlv_get_work_counters (sums of the ranks' shares = the reference's Stats),
+ * mlv_present_wait (every GPU delivers the rows it owns straight to the host frame; or, by flag, exchange of the stripes over
+ * peer memory / NCCL and then rank 0's image; depth rows are collected from their owners on the host), mlv_get_stats / mlv_get_work_counters (sums of the ranks' shares = the reference's Stats),
  * mlv_reset_stats, mlv_finish, mlv_kernel_launch_count, mlv_destroy_device. Every other entry point returns
  * MLV_ERR_STATE for a group. host/malevich_compat.c creates a group when MLV_NUM_GPUS is set, so the reference's
  * render() runs on N GPUs unchanged. */
@@ -283,6 +286,17 @@ MLV_API int mlv_composite_broadcast_async(mlv_device *dev);
  * rank's own tiles); completed by mlv_present_wait / mlv_finish. Call it after mlv_composite_wait / mlv_composite_join. */
 MLV_API int mlv_composite_readback_async(mlv_device *dev, uint32_t *colors);
 MLV_API int mlv_composite_join(mlv_device *dev);
+/* Composite in HOST memory: this rank packs the stripes it owns and copies them to their rows of frame_colors -- the FULL
+ * row-major frame (width * height words) in pinned host memory shared by all ranks -- on the read-back stream, over its own
+ * PCIe link; nothing is exchanged between the GPUs. The frame is complete when every rank's mlv_present_wait has returned.
+ * A single-rank device reads its whole frame back; a device group fans the call out. */
+MLV_API int mlv_present_owned_rows_async(mlv_device *dev, uint32_t *frame_colors);
+/* Page-lock host memory the caller owns (malloc, or a MAP_SHARED mapping that several rank processes open: the shared frame
+ * of mlv_present_owned_rows_async) for this device's CUDA context, so that the asynchronous read-backs into it run at full
+ * PCIe rate and really are asynchronous; undo it before the memory is freed or unmapped. A host that does not link CUDA
+ * has no other way to do this (the reference's frame buffer is a plain static array, main.c:113). */
+MLV_API int mlv_register_host_memory(mlv_device *dev, void *ptr, size_t bytes);
+MLV_API int mlv_unregister_host_memory(mlv_device *dev, void *ptr);
 
 /* ---- debug read-back of the last draw (needs MLV_DEVICE_DEBUG_CAPTURE). Each synchronises.
  * Pass NULL data pointers to query the counts only. */

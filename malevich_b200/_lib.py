@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "mlv_begin_command_list", "mlv_finish_command_list", "mlv_execute_command_list", "mlv_command_list_set_constants", "mlv_command_list_info", "mlv_release_command_list",
     "mlv_present_readback", "mlv_present_readback_async", "mlv_present_wait", "mlv_get_stats", "mlv_reset_stats", "mlv_get_work_counters",
     "mlv_resolve", "mlv_resolved_color_device_ptr", "mlv_resolved_depth_device_ptr",
-    "mlv_composite_peer_export", "mlv_composite_peer_attach", "mlv_composite_broadcast", "mlv_composite_wait", "mlv_composite_broadcast_async", "mlv_composite_join", "mlv_composite_readback_async", "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
+    "mlv_composite_peer_export", "mlv_composite_peer_attach", "mlv_composite_broadcast", "mlv_composite_wait", "mlv_composite_broadcast_async", "mlv_composite_join", "mlv_composite_readback_async", "mlv_present_owned_rows_async", "mlv_register_host_memory", "mlv_unregister_host_memory", "mlv_composite_layout", "mlv_composite_pack", "mlv_composite_unpack",
     "mlv_debug_read_vs_out", "mlv_debug_read_triangles", "mlv_debug_read_bins", "mlv_debug_read_masks",
     "mlv_debug_read_tile_min_depths", "mlv_debug_read_keys", "mlv_read_bin_lists", "mlv_fnv64_words", "mlv_profile_begin", "mlv_profile_end", "mlv_profile_read_events", "mlv_kernel_launch_count",
     "mlv_timeline_begin", "mlv_timeline_end", "mlv_timeline_reset", "mlv_timeline_read",
@@ -33,7 +33,7 @@ PS_PASSTHROUGH, PS_BASIC, PS_ENV_LIGHTING, PS_BASIC_TRILINEAR = 0, 1, 2, 3
 FORMAT_R8G8B8A8_UNORM, FORMAT_R32G32B32A32_FLOAT = 0, 1
 BUFFER_VERTEX, BUFFER_INDEX = 0, 1
 INDEX_U32, INDEX_U16 = 0, 1
-DEVICE_DEBUG_CAPTURE, DEVICE_GROUP_SAME_GPU, DEVICE_GROUP_NCCL = 1, 2, 4
+DEVICE_DEBUG_CAPTURE, DEVICE_GROUP_SAME_GPU, DEVICE_GROUP_NCCL, DEVICE_GROUP_PEER_EXCHANGE = 1, 2, 4, 8
 ALL_DRAWS = 0xFFFFFFFF
 
 
@@ -153,6 +153,9 @@ def load() -> C.CDLL:
         "mlv_composite_broadcast_async": (i32, [vp]),
         "mlv_composite_join": (i32, [vp]),
         "mlv_composite_readback_async": (i32, [vp, vp]),
+        "mlv_present_owned_rows_async": (i32, [vp, vp]),
+        "mlv_register_host_memory": (i32, [vp, vp, C.c_size_t]),
+        "mlv_unregister_host_memory": (i32, [vp, vp]),
         "mlv_composite_pack": (i32, [vp]),
         "mlv_composite_unpack": (i32, [vp]),
         "mlv_debug_read_vs_out": (i32, [vp, vp, P(u32)]),

@@ -191,6 +191,9 @@ struct mlv_device {
 	cudaStream_t readback_stream;
 	cudaEvent_t ev_resolved, ev_readback_done;
 	bool readback_in_flight;
+	cudaEvent_t ev_owned_prev; // mlv_present_owned_rows_async: completion of the copy issued one call earlier (its chunk is packed again by the next call)
+	bool owned_prev_recorded;
+	uint32_t owned_parity;
 	cudaEvent_t ev_main_sync;
 	uint32_t bin_begin, bin_end; // bins this rank can touch: everything, or one contiguous band
 	uint32_t tri_capacity; // slots (direct + overflow)
@@ -391,7 +394,12 @@ const char *mlv_last_error_string(void) { return g_last_error; }
 		}                                                                          \
 		return MLV_OK;                                                             \
 	}
-#define GROUP_CHILD(obj) ((obj) ? ((obj)->children ? (*(obj)->children)[gi] : (obj)) : nullptr)
+#define GROUP_CHILD(obj) ((obj) ? (*(obj)->children)[gi] : nullptr)
+// a resource handed to a device group must be one the SAME group created (one replica per GPU)
+#define GROUP_OWNS(dev, obj)                                                                                                        \
+	if((dev) && (dev)->children && (obj) && (!(obj)->children || (obj)->children->size() != (dev)->children->size()))                 \
+		return fail(MLV_ERR_INVALID_ARGUMENT, "the resource does not belong to this device group");                                     \
+	if((dev) && !(dev)->children && (obj) && (obj)->children) return fail(MLV_ERR_INVALID_ARGUMENT, "the resource belongs to a device group, not to this device");
 static int group_create(const mlv_device_desc *desc, mlv_device **out_device);
 static void group_destroy(mlv_device *dev);
 static int group_present(mlv_device *dev, uint32_t *colors, float *depths, bool wait);
@@ -493,6 +501,7 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	CREATE_TRY(cudaStreamCreateWithFlags(&dev->readback_stream, cudaStreamNonBlocking));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_resolved, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_readback_done, cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_owned_prev, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_main_sync, cudaEventDisableTiming));
 	for(uint32_t i = 0; i < dev->num_ctx; ++i) {
 		DrawCtx &c = dev->ctxs[i];
@@ -607,7 +616,7 @@ void mlv_destroy_device(mlv_device *dev) {
 		cudaStreamSynchronize(dev->readback_stream);
 		cudaStreamDestroy(dev->readback_stream);
 	}
-	for(cudaEvent_t e : { dev->ev_last_draw, dev->ev_resolved, dev->ev_readback_done, dev->ev_main_sync, dev->ev_frame_done, dev->ev_xchg_done, dev->ev_fb_free[0], dev->ev_fb_free[1] })
+	for(cudaEvent_t e : { dev->ev_last_draw, dev->ev_resolved, dev->ev_readback_done, dev->ev_owned_prev, dev->ev_main_sync, dev->ev_frame_done, dev->ev_xchg_done, dev->ev_fb_free[0], dev->ev_fb_free[1] })
 		if(e) cudaEventDestroy(e);
 	if(dev->prof_events) {
 		for(cudaEvent_t e : *dev->prof_events) cudaEventDestroy(e);
@@ -678,6 +687,7 @@ int mlv_create_buffer(mlv_device *dev, const void *data, size_t bytes, int kind,
 }
 
 int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t bytes) {
+	GROUP_OWNS(dev, buf);
 	GROUP_EACH(dev, mlv_update_buffer(c, GROUP_CHILD(buf), data, bytes));
 	if(int rc = use_device(dev)) return rc;
 	if(!buf || !data || bytes > buf->bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer update");
@@ -693,6 +703,7 @@ int mlv_update_buffer(mlv_device *dev, mlv_buffer *buf, const void *data, size_t
 }
 
 int mlv_update_buffer_range(mlv_device *dev, mlv_buffer *buf, size_t offset, const void *data, size_t bytes) {
+	GROUP_OWNS(dev, buf);
 	GROUP_EACH(dev, mlv_update_buffer_range(c, GROUP_CHILD(buf), offset, data, bytes));
 	if(int rc = use_device(dev)) return rc;
 	if(!buf || !data || offset > buf->bytes || bytes > buf->bytes - offset) return fail(MLV_ERR_INVALID_ARGUMENT, "bad buffer range update");
@@ -789,6 +800,7 @@ int mlv_create_texture2d(mlv_device *dev, const void *texels, uint32_t width, ui
 }
 
 int mlv_texture_srgb_to_linear(mlv_device *dev, mlv_texture *tex) {
+	GROUP_OWNS(dev, tex);
 	GROUP_EACH(dev, mlv_texture_srgb_to_linear(c, GROUP_CHILD(tex)));
 	if(int rc = immediate_only(dev, "mlv_texture_srgb_to_linear")) return rc;
 	if(int rc = use_device(dev)) return rc;
@@ -818,6 +830,7 @@ static uint32_t mip_extent_host(uint32_t e, uint32_t level) {
 }
 
 int mlv_texture_generate_mips(mlv_device *dev, mlv_texture *tex) {
+	GROUP_OWNS(dev, tex);
 	GROUP_EACH(dev, mlv_texture_generate_mips(c, GROUP_CHILD(tex)));
 	if(int rc = immediate_only(dev, "mlv_texture_generate_mips")) return rc;
 	if(int rc = use_device(dev)) return rc;
@@ -907,6 +920,7 @@ void mlv_release_texture(mlv_device *dev, mlv_texture *tex) {
 // ---- pipeline state ------------------------------------------------------------------------------
 
 int mlv_ia_set_vertex_buffer(mlv_device *dev, mlv_buffer *vb) {
+	GROUP_OWNS(dev, vb);
 	GROUP_EACH(dev, mlv_ia_set_vertex_buffer(c, GROUP_CHILD(vb)));
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	if(vb && vb->kind != MLV_BUFFER_VERTEX) return fail(MLV_ERR_INVALID_ARGUMENT, "buffer is not a vertex buffer");
@@ -914,6 +928,7 @@ int mlv_ia_set_vertex_buffer(mlv_device *dev, mlv_buffer *vb) {
 	return MLV_OK;
 }
 int mlv_ia_set_index_buffer(mlv_device *dev, mlv_buffer *ib) {
+	GROUP_OWNS(dev, ib);
 	GROUP_EACH(dev, mlv_ia_set_index_buffer(c, GROUP_CHILD(ib)));
 	if(!dev) return fail(MLV_ERR_INVALID_ARGUMENT, "null device");
 	if(ib && ib->kind != MLV_BUFFER_INDEX) return fail(MLV_ERR_INVALID_ARGUMENT, "buffer is not an index buffer");
@@ -956,6 +971,7 @@ int mlv_vs_set_constant_buffer(mlv_device *dev, uint32_t slot, const void *data,
 	return MLV_OK;
 }
 int mlv_vs_set_shader_resource(mlv_device *dev, uint32_t slot, mlv_texture *tex) {
+	GROUP_OWNS(dev, tex);
 	GROUP_EACH(dev, mlv_vs_set_shader_resource(c, slot, GROUP_CHILD(tex)));
 	if(!dev || slot >= MLV_SHADER_RESOURCE_SLOT_COUNT) return fail(MLV_ERR_INVALID_ARGUMENT, "bad shader resource slot");
 	dev->vs_srv[slot] = tex;
@@ -978,6 +994,7 @@ int mlv_ps_set_shader(mlv_device *dev, int ps_id) {
 	return MLV_OK;
 }
 int mlv_ps_set_shader_resource(mlv_device *dev, uint32_t slot, mlv_texture *tex) {
+	GROUP_OWNS(dev, tex);
 	GROUP_EACH(dev, mlv_ps_set_shader_resource(c, slot, GROUP_CHILD(tex)));
 	if(!dev || slot >= MLV_SHADER_RESOURCE_SLOT_COUNT) return fail(MLV_ERR_INVALID_ARGUMENT, "bad shader resource slot");
 	dev->ps_srv[slot] = tex;
@@ -1878,6 +1895,67 @@ int mlv_composite_pack(mlv_device *dev) {
 	return check_launch(dev, "k_composite_pack");
 }
 
+// COMPOSITE IN HOST MEMORY. A frame whose destination is the host does not need the ranks to exchange anything: every rank
+// packs the stripes it owns (k_composite_pack, row-major in stripe order) and copies them straight to their rows of ONE
+// host frame -- pinned memory shared by the ranks (one process: any pinned buffer; several processes: a shared mapping
+// registered with cudaHostRegister in each) -- over its OWN PCIe link. N links carry the frame in parallel and NVLink is not
+// involved; the frame is complete when every rank's mlv_present_wait has returned. Two packed chunks alternate, so the copy
+// of frame f is still in flight while frame f+1 is packed.
+int mlv_present_owned_rows_async(mlv_device *dev, uint32_t *frame_colors) {
+	if(dev && dev->children) { // a device group: every GPU delivers its band
+		if(!frame_colors) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+		for(mlv_device *c : *dev->children)
+			if(int rc = mlv_present_owned_rows_async(c, frame_colors)) return rc;
+		return MLV_OK;
+	}
+	if(int rc = immediate_only(dev, "mlv_present_owned_rows_async")) return rc;
+	if(int rc = use_device(dev)) return rc;
+	if(!frame_colors) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	if(dev->part.num_ranks <= 1) return mlv_present_readback_async(dev, frame_colors, nullptr);
+	if(int rc = flush_clears(dev)) return rc;
+	const int n = dev->part.num_ranks, me = dev->part.rank, sh = dev->part.stripe_h;
+	dev->owned_parity ^= 1u;
+	uint4 *chunk = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(dev->gather) + dev->chunk_bytes * (size_t)((me + (int)dev->owned_parity) % n));
+	// the chunk written now was read by the copy issued two calls ago: that copy is complete once the previous one is
+	// (same stream), and the host has normally collected it (mlv_present_wait) long before
+	if(dev->owned_prev_recorded) CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_owned_prev, 0));
+	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
+	prof_pre(dev, MLV_STAGE_COMPOSITE);
+	launch_pdl(k_composite_pack, (items + 255) / 256, 256, dev->stream, dev->fb, chunk, dev->W, dev->H, dev->part);
+	if(int rc = check_launch(dev, "k_composite_pack")) return rc;
+	CUDA_TRY(cudaEventRecord(dev->ev_resolved, dev->stream));
+	CUDA_TRY(cudaStreamWaitEvent(dev->readback_stream, dev->ev_resolved, 0));
+	if(dev->readback_in_flight) { // the event of the copy before this one, for the call after this one
+		CUDA_TRY(cudaEventRecord(dev->ev_owned_prev, dev->readback_stream));
+		dev->owned_prev_recorded = true;
+	}
+	const size_t row_bytes = (size_t)dev->W * 4;
+	uint32_t local = 0;
+	for(int stripe = me; stripe * sh < dev->ht; stripe += n, ++local) { // (ty / sh) % n == me
+		const int ty0 = stripe * sh, ty1 = (ty0 + sh < dev->ht) ? ty0 + sh : dev->ht;
+		CUDA_TRY(cudaMemcpyAsync((char *)frame_colors + (size_t)ty0 * 8 * row_bytes, (const char *)chunk + (size_t)local * sh * 8 * row_bytes, (size_t)(ty1 - ty0) * 8 * row_bytes,
+		                         cudaMemcpyDeviceToHost, dev->readback_stream));
+	}
+	CUDA_TRY(cudaEventRecord(dev->ev_readback_done, dev->readback_stream));
+	dev->readback_in_flight = true;
+	return MLV_OK;
+}
+
+int mlv_register_host_memory(mlv_device *dev, void *ptr, size_t bytes) {
+	if(!dev || !ptr || !bytes) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	mlv_device *d = dev->children ? (*dev->children)[0] : dev;
+	if(int rc = use_device(d)) return rc;
+	CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable)); // portable: every device of a group may copy into it
+	return MLV_OK;
+}
+int mlv_unregister_host_memory(mlv_device *dev, void *ptr) {
+	if(!dev || !ptr) return fail(MLV_ERR_INVALID_ARGUMENT, "null argument");
+	mlv_device *d = dev->children ? (*dev->children)[0] : dev;
+	if(int rc = use_device(d)) return rc;
+	CUDA_TRY(cudaHostUnregister(ptr));
+	return MLV_OK;
+}
+
 int mlv_composite_unpack(mlv_device *dev) {
 	if(int rc = immediate_only(dev, "mlv_composite_unpack")) return rc;
 	if(int rc = use_device(dev)) return rc;
@@ -2493,7 +2571,7 @@ static int group_create(const mlv_device_desc *desc, mlv_device **out_device) {
 	mlv_device_desc cd = *desc;
 	cd.num_gpus = 0;
 	cd.num_ranks = n;
-	cd.flags = desc->flags & ~(uint32_t)(MLV_DEVICE_GROUP_SAME_GPU | MLV_DEVICE_GROUP_NCCL);
+	cd.flags = desc->flags & ~(uint32_t)(MLV_DEVICE_GROUP_SAME_GPU | MLV_DEVICE_GROUP_NCCL | MLV_DEVICE_GROUP_PEER_EXCHANGE);
 	cd.stripe_height_tiles = desc->stripe_height_tiles ? desc->stripe_height_tiles : (ht + n - 1u) / n;
 	std::vector<mlv_peer_info> infos(n);
 	for(uint32_t i = 0; i < n; ++i) {
@@ -2541,14 +2619,21 @@ static int group_present(mlv_device *dev, uint32_t *colors, float *depths, bool 
 		const int rc_end = g->GroupEnd();
 		if(rc != 0 || rc_end != 0) return fail(MLV_ERR_CUDA, "ncclAllGather: %s", g->GetErrorString(rc ? rc : rc_end));
 		if(int rc2 = mlv_composite_unpack(ch[0])) return rc2; // (only the rank that is read back needs the row-major image)
-	} else {
+	} else if(dev->desc.flags & MLV_DEVICE_GROUP_PEER_EXCHANGE) {
 		for(mlv_device *c : ch)
 			if(int rc = mlv_composite_broadcast_async(c)) return rc;
 		for(mlv_device *c : ch)
 			if(int rc = mlv_composite_join(c)) return rc;
 	}
-	if(colors)
-		if(int rc = dev->group_nccl ? mlv_present_copy_async(ch[0], colors) : mlv_composite_readback_async(ch[0], colors)) return rc;
+	if(colors) {
+		if(dev->group_nccl) {
+			if(int rc = mlv_present_copy_async(ch[0], colors)) return rc;
+		} else if(dev->desc.flags & MLV_DEVICE_GROUP_PEER_EXCHANGE) {
+			if(int rc = mlv_composite_readback_async(ch[0], colors)) return rc;
+		} else { // default: the frame is composed in host memory, every GPU delivers its band over its own PCIe link
+			if(int rc = mlv_present_owned_rows_async(dev, colors)) return rc;
+		}
+	}
 	if(depths) {
 		const size_t pixels = (size_t)dev->W * dev->H;
 		if(!dev->group_scratch_color && !(dev->group_scratch_color = (uint32_t *)malloc(pixels * 4))) return fail(MLV_ERR_OUT_OF_MEMORY, "host allocation failed");
@@ -2566,11 +2651,11 @@ static int group_present(mlv_device *dev, uint32_t *colors, float *depths, bool 
 }
 
 static int group_present_wait(mlv_device *dev) {
-	mlv_device *c0 = (*dev->children)[0];
-	cudaSetDevice(c0->cuda_dev);
-	if(c0->readback_in_flight) {
-		CUDA_TRY(cudaEventSynchronize(c0->ev_readback_done));
-		c0->readback_in_flight = false;
+	for(mlv_device *c : *dev->children) {
+		if(!c->readback_in_flight) continue;
+		cudaSetDevice(c->cuda_dev);
+		CUDA_TRY(cudaEventSynchronize(c->ev_readback_done));
+		c->readback_in_flight = false;
 	}
 	return MLV_OK;
 }

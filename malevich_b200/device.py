@@ -122,7 +122,7 @@ class Device:
 
     def __init__(self, width: int, height: int, cuda_device: int = -1, num_ranks: int = 1, rank: int = 0,
                  stripe_height_tiles: int = 1, debug_capture: bool = False, max_pairs_per_draw: int = 0,
-                 num_gpus: int = 0, group_same_gpu: bool = False, group_nccl: bool = False):
+                 num_gpus: int = 0, group_same_gpu: bool = False, group_nccl: bool = False, group_peer_exchange: bool = False):
         """num_gpus > 1: a device GROUP -- one host thread, num_gpus CUDA devices in this process, the sort-first fan-out
         and the exchange of the stripes behind the same calls (include/malevich_b200.h, DEVICE GROUPS); stripe_height_tiles
         0 = one contiguous band per GPU. group_same_gpu puts every rank on one CUDA device (tests on a single-GPU box)."""
@@ -132,7 +132,7 @@ class Device:
         desc = L.DeviceDesc(width=width, height=height, cuda_device=cuda_device, num_ranks=num_ranks, rank=rank,
                             stripe_height_tiles=stripe_height_tiles, max_pairs_per_draw=max_pairs_per_draw,
                             flags=(L.DEVICE_DEBUG_CAPTURE if debug_capture else 0) | (L.DEVICE_GROUP_SAME_GPU if group_same_gpu else 0) |
-                            (L.DEVICE_GROUP_NCCL if group_nccl else 0), num_gpus=num_gpus)
+                            (L.DEVICE_GROUP_NCCL if group_nccl else 0) | (L.DEVICE_GROUP_PEER_EXCHANGE if group_peer_exchange else 0), num_gpus=num_gpus)
         self._h = C.c_void_p()
         L.check(self._lib.mlv_create_device(C.byref(desc), C.byref(self._h)))
         self.graphics_pipeline = Pipeline()
@@ -371,6 +371,18 @@ class Device:
     def present_into(self, colors: np.ndarray, depths: Optional[np.ndarray] = None):
         L.check(self._lib.mlv_present_readback(self._h, colors.ctypes.data_as(C.c_void_p),
                                                depths.ctypes.data_as(C.c_void_p) if depths is not None else None))
+
+    def present_owned_rows_async(self, frame_colors: np.ndarray):
+        """Composite in host memory: this rank copies the rows it owns into the FULL frame `frame_colors` (pinned, shared by all
+        ranks) over its own PCIe link; present_wait() completes it."""
+        L.check(self._lib.mlv_present_owned_rows_async(self._h, frame_colors.ctypes.data_as(C.c_void_p)))
+
+    def register_host_memory(self, address: int, nbytes: int):
+        """Page-lock caller-owned host memory (e.g. the shared mapping of hostframe.SharedHostFrames) for asynchronous read-backs."""
+        L.check(self._lib.mlv_register_host_memory(self._h, C.c_void_p(address), nbytes))
+
+    def unregister_host_memory(self, address: int):
+        L.check(self._lib.mlv_unregister_host_memory(self._h, C.c_void_p(address)))
 
     def present_async(self, colors: np.ndarray, depths: Optional[np.ndarray] = None):
         """Non-blocking present into (page-locked) arrays; `present_wait` or `finish` says when they are complete."""

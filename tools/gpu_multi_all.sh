@@ -13,5 +13,6 @@ PY
 }
 run ""
 run _nccl --composite nccl
-timeout 200 python tools/group_bench.py $N 2>&1 | tail -1 > gpurun_out/group_n${N}_peer.json; cut -c1-330 gpurun_out/group_n${N}_peer.json
+timeout 200 python tools/group_bench.py $N 2>&1 | tail -1 > gpurun_out/group_n${N}_host.json; cut -c1-400 gpurun_out/group_n${N}_host.json
+timeout 200 python tools/group_bench.py $N --peer 2>&1 | tail -1 > gpurun_out/group_n${N}_peer.json; cut -c1-330 gpurun_out/group_n${N}_peer.json
 timeout 200 python tools/group_bench.py $N --nccl 2>&1 | tail -1 > gpurun_out/group_n${N}_nccl.json; cut -c1-330 gpurun_out/group_n${N}_nccl.json

@@ -12,7 +12,8 @@ from malevich_b200 import Device, scenes, _lib as L
 ap = argparse.ArgumentParser()
 ap.add_argument("num_gpus", type=int)
 ap.add_argument("--config", type=int, default=5)
-ap.add_argument("--nccl", action="store_true")
+ap.add_argument("--nccl", action="store_true", help="compose on the device with pack + ncclAllGather + unpack, read rank 0's image back")
+ap.add_argument("--peer", action="store_true", help="compose on the device with the asynchronous peer-memory exchange, read rank 0's image back (default: compose in host memory, every GPU delivers its band)")
 ap.add_argument("--stripe", type=int, default=0)
 ap.add_argument("--frames", type=int, default=40)
 ap.add_argument("--same-gpu", action="store_true")
@@ -20,7 +21,7 @@ a = ap.parse_args()
 KEYS = {1: "config1_toon_1280x720", 2: "config2_ftm_1920x1080", 3: "config3_emily_1920x1080", 4: "config4_locomotive_3840x2160", 5: "config5_synthetic_3840x2160"}
 golden = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "gpu_frames.json")))[KEYS[a.config]]
 sc = scenes.CONFIGS[a.config]()
-with Device(sc.width, sc.height, cuda_device=0, num_gpus=a.num_gpus, group_same_gpu=a.same_gpu, group_nccl=a.nccl, stripe_height_tiles=a.stripe) as dev:
+with Device(sc.width, sc.height, cuda_device=0, num_gpus=a.num_gpus, group_same_gpu=a.same_gpu, group_nccl=a.nccl, group_peer_exchange=a.peer, stripe_height_tiles=a.stripe) as dev:
     scenes.upload(dev, sc)
     scenes.render(dev, sc)
     col, dep = dev.present()
@@ -52,7 +53,7 @@ with Device(sc.width, sc.height, cuda_device=0, num_gpus=a.num_gpus, group_same_
     ms = 1e3 * (time.perf_counter() - t0) / a.frames
     colors = bufs[(a.frames - 1) & 1]
     cl.release()
-print(json.dumps({"tool": "group_bench", "num_gpus": a.num_gpus, "config": KEYS[a.config], "exchange": "ncclAllGather" if a.nccl else "peer memory",
+print(json.dumps({"tool": "group_bench", "num_gpus": a.num_gpus, "config": KEYS[a.config], "exchange": "ncclAllGather" if a.nccl else ("peer memory" if a.peer else "none: every GPU copies its band to the host frame over its own PCIe link"),
                   "stripe_height_tiles": a.stripe or "one band per GPU", "ms_per_frame_incl_readback": round(ms, 4), "frames_per_s": round(1e3 / ms, 1),
                   "color_fnv": L.fnv64_words(col), "depth_fnv": L.fnv64_words(dep), "matches_golden": {"color": L.fnv64_words(col) == golden["color_fnv"], "depth": L.fnv64_words(dep) == golden["depth_fnv"]},
                   "replayed_frame_matches": L.fnv64_words(colors) == golden["color_fnv"], "stats": stats,
