@@ -5,7 +5,7 @@ small counters that tell the consumer -- rank 0, the process that would blit the
 
     frame f lives in slot f % slots
     done[r]   = number of frames whose rows rank r has delivered (written by rank r after its present_wait)
-    consumed  = number of frames rank 0 has taken (written by rank 0)
+    consumed  = number of frames rank 0 has taken AND let go of (written by rank 0: taking frame f lets go of every frame before f)
 
 No CUDA here: the mapping is page-locked for a device with Device.register_host_memory by its user."""
 import mmap
@@ -23,6 +23,15 @@ class SharedHostFrames:
         header = 4096  # counters on their own page
         total = header + slots * self.frame_bytes
         if create:
+            try:
+                os.unlink(self.path)  # left behind by a run that died
+            except FileNotFoundError:
+                pass
+            # tmpfs pages are allocated on first touch and a full /dev/shm answers with SIGBUS, not with an error: refuse up
+            # front (a container's default /dev/shm is 64 MB, two 4K frames are 66 MB)
+            vfs = os.statvfs("/dev/shm")
+            if vfs.f_bavail * vfs.f_frsize < total + (8 << 20):
+                raise OSError(f"/dev/shm has {vfs.f_bavail * vfs.f_frsize >> 20} MB free, the shared frames need {total >> 20} MB")
             with open(self.path, "wb") as f:
                 f.truncate(total)
         self._fd = os.open(self.path, os.O_RDWR)
@@ -47,11 +56,15 @@ class SharedHostFrames:
 
     # -- consumer side (rank 0) ----------------------------------------------------------------------
     def take(self, f: int, timeout_s: float = 10.0) -> np.ndarray:
-        """Frame f, once every rank has delivered its rows of it; marks it consumed."""
+        """Frame f, once every rank has delivered its rows of it. The view stays valid until the next take() (or release()):
+        taking frame f lets go of the frames before it, whose slots the producers may then overwrite."""
         self._spin(lambda: int(self._counters[:self.world].min()) > f, timeout_s, f"frame {f}")
-        out = self.frames[f % self.slots]
-        self._counters[self.world] = f + 1
-        return out
+        self._counters[self.world] = max(int(self._counters[self.world]), f)
+        return self.frames[f % self.slots]
+
+    def release(self, f: int):
+        """The consumer is done with frame f (and everything before it)."""
+        self._counters[self.world] = max(int(self._counters[self.world]), f + 1)
 
     def reset(self):
         self._counters[self.rank] = 0

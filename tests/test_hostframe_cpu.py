@@ -63,8 +63,15 @@ def test_slot_reuse_waits_for_the_consumer():
         except TimeoutError:
             pass
         sh.delivered = 2
-        sh.publish(1)
+        sh.publish(2)
         sh.take(0)
+        try:
+            sh.slot_for_next(timeout_s=0.05)  # frame 0 is still in the consumer's hands
+            raise AssertionError("expected a timeout")
+        except TimeoutError:
+            pass
+        sh.delivered = 2
+        sh.take(1)  # ... taking frame 1 lets go of it
         assert sh.slot_for_next(timeout_s=0.05) is sh.frames[0]
     finally:
         sh.close(unlink=True)
