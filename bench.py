@@ -288,13 +288,19 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             dev.resolve()
     scenes.render(dev, scene)  # sizes every arena before the recording
     dev.finish()
-    frame_list = None if args.immediate else dev.record(record_frame)
+    # The frame is recorded TWICE: a recording that opens with a full clear alternates between the two tiled framebuffers of the
+    # device (include/malevich_b200.h, command lists), so replaying the two lists in turn lets frame f+1 start while the exchange
+    # (N > 1) or the asynchronous present (resolve / pack + copy on the read-back stream) of frame f still reads the other one.
+    n_lists = 2
+    frame_lists = None if args.immediate else [dev.record(record_frame) for _ in range(n_lists)]
+    frame_list = frame_lists[0] if frame_lists else None
     # the same frame without the device-resident resolve: what the end-to-end loops replay (the present resolves and copies
     # on its own, and a recording that writes the resolved image has to wait for a read-back of that image still in flight)
     def record_draws():
         dev.reset_stats()
         scenes.render(dev, scene)
-    draws_list = None if args.immediate else (frame_list if multi else dev.record(record_draws))
+    draws_lists = None if args.immediate else (frame_lists if multi else [dev.record(record_draws) for _ in range(n_lists)])
+    frame_no = [0]
 
     pending = [False]  # p2p: an exchange has been started and not yet joined
 
@@ -304,8 +310,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             pending[0] = False
 
     def render_frame():
-        if frame_list is not None:
-            frame_list.execute()
+        if frame_lists is not None:
+            frame_lists[frame_no[0] % n_lists].execute()
+            frame_no[0] += 1
         else:
             record_frame()
 
@@ -493,31 +500,38 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         return host_frames[(e2e_n[0] - 1) % 2]
 
     def frame_e2e_static():
-        if draws_list is not None:
-            draws_list.set_constants(cb_host)  # update(): the camera of this frame
-            draws_list.execute()
+        if draws_lists is not None:
+            dl = draws_lists[frame_no[0] % n_lists]
+            frame_no[0] += 1
+            dl.set_constants(cb_host)  # update(): the camera of this frame
+            dl.execute()
         else:
             record_draws()  # (the Python mirror sends the constant buffer with every draw)
         deliver()
 
-    def time_e2e(step):
+    def time_e2e(step, frames):
+        """Wall clock over `frames` frames, the last one included: the clock stops when this rank holds (rank 0: when the host
+        frame holds every rank's rows of) the last frame -- the pipeline's drain (one render + one read-back) is inside the timed
+        region, which is why at least `frames` >= --steps frames are timed: over 20 frames the drain alone is 5-10 % of the figure."""
         for _ in range(2):
             step()
         flush_e2e()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(frames):
             step()
         flush_e2e()
+        t1 = time.perf_counter()
         barrier()
-        return reduce_max((time.perf_counter() - t0) * 1e3 / args.steps)
+        return reduce_max((t1 - t0) * 1e3 / frames)
 
     e2e_streaming = None
     if not multi or composite == "p2p":
-        e2e_static_ms = time_e2e(frame_e2e_static)
+        e2e_frames = max(args.steps, 200)
+        e2e_static_ms = time_e2e(frame_e2e_static, e2e_frames)
         static_ok = bool(np.array_equal(last_delivered(), colors)) if rank == 0 else None
         e2e = {"value": 1e3 / e2e_static_ms, "unit": UNIT, "ms_per_step": e2e_static_ms, "h2d_bytes_per_step": 192 * len(scene.objects), "d2h_bytes_per_step": int(d2h),
-               "image_matches_resident_path": static_ok,
+               "image_matches_resident_path": static_ok, "frames_timed": e2e_frames,
                "note": "the reference's frame loop (main.c:1587-1602): geometry and textures resident (loaded once by init()), per frame the PerFrameCB of every draw replaced from host memory "
                        "(update(), main.c:1595-1597), the recorded frame replayed, the framebuffer read back to pinned host memory (double-buffered: the host collects frame f-1 while frame f is queued"
                        + ("; composed in host memory: every rank copies the rows it owns into one shared pinned frame over its own PCIe link, rank 0 takes the frame when all rows have arrived)" if e2e_composite == "host"
@@ -571,18 +585,18 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             else:
                 record_slab_frame()
             deliver()
-        e2e_streaming_ms = time_e2e(frame_e2e_streaming)
+        e2e_streaming_ms = time_e2e(frame_e2e_streaming, max(args.steps, 40))
         streaming_ok = bool(np.array_equal(last_delivered(), colors)) if rank == 0 else None
         e2e_streaming = {"value": 1e3 / e2e_streaming_ms, "unit": UNIT, "ms_per_step": e2e_streaming_ms, "h2d_bytes_per_step": int(vb_slab.nbytes + ib_slab.nbytes + 192 * len(scene.objects)),
-                         "d2h_bytes_per_step": int(d2h), "image_matches_resident_path": streaming_ok,
+                         "d2h_bytes_per_step": int(d2h), "image_matches_resident_path": streaming_ok, "frames_timed": max(args.steps, 40),
                          "note": "a host that streams its geometry: one vertex slab + one index slab (draws address them with start index / base vertex) re-uploaded from pinned host memory every frame"
                                  + (", each rank uploading its shard over its own PCIe link and an in-place ncclAllGather replicating it over NVLink (2 collectives per frame)" if multi else "")
                                  + "; same read-back as e2e; textures stay resident"}
     else:
         # --composite nccl: e2e = static geometry with a blocking read-back by rank 0
         def frame_e2e_nccl():
-            if frame_list is not None:
-                frame_list.set_constants(cb_host)
+            if frame_lists is not None:
+                frame_lists[frame_no[0] % n_lists].set_constants(cb_host)
             frame()
             dev.finish()
             if rank == 0:

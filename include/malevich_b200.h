@@ -205,7 +205,13 @@ MLV_API int mlv_draw(mlv_device *dev, uint32_t vertex_count);                   
  * one launch instead of ~7 per draw. The recording binds buffer and texture OBJECTS, not their contents: mlv_update_buffer
  * between executions is honoured (the execution waits for it). The vertex-shader constant buffer is recorded by value;
  * mlv_command_list_set_constants replaces it (for one draw or MLV_ALL_DRAWS) without re-recording -- what update()
- * (main.c:1480-1562) changes per frame. Buffers, textures and the list must outlive its executions. */
+ * (main.c:1480-1562) changes per frame. Buffers, textures and the list must outlive its executions.
+ * The device keeps a PAIR of tiled framebuffers. In immediate mode a frame that opens with a full clear (colour + depth) is
+ * drawn into the one nothing still reads -- the exchange of the previous frame, or its asynchronous present, which resolves /
+ * packs and copies on a stream of its own -- so the next frame starts at once. A recorded list addresses ONE of the two; a
+ * recording that opens with a full clear takes the one the previous such recording did not, so a host that records its frame
+ * twice and replays the two lists in turn gets the same overlap. Either way the images are the same: nothing of the old
+ * contents survives a full clear. */
 typedef struct mlv_command_list mlv_command_list;
 #define MLV_ALL_DRAWS 0xffffffffu
 MLV_API int mlv_begin_command_list(mlv_device *dev);

@@ -151,9 +151,13 @@ struct mlv_device {
 	// exchange stream while frame f+1 is already being drawn, so a frame that starts with a full clear is drawn into
 	// the other framebuffer of the pair instead of waiting for the broadcast.
 	uint4 *fb_pair[2];
+	int last_recorded_fb;      // the framebuffer the last recording that opened with a full clear addresses (-1: none yet)
 	int fb_sel;
 	bool fb_busy[2];           // a broadcast on the exchange stream reads fb_pair[i]; ev_fb_free[i] fires when it is done
 	cudaEvent_t ev_fb_free[2];
+	bool fb_reading[2];        // an asynchronous present on the read-back stream (resolve / pack) reads fb_pair[i]; ev_fb_read[i] fires when it is done
+	cudaEvent_t ev_fb_read[2];
+	cudaEvent_t ev_present_src; // everything the present reads has been written (main stream)
 	cudaStream_t xchg_stream;
 	cudaEvent_t ev_frame_done, ev_xchg_done;
 	bool xchg_pending;         // mlv_composite_join has not yet been called for the last mlv_composite_broadcast_async
@@ -191,8 +195,6 @@ struct mlv_device {
 	cudaStream_t readback_stream;
 	cudaEvent_t ev_resolved, ev_readback_done;
 	bool readback_in_flight;
-	cudaEvent_t ev_owned_prev; // mlv_present_owned_rows_async: completion of the copy issued one call earlier (its chunk is packed again by the next call)
-	bool owned_prev_recorded;
 	uint32_t owned_parity;
 	cudaEvent_t ev_main_sync;
 	uint32_t bin_begin, bin_end; // bins this rank can touch: everything, or one contiguous band
@@ -501,7 +503,6 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	CREATE_TRY(cudaStreamCreateWithFlags(&dev->readback_stream, cudaStreamNonBlocking));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_resolved, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_readback_done, cudaEventDisableTiming));
-	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_owned_prev, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_main_sync, cudaEventDisableTiming));
 	for(uint32_t i = 0; i < dev->num_ctx; ++i) {
 		DrawCtx &c = dev->ctxs[i];
@@ -515,6 +516,9 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 		CREATE_TRY(cudaMalloc(&c.touch_bits, touch_bytes));
 		CREATE_TRY(cudaMemsetAsync(c.touch_bits, 0, touch_bytes, dev->stream));
 	}
+	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_fb_read[0], cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_fb_read[1], cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_present_src, cudaEventDisableTiming));
 	if(num_ranks > 1) {
 		int prio_lo = 0, prio_hi = 0; // the exchange is short and latency-critical: its CTAs go first when SM slots free up
 		CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -527,6 +531,7 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	const size_t nb = dev->num_bins;
 	CREATE_TRY(cudaMalloc(&dev->fb_pair[0], nb * 32 * sizeof(uint4)));
 	dev->fb = dev->fb_pair[0];
+	dev->last_recorded_fb = -1;
 	CREATE_TRY(cudaMalloc(&dev->tile_min, nb * sizeof(float)));
 	CREATE_TRY(cudaMalloc(&dev->bin_count, nb * sizeof(uint32_t)));
 	CREATE_TRY(cudaMalloc(&dev->bin_offset, nb * sizeof(uint32_t)));
@@ -543,10 +548,10 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	dev->present_color = dev->resolved_color;
 	CREATE_TRY(cudaMalloc(&dev->resolved_depth, (size_t)dev->W * dev->H * 4));
 	CREATE_TRY(cudaMemsetAsync(dev->fb, 0, nb * 32 * sizeof(uint4), dev->stream));
-	if(num_ranks > 1) {
-		CREATE_TRY(cudaMalloc(&dev->fb_pair[1], nb * 32 * sizeof(uint4)));
-		CREATE_TRY(cudaMemsetAsync(dev->fb_pair[1], 0, nb * 32 * sizeof(uint4), dev->stream));
-	}
+	// the second framebuffer of the pair: a frame that opens with a full clear is drawn into the one that nothing still reads
+	// (the exchange of the previous frame, or its asynchronous present on the read-back stream)
+	CREATE_TRY(cudaMalloc(&dev->fb_pair[1], nb * 32 * sizeof(uint4)));
+	CREATE_TRY(cudaMemsetAsync(dev->fb_pair[1], 0, nb * 32 * sizeof(uint4), dev->stream));
 	CREATE_TRY(cudaMemsetAsync(dev->tile_min, 0, nb * sizeof(float), dev->stream));
 	CREATE_TRY(cudaMemsetAsync(dev->bin_count, 0, nb * sizeof(uint32_t), dev->stream));
 	CREATE_TRY(cudaMemsetAsync(dev->ctr, 0, sizeof(Counters), dev->stream));
@@ -616,7 +621,7 @@ void mlv_destroy_device(mlv_device *dev) {
 		cudaStreamSynchronize(dev->readback_stream);
 		cudaStreamDestroy(dev->readback_stream);
 	}
-	for(cudaEvent_t e : { dev->ev_last_draw, dev->ev_resolved, dev->ev_readback_done, dev->ev_owned_prev, dev->ev_main_sync, dev->ev_frame_done, dev->ev_xchg_done, dev->ev_fb_free[0], dev->ev_fb_free[1] })
+	for(cudaEvent_t e : { dev->ev_last_draw, dev->ev_resolved, dev->ev_readback_done, dev->ev_main_sync, dev->ev_frame_done, dev->ev_xchg_done, dev->ev_fb_free[0], dev->ev_fb_free[1], dev->ev_fb_read[0], dev->ev_fb_read[1], dev->ev_present_src })
 		if(e) cudaEventDestroy(e);
 	if(dev->prof_events) {
 		for(cudaEvent_t e : *dev->prof_events) cudaEventDestroy(e);
@@ -637,6 +642,7 @@ int mlv_finish(mlv_device *dev) {
 	CUDA_TRY(cudaStreamSynchronize(dev->copy_stream)); // uploads no draw has consumed yet
 	CUDA_TRY(cudaStreamSynchronize(dev->readback_stream));
 	dev->readback_in_flight = false;
+	dev->fb_reading[0] = dev->fb_reading[1] = false;
 	if(dev->xchg_stream) {
 		CUDA_TRY(cudaStreamSynchronize(dev->xchg_stream));
 		dev->fb_busy[0] = dev->fb_busy[1] = false;
@@ -1006,18 +1012,41 @@ int mlv_ps_set_shader_resource(mlv_device *dev, uint32_t slot, mlv_texture *tex)
 // Called before anything on the main stream WRITES the tiled framebuffer (a clear, a draw): an asynchronous broadcast
 // may still be reading it on the exchange stream. A frame that starts with a full clear moves to the other framebuffer
 // of the pair (nothing of the old contents survives such a clear); anything else waits for the broadcast.
-static int acquire_framebuffer(mlv_device *dev, bool full_clear) {
-	if(dev->recording) return MLV_OK; // a recorded list addresses one framebuffer of the pair; mlv_execute_command_list waits for it
-	if(!dev->xchg_stream || !(dev->fb_busy[0] || dev->fb_busy[1])) return MLV_OK;
-	if(full_clear && dev->fb_busy[dev->fb_sel]) {
-		dev->fb_sel ^= 1;
-		dev->fb = dev->fb_pair[dev->fb_sel];
-	}
+static int wait_framebuffer_readers(mlv_device *dev) { // the main stream waits for whatever still reads fb_pair[fb_sel] on another stream
 	if(dev->fb_busy[dev->fb_sel]) {
 		CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_fb_free[dev->fb_sel], 0));
 		dev->fb_busy[dev->fb_sel] = false;
 	}
+	if(dev->fb_reading[dev->fb_sel]) {
+		CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_fb_read[dev->fb_sel], 0));
+		dev->fb_reading[dev->fb_sel] = false;
+	}
 	return MLV_OK;
+}
+
+static int acquire_framebuffer(mlv_device *dev, bool full_clear) {
+	if(dev->recording) {
+		// A recorded list addresses ONE framebuffer of the pair; mlv_execute_command_list waits for it. A recording that OPENS
+		// with a full clear keeps nothing of what the framebuffer held, so it may address either one -- and consecutive such
+		// recordings alternate: a host that records its frame twice and replays the two lists in turn never makes frame f+1
+		// wait for the exchange / read-back that still reads frame f (the deferred-context form of what immediate mode does).
+		mlv_command_list *l = dev->recording;
+		if(l->launches == 0) {
+			if(full_clear && dev->fb_pair[1] && dev->last_recorded_fb == dev->fb_sel) {
+				dev->fb_sel ^= 1;
+				dev->fb = dev->fb_pair[dev->fb_sel];
+				l->fb_sel = dev->fb_sel;
+			}
+			if(full_clear) dev->last_recorded_fb = l->fb_sel;
+		}
+		return MLV_OK;
+	}
+	if(!(dev->fb_busy[0] || dev->fb_busy[1] || dev->fb_reading[0] || dev->fb_reading[1])) return MLV_OK;
+	if(full_clear && (dev->fb_busy[dev->fb_sel] || dev->fb_reading[dev->fb_sel])) {
+		dev->fb_sel ^= 1;
+		dev->fb = dev->fb_pair[dev->fb_sel];
+	}
+	return wait_framebuffer_readers(dev);
 }
 
 static int flush_clears(mlv_device *dev) {
@@ -1671,10 +1700,7 @@ int mlv_execute_command_list(mlv_device *dev, mlv_command_list *list) {
 		dev->fb_sel = list->fb_sel;
 		dev->fb = dev->fb_pair[dev->fb_sel];
 	}
-	if(dev->xchg_stream && dev->fb_busy[dev->fb_sel]) {
-		CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_fb_free[dev->fb_sel], 0));
-		dev->fb_busy[dev->fb_sel] = false;
-	}
+	if(int rc = wait_framebuffer_readers(dev)) return rc;
 	if(list->has_resolve && dev->readback_in_flight) CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_readback_done, 0));
 	for(mlv_buffer *b : *list->buffers) {
 		if(!b->ready_pending) continue;
@@ -1775,14 +1801,29 @@ int mlv_present_readback_async(mlv_device *dev, uint32_t *colors, float *depths)
 	if(int rc = immediate_only(dev, "mlv_present_readback_async")) return rc;
 	if(int rc = use_device(dev)) return rc;
 	if(int rc = flush_clears(dev)) return rc;
-	if(dev->readback_in_flight) CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_readback_done, 0)); // the resolved images are reused
+	// The resolve runs on the READ-BACK stream, behind the copies of the previous present (the resolved images are reused:
+	// stream order) and beside whatever the main stream does next: a frame that opens with a full clear goes to the other
+	// framebuffer of the pair, so the next frame's kernels start while this one is still being resolved and copied.
 	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
-	prof_pre(dev, MLV_STAGE_RESOLVE);
-	launch_pdl(k_resolve, (items + 255) / 256, 256, dev->stream, dev->fb, dev->resolved_color, depths ? dev->resolved_depth : nullptr, dev->W, dev->H);
+	const bool profiled = dev->prof_on; // (per-stage profiling brackets launches on the main stream)
+	cudaStream_t rs = profiled ? dev->stream : dev->readback_stream;
+	if(profiled) {
+		if(dev->readback_in_flight) CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_readback_done, 0));
+		prof_pre(dev, MLV_STAGE_RESOLVE);
+	} else {
+		CUDA_TRY(cudaEventRecord(dev->ev_present_src, dev->stream));
+		CUDA_TRY(cudaStreamWaitEvent(rs, dev->ev_present_src, 0));
+	}
+	launch_pdl(k_resolve, (items + 255) / 256, 256, rs, dev->fb, dev->resolved_color, depths ? dev->resolved_depth : nullptr, dev->W, dev->H);
 	dev->present_color = dev->resolved_color;
 	if(int rc = check_launch(dev, "k_resolve")) return rc;
-	CUDA_TRY(cudaEventRecord(dev->ev_resolved, dev->stream));
-	CUDA_TRY(cudaStreamWaitEvent(dev->readback_stream, dev->ev_resolved, 0));
+	if(profiled) {
+		CUDA_TRY(cudaEventRecord(dev->ev_resolved, dev->stream));
+		CUDA_TRY(cudaStreamWaitEvent(dev->readback_stream, dev->ev_resolved, 0));
+	} else {
+		CUDA_TRY(cudaEventRecord(dev->ev_fb_read[dev->fb_sel], rs));
+		dev->fb_reading[dev->fb_sel] = true;
+	}
 	const size_t bytes = (size_t)dev->W * dev->H * 4;
 	if(colors) CUDA_TRY(cudaMemcpyAsync(colors, dev->resolved_color, bytes, cudaMemcpyDeviceToHost, dev->readback_stream));
 	if(depths) CUDA_TRY(cudaMemcpyAsync(depths, dev->resolved_depth, bytes, cudaMemcpyDeviceToHost, dev->readback_stream));
@@ -1916,18 +1957,27 @@ int mlv_present_owned_rows_async(mlv_device *dev, uint32_t *frame_colors) {
 	const int n = dev->part.num_ranks, me = dev->part.rank, sh = dev->part.stripe_h;
 	dev->owned_parity ^= 1u;
 	uint4 *chunk = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(dev->gather) + dev->chunk_bytes * (size_t)((me + (int)dev->owned_parity) % n));
-	// the chunk written now was read by the copy issued two calls ago: that copy is complete once the previous one is
-	// (same stream), and the host has normally collected it (mlv_present_wait) long before
-	if(dev->owned_prev_recorded) CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_owned_prev, 0));
+	// Pack and copies run on the READ-BACK stream, behind the copies of the previous call (stream order protects the packed
+	// chunks) and beside whatever the main stream does next: a frame that opens with a full clear is drawn into the other
+	// framebuffer of the pair while this one is packed and copied.
 	const uint32_t items = (uint32_t)(dev->W / 8) * (uint32_t)dev->H;
-	prof_pre(dev, MLV_STAGE_COMPOSITE);
-	launch_pdl(k_composite_pack, (items + 255) / 256, 256, dev->stream, dev->fb, chunk, dev->W, dev->H, dev->part);
+	const bool profiled = dev->prof_on;
+	cudaStream_t rs = profiled ? dev->stream : dev->readback_stream;
+	if(profiled) {
+		if(dev->readback_in_flight) CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_readback_done, 0));
+		prof_pre(dev, MLV_STAGE_COMPOSITE);
+	} else {
+		CUDA_TRY(cudaEventRecord(dev->ev_present_src, dev->stream));
+		CUDA_TRY(cudaStreamWaitEvent(rs, dev->ev_present_src, 0));
+	}
+	launch_pdl(k_composite_pack, (items + 255) / 256, 256, rs, dev->fb, chunk, dev->W, dev->H, dev->part);
 	if(int rc = check_launch(dev, "k_composite_pack")) return rc;
-	CUDA_TRY(cudaEventRecord(dev->ev_resolved, dev->stream));
-	CUDA_TRY(cudaStreamWaitEvent(dev->readback_stream, dev->ev_resolved, 0));
-	if(dev->readback_in_flight) { // the event of the copy before this one, for the call after this one
-		CUDA_TRY(cudaEventRecord(dev->ev_owned_prev, dev->readback_stream));
-		dev->owned_prev_recorded = true;
+	if(profiled) {
+		CUDA_TRY(cudaEventRecord(dev->ev_resolved, dev->stream));
+		CUDA_TRY(cudaStreamWaitEvent(dev->readback_stream, dev->ev_resolved, 0));
+	} else {
+		CUDA_TRY(cudaEventRecord(dev->ev_fb_read[dev->fb_sel], rs));
+		dev->fb_reading[dev->fb_sel] = true;
 	}
 	const size_t row_bytes = (size_t)dev->W * 4;
 	uint32_t local = 0;

@@ -168,3 +168,38 @@ def test_command_lists_of_sort_first_ranks_compose_to_the_single_device_image():
         finally:
             for d in devs:
                 d.close()
+
+
+@pytest.mark.parametrize("num_ranks", [1, 2])
+def test_two_recordings_alternate_framebuffers_under_asynchronous_presents(num_ranks):
+    """A frame recorded twice (each recording opens with a full clear, so each takes the other tiled framebuffer of the pair),
+    the two lists replayed in turn with a different camera each time, every frame handed to an asynchronous present whose
+    resolve / pack and copy run on the read-back stream while the next frame is already being drawn: every delivered frame
+    is the frame of ITS camera, bit for bit what immediate mode gives."""
+    from malevich_b200 import camera, scenes
+    sc = cases.SMALL["ftm_320x200"]()
+    poses = [((-8.0, 5.0, 1.2), -2.8, 0.1), ((-2.0, 1.5, 1.0), -2.0, 0.3), scenes.FTM_SCREENSHOT_POSE, ((-6.0, 3.0, 2.0), -2.5, 0.2)]
+    cbs = [camera.per_frame_cb(sc.width, sc.height, *p) for p in poses]
+    want = []
+    for cb in cbs:
+        col, dep, _ = _immediate(scenes.ftm(sc.width, sc.height, cb=cb))
+        want.append(col)
+    with _device(sc.width, sc.height, num_ranks=num_ranks, rank=0, stripe_height_tiles=3) as dev:
+        scenes.upload(dev, sc)
+        lists = [dev.record(lambda: scenes.render(dev, sc)) for _ in range(2)]
+        frames = [np.zeros((sc.height, sc.width), np.uint32) for _ in range(len(cbs) * 3)]
+        owned = np.array([((y // 8) // 3) % num_ranks == 0 for y in range(sc.height)])
+        for it in range(len(frames)):
+            cl = lists[it % 2]
+            cl.set_constants(cbs[it % len(cbs)])
+            cl.execute()
+            if it >= 2:
+                dev.present_wait()  # bounds the frames in flight like a double-buffered host does
+            dev.present_owned_rows_async(frames[it])  # (one rank: the whole frame; rank 0 of 2: the rows it owns)
+        dev.present_wait()
+        dev.finish()
+        for it, f in enumerate(frames):
+            assert np.array_equal(f[owned], want[it % len(cbs)][owned]), it
+            assert not f[~owned].any()
+        for cl in lists:
+            cl.release()
