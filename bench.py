@@ -443,10 +443,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             try:
                 name = f"mlv_frames_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
                 if rank == 0:
-                    shared = SharedHostFrames(name, scene.height, scene.width, world, rank, slots=2, create=True)
+                    shared = SharedHostFrames(name, scene.height, scene.width, world, rank, slots=3, create=True)
                 dist.barrier()
                 if rank != 0:
-                    shared = SharedHostFrames(name, scene.height, scene.width, world, rank, slots=2)
+                    shared = SharedHostFrames(name, scene.height, scene.width, world, rank, slots=3)
                 dev.register_host_memory(shared.address, shared.nbytes)
                 shared.reset()
             except Exception as e:  # noqa: BLE001 -- e.g. no /dev/shm, or the mapping cannot be page-locked

@@ -500,7 +500,12 @@ int mlv_create_device(const mlv_device_desc *desc, mlv_device **out_device) {
 	}
 	CREATE_TRY(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_last_draw, cudaEventDisableTiming));
-	CREATE_TRY(cudaStreamCreateWithFlags(&dev->readback_stream, cudaStreamNonBlocking));
+	{ // the resolve / pack of an asynchronous present is short and the frame's way out: its CTAs go first when SM slots free up
+		// (at the lowest priority the next frame's kernels starved it: the copy, and with it the host's next frame, came a frame late)
+		int prio_lo = 0, prio_hi = 0;
+		CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		CREATE_TRY(cudaStreamCreateWithPriority(&dev->readback_stream, cudaStreamNonBlocking, prio_hi));
+	}
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_resolved, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_readback_done, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&dev->ev_main_sync, cudaEventDisableTiming));

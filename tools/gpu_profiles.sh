@@ -12,13 +12,13 @@ timeout 120 python tools/timeline_frame.py 1 0 5 gpurun_out/timeline_config5_n1.
 timeout 120 python tools/timeline_frame.py 8 3 5 gpurun_out/timeline_config5_rank3of8.json > gpurun_out/timeline_config5_rank3of8.txt 2>&1
 timeout 120 python tools/timeline_frame.py 1 0 2 gpurun_out/timeline_config2_n1.json > gpurun_out/timeline_config2_n1.txt 2>&1
 timeout 120 python tools/launch_table.py 1 0 5 > gpurun_out/launch_table_config5_n1.txt 2>&1
-timeout 120 python tools/trace_frame.py 5 gpurun_out/trace_config5.json > /dev/null 2>&1
+[ -n "$QUICK" ] || timeout 120 python tools/trace_frame.py 5 gpurun_out/trace_config5.json > /dev/null 2>&1
 for c in 5 1 2 3 4; do
   timeout 400 python bench.py --config $c --steps 20 --warmup 3 > gpurun_out/bench_c${c}.json 2> gpurun_out/bench_c${c}.err
   tail -2 gpurun_out/bench_c${c}.err
 done
-timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+timeout 300 python bench.py --impl reference --steps ${REF_STEPS:-20} --warmup ${REF_WARMUP:-3} > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 timeout 300 compute-sanitizer --tool memcheck python __graft_entry__.py smoke > gpurun_out/sanitizer_memcheck.log 2>&1; tail -2 gpurun_out/sanitizer_memcheck.log
-timeout 300 compute-sanitizer --tool racecheck python __graft_entry__.py smoke > gpurun_out/sanitizer_racecheck.log 2>&1; tail -2 gpurun_out/sanitizer_racecheck.log
-timeout 300 compute-sanitizer --tool synccheck python __graft_entry__.py smoke > gpurun_out/sanitizer_synccheck.log 2>&1; tail -2 gpurun_out/sanitizer_synccheck.log
+[ -n "$QUICK" ] || timeout 300 compute-sanitizer --tool racecheck python __graft_entry__.py smoke > gpurun_out/sanitizer_racecheck.log 2>&1; tail -2 gpurun_out/sanitizer_racecheck.log
+[ -n "$QUICK" ] || timeout 300 compute-sanitizer --tool synccheck python __graft_entry__.py smoke > gpurun_out/sanitizer_synccheck.log 2>&1; tail -2 gpurun_out/sanitizer_synccheck.log
 ls -la gpurun_out/full.ncu-rep gpurun_out/launches.csv

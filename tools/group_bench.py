@@ -15,7 +15,7 @@ ap.add_argument("--config", type=int, default=5)
 ap.add_argument("--nccl", action="store_true", help="compose on the device with pack + ncclAllGather + unpack, read rank 0's image back")
 ap.add_argument("--peer", action="store_true", help="compose on the device with the asynchronous peer-memory exchange, read rank 0's image back (default: compose in host memory, every GPU delivers its band)")
 ap.add_argument("--stripe", type=int, default=0)
-ap.add_argument("--frames", type=int, default=40)
+ap.add_argument("--frames", type=int, default=200)
 ap.add_argument("--same-gpu", action="store_true")
 a = ap.parse_args()
 KEYS = {1: "config1_toon_1280x720", 2: "config2_ftm_1920x1080", 3: "config3_emily_1920x1080", 4: "config4_locomotive_3840x2160", 5: "config5_synthetic_3840x2160"}
@@ -26,7 +26,7 @@ with Device(sc.width, sc.height, cuda_device=0, num_gpus=a.num_gpus, group_same_
     scenes.render(dev, sc)
     col, dep = dev.present()
     stats = dev.stats()
-    cl = dev.record(lambda: scenes.render(dev, sc))
+    cls = [dev.record(lambda: scenes.render(dev, sc)) for _ in range(2)]  # two recordings: they alternate between the two tiled framebuffers of every GPU
     # pinned host memory (through torch, when present) and a read-back one frame behind: the host collects frame f-1 while the
     # GPUs render frame f -- what bench.py's e2e does with one process per GPU
     try:
@@ -38,7 +38,7 @@ with Device(sc.width, sc.height, cuda_device=0, num_gpus=a.num_gpus, group_same_
         pinned = False
     colors = bufs[0]
     def frame(f):
-        cl.execute()
+        cls[f & 1].execute()
         dev.present_wait()            # frame f-1 has arrived in bufs[(f-1) & 1]
         dev.present_async(bufs[f & 1])
     for f in range(6):
@@ -52,7 +52,8 @@ with Device(sc.width, sc.height, cuda_device=0, num_gpus=a.num_gpus, group_same_
     dev.finish()
     ms = 1e3 * (time.perf_counter() - t0) / a.frames
     colors = bufs[(a.frames - 1) & 1]
-    cl.release()
+    for cl in cls:
+        cl.release()
 print(json.dumps({"tool": "group_bench", "num_gpus": a.num_gpus, "config": KEYS[a.config], "exchange": "ncclAllGather" if a.nccl else ("peer memory" if a.peer else "none: every GPU copies its band to the host frame over its own PCIe link"),
                   "stripe_height_tiles": a.stripe or "one band per GPU", "ms_per_frame_incl_readback": round(ms, 4), "frames_per_s": round(1e3 / ms, 1),
                   "color_fnv": L.fnv64_words(col), "depth_fnv": L.fnv64_words(dep), "matches_golden": {"color": L.fnv64_words(col) == golden["color_fnv"], "depth": L.fnv64_words(dep) == golden["depth_fnv"]},

@@ -59,7 +59,7 @@ src_dir = os.path.dirname(os.path.abspath(bench_json))
 import shutil
 for name, dst in [(f"bench_c{c}.json", f"bench_config{c}_n1.json") for c in (1, 2, 3, 4)] + [("bench_ref.json", "bench_reference_arm_config5.json")] + \
                  [(f"bench_n{n}.json", f"bench_config5_n{n}.json") for n in (2, 4, 8)] + [(f"bench_n{n}_nccl.json", f"bench_config5_n{n}_nccl.json") for n in (2, 4, 8)] + \
-                 [(f"group_n{n}_{m}.json", f"group_config5_n{n}_{m}.json") for n in (2, 4, 8) for m in ("peer", "nccl")] + [("group_n8_ftm.json", "group_config2_n8_peer.json"), ("group_n2_ftm.json", "group_config2_n2_peer.json")]:
+                 [(f"group_n{n}_{m}.json", f"group_config5_n{n}_{m}.json") for n in (2, 4, 8) for m in ("peer", "nccl")] + [(f"group_n{n}.json", f"group_config5_n{n}_host.json") for n in (2, 4, 8)] + [("group_n8_ftm.json", "group_config2_n8_peer.json"), ("group_n2_ftm.json", "group_config2_n2_peer.json")]:
     path = os.path.join(src_dir, name)
     if os.path.exists(path) and open(path).read().strip():
         json.dump(json.loads(open(path).read().strip().splitlines()[-1]), open(out(dst), "w"), indent=1)
