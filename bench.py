@@ -293,7 +293,6 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # (N > 1) or the asynchronous present (resolve / pack + copy on the read-back stream) of frame f still reads the other one.
     n_lists = 2
     frame_lists = None if args.immediate else [dev.record(record_frame) for _ in range(n_lists)]
-    frame_list = frame_lists[0] if frame_lists else None
     # the same frame without the device-resident resolve: what the end-to-end loops replay (the present resolves and copies
     # on its own, and a recording that writes the resolved image has to wait for a read-back of that image still in flight)
     def record_draws():

@@ -211,7 +211,9 @@ MLV_API int mlv_draw(mlv_device *dev, uint32_t vertex_count);                   
  * packs and copies on a stream of its own -- so the next frame starts at once. A recorded list addresses ONE of the two; a
  * recording that opens with a full clear takes the one the previous such recording did not, so a host that records its frame
  * twice and replays the two lists in turn gets the same overlap. Either way the images are the same: nothing of the old
- * contents survives a full clear. */
+ * contents survives a full clear. A list that does NOT open with a full clear draws over what its framebuffer holds; when
+ * those contents live in the other one (only possible after asynchronous presents or exchanges made a frame move over)
+ * mlv_execute_command_list fails with MLV_ERR_STATE instead of drawing over the wrong image. */
 typedef struct mlv_command_list mlv_command_list;
 #define MLV_ALL_DRAWS 0xffffffffu
 MLV_API int mlv_begin_command_list(mlv_device *dev);
@@ -227,11 +229,14 @@ MLV_API void mlv_release_command_list(mlv_device *dev, mlv_command_list *list);
  * With num_ranks > 1 only the tiles this rank owns are meaningful unless the caller composited
  * the ranks first (mlv_composite_*). */
 MLV_API int mlv_present_readback(mlv_device *dev, uint32_t *colors, float *depths);
-/* The same without blocking the host: resolve on the device stream, then the device-to-host copies on a read-back stream
- * of their own, so the read-back of frame f overlaps the uploads and the rendering of frame f+1. `colors` / `depths`
- * should be page-locked and must stay untouched until mlv_present_wait (or mlv_finish) returns; the next resolve waits
- * for the copies on the device, so at most one read-back is in flight. Capacity errors of the frame are reported by the
- * next synchronising call (mlv_get_stats, mlv_present_readback). */
+/* The same without blocking the host OR the device stream: the resolve and the device-to-host copies run on a read-back
+ * stream of their own (highest priority, ordered after everything issued so far), so frame f leaves while frame f+1 is
+ * uploaded and rendered -- a frame that opens with a colour + depth clear is drawn into the other tiled framebuffer of the
+ * device's pair and does not wait for the resolve that still reads the first; anything else that writes the framebuffer
+ * waits for it. `colors` / `depths` should be page-locked (mlv_register_host_memory) and must stay untouched until
+ * mlv_present_wait (or mlv_finish) returns; presents follow each other on the read-back stream, which protects the
+ * resolved device images (they belong to the present until then: use mlv_resolve for a device-resident image). Capacity
+ * errors of the frame are reported by the next synchronising call (mlv_get_stats, mlv_present_readback). */
 MLV_API int mlv_present_readback_async(mlv_device *dev, uint32_t *colors, float *depths);
 MLV_API int mlv_present_wait(mlv_device *dev);
 MLV_API int mlv_get_stats(mlv_device *dev, mlv_stats *out);  /* stats main.c:231,1268 */

@@ -94,6 +94,7 @@ struct mlv_command_list {
 	uint64_t launches;               // kernels per execution
 	uint32_t draws;
 	int fb_sel;                      // the tiled framebuffer of the pair the recorded kernels address
+	bool opens_with_full_clear;      // nothing of the framebuffer's old contents survives the recording's first operation
 	bool has_resolve;
 	uint32_t last_index_count, last_direct_slots;
 	std::vector<mlv_buffer *> *buffers;    // every buffer a recorded draw binds (an execution waits for uploads still in flight)
@@ -1042,7 +1043,10 @@ static int acquire_framebuffer(mlv_device *dev, bool full_clear) {
 				dev->fb = dev->fb_pair[dev->fb_sel];
 				l->fb_sel = dev->fb_sel;
 			}
-			if(full_clear) dev->last_recorded_fb = l->fb_sel;
+			if(full_clear) {
+				dev->last_recorded_fb = l->fb_sel;
+				l->opens_with_full_clear = true;
+			}
 		}
 		return MLV_OK;
 	}
@@ -1698,14 +1702,19 @@ int mlv_execute_command_list(mlv_device *dev, mlv_command_list *list) {
 	if(int rc = use_device(dev)) return rc;
 	if(int rc = immediate_only(dev, "mlv_execute_command_list")) return rc;
 	if(!list || list->owner != dev) return fail(MLV_ERR_INVALID_ARGUMENT, "command list does not belong to this device");
-	if(int rc = flush_clears(dev)) return rc; // clears issued in immediate mode come first
-	// what the recorded kernels could not wait for inside the capture: the framebuffer they address (an asynchronous
-	// exchange may still read it), a read-back of the resolved image in flight, uploads of the buffers they bind
+	// The recorded kernels address ONE framebuffer of the pair. A list that draws over what is there (no full clear of its own)
+	// needs those contents in ITS framebuffer: a full clear still pending from immediate mode is simply issued there;
+	// otherwise the contents live where immediate mode (or another list) left them.
 	if(dev->fb_sel != list->fb_sel) {
+		if(!list->opens_with_full_clear && !(dev->pend_color && dev->pend_depth))
+			return fail(MLV_ERR_STATE, "the command list draws over framebuffer contents that live in the other tiled framebuffer of the pair (record it with its clears, or re-record it)");
 		dev->fb_sel = list->fb_sel;
 		dev->fb = dev->fb_pair[dev->fb_sel];
 	}
+	// what the recorded kernels could not wait for inside the capture: the framebuffer they address (an asynchronous
+	// exchange or present may still read it), a read-back of the resolved image in flight, uploads of the buffers they bind
 	if(int rc = wait_framebuffer_readers(dev)) return rc;
+	if(int rc = flush_clears(dev)) return rc; // clears issued in immediate mode come first (nothing reads this framebuffer any more: no flip)
 	if(list->has_resolve && dev->readback_in_flight) CUDA_TRY(cudaStreamWaitEvent(dev->stream, dev->ev_readback_done, 0));
 	for(mlv_buffer *b : *list->buffers) {
 		if(!b->ready_pending) continue;

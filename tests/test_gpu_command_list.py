@@ -203,3 +203,51 @@ def test_two_recordings_alternate_framebuffers_under_asynchronous_presents(num_r
             assert not f[~owned].any()
         for cl in lists:
             cl.release()
+
+
+def test_a_list_without_clears_draws_over_the_contents_of_its_own_framebuffer():
+    """A recording that does not open with a full clear is bound to the tiled framebuffer it was recorded on. Clears that
+    are still pending from immediate mode are issued THERE (seen through a clear colour that changes every frame); when the
+    contents it would draw over have moved to the other framebuffer of the pair (an asynchronous present made the next
+    cleared frame move over) the execution is refused."""
+    from malevich_b200 import scenes
+    sc = cases.SMALL["loco_320x200"]  # one small mesh: 98 % of the frame shows the clear colour()
+    colors = [(0.1, 0.2, 0.3, 1.0), (0.9, 0.1, 0.4, 1.0), (0.2, 0.8, 0.6, 1.0)]
+
+    def frame(dev, rgba, draw):
+        dev.clear_render_target_view(rgba)
+        dev.clear_depth_stencil_view(scenes.CLEAR_DEPTH)
+        draw()
+    want = []
+    with _device(sc.width, sc.height) as one:
+        for rgba in colors:
+            frame(one, rgba, lambda: scenes.render(one, sc, clear=False))
+            want.append(one.present())
+    assert not np.array_equal(want[0][0], want[1][0])  # the background shows
+    with _device(sc.width, sc.height) as dev:
+        scenes.upload(dev, sc)
+        scenes.render(dev, sc)  # sizes the arenas
+        dev.finish()
+        draws = dev.record(lambda: scenes.render(dev, sc, clear=False))
+        host = np.zeros((sc.height, sc.width), np.uint32)
+        for it, rgba in enumerate(colors):
+            # the asynchronous present of the previous frame keeps the framebuffer busy: the pending full clear must still be
+            # issued on the LIST's framebuffer (a clear that moved to the other one would leave the old background behind)
+            frame(dev, rgba, draws.execute)
+            dev.present_async(host)
+            if it == len(colors) - 1:
+                dev.present_wait()
+                assert np.array_equal(host, want[it][0]), it
+        col, dep = dev.present()
+        assert np.array_equal(col, want[-1][0]) and np.array_equal(dep.view(np.uint32), want[-1][1].view(np.uint32))
+        # an immediate frame that opens with a full clear while a present still reads the framebuffer moves to the other one ...
+        dev.present_async(host)
+        frame(dev, colors[0], lambda: scenes.render(dev, sc, clear=False))
+        # ... and the list, which draws over "what is there", must not silently draw over the old image in its own framebuffer
+        with pytest.raises(Exception) as e:
+            draws.execute()
+        assert "other tiled framebuffer" in str(e.value)
+        dev.present_wait()
+        col, dep = dev.present()  # the immediate frame is intact
+        assert np.array_equal(col, want[0][0]) and np.array_equal(dep.view(np.uint32), want[0][1].view(np.uint32))
+        draws.release()
