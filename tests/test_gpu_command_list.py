@@ -211,7 +211,7 @@ def test_a_list_without_clears_draws_over_the_contents_of_its_own_framebuffer():
     contents it would draw over have moved to the other framebuffer of the pair (an asynchronous present made the next
     cleared frame move over) the execution is refused."""
     from malevich_b200 import scenes
-    sc = cases.SMALL["loco_320x200"]  # one small mesh: 98 % of the frame shows the clear colour()
+    sc = cases.SMALL["loco_320x200"]()  # one small mesh: 98 % of the frame shows the clear colour
     colors = [(0.1, 0.2, 0.3, 1.0), (0.9, 0.1, 0.4, 1.0), (0.2, 0.8, 0.6, 1.0)]
 
     def frame(dev, rgba, draw):
