@@ -114,3 +114,64 @@ def test_gloo_sharded_upload_replicates_the_buffer(world, tmp_path):
     mp.spawn(_shard_worker, args=(world, 29700 + world, (1, 17, 4096, 100003, 1200000), str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / f"shard{r}.txt").read() == "OK"
+
+
+def _host_composite_worker(rank, world, port, stripe_h, frame_path, name, out_dir):
+    """What bench.py's end-to-end loop does at N > 1 with the frame composed in HOST memory: no collective on the data path.
+    Every rank packs the stripes it owns (k_composite_pack's layout = partition.pack) and copies them to their rows of ONE
+    shared frame (mlv_present_owned_rows_async's row arithmetic, restated here), publishes the frame, and rank 0 takes it
+    once every rank has -- several frames in a row through the slots of the shared mapping."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from malevich_b200.hostframe import SharedHostFrames
+        full = np.load(frame_path)
+        h, w = full.shape
+        ht = h // 8
+        shared = SharedHostFrames(name, h, w, world, rank, slots=3, create=(rank == 0)) if rank == 0 else None
+        dist.barrier()  # the mapping exists
+        if rank != 0:
+            shared = SharedHostFrames(name, h, w, world, rank, slots=3)
+        shared.reset()
+        dist.barrier()
+        ok, frames = True, 5
+        for f in range(frames + 1):
+            if f > 0:
+                shared.publish(f)  # (after mlv_present_wait: this rank's rows of frame f-1 are in host memory)
+                if rank == 0:
+                    got = shared.take(f - 1)
+                    ok = ok and np.array_equal(got, full + np.uint32(f - 1))
+            if f == frames:
+                break
+            rendered = np.full_like(full, 0xDEADBEEF)  # this rank's device renders only the stripes it owns
+            for ty in partition.owned_tile_rows(h, world, rank, stripe_h):
+                rendered[ty * 8:(ty + 1) * 8] = full[ty * 8:(ty + 1) * 8] + np.uint32(f)
+            chunk = partition.pack(rendered, world, rank, stripe_h)
+            dst = shared.slot_for_next()
+            local = 0
+            stripe = rank
+            while stripe * stripe_h < ht:  # (ty / stripe_h) % world == rank, one copy per stripe
+                ty0, ty1 = stripe * stripe_h, min(stripe * stripe_h + stripe_h, ht)
+                dst[ty0 * 8:ty1 * 8] = chunk[local * stripe_h * 8:local * stripe_h * 8 + (ty1 - ty0) * 8]
+                stripe += world
+                local += 1
+        dist.barrier()
+        shared.close(unlink=(rank == 0))
+        with open(os.path.join(out_dir, f"hostcomp{rank}.txt"), "w") as fo:
+            fo.write("OK" if ok else "MISMATCH")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,stripe_h", [(2, 13), (2, 1), (3, 2)])
+def test_gloo_host_memory_composite_reproduces_the_full_frame(world, stripe_h, tmp_path):
+    frame = np.load(os.path.join(ROOT, "tests", "golden", "small_frames.npz"))["toon_320x200/colors"]
+    frame_path = str(tmp_path / "frame.npy")
+    np.save(frame_path, frame)
+    port = 29700 + world * 20 + stripe_h
+    name = f"mlv_test_hostcomp_{os.getpid()}_{world}_{stripe_h}"
+    mp.spawn(_host_composite_worker, args=(world, port, stripe_h, frame_path, name, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"hostcomp{r}.txt").read() == "OK"
