@@ -305,7 +305,7 @@ MLV_API int mlv_present_owned_rows_async(mlv_device *dev, uint32_t *frame_colors
 /* Page-lock host memory the caller owns (malloc, or a MAP_SHARED mapping that several rank processes open: the shared frame
  * of mlv_present_owned_rows_async) for this device's CUDA context, so that the asynchronous read-backs into it run at full
  * PCIe rate and really are asynchronous; undo it before the memory is freed or unmapped. A host that does not link CUDA
- * has no other way to do this (the reference's frame buffer is a plain static array, main.c:113). */
+ * has no other way to do this (the reference's frame buffer is a plain static array, main.c:35). */
 MLV_API int mlv_register_host_memory(mlv_device *dev, void *ptr, size_t bytes);
 MLV_API int mlv_unregister_host_memory(mlv_device *dev, void *ptr);
 
