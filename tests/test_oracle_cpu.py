@@ -232,6 +232,10 @@ def test_c_abi_argument_errors_without_gpu():
     assert lib.mlv_create_device(ctypes.byref(bad), ctypes.byref(h)) == L.MLV_ERR_INVALID_ARGUMENT
     assert b"multiples of 8" in lib.mlv_last_error_string()
     assert lib.mlv_draw_indexed(None, 24) == L.MLV_ERR_INVALID_ARGUMENT
+    buf = (ctypes.c_uint32 * 16)()
+    for call in (lambda: lib.mlv_present_owned_rows_async(None, buf), lambda: lib.mlv_register_host_memory(None, buf, 64), lambda: lib.mlv_unregister_host_memory(None, buf),
+                 lambda: lib.mlv_present_readback_async(None, buf, None), lambda: lib.mlv_execute_command_list(None, None)):
+        assert call() == L.MLV_ERR_INVALID_ARGUMENT
     import torch
     if not torch.cuda.is_available():
         ok = L.DeviceDesc(width=320, height=200, cuda_device=-1)
