@@ -439,18 +439,30 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         if e2e_composite == "host":
             from malevich_b200.hostframe import SharedHostFrames
             ok = torch.ones(1, device="cuda")
-            try:
-                name = f"mlv_frames_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
-                if rank == 0:
-                    shared = SharedHostFrames(name, scene.height, scene.width, world, rank, slots=3, create=True)
-                dist.barrier()
+            name = f"mlv_frames_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
+
+            def attempt(step):  # every rank reaches every collective below whatever fails on it
+                try:
+                    step()
+                except Exception as e:  # noqa: BLE001 -- e.g. /dev/shm too small, or the mapping cannot be page-locked
+                    print(f"[bench] rank {rank}: shared host frame unavailable ({e}); rank 0 reads the composited frame back", file=sys.stderr)
+                    ok.zero_()
+
+            def create():
+                nonlocal shared
+                shared = SharedHostFrames(name, scene.height, scene.width, world, rank, slots=3, create=True)
+
+            def attach():
+                nonlocal shared
                 if rank != 0:
                     shared = SharedHostFrames(name, scene.height, scene.width, world, rank, slots=3)
                 dev.register_host_memory(shared.address, shared.nbytes)
                 shared.reset()
-            except Exception as e:  # noqa: BLE001 -- e.g. no /dev/shm, or the mapping cannot be page-locked
-                print(f"[bench] rank {rank}: shared host frame unavailable ({e}); rank 0 reads the composited frame back", file=sys.stderr)
-                ok.zero_()
+            if rank == 0:
+                attempt(create)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # (also the barrier: the mapping exists, or nobody goes on)
+            if ok.item() != 0:
+                attempt(attach)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if ok.item() == 0:
                 e2e_composite = "device"
